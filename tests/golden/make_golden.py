@@ -1,0 +1,42 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built by
+`make -C oracle ref` from /root/reference/src).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Inputs are regenerated from seeds by tests/_cases.py, so the fixtures hold outputs only.
+Single-threaded so that the OpenMP error reduction (src/tvl1flow.cpp:151) is order-stable.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle.loader import CpuTvl1, build  # noqa: E402
+import _cases  # noqa: E402
+
+
+def main():
+    build(ref=True)
+    out = {}
+    for dt in (np.float64, np.float32):
+        R = CpuTvl1("reference", dt)
+        R.set_threads(1)
+        tag = "f64" if dt == np.float64 else "f32"
+        out.update({"%s/%s" % (tag, k): v for k, v in _cases.run_function_cases(R).items()})
+        for name, case in _cases.SOLVER_CASES.items():
+            u1, u2, iters, errs = _cases.run_solver_case(R, case)
+            out["%s/%s/u1" % (tag, name)] = u1
+            out["%s/%s/u2" % (tag, name)] = u2
+            out["%s/%s/iters" % (tag, name)] = iters
+            out["%s/%s/errs" % (tag, name)] = errs
+    path = os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()
