@@ -1,0 +1,139 @@
+/* tvl1_b200.h -- C ABI of the B200 (sm_100a) TV-L1 optical-flow solver.
+ *
+ * This is the drop-in boundary for the TV-L1 path of 12334zq/optical-flow-1.  Plain C, plain
+ * pointers and sizes.  Citations are relative to the reference tree (/root/reference).
+ *
+ *   reference interface                                    entry point here
+ *   ------------------------------------------------------------------------------------------
+ *   Dual_TVL1_optic_flow_multiscale  src/tvl1flow.h:56-70   tvl1_solve_f32 / _f64, tvl1_solve_batch_*
+ *   Dual_TVL1_optic_flow             src/tvl1flow.h:36-48   tvl1_single_scale_f32 / _f64
+ *   (C99 float variant of both)      3rdparty/tvl1flow_3/tvl1flow_lib.c:47-60, :299-314
+ *   image_normalization_2            src/utils.h:27         tvl1_normalize_f32            (test hook)
+ *   gaussian                         src/operators.h:128    tvl1_gaussian_f32             (test hook)
+ *   zoom_size / zoom_out / zoom_in   src/zoom.h:20,32,57    tvl1_zoom_size, tvl1_zoom_out_f32, tvl1_zoom_in_f32
+ *   centered_gradient + 3x bicubic_interpolation_warp + rho_c/grad loop
+ *                                    src/tvl1flow.cpp:84,94-109   tvl1_warp_f32           (test hook)
+ *   loop body of the while           src/tvl1flow.cpp:114-181     tvl1_iterate_f32        (test hook)
+ *
+ * The C++ symbols with the reference's exact (mangled) signatures are exported by the same
+ * shared object (csrc/tvl1flow_dropin.cpp) and are implemented on top of this ABI only.
+ *
+ * Conventions
+ *  - images and flow fields are dense row-major planes, index p = i*nx + j, no padding
+ *    (src/tvl1flow.cpp:61, SURVEY 8b "Data layout").  Batches are npairs such planes back to back.
+ *  - every function returns 0 on success or a TVL1_ERR_* code; tvl1_last_error() gives text.
+ *  - there is no CPU fallback: without a CUDA device tvl1_create() fails.
+ *  - a tvl1_ctx is bound to one device and one host thread at a time; use one context per
+ *    thread / per GPU for concurrent calls.
+ */
+#ifndef TVL1_B200_H
+#define TVL1_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVL1_OK 0
+#define TVL1_ERR_CUDA 1          /* a CUDA runtime call failed */
+#define TVL1_ERR_SIGMA 2         /* "GaussianSmooth: sigma too large" (src/operators.cpp:520-522) */
+#define TVL1_ERR_ARG 3           /* bad argument (null pointer, non-positive size, ...) */
+#define TVL1_ERR_NODEVICE 4      /* no usable CUDA device */
+
+#define TVL1_MAX_ITERATIONS 300      /* src/tvl1flow.cpp:22 */
+#define TVL1_PRESMOOTHING_SIGMA 0.8  /* src/tvl1flow.cpp:23 */
+#define TVL1_GRAD_IS_ZERO 1E-10      /* src/tvl1flow.cpp:24 */
+#define TVL1_ZOOM_SIGMA_ZERO 0.6     /* src/zoom.cpp:15 */
+
+typedef struct tvl1_ctx tvl1_ctx;
+
+/* Solver parameters: the reference's own set (src/tvl1flow.h:56-70), same meaning and order. */
+typedef struct tvl1_params {
+    double tau;      /* time step */
+    double lambda;   /* weight of the data term */
+    double theta;    /* weight of (u - v)^2 */
+    int nscales;     /* number of pyramid levels (not clamped here; the CLI clamps, tvl1flow_main.cpp:185-188) */
+    double zfactor;  /* pyramid down-sampling factor, 0 < zfactor < 1 */
+    int warps;       /* warps per level */
+    double epsilon;  /* stopping threshold; the loop stops after the first iteration whose mean
+                        squared update is <= epsilon^2, or after TVL1_MAX_ITERATIONS */
+} tvl1_params;
+
+/* Counters of the most recent solve on a context (all device work is stream-ordered). */
+typedef struct tvl1_stats {
+    unsigned long long kernel_launches;   /* kernels of this library launched */
+    unsigned long long iterate_launches;  /* of which: fused iteration kernel */
+    unsigned long long pixel_iterations;  /* sum over iteration launches of (pixels of every pair still iterating) */
+    unsigned long long pixel_warps;       /* pixels processed by the warp+precompute kernel */
+    double iterate_ms;                    /* device time inside iteration launches (CUDA events; 0 unless profiling on) */
+    double warp_ms;                       /* device time inside warp launches (same) */
+    double total_ms;                      /* device time of the whole solve (same) */
+    unsigned long long host_syncs;        /* stream synchronisations issued for loop control */
+} tvl1_stats;
+
+/* -- life cycle --------------------------------------------------------------------------- */
+int tvl1_device_count(void);
+int tvl1_create(int device, tvl1_ctx **out);
+void tvl1_destroy(tvl1_ctx *ctx);
+const char *tvl1_last_error(const tvl1_ctx *ctx);  /* ctx may be NULL: error of the last failed tvl1_create */
+int tvl1_set_profiling(tvl1_ctx *ctx, int on);     /* bracket kernels with CUDA events (tvl1_stats *_ms) */
+int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs);  /* pairs advanced in lock-step per workspace (default 32) */
+int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out);
+void tvl1_default_params(tvl1_params *p);          /* tvl1flow_main.cpp:24-33 with nscales = 5 */
+
+/* -- the solver: Dual_TVL1_optic_flow_multiscale (src/tvl1flow.cpp:219-328) ---------------- */
+/* HOST buffers.  iters_out / errs_out may be NULL; otherwise [nscales*warps] per pair, coarsest
+ * level first, exactly the numbers the reference prints in verbose mode (tvl1flow.cpp:184-188). */
+int tvl1_solve_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2,
+                   int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
+int tvl1_solve_f64(tvl1_ctx *ctx, const double *I0, const double *I1, double *u1, double *u2,
+                   int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
+/* npairs independent frame pairs of one shape, HOST buffers [npairs][ny][nx]. */
+int tvl1_solve_batch_f32(tvl1_ctx *ctx, int npairs, const float *I0, const float *I1, float *u1,
+                         float *u2, int nx, int ny, const tvl1_params *prm, int *iters_out,
+                         double *errs_out);
+int tvl1_solve_batch_f64(tvl1_ctx *ctx, int npairs, const double *I0, const double *I1, double *u1,
+                         double *u2, int nx, int ny, const tvl1_params *prm, int *iters_out,
+                         double *errs_out);
+/* Same, DEVICE buffers (dense, 16-byte aligned).  Work is issued on the context's stream and
+ * complete on return.  iters_out / errs_out are HOST pointers. */
+int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const float *dI1,
+                             float *du1, float *du2, int nx, int ny, const tvl1_params *prm,
+                             int *iters_out, double *errs_out);
+
+/* -- one level: Dual_TVL1_optic_flow (src/tvl1flow.cpp:46-212) ----------------------------- */
+/* u1,u2 are in/out (the initial flow is used, tvl1flow.cpp:94); nscales/zfactor of prm ignored;
+ * iters_out/errs_out are [warps]. */
+int tvl1_single_scale_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2,
+                          int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
+int tvl1_single_scale_f64(tvl1_ctx *ctx, const double *I0, const double *I1, double *u1, double *u2,
+                          int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
+
+/* -- per-kernel hooks (HOST buffers; used by the parity tests) ----------------------------- */
+void tvl1_zoom_size(int nx, int ny, int *nxx, int *nyy, double factor);
+int tvl1_normalize_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *I0n, float *I1n,
+                       int nx, int ny);
+int tvl1_gaussian_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, double sigma);
+int tvl1_zoom_out_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, double factor);
+int tvl1_zoom_in_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, int nxx, int nyy,
+                     double scale);
+/* centered_gradient + the three warps + rho_c/grad, fused (tvl1flow.cpp:84,94-109) */
+int tvl1_warp_f32(tvl1_ctx *ctx, const float *I0, const float *I1, const float *u1, const float *u2,
+                  int nx, int ny, float *I1wx, float *I1wy, float *rho_c, float *grad);
+/* exactly `iters` passes of the loop body (tvl1flow.cpp:114-181), no stopping test.
+ * u1..p22 in/out; errs_out[iters] = mean squared update of each pass (may be NULL). */
+int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12, float *p21,
+                     float *p22, const float *rho_c, const float *I1wx, const float *I1wy,
+                     const float *grad, int nx, int ny, double tau, double lambda, double theta,
+                     int iters, double *errs_out);
+
+/* -- bench hook: the fused iteration kernel alone on synthetic device-resident state -------- */
+/* Runs `launches` iteration launches over `npairs` pairs of nx*ny (state and constants are
+ * seeded pseudo-random, resident in HBM) and returns the CUDA-event time of those launches. */
+int tvl1_bench_iterate(tvl1_ctx *ctx, int npairs, int nx, int ny, int launches, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVL1_B200_H */

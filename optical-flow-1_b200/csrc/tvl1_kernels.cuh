@@ -1,0 +1,686 @@
+// Device kernels of the B200 TV-L1 solver (sm_100a).  fp32 storage and arithmetic, fp64 only for
+// the stopping-test reduction and for pyramid sample coordinates.
+//
+// Data layout in HBM:
+//   * every image / field is a row-major plane with a row pitch that is a multiple of 4 floats, so
+//     every row start is 16-byte aligned (float4 / TMA friendly).  Columns [nx, pitch) are padding:
+//     never read into a valid result, may hold garbage.
+//   * a batch of B pairs stores plane b at  base + b * plane0   (plane0 = pitch*ny of the finest
+//     level, fixed for all levels so buffers are reused across the pyramid).
+//   * flow + dual state: state[set][field][b][plane0], set in {0,1} (ping-pong), field in
+//     {u1,u2,p11,p12,p21,p22}.  PairCtl[b].cur names the live set of pair b.
+//   * per-warp constants: consts[field][b][plane0], field in {I1wx, I1wy, rho_c, grad}.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tvl1 {
+
+constexpr int kMaxIterations = 300;       // src/tvl1flow.cpp:22
+constexpr float kGradIsZero = 1e-10f;     // src/tvl1flow.cpp:24
+constexpr int kMaxTaps = 16;              // (int)(5*sigma)+1 <= 16  <=>  sigma < 3.2 (zfactor > 0.19)
+
+enum Field { F_U1 = 0, F_U2, F_P11, F_P12, F_P21, F_P22, F_COUNT };
+enum Const { C_IX = 0, C_IY, C_RHO, C_GRAD, C_COUNT };
+
+struct Level {
+    int nx, ny, pitch;
+};
+
+// Per-pair loop control, owned by the device (src/tvl1flow.cpp:111-113 lives here).
+struct PairCtl {
+    int cur;              // live state set
+    int active;           // 1 while the current warp step still iterates
+    int n;                // iterations done in the current warp step
+    unsigned int arrive;  // CTA arrival counter (last-block election)
+    double err;           // mean squared update of the last iteration
+};
+
+struct GaussTaps {
+    int size;             // taps on one side incl. centre: (int)(5*sigma)+1, src/operators.cpp:515
+    float w[kMaxTaps];
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float *p)
+{
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+__device__ __forceinline__ void st4(float *p, float4 v)
+{
+    *reinterpret_cast<float4 *>(p) = v;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi)
+{
+    return min(max(v, lo), hi);
+}
+// order-preserving float <-> uint map for atomicMin/atomicMax
+__device__ __forceinline__ unsigned int f2ord(float f)
+{
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (a) pyramid
+// ------------------------------------------------------------------------------------------------
+
+// Joint min / max of both images of each pair: getminmax x2, src/utils.cpp:509-525 and :293-308.
+// in0/in1: dense [B][n] floats.  mm[b] = {ord(min), ord(max)}, pre-set to {~0u, 0u}.
+__global__ void k_minmax(const float *__restrict__ in0, const float *__restrict__ in1, size_t n,
+                         unsigned int *__restrict__ mm)
+{
+    const int b = blockIdx.y;
+    const float *a = in0 + (size_t) b * n;
+    const float *c = in1 + (size_t) b * n;
+    float lo = INFINITY, hi = -INFINITY;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t) gridDim.x * blockDim.x) {
+        const float x = __ldg(a + i), y = __ldg(c + i);
+        lo = fminf(lo, fminf(x, y));
+        hi = fmaxf(hi, fmaxf(x, y));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float slo[32], shi[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { slo[w] = lo; shi[w] = hi; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        lo = lane < nw ? slo[lane] : INFINITY;
+        hi = lane < nw ? shi[lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) {
+            atomicMin(&mm[2 * b], f2ord(lo));
+            atomicMax(&mm[2 * b + 1], f2ord(hi));
+        }
+    }
+}
+
+// Separable Gaussian with the reference's boundary rule, optionally fused with the [0,255]
+// normalisation on load and with a decimation by D on store.
+//   gaussian            src/operators.cpp:506-624  (rows then columns, reflecting boundary:
+//                       x<0 -> -x, x>=n -> 2n-1-x; sum order B0*c + sum_j Bj*(l_j + r_j))
+//   image_normalization src/utils.cpp:310-318      ("255*(I-min)/den" when den > 0)
+//   zoom_out, f = 1/D   src/zoom.cpp:41-78         (sample points j/f are integers, where the cubic
+//                       returns the centre tap exactly -> blur followed by [D*i, D*j] decimation)
+// One CTA produces a TW x TH output tile from a (D*TW+2r) x (D*TH+2r) input tile in shared memory.
+// z = image index in [0, nimg); pair (for min/max) = z % B.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__restrict__ out,
+        int out_pitch, size_t out_stride, int nx, int ny, int onx, int ony, GaussTaps taps,
+        const unsigned int *__restrict__ mm, int B)
+{
+    constexpr int TW = 64 / D, TH = 32 / D;        // output tile
+    constexpr int IW = 64, IH = 32;                // input footprint without halo
+    constexpr int RMAX = kMaxTaps - 1;
+    __shared__ float s_in[(IH + 2 * RMAX)][IW + 2 * RMAX + 1];
+    __shared__ float s_row[(IH + 2 * RMAX)][TW + 1];
+
+    const int r = taps.size - 1;
+    const int z = blockIdx.z;
+    const float *src = in + (size_t) z * in_stride;
+    float *dst = out + (size_t) z * out_stride;
+    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+    const int ix0 = ox0 * D - r, iy0 = oy0 * D - r;
+    const int iw = IW + 2 * r - (D - 1), ih = IH + 2 * r - (D - 1);
+
+    float mn = 0.f, den = 0.f;
+    if (mm) {
+        mn = ord2f(mm[2 * (z % B)]);
+        den = ord2f(mm[2 * (z % B) + 1]) - mn;
+    }
+
+    for (int t = threadIdx.x; t < iw * ih; t += blockDim.x) {
+        const int ly = t / iw, lx = t - ly * iw;
+        int gx = ix0 + lx, gy = iy0 + ly;
+        gx = gx < 0 ? -gx : (gx >= nx ? 2 * nx - 1 - gx : gx);
+        gy = gy < 0 ? -gy : (gy >= ny ? 2 * ny - 1 - gy : gy);
+        gx = clampi(gx, 0, nx - 1);   // only reachable for tiles hanging over the image edge
+        gy = clampi(gy, 0, ny - 1);
+        float v = __ldg(src + (size_t) gy * in_pitch + gx);
+        if (den > 0.f) v = 255.0f * (v - mn) / den;
+        s_in[ly][lx] = v;
+    }
+    __syncthreads();
+
+    // row pass: every input row of the tile, output columns only
+    for (int t = threadIdx.x; t < TW * ih; t += blockDim.x) {
+        const int ly = t / TW, ox = t - ly * TW;
+        const int c = ox * D + r;
+        float sum = taps.w[0] * s_in[ly][c];
+        for (int j = 1; j <= r; j++) sum += taps.w[j] * (s_in[ly][c - j] + s_in[ly][c + j]);
+        s_row[ly][ox] = sum;
+    }
+    __syncthreads();
+
+    // column pass on output rows
+    for (int t = threadIdx.x; t < TW * TH; t += blockDim.x) {
+        const int oy = t / TW, ox = t - oy * TW;
+        const int gx = ox0 + ox, gy = oy0 + oy;
+        if (gx >= onx || gy >= ony) continue;
+        const int c = oy * D + r;
+        float sum = taps.w[0] * s_row[c][ox];
+        for (int j = 1; j <= r; j++) sum += taps.w[j] * (s_row[c - j][ox] + s_row[c + j][ox]);
+        dst[(size_t) gy * out_pitch + gx] = sum;
+    }
+}
+
+// Keys cubic through v0..v3 at offset t from v1: src/bicubic_interpolation.cpp:108-123.
+__device__ __forceinline__ float cubic_cell(float v0, float v1, float v2, float v3, float t)
+{
+    return v1 + 0.5f * t * (v2 - v0 + t * (2.0f * v0 - 5.0f * v1 + 4.0f * v2 - v3
+                                           + t * (3.0f * (v1 - v2) + v3 - v0)));
+}
+
+// bicubic_interpolation_at with border_out = false and non-negative coordinates
+// (src/bicubic_interpolation.cpp:153-245): neighbours x-1,x,x+1,x+2 index-clamped (Neumann),
+// fractions relative to the (unclamped, since 0 <= uu < nx) base index; y first inside each
+// x column, then x.
+__device__ __forceinline__ float bicubic_clamped(const float *__restrict__ img, int pitch, int nx,
+                                                 int ny, double uu, double vv)
+{
+    const int x = clampi((int) uu, 0, nx - 1), y = clampi((int) vv, 0, ny - 1);
+    const float tx = (float) (uu - x), ty = (float) (vv - y);
+    const int xs[4] = { max(x - 1, 0), x, min(x + 1, nx - 1), min(x + 2, nx - 1) };
+    const int ys[4] = { max(y - 1, 0), y, min(y + 1, ny - 1), min(y + 2, ny - 1) };
+    float col[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        col[a] = cubic_cell(__ldg(img + (size_t) ys[0] * pitch + xs[a]),
+                            __ldg(img + (size_t) ys[1] * pitch + xs[a]),
+                            __ldg(img + (size_t) ys[2] * pitch + xs[a]),
+                            __ldg(img + (size_t) ys[3] * pitch + xs[a]), ty);
+    }
+    return cubic_cell(col[0], col[1], col[2], col[3], tx);
+}
+
+// Bicubic resampling of nimg planes: out(i1, j1) = scale * in(j1 / fx, i1 / fy).
+//   zoom_out (general factor)  src/zoom.cpp:67-75      fx = fy = factor, scale = 1
+//   zoom_in + flow rescale     src/zoom.cpp:132-155, src/tvl1flow.cpp:302-309
+//                              fx = nxx/nx, fy = nyy/ny, scale = 1/zfactor
+// Sample coordinates are formed in fp64 exactly as the reference does (a division), so base
+// index and fraction agree bit for bit.
+__global__ void k_resample(const float *__restrict__ in, int in_pitch, size_t in_stride, int nx,
+                           int ny, float *__restrict__ out, int out_pitch, size_t out_stride,
+                           int onx, int ony, double fx, double fy, float scale)
+{
+    const int j1 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i1 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j1 >= onx || i1 >= ony) return;
+    const float *src = in + (size_t) blockIdx.z * in_stride;
+    const double j2 = j1 / fx, i2 = i1 / fy;
+    const float g = bicubic_clamped(src, in_pitch, nx, ny, j2, i2);
+    out[(size_t) blockIdx.z * out_stride + (size_t) i1 * out_pitch + j1] = g * scale;
+}
+
+// zoom_in of both flow components of every pair between the ping-pong state sets:
+// reads set cur (coarse level), writes set cur^1 (fine level), then k_flip_cur flips.
+__global__ void k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride,
+                               size_t set_stride, const PairCtl *__restrict__ ctl, Level coarse,
+                               Level fine, double fx, double fy, float scale)
+{
+    const int j1 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i1 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j1 >= fine.nx || i1 >= fine.ny) return;
+    const int b = blockIdx.z >> 1, comp = blockIdx.z & 1;
+    const int cur = ctl[b].cur;
+    const float *src = state + (size_t) cur * set_stride + (size_t) comp * field_stride + (size_t) b * plane0;
+    float *dst = state + (size_t) (cur ^ 1) * set_stride + (size_t) comp * field_stride + (size_t) b * plane0;
+    const double j2 = j1 / fx, i2 = i1 / fy;
+    dst[(size_t) i1 * fine.pitch + j1] =
+        bicubic_clamped(src, coarse.pitch, coarse.nx, coarse.ny, j2, i2) * scale;
+}
+
+__global__ void k_flip_cur(PairCtl *ctl, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) ctl[b].cur ^= 1;
+}
+
+// Zeroes the dual variable of every pair in its live set (src/tvl1flow.cpp:87-90) and, when
+// zero_u is set, the flow too (coarsest level, :278-280).
+__global__ void k_zero_fields(float *__restrict__ state, size_t plane0, size_t field_stride,
+                              size_t set_stride, const PairCtl *__restrict__ ctl, size_t n4,
+                              int first_field)
+{
+    const int b = blockIdx.z;
+    const int f = first_field + blockIdx.y;
+    float4 *dst = reinterpret_cast<float4 *>(state + (size_t) ctl[b].cur * set_stride +
+                                             (size_t) f * field_stride + (size_t) b * plane0);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (size_t) gridDim.x * blockDim.x)
+        dst[i] = z;
+}
+
+// start of a warp step: n = 0, error = INFINITY (src/tvl1flow.cpp:111-112)
+__global__ void k_begin_warp(PairCtl *ctl, int *active_pairs, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        ctl[b].active = 1;
+        ctl[b].n = 0;
+        ctl[b].arrive = 0u;
+        ctl[b].err = INFINITY;
+    }
+    if (b == 0) *active_pairs = B;
+}
+
+__global__ void k_init_ctl(PairCtl *ctl, unsigned int *mm, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        ctl[b].cur = 0; ctl[b].active = 0; ctl[b].n = 0; ctl[b].arrive = 0u; ctl[b].err = 0.0;
+        mm[2 * b] = 0xffffffffu;
+        mm[2 * b + 1] = 0u;
+    }
+}
+
+// dense <-> pitched copies of the flow (live set), and fp64 <-> fp32 conversion at the boundary
+__global__ void k_export_flow(const float *__restrict__ state, size_t plane0, size_t field_stride,
+                              size_t set_stride, const PairCtl *__restrict__ ctl, Level lv,
+                              float *__restrict__ u1, float *__restrict__ u2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j >= lv.nx || i >= lv.ny) return;
+    const int b = blockIdx.z;
+    const float *s = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0 + (size_t) i * lv.pitch + j;
+    const size_t o = ((size_t) b * lv.ny + i) * lv.nx + j;
+    u1[o] = s[0];
+    u2[o] = s[field_stride];
+}
+
+__global__ void k_import_flow(float *__restrict__ state, size_t plane0, size_t field_stride,
+                              size_t set_stride, const PairCtl *__restrict__ ctl, Level lv,
+                              const float *__restrict__ u1, const float *__restrict__ u2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j >= lv.nx || i >= lv.ny) return;
+    const int b = blockIdx.z;
+    float *s = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0 + (size_t) i * lv.pitch + j;
+    const size_t o = ((size_t) b * lv.ny + i) * lv.nx + j;
+    s[0] = u1[o];
+    s[field_stride] = u2[o];
+}
+
+// dense [nimg][ny][nx] -> pitched planes (used where no blur precedes: single-scale entry, hooks)
+__global__ void k_pack(const float *__restrict__ in, float *__restrict__ out, int nx, int ny,
+                       int pitch, size_t out_stride)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    out[(size_t) blockIdx.z * out_stride + (size_t) i * pitch + j] =
+        in[((size_t) blockIdx.z * ny + i) * nx + j];
+}
+__global__ void k_unpack(const float *__restrict__ in, float *__restrict__ out, int nx, int ny,
+                         int pitch, size_t in_stride)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    out[((size_t) blockIdx.z * ny + i) * nx + j] =
+        in[(size_t) blockIdx.z * in_stride + (size_t) i * pitch + j];
+}
+
+__global__ void k_f64_to_f32(const double *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t) gridDim.x * blockDim.x)
+        out[i] = (float) in[i];
+}
+__global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ out, size_t n)
+{
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t) gridDim.x * blockDim.x)
+        out[i] = (double) in[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// (b) warp + precompute
+// ------------------------------------------------------------------------------------------------
+
+// Catmull-Rom / Keys(a=-1/2) weights of the four taps at fraction t; algebraically the cubic of
+// src/bicubic_interpolation.cpp:108-123 written as a dot product so that one set of weights
+// serves I1, dI1/dx and dI1/dy.
+__device__ __forceinline__ void keys_weights(float t, float w[4])
+{
+    const float t2 = t * t, t3 = t2 * t;
+    w[0] = 0.5f * (-t + 2.0f * t2 - t3);
+    w[1] = 0.5f * (2.0f - 5.0f * t2 + 3.0f * t3);
+    w[2] = 0.5f * (t + 4.0f * t2 - 3.0f * t3);
+    w[3] = 0.5f * (t3 - t2);
+}
+
+// One kernel for src/tvl1flow.cpp:84 and :94-109:
+//   centered_gradient(I1)                      src/operators.cpp:335-406
+//   bicubic_interpolation_warp(I1 / I1x / I1y) src/bicubic_interpolation.cpp:352-374, :153-245
+//   grad = I1wx^2 + I1wy^2,  rho_c = I1w - I1wx*u1 - I1wy*u2 - I0
+// The gradient planes are never materialised: centered_gradient is linear, so the warped
+// derivatives are taken from a 6x6 (corner-less, 32-tap) neighbourhood of I1 with index-clamped
+// outer taps, which is exactly 0.5*(I1[clamp(k+1)] - I1[clamp(k-1)]) pushed through the same
+// bicubic weights.  With border_out = true the result is non-zero iff
+// 1 <= (int)(j+u1) <= nx-3 and 1 <= (int)(i+u2) <= ny-3 (all three warps share this test);
+// (int) truncation of the non-negative coordinate equals j + floor(u1), formed exactly.
+__device__ __forceinline__ void warp_pixel(const float *__restrict__ I1, int pitch, int nx, int ny,
+                                           int j, int i, float u1, float u2, float I0v,
+                                           float &Ix, float &Iy, float &rho, float &grad)
+{
+    const float fu = floorf(u1), fv = floorf(u2);
+    const float xf = (float) j + fu, yf = (float) i + fv;
+    float w = 0.f, wx = 0.f, wy = 0.f;
+    if (xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3)) {
+        const int x = (int) xf, y = (int) yf;
+        float ax[4], ay[4];
+        keys_weights(u1 - fu, ax);
+        keys_weights(u2 - fv, ay);
+        const int xm2 = max(x - 2, 0), xp3 = min(x + 3, nx - 1);
+        float rowI[6];   // x-interpolated I1 on rows y-2 .. y+3 (outer rows index-clamped)
+        float accx = 0.f;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const int yy = clampi(y - 2 + r, 0, ny - 1);
+            const float *row = I1 + (size_t) yy * pitch;
+            const float c1 = __ldg(row + x - 1), c2 = __ldg(row + x), c3 = __ldg(row + x + 1),
+                        c4 = __ldg(row + x + 2);
+            rowI[r] = ax[0] * c1 + ax[1] * c2 + ax[2] * c3 + ax[3] * c4;
+            if (r >= 1 && r <= 4) {
+                const float c0 = __ldg(row + xm2), c5 = __ldg(row + xp3);
+                const float dxr = ax[0] * (c2 - c0) + ax[1] * (c3 - c1) + ax[2] * (c4 - c2) + ax[3] * (c5 - c3);
+                accx += ay[r - 1] * dxr;
+            }
+        }
+        w = ay[0] * rowI[1] + ay[1] * rowI[2] + ay[2] * rowI[3] + ay[3] * rowI[4];
+        wx = 0.5f * accx;
+        wy = 0.5f * (ay[0] * (rowI[2] - rowI[0]) + ay[1] * (rowI[3] - rowI[1]) +
+                     ay[2] * (rowI[4] - rowI[2]) + ay[3] * (rowI[5] - rowI[3]));
+    }
+    Ix = wx;
+    Iy = wy;
+    grad = wx * wx + wy * wy;
+    rho = w - wx * u1 - wy * u2 - I0v;
+}
+
+__global__ void __launch_bounds__(256)
+k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_stride,
+       const float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
+       const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= lv.nx || i >= lv.ny) return;
+    const int b = blockIdx.z;
+    const size_t p = (size_t) i * lv.pitch + j;
+    const float *u = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0 + p;
+    const float u1 = __ldg(u), u2 = __ldg(u + field_stride);
+    float Ix, Iy, rho, grad;
+    warp_pixel(I1 + (size_t) b * img_stride, lv.pitch, lv.nx, lv.ny, j, i, u1, u2,
+               __ldg(I0 + (size_t) b * img_stride + p), Ix, Iy, rho, grad);
+    float *c = consts + (size_t) b * plane0 + p;
+    c[(size_t) C_IX * field_stride] = Ix;
+    c[(size_t) C_IY * field_stride] = Iy;
+    c[(size_t) C_RHO * field_stride] = rho;
+    c[(size_t) C_GRAD * field_stride] = grad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (c) fused primal-dual iteration, one iteration per launch (T = 1), register marching
+// ------------------------------------------------------------------------------------------------
+//
+// One launch = one pass of the loop body src/tvl1flow.cpp:114-181 for every pair still iterating:
+//   TH (:117-143), divergence x2 (src/operators.cpp:35-78), u update + error (:150-162),
+//   forward_gradient x2 (src/operators.cpp:86-125), p update (:169-181), stopping rule (:113).
+// v, div p and grad u are never materialised.
+//
+// Mapping: a warp owns a strip of 124 columns x R rows.  Lane l holds 4 consecutive pixels
+// (float4); lanes 0..30 are owners, lane 31 only evaluates u_new for the column group to the right
+// so that its left neighbour can take the forward x-difference by shuffle.  The warp marches down
+// its strip keeping u_new of the current row and the p12/p22 row above in registers, so every
+// plane element is loaded once per launch (plus one halo row per strip and one halo lane per warp).
+// State is read from set `cur` and written to set `cur^1` (neighbouring strips read each other's
+// old values, hence ping-pong).  Per-CTA error partials are reduced in a fixed order by the last
+// CTA of each pair (deterministic, fp64), which also applies the stopping rule on the device.
+
+struct IterParams {
+    float *state;
+    const float *consts;
+    PairCtl *ctl;
+    double *partials;            // [B][parts_per_pair]
+    int *active_pairs;
+    int *stat_iters;             // [B][stat_stride]
+    double *stat_errs;
+    unsigned long long *px_iters;
+    size_t plane0, field_stride, set_stride;
+    Level lv;
+    int parts_per_pair;
+    int stat_stride, stat_slot;
+    int max_iter;
+    float l_t, theta, taut;
+    double eps2;
+};
+
+struct Row4 {                    // one image row segment of 4 pixels, everything the update needs
+    float4 u1, u2, ix, iy, rho, grad, p11, p12, p21, p22;
+};
+
+__device__ __forceinline__ float th_coeff(float rho, float grad, float l_t)
+{
+    // src/tvl1flow.cpp:123-139: d = c * (I1wx, I1wy)
+    const float thr = l_t * grad;
+    return (rho < -thr) ? l_t : ((rho > thr) ? -l_t : ((grad < kGradIsZero) ? 0.f : (-rho / grad)));
+}
+
+#define TVL1_F4_GET(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
+
+template <int R, int WY>
+__global__ void __launch_bounds__(32 * WY)
+k_iterate_t1(const IterParams P)
+{
+    const int b = blockIdx.z;
+    PairCtl *ctl = P.ctl + b;
+    if (!ctl->active) return;                       // uniform for the whole CTA
+
+    const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cur = ctl->cur;
+    const float *sin = P.state + (size_t) cur * P.set_stride + (size_t) b * P.plane0;
+    float *sout = P.state + (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0;
+    const float *cst = P.consts + (size_t) b * P.plane0;
+    const size_t fs = P.field_stride;
+
+    const int x0 = blockIdx.x * 124 + lane * 4;
+    const int ys = (blockIdx.y * WY + warp) * R;
+    const int ye = min(ys + R, ny);
+    const bool in_alloc = x0 < pitch;               // float4 lies inside the row allocation
+    const bool owner = in_alloc && lane < 31 && x0 < nx;
+
+    float err = 0.f;
+
+    if (ys < ny) {                                  // warp-uniform
+        auto load_row = [&](int y, Row4 &r) {
+            if (in_alloc) {
+                const size_t o = (size_t) y * pitch + x0;
+                r.u1 = ldg4(sin + F_U1 * fs + o);
+                r.u2 = ldg4(sin + F_U2 * fs + o);
+                r.p11 = ldg4(sin + F_P11 * fs + o);
+                r.p12 = ldg4(sin + F_P12 * fs + o);
+                r.p21 = ldg4(sin + F_P21 * fs + o);
+                r.p22 = ldg4(sin + F_P22 * fs + o);
+                r.ix = ldg4(cst + C_IX * fs + o);
+                r.iy = ldg4(cst + C_IY * fs + o);
+                r.rho = ldg4(cst + C_RHO * fs + o);
+                r.grad = ldg4(cst + C_GRAD * fs + o);
+            } else {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                r.u1 = r.u2 = r.p11 = r.p12 = r.p21 = r.p22 = r.ix = r.iy = r.rho = r.grad = z;
+            }
+        };
+        // u_new of one row; a12/a22 = p12/p22 of the row above (0 on the first image row)
+        auto primal = [&](int y, const Row4 &r, const float4 &a12, const float4 &a22, float4 &n1,
+                          float4 &n2, bool count) {
+            // left neighbours of p11/p21: previous lane's .w, or a scalar load for lane 0
+            float l11 = __shfl_up_sync(0xffffffffu, r.p11.w, 1);
+            float l21 = __shfl_up_sync(0xffffffffu, r.p21.w, 1);
+            if (lane == 0) {
+                const bool has = x0 > 0;
+                const size_t o = (size_t) y * pitch + x0 - 1;
+                l11 = has ? __ldg(sin + F_P11 * fs + o) : 0.f;
+                l21 = has ? __ldg(sin + F_P21 * fs + o) : 0.f;
+            }
+            const bool last_row = (y == ny - 1);
+            float o1[4], o2[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float u1 = TVL1_F4_GET(r.u1, k), u2 = TVL1_F4_GET(r.u2, k);
+                const float ix = TVL1_F4_GET(r.ix, k), iy = TVL1_F4_GET(r.iy, k);
+                const float rho = TVL1_F4_GET(r.rho, k) + (ix * u1 + iy * u2);
+                const float c = th_coeff(rho, TVL1_F4_GET(r.grad, k), P.l_t);
+                const float v1 = u1 + c * ix, v2 = u2 + c * iy;
+                // divergence, src/operators.cpp:35-78: "+p1" dropped on the last column,
+                // "+p2" on the last row, p[-1] = 0
+                const bool last_col = (x0 + k >= nx - 1);
+                const float p11c = last_col ? 0.f : TVL1_F4_GET(r.p11, k);
+                const float p21c = last_col ? 0.f : TVL1_F4_GET(r.p21, k);
+                const float p11l = (k == 0) ? l11 : TVL1_F4_GET(r.p11, (k + 3) & 3);
+                const float p21l = (k == 0) ? l21 : TVL1_F4_GET(r.p21, (k + 3) & 3);
+                const float p12c = last_row ? 0.f : TVL1_F4_GET(r.p12, k);
+                const float p22c = last_row ? 0.f : TVL1_F4_GET(r.p22, k);
+                const float d1 = (p11c - p11l) + (p12c - TVL1_F4_GET(a12, k));
+                const float d2 = (p21c - p21l) + (p22c - TVL1_F4_GET(a22, k));
+                o1[k] = v1 + P.theta * d1;
+                o2[k] = v2 + P.theta * d2;
+                if (count && owner && x0 + k < nx) {
+                    const float e1 = o1[k] - u1, e2 = o2[k] - u2;
+                    err += e1 * e1 + e2 * e2;
+                }
+            }
+            n1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            n2 = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        };
+
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        Row4 ra, rb;
+        float4 a12 = zero4, a22 = zero4;
+        if (ys > 0 && in_alloc) {
+            const size_t o = (size_t) (ys - 1) * pitch + x0;
+            a12 = ldg4(sin + F_P12 * fs + o);
+            a22 = ldg4(sin + F_P22 * fs + o);
+        }
+        load_row(ys, ra);
+        float4 ua1, ua2, ub1 = zero4, ub2 = zero4;
+        primal(ys, ra, a12, a22, ua1, ua2, true);
+
+        for (int y = ys; y < ye; y++) {
+            const bool has_below = (y + 1 < ny);
+            if (has_below) {
+                load_row(y + 1, rb);
+                primal(y + 1, rb, ra.p12, ra.p22, ub1, ub2, y + 1 < ye);
+            }
+            // forward gradient of u_new (src/operators.cpp:86-125) and dual update (:169-181)
+            const float r1 = __shfl_down_sync(0xffffffffu, ua1.x, 1);
+            const float r2 = __shfl_down_sync(0xffffffffu, ua2.x, 1);
+            float q11[4], q12[4], q21[4], q22[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool last_col = (x0 + k >= nx - 1);
+                const float c1 = TVL1_F4_GET(ua1, k), c2 = TVL1_F4_GET(ua2, k);
+                const float e1 = (k == 3) ? r1 : TVL1_F4_GET(ua1, (k + 1) & 3);
+                const float e2 = (k == 3) ? r2 : TVL1_F4_GET(ua2, (k + 1) & 3);
+                const float u1x = last_col ? 0.f : e1 - c1;
+                const float u2x = last_col ? 0.f : e2 - c2;
+                const float u1y = has_below ? TVL1_F4_GET(ub1, k) - c1 : 0.f;
+                const float u2y = has_below ? TVL1_F4_GET(ub2, k) - c2 : 0.f;
+                const float g1 = sqrtf(u1x * u1x + u1y * u1y);
+                const float g2 = sqrtf(u2x * u2x + u2y * u2y);
+                const float i1 = 1.0f / (1.0f + P.taut * g1);
+                const float i2 = 1.0f / (1.0f + P.taut * g2);
+                q11[k] = (TVL1_F4_GET(ra.p11, k) + P.taut * u1x) * i1;
+                q12[k] = (TVL1_F4_GET(ra.p12, k) + P.taut * u1y) * i1;
+                q21[k] = (TVL1_F4_GET(ra.p21, k) + P.taut * u2x) * i2;
+                q22[k] = (TVL1_F4_GET(ra.p22, k) + P.taut * u2y) * i2;
+            }
+            if (owner) {
+                const size_t o = (size_t) y * pitch + x0;
+                st4(sout + F_U1 * fs + o, ua1);
+                st4(sout + F_U2 * fs + o, ua2);
+                st4(sout + F_P11 * fs + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
+                st4(sout + F_P12 * fs + o, make_float4(q12[0], q12[1], q12[2], q12[3]));
+                st4(sout + F_P21 * fs + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
+                st4(sout + F_P22 * fs + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
+            }
+            ra = rb;
+            ua1 = ub1;
+            ua2 = ub2;
+        }
+    }
+
+    // ---- error reduction: warp shuffle -> CTA -> fixed-order sum by the pair's last CTA ----
+    __shared__ double s_part[32];
+    __shared__ int s_last;
+    double e = warp_sum((double) err);
+    if (lane == 0) s_part[warp] = e;
+    __syncthreads();
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < WY; w++) s += s_part[w];
+        P.partials[(size_t) b * P.parts_per_pair + blk] = s;
+        __threadfence();
+        const unsigned int t = atomicAdd(&ctl->arrive, 1u);
+        s_last = (t == (unsigned int) nblk - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    __threadfence();
+    const volatile double *part = P.partials + (size_t) b * P.parts_per_pair;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += 32 * WY) s += part[i];
+    s = warp_sum(s);
+    if (lane == 0) s_part[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < WY; w++) tot += s_part[w];
+        const double error = tot / ((double) nx * (double) ny);   // src/tvl1flow.cpp:162
+        const int n = ctl->n + 1;
+        ctl->n = n;
+        ctl->err = error;
+        ctl->cur = cur ^ 1;
+        ctl->arrive = 0u;
+        atomicAdd(P.px_iters, (unsigned long long) nx * (unsigned long long) ny);
+        if (!(error > P.eps2 && n < P.max_iter)) {                // src/tvl1flow.cpp:113
+            ctl->active = 0;
+            P.stat_iters[(size_t) b * P.stat_stride + P.stat_slot] = n;
+            P.stat_errs[(size_t) b * P.stat_stride + P.stat_slot] = error;
+            atomicSub(P.active_pairs, 1);
+        }
+    }
+}
+
+} // namespace tvl1

@@ -1,0 +1,960 @@
+// Host side of the C ABI declared in include/tvl1_b200.h: device memory, the coarse-to-fine
+// driver (src/tvl1flow.cpp:219-328) and the per-level driver (src/tvl1flow.cpp:46-212) of the
+// reference, re-designed for a GPU: batches of independent frame pairs advance in lock-step, one
+// launch per primal-dual iteration for the whole batch, with the stopping rule evaluated on the
+// device per pair.  The host only decides how many launches to enqueue before it looks at the
+// "pairs still iterating" counter again.
+#include "../../include/tvl1_b200.h"
+#include "tvl1_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace tvl1;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kIterR = 8;      // rows per warp strip in k_iterate_t1
+constexpr int kIterWY = 4;     // warps per CTA
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+struct Workspace {
+    int nx = 0, ny = 0, nscales = 0, B = 0;
+    double zfactor = 0;
+    std::vector<Level> lv;
+    std::vector<size_t> pyr_off;     // float offset of level s: [I0 x B][I1 x B] planes of pitch*ny
+    size_t plane0 = 0, field_stride = 0, set_stride = 0;
+    float *pyr = nullptr, *state = nullptr, *consts = nullptr, *tmp = nullptr;
+    PairCtl *ctl = nullptr;
+    unsigned int *mm = nullptr;
+    double *partials = nullptr;
+    int *active = nullptr;
+    int *stat_iters = nullptr;
+    double *stat_errs = nullptr;
+    unsigned long long *counters = nullptr;   // [0] pixel-iterations
+    int parts_per_pair = 0;
+    int stat_stride = 0;
+    size_t bytes = 0;
+
+    size_t plane(int s) const { return (size_t) lv[s].pitch * lv[s].ny; }
+    float *I0(int s) const { return pyr + pyr_off[s]; }
+    float *I1(int s) const { return pyr + pyr_off[s] + (size_t) B * plane(s); }
+};
+
+struct EventPair { cudaEvent_t a, b; int kind; };   // kind 0 iterate, 1 warp, 2 total
+
+} // namespace
+
+struct tvl1_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool profiling = false;
+    int max_batch = 32;
+    tvl1_stats stats{};
+    Workspace ws;
+    int *h_active = nullptr;                 // pinned
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<EventPair> ev_used;
+    // staging for the host-buffer entry points
+    void *stage_in[2] = { nullptr, nullptr };
+    void *stage_out[2] = { nullptr, nullptr };
+    float *stage_f32[4] = { nullptr, nullptr, nullptr, nullptr };
+    size_t stage_bytes = 0, stage_f32_bytes = 0;
+    int sm_count = 148;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                     __FILE__, __LINE__);                                                          \
+            ctx->err = buf_;                                                                       \
+            return TVL1_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define CKL(ctx_) CK(cudaGetLastError()); (ctx_)->stats.kernel_launches++
+
+#define TRY(expr)                                                                                  \
+    do {                                                                                           \
+        int rc_ = (expr);                                                                          \
+        if (rc_ != TVL1_OK) return rc_;                                                            \
+    } while (0)
+
+int fail_arg(tvl1_ctx *ctx, const char *msg)
+{
+    if (ctx) ctx->err = msg;
+    return TVL1_ERR_ARG;
+}
+
+// 1-D Gaussian kernel of src/operators.cpp:515-539 (fp64 on the host, stored as fp32 taps)
+int make_taps(double sigma, GaussTaps &t)
+{
+    const double den = 2 * sigma * sigma;
+    const int size = (int) (5 * sigma) + 1;
+    if (size > kMaxTaps || size < 1) return -1;
+    double B[kMaxTaps];
+    for (int i = 0; i < size; i++) B[i] = 1 / (sigma * std::sqrt(2.0 * 3.1415926)) * std::exp(-i * i / den);
+    double norm = 0;
+    for (int i = 0; i < size; i++) norm += B[i];
+    norm *= 2;
+    norm -= B[0];
+    t.size = size;
+    for (int i = 0; i < kMaxTaps; i++) t.w[i] = i < size ? (float) (B[i] / norm) : 0.f;
+    return size;
+}
+
+void free_workspace(Workspace &w)
+{
+    cudaFree(w.pyr); cudaFree(w.state); cudaFree(w.consts); cudaFree(w.tmp); cudaFree(w.ctl);
+    cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.active); cudaFree(w.stat_iters);
+    cudaFree(w.stat_errs); cudaFree(w.counters);
+    w = Workspace();
+}
+
+int iterate_parts(const Level &l)
+{
+    return ceil_div(l.nx, 124) * ceil_div(l.ny, kIterR * kIterWY);
+}
+
+int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride)
+{
+    Workspace &w = ctx->ws;
+    if (w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
+        w.stat_stride >= stat_stride)
+        return TVL1_OK;
+    free_workspace(w);
+    w.nx = nx; w.ny = ny; w.nscales = nscales; w.zfactor = zfactor; w.B = B;
+    w.stat_stride = stat_stride;
+    w.lv.resize(nscales);
+    w.pyr_off.resize(nscales);
+    int cx = nx, cy = ny;
+    size_t off = 0;
+    int parts = 0;
+    for (int s = 0; s < nscales; s++) {
+        if (s > 0) {
+            int nxx, nyy;
+            tvl1_zoom_size(cx, cy, &nxx, &nyy, zfactor);
+            cx = nxx; cy = nyy;
+        }
+        if (cx < 1 || cy < 1) return fail_arg(ctx, "pyramid level has zero size (nscales too large)");
+        w.lv[s] = Level{ cx, cy, round_up(cx, 4) };
+        w.pyr_off[s] = off;
+        off += 2 * (size_t) B * w.plane(s);
+        parts = std::max(parts, iterate_parts(w.lv[s]));
+    }
+    w.plane0 = w.plane(0);
+    w.field_stride = (size_t) B * w.plane0;
+    w.set_stride = (size_t) F_COUNT * w.field_stride;
+    w.parts_per_pair = parts;
+    const size_t fl = sizeof(float);
+    CK(cudaMalloc(&w.pyr, off * fl));
+    CK(cudaMalloc(&w.state, 2 * w.set_stride * fl));
+    CK(cudaMalloc(&w.consts, (size_t) C_COUNT * w.field_stride * fl));
+    if (zfactor != 0.5 && nscales > 1) CK(cudaMalloc(&w.tmp, 2 * w.field_stride * fl));
+    CK(cudaMalloc(&w.ctl, sizeof(PairCtl) * B));
+    CK(cudaMalloc(&w.mm, sizeof(unsigned int) * 2 * B));
+    CK(cudaMalloc(&w.partials, sizeof(double) * (size_t) B * parts));
+    CK(cudaMalloc(&w.active, sizeof(int)));
+    CK(cudaMalloc(&w.stat_iters, sizeof(int) * (size_t) B * stat_stride));
+    CK(cudaMalloc(&w.stat_errs, sizeof(double) * (size_t) B * stat_stride));
+    CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * 4));
+    w.bytes = (off + 2 * w.set_stride + C_COUNT * w.field_stride) * fl;
+    // padding columns are never consumed, but keep them finite
+    CK(cudaMemsetAsync(w.state, 0, 2 * w.set_stride * fl, ctx->stream));
+    CK(cudaMemsetAsync(w.consts, 0, (size_t) C_COUNT * w.field_stride * fl, ctx->stream));
+    CK(cudaMemsetAsync(w.pyr, 0, off * fl, ctx->stream));
+    return TVL1_OK;
+}
+
+// ---- profiling events ---------------------------------------------------------------------------
+cudaEvent_t take_event(tvl1_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Span {
+    tvl1_ctx *ctx; int idx = -1;
+    Span(tvl1_ctx *c, int kind) : ctx(c)
+    {
+        if (!c->profiling) return;
+        EventPair p{ take_event(c), take_event(c), kind };
+        cudaEventRecord(p.a, c->stream);
+        c->ev_used.push_back(p);
+        idx = (int) c->ev_used.size() - 1;
+    }
+    void end() { if (idx >= 0) { cudaEventRecord(ctx->ev_used[idx].b, ctx->stream); idx = -1; } }
+    ~Span() { end(); }
+};
+
+void resolve_events(tvl1_ctx *ctx)
+{
+    for (auto &p : ctx->ev_used) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (p.kind == 0) ctx->stats.iterate_ms += ms;
+            else if (p.kind == 1) ctx->stats.warp_ms += ms;
+            else ctx->stats.total_ms += ms;
+        }
+        ctx->ev_pool.push_back(p.a);
+        ctx->ev_pool.push_back(p.b);
+    }
+    ctx->ev_used.clear();
+}
+
+// ---- launch helpers -----------------------------------------------------------------------------
+int launch_gauss(tvl1_ctx *ctx, int D, const float *in, int in_pitch, size_t in_stride, float *out,
+                 int out_pitch, size_t out_stride, int nx, int ny, int onx, int ony,
+                 const GaussTaps &taps, const unsigned int *mm, int B, int nimg)
+{
+    cudaStream_t st = ctx->stream;
+    if (D == 1) {
+        dim3 g(ceil_div(onx, 64), ceil_div(ony, 32), nimg);
+        k_gauss<1><<<g, 256, 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
+                                      onx, ony, taps, mm, B);
+    } else {
+        dim3 g(ceil_div(onx, 32), ceil_div(ony, 16), nimg);
+        k_gauss<2><<<g, 256, 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
+                                      onx, ony, taps, mm, B);
+    }
+    CKL(ctx);
+    return TVL1_OK;
+}
+
+IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &prm, int stat_slot,
+                       int max_iter)
+{
+    const Workspace &w = ctx->ws;
+    IterParams P;
+    P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
+    P.active_pairs = w.active; P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
+    P.px_iters = w.counters;
+    P.plane0 = w.plane0; P.field_stride = w.field_stride; P.set_stride = w.set_stride;
+    P.lv = lv; P.parts_per_pair = w.parts_per_pair;
+    P.stat_stride = w.stat_stride; P.stat_slot = stat_slot; P.max_iter = max_iter;
+    P.l_t = (float) (prm.lambda * prm.theta);                   // src/tvl1flow.cpp:62
+    P.theta = (float) prm.theta;
+    P.taut = (float) (prm.tau / prm.theta);                     // src/tvl1flow.cpp:171
+    P.eps2 = prm.epsilon * prm.epsilon;                         // src/tvl1flow.cpp:113
+    return P;
+}
+
+int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
+{
+    dim3 g(ceil_div(P.lv.nx, 124), ceil_div(P.lv.ny, kIterR * kIterWY), B);
+    k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    CKL(ctx);
+    ctx->stats.iterate_launches++;
+    return TVL1_OK;
+}
+
+int launch_warp(tvl1_ctx *ctx, int s, int B)
+{
+    const Workspace &w = ctx->ws;
+    const Level &l = w.lv[s];
+    dim3 g(ceil_div(l.nx, 32), ceil_div(l.ny, 8), B);
+    k_warp<<<g, dim3(32, 8), 0, ctx->stream>>>(w.I0(s), w.I1(s), w.plane(s), w.state, w.plane0,
+                                               w.field_stride, w.set_stride, w.ctl, w.consts, l);
+    CKL(ctx);
+    ctx->stats.pixel_warps += (unsigned long long) B * l.nx * l.ny;
+    return TVL1_OK;
+}
+
+int launch_zero(tvl1_ctx *ctx, int s, int B, int first_field, int nfields)
+{
+    const Workspace &w = ctx->ws;
+    const size_t n4 = w.plane(s) / 4;
+    dim3 g((unsigned) std::min<size_t>((n4 + 255) / 256, 1024), nfields, B);
+    k_zero_fields<<<g, 256, 0, ctx->stream>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                              n4, first_field);
+    CKL(ctx);
+    return TVL1_OK;
+}
+
+// The while loop of src/tvl1flow.cpp:113 for the whole batch: enqueue `chunk` iteration launches,
+// then read back how many pairs still iterate.  Launches for pairs that already stopped exit at
+// once, so over-shooting costs microseconds while every look costs a stream synchronisation.
+int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint)
+{
+    int launched = 0;
+    int chunk = std::max(1, std::min(chunk_hint, P.max_iter));
+    int used = 0;
+    while (launched < P.max_iter) {
+        const int k = std::min(chunk, P.max_iter - launched);
+        {
+            Span sp(ctx, 0);
+            for (int i = 0; i < k; i++) TRY(launch_iterate(ctx, P, B));
+        }
+        launched += k;
+        if (launched >= P.max_iter) { used = launched; break; }   // every pair hit the cap or stopped
+        CK(cudaMemcpyAsync(ctx->h_active, ctx->ws.active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.host_syncs++;
+        used = launched;
+        if (*ctx->h_active == 0) break;
+        chunk = std::max(4, chunk / 2);
+    }
+    chunk_hint = used;
+    return TVL1_OK;
+}
+
+// One pyramid level: src/tvl1flow.cpp:46-212 for every pair of the batch.
+int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base, int &chunk_hint)
+{
+    const Workspace &w = ctx->ws;
+    TRY(launch_zero(ctx, s, B, F_P11, 4));                                  // :87-90
+    for (int wi = 0; wi < prm.warps; wi++) {                                // :92
+        {
+            Span sp(ctx, 1);
+            TRY(launch_warp(ctx, s, B));                                    // :84, :94-109
+        }
+        k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.active, B);   // :111-112
+        CKL(ctx);
+        const IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations);
+        TRY(run_iterations(ctx, P, B, chunk_hint));                         // :113-182
+    }
+    return TVL1_OK;
+}
+
+int check_sigma(tvl1_ctx *ctx, double sigma, int width, GaussTaps &taps)
+{
+    const int size = make_taps(sigma, taps);
+    if (size < 0) return fail_arg(ctx, "Gaussian window larger than this build supports (zfactor too small)");
+    if (size > width) {                                                     // src/operators.cpp:520-522
+        ctx->err = "GaussianSmooth: sigma too large";
+        return TVL1_ERR_SIGMA;
+    }
+    return TVL1_OK;
+}
+
+void reset_stats(tvl1_ctx *ctx) { ctx->stats = tvl1_stats{}; }
+
+int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_out)
+{
+    const Workspace &w = ctx->ws;
+    unsigned long long c[4] = { 0, 0, 0, 0 };
+    CK(cudaMemcpyAsync(c, w.counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    if (iters_out)
+        CK(cudaMemcpy2DAsync(iters_out, sizeof(int) * nstat, w.stat_iters, sizeof(int) * w.stat_stride,
+                             sizeof(int) * nstat, B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (errs_out)
+        CK(cudaMemcpy2DAsync(errs_out, sizeof(double) * nstat, w.stat_errs, sizeof(double) * w.stat_stride,
+                             sizeof(double) * nstat, B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.pixel_iterations += c[0];
+    return TVL1_OK;
+}
+
+// Dual_TVL1_optic_flow_multiscale for B <= max_batch pairs, device-resident dense inputs/outputs.
+int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, float *du1, float *du2,
+                   int nx, int ny, const tvl1_params &prm, int *iters_out, double *errs_out)
+{
+    const int ns = prm.nscales;
+    const int nstat = ns * prm.warps;
+    TRY(ensure_workspace(ctx, nx, ny, ns, prm.zfactor, B, nstat));
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+
+    // validate the blur windows first: the reference throws before producing anything
+    GaussTaps pre, zoom;
+    TRY(check_sigma(ctx, TVL1_PRESMOOTHING_SIGMA, nx, pre));
+    const double zsigma = TVL1_ZOOM_SIGMA_ZERO * std::sqrt(1.0 / (prm.zfactor * prm.zfactor) - 1.0);
+    for (int s = 1; s < ns; s++) TRY(check_sigma(ctx, zsigma, w.lv[s - 1].nx, zoom));
+
+    Span total(ctx, 2);
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 4, st));
+    k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
+    CKL(ctx);
+
+    // normalisation + pre-smoothing, src/tvl1flow.cpp:255-259
+    const size_t n = (size_t) nx * ny;
+    {
+        dim3 g((unsigned) std::min<size_t>((n + 2047) / 2048, 256), B);
+        k_minmax<<<g, 256, 0, st>>>(dI0, dI1, n, w.mm);
+        CKL(ctx);
+    }
+    TRY(launch_gauss(ctx, 1, dI0, nx, n, w.I0(0), w.lv[0].pitch, w.plane(0), nx, ny, nx, ny, pre, w.mm, B, B));
+    TRY(launch_gauss(ctx, 1, dI1, nx, n, w.I1(0), w.lv[0].pitch, w.plane(0), nx, ny, nx, ny, pre, w.mm, B, B));
+
+    // pyramid, src/tvl1flow.cpp:262-275 (zoom_out, src/zoom.cpp:41-78)
+    for (int s = 1; s < ns; s++) {
+        const Level &a = w.lv[s - 1], &c = w.lv[s];
+        if (prm.zfactor == 0.5) {
+            TRY(launch_gauss(ctx, 2, w.I0(s - 1), a.pitch, w.plane(s - 1), w.I0(s), c.pitch, w.plane(s),
+                             a.nx, a.ny, c.nx, c.ny, zoom, nullptr, B, 2 * B));
+        } else {
+            TRY(launch_gauss(ctx, 1, w.I0(s - 1), a.pitch, w.plane(s - 1), w.tmp, a.pitch, w.plane(s - 1),
+                             a.nx, a.ny, a.nx, a.ny, zoom, nullptr, B, 2 * B));
+            dim3 g(ceil_div(c.nx, 32), ceil_div(c.ny, 8), 2 * B);
+            k_resample<<<g, dim3(32, 8), 0, st>>>(w.tmp, a.pitch, w.plane(s - 1), a.nx, a.ny, w.I0(s),
+                                                  c.pitch, w.plane(s), c.nx, c.ny, prm.zfactor,
+                                                  prm.zfactor, 1.0f);
+            CKL(ctx);
+        }
+    }
+
+    // coarse-to-fine, src/tvl1flow.cpp:278-310
+    TRY(launch_zero(ctx, ns - 1, B, F_U1, 2));
+    int chunk_hint = 16;
+    for (int s = ns - 1; s >= 0; s--) {
+        TRY(run_level(ctx, s, B, prm, (ns - 1 - s) * prm.warps, chunk_hint));
+        if (!s) break;
+        const Level &c = w.lv[s], &f = w.lv[s - 1];
+        dim3 g(ceil_div(f.nx, 32), ceil_div(f.ny, 8), 2 * B);
+        k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                                  c, f, (double) f.nx / c.nx, (double) f.ny / c.ny,
+                                                  (float) (1.0 / prm.zfactor));
+        CKL(ctx);
+        k_flip_cur<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, B);
+        CKL(ctx);
+        chunk_hint = std::max(chunk_hint, 8);
+    }
+    {
+        dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
+        k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                                 w.lv[0], du1, du2);
+        CKL(ctx);
+    }
+    total.end();
+    TRY(fetch_stats(ctx, B, nstat, iters_out, errs_out));
+    return TVL1_OK;
+}
+
+// Dual_TVL1_optic_flow (one level, no normalisation / blur), device-resident dense buffers.
+int run_single_scale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, float *du1, float *du2,
+                     int nx, int ny, const tvl1_params &prm, int *iters_out, double *errs_out)
+{
+    TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, B, prm.warps));
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    Span total(ctx, 2);
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 4, st));
+    k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
+    CKL(ctx);
+    dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
+    k_pack<<<g, dim3(32, 8), 0, st>>>(dI0, w.I0(0), nx, ny, w.lv[0].pitch, w.plane(0));
+    CKL(ctx);
+    k_pack<<<g, dim3(32, 8), 0, st>>>(dI1, w.I1(0), nx, ny, w.lv[0].pitch, w.plane(0));
+    CKL(ctx);
+    k_import_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                             w.lv[0], du1, du2);
+    CKL(ctx);
+    int chunk_hint = 16;
+    TRY(run_level(ctx, 0, B, prm, 0, chunk_hint));
+    k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                             w.lv[0], du1, du2);
+    CKL(ctx);
+    total.end();
+    TRY(fetch_stats(ctx, B, prm.warps, iters_out, errs_out));
+    return TVL1_OK;
+}
+
+int ensure_stage(tvl1_ctx *ctx, size_t bytes_each, bool need_f32)
+{
+    if (ctx->stage_bytes < bytes_each) {
+        for (int i = 0; i < 2; i++) { cudaFree(ctx->stage_in[i]); cudaFree(ctx->stage_out[i]); }
+        ctx->stage_bytes = 0;
+        for (int i = 0; i < 2; i++) {
+            CK(cudaMalloc(&ctx->stage_in[i], bytes_each));
+            CK(cudaMalloc(&ctx->stage_out[i], bytes_each));
+        }
+        ctx->stage_bytes = bytes_each;
+    }
+    if (need_f32 && ctx->stage_f32_bytes < bytes_each / 2) {
+        for (int i = 0; i < 4; i++) cudaFree(ctx->stage_f32[i]);
+        ctx->stage_f32_bytes = 0;
+        for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->stage_f32[i], bytes_each / 2));
+        ctx->stage_f32_bytes = bytes_each / 2;
+    }
+    return TVL1_OK;
+}
+
+int check_common(tvl1_ctx *ctx, const void *a, const void *b, const void *c, const void *d, int nx,
+                 int ny, const tvl1_params *prm, bool multiscale)
+{
+    if (!ctx) return TVL1_ERR_ARG;
+    if (!a || !b || !c || !d || !prm) return fail_arg(ctx, "null pointer argument");
+    if (nx < 1 || ny < 1) return fail_arg(ctx, "image size must be positive");
+    if (prm->warps < 1) return fail_arg(ctx, "warps must be >= 1");
+    if (multiscale && prm->nscales < 1) return fail_arg(ctx, "nscales must be >= 1");
+    if (multiscale && !(prm->zfactor > 0.0 && prm->zfactor < 1.0) && prm->nscales > 1)
+        return fail_arg(ctx, "zfactor must be in (0,1)");
+    if (!(prm->theta != 0.0)) return fail_arg(ctx, "theta must be non-zero");
+    CK(cudaSetDevice(ctx->device));
+    return TVL1_OK;
+}
+
+// host-buffer driver shared by the f32/f64, multiscale/single-scale entry points
+template <typename T>
+int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2, int nx, int ny,
+               const tvl1_params *prm, int *iters_out, double *errs_out, bool multiscale)
+{
+    TRY(check_common(ctx, I0, I1, u1, u2, nx, ny, prm, multiscale));
+    if (npairs < 1) return fail_arg(ctx, "npairs must be >= 1");
+    reset_stats(ctx);
+    const bool f64 = sizeof(T) == 8;
+    const size_t n = (size_t) nx * ny;
+    const int Bmax = std::min(npairs, ctx->max_batch);
+    TRY(ensure_stage(ctx, (size_t) Bmax * n * sizeof(T), f64));
+    const int nstat = (multiscale ? prm->nscales : 1) * prm->warps;
+    cudaStream_t st = ctx->stream;
+    for (int first = 0; first < npairs; first += Bmax) {
+        const int B = std::min(Bmax, npairs - first);
+        const size_t cnt = (size_t) B * n, off = (size_t) first * n;
+        CK(cudaMemcpyAsync(ctx->stage_in[0], I0 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->stage_in[1], I1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+        float *d0, *d1, *o0, *o1;
+        if (f64) {
+            d0 = ctx->stage_f32[0]; d1 = ctx->stage_f32[1]; o0 = ctx->stage_f32[2]; o1 = ctx->stage_f32[3];
+            const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
+            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[0], d0, cnt);
+            CKL(ctx);
+            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[1], d1, cnt);
+            CKL(ctx);
+        } else {
+            d0 = (float *) ctx->stage_in[0]; d1 = (float *) ctx->stage_in[1];
+            o0 = (float *) ctx->stage_out[0]; o1 = (float *) ctx->stage_out[1];
+        }
+        if (!multiscale) {   // u1,u2 are in/out: the initial flow is used (src/tvl1flow.cpp:94)
+            CK(cudaMemcpyAsync(ctx->stage_out[0], u1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->stage_out[1], u2 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+            if (f64) {
+                const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
+                k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[0], o0, cnt);
+                CKL(ctx);
+                k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[1], o1, cnt);
+                CKL(ctx);
+            }
+        }
+        int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
+        double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
+        if (multiscale) TRY(run_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
+        else TRY(run_single_scale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
+        if (f64) {
+            const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
+            k_f32_to_f64<<<g, 256, 0, st>>>(o0, (double *) ctx->stage_out[0], cnt);
+            CKL(ctx);
+            k_f32_to_f64<<<g, 256, 0, st>>>(o1, (double *) ctx->stage_out[1], cnt);
+            CKL(ctx);
+        }
+        CK(cudaMemcpyAsync(u1 + off, ctx->stage_out[0], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(u2 + off, ctx->stage_out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    resolve_events(ctx);
+    return TVL1_OK;
+}
+
+// ---- RAII device scratch for the per-kernel hooks -----------------------------------------------
+struct Dev {
+    std::vector<void *> ptrs;
+    ~Dev() { for (void *p : ptrs) cudaFree(p); }
+    float *alloc(size_t floats)
+    {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(floats, 4) * sizeof(float)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, std::max<size_t>(floats, 4) * sizeof(float));
+        ptrs.push_back(p);
+        return (float *) p;
+    }
+};
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int tvl1_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int tvl1_create(int device, tvl1_ctx **out)
+{
+    if (!out) return TVL1_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (this library has no CPU fallback)";
+        return TVL1_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return TVL1_ERR_ARG; }
+    tvl1_ctx *ctx = new tvl1_ctx();
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMallocHost(&ctx->h_active, sizeof(int))) != cudaSuccess) {
+        g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        delete ctx;
+        return TVL1_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return TVL1_OK;
+}
+
+void tvl1_destroy(tvl1_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_workspace(ctx->ws);
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->stage_in[i]); cudaFree(ctx->stage_out[i]); }
+    for (int i = 0; i < 4; i++) cudaFree(ctx->stage_f32[i]);
+    resolve_events(ctx);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->h_active) cudaFreeHost(ctx->h_active);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *tvl1_last_error(const tvl1_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int tvl1_set_profiling(tvl1_ctx *ctx, int on)
+{
+    if (!ctx) return TVL1_ERR_ARG;
+    ctx->profiling = on != 0;
+    return TVL1_OK;
+}
+
+int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs)
+{
+    if (!ctx || pairs < 1) return TVL1_ERR_ARG;
+    ctx->max_batch = pairs;
+    return TVL1_OK;
+}
+
+int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out)
+{
+    if (!ctx || !out) return TVL1_ERR_ARG;
+    *out = ctx->stats;
+    return TVL1_OK;
+}
+
+void tvl1_default_params(tvl1_params *p)
+{
+    if (!p) return;
+    p->tau = 0.25; p->lambda = 0.15; p->theta = 0.3; p->nscales = 5; p->zfactor = 0.5;
+    p->warps = 5; p->epsilon = 0.01;
+}
+
+void tvl1_zoom_size(int nx, int ny, int *nxx, int *nyy, double factor)
+{
+    // src/zoom.cpp:22-34
+    *nxx = (int) (nx * factor + 0.5);
+    *nyy = (int) (ny * factor + 0.5);
+}
+
+int tvl1_solve_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2, int nx,
+                   int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    return solve_host<float>(ctx, 1, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int tvl1_solve_f64(tvl1_ctx *ctx, const double *I0, const double *I1, double *u1, double *u2, int nx,
+                   int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    return solve_host<double>(ctx, 1, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int tvl1_solve_batch_f32(tvl1_ctx *ctx, int npairs, const float *I0, const float *I1, float *u1,
+                         float *u2, int nx, int ny, const tvl1_params *prm, int *iters_out,
+                         double *errs_out)
+{
+    return solve_host<float>(ctx, npairs, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int tvl1_solve_batch_f64(tvl1_ctx *ctx, int npairs, const double *I0, const double *I1, double *u1,
+                         double *u2, int nx, int ny, const tvl1_params *prm, int *iters_out,
+                         double *errs_out)
+{
+    return solve_host<double>(ctx, npairs, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const float *dI1,
+                             float *du1, float *du2, int nx, int ny, const tvl1_params *prm,
+                             int *iters_out, double *errs_out)
+{
+    TRY(check_common(ctx, dI0, dI1, du1, du2, nx, ny, prm, true));
+    if (npairs < 1) return fail_arg(ctx, "npairs must be >= 1");
+    reset_stats(ctx);
+    const size_t n = (size_t) nx * ny;
+    const int nstat = prm->nscales * prm->warps;
+    const int Bmax = std::min(npairs, ctx->max_batch);
+    for (int first = 0; first < npairs; first += Bmax) {
+        const int B = std::min(Bmax, npairs - first);
+        const size_t off = (size_t) first * n;
+        TRY(run_multiscale(ctx, B, dI0 + off, dI1 + off, du1 + off, du2 + off, nx, ny, *prm,
+                           iters_out ? iters_out + (size_t) first * nstat : nullptr,
+                           errs_out ? errs_out + (size_t) first * nstat : nullptr));
+    }
+    resolve_events(ctx);
+    return TVL1_OK;
+}
+
+int tvl1_single_scale_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2,
+                          int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    return solve_host<float>(ctx, 1, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, false);
+}
+
+int tvl1_single_scale_f64(tvl1_ctx *ctx, const double *I0, const double *I1, double *u1, double *u2,
+                          int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    return solve_host<double>(ctx, 1, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, false);
+}
+
+// ---- hooks --------------------------------------------------------------------------------------
+
+int tvl1_normalize_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *I0n, float *I1n,
+                       int nx, int ny)
+{
+    if (!ctx || !I0 || !I1 || !I0n || !I1n || nx < 1 || ny < 1) return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    Dev d;
+    const size_t n = (size_t) nx * ny;
+    float *a = d.alloc(n), *b = d.alloc(n), *oa = d.alloc(n), *ob = d.alloc(n);
+    unsigned int *mm = (unsigned int *) d.alloc(4);
+    PairCtl *ctl = (PairCtl *) d.alloc(sizeof(PairCtl));
+    if (!a || !b || !oa || !ob || !mm || !ctl) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(a, I0, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b, I1, n * 4, cudaMemcpyHostToDevice, st));
+    k_init_ctl<<<1, 32, 0, st>>>(ctl, mm, 1);
+    CKL(ctx);
+    k_minmax<<<dim3(64, 1), 256, 0, st>>>(a, b, n, mm);
+    CKL(ctx);
+    GaussTaps id{};
+    id.size = 1;
+    id.w[0] = 1.0f;   // identity blur: the normalisation is fused into the blur kernel's load
+    TRY(launch_gauss(ctx, 1, a, nx, n, oa, nx, n, nx, ny, nx, ny, id, mm, 1, 1));
+    TRY(launch_gauss(ctx, 1, b, nx, n, ob, nx, n, nx, ny, nx, ny, id, mm, 1, 1));
+    CK(cudaMemcpyAsync(I0n, oa, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(I1n, ob, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_gaussian_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, double sigma)
+{
+    if (!ctx || !I || !out || nx < 1 || ny < 1) return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    GaussTaps taps;
+    TRY(check_sigma(ctx, sigma, nx, taps));
+    Dev d;
+    const size_t n = (size_t) nx * ny;
+    float *a = d.alloc(n), *o = d.alloc(n);
+    if (!a || !o) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(a, I, n * 4, cudaMemcpyHostToDevice, st));
+    TRY(launch_gauss(ctx, 1, a, nx, n, o, nx, n, nx, ny, nx, ny, taps, nullptr, 1, 1));
+    CK(cudaMemcpyAsync(out, o, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_zoom_out_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, double factor)
+{
+    if (!ctx || !I || !out || nx < 1 || ny < 1 || !(factor > 0.0 && factor < 1.0))
+        return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int nxx, nyy;
+    tvl1_zoom_size(nx, ny, &nxx, &nyy, factor);
+    if (nxx < 1 || nyy < 1) return fail_arg(ctx, "zoomed image is empty");
+    GaussTaps taps;
+    TRY(check_sigma(ctx, TVL1_ZOOM_SIGMA_ZERO * std::sqrt(1.0 / (factor * factor) - 1.0), nx, taps));
+    Dev d;
+    const size_t n = (size_t) nx * ny, m = (size_t) nxx * nyy;
+    float *a = d.alloc(n), *t = d.alloc(n), *o = d.alloc(m);
+    if (!a || !t || !o) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(a, I, n * 4, cudaMemcpyHostToDevice, st));
+    if (factor == 0.5) {
+        TRY(launch_gauss(ctx, 2, a, nx, n, o, nxx, m, nx, ny, nxx, nyy, taps, nullptr, 1, 1));
+    } else {
+        TRY(launch_gauss(ctx, 1, a, nx, n, t, nx, n, nx, ny, nx, ny, taps, nullptr, 1, 1));
+        dim3 g(ceil_div(nxx, 32), ceil_div(nyy, 8), 1);
+        k_resample<<<g, dim3(32, 8), 0, st>>>(t, nx, n, nx, ny, o, nxx, m, nxx, nyy, factor, factor, 1.0f);
+        CKL(ctx);
+    }
+    CK(cudaMemcpyAsync(out, o, m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_zoom_in_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, int nxx, int nyy,
+                     double scale)
+{
+    if (!ctx || !I || !out || nx < 1 || ny < 1 || nxx < 1 || nyy < 1) return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    Dev d;
+    const size_t n = (size_t) nx * ny, m = (size_t) nxx * nyy;
+    float *a = d.alloc(n), *o = d.alloc(m);
+    if (!a || !o) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(a, I, n * 4, cudaMemcpyHostToDevice, st));
+    dim3 g(ceil_div(nxx, 32), ceil_div(nyy, 8), 1);
+    k_resample<<<g, dim3(32, 8), 0, st>>>(a, nx, n, nx, ny, o, nxx, m, nxx, nyy, (double) nxx / nx,
+                                          (double) nyy / ny, (float) scale);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(out, o, m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_warp_f32(tvl1_ctx *ctx, const float *I0, const float *I1, const float *u1, const float *u2,
+                  int nx, int ny, float *I1wx, float *I1wy, float *rho_c, float *grad)
+{
+    if (!ctx || !I0 || !I1 || !u1 || !u2 || !I1wx || !I1wy || !rho_c || !grad || nx < 1 || ny < 1)
+        return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1));
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t) nx * ny;
+    Dev d;
+    float *buf = d.alloc(4 * n);
+    if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    const float *src[4] = { I0, I1, u1, u2 };
+    for (int k = 0; k < 4; k++) CK(cudaMemcpyAsync(buf + k * n, src[k], n * 4, cudaMemcpyHostToDevice, st));
+    k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
+    CKL(ctx);
+    dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
+    k_pack<<<g, dim3(32, 8), 0, st>>>(buf, w.I0(0), nx, ny, w.lv[0].pitch, w.plane(0));
+    CKL(ctx);
+    k_pack<<<g, dim3(32, 8), 0, st>>>(buf + n, w.I1(0), nx, ny, w.lv[0].pitch, w.plane(0));
+    CKL(ctx);
+    k_import_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                             w.lv[0], buf + 2 * n, buf + 3 * n);
+    CKL(ctx);
+    TRY(launch_warp(ctx, 0, 1));
+    float *outs[4] = { I1wx, I1wy, rho_c, grad };
+    const int which[4] = { C_IX, C_IY, C_RHO, C_GRAD };
+    for (int k = 0; k < 4; k++) {
+        k_unpack<<<g, dim3(32, 8), 0, st>>>(w.consts + (size_t) which[k] * w.field_stride, buf + k * n,
+                                            nx, ny, w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+        CK(cudaMemcpyAsync(outs[k], buf + k * n, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12, float *p21,
+                     float *p22, const float *rho_c, const float *I1wx, const float *I1wy,
+                     const float *grad, int nx, int ny, double tau, double lambda, double theta,
+                     int iters, double *errs_out)
+{
+    if (!ctx || !u1 || !u2 || !p11 || !p12 || !p21 || !p22 || !rho_c || !I1wx || !I1wy || !grad ||
+        nx < 1 || ny < 1 || iters < 0)
+        return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1));
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t) nx * ny;
+    Dev d;
+    float *buf = d.alloc(n);
+    if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
+    CKL(ctx);
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 4, st));
+    dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
+    float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
+    for (int f = 0; f < 6; f++) {
+        CK(cudaMemcpyAsync(buf, st_host[f], n * 4, cudaMemcpyHostToDevice, st));
+        k_pack<<<g, dim3(32, 8), 0, st>>>(buf, w.state + (size_t) f * w.field_stride, nx, ny,
+                                          w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+    }
+    const float *c_host[4] = { I1wx, I1wy, rho_c, grad };   // order of enum Const
+    for (int c = 0; c < 4; c++) {
+        CK(cudaMemcpyAsync(buf, c_host[c], n * 4, cudaMemcpyHostToDevice, st));
+        k_pack<<<g, dim3(32, 8), 0, st>>>(buf, w.consts + (size_t) c * w.field_stride, nx, ny,
+                                          w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+    }
+    tvl1_params prm;
+    tvl1_default_params(&prm);
+    prm.tau = tau; prm.lambda = lambda; prm.theta = theta; prm.epsilon = 0.0;
+    int cur = 0;
+    for (int k = 0; k < iters; k++) {
+        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.active, 1);
+        CKL(ctx);
+        const IterParams P = iter_params(ctx, w.lv[0], prm, 0, 1);   // max_iter 1: record and stop
+        TRY(launch_iterate(ctx, P, 1));
+        cur ^= 1;
+        if (errs_out) CK(cudaMemcpyAsync(errs_out + k, w.stat_errs, sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    for (int f = 0; f < 6; f++) {
+        k_unpack<<<g, dim3(32, 8), 0, st>>>(w.state + (size_t) cur * w.set_stride + (size_t) f * w.field_stride,
+                                            buf, nx, ny, w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+        CK(cudaMemcpyAsync(st_host[f], buf, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_bench_iterate(tvl1_ctx *ctx, int npairs, int nx, int ny, int launches, double *ms_out)
+{
+    if (!ctx || npairs < 1 || nx < 1 || ny < 1 || launches < 1 || !ms_out) return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, npairs, 1));
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    // deterministic, smooth-ish content: a previous solve's leftovers are as good as anything, but
+    // start from a defined state (flow 0, dual 0, constants 0 => every pixel takes the grad<eps branch)
+    k_init_ctl<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.mm, npairs);
+    CKL(ctx);
+    k_begin_warp<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.active, npairs);
+    CKL(ctx);
+    tvl1_params prm;
+    tvl1_default_params(&prm);
+    prm.epsilon = 0.0;
+    IterParams P = iter_params(ctx, w.lv[0], prm, 0, 1 << 30);
+    P.eps2 = -1.0;   // never stop: every launch does the full work
+    for (int i = 0; i < 3; i++) TRY(launch_iterate(ctx, P, npairs));
+    cudaEvent_t a = take_event(ctx), b = take_event(ctx);
+    CK(cudaEventRecord(a, st));
+    for (int i = 0; i < launches; i++) TRY(launch_iterate(ctx, P, npairs));
+    CK(cudaEventRecord(b, st));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    ctx->ev_pool.push_back(a);
+    ctx->ev_pool.push_back(b);
+    *ms_out = ms;
+    return TVL1_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,142 @@
+// Drop-in replacements for the reference's TV-L1 library entry points, with the reference's exact
+// C++ signatures (and therefore mangled names; the reference cannot use extern "C" because
+// src/tvl1occflow.h:63-79,111-129 overloads the same names):
+//
+//   void Dual_TVL1_optic_flow_multiscale(ofpix_t*, ofpix_t*, ofpix_t*, ofpix_t*, const int, const int,
+//        const double, const double, const double, const int, const double, const int, const double,
+//        const bool)                                                  src/tvl1flow.h:56-70
+//   void Dual_TVL1_optic_flow(ofpix_t*, ofpix_t*, ofpix_t*, ofpix_t*, const int, const int,
+//        const double, const double, const double, const int, const double, const bool)
+//                                                                     src/tvl1flow.h:36-48
+//
+// ofpix_t is double as shipped (src/of.h:4-10): _Z31Dual_TVL1_optic_flow_multiscalePdS_S_S_iidddididb
+// and _Z20Dual_TVL1_optic_flowPdS_S_S_iidddidb.  The float overloads below cover a reference built
+// with OFPIX_DOUBLE commented out.  tvl1flow_main.cpp links against this object unchanged.
+//
+// Host C++ only: everything GPU goes through the C ABI of include/tvl1_b200.h.
+// Behaviour kept from the reference: void return, failures surface as exceptions
+// (std::runtime_error("GaussianSmooth: sigma too large") from src/operators.cpp:520-522), verbose mode
+// prints "Scale %d: %dx%d" (src/tvl1flow.cpp:285) and "Warping: %d, Iterations: %d, Error: %f"
+// (:185-187) on stderr; I0/I1 are not modified; u1/u2 are fully overwritten (multiscale) or
+// used as the initial flow (single level).
+#include "../../include/tvl1_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct ThreadCtx {
+    tvl1_ctx *ctx = nullptr;
+    ~ThreadCtx() { tvl1_destroy(ctx); }
+};
+
+// one context per calling host thread: the reference is re-entrant, and batch sharding drives one
+// host thread per GPU (TVL1_DEVICE selects the device for the calling thread's first call).
+tvl1_ctx *thread_ctx()
+{
+    static thread_local ThreadCtx tc;
+    if (!tc.ctx) {
+        int dev = 0;
+        if (const char *e = std::getenv("TVL1_DEVICE")) dev = std::atoi(e);
+        if (tvl1_create(dev, &tc.ctx) != TVL1_OK)
+            throw std::runtime_error(std::string("tvl1_b200: ") + tvl1_last_error(nullptr));
+    }
+    return tc.ctx;
+}
+
+[[noreturn]] void raise(tvl1_ctx *ctx, int rc)
+{
+    if (rc == TVL1_ERR_SIGMA) throw std::runtime_error("GaussianSmooth: sigma too large");
+    throw std::runtime_error(std::string("tvl1_b200: ") + tvl1_last_error(ctx));
+}
+
+void print_level(int warps, const int *iters, const double *errs)
+{
+    for (int w = 0; w < warps; w++)
+        fprintf(stderr, "Warping: %d, Iterations: %d, Error: %f\n", w, iters[w], errs[w]);
+}
+
+template <typename T>
+void multiscale(T *I0, T *I1, T *u1, T *u2, int nx, int ny, double tau, double lambda, double theta,
+                int nscales, double zfactor, int warps, double epsilon, bool verbose)
+{
+    tvl1_ctx *ctx = thread_ctx();
+    tvl1_params p{ tau, lambda, theta, nscales, zfactor, warps, epsilon };
+    std::vector<int> iters((size_t) nscales * warps);
+    std::vector<double> errs((size_t) nscales * warps);
+    int rc;
+    if (sizeof(T) == 8)
+        rc = tvl1_solve_f64(ctx, (const double *) I0, (const double *) I1, (double *) u1, (double *) u2,
+                            nx, ny, &p, iters.data(), errs.data());
+    else
+        rc = tvl1_solve_f32(ctx, (const float *) I0, (const float *) I1, (float *) u1, (float *) u2,
+                            nx, ny, &p, iters.data(), errs.data());
+    if (rc != TVL1_OK) raise(ctx, rc);
+    if (verbose) {
+        std::vector<int> sx(nscales), sy(nscales);
+        sx[0] = nx; sy[0] = ny;
+        for (int s = 1; s < nscales; s++) tvl1_zoom_size(sx[s - 1], sy[s - 1], &sx[s], &sy[s], zfactor);
+        for (int s = nscales - 1; s >= 0; s--) {
+            fprintf(stderr, "Scale %d: %dx%d\n", s, sx[s], sy[s]);
+            const size_t k = (size_t) (nscales - 1 - s) * warps;
+            print_level(warps, iters.data() + k, errs.data() + k);
+        }
+    }
+}
+
+template <typename T>
+void single_scale(T *I0, T *I1, T *u1, T *u2, int nx, int ny, double tau, double lambda, double theta,
+                  int warps, double epsilon, bool verbose)
+{
+    tvl1_ctx *ctx = thread_ctx();
+    tvl1_params p{ tau, lambda, theta, 1, 0.5, warps, epsilon };
+    std::vector<int> iters(warps);
+    std::vector<double> errs(warps);
+    int rc;
+    if (sizeof(T) == 8)
+        rc = tvl1_single_scale_f64(ctx, (const double *) I0, (const double *) I1, (double *) u1,
+                                   (double *) u2, nx, ny, &p, iters.data(), errs.data());
+    else
+        rc = tvl1_single_scale_f32(ctx, (const float *) I0, (const float *) I1, (float *) u1,
+                                   (float *) u2, nx, ny, &p, iters.data(), errs.data());
+    if (rc != TVL1_OK) raise(ctx, rc);
+    if (verbose) print_level(warps, iters.data(), errs.data());
+}
+
+} // namespace
+
+// ---- ofpix_t = double (reference as shipped) ----------------------------------------------------
+void Dual_TVL1_optic_flow_multiscale(double *I0, double *I1, double *u1, double *u2, const int nxx,
+                                     const int nyy, const double tau, const double lambda,
+                                     const double theta, const int nscales, const double zfactor,
+                                     const int warps, const double epsilon, const bool verbose)
+{
+    multiscale<double>(I0, I1, u1, u2, nxx, nyy, tau, lambda, theta, nscales, zfactor, warps, epsilon, verbose);
+}
+
+void Dual_TVL1_optic_flow(double *I0, double *I1, double *u1, double *u2, const int nx, const int ny,
+                          const double tau, const double lambda, const double theta, const int warps,
+                          const double epsilon, const bool verbose)
+{
+    single_scale<double>(I0, I1, u1, u2, nx, ny, tau, lambda, theta, warps, epsilon, verbose);
+}
+
+// ---- ofpix_t = float (src/of.h with OFPIX_DOUBLE commented out) ---------------------------------
+void Dual_TVL1_optic_flow_multiscale(float *I0, float *I1, float *u1, float *u2, const int nxx,
+                                     const int nyy, const double tau, const double lambda,
+                                     const double theta, const int nscales, const double zfactor,
+                                     const int warps, const double epsilon, const bool verbose)
+{
+    multiscale<float>(I0, I1, u1, u2, nxx, nyy, tau, lambda, theta, nscales, zfactor, warps, epsilon, verbose);
+}
+
+void Dual_TVL1_optic_flow(float *I0, float *I1, float *u1, float *u2, const int nx, const int ny,
+                          const double tau, const double lambda, const double theta, const int warps,
+                          const double epsilon, const bool verbose)
+{
+    single_scale<float>(I0, I1, u1, u2, nx, ny, tau, lambda, theta, warps, epsilon, verbose);
+}

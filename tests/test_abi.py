@@ -1,0 +1,103 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/tvl1_b200.h declares plus the reference's mangled C++ entry points, and fails loudly
+(no CPU fallback) when no CUDA device is present.  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import optical_flow_1_b200 as pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tvl1_b200.h")
+
+# src/tvl1flow.h:36-70 with ofpix_t = double (src/of.h:4-10), and the float variant
+MANGLED = [
+    "_Z31Dual_TVL1_optic_flow_multiscalePdS_S_S_iidddididb",
+    "_Z20Dual_TVL1_optic_flowPdS_S_S_iidddidb",
+    "_Z31Dual_TVL1_optic_flow_multiscalePfS_S_S_iidddididb",
+    "_Z20Dual_TVL1_optic_flowPfS_S_S_iidddidb",
+]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(pkg.library_path()):
+        pkg.build_library()
+    return C.CDLL(pkg.library_path())
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tvl1_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ("tvl1_create", "tvl1_destroy", "tvl1_solve_f32", "tvl1_solve_f64",
+                 "tvl1_solve_batch_f32", "tvl1_solve_batch_f64", "tvl1_solve_batch_dev_f32",
+                 "tvl1_single_scale_f32", "tvl1_single_scale_f64", "tvl1_warp_f32",
+                 "tvl1_iterate_f32", "tvl1_gaussian_f32", "tvl1_zoom_out_f32", "tvl1_zoom_in_f32"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), "missing export: " + name
+
+
+def test_library_exports_reference_cxx_symbols(lib):
+    for name in MANGLED:
+        assert hasattr(lib, name), "missing drop-in symbol: " + name
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(HEADER).read()
+    assert "torch" not in src.lower() and "at::" not in src and "c10::" not in src
+
+
+def test_zoom_size_matches_oracle(lib, oracle_f64):
+    a, b = C.c_int(), C.c_int()
+    for nx, ny, f in [(640, 480, 0.5), (1024, 436, 0.5), (109, 55, 0.5), (61, 47, 0.7), (1920, 1080, 0.3)]:
+        lib.tvl1_zoom_size(C.c_int(nx), C.c_int(ny), C.byref(a), C.byref(b), C.c_double(f))
+        assert (a.value, b.value) == oracle_f64.zoom_size(nx, ny, f)
+
+
+def test_default_params(lib):
+    p = pkg.Params()
+    lib.tvl1_default_params(C.byref(p))
+    # tvl1flow_main.cpp:24-33
+    assert (p.tau, p.lam, p.theta, p.zfactor, p.warps, p.epsilon) == (0.25, 0.15, 0.3, 0.5, 5, 0.01)
+
+
+def test_clamp_nscales_is_the_cli_rule():
+    # tvl1flow_main.cpp:185-188
+    assert pkg.clamp_nscales(640, 480, 100, 0.5) == 6
+    assert pkg.clamp_nscales(1920, 1080, 100, 0.5) == 8
+    assert pkg.clamp_nscales(1920, 1080, 5, 0.5) == 5
+    assert pkg.clamp_nscales(64, 48, 100, 0.5) == 3
+
+
+def test_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.TVL1Error) as e:
+        pkg.TVL1(device=0)
+    assert e.value.code == 4 and "no CPU fallback" in str(e.value)
+
+
+def test_product_path_never_touches_the_oracle():
+    """Nothing under the package directory (or the alias) may import, link or execute oracle/."""
+    for base in ("optical-flow-1_b200", "optical_flow_1_b200"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+    out = subprocess.run(["ldd", pkg.library_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libof_ref" not in out

@@ -1,0 +1,280 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs, against the committed golden vectors of the unmodified reference, and -- at
+BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star; the CUDA path computes in fp32, the reference in fp64):
+  flow: mean |d| <= 1e-3 px and max |d| <= 1e-2 px, iteration counts identical per (level, warp).
+Per-kernel hooks are compared with fp32-rounding-sized bounds stated at each test.
+"""
+import numpy as np
+import pytest
+
+import _cases
+import optical_flow_1_b200 as pkg
+from oracle.loader import CpuTvl1, available
+
+pytestmark = pytest.mark.gpu
+
+MEAN_TOL = 1e-3
+MAX_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    g = pkg.TVL1(device=0)
+    yield g
+    g.close()
+
+
+def flow_diff(u1, u2, r1, r2):
+    d = np.concatenate([np.abs(u1.astype(np.float64) - r1).ravel(),
+                        np.abs(u2.astype(np.float64) - r2).ravel()])
+    return d.mean(), d.max()
+
+
+def assert_flow_close(u1, u2, r1, r2, what=""):
+    mean, mx = flow_diff(u1, u2, r1, r2)
+    assert mean <= MEAN_TOL and mx <= MAX_TOL, "%s mean|d|=%g max|d|=%g" % (what, mean, mx)
+
+
+# ---- per-kernel hooks vs the oracle (fp64 port) -------------------------------------------------
+
+def test_normalize(gpu, oracle_f64):
+    x = _cases.func_inputs()
+    a0, a1 = gpu.image_normalization_2(x["I"], x["J"])
+    r0, r1 = oracle_f64.normalize(x["I"].astype(np.float32), x["J"].astype(np.float32))
+    # values in [0,255]: a few fp32 ulps (255 * 6e-8 ~ 1.5e-5)
+    assert np.abs(a0 - r0).max() < 1e-4 and np.abs(a1 - r1).max() < 1e-4
+    # constant images are copied unchanged (src/utils.cpp:319-325)
+    c = np.full((9, 12), 7.25, np.float32)
+    b0, b1 = gpu.image_normalization_2(c, c)
+    assert np.array_equal(b0, c) and np.array_equal(b1, c)
+
+
+@pytest.mark.parametrize("sigma", [_cases.SIGMA_PRE, _cases.SIGMA_ZOOM_HALF, 1.7])
+@pytest.mark.parametrize("shape", [_cases.FUNC_SHAPE, (70, 131), (9, 7)])
+def test_gaussian(gpu, oracle_f64, sigma, shape):
+    I = np.random.RandomState(3).uniform(0, 255, shape).astype(np.float32)
+    if (int)(5 * sigma) + 1 > shape[1]:
+        with pytest.raises(pkg.TVL1Error) as e:
+            gpu.gaussian(I, sigma)
+        assert e.value.code == 2     # the reference throws here (src/operators.cpp:520-522)
+        with pytest.raises(RuntimeError):
+            oracle_f64.gaussian(I, sigma)
+        return
+    if (int)(5 * sigma) + 1 > shape[0]:
+        pytest.skip("window taller than the image: undefined behaviour in the reference")
+    got = gpu.gaussian(I, sigma)
+    ref = oracle_f64.gaussian(I, sigma)
+    assert np.abs(got - ref).max() < 2e-4     # ~20 fp32 roundings of values <= 255
+
+
+@pytest.mark.parametrize("factor", [0.5, 0.7, 0.3])
+@pytest.mark.parametrize("shape", [_cases.FUNC_SHAPE, (109, 218)])
+def test_zoom_out(gpu, oracle_f64, factor, shape):
+    I = np.random.RandomState(4).uniform(0, 255, shape).astype(np.float32)
+    got = gpu.zoom_out(I, factor)
+    ref = oracle_f64.zoom_out(I, factor)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 5e-4
+
+
+def test_zoom_in(gpu, oracle_f64):
+    I = np.random.RandomState(5).uniform(-8, 8, (27, 35)).astype(np.float32)
+    for (nxx, nyy) in [(70, 54), (71, 53), (69, 55), (50, 38)]:
+        got = gpu.zoom_in(I, nxx, nyy, scale=2.0)
+        ref = oracle_f64.zoom_in(I, nxx, nyy) * 2.0
+        assert np.abs(got - ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("shape", [_cases.FUNC_SHAPE, (64, 128), (50, 77)])
+def test_warp_precompute(gpu, oracle_f64, shape):
+    rs = np.random.RandomState(6)
+    ny, nx = shape
+    yy, xx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    I1 = (128 + 60 * np.sin(0.21 * xx + 0.13 * yy) + 40 * np.cos(0.17 * yy - 0.05 * xx)).astype(np.float32)
+    I0 = (I1 + rs.uniform(-5, 5, shape)).astype(np.float32)
+    # flows that cross the validity box on every side, fractional parts spread over [0,1)
+    u1 = rs.uniform(-6, 6, shape).astype(np.float32)
+    u2 = rs.uniform(-6, 6, shape).astype(np.float32)
+    u1[0, :] = 0.0
+    u2[:, 0] = 0.0
+    got = gpu.warp_precompute(I0, I1, u1, u2)
+    ref = oracle_f64.warp_precompute(I0, I1, u1, u2)
+    # validity box identical: exactly zero outside (src/bicubic_interpolation.cpp:214-215)
+    uu, vv = xx + u1.astype(np.float64), yy + u2.astype(np.float64)
+    inside = (uu >= 1) & (uu < nx - 2) & (vv >= 1) & (vv < ny - 2)
+    assert np.all(got["I1wx"][~inside] == 0) and np.all(got["I1wy"][~inside] == 0)
+    assert np.all(got["grad"][~inside] == 0)
+    assert np.array_equal(got["rho_c"][~inside], -I0[~inside])
+    # inside: bicubic of values ~255 with fp32 weights; rho_c multiplies by |u| <= 6
+    assert np.abs(got["I1wx"] - ref["I1wx"]).max() < 2e-4
+    assert np.abs(got["I1wy"] - ref["I1wy"]).max() < 2e-4
+    assert np.abs(got["rho_c"] - ref["rho_c"]).max() < 2e-3
+    assert np.allclose(got["grad"], ref["grad"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [_cases.FUNC_SHAPE, (40, 128), (33, 250), (8, 124), (9, 125)])
+@pytest.mark.parametrize("iters", [1, 3])
+def test_iterate(gpu, oracle_f64, shape, iters):
+    """The fused iteration kernel against src/tvl1flow.cpp:114-181 on arbitrary state (random dual
+    variables exercise the boundary rules of divergence / forward_gradient)."""
+    rs = np.random.RandomState(8)
+    f = lambda lo, hi: rs.uniform(lo, hi, shape).astype(np.float32)
+    u1, u2 = f(-3, 3), f(-3, 3)
+    p = [f(-1, 1) for _ in range(4)]
+    ix, iy = f(-20, 20), f(-20, 20)
+    ix[rs.uniform(size=shape) < 0.1] = 0.0
+    iy[ix == 0] = 0.0                      # exercises grad < GRAD_IS_ZERO
+    grad = (ix * ix + iy * iy).astype(np.float32)
+    rho_c = f(-30, 30)
+    args = (u1, u2, *p, rho_c, ix, iy, grad, 0.25, 0.15, 0.3, iters)
+    got = gpu.iterate(*args)
+    ref = oracle_f64.iterate(*args)
+    for k, name in enumerate(("u1", "u2", "p11", "p12", "p21", "p22")):
+        assert np.abs(got[k] - ref[k]).max() < 2e-4 * iters, name
+    assert np.allclose(got[6], ref[6], rtol=1e-4)
+
+
+def test_iterate_keeps_dual_boundary_invariants(gpu):
+    """forward_gradient is 0 on the last column / row, so p11,p21 stay 0 there when they start at 0
+    (the reference relies on this when it drops those terms in divergence)."""
+    shape = (21, 37)
+    rs = np.random.RandomState(9)
+    f = lambda lo, hi: rs.uniform(lo, hi, shape).astype(np.float32)
+    z = np.zeros(shape, np.float32)
+    ix, iy = f(-20, 20), f(-20, 20)
+    out = gpu.iterate(f(-1, 1), f(-1, 1), z, z, z, z, f(-30, 30), ix, iy, ix * ix + iy * iy,
+                      0.25, 0.15, 0.3, 4)
+    assert np.all(out[2][:, -1] == 0) and np.all(out[4][:, -1] == 0)
+    assert np.all(out[3][-1, :] == 0) and np.all(out[5][-1, :] == 0)
+
+
+# ---- the solver against the golden vectors of the unmodified reference --------------------------
+
+@pytest.mark.parametrize("name", sorted(_cases.SOLVER_CASES))
+def test_solver_vs_golden(gpu, golden, name):
+    case = _cases.SOLVER_CASES[name]
+    I0, I1 = _cases.solver_inputs(case)
+    u1, u2, iters, errs = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **case["kw"])
+    pre = "f64/%s/" % name
+    assert np.array_equal(iters, golden[pre + "iters"]), (iters.tolist(), golden[pre + "iters"].tolist())
+    assert_flow_close(u1, u2, golden[pre + "u1"], golden[pre + "u2"], name)
+    assert np.allclose(errs, golden[pre + "errs"], rtol=1e-3, atol=1e-6)
+
+
+def test_solver_f64_entry_matches_f32_entry(gpu):
+    case = _cases.SOLVER_CASES["ms_64x48"]
+    I0, I1 = _cases.solver_inputs(case)
+    a = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **case["kw"])
+    b = gpu.Dual_TVL1_optic_flow_multiscale(I0.astype(np.float64), I1.astype(np.float64), **case["kw"])
+    assert b[0].dtype == np.float64
+    assert np.array_equal(a[0].astype(np.float64), b[0]) and np.array_equal(a[2], b[2])
+
+
+def test_single_scale_entry(gpu, oracle_f64):
+    """Dual_TVL1_optic_flow: the initial flow is used (src/tvl1flow.cpp:94)."""
+    I0, I1 = _cases.synth.make_pair(96, 72, seed=21, scale=0.3)
+    rs = np.random.RandomState(2)
+    u1 = rs.uniform(-0.5, 0.5, I0.shape).astype(np.float32)
+    u2 = rs.uniform(-0.5, 0.5, I0.shape).astype(np.float32)
+    g = gpu.Dual_TVL1_optic_flow(I0, I1, u1, u2, warps=3, eps=0.01)
+    r = oracle_f64.single_scale(I0, I1, u1, u2, warps=3, eps=0.01)
+    assert np.array_equal(g[2], r[2]), (g[2], r[2])
+    assert_flow_close(g[0], g[1], r[0], r[1], "single scale")
+
+
+def test_eps_zero_runs_to_the_cap(gpu):
+    I0, I1 = _cases.synth.make_pair(48, 40, seed=3, scale=0.3)
+    _, _, iters, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, nscales=2, warps=2, eps=0.0)
+    assert np.all(iters == 300)     # MAX_ITERATIONS, src/tvl1flow.cpp:22,113
+
+
+def test_sigma_too_large_is_an_error(gpu):
+    I0, I1 = _cases.synth.make_pair(40, 32, seed=3)
+    with pytest.raises(pkg.TVL1Error) as e:
+        gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, nscales=5)   # level 3 is 5 px wide < 6 taps
+    assert e.value.code == 2
+
+
+def test_identical_images_give_zero_flow(gpu):
+    I0, _ = _cases.synth.make_pair(128, 96, seed=8)
+    u1, u2, iters, errs = gpu.Dual_TVL1_optic_flow_multiscale(I0, I0, nscales=3)
+    assert np.all(u1 == 0) and np.all(u2 == 0)
+    assert np.all(iters == 1) and np.all(errs == 0)
+
+
+def test_batch_equals_individual_solves(gpu):
+    """Pairs of a batch are independent units: batching must not change a single bit."""
+    pairs = [_cases.synth.make_pair(100, 76, seed=40 + b, scale=0.4) for b in range(5)]
+    I0 = np.stack([p[0] for p in pairs])
+    I1 = np.stack([p[1] for p in pairs])
+    kw = dict(nscales=3, warps=3, eps=0.01)
+    bu1, bu2, bit, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    for b in range(5):
+        u1, u2, it, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0[b], I1[b], **kw)
+        assert np.array_equal(it, bit[b])
+        assert np.array_equal(u1, bu1[b]) and np.array_equal(u2, bu2[b])
+    # chunking by max_batch must not matter either
+    gpu.set_max_batch(2)
+    cu1, cu2, cit, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    gpu.set_max_batch(32)
+    assert np.array_equal(cu1, bu1) and np.array_equal(cu2, bu2) and np.array_equal(cit, bit)
+
+
+# ---- BASELINE.json configs --------------------------------------------------------------------
+
+def reference_cpu():
+    """The compiled reference when it travelled with the snapshot, else the oracle port."""
+    kind = "reference" if available("reference", np.float64) else "port"
+    return CpuTvl1(kind, np.float64), kind
+
+
+@pytest.mark.parametrize("nx,ny", [(640, 480), (1024, 436)])
+def test_baseline_configs_vs_reference(gpu, nx, ny):
+    """configs[0] and configs[1]: default parameters, 5 scales x 5 warps."""
+    cpu, kind = reference_cpu()
+    I0, I1 = _cases.synth.make_pair(nx, ny, seed=1234)
+    kw = dict(tau=0.25, lam=0.15, theta=0.3, nscales=5, zfactor=0.5, warps=5, eps=0.01)
+    u1, u2, iters, errs = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    r1, r2, riters, rerrs = cpu.multiscale(I0, I1, **kw)
+    mean, mx = flow_diff(u1, u2, r1, r2)
+    print("%dx%d vs %s: mean|d|=%.3g max|d|=%.3g iters=%s" % (nx, ny, kind, mean, mx, iters.tolist()))
+    assert np.array_equal(iters, riters), (iters.tolist(), riters.tolist())
+    assert mean <= MEAN_TOL and mx <= MAX_TOL
+
+
+def test_1080p_properties(gpu):
+    """Full-size (1920x1080, 5 scales x 5 warps) checks that do not need the CPU oracle:
+    run-to-run determinism, batch-position independence, and the zero-motion fixed point."""
+    nx, ny = 1920, 1080
+    a = _cases.synth.make_pair(nx, ny, seed=1234)
+    b = _cases.synth.make_pair(nx, ny, seed=1235)
+    I0 = np.stack([a[0], b[0], a[0]])
+    I1 = np.stack([a[1], b[1], a[0]])
+    u1, u2, iters, errs = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1)
+    v1, v2, jters, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0[::-1].copy(), I1[::-1].copy())
+    assert np.array_equal(u1, v1[::-1]) and np.array_equal(u2, v2[::-1]) and np.array_equal(iters, jters[::-1])
+    assert np.all(u1[2] == 0) and np.all(u2[2] == 0) and np.all(iters[2] == 1)
+    assert iters.min() >= 1 and iters.max() <= 300
+    # the synthetic motion is (2.3, 1.4) outside the disc and (-3.3, 2.6) inside it
+    yy, xx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    r2 = (xx - 0.5 * nx) ** 2 + (yy - 0.5 * ny) ** 2
+    bg = r2 > (0.25 * ny + 40) ** 2
+    bg[:40] = bg[-40:] = False
+    bg[:, :40] = bg[:, -40:] = False
+    disc = r2 < (0.25 * ny - 40) ** 2
+    assert abs(np.median(u1[0][bg]) - 2.3) < 0.1 and abs(np.median(u2[0][bg]) - 1.4) < 0.1
+    assert abs(np.median(u1[0][disc]) + 3.3) < 0.1 and abs(np.median(u2[0][disc]) - 2.6) < 0.1
+
+
+def test_1080p_vs_reference(gpu):
+    """configs[2] unit of work (one 1080p pair) against the CPU reference / oracle."""
+    cpu, kind = reference_cpu()
+    I0, I1 = _cases.synth.make_pair(1920, 1080, seed=1234)
+    u1, u2, iters, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1)
+    r1, r2, riters, _ = cpu.multiscale(I0, I1)
+    mean, mx = flow_diff(u1, u2, r1, r2)
+    print("1080p vs %s: mean|d|=%.3g max|d|=%.3g iters=%s" % (kind, mean, mx, iters.tolist()))
+    assert np.array_equal(iters, riters), (iters.tolist(), riters.tolist())
+    assert mean <= MEAN_TOL and mx <= MAX_TOL
