@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- TV-L1 1080p frame-pairs/s on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1
+          --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[2] -- a batch of synthetic 1920x1080 frame
+pairs, default parameters (tau .25, lambda .15, theta .3, 5 scales x 5 warps, eps .01).  One step =
+one pass of the solver over one batch of `--pairs` pairs per rank (default 256).  Pairs are
+independent units, so ranks shard the batch with no data-path collective (weak scaling: every
+rank gets its own `--pairs` pairs).
+
+  value : whole-job frame-pairs/s, inputs already resident in HBM (tvl1_solve_batch_dev_f32)
+  e2e   : same metric through the host-buffer C ABI (tvl1_solve_batch_f32): pinned host inputs,
+          H2D and D2H inside the timed region
+  roofline : the fused iteration kernel, algorithmic 64 B per pixel-iteration
+             / CUDA-event time of its launches inside the timed region
+  cpu_baseline : the reference's own CPU code (oracle/_ref, else the oracle port) on a bounded
+             sample of the same workload, all host threads
+
+--impl reference times that CPU implementation alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "TV-L1 1080p frame-pairs/sec"
+UNIT = "frame-pairs/s"
+ALGO_BYTES_PER_PIXEL_ITERATION = 64      # BASELINE.md section 3, SURVEY.md 8d
+PARAMS = dict(tau=0.25, lam=0.15, theta=0.3, nscales=5, zfactor=0.5, warps=5, eps=0.01)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=256, help="frame pairs per rank per step")
+    ap.add_argument("--e2e-pairs", type=int, default=64, help="frame pairs per rank per e2e step")
+    ap.add_argument("--nx", type=int, default=1920)
+    ap.add_argument("--ny", type=int, default=1080)
+    ap.add_argument("--max-batch", type=int, default=32, help="pairs advanced in lock-step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config(args, n_gpus):
+    return {
+        "workload": "batch of %d synthetic %dx%d frame pairs per rank (BASELINE.json configs[2]), "
+                    "5 scales x 5 warps, default params" % (args.pairs, args.nx, args.ny),
+        "pairs_per_rank_per_step": args.pairs,
+        "global_pairs_per_step": args.pairs * n_gpus,
+        "nx": args.nx, "ny": args.ny,
+        "params": PARAMS,
+        "lockstep_batch": args.max_batch,
+        "parallelism": "batch-sharded x%d, no collective" % n_gpus,
+        "l2": "inputs (%.1f GB per rank) and solver state exceed the 126 MB L2; no explicit flush"
+              % (args.pairs * 2 * args.nx * args.ny * 4 / 1e9),
+    }
+
+
+# ---- clocks -----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---- CPU reference leg ---------------------------------------------------------------------------
+def cpu_solver():
+    import numpy as np
+    from oracle.loader import CpuTvl1, available
+    kind = "reference" if available("reference", np.float64) else "port"
+    return CpuTvl1(kind, np.float64), kind
+
+
+def cpu_sample(args, budget_s, max_pairs=4):
+    """Times the reference's CPU implementation on whole 1080p pairs of the same workload."""
+    import numpy as np
+    from optical_flow_1_b200 import synth
+    cpu, kind = cpu_solver()
+    times = []
+    t_all = time.perf_counter()
+    for b in range(max_pairs):
+        I0, I1 = synth.make_pair(args.nx, args.ny, seed=1234 + b)
+        I0, I1 = I0.astype(np.float64), I1.astype(np.float64)
+        t = time.perf_counter()
+        cpu.multiscale(I0, I1, want_iters=False, **PARAMS)
+        times.append(time.perf_counter() - t)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    return {
+        "value": len(times) / sum(times), "unit": UNIT, "cores": cpu.max_threads(), "kind": kind,
+        "sample": "%d of the workload's %dx%d pairs (seeds 1234..), Dual_TVL1_optic_flow_multiscale "
+                  "in fp64, g++ -O3 -fopenmp, %d threads, %.1f s" % (
+                      len(times), args.nx, args.ny, cpu.max_threads(), sum(times)),
+    }
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import numpy as np
+    from optical_flow_1_b200 import synth
+    cpu, kind = cpu_solver()
+    I0, I1 = synth.make_pair(args.nx, args.ny, seed=1234)
+    I0, I1 = I0.astype(np.float64), I1.astype(np.float64)
+    for _ in range(args.warmup):
+        cpu.multiscale(I0, I1, want_iters=False, **PARAMS)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.multiscale(I0, I1, want_iters=False, **PARAMS)
+    dt = time.perf_counter() - t
+    v = args.steps / dt
+    sample = ("each step = 1 pair of the workload (%dx%d, seed 1234), fp64, g++ -O3 -fopenmp, %d threads"
+              % (args.nx, args.ny, cpu.max_threads()))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config(args, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.max_threads(), "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---- our arm -------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import optical_flow_1_b200 as pkg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the solver has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nx, ny, P = args.nx, args.ny, args.pairs
+    solver = pkg.TVL1(device=local_rank, max_batch=args.max_batch, profiling=True)
+    stream = torch.cuda.ExternalStream(solver.stream(), device=dev)
+
+    # synthetic inputs generated straight into HBM; rank r uses seeds 1234 + r*P ...
+    I0, I1 = pkg.synth.make_batch_torch(P, nx, ny, seed=1234 + rank * P, device=dev)
+    u1 = torch.empty_like(I0)
+    u2 = torch.empty_like(I0)
+    torch.cuda.synchronize()
+
+    def step_device():
+        solver.solve_batch_device(I0.data_ptr(), I1.data_ptr(), u1.data_ptr(), u2.data_ptr(),
+                                  P, nx, ny, **PARAMS)
+        return solver.stats()
+
+    for _ in range(args.warmup):
+        step_device()
+
+    barrier()
+    clocks = ClockSampler(local_rank)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    acc = None
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        st = step_device()
+        if acc is None:
+            acc = st
+        else:
+            for k, v in st.items():
+                acc[k] = [a + b for a, b in zip(acc[k], v)] if isinstance(v, list) else acc[k] + v
+    e1.record(stream)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    ms = max_over_ranks(dev_ms)
+    value = world * P * args.steps / (ms / 1e3)
+
+    # roofline of the fused iteration kernel over the timed region (this rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    it_ms = acc["iterate_ms"]
+    achieved = ALGO_BYTES_PER_PIXEL_ITERATION * acc["pixel_iterations"] / (it_ms / 1e3) / 1e9 if it_ms > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except (OSError, ValueError):
+        pass
+    per_level = []
+    for l in range(PARAMS["nscales"]):
+        lms, lpx = acc["level_iterate_ms"][l], acc["level_pixel_iterations"][l]
+        per_level.append({"level": l, "launches": acc["level_iterate_launches"][l], "ms": lms,
+                          "GBps": ALGO_BYTES_PER_PIXEL_ITERATION * lpx / (lms / 1e3) / 1e9 if lms > 0 else None})
+    roofline = {
+        "kernel": "k_iterate_t1 (fused TH + div + u update + grad + p update + stop test)",
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak if achieved else None,
+        "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+        "traffic_source": traffic.get("source") if traffic else None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_pixel_iteration": ALGO_BYTES_PER_PIXEL_ITERATION,
+        "pixel_iterations": acc["pixel_iterations"], "launches": acc["iterate_launches"],
+        "kernel_ms": it_ms, "kernel_share_of_step": it_ms / (dev_ms if dev_ms > 0 else 1),
+        "per_level": per_level,
+    }
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    E = min(args.e2e_pairs, P)
+    hI0 = torch.empty((E, ny, nx), dtype=torch.float32).pin_memory()
+    hI1 = torch.empty_like(hI0).pin_memory()
+    hu1 = torch.empty_like(hI0).pin_memory()
+    hu2 = torch.empty_like(hI0).pin_memory()
+    hI0.copy_(I0[:E])
+    hI1.copy_(I1[:E])
+    torch.cuda.synchronize()
+
+    def step_host():
+        solver.solve_batch_host_ptr(hI0.data_ptr(), hI1.data_ptr(), hu1.data_ptr(), hu2.data_ptr(),
+                                    E, nx, ny, dtype="float32", **PARAMS)
+        return float(hu1[0, ny // 2, nx // 2])       # touch the result on the host
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_host()
+    barrier()
+    e_steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    e2e_launches = solver.stats()["kernel_launches"]
+    e2e = {"value": world * E * e_steps / (e_ms / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": 2 * E * nx * ny * 4, "d2h_bytes_per_step": 2 * E * nx * ny * 4,
+           "pairs_per_rank_per_step": E, "steps": e_steps, "ms_per_step": e_ms / e_steps,
+           "api": "tvl1_solve_batch_f32 (host pinned fp32 in, host fp32 out)", "timer": "wall clock, max over ranks"}
+    # the device-resident result must equal the host-path result for the same pairs
+    same = bool(torch.equal(hu1, u1[:E].cpu()) and torch.equal(hu2, u2[:E].cpu()))
+
+    total_launches = sum_over_ranks(acc["kernel_launches"])
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_sample(args, args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config(args, world), "clocks": clk, "e2e": e2e,
+            "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_base,
+            "timer": {"device_ms_rank0": dev_ms, "wall_ms_rank0": wall_ms},
+            "host_syncs_per_step": acc["host_syncs"] / args.steps,
+            "e2e_matches_device_path": same,
+        }
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

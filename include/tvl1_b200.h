@@ -45,6 +45,7 @@ extern "C" {
 #define TVL1_PRESMOOTHING_SIGMA 0.8  /* src/tvl1flow.cpp:23 */
 #define TVL1_GRAD_IS_ZERO 1E-10      /* src/tvl1flow.cpp:24 */
 #define TVL1_ZOOM_SIGMA_ZERO 0.6     /* src/zoom.cpp:15 */
+#define TVL1_MAX_LEVELS 16           /* pyramid levels this build keeps statistics for */
 
 typedef struct tvl1_ctx tvl1_ctx;
 
@@ -70,6 +71,10 @@ typedef struct tvl1_stats {
     double warp_ms;                       /* device time inside warp launches (same) */
     double total_ms;                      /* device time of the whole solve (same) */
     unsigned long long host_syncs;        /* stream synchronisations issued for loop control */
+    /* per pyramid level (0 = finest), iteration kernel only */
+    unsigned long long level_pixel_iterations[TVL1_MAX_LEVELS];
+    unsigned long long level_iterate_launches[TVL1_MAX_LEVELS];
+    double level_iterate_ms[TVL1_MAX_LEVELS];
 } tvl1_stats;
 
 /* -- life cycle --------------------------------------------------------------------------- */
@@ -80,6 +85,7 @@ const char *tvl1_last_error(const tvl1_ctx *ctx);  /* ctx may be NULL: error of 
 int tvl1_set_profiling(tvl1_ctx *ctx, int on);     /* bracket kernels with CUDA events (tvl1_stats *_ms) */
 int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs);  /* pairs advanced in lock-step per workspace (default 32) */
 int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out);
+void *tvl1_get_stream(const tvl1_ctx *ctx);        /* the cudaStream_t all work of this context is issued on */
 void tvl1_default_params(tvl1_params *p);          /* tvl1flow_main.cpp:24-33 with nscales = 5 */
 
 /* -- the solver: Dual_TVL1_optic_flow_multiscale (src/tvl1flow.cpp:219-328) ---------------- */

@@ -360,6 +360,38 @@ __global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ 
         out[i] = (double) in[i];
 }
 
+// Seeded pseudo-random content for the kernel-only benchmark (tvl1_bench_iterate): flow in
+// [-3,3], dual in [-1,1], image gradients in [-20,20] with about 10% exact zeros (so all three
+// branches of the thresholding step occur), rho_c in [-30,30], grad = Ix^2 + Iy^2.
+__device__ __forceinline__ float hash_unit(unsigned long long i, unsigned int salt)
+{
+    unsigned long long z = i * 0x9E3779B97F4A7C15ull + ((unsigned long long) salt << 32 | 0x632BE5ABu);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float) (z >> 40) * (1.0f / 16777216.0f);
+}
+__global__ void k_fill_bench(float *__restrict__ state, float *__restrict__ consts, size_t field_stride,
+                             size_t set_stride)
+{
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < field_stride;
+         i += (size_t) gridDim.x * blockDim.x) {
+        for (int set = 0; set < 2; set++) {
+            float *s = state + set * set_stride + i;
+            s[F_U1 * field_stride] = 6.f * hash_unit(i, 1) - 3.f;
+            s[F_U2 * field_stride] = 6.f * hash_unit(i, 2) - 3.f;
+            for (int f = F_P11; f <= F_P22; f++) s[f * field_stride] = 2.f * hash_unit(i, 3 + f) - 1.f;
+        }
+        const bool flat = hash_unit(i, 11) < 0.1f;
+        const float ix = flat ? 0.f : 40.f * hash_unit(i, 12) - 20.f;
+        const float iy = flat ? 0.f : 40.f * hash_unit(i, 13) - 20.f;
+        consts[C_IX * field_stride + i] = ix;
+        consts[C_IY * field_stride + i] = iy;
+        consts[C_RHO * field_stride + i] = 60.f * hash_unit(i, 14) - 30.f;
+        consts[C_GRAD * field_stride + i] = ix * ix + iy * iy;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // (b) warp + precompute
 // ------------------------------------------------------------------------------------------------
@@ -479,6 +511,7 @@ struct IterParams {
     int parts_per_pair;
     int stat_stride, stat_slot;
     int max_iter;
+    int level;                   // pyramid level (statistics only)
     float l_t, theta, taut;
     double eps2;
 };

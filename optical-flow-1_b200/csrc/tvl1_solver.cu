@@ -39,7 +39,7 @@ struct Workspace {
     int *active = nullptr;
     int *stat_iters = nullptr;
     double *stat_errs = nullptr;
-    unsigned long long *counters = nullptr;   // [0] pixel-iterations
+    unsigned long long *counters = nullptr;   // [level] pixel-iterations
     int parts_per_pair = 0;
     int stat_stride = 0;
     size_t bytes = 0;
@@ -49,7 +49,7 @@ struct Workspace {
     float *I1(int s) const { return pyr + pyr_off[s] + (size_t) B * plane(s); }
 };
 
-struct EventPair { cudaEvent_t a, b; int kind; };   // kind 0 iterate, 1 warp, 2 total
+struct EventPair { cudaEvent_t a, b; int kind, level; };   // kind 0 iterate, 1 warp, 2 total
 
 } // namespace
 
@@ -171,7 +171,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     CK(cudaMalloc(&w.active, sizeof(int)));
     CK(cudaMalloc(&w.stat_iters, sizeof(int) * (size_t) B * stat_stride));
     CK(cudaMalloc(&w.stat_errs, sizeof(double) * (size_t) B * stat_stride));
-    CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * 4));
+    CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * TVL1_MAX_LEVELS));
     w.bytes = (off + 2 * w.set_stride + C_COUNT * w.field_stride) * fl;
     // padding columns are never consumed, but keep them finite
     CK(cudaMemsetAsync(w.state, 0, 2 * w.set_stride * fl, ctx->stream));
@@ -195,10 +195,10 @@ cudaEvent_t take_event(tvl1_ctx *ctx)
 
 struct Span {
     tvl1_ctx *ctx; int idx = -1;
-    Span(tvl1_ctx *c, int kind) : ctx(c)
+    Span(tvl1_ctx *c, int kind, int level = 0) : ctx(c)
     {
         if (!c->profiling) return;
-        EventPair p{ take_event(c), take_event(c), kind };
+        EventPair p{ take_event(c), take_event(c), kind, level };
         cudaEventRecord(p.a, c->stream);
         c->ev_used.push_back(p);
         idx = (int) c->ev_used.size() - 1;
@@ -212,7 +212,10 @@ void resolve_events(tvl1_ctx *ctx)
     for (auto &p : ctx->ev_used) {
         float ms = 0.f;
         if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
-            if (p.kind == 0) ctx->stats.iterate_ms += ms;
+            if (p.kind == 0) {
+                ctx->stats.iterate_ms += ms;
+                ctx->stats.level_iterate_ms[std::min(p.level, TVL1_MAX_LEVELS - 1)] += ms;
+            }
             else if (p.kind == 1) ctx->stats.warp_ms += ms;
             else ctx->stats.total_ms += ms;
         }
@@ -242,13 +245,14 @@ int launch_gauss(tvl1_ctx *ctx, int D, const float *in, int in_pitch, size_t in_
 }
 
 IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &prm, int stat_slot,
-                       int max_iter)
+                       int max_iter, int level = 0)
 {
     const Workspace &w = ctx->ws;
     IterParams P;
     P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
     P.active_pairs = w.active; P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
-    P.px_iters = w.counters;
+    P.px_iters = w.counters + std::min(level, TVL1_MAX_LEVELS - 1);
+    P.level = level;
     P.plane0 = w.plane0; P.field_stride = w.field_stride; P.set_stride = w.set_stride;
     P.lv = lv; P.parts_per_pair = w.parts_per_pair;
     P.stat_stride = w.stat_stride; P.stat_slot = stat_slot; P.max_iter = max_iter;
@@ -265,6 +269,7 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
     k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     CKL(ctx);
     ctx->stats.iterate_launches++;
+    ctx->stats.level_iterate_launches[std::min(P.level, TVL1_MAX_LEVELS - 1)]++;
     return TVL1_OK;
 }
 
@@ -302,7 +307,7 @@ int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint)
     while (launched < P.max_iter) {
         const int k = std::min(chunk, P.max_iter - launched);
         {
-            Span sp(ctx, 0);
+            Span sp(ctx, 0, P.level);
             for (int i = 0; i < k; i++) TRY(launch_iterate(ctx, P, B));
         }
         launched += k;
@@ -330,7 +335,7 @@ int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base
         }
         k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.active, B);   // :111-112
         CKL(ctx);
-        const IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations);
+        const IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations, s);
         TRY(run_iterations(ctx, P, B, chunk_hint));                         // :113-182
     }
     return TVL1_OK;
@@ -352,7 +357,7 @@ void reset_stats(tvl1_ctx *ctx) { ctx->stats = tvl1_stats{}; }
 int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_out)
 {
     const Workspace &w = ctx->ws;
-    unsigned long long c[4] = { 0, 0, 0, 0 };
+    unsigned long long c[TVL1_MAX_LEVELS] = { 0 };
     CK(cudaMemcpyAsync(c, w.counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
     if (iters_out)
         CK(cudaMemcpy2DAsync(iters_out, sizeof(int) * nstat, w.stat_iters, sizeof(int) * w.stat_stride,
@@ -361,7 +366,10 @@ int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_ou
         CK(cudaMemcpy2DAsync(errs_out, sizeof(double) * nstat, w.stat_errs, sizeof(double) * w.stat_stride,
                              sizeof(double) * nstat, B, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.pixel_iterations += c[0];
+    for (int l = 0; l < TVL1_MAX_LEVELS; l++) {
+        ctx->stats.pixel_iterations += c[l];
+        ctx->stats.level_pixel_iterations[l] += c[l];
+    }
     return TVL1_OK;
 }
 
@@ -382,7 +390,7 @@ int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, flo
     for (int s = 1; s < ns; s++) TRY(check_sigma(ctx, zsigma, w.lv[s - 1].nx, zoom));
 
     Span total(ctx, 2);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 4, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * TVL1_MAX_LEVELS, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
 
@@ -448,7 +456,7 @@ int run_single_scale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, f
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
     Span total(ctx, 2);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 4, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * TVL1_MAX_LEVELS, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
@@ -652,6 +660,8 @@ int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs)
     ctx->max_batch = pairs;
     return TVL1_OK;
 }
+
+void *tvl1_get_stream(const tvl1_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
 
 int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out)
 {
@@ -887,7 +897,7 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
     if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
     CKL(ctx);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 4, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * TVL1_MAX_LEVELS, st));
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
     float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
     for (int f = 0; f < 6; f++) {
@@ -932,8 +942,8 @@ int tvl1_bench_iterate(tvl1_ctx *ctx, int npairs, int nx, int ny, int launches, 
     TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, npairs, 1));
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
-    // deterministic, smooth-ish content: a previous solve's leftovers are as good as anything, but
-    // start from a defined state (flow 0, dual 0, constants 0 => every pixel takes the grad<eps branch)
+    k_fill_bench<<<ctx->sm_count * 8, 256, 0, st>>>(w.state, w.consts, w.field_stride, w.set_stride);
+    CKL(ctx);
     k_init_ctl<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.mm, npairs);
     CKL(ctx);
     k_begin_warp<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.active, npairs);

@@ -42,10 +42,17 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("iterate_launches", C.c_ulonglong),
                 ("pixel_iterations", C.c_ulonglong), ("pixel_warps", C.c_ulonglong),
                 ("iterate_ms", C.c_double), ("warp_ms", C.c_double), ("total_ms", C.c_double),
-                ("host_syncs", C.c_ulonglong)]
+                ("host_syncs", C.c_ulonglong),
+                ("level_pixel_iterations", C.c_ulonglong * 16),
+                ("level_iterate_launches", C.c_ulonglong * 16),
+                ("level_iterate_ms", C.c_double * 16)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        out = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            out[k] = list(v) if hasattr(v, "__len__") else v
+        return out
 
 
 def library_path():
@@ -112,6 +119,11 @@ class TVL1:
 
     def set_max_batch(self, pairs):
         self._ck(self.lib.tvl1_set_max_batch(self.ctx, C.c_int(int(pairs))))
+
+    def stream(self):
+        """cudaStream_t (as int) that all work of this context is issued on."""
+        self.lib.tvl1_get_stream.restype = C.c_void_p
+        return int(self.lib.tvl1_get_stream(self.ctx) or 0)
 
     def stats(self):
         s = Stats()
