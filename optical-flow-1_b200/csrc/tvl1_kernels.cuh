@@ -18,6 +18,7 @@ namespace tvl1 {
 
 constexpr int kMaxIterations = 300;       // src/tvl1flow.cpp:22
 constexpr float kGradIsZero = 1e-10f;     // src/tvl1flow.cpp:24
+constexpr int kStatLevels = 16;           // == TVL1_MAX_LEVELS
 constexpr int kMaxTaps = 16;              // (int)(5*sigma)+1 <= 16  <=>  sigma < 3.2 (zfactor > 0.19)
 
 enum Field { F_U1 = 0, F_U2, F_P11, F_P12, F_P21, F_P22, F_COUNT };
@@ -34,6 +35,12 @@ struct PairCtl {
     int n;                // iterations done in the current warp step
     unsigned int arrive;  // CTA arrival counter (last-block election)
     double err;           // mean squared update of the last iteration
+};
+
+// Whole-batch loop state of the current warp step.
+struct LoopCtl {
+    int active_pairs;     // pairs still iterating
+    int max_n;            // largest iteration count among the pairs that already stopped
 };
 
 struct GaussTaps {
@@ -276,7 +283,7 @@ __global__ void k_zero_fields(float *__restrict__ state, size_t plane0, size_t f
 }
 
 // start of a warp step: n = 0, error = INFINITY (src/tvl1flow.cpp:111-112)
-__global__ void k_begin_warp(PairCtl *ctl, int *active_pairs, int B)
+__global__ void k_begin_warp(PairCtl *ctl, LoopCtl *loop, int B)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) {
@@ -285,7 +292,7 @@ __global__ void k_begin_warp(PairCtl *ctl, int *active_pairs, int B)
         ctl[b].arrive = 0u;
         ctl[b].err = INFINITY;
     }
-    if (b == 0) *active_pairs = B;
+    if (b == 0) { loop->active_pairs = B; loop->max_n = 0; }
 }
 
 __global__ void k_init_ctl(PairCtl *ctl, unsigned int *mm, int B)
@@ -502,10 +509,12 @@ struct IterParams {
     const float *consts;
     PairCtl *ctl;
     double *partials;            // [B][parts_per_pair]
-    int *active_pairs;
+    LoopCtl *loop;
+    cudaGraphConditionalHandle cond;   // while-node handle when launched from the solve graph, else 0
+    int use_cond;
     int *stat_iters;             // [B][stat_stride]
     double *stat_errs;
-    unsigned long long *px_iters;
+    unsigned long long *px_iters;  // [level] pixel-iterations; [TVL1_MAX_LEVELS + level] launches
     size_t plane0, field_stride, set_stride;
     Level lv;
     int parts_per_pair;
@@ -535,6 +544,8 @@ k_iterate_t1(const IterParams P)
 {
     const int b = blockIdx.z;
     PairCtl *ctl = P.ctl + b;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && b == 0 && threadIdx.x == 0)
+        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
     if (!ctl->active) return;                       // uniform for the whole CTA
 
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
@@ -706,12 +717,15 @@ k_iterate_t1(const IterParams P)
         ctl->err = error;
         ctl->cur = cur ^ 1;
         ctl->arrive = 0u;
-        atomicAdd(P.px_iters, (unsigned long long) nx * (unsigned long long) ny);
+        atomicAdd(P.px_iters + P.level, (unsigned long long) nx * (unsigned long long) ny);
         if (!(error > P.eps2 && n < P.max_iter)) {                // src/tvl1flow.cpp:113
             ctl->active = 0;
             P.stat_iters[(size_t) b * P.stat_stride + P.stat_slot] = n;
             P.stat_errs[(size_t) b * P.stat_stride + P.stat_slot] = error;
-            atomicSub(P.active_pairs, 1);
+            atomicMax(&P.loop->max_n, n);
+            const int left = atomicSub(&P.loop->active_pairs, 1) - 1;
+            // the last pair to stop ends the device-side while loop of the solve graph
+            if (left == 0 && P.use_cond) cudaGraphSetConditional(P.cond, 0);
         }
     }
 }

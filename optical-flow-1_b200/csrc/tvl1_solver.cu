@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -36,10 +37,10 @@ struct Workspace {
     PairCtl *ctl = nullptr;
     unsigned int *mm = nullptr;
     double *partials = nullptr;
-    int *active = nullptr;
+    LoopCtl *loop = nullptr;
     int *stat_iters = nullptr;
     double *stat_errs = nullptr;
-    unsigned long long *counters = nullptr;   // [level] pixel-iterations
+    unsigned long long *counters = nullptr;   // [level] pixel-iterations, [16 + level] iteration launches
     int parts_per_pair = 0;
     int stat_stride = 0;
     size_t bytes = 0;
@@ -51,6 +52,19 @@ struct Workspace {
 
 struct EventPair { cudaEvent_t a, b; int kind, level; };   // kind 0 iterate, 1 warp, 2 total
 
+// The coarse-to-fine part of one solve, captured once per (workspace, parameters) as a CUDA graph
+// whose primal-dual loops are conditional WHILE nodes: the device ends each loop itself
+// (cudaGraphSetConditional from the iteration kernel), so a solve needs no host round trip.
+struct SolveGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    tvl1_params prm{};
+    bool multiscale = false, profiling = false;
+    unsigned long long static_launches = 0;   // kernel nodes outside the while bodies
+    unsigned long long pixel_warps = 0;
+    std::vector<EventPair> events;            // external event-record nodes (profiling)
+};
+
 } // namespace
 
 struct tvl1_ctx {
@@ -61,7 +75,11 @@ struct tvl1_ctx {
     int max_batch = 32;
     tvl1_stats stats{};
     Workspace ws;
-    int *h_active = nullptr;                 // pinned
+    LoopCtl *h_loop = nullptr;               // pinned
+    cudaStream_t body_stream = nullptr;      // capture stream for while-node bodies
+    bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
+    bool capturing = false;
+    SolveGraph sg;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<EventPair> ev_used;
     // staging for the host-buffer entry points
@@ -117,10 +135,18 @@ int make_taps(double sigma, GaussTaps &t)
     return size;
 }
 
+void free_graph(SolveGraph &g, std::vector<cudaEvent_t> &pool)
+{
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    for (auto &p : g.events) { pool.push_back(p.a); pool.push_back(p.b); }
+    g = SolveGraph();
+}
+
 void free_workspace(Workspace &w)
 {
     cudaFree(w.pyr); cudaFree(w.state); cudaFree(w.consts); cudaFree(w.tmp); cudaFree(w.ctl);
-    cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.active); cudaFree(w.stat_iters);
+    cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.loop); cudaFree(w.stat_iters);
     cudaFree(w.stat_errs); cudaFree(w.counters);
     w = Workspace();
 }
@@ -136,6 +162,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     if (w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
         w.stat_stride >= stat_stride)
         return TVL1_OK;
+    free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(w);
     w.nx = nx; w.ny = ny; w.nscales = nscales; w.zfactor = zfactor; w.B = B;
     w.stat_stride = stat_stride;
@@ -168,10 +195,10 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     CK(cudaMalloc(&w.ctl, sizeof(PairCtl) * B));
     CK(cudaMalloc(&w.mm, sizeof(unsigned int) * 2 * B));
     CK(cudaMalloc(&w.partials, sizeof(double) * (size_t) B * parts));
-    CK(cudaMalloc(&w.active, sizeof(int)));
+    CK(cudaMalloc(&w.loop, sizeof(LoopCtl)));
     CK(cudaMalloc(&w.stat_iters, sizeof(int) * (size_t) B * stat_stride));
     CK(cudaMalloc(&w.stat_errs, sizeof(double) * (size_t) B * stat_stride));
-    CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * TVL1_MAX_LEVELS));
+    CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS));
     w.bytes = (off + 2 * w.set_stride + C_COUNT * w.field_stride) * fl;
     // padding columns are never consumed, but keep them finite
     CK(cudaMemsetAsync(w.state, 0, 2 * w.set_stride * fl, ctx->stream));
@@ -199,26 +226,41 @@ struct Span {
     {
         if (!c->profiling) return;
         EventPair p{ take_event(c), take_event(c), kind, level };
-        cudaEventRecord(p.a, c->stream);
-        c->ev_used.push_back(p);
-        idx = (int) c->ev_used.size() - 1;
+        if (c->capturing) {
+            cudaEventRecordWithFlags(p.a, c->stream, cudaEventRecordExternal);
+            c->sg.events.push_back(p);
+            idx = (int) c->sg.events.size() - 1;
+        } else {
+            cudaEventRecord(p.a, c->stream);
+            c->ev_used.push_back(p);
+            idx = (int) c->ev_used.size() - 1;
+        }
     }
-    void end() { if (idx >= 0) { cudaEventRecord(ctx->ev_used[idx].b, ctx->stream); idx = -1; } }
+    void end()
+    {
+        if (idx < 0) return;
+        if (ctx->capturing) cudaEventRecordWithFlags(ctx->sg.events[idx].b, ctx->stream, cudaEventRecordExternal);
+        else cudaEventRecord(ctx->ev_used[idx].b, ctx->stream);
+        idx = -1;
+    }
     ~Span() { end(); }
 };
+
+void add_span_time(tvl1_ctx *ctx, const EventPair &p)
+{
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) != cudaSuccess || cudaEventElapsedTime(&ms, p.a, p.b) != cudaSuccess) return;
+    if (p.kind == 0) {
+        ctx->stats.iterate_ms += ms;
+        ctx->stats.level_iterate_ms[std::min(p.level, TVL1_MAX_LEVELS - 1)] += ms;
+    } else if (p.kind == 1) ctx->stats.warp_ms += ms;
+    else ctx->stats.total_ms += ms;
+}
 
 void resolve_events(tvl1_ctx *ctx)
 {
     for (auto &p : ctx->ev_used) {
-        float ms = 0.f;
-        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
-            if (p.kind == 0) {
-                ctx->stats.iterate_ms += ms;
-                ctx->stats.level_iterate_ms[std::min(p.level, TVL1_MAX_LEVELS - 1)] += ms;
-            }
-            else if (p.kind == 1) ctx->stats.warp_ms += ms;
-            else ctx->stats.total_ms += ms;
-        }
+        add_span_time(ctx, p);
         ctx->ev_pool.push_back(p.a);
         ctx->ev_pool.push_back(p.b);
     }
@@ -250,9 +292,10 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
     const Workspace &w = ctx->ws;
     IterParams P;
     P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
-    P.active_pairs = w.active; P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
-    P.px_iters = w.counters + std::min(level, TVL1_MAX_LEVELS - 1);
-    P.level = level;
+    P.loop = w.loop; P.cond = 0; P.use_cond = 0;
+    P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
+    P.px_iters = w.counters;
+    P.level = std::min(level, TVL1_MAX_LEVELS - 1);
     P.plane0 = w.plane0; P.field_stride = w.field_stride; P.set_stride = w.set_stride;
     P.lv = lv; P.parts_per_pair = w.parts_per_pair;
     P.stat_stride = w.stat_stride; P.stat_slot = stat_slot; P.max_iter = max_iter;
@@ -267,9 +310,7 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
 {
     dim3 g(ceil_div(P.lv.nx, 124), ceil_div(P.lv.ny, kIterR * kIterWY), B);
     k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
-    CKL(ctx);
-    ctx->stats.iterate_launches++;
-    ctx->stats.level_iterate_launches[std::min(P.level, TVL1_MAX_LEVELS - 1)]++;
+    CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
     return TVL1_OK;
 }
 
@@ -296,14 +337,51 @@ int launch_zero(tvl1_ctx *ctx, int s, int B, int first_field, int nfields)
     return TVL1_OK;
 }
 
-// The while loop of src/tvl1flow.cpp:113 for the whole batch: enqueue `chunk` iteration launches,
-// then read back how many pairs still iterate.  Launches for pairs that already stopped exit at
-// once, so over-shooting costs microseconds while every look costs a stream synchronisation.
+// The while loop of src/tvl1flow.cpp:113 for the whole batch, as a conditional WHILE node of the
+// solve graph: the body is one launch of the fused iteration kernel; the kernel clears the
+// condition when the last pair stops.  (default launch value 1 => at least one iteration)
+int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
+{
+    cudaStreamCaptureStatus status;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    CK(cudaStreamGetCaptureInfo_v2(ctx->stream, &status, nullptr, &g, &deps, &ndeps));
+    cudaGraphConditionalHandle h;
+    CK(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = { cudaGraphNodeTypeConditional };
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = h;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    CK(cudaGraphAddNode(&node, g, deps, ndeps, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    CK(cudaStreamBeginCaptureToGraph(ctx->body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    P.cond = h;
+    P.use_cond = 1;
+    std::swap(ctx->stream, ctx->body_stream);
+    const int rc = launch_iterate(ctx, P, B);
+    std::swap(ctx->stream, ctx->body_stream);
+    cudaGraph_t ended = nullptr;
+    CK(cudaStreamEndCapture(ctx->body_stream, &ended));
+    TRY(rc);
+    CK(cudaStreamUpdateCaptureDependencies(ctx->stream, &node, 1, cudaStreamSetCaptureDependencies));
+    return TVL1_OK;
+}
+
+// Host-driven variant of the same loop (TVL1_NO_GRAPH=1, and the per-kernel hooks): enqueue a
+// chunk of iteration launches, then read back how many pairs still iterate.  Launches for pairs
+// that already stopped exit at once, so over-shooting costs microseconds while every look costs
+// a stream synchronisation; the first chunk is the count the previous warp step needed.
 int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint)
 {
+    if (ctx->capturing) {
+        Span sp(ctx, 0, P.level);
+        return add_while_loop(ctx, P, B);
+    }
     int launched = 0;
     int chunk = std::max(1, std::min(chunk_hint, P.max_iter));
-    int used = 0;
     while (launched < P.max_iter) {
         const int k = std::min(chunk, P.max_iter - launched);
         {
@@ -311,15 +389,13 @@ int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint)
             for (int i = 0; i < k; i++) TRY(launch_iterate(ctx, P, B));
         }
         launched += k;
-        if (launched >= P.max_iter) { used = launched; break; }   // every pair hit the cap or stopped
-        CK(cudaMemcpyAsync(ctx->h_active, ctx->ws.active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_loop, ctx->ws.loop, sizeof(LoopCtl), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->stats.host_syncs++;
-        used = launched;
-        if (*ctx->h_active == 0) break;
-        chunk = std::max(4, chunk / 2);
+        if (ctx->h_loop->active_pairs == 0) break;
+        chunk = std::max(2, chunk_hint / 4);
     }
-    chunk_hint = used;
+    chunk_hint = std::max(1, ctx->h_loop->max_n);
     return TVL1_OK;
 }
 
@@ -333,7 +409,7 @@ int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base
             Span sp(ctx, 1);
             TRY(launch_warp(ctx, s, B));                                    // :84, :94-109
         }
-        k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.active, B);   // :111-112
+        k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.loop, B);   // :111-112
         CKL(ctx);
         const IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations, s);
         TRY(run_iterations(ctx, P, B, chunk_hint));                         // :113-182
@@ -357,7 +433,7 @@ void reset_stats(tvl1_ctx *ctx) { ctx->stats = tvl1_stats{}; }
 int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_out)
 {
     const Workspace &w = ctx->ws;
-    unsigned long long c[TVL1_MAX_LEVELS] = { 0 };
+    unsigned long long c[2 * TVL1_MAX_LEVELS] = { 0 };
     CK(cudaMemcpyAsync(c, w.counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
     if (iters_out)
         CK(cudaMemcpy2DAsync(iters_out, sizeof(int) * nstat, w.stat_iters, sizeof(int) * w.stat_stride,
@@ -369,6 +445,69 @@ int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_ou
     for (int l = 0; l < TVL1_MAX_LEVELS; l++) {
         ctx->stats.pixel_iterations += c[l];
         ctx->stats.level_pixel_iterations[l] += c[l];
+        ctx->stats.iterate_launches += c[TVL1_MAX_LEVELS + l];
+        ctx->stats.level_iterate_launches[l] += c[TVL1_MAX_LEVELS + l];
+        ctx->stats.kernel_launches += c[TVL1_MAX_LEVELS + l];
+    }
+    return TVL1_OK;
+}
+
+// src/tvl1flow.cpp:278-310 (multiscale) or the single level of Dual_TVL1_optic_flow.
+int enqueue_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multiscale)
+{
+    const Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const int ns = multiscale ? prm.nscales : 1;
+    if (multiscale) TRY(launch_zero(ctx, ns - 1, B, F_U1, 2));
+    int chunk_hint = 16;
+    for (int s = ns - 1; s >= 0; s--) {
+        TRY(run_level(ctx, s, B, prm, (ns - 1 - s) * prm.warps, chunk_hint));
+        if (!s) break;
+        const Level &c = w.lv[s], &f = w.lv[s - 1];
+        dim3 g(ceil_div(f.nx, 32), ceil_div(f.ny, 8), 2 * B);
+        k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                                  c, f, (double) f.nx / c.nx, (double) f.ny / c.ny,
+                                                  (float) (1.0 / prm.zfactor));
+        CKL(ctx);
+        k_flip_cur<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, B);
+        CKL(ctx);
+        chunk_hint = std::max(chunk_hint, 4);
+    }
+    return TVL1_OK;
+}
+
+bool same_params(const tvl1_params &a, const tvl1_params &b)
+{
+    return a.tau == b.tau && a.lambda == b.lambda && a.theta == b.theta && a.nscales == b.nscales &&
+           a.zfactor == b.zfactor && a.warps == b.warps && a.epsilon == b.epsilon;
+}
+
+int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multiscale)
+{
+    if (!ctx->use_graph) return enqueue_coarse_to_fine(ctx, B, prm, multiscale);
+    SolveGraph &sg = ctx->sg;
+    if (!sg.exec || !same_params(sg.prm, prm) || sg.multiscale != multiscale || sg.profiling != ctx->profiling) {
+        free_graph(sg, ctx->ev_pool);
+        sg.prm = prm; sg.multiscale = multiscale; sg.profiling = ctx->profiling;
+        const tvl1_stats keep = ctx->stats;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+        ctx->capturing = true;
+        const int rc = enqueue_coarse_to_fine(ctx, B, prm, multiscale);
+        ctx->capturing = false;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &sg.graph);
+        sg.static_launches = ctx->stats.kernel_launches - keep.kernel_launches;
+        sg.pixel_warps = ctx->stats.pixel_warps - keep.pixel_warps;
+        ctx->stats = keep;
+        if (rc != TVL1_OK) { free_graph(sg, ctx->ev_pool); return rc; }
+        CK(e);
+        CK(cudaGraphInstantiate(&sg.exec, sg.graph, 0));
+    }
+    CK(cudaGraphLaunch(sg.exec, ctx->stream));
+    ctx->stats.kernel_launches += sg.static_launches;
+    ctx->stats.pixel_warps += sg.pixel_warps;
+    if (!sg.events.empty()) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (const auto &p : sg.events) add_span_time(ctx, p);
     }
     return TVL1_OK;
 }
@@ -390,7 +529,7 @@ int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, flo
     for (int s = 1; s < ns; s++) TRY(check_sigma(ctx, zsigma, w.lv[s - 1].nx, zoom));
 
     Span total(ctx, 2);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
 
@@ -421,22 +560,7 @@ int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, flo
         }
     }
 
-    // coarse-to-fine, src/tvl1flow.cpp:278-310
-    TRY(launch_zero(ctx, ns - 1, B, F_U1, 2));
-    int chunk_hint = 16;
-    for (int s = ns - 1; s >= 0; s--) {
-        TRY(run_level(ctx, s, B, prm, (ns - 1 - s) * prm.warps, chunk_hint));
-        if (!s) break;
-        const Level &c = w.lv[s], &f = w.lv[s - 1];
-        dim3 g(ceil_div(f.nx, 32), ceil_div(f.ny, 8), 2 * B);
-        k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
-                                                  c, f, (double) f.nx / c.nx, (double) f.ny / c.ny,
-                                                  (float) (1.0 / prm.zfactor));
-        CKL(ctx);
-        k_flip_cur<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, B);
-        CKL(ctx);
-        chunk_hint = std::max(chunk_hint, 8);
-    }
+    TRY(run_coarse_to_fine(ctx, B, prm, true));
     {
         dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
         k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
@@ -456,7 +580,7 @@ int run_single_scale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, f
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
     Span total(ctx, 2);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
@@ -467,8 +591,7 @@ int run_single_scale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, f
     k_import_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
                                              w.lv[0], du1, du2);
     CKL(ctx);
-    int chunk_hint = 16;
-    TRY(run_level(ctx, 0, B, prm, 0, chunk_hint));
+    TRY(run_coarse_to_fine(ctx, B, prm, false));
     k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
                                              w.lv[0], du1, du2);
     CKL(ctx);
@@ -617,12 +740,14 @@ int tvl1_create(int device, tvl1_ctx **out)
     ctx->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMallocHost(&ctx->h_active, sizeof(int))) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&ctx->body_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMallocHost(&ctx->h_loop, sizeof(LoopCtl))) != cudaSuccess) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
         delete ctx;
         return TVL1_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     *out = ctx;
     return TVL1_OK;
 }
@@ -632,12 +757,14 @@ void tvl1_destroy(tvl1_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(ctx->ws);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->stage_in[i]); cudaFree(ctx->stage_out[i]); }
     for (int i = 0; i < 4; i++) cudaFree(ctx->stage_f32[i]);
     resolve_events(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    if (ctx->h_active) cudaFreeHost(ctx->h_active);
+    if (ctx->h_loop) cudaFreeHost(ctx->h_loop);
+    if (ctx->body_stream) cudaStreamDestroy(ctx->body_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -897,7 +1024,7 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
     if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
     CKL(ctx);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
     float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
     for (int f = 0; f < 6; f++) {
@@ -918,7 +1045,7 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
     prm.tau = tau; prm.lambda = lambda; prm.theta = theta; prm.epsilon = 0.0;
     int cur = 0;
     for (int k = 0; k < iters; k++) {
-        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.active, 1);
+        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.loop, 1);
         CKL(ctx);
         const IterParams P = iter_params(ctx, w.lv[0], prm, 0, 1);   // max_iter 1: record and stop
         TRY(launch_iterate(ctx, P, 1));
@@ -946,7 +1073,7 @@ int tvl1_bench_iterate(tvl1_ctx *ctx, int npairs, int nx, int ny, int launches, 
     CKL(ctx);
     k_init_ctl<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.mm, npairs);
     CKL(ctx);
-    k_begin_warp<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.active, npairs);
+    k_begin_warp<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.loop, npairs);
     CKL(ctx);
     tvl1_params prm;
     tvl1_default_params(&prm);
