@@ -12,6 +12,7 @@
 //   * per-warp constants: consts[field][b][plane0], field in {I1wx, I1wy, rho_c, grad}.
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 namespace tvl1 {
@@ -136,7 +137,7 @@ __global__ void k_minmax(const float *__restrict__ in0, const float *__restrict_
 template <int D>
 __global__ void __launch_bounds__(256)
 k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__restrict__ out,
-        int out_pitch, size_t out_stride, int nx, int ny, int onx, int ony, GaussTaps taps,
+        int out_pitch, size_t out_stride, int nx, int ny, int onx, int ony, const GaussTaps taps,
         const unsigned int *__restrict__ mm, int B)
 {
     constexpr int TW = 64 / D, TH = 32 / D;        // output tile
@@ -144,7 +145,9 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
     constexpr int RMAX = kMaxTaps - 1;
     __shared__ float s_in[(IH + 2 * RMAX)][IW + 2 * RMAX + 1];
     __shared__ float s_row[(IH + 2 * RMAX)][TW + 1];
+    __shared__ float s_w[kMaxTaps];
 
+    const int tx = threadIdx.x, ty = threadIdx.y;  // block (32, 8)
     const int r = taps.size - 1;
     const int z = blockIdx.z;
     const float *src = in + (size_t) z * in_stride;
@@ -153,44 +156,56 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
     const int ix0 = ox0 * D - r, iy0 = oy0 * D - r;
     const int iw = IW + 2 * r - (D - 1), ih = IH + 2 * r - (D - 1);
 
+    if (ty == 0) {
+#pragma unroll
+        for (int i = 0; i < kMaxTaps; i++)
+            if (tx == i) s_w[i] = taps.w[i];
+    }
     float mn = 0.f, den = 0.f;
     if (mm) {
         mn = ord2f(mm[2 * (z % B)]);
         den = ord2f(mm[2 * (z % B) + 1]) - mn;
     }
 
-    for (int t = threadIdx.x; t < iw * ih; t += blockDim.x) {
-        const int ly = t / iw, lx = t - ly * iw;
-        int gx = ix0 + lx, gy = iy0 + ly;
-        gx = gx < 0 ? -gx : (gx >= nx ? 2 * nx - 1 - gx : gx);
+    for (int ly = ty; ly < ih; ly += 8) {
+        int gy = iy0 + ly;
         gy = gy < 0 ? -gy : (gy >= ny ? 2 * ny - 1 - gy : gy);
-        gx = clampi(gx, 0, nx - 1);   // only reachable for tiles hanging over the image edge
-        gy = clampi(gy, 0, ny - 1);
-        float v = __ldg(src + (size_t) gy * in_pitch + gx);
-        if (den > 0.f) v = 255.0f * (v - mn) / den;
-        s_in[ly][lx] = v;
+        gy = clampi(gy, 0, ny - 1);   // only reachable for tiles hanging over the image edge
+        const float *row = src + (size_t) gy * in_pitch;
+        for (int lx = tx; lx < iw; lx += 32) {
+            int gx = ix0 + lx;
+            gx = gx < 0 ? -gx : (gx >= nx ? 2 * nx - 1 - gx : gx);
+            gx = clampi(gx, 0, nx - 1);
+            float v = __ldg(row + gx);
+            if (den > 0.f) v = 255.0f * (v - mn) / den;
+            s_in[ly][lx] = v;
+        }
     }
     __syncthreads();
 
     // row pass: every input row of the tile, output columns only
-    for (int t = threadIdx.x; t < TW * ih; t += blockDim.x) {
-        const int ly = t / TW, ox = t - ly * TW;
-        const int c = ox * D + r;
-        float sum = taps.w[0] * s_in[ly][c];
-        for (int j = 1; j <= r; j++) sum += taps.w[j] * (s_in[ly][c - j] + s_in[ly][c + j]);
-        s_row[ly][ox] = sum;
+    for (int ly = ty; ly < ih; ly += 8) {
+        for (int ox = tx; ox < TW; ox += 32) {
+            const int c = ox * D + r;
+            float sum = s_w[0] * s_in[ly][c];
+            for (int j = 1; j <= r; j++) sum += s_w[j] * (s_in[ly][c - j] + s_in[ly][c + j]);
+            s_row[ly][ox] = sum;
+        }
     }
     __syncthreads();
 
     // column pass on output rows
-    for (int t = threadIdx.x; t < TW * TH; t += blockDim.x) {
-        const int oy = t / TW, ox = t - oy * TW;
-        const int gx = ox0 + ox, gy = oy0 + oy;
-        if (gx >= onx || gy >= ony) continue;
+    for (int oy = ty; oy < TH; oy += 8) {
+        const int gy = oy0 + oy;
+        if (gy >= ony) break;
         const int c = oy * D + r;
-        float sum = taps.w[0] * s_row[c][ox];
-        for (int j = 1; j <= r; j++) sum += taps.w[j] * (s_row[c - j][ox] + s_row[c + j][ox]);
-        dst[(size_t) gy * out_pitch + gx] = sum;
+        for (int ox = tx; ox < TW; ox += 32) {
+            const int gx = ox0 + ox;
+            if (gx >= onx) break;
+            float sum = s_w[0] * s_row[c][ox];
+            for (int j = 1; j <= r; j++) sum += s_w[j] * (s_row[c - j][ox] + s_row[c + j][ox]);
+            dst[(size_t) gy * out_pitch + gx] = sum;
+        }
     }
 }
 
@@ -244,20 +259,64 @@ __global__ void k_resample(const float *__restrict__ in, int in_pitch, size_t in
 
 // zoom_in of both flow components of every pair between the ping-pong state sets:
 // reads set cur (coarse level), writes set cur^1 (fine level), then k_flip_cur flips.
-__global__ void k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride,
-                               size_t set_stride, const PairCtl *__restrict__ ctl, Level coarse,
-                               Level fine, double fx, double fy, float scale)
+// One CTA makes a 64x16 tile of the fine level; the coarse footprint of the tile (index-clamped,
+// so the gather below needs no boundary logic) is staged in shared memory for both components.
+constexpr int kZiTW = 64, kZiTH = 16, kZiCW = kZiTW + 8, kZiCH = kZiTH + 8;
+
+__global__ void __launch_bounds__(256)
+k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
+               const PairCtl *__restrict__ ctl, Level coarse, Level fine, double fx, double fy,
+               float scale)
 {
-    const int j1 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i1 = blockIdx.y * blockDim.y + threadIdx.y;
-    if (j1 >= fine.nx || i1 >= fine.ny) return;
-    const int b = blockIdx.z >> 1, comp = blockIdx.z & 1;
+    __shared__ float s_c[2][kZiCH][kZiCW];
+    const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
+    const int b = blockIdx.z;
     const int cur = ctl[b].cur;
-    const float *src = state + (size_t) cur * set_stride + (size_t) comp * field_stride + (size_t) b * plane0;
-    float *dst = state + (size_t) (cur ^ 1) * set_stride + (size_t) comp * field_stride + (size_t) b * plane0;
-    const double j2 = j1 / fx, i2 = i1 / fy;
-    dst[(size_t) i1 * fine.pitch + j1] =
-        bicubic_clamped(src, coarse.pitch, coarse.nx, coarse.ny, j2, i2) * scale;
+    const float *src = state + (size_t) cur * set_stride + (size_t) b * plane0;
+    float *dst = state + (size_t) (cur ^ 1) * set_stride + (size_t) b * plane0;
+    const int X0 = blockIdx.x * kZiTW, Y0 = blockIdx.y * kZiTH;
+    const int X1 = min(X0 + kZiTW, fine.nx) - 1, Y1 = min(Y0 + kZiTH, fine.ny) - 1;
+    // coarse footprint: taps x-1 .. x+2 around x = (int)(j1 / fx), monotone in j1
+    const int xlo = (int) (X0 / fx) - 1, xhi = (int) (X1 / fx) + 2;
+    const int ylo = (int) (Y0 / fy) - 1, yhi = (int) (Y1 / fy) + 2;
+    const int cw = xhi - xlo + 1, ch = yhi - ylo + 1;
+    const bool staged = (cw <= kZiCW) && (ch <= kZiCH);   // always true when fx, fy >= 1
+    if (staged) {
+        for (int ly = ty; ly < ch; ly += 8) {
+            const size_t ro = (size_t) clampi(ylo + ly, 0, coarse.ny - 1) * coarse.pitch;
+            for (int lx = tx; lx < cw; lx += 32) {
+                const size_t o = ro + clampi(xlo + lx, 0, coarse.nx - 1);
+                s_c[0][ly][lx] = __ldg(src + o);
+                s_c[1][ly][lx] = __ldg(src + field_stride + o);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int j1 = X0 + tx + 32 * (q & 1), i1 = Y0 + ty + 8 * (q >> 1);
+        if (j1 >= fine.nx || i1 >= fine.ny) continue;
+        const double j2 = j1 / fx, i2 = i1 / fy;
+        const size_t o = (size_t) i1 * fine.pitch + j1;
+        if (!staged) {
+            dst[o] = bicubic_clamped(src, coarse.pitch, coarse.nx, coarse.ny, j2, i2) * scale;
+            dst[field_stride + o] =
+                bicubic_clamped(src + field_stride, coarse.pitch, coarse.nx, coarse.ny, j2, i2) * scale;
+            continue;
+        }
+        const int x = clampi((int) j2, 0, coarse.nx - 1), y = clampi((int) i2, 0, coarse.ny - 1);
+        const float fxr = (float) (j2 - x), fyr = (float) (i2 - y);
+        const int cx = x - 1 - xlo, cy = y - 1 - ylo;
+#pragma unroll
+        for (int comp = 0; comp < 2; comp++) {
+            float col[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+                col[a] = cubic_cell(s_c[comp][cy][cx + a], s_c[comp][cy + 1][cx + a],
+                                    s_c[comp][cy + 2][cx + a], s_c[comp][cy + 3][cx + a], fyr);
+            dst[(size_t) comp * field_stride + o] = cubic_cell(col[0], col[1], col[2], col[3], fxr) * scale;
+        }
+    }
 }
 
 __global__ void k_flip_cur(PairCtl *ctl, int B)
@@ -425,65 +484,126 @@ __device__ __forceinline__ void keys_weights(float t, float w[4])
 // bicubic weights.  With border_out = true the result is non-zero iff
 // 1 <= (int)(j+u1) <= nx-3 and 1 <= (int)(i+u2) <= ny-3 (all three warps share this test);
 // (int) truncation of the non-negative coordinate equals j + floor(u1), formed exactly.
-__device__ __forceinline__ void warp_pixel(const float *__restrict__ I1, int pitch, int nx, int ny,
-                                           int j, int i, float u1, float u2, float I0v,
-                                           float &Ix, float &Iy, float &rho, float &grad)
+// `fetch(r, c)` returns I1 at row y-2+r, column x-2+c with index clamping already applied.
+template <class Fetch>
+__device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, float &w, float &wx, float &wy)
 {
-    const float fu = floorf(u1), fv = floorf(u2);
-    const float xf = (float) j + fu, yf = (float) i + fv;
-    float w = 0.f, wx = 0.f, wy = 0.f;
-    if (xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3)) {
-        const int x = (int) xf, y = (int) yf;
-        float ax[4], ay[4];
-        keys_weights(u1 - fu, ax);
-        keys_weights(u2 - fv, ay);
-        const int xm2 = max(x - 2, 0), xp3 = min(x + 3, nx - 1);
-        float rowI[6];   // x-interpolated I1 on rows y-2 .. y+3 (outer rows index-clamped)
-        float accx = 0.f;
+    float ax[4], ay[4];
+    keys_weights(tx, ax);
+    keys_weights(ty, ay);
+    float rowI[6];   // x-interpolated I1 on rows y-2 .. y+3
+    float accx = 0.f;
 #pragma unroll
-        for (int r = 0; r < 6; r++) {
-            const int yy = clampi(y - 2 + r, 0, ny - 1);
-            const float *row = I1 + (size_t) yy * pitch;
-            const float c1 = __ldg(row + x - 1), c2 = __ldg(row + x), c3 = __ldg(row + x + 1),
-                        c4 = __ldg(row + x + 2);
-            rowI[r] = ax[0] * c1 + ax[1] * c2 + ax[2] * c3 + ax[3] * c4;
-            if (r >= 1 && r <= 4) {
-                const float c0 = __ldg(row + xm2), c5 = __ldg(row + xp3);
-                const float dxr = ax[0] * (c2 - c0) + ax[1] * (c3 - c1) + ax[2] * (c4 - c2) + ax[3] * (c5 - c3);
-                accx += ay[r - 1] * dxr;
-            }
+    for (int r = 0; r < 6; r++) {
+        const float c1 = fetch(r, 1), c2 = fetch(r, 2), c3 = fetch(r, 3), c4 = fetch(r, 4);
+        rowI[r] = ax[0] * c1 + ax[1] * c2 + ax[2] * c3 + ax[3] * c4;
+        if (r >= 1 && r <= 4) {
+            const float c0 = fetch(r, 0), c5 = fetch(r, 5);
+            const float dxr = ax[0] * (c2 - c0) + ax[1] * (c3 - c1) + ax[2] * (c4 - c2) + ax[3] * (c5 - c3);
+            accx += ay[r - 1] * dxr;
         }
-        w = ay[0] * rowI[1] + ay[1] * rowI[2] + ay[2] * rowI[3] + ay[3] * rowI[4];
-        wx = 0.5f * accx;
-        wy = 0.5f * (ay[0] * (rowI[2] - rowI[0]) + ay[1] * (rowI[3] - rowI[1]) +
-                     ay[2] * (rowI[4] - rowI[2]) + ay[3] * (rowI[5] - rowI[3]));
     }
-    Ix = wx;
-    Iy = wy;
-    grad = wx * wx + wy * wy;
-    rho = w - wx * u1 - wy * u2 - I0v;
+    w = ay[0] * rowI[1] + ay[1] * rowI[2] + ay[2] * rowI[3] + ay[3] * rowI[4];
+    wx = 0.5f * accx;
+    wy = 0.5f * (ay[0] * (rowI[2] - rowI[0]) + ay[1] * (rowI[3] - rowI[1]) +
+                 ay[2] * (rowI[4] - rowI[2]) + ay[3] * (rowI[5] - rowI[3]));
 }
+
+// Shared-memory-staged gather: a CTA owns a 64x16 tile of output pixels.  The flow is smooth, so
+// the 6x6 neighbourhoods of all its sample points fall into a small bounding box of I1; the CTA
+// reduces that box (min/max of the integer sample positions of its valid pixels), stages it with
+// coalesced, index-clamped loads, and gathers from shared memory.  A tile whose box does not fit
+// (flow range > ~30 px inside one tile) gathers from global memory instead (same arithmetic).
+constexpr int kWarpTW = 64, kWarpTH = 16, kWarpBox = 5120;
 
 __global__ void __launch_bounds__(256)
 k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_stride,
        const float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
        const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv)
 {
-    const int j = blockIdx.x * 32 + threadIdx.x;
-    const int i = blockIdx.y * 8 + threadIdx.y;
-    if (j >= lv.nx || i >= lv.ny) return;
+    __shared__ float s_box[kWarpBox];
+    __shared__ int s_red[8][4];
+    const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
     const int b = blockIdx.z;
-    const size_t p = (size_t) i * lv.pitch + j;
-    const float *u = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0 + p;
-    const float u1 = __ldg(u), u2 = __ldg(u + field_stride);
-    float Ix, Iy, rho, grad;
-    warp_pixel(I1 + (size_t) b * img_stride, lv.pitch, lv.nx, lv.ny, j, i, u1, u2,
-               __ldg(I0 + (size_t) b * img_stride + p), Ix, Iy, rho, grad);
-    float *c = consts + (size_t) b * plane0 + p;
-    c[(size_t) C_IX * field_stride] = Ix;
-    c[(size_t) C_IY * field_stride] = Iy;
-    c[(size_t) C_RHO * field_stride] = rho;
-    c[(size_t) C_GRAD * field_stride] = grad;
+    const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
+    const float *img1 = I1 + (size_t) b * img_stride;
+    const float *u = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0;
+    const int X0 = blockIdx.x * kWarpTW, Y0 = blockIdx.y * kWarpTH;
+
+    float u1[4], u2[4], ftx[4], fty[4];
+    int sx[4], sy[4];
+    bool inside[4], valid[4];
+    int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
+        inside[q] = j < nx && i < ny;
+        valid[q] = false;
+        u1[q] = u2[q] = 0.f;
+        if (inside[q]) {
+            const size_t p = (size_t) i * pitch + j;
+            u1[q] = __ldg(u + p);
+            u2[q] = __ldg(u + field_stride + p);
+            const float fu = floorf(u1[q]), fv = floorf(u2[q]);
+            const float xf = (float) j + fu, yf = (float) i + fv;
+            valid[q] = xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
+            if (valid[q]) {
+                sx[q] = (int) xf; sy[q] = (int) yf;
+                ftx[q] = u1[q] - fu; fty[q] = u2[q] - fv;
+                bx0 = min(bx0, sx[q]); bx1 = max(bx1, sx[q]);
+                by0 = min(by0, sy[q]); by1 = max(by1, sy[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+        bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+        by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+        by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    if (tx == 0) { s_red[ty][0] = bx0; s_red[ty][1] = bx1; s_red[ty][2] = by0; s_red[ty][3] = by1; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        bx0 = min(bx0, s_red[w][0]); bx1 = max(bx1, s_red[w][1]);
+        by0 = min(by0, s_red[w][2]); by1 = max(by1, s_red[w][3]);
+    }
+    const bool any = bx1 >= bx0;
+    bx0 -= 2; by0 -= 2;
+    const int bw = any ? bx1 + 3 - bx0 + 1 : 0, bh = any ? by1 + 3 - by0 + 1 : 0;
+    const bool staged = any && (long long) bw * bh <= kWarpBox;
+    if (staged) {
+        for (int ly = ty; ly < bh; ly += 8) {
+            const float *row = img1 + (size_t) clampi(by0 + ly, 0, ny - 1) * pitch;
+            for (int lx = tx; lx < bw; lx += 32) s_box[ly * bw + lx] = __ldg(row + clampi(bx0 + lx, 0, nx - 1));
+        }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (!inside[q]) continue;
+        const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
+        const size_t p = (size_t) i * pitch + j;
+        float w = 0.f, wx = 0.f, wy = 0.f;
+        if (valid[q]) {
+            if (staged) {
+                const float *base = s_box + (sy[q] - 2 - by0) * bw + (sx[q] - 2 - bx0);
+                warp_gather([&](int r, int c) { return base[r * bw + c]; }, ftx[q], fty[q], w, wx, wy);
+            } else {
+                const int x = sx[q], y = sy[q];
+                warp_gather([&](int r, int c) {
+                    return __ldg(img1 + (size_t) clampi(y - 2 + r, 0, ny - 1) * pitch + clampi(x - 2 + c, 0, nx - 1));
+                }, ftx[q], fty[q], w, wx, wy);
+            }
+        }
+        float *c = consts + (size_t) b * plane0 + p;
+        c[(size_t) C_IX * field_stride] = wx;
+        c[(size_t) C_IY * field_stride] = wy;
+        c[(size_t) C_RHO * field_stride] = w - wx * u1[q] - wy * u2[q] - __ldg(I0 + (size_t) b * img_stride + p);
+        c[(size_t) C_GRAD * field_stride] = wx * wx + wy * wy;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

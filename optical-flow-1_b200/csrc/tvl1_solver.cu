@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace tvl1;
@@ -80,6 +81,8 @@ struct tvl1_ctx {
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool capturing = false;
     SolveGraph sg;
+    tvl1_ctx *lane2 = nullptr;               // sibling context for copy/compute overlap (host-buffer batches)
+    bool two_lanes = true;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<EventPair> ev_used;
     // staging for the host-buffer entry points
@@ -275,11 +278,11 @@ int launch_gauss(tvl1_ctx *ctx, int D, const float *in, int in_pitch, size_t in_
     cudaStream_t st = ctx->stream;
     if (D == 1) {
         dim3 g(ceil_div(onx, 64), ceil_div(ony, 32), nimg);
-        k_gauss<1><<<g, 256, 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
+        k_gauss<1><<<g, dim3(32, 8), 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
                                       onx, ony, taps, mm, B);
     } else {
         dim3 g(ceil_div(onx, 32), ceil_div(ony, 16), nimg);
-        k_gauss<2><<<g, 256, 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
+        k_gauss<2><<<g, dim3(32, 8), 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
                                       onx, ony, taps, mm, B);
     }
     CKL(ctx);
@@ -318,7 +321,7 @@ int launch_warp(tvl1_ctx *ctx, int s, int B)
 {
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
-    dim3 g(ceil_div(l.nx, 32), ceil_div(l.ny, 8), B);
+    dim3 g(ceil_div(l.nx, kWarpTW), ceil_div(l.ny, kWarpTH), B);
     k_warp<<<g, dim3(32, 8), 0, ctx->stream>>>(w.I0(s), w.I1(s), w.plane(s), w.state, w.plane0,
                                                w.field_stride, w.set_stride, w.ctl, w.consts, l);
     CKL(ctx);
@@ -464,7 +467,7 @@ int enqueue_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool mu
         TRY(run_level(ctx, s, B, prm, (ns - 1 - s) * prm.warps, chunk_hint));
         if (!s) break;
         const Level &c = w.lv[s], &f = w.lv[s - 1];
-        dim3 g(ceil_div(f.nx, 32), ceil_div(f.ny, 8), 2 * B);
+        dim3 g(ceil_div(f.nx, kZiTW), ceil_div(f.ny, kZiTH), B);
         k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
                                                   c, f, (double) f.nx / c.nx, (double) f.ny / c.ny,
                                                   (float) (1.0 / prm.zfactor));
@@ -635,7 +638,73 @@ int check_common(tvl1_ctx *ctx, const void *a, const void *b, const void *c, con
     return TVL1_OK;
 }
 
-// host-buffer driver shared by the f32/f64, multiscale/single-scale entry points
+// One chunk of <= max_batch pairs through one lane (context): H2D, solve, D2H, all on the lane's
+// stream.
+template <typename T>
+int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1, T *u2, int nx, int ny,
+                const tvl1_params *prm, int *iters_out, double *errs_out, bool multiscale, int nstat)
+{
+    const bool f64 = sizeof(T) == 8;
+    const size_t n = (size_t) nx * ny;
+    cudaStream_t st = ctx->stream;
+    const size_t cnt = (size_t) B * n, off = (size_t) first * n;
+    CK(cudaMemcpyAsync(ctx->stage_in[0], I0 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->stage_in[1], I1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+    float *d0, *d1, *o0, *o1;
+    const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
+    if (f64) {
+        d0 = ctx->stage_f32[0]; d1 = ctx->stage_f32[1]; o0 = ctx->stage_f32[2]; o1 = ctx->stage_f32[3];
+        k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[0], d0, cnt);
+        CKL(ctx);
+        k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[1], d1, cnt);
+        CKL(ctx);
+    } else {
+        d0 = (float *) ctx->stage_in[0]; d1 = (float *) ctx->stage_in[1];
+        o0 = (float *) ctx->stage_out[0]; o1 = (float *) ctx->stage_out[1];
+    }
+    if (!multiscale) {   // u1,u2 are in/out: the initial flow is used (src/tvl1flow.cpp:94)
+        CK(cudaMemcpyAsync(ctx->stage_out[0], u1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->stage_out[1], u2 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+        if (f64) {
+            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[0], o0, cnt);
+            CKL(ctx);
+            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[1], o1, cnt);
+            CKL(ctx);
+        }
+    }
+    int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
+    double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
+    if (multiscale) TRY(run_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
+    else TRY(run_single_scale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
+    if (f64) {
+        k_f32_to_f64<<<g, 256, 0, st>>>(o0, (double *) ctx->stage_out[0], cnt);
+        CKL(ctx);
+        k_f32_to_f64<<<g, 256, 0, st>>>(o1, (double *) ctx->stage_out[1], cnt);
+        CKL(ctx);
+    }
+    CK(cudaMemcpyAsync(u1 + off, ctx->stage_out[0], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(u2 + off, ctx->stage_out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+void add_stats(tvl1_stats &a, const tvl1_stats &b)
+{
+    a.kernel_launches += b.kernel_launches; a.iterate_launches += b.iterate_launches;
+    a.pixel_iterations += b.pixel_iterations; a.pixel_warps += b.pixel_warps;
+    a.iterate_ms += b.iterate_ms; a.warp_ms += b.warp_ms; a.total_ms += b.total_ms;
+    a.host_syncs += b.host_syncs;
+    for (int l = 0; l < TVL1_MAX_LEVELS; l++) {
+        a.level_pixel_iterations[l] += b.level_pixel_iterations[l];
+        a.level_iterate_launches[l] += b.level_iterate_launches[l];
+        a.level_iterate_ms[l] += b.level_iterate_ms[l];
+    }
+}
+
+// Host-buffer driver shared by the f32/f64, multiscale/single-scale entry points.  A batch larger
+// than max_batch is cut into chunks; two lanes (this context and a private sibling on the same
+// GPU, each with its own stream, workspace and host thread) take alternate chunks, so the H2D/D2H
+// copies of one chunk overlap the kernels of the other.
 template <typename T>
 int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2, int nx, int ny,
                const tvl1_params *prm, int *iters_out, double *errs_out, bool multiscale)
@@ -646,54 +715,55 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     const bool f64 = sizeof(T) == 8;
     const size_t n = (size_t) nx * ny;
     const int Bmax = std::min(npairs, ctx->max_batch);
-    TRY(ensure_stage(ctx, (size_t) Bmax * n * sizeof(T), f64));
+    const int nchunks = ceil_div(npairs, Bmax);
     const int nstat = (multiscale ? prm->nscales : 1) * prm->warps;
-    cudaStream_t st = ctx->stream;
-    for (int first = 0; first < npairs; first += Bmax) {
-        const int B = std::min(Bmax, npairs - first);
-        const size_t cnt = (size_t) B * n, off = (size_t) first * n;
-        CK(cudaMemcpyAsync(ctx->stage_in[0], I0 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->stage_in[1], I1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-        float *d0, *d1, *o0, *o1;
-        if (f64) {
-            d0 = ctx->stage_f32[0]; d1 = ctx->stage_f32[1]; o0 = ctx->stage_f32[2]; o1 = ctx->stage_f32[3];
-            const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
-            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[0], d0, cnt);
-            CKL(ctx);
-            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[1], d1, cnt);
-            CKL(ctx);
-        } else {
-            d0 = (float *) ctx->stage_in[0]; d1 = (float *) ctx->stage_in[1];
-            o0 = (float *) ctx->stage_out[0]; o1 = (float *) ctx->stage_out[1];
-        }
-        if (!multiscale) {   // u1,u2 are in/out: the initial flow is used (src/tvl1flow.cpp:94)
-            CK(cudaMemcpyAsync(ctx->stage_out[0], u1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(ctx->stage_out[1], u2 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-            if (f64) {
-                const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
-                k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[0], o0, cnt);
-                CKL(ctx);
-                k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[1], o1, cnt);
-                CKL(ctx);
+    tvl1_ctx *lanes[2] = { ctx, nullptr };
+    int nlanes = 1;
+    if (nchunks > 1 && ctx->two_lanes) {
+        if (!ctx->lane2) {
+            if (tvl1_create(ctx->device, &ctx->lane2) != TVL1_OK) {
+                ctx->err = std::string("second lane: ") + tvl1_last_error(nullptr);
+                return TVL1_ERR_CUDA;
             }
+            ctx->lane2->two_lanes = false;
         }
-        int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
-        double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
-        if (multiscale) TRY(run_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
-        else TRY(run_single_scale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
-        if (f64) {
-            const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
-            k_f32_to_f64<<<g, 256, 0, st>>>(o0, (double *) ctx->stage_out[0], cnt);
-            CKL(ctx);
-            k_f32_to_f64<<<g, 256, 0, st>>>(o1, (double *) ctx->stage_out[1], cnt);
-            CKL(ctx);
-        }
-        CK(cudaMemcpyAsync(u1 + off, ctx->stage_out[0], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(u2 + off, ctx->stage_out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        ctx->lane2->max_batch = ctx->max_batch;
+        ctx->lane2->profiling = ctx->profiling;
+        ctx->lane2->use_graph = ctx->use_graph;
+        reset_stats(ctx->lane2);
+        lanes[1] = ctx->lane2;
+        nlanes = 2;
     }
-    resolve_events(ctx);
-    return TVL1_OK;
+    for (int l = 0; l < nlanes; l++) {
+        tvl1_ctx *c = lanes[l];
+        const int rc = [&]() -> int {
+            tvl1_ctx *ctx = c;   // for CK
+            CK(cudaSetDevice(ctx->device));
+            return ensure_stage(ctx, (size_t) Bmax * n * sizeof(T), f64);
+        }();
+        if (rc != TVL1_OK) { if (c != ctx) ctx->err = c->err; return rc; }
+    }
+    int rcs[2] = { TVL1_OK, TVL1_OK };
+    auto work = [&](int l) {
+        tvl1_ctx *c = lanes[l];
+        cudaSetDevice(c->device);
+        for (int k = l; k < nchunks && rcs[l] == TVL1_OK; k += nlanes) {
+            const int first = k * Bmax, B = std::min(Bmax, npairs - first);
+            rcs[l] = solve_chunk<T>(c, first, B, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out,
+                                    multiscale, nstat);
+        }
+        resolve_events(c);
+    };
+    if (nlanes == 2) {
+        std::thread t(work, 1);
+        work(0);
+        t.join();
+        add_stats(ctx->stats, ctx->lane2->stats);
+        if (rcs[1] != TVL1_OK) { ctx->err = ctx->lane2->err; return rcs[1]; }
+    } else {
+        work(0);
+    }
+    return rcs[0];
 }
 
 // ---- RAII device scratch for the per-kernel hooks -----------------------------------------------
@@ -755,6 +825,7 @@ int tvl1_create(int device, tvl1_ctx **out)
 void tvl1_destroy(tvl1_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->lane2) { tvl1_destroy(ctx->lane2); ctx->lane2 = nullptr; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_graph(ctx->sg, ctx->ev_pool);
