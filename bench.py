@@ -285,6 +285,8 @@ def run_ours(args, rank, local_rank, world):
         "kernel_ms": it_ms, "kernel_share_of_step": it_ms / (dev_ms if dev_ms > 0 else 1),
         "per_level": per_level,
     }
+    breakdown = {k: acc[k] / args.steps for k in ("total_ms", "iterate_ms", "warp_ms", "pyramid_ms",
+                                                   "zoom_in_ms", "export_ms")}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     solver.close()
@@ -335,6 +337,7 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_base,
             "timer": {"device_ms_rank0": dev_ms, "wall_ms_rank0": wall_ms},
             "host_syncs_per_step": acc["host_syncs"] / args.steps,
+            "device_ms_per_step_by_kernel_group": breakdown,
             "e2e_matches_device_path": same,
         }
         print(json.dumps(line))

@@ -70,6 +70,9 @@ typedef struct tvl1_stats {
     double iterate_ms;                    /* device time inside iteration launches (CUDA events; 0 unless profiling on) */
     double warp_ms;                       /* device time inside warp launches (same) */
     double total_ms;                      /* device time of the whole solve (same) */
+    double pyramid_ms;                    /* min/max + normalise + blur + zoom_out (same) */
+    double zoom_in_ms;                    /* flow up-sampling between levels (same) */
+    double export_ms;                     /* flow export to the caller's dense layout (same) */
     unsigned long long host_syncs;        /* stream synchronisations issued for loop control */
     /* per pyramid level (0 = finest), iteration kernel only */
     unsigned long long level_pixel_iterations[TVL1_MAX_LEVELS];

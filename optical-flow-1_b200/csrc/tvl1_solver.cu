@@ -51,7 +51,7 @@ struct Workspace {
     float *I1(int s) const { return pyr + pyr_off[s] + (size_t) B * plane(s); }
 };
 
-struct EventPair { cudaEvent_t a, b; int kind, level; };   // kind 0 iterate, 1 warp, 2 total
+struct EventPair { cudaEvent_t a, b; int kind, level; };   // kind 0 iterate, 1 warp, 2 total, 3 pyramid, 4 zoom_in, 5 export
 
 // The coarse-to-fine part of one solve, captured once per (workspace, parameters) as a CUDA graph
 // whose primal-dual loops are conditional WHILE nodes: the device ends each loop itself
@@ -257,7 +257,10 @@ void add_span_time(tvl1_ctx *ctx, const EventPair &p)
         ctx->stats.iterate_ms += ms;
         ctx->stats.level_iterate_ms[std::min(p.level, TVL1_MAX_LEVELS - 1)] += ms;
     } else if (p.kind == 1) ctx->stats.warp_ms += ms;
-    else ctx->stats.total_ms += ms;
+    else if (p.kind == 2) ctx->stats.total_ms += ms;
+    else if (p.kind == 3) ctx->stats.pyramid_ms += ms;
+    else if (p.kind == 4) ctx->stats.zoom_in_ms += ms;
+    else ctx->stats.export_ms += ms;
 }
 
 void resolve_events(tvl1_ctx *ctx)
@@ -467,6 +470,7 @@ int enqueue_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool mu
         TRY(run_level(ctx, s, B, prm, (ns - 1 - s) * prm.warps, chunk_hint));
         if (!s) break;
         const Level &c = w.lv[s], &f = w.lv[s - 1];
+        Span zs(ctx, 4);
         dim3 g(ceil_div(f.nx, kZiTW), ceil_div(f.ny, kZiTH), B);
         k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
                                                   c, f, (double) f.nx / c.nx, (double) f.ny / c.ny,
@@ -538,6 +542,7 @@ int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, flo
 
     // normalisation + pre-smoothing, src/tvl1flow.cpp:255-259
     const size_t n = (size_t) nx * ny;
+    Span pyr(ctx, 3);
     {
         dim3 g((unsigned) std::min<size_t>((n + 2047) / 2048, 256), B);
         k_minmax<<<g, 256, 0, st>>>(dI0, dI1, n, w.mm);
@@ -563,8 +568,10 @@ int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, flo
         }
     }
 
+    pyr.end();
     TRY(run_coarse_to_fine(ctx, B, prm, true));
     {
+        Span ex(ctx, 5);
         dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
         k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
                                                  w.lv[0], du1, du2);
@@ -693,6 +700,7 @@ void add_stats(tvl1_stats &a, const tvl1_stats &b)
     a.kernel_launches += b.kernel_launches; a.iterate_launches += b.iterate_launches;
     a.pixel_iterations += b.pixel_iterations; a.pixel_warps += b.pixel_warps;
     a.iterate_ms += b.iterate_ms; a.warp_ms += b.warp_ms; a.total_ms += b.total_ms;
+    a.pyramid_ms += b.pyramid_ms; a.zoom_in_ms += b.zoom_in_ms; a.export_ms += b.export_ms;
     a.host_syncs += b.host_syncs;
     for (int l = 0; l < TVL1_MAX_LEVELS; l++) {
         a.level_pixel_iterations[l] += b.level_pixel_iterations[l];

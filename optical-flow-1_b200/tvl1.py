@@ -42,6 +42,7 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("iterate_launches", C.c_ulonglong),
                 ("pixel_iterations", C.c_ulonglong), ("pixel_warps", C.c_ulonglong),
                 ("iterate_ms", C.c_double), ("warp_ms", C.c_double), ("total_ms", C.c_double),
+                ("pyramid_ms", C.c_double), ("zoom_in_ms", C.c_double), ("export_ms", C.c_double),
                 ("host_syncs", C.c_ulonglong),
                 ("level_pixel_iterations", C.c_ulonglong * 16),
                 ("level_iterate_launches", C.c_ulonglong * 16),
