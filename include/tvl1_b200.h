@@ -137,6 +137,16 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
                      const float *grad, int nx, int ny, double tau, double lambda, double theta,
                      int iters, double *errs_out);
 
+/* The same loop body through the cluster-resident kernel (whole while loop on chip): runs until the
+ * stopping rule fires (epsilon < 0: never) or max_iter passes.  cluster = 0 picks the cluster size
+ * automatically, otherwise 1/2/4/8/16 is forced (TVL1_ERR_ARG if the level does not fit).  grad is
+ * recomputed from I1wx,I1wy on chip.  iters_out = passes done, errs_out[max_iter] = error of each. */
+int tvl1_iterate_resident_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12, float *p21,
+                              float *p22, const float *rho_c, const float *I1wx, const float *I1wy,
+                              int nx, int ny, double tau, double lambda, double theta, double epsilon,
+                              int max_iter, int cluster, int *iters_out, double *errs_out,
+                              int *cluster_out);
+
 /* -- bench hook: the fused iteration kernel alone on synthetic device-resident state -------- */
 /* Runs `launches` iteration launches over `npairs` pairs of nx*ny (state and constants are
  * seeded pseudo-random, resident in HBM) and returns the CUDA-event time of those launches. */

@@ -12,6 +12,7 @@
 //   * per-warp constants: consts[field][b][plane0], field in {I1wx, I1wy, rho_c, grad}.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <limits.h>
 #include <stdint.h>
 
@@ -484,6 +485,13 @@ __device__ __forceinline__ void keys_weights(float t, float w[4])
 // bicubic weights.  With border_out = true the result is non-zero iff
 // 1 <= (int)(j+u1) <= nx-3 and 1 <= (int)(i+u2) <= ny-3 (all three warps share this test);
 // (int) truncation of the non-negative coordinate equals j + floor(u1), formed exactly.
+// |grad I1w|^2 (src/tvl1flow.cpp:100-104) with a fixed evaluation order, so that every kernel that
+// needs it (stored by k_warp, recomputed by the cluster-resident iteration kernel) agrees bitwise.
+__device__ __forceinline__ float grad_of(float ix, float iy)
+{
+    return __fmaf_rn(ix, ix, __fmul_rn(iy, iy));
+}
+
 // `fetch(r, c)` returns I1 at row y-2+r, column x-2+c with index clamping already applied.
 template <class Fetch>
 __device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, float &w, float &wx, float &wy)
@@ -491,6 +499,8 @@ __device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, flo
     float ax[4], ay[4];
     keys_weights(tx, ax);
     keys_weights(ty, ay);
+    // x-derivative taps: sum_a ax[a] * (c[a+3] - c[a+1]) regrouped per column
+    const float d0 = -ax[0], d1 = -ax[1], d2 = ax[0] - ax[2], d3 = ax[1] - ax[3], d4 = ax[2], d5 = ax[3];
     float rowI[6];   // x-interpolated I1 on rows y-2 .. y+3
     float accx = 0.f;
 #pragma unroll
@@ -499,7 +509,7 @@ __device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, flo
         rowI[r] = ax[0] * c1 + ax[1] * c2 + ax[2] * c3 + ax[3] * c4;
         if (r >= 1 && r <= 4) {
             const float c0 = fetch(r, 0), c5 = fetch(r, 5);
-            const float dxr = ax[0] * (c2 - c0) + ax[1] * (c3 - c1) + ax[2] * (c4 - c2) + ax[3] * (c5 - c3);
+            const float dxr = d0 * c0 + d1 * c1 + d2 * c2 + d3 * c3 + d4 * c4 + d5 * c5;
             accx += ay[r - 1] * dxr;
         }
     }
@@ -516,7 +526,7 @@ __device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, flo
 // (flow range > ~30 px inside one tile) gathers from global memory instead (same arithmetic).
 constexpr int kWarpTW = 64, kWarpTH = 16, kWarpBox = 5120;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_stride,
        const float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
        const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv)
@@ -530,9 +540,11 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
     const float *u = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0;
     const int X0 = blockIdx.x * kWarpTW, Y0 = blockIdx.y * kWarpTH;
 
-    float u1[4], u2[4], ftx[4], fty[4];
+    float u1[4], u2[4], ftx[4], fty[4], i0v[4];
     int sx[4], sy[4];
     bool inside[4], valid[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { i0v[q] = 0.f; sx[q] = sy[q] = 0; ftx[q] = fty[q] = 0.f; }
     int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -544,6 +556,7 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
             const size_t p = (size_t) i * pitch + j;
             u1[q] = __ldg(u + p);
             u2[q] = __ldg(u + field_stride + p);
+            i0v[q] = __ldg(I0 + (size_t) b * img_stride + p);
             const float fu = floorf(u1[q]), fv = floorf(u2[q]);
             const float xf = (float) j + fu, yf = (float) i + fv;
             valid[q] = xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
@@ -601,8 +614,8 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
         float *c = consts + (size_t) b * plane0 + p;
         c[(size_t) C_IX * field_stride] = wx;
         c[(size_t) C_IY * field_stride] = wy;
-        c[(size_t) C_RHO * field_stride] = w - wx * u1[q] - wy * u2[q] - __ldg(I0 + (size_t) b * img_stride + p);
-        c[(size_t) C_GRAD * field_stride] = wx * wx + wy * wy;
+        c[(size_t) C_RHO * field_stride] = w - wx * u1[q] - wy * u2[q] - i0v[q];
+        c[(size_t) C_GRAD * field_stride] = grad_of(wx, wy);
     }
 }
 
@@ -846,6 +859,311 @@ k_iterate_t1(const IterParams P)
             const int left = atomicSub(&P.loop->active_pairs, 1) - 1;
             // the last pair to stop ends the device-side while loop of the solve graph
             if (left == 0 && P.use_cond) cudaGraphSetConditional(P.cond, 0);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// (c') cluster-resident iteration kernel: the whole while loop of one warp step on chip
+// ------------------------------------------------------------------------------------------------
+//
+// For pyramid levels small enough to live on chip, one thread-block CLUSTER owns one frame pair:
+// each CTA keeps a band of rows of the six evolving planes (u1,u2,p11,p12,p21,p22) in shared
+// memory, the per-warp constants of its pixels in registers, and the cluster runs the complete
+// loop of src/tvl1flow.cpp:113-182 without touching HBM between iterations:
+//   * state is brought in once with TMA bulk copies (cp.async.bulk + mbarrier) and written back
+//     once with TMA bulk stores;
+//   * band neighbours exchange their 1-row halos through distributed shared memory (the row of
+//     u_new a CTA's upper neighbour needs for the forward y-difference, the row of p12/p22 its
+//     lower neighbour needs for the divergence), pushed by the producer;
+//   * the mean squared update is reduced per CTA, broadcast to every CTA of the cluster through
+//     DSMEM and summed in rank order, so every CTA takes the same exact stop decision after every
+//     single iteration (no replay, no host, bit-reproducible).
+// Two barriers per iteration (cluster barrier, or __syncthreads for a 1-CTA cluster).
+namespace cg = cooperative_groups;
+
+constexpr int kResThreads = 512;
+constexpr int kResQuads = 4;                       // float4 pixel groups per thread
+constexpr int kResMaxCluster = 16;
+constexpr size_t kResSmemLimit = 227 * 1024;
+
+struct ResParams {
+    float *state;
+    const float *consts;
+    PairCtl *ctl;
+    int *stat_iters;
+    double *stat_errs;
+    unsigned long long *counters;    // [level] pixel-iterations; [kStatLevels + level] launches
+    double *err_trace;               // optional [max_iter] per-iteration error of pair 0 (tests)
+    size_t plane0, field_stride, set_stride;
+    Level lv;
+    int rows_per_cta;
+    int stat_stride, stat_slot;
+    int max_iter;
+    int level;
+    float l_t, theta, taut;
+    double eps2;
+};
+
+__host__ __device__ inline size_t resident_smem_bytes(int pitch, int rows_per_cta)
+{
+    // u1,u2: rows+1 (halo below) | p11,p21: rows | p12,p22: rows+1 (halo above) | slots | mbarrier
+    return (size_t) pitch * (6 * rows_per_cta + 4) * sizeof(float) + (2 * kResMaxCluster) * sizeof(double) + 16;
+}
+
+__device__ __forceinline__ unsigned int smem_u32(const void *p)
+{
+    return (unsigned int) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+__global__ void __launch_bounds__(kResThreads, 1)
+k_iterate_resident(const ResParams P)
+{
+    extern __shared__ __align__(128) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int) cluster.num_blocks();
+    const int rank = (int) cluster.block_rank();
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
+    const int RB = P.rows_per_cta;
+    const int r0 = rank * RB;
+    const int rows = min(RB, ny - r0);              // >= 1 by construction (host)
+    const int qpr = pitch >> 2;
+    const int nquads = rows * qpr;
+
+    float *sU1 = smem;
+    float *sU2 = sU1 + (size_t) (RB + 1) * pitch;
+    float *sP11 = sU2 + (size_t) (RB + 1) * pitch;
+    float *sP21 = sP11 + (size_t) RB * pitch;
+    float *sP12 = sP21 + (size_t) RB * pitch;       // row 0 = halo above, own rows at 1..rows
+    float *sP22 = sP12 + (size_t) (RB + 1) * pitch;
+    double *sSlots = reinterpret_cast<double *>(sP22 + (size_t) (RB + 1) * pitch);   // [C] cluster partials
+    double *sWarp = sSlots + kResMaxCluster;                                          // [16] warp partials
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(sWarp + kResMaxCluster);
+
+    PairCtl *ctl = P.ctl + b;
+    const int cur = ctl->cur;
+    const size_t fs = P.field_stride;
+    const float *gin = P.state + (size_t) cur * P.set_stride + (size_t) b * P.plane0;
+    float *gout = P.state + (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0;
+    const float *cst = P.consts + (size_t) b * P.plane0;
+
+    // ---- bring the band in: TMA bulk copies signalled on one mbarrier -------------------------
+    const unsigned int band_bytes = (unsigned int) ((size_t) rows * pitch * sizeof(float));
+    const unsigned int row_bytes = (unsigned int) (pitch * sizeof(float));
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int total = 6u * band_bytes + (r0 > 0 ? 2u * row_bytes : 0u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(total) : "memory");
+        const size_t go = (size_t) r0 * pitch;
+        float *dsts[6] = { sU1, sU2, sP11, sP12 + pitch, sP21, sP22 + pitch };   // order of enum Field
+#pragma unroll
+        for (int f = 0; f < 6; f++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(dsts[f])), "l"(gin + (size_t) f * fs + go), "r"(band_bytes), "r"(smem_u32(mbar)) : "memory");
+        if (r0 > 0) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(sP12)), "l"(gin + (size_t) F_P12 * fs + go - pitch), "r"(row_bytes), "r"(smem_u32(mbar)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(sP22)), "l"(gin + (size_t) F_P22 * fs + go - pitch), "r"(row_bytes), "r"(smem_u32(mbar)) : "memory");
+        }
+    }
+    if (r0 == 0)
+        for (int i = tid; i < pitch; i += kResThreads) sP12[i] = sP22[i] = 0.f;     // p[-1] = 0
+
+    // ---- per-thread pixel groups and their constants (registers) -------------------------------
+    int qoff[kResQuads];          // float offset of the group inside a band plane (row*pitch + x0)
+    int qx0[kResQuads], qrow[kResQuads];
+    bool qok[kResQuads];
+    float4 cix[kResQuads], ciy[kResQuads], crho[kResQuads];
+#pragma unroll
+    for (int k = 0; k < kResQuads; k++) {
+        const int q = tid + k * kResThreads;
+        qok[k] = q < nquads;
+        const int lr = qok[k] ? q / qpr : 0;
+        const int cq = qok[k] ? q - lr * qpr : 0;
+        qrow[k] = lr;
+        qx0[k] = cq * 4;
+        qoff[k] = lr * pitch + cq * 4;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        cix[k] = ciy[k] = crho[k] = z;
+        if (qok[k]) {
+            const size_t o = (size_t) (r0 + lr) * pitch + cq * 4;
+            cix[k] = ldg4(cst + C_IX * fs + o);
+            ciy[k] = ldg4(cst + C_IY * fs + o);
+            crho[k] = ldg4(cst + C_RHO * fs + o);
+        }
+    }
+    {   // wait for the bulk copies (phase 0 of the mbarrier)
+        unsigned int done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(mbar)) : "memory");
+    }
+    __syncthreads();
+
+    // DSMEM views of the neighbours' halo rows
+    float *upU1 = nullptr, *upU2 = nullptr, *dnP12 = nullptr, *dnP22 = nullptr;
+    if (rank > 0) {             // upper neighbour always holds RB rows: its halo-below row is row RB
+        upU1 = cluster.map_shared_rank(sU1 + (size_t) RB * pitch, rank - 1);
+        upU2 = cluster.map_shared_rank(sU2 + (size_t) RB * pitch, rank - 1);
+    }
+    if (rank < C - 1) {
+        dnP12 = cluster.map_shared_rank(sP12, rank + 1);
+        dnP22 = cluster.map_shared_rank(sP22, rank + 1);
+    }
+    if (C > 1) cluster.sync();  // every CTA of the cluster is resident before any remote store
+
+    const double npix = (double) nx * (double) ny;
+    int n = 0;
+    double error = INFINITY;                                            // src/tvl1flow.cpp:111-112
+    while (true) {
+        n++;
+        // ---- phase A: thresholding, divergence, primal update, error (:117-161) ----------------
+        float errp = 0.f;
+#pragma unroll
+        for (int k = 0; k < kResQuads; k++) {
+            const int o = qoff[k], x0 = qx0[k];
+            const int gy = r0 + qrow[k];
+            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
+            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
+            const float4 p12 = lds4(sP12 + o + pitch), p22 = lds4(sP22 + o + pitch);
+            const float4 a12 = lds4(sP12 + o), a22 = lds4(sP22 + o);
+            float l11 = __shfl_up_sync(0xffffffffu, p11.w, 1);
+            float l21 = __shfl_up_sync(0xffffffffu, p21.w, 1);
+            if (x0 == 0) { l11 = 0.f; l21 = 0.f; }
+            else if (lane == 0) { l11 = sP11[o - 1]; l21 = sP21[o - 1]; }
+            const bool last_row = (gy == ny - 1);
+            float o1[4], o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float a = TVL1_F4_GET(u1, e), c = TVL1_F4_GET(u2, e);
+                const float ix = TVL1_F4_GET(cix[k], e), iy = TVL1_F4_GET(ciy[k], e);
+                const float rho = TVL1_F4_GET(crho[k], e) + (ix * a + iy * c);
+                const float tc = th_coeff(rho, grad_of(ix, iy), P.l_t);
+                const float v1 = a + tc * ix, v2 = c + tc * iy;
+                const bool last_col = (x0 + e >= nx - 1);
+                const float p11c = last_col ? 0.f : TVL1_F4_GET(p11, e);
+                const float p21c = last_col ? 0.f : TVL1_F4_GET(p21, e);
+                const float p11l = (e == 0) ? l11 : TVL1_F4_GET(p11, (e + 3) & 3);
+                const float p21l = (e == 0) ? l21 : TVL1_F4_GET(p21, (e + 3) & 3);
+                const float p12c = last_row ? 0.f : TVL1_F4_GET(p12, e);
+                const float p22c = last_row ? 0.f : TVL1_F4_GET(p22, e);
+                const float d1 = (p11c - p11l) + (p12c - TVL1_F4_GET(a12, e));
+                const float d2 = (p21c - p21l) + (p22c - TVL1_F4_GET(a22, e));
+                o1[e] = v1 + P.theta * d1;
+                o2[e] = v2 + P.theta * d2;
+                if (qok[k] && x0 + e < nx) {
+                    const float e1 = o1[e] - a, e2 = o2[e] - c;
+                    errp += e1 * e1 + e2 * e2;
+                }
+            }
+            if (qok[k]) {
+                const float4 n1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                const float4 n2 = make_float4(o2[0], o2[1], o2[2], o2[3]);
+                st4(sU1 + o, n1);
+                st4(sU2 + o, n2);
+                if (qrow[k] == 0 && rank > 0) {     // my first row is the upper neighbour's row below
+                    st4(upU1 + x0, n1);
+                    st4(upU2 + x0, n2);
+                }
+            }
+        }
+        {
+            const double e = warp_sum((double) errp);
+            if (lane == 0) sWarp[warp] = e;
+        }
+        if (C > 1) cluster.sync(); else __syncthreads();
+
+        // ---- phase B: forward gradient of u_new, dual update (:165-181) -------------------------
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < kResThreads / 32; w++) s += sWarp[w];
+            for (int r = 0; r < C; r++) *cluster.map_shared_rank(sSlots + rank, r) = s;
+        }
+#pragma unroll
+        for (int k = 0; k < kResQuads; k++) {
+            const int o = qoff[k], x0 = qx0[k];
+            const int gy = r0 + qrow[k];
+            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
+            const float4 b1 = lds4(sU1 + o + pitch), b2 = lds4(sU2 + o + pitch);
+            float r1 = __shfl_down_sync(0xffffffffu, u1.x, 1);
+            float r2 = __shfl_down_sync(0xffffffffu, u2.x, 1);
+            if (lane == 31 && x0 + 4 < pitch) { r1 = sU1[o + 4]; r2 = sU2[o + 4]; }
+            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
+            const float4 p12 = lds4(sP12 + o + pitch), p22 = lds4(sP22 + o + pitch);
+            const bool has_below = (gy + 1 < ny);
+            float q11[4], q12[4], q21[4], q22[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const bool last_col = (x0 + e >= nx - 1);
+                const float c1 = TVL1_F4_GET(u1, e), c2 = TVL1_F4_GET(u2, e);
+                const float e1 = (e == 3) ? r1 : TVL1_F4_GET(u1, (e + 1) & 3);
+                const float e2 = (e == 3) ? r2 : TVL1_F4_GET(u2, (e + 1) & 3);
+                const float u1x = last_col ? 0.f : e1 - c1;
+                const float u2x = last_col ? 0.f : e2 - c2;
+                const float u1y = has_below ? TVL1_F4_GET(b1, e) - c1 : 0.f;
+                const float u2y = has_below ? TVL1_F4_GET(b2, e) - c2 : 0.f;
+                const float g1 = sqrtf(u1x * u1x + u1y * u1y);
+                const float g2 = sqrtf(u2x * u2x + u2y * u2y);
+                const float i1 = 1.0f / (1.0f + P.taut * g1);
+                const float i2 = 1.0f / (1.0f + P.taut * g2);
+                q11[e] = (TVL1_F4_GET(p11, e) + P.taut * u1x) * i1;
+                q12[e] = (TVL1_F4_GET(p12, e) + P.taut * u1y) * i1;
+                q21[e] = (TVL1_F4_GET(p21, e) + P.taut * u2x) * i2;
+                q22[e] = (TVL1_F4_GET(p22, e) + P.taut * u2y) * i2;
+            }
+            if (qok[k]) {
+                const float4 n12 = make_float4(q12[0], q12[1], q12[2], q12[3]);
+                const float4 n22 = make_float4(q22[0], q22[1], q22[2], q22[3]);
+                st4(sP11 + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
+                st4(sP21 + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
+                st4(sP12 + o + pitch, n12);
+                st4(sP22 + o + pitch, n22);
+                if (qrow[k] == rows - 1 && rank < C - 1) {   // my last row is the lower neighbour's row above
+                    st4(dnP12 + x0, n12);
+                    st4(dnP22 + x0, n22);
+                }
+            }
+        }
+        if (C > 1) cluster.sync(); else __syncthreads();
+
+        // ---- stopping rule (:113), identical in every CTA of the cluster -------------------------
+        double tot = 0.0;
+        for (int r = 0; r < C; r++) tot += sSlots[r];
+        error = tot / npix;                                              // :162
+        if (P.err_trace && b == 0 && rank == 0 && tid == 0) P.err_trace[n - 1] = error;
+        if (!(error > P.eps2 && n < P.max_iter)) break;
+    }
+
+    // ---- write the band back (other ping-pong set) with TMA bulk stores --------------------------
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        const size_t go = (size_t) r0 * pitch;
+        const float *srcs[6] = { sU1, sU2, sP11, sP12 + pitch, sP21, sP22 + pitch };
+#pragma unroll
+        for (int f = 0; f < 6; f++)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(gout + (size_t) f * fs + go), "r"(smem_u32(srcs[f])), "r"(band_bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (rank == 0) {
+            ctl->cur = cur ^ 1;
+            ctl->n = n;
+            ctl->err = error;
+            ctl->active = 0;
+            P.stat_iters[(size_t) b * P.stat_stride + P.stat_slot] = n;
+            P.stat_errs[(size_t) b * P.stat_stride + P.stat_slot] = error;
+            atomicAdd(P.counters + P.level, (unsigned long long) n * (unsigned long long) nx * (unsigned long long) ny);
+            if (b == 0) atomicAdd(P.counters + kStatLevels + P.level, 1ull);
         }
     }
 }

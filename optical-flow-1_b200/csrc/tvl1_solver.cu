@@ -45,6 +45,9 @@ struct Workspace {
     int parts_per_pair = 0;
     int stat_stride = 0;
     size_t bytes = 0;
+    // cluster-resident iteration kernel: cluster size per level (0 = streaming kernel) and band height
+    std::vector<int> res_cluster, res_rows;
+    int resident_key = -1;
 
     size_t plane(int s) const { return (size_t) lv[s].pitch * lv[s].ny; }
     float *I0(int s) const { return pyr + pyr_off[s]; }
@@ -79,6 +82,8 @@ struct tvl1_ctx {
     LoopCtl *h_loop = nullptr;               // pinned
     cudaStream_t body_stream = nullptr;      // capture stream for while-node bodies
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
+    bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
+    int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
     SolveGraph sg;
     tvl1_ctx *lane2 = nullptr;               // sibling context for copy/compute overlap (host-buffer batches)
@@ -159,18 +164,63 @@ int iterate_parts(const Level &l)
     return ceil_div(l.nx, 124) * ceil_div(l.ny, kIterR * kIterWY);
 }
 
+// Smallest cluster (1,2,4,8,16 CTAs) whose row bands fit one SM each: <= 2048 float4 groups per CTA
+// (512 threads x 4) and the six state planes of the band in <= 227 KB of shared memory.  Returns 0
+// when the level has to stream through HBM instead.
+int pick_cluster(tvl1_ctx *ctx, const Level &l, int *rows_out)
+{
+    if (!ctx->use_resident) return 0;
+    static bool attr_done[64] = { false };
+    for (int C = 1; C <= kResMaxCluster; C *= 2) {
+        if (ctx->force_cluster && C != ctx->force_cluster) continue;
+        const int RB = ceil_div(l.ny, C);
+        if ((C - 1) * RB >= l.ny) continue;                        // every CTA needs at least one row
+        if (RB * (l.pitch / 4) > kResThreads * kResQuads) continue;
+        const size_t smem = resident_smem_bytes(l.pitch, RB);
+        if (smem > kResSmemLimit) continue;
+        if (!attr_done[ctx->device & 63]) {
+            if (cudaFuncSetAttribute(k_iterate_resident, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int) kResSmemLimit) != cudaSuccess ||
+                cudaFuncSetAttribute(k_iterate_resident, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                cudaGetLastError();
+                return 0;
+            }
+            attr_done[ctx->device & 63] = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C, 1, 1);
+        cfg.blockDim = dim3(kResThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, k_iterate_resident, &cfg) != cudaSuccess || nclusters < 1) {
+            cudaGetLastError();
+            continue;
+        }
+        *rows_out = RB;
+        return C;
+    }
+    return 0;
+}
+
 int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride)
 {
     Workspace &w = ctx->ws;
     if (w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
-        w.stat_stride >= stat_stride)
+        w.stat_stride >= stat_stride && w.resident_key == (ctx->use_resident ? 1 + ctx->force_cluster : 0))
         return TVL1_OK;
     free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(w);
     w.nx = nx; w.ny = ny; w.nscales = nscales; w.zfactor = zfactor; w.B = B;
     w.stat_stride = stat_stride;
+    w.resident_key = ctx->use_resident ? 1 + ctx->force_cluster : 0;
     w.lv.resize(nscales);
     w.pyr_off.resize(nscales);
+    w.res_cluster.assign(nscales, 0);
+    w.res_rows.assign(nscales, 0);
     int cx = nx, cy = ny;
     size_t off = 0;
     int parts = 0;
@@ -185,6 +235,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
         w.pyr_off[s] = off;
         off += 2 * (size_t) B * w.plane(s);
         parts = std::max(parts, iterate_parts(w.lv[s]));
+        w.res_cluster[s] = pick_cluster(ctx, w.lv[s], &w.res_rows[s]);
     }
     w.plane0 = w.plane(0);
     w.field_stride = (size_t) B * w.plane0;
@@ -320,6 +371,37 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
     return TVL1_OK;
 }
 
+// The whole while loop of one warp step for every pair, on chip (one cluster per pair).
+int launch_resident(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_slot, int max_iter,
+                    double eps2, double *err_trace)
+{
+    const Workspace &w = ctx->ws;
+    ResParams P;
+    P.state = w.state; P.consts = w.consts; P.ctl = w.ctl;
+    P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs; P.counters = w.counters;
+    P.err_trace = err_trace;
+    P.plane0 = w.plane0; P.field_stride = w.field_stride; P.set_stride = w.set_stride;
+    P.lv = w.lv[s]; P.rows_per_cta = w.res_rows[s];
+    P.stat_stride = w.stat_stride; P.stat_slot = stat_slot; P.max_iter = max_iter;
+    P.level = std::min(s, TVL1_MAX_LEVELS - 1);
+    P.l_t = (float) (prm.lambda * prm.theta);
+    P.theta = (float) prm.theta;
+    P.taut = (float) (prm.tau / prm.theta);
+    P.eps2 = eps2;
+    const int C = w.res_cluster[s];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, 1, B);
+    cfg.blockDim = dim3(kResThreads);
+    cfg.dynamicSmemBytes = resident_smem_bytes(P.lv.pitch, P.rows_per_cta);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_iterate_resident, P));
+    return TVL1_OK;          // counted on the device like the streaming kernel
+}
+
 int launch_warp(tvl1_ctx *ctx, int s, int B)
 {
     const Workspace &w = ctx->ws;
@@ -414,6 +496,12 @@ int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base
         {
             Span sp(ctx, 1);
             TRY(launch_warp(ctx, s, B));                                    // :84, :94-109
+        }
+        if (w.res_cluster[s] > 0) {                                         // :111-182 on chip
+            Span sp(ctx, 0, std::min(s, TVL1_MAX_LEVELS - 1));
+            TRY(launch_resident(ctx, s, B, prm, stat_base + wi, kMaxIterations,
+                                prm.epsilon * prm.epsilon, nullptr));
+            continue;
         }
         k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.loop, B);   // :111-112
         CKL(ctx);
@@ -826,6 +914,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
+    if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     *out = ctx;
     return TVL1_OK;
 }
@@ -1134,6 +1223,70 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
     for (int f = 0; f < 6; f++) {
         k_unpack<<<g, dim3(32, 8), 0, st>>>(w.state + (size_t) cur * w.set_stride + (size_t) f * w.field_stride,
                                             buf, nx, ny, w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+        CK(cudaMemcpyAsync(st_host[f], buf, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_iterate_resident_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12, float *p21,
+                              float *p22, const float *rho_c, const float *I1wx, const float *I1wy,
+                              int nx, int ny, double tau, double lambda, double theta, double epsilon,
+                              int max_iter, int cluster, int *iters_out, double *errs_out, int *cluster_out)
+{
+    if (!ctx || !u1 || !u2 || !p11 || !p12 || !p21 || !p22 || !rho_c || !I1wx || !I1wy || nx < 1 ||
+        ny < 1 || max_iter < 1 || max_iter > 100000)
+        return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const int saved_force = ctx->force_cluster;
+    const bool saved_res = ctx->use_resident;
+    ctx->force_cluster = cluster;
+    ctx->use_resident = true;
+    const int rc0 = ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1);
+    ctx->force_cluster = saved_force;
+    ctx->use_resident = saved_res;
+    TRY(rc0);
+    Workspace &w = ctx->ws;
+    if (cluster_out) *cluster_out = w.res_cluster[0];
+    if (w.res_cluster[0] == 0) return fail_arg(ctx, "level does not fit the cluster-resident kernel with this cluster size");
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t) nx * ny;
+    Dev d;
+    float *buf = d.alloc(n);
+    double *trace = (double *) d.alloc(2 * (size_t) max_iter);
+    if (!buf || !trace) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
+    CKL(ctx);
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
+    float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
+    for (int f = 0; f < 6; f++) {
+        CK(cudaMemcpyAsync(buf, st_host[f], n * 4, cudaMemcpyHostToDevice, st));
+        k_pack<<<g, dim3(32, 8), 0, st>>>(buf, w.state + (size_t) f * w.field_stride, nx, ny,
+                                          w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+    }
+    const float *c_host[3] = { I1wx, I1wy, rho_c };   // order of enum Const; grad is recomputed on chip
+    for (int c = 0; c < 3; c++) {
+        CK(cudaMemcpyAsync(buf, c_host[c], n * 4, cudaMemcpyHostToDevice, st));
+        k_pack<<<g, dim3(32, 8), 0, st>>>(buf, w.consts + (size_t) c * w.field_stride, nx, ny,
+                                          w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+    }
+    tvl1_params prm;
+    tvl1_default_params(&prm);
+    prm.tau = tau; prm.lambda = lambda; prm.theta = theta;
+    const double eps2 = epsilon < 0 ? -1.0 : epsilon * epsilon;      // negative: never stop early
+    TRY(launch_resident(ctx, 0, 1, prm, 0, max_iter, eps2, trace));
+    int it = 0;
+    CK(cudaMemcpyAsync(&it, w.stat_iters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (iters_out) *iters_out = it;
+    if (errs_out) CK(cudaMemcpyAsync(errs_out, trace, sizeof(double) * it, cudaMemcpyDeviceToHost, st));
+    for (int f = 0; f < 6; f++) {      // the kernel wrote set 1 (cur was 0)
+        k_unpack<<<g, dim3(32, 8), 0, st>>>(w.state + w.set_stride + (size_t) f * w.field_stride, buf, nx, ny,
+                                            w.lv[0].pitch, w.plane0);
         CKL(ctx);
         CK(cudaMemcpyAsync(st_host[f], buf, n * 4, cudaMemcpyDeviceToHost, st));
     }

@@ -277,6 +277,21 @@ class TVL1:
                                            C.c_double(theta), C.c_int(iters), _fp(errs)))
         return (*st, errs[:iters])
 
+    def iterate_resident(self, u1, u2, p11, p12, p21, p22, rho_c, I1wx, I1wy, tau, lam, theta, eps,
+                         max_iter, cluster=0):
+        """Cluster-resident kernel: whole while loop on chip.  Returns
+        (u1,u2,p11,p12,p21,p22, n, errs[n], cluster_size_used)."""
+        st = [np.array(a, dtype=np.float32, order="C", copy=True) for a in (u1, u2, p11, p12, p21, p22)]
+        cs = [self._f32(a) for a in (rho_c, I1wx, I1wy)]
+        ny, nx = st[0].shape
+        errs = np.zeros(max_iter, np.float64)
+        n, c = C.c_int(), C.c_int()
+        self._ck(self.lib.tvl1_iterate_resident_f32(
+            self.ctx, *[_fp(a) for a in st], *[_fp(a) for a in cs], C.c_int(nx), C.c_int(ny),
+            C.c_double(tau), C.c_double(lam), C.c_double(theta), C.c_double(eps), C.c_int(max_iter),
+            C.c_int(cluster), C.byref(n), _fp(errs), C.byref(c)))
+        return (*st, n.value, errs[:n.value], c.value)
+
     def bench_iterate(self, npairs, nx, ny, launches):
         ms = C.c_double()
         self._ck(self.lib.tvl1_bench_iterate(self.ctx, C.c_int(npairs), C.c_int(nx), C.c_int(ny),

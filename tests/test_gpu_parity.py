@@ -150,6 +150,67 @@ def test_iterate_keeps_dual_boundary_invariants(gpu):
     assert np.all(out[3][-1, :] == 0) and np.all(out[5][-1, :] == 0)
 
 
+def _iterate_inputs(shape, seed=8):
+    rs = np.random.RandomState(seed)
+    f = lambda lo, hi: rs.uniform(lo, hi, shape).astype(np.float32)
+    u1, u2 = f(-3, 3), f(-3, 3)
+    p = [f(-1, 1) for _ in range(4)]
+    ix, iy = f(-20, 20), f(-20, 20)
+    ix[rs.uniform(size=shape) < 0.1] = 0.0
+    iy[ix == 0] = 0.0
+    grad = (ix * ix + iy * iy).astype(np.float32)
+    rho_c = f(-30, 30)
+    return u1, u2, p, rho_c, ix, iy, grad
+
+
+@pytest.mark.parametrize("shape,cluster", [
+    ((68, 120), 0), ((68, 120), 1), ((68, 120), 2), ((30, 40), 1), ((30, 40), 4), ((47, 61), 2),
+    ((135, 240), 0), ((135, 240), 4), ((135, 240), 8), ((135, 240), 16), ((270, 480), 0), ((109, 256), 0),
+    ((17, 23), 16),
+])
+def test_iterate_resident_fixed_count(gpu, oracle_f64, shape, cluster):
+    """The cluster-resident kernel (whole loop on chip, DSMEM halos) against src/tvl1flow.cpp:114-181
+    for a fixed number of passes, for every cluster size."""
+    u1, u2, p, rho_c, ix, iy, grad = _iterate_inputs(shape)
+    iters = 5
+    got = gpu.iterate_resident(u1, u2, *p, rho_c, ix, iy, 0.25, 0.15, 0.3, -1.0, iters, cluster)
+    ref = oracle_f64.iterate(u1, u2, *p, rho_c, ix, iy, grad, 0.25, 0.15, 0.3, iters)
+    assert got[6] == iters
+    if cluster:
+        assert got[8] == cluster
+    for k, name in enumerate(("u1", "u2", "p11", "p12", "p21", "p22")):
+        assert np.abs(got[k] - ref[k]).max() < 2e-4 * iters, (name, got[8])
+    assert np.allclose(got[7], ref[6], rtol=1e-4)
+
+
+def test_iterate_resident_matches_streaming_kernel(gpu):
+    u1, u2, p, rho_c, ix, iy, grad = _iterate_inputs((68, 120), seed=12)
+    a = gpu.iterate_resident(u1, u2, *p, rho_c, ix, iy, 0.25, 0.15, 0.3, -1.0, 4, 1)
+    b = gpu.iterate(u1, u2, *p, rho_c, ix, iy, grad, 0.25, 0.15, 0.3, 4)
+    for k in range(6):
+        assert np.abs(a[k] - b[k]).max() < 1e-5
+    assert np.allclose(a[7], b[6], rtol=1e-6)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+def test_iterate_resident_stopping_rule(gpu, oracle_f64, cluster):
+    """Stops after the first pass whose mean squared update is <= eps^2 (src/tvl1flow.cpp:113),
+    decided on chip, identically for every cluster size."""
+    I0, I1 = _cases.synth.make_pair(120, 68, seed=5, scale=0.2)
+    z = np.zeros_like(I0)
+    c = oracle_f64.warp_precompute(I0, I1, z, z)
+    eps = 0.05
+    ref = oracle_f64.iterate(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], c["grad"], 0.25, 0.15, 0.3, 300)
+    n_ref = int(np.argmax(ref[6] <= eps * eps)) + 1 if np.any(ref[6] <= eps * eps) else 300
+    got = gpu.iterate_resident(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, eps, 300, cluster)
+    assert 1 < n_ref < 300
+    assert got[6] == n_ref, (got[6], n_ref)
+    assert np.allclose(got[7], ref[6][:n_ref], rtol=1e-3)
+    # cap
+    got = gpu.iterate_resident(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, 0.0, 37, cluster)
+    assert got[6] == 37
+
+
 # ---- the solver against the golden vectors of the unmodified reference --------------------------
 
 @pytest.mark.parametrize("name", sorted(_cases.SOLVER_CASES))
