@@ -662,11 +662,59 @@ struct Row4 {                    // one image row segment of 4 pixels, everythin
     float4 u1, u2, ix, iy, rho, grad, p11, p12, p21, p22;
 };
 
+// Hardware approximations (MUFU.RCP / MUFU.RSQ based, <= 1-2 ulp): the IEEE-rounded division and
+// square root cost ~10 instructions plus a slow-path branch each and made this HBM-bound kernel
+// issue-bound; their rounding difference is far below the fp32-vs-fp64 gap to the reference.
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float th_coeff(float rho, float grad, float l_t)
 {
     // src/tvl1flow.cpp:123-139: d = c * (I1wx, I1wy)
     const float thr = l_t * grad;
-    return (rho < -thr) ? l_t : ((rho > thr) ? -l_t : ((grad < kGradIsZero) ? 0.f : (-rho / grad)));
+    const float q = -rho * fast_rcp(grad);          // unused (and possibly inf/nan) when grad ~ 0
+    return (rho < -thr) ? l_t : ((rho > thr) ? -l_t : ((grad < kGradIsZero) ? 0.f : q));
+}
+
+// u_new of one pixel: thresholding step (:117-143), divergence of the dual variables
+// (src/operators.cpp:35-78; the caller passes 0 for the terms the reference drops or reads as 0)
+// and the primal update (:156-157).
+__device__ __forceinline__ void primal_px(float u1, float u2, float ix, float iy, float rho_c, float grad,
+                                          float p11c, float p11l, float p12c, float p12a, float p21c,
+                                          float p21l, float p22c, float p22a, float l_t, float theta,
+                                          float &o1, float &o2)
+{
+    const float rho = rho_c + (ix * u1 + iy * u2);
+    const float c = th_coeff(rho, grad, l_t);
+    const float v1 = u1 + c * ix, v2 = u2 + c * iy;
+    const float d1 = (p11c - p11l) + (p12c - p12a);
+    const float d2 = (p21c - p21l) + (p22c - p22a);
+    o1 = v1 + theta * d1;
+    o2 = v2 + theta * d2;
+}
+
+// dual update of one pixel from the forward differences of u_new (:169-181)
+__device__ __forceinline__ void dual_px(float u1x, float u1y, float u2x, float u2y, float taut,
+                                        float &p11, float &p12, float &p21, float &p22)
+{
+    const float g1 = fast_sqrt(u1x * u1x + u1y * u1y);
+    const float g2 = fast_sqrt(u2x * u2x + u2y * u2y);
+    const float i1 = fast_rcp(1.0f + taut * g1);
+    const float i2 = fast_rcp(1.0f + taut * g2);
+    p11 = (p11 + taut * u1x) * i1;
+    p12 = (p12 + taut * u1y) * i1;
+    p21 = (p21 + taut * u2x) * i2;
+    p22 = (p22 + taut * u2y) * i2;
 }
 
 #define TVL1_F4_GET(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
@@ -729,34 +777,61 @@ k_iterate_t1(const IterParams P)
                 l21 = has ? __ldg(sin + F_P21 * fs + o) : 0.f;
             }
             const bool last_row = (y == ny - 1);
+            const bool tally = count && owner;
             float o1[4], o2[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const float u1 = TVL1_F4_GET(r.u1, k), u2 = TVL1_F4_GET(r.u2, k);
-                const float ix = TVL1_F4_GET(r.ix, k), iy = TVL1_F4_GET(r.iy, k);
-                const float rho = TVL1_F4_GET(r.rho, k) + (ix * u1 + iy * u2);
-                const float c = th_coeff(rho, TVL1_F4_GET(r.grad, k), P.l_t);
-                const float v1 = u1 + c * ix, v2 = u2 + c * iy;
                 // divergence, src/operators.cpp:35-78: "+p1" dropped on the last column,
                 // "+p2" on the last row, p[-1] = 0
                 const bool last_col = (x0 + k >= nx - 1);
-                const float p11c = last_col ? 0.f : TVL1_F4_GET(r.p11, k);
-                const float p21c = last_col ? 0.f : TVL1_F4_GET(r.p21, k);
-                const float p11l = (k == 0) ? l11 : TVL1_F4_GET(r.p11, (k + 3) & 3);
-                const float p21l = (k == 0) ? l21 : TVL1_F4_GET(r.p21, (k + 3) & 3);
-                const float p12c = last_row ? 0.f : TVL1_F4_GET(r.p12, k);
-                const float p22c = last_row ? 0.f : TVL1_F4_GET(r.p22, k);
-                const float d1 = (p11c - p11l) + (p12c - TVL1_F4_GET(a12, k));
-                const float d2 = (p21c - p21l) + (p22c - TVL1_F4_GET(a22, k));
-                o1[k] = v1 + P.theta * d1;
-                o2[k] = v2 + P.theta * d2;
-                if (count && owner && x0 + k < nx) {
-                    const float e1 = o1[k] - u1, e2 = o2[k] - u2;
-                    err += e1 * e1 + e2 * e2;
-                }
+                primal_px(u1, u2, TVL1_F4_GET(r.ix, k), TVL1_F4_GET(r.iy, k), TVL1_F4_GET(r.rho, k),
+                          TVL1_F4_GET(r.grad, k),
+                          last_col ? 0.f : TVL1_F4_GET(r.p11, k), (k == 0) ? l11 : TVL1_F4_GET(r.p11, (k + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(r.p12, k), TVL1_F4_GET(a12, k),
+                          last_col ? 0.f : TVL1_F4_GET(r.p21, k), (k == 0) ? l21 : TVL1_F4_GET(r.p21, (k + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(r.p22, k), TVL1_F4_GET(a22, k),
+                          P.l_t, P.theta, o1[k], o2[k]);
+                const float e1 = o1[k] - u1, e2 = o2[k] - u2;
+                const float sq = e1 * e1 + e2 * e2;
+                err += (tally && x0 + k < nx) ? sq : 0.f;
             }
             n1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
             n2 = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        };
+        // One step of the march: `c` (row y) is complete, `d` receives row y+1; then the forward
+        // gradient of u_new (src/operators.cpp:86-125), the dual update (:169-181) and the stores
+        // of row y.  Called with the roles of the two register sets alternating, so nothing is copied.
+        auto step = [&](int y, Row4 &c, float4 &uc1, float4 &uc2, Row4 &d, float4 &ud1, float4 &ud2) {
+            const bool has_below = (y + 1 < ny);
+            if (has_below) {
+                load_row(y + 1, d);
+                primal(y + 1, d, c.p12, c.p22, ud1, ud2, y + 1 < ye);
+            }
+            const float r1 = __shfl_down_sync(0xffffffffu, uc1.x, 1);
+            const float r2 = __shfl_down_sync(0xffffffffu, uc2.x, 1);
+            float q11[4], q12[4], q21[4], q22[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool last_col = (x0 + k >= nx - 1);
+                const float c1 = TVL1_F4_GET(uc1, k), c2 = TVL1_F4_GET(uc2, k);
+                const float e1 = (k == 3) ? r1 : TVL1_F4_GET(uc1, (k + 1) & 3);
+                const float e2 = (k == 3) ? r2 : TVL1_F4_GET(uc2, (k + 1) & 3);
+                q11[k] = TVL1_F4_GET(c.p11, k); q12[k] = TVL1_F4_GET(c.p12, k);
+                q21[k] = TVL1_F4_GET(c.p21, k); q22[k] = TVL1_F4_GET(c.p22, k);
+                dual_px(last_col ? 0.f : e1 - c1, has_below ? TVL1_F4_GET(ud1, k) - c1 : 0.f,
+                        last_col ? 0.f : e2 - c2, has_below ? TVL1_F4_GET(ud2, k) - c2 : 0.f,
+                        P.taut, q11[k], q12[k], q21[k], q22[k]);
+            }
+            if (owner) {
+                const size_t o = (size_t) y * pitch + x0;
+                st4(sout + F_U1 * fs + o, uc1);
+                st4(sout + F_U2 * fs + o, uc2);
+                st4(sout + F_P11 * fs + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
+                st4(sout + F_P12 * fs + o, make_float4(q12[0], q12[1], q12[2], q12[3]));
+                st4(sout + F_P21 * fs + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
+                st4(sout + F_P22 * fs + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
+            }
         };
 
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -768,50 +843,12 @@ k_iterate_t1(const IterParams P)
             a22 = ldg4(sin + F_P22 * fs + o);
         }
         load_row(ys, ra);
+        rb = ra;
         float4 ua1, ua2, ub1 = zero4, ub2 = zero4;
         primal(ys, ra, a12, a22, ua1, ua2, true);
-
-        for (int y = ys; y < ye; y++) {
-            const bool has_below = (y + 1 < ny);
-            if (has_below) {
-                load_row(y + 1, rb);
-                primal(y + 1, rb, ra.p12, ra.p22, ub1, ub2, y + 1 < ye);
-            }
-            // forward gradient of u_new (src/operators.cpp:86-125) and dual update (:169-181)
-            const float r1 = __shfl_down_sync(0xffffffffu, ua1.x, 1);
-            const float r2 = __shfl_down_sync(0xffffffffu, ua2.x, 1);
-            float q11[4], q12[4], q21[4], q22[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const bool last_col = (x0 + k >= nx - 1);
-                const float c1 = TVL1_F4_GET(ua1, k), c2 = TVL1_F4_GET(ua2, k);
-                const float e1 = (k == 3) ? r1 : TVL1_F4_GET(ua1, (k + 1) & 3);
-                const float e2 = (k == 3) ? r2 : TVL1_F4_GET(ua2, (k + 1) & 3);
-                const float u1x = last_col ? 0.f : e1 - c1;
-                const float u2x = last_col ? 0.f : e2 - c2;
-                const float u1y = has_below ? TVL1_F4_GET(ub1, k) - c1 : 0.f;
-                const float u2y = has_below ? TVL1_F4_GET(ub2, k) - c2 : 0.f;
-                const float g1 = sqrtf(u1x * u1x + u1y * u1y);
-                const float g2 = sqrtf(u2x * u2x + u2y * u2y);
-                const float i1 = 1.0f / (1.0f + P.taut * g1);
-                const float i2 = 1.0f / (1.0f + P.taut * g2);
-                q11[k] = (TVL1_F4_GET(ra.p11, k) + P.taut * u1x) * i1;
-                q12[k] = (TVL1_F4_GET(ra.p12, k) + P.taut * u1y) * i1;
-                q21[k] = (TVL1_F4_GET(ra.p21, k) + P.taut * u2x) * i2;
-                q22[k] = (TVL1_F4_GET(ra.p22, k) + P.taut * u2y) * i2;
-            }
-            if (owner) {
-                const size_t o = (size_t) y * pitch + x0;
-                st4(sout + F_U1 * fs + o, ua1);
-                st4(sout + F_U2 * fs + o, ua2);
-                st4(sout + F_P11 * fs + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
-                st4(sout + F_P12 * fs + o, make_float4(q12[0], q12[1], q12[2], q12[3]));
-                st4(sout + F_P21 * fs + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
-                st4(sout + F_P22 * fs + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
-            }
-            ra = rb;
-            ua1 = ub1;
-            ua2 = ub2;
+        for (int y = ys; y < ye; y += 2) {
+            step(y, ra, ua1, ua2, rb, ub1, ub2);
+            if (y + 1 < ye) step(y + 1, rb, ub1, ub2, ra, ua1, ua2);
         }
     }
 
@@ -1046,24 +1083,16 @@ k_iterate_resident(const ResParams P)
             for (int e = 0; e < 4; e++) {
                 const float a = TVL1_F4_GET(u1, e), c = TVL1_F4_GET(u2, e);
                 const float ix = TVL1_F4_GET(cix[k], e), iy = TVL1_F4_GET(ciy[k], e);
-                const float rho = TVL1_F4_GET(crho[k], e) + (ix * a + iy * c);
-                const float tc = th_coeff(rho, grad_of(ix, iy), P.l_t);
-                const float v1 = a + tc * ix, v2 = c + tc * iy;
                 const bool last_col = (x0 + e >= nx - 1);
-                const float p11c = last_col ? 0.f : TVL1_F4_GET(p11, e);
-                const float p21c = last_col ? 0.f : TVL1_F4_GET(p21, e);
-                const float p11l = (e == 0) ? l11 : TVL1_F4_GET(p11, (e + 3) & 3);
-                const float p21l = (e == 0) ? l21 : TVL1_F4_GET(p21, (e + 3) & 3);
-                const float p12c = last_row ? 0.f : TVL1_F4_GET(p12, e);
-                const float p22c = last_row ? 0.f : TVL1_F4_GET(p22, e);
-                const float d1 = (p11c - p11l) + (p12c - TVL1_F4_GET(a12, e));
-                const float d2 = (p21c - p21l) + (p22c - TVL1_F4_GET(a22, e));
-                o1[e] = v1 + P.theta * d1;
-                o2[e] = v2 + P.theta * d2;
-                if (qok[k] && x0 + e < nx) {
-                    const float e1 = o1[e] - a, e2 = o2[e] - c;
-                    errp += e1 * e1 + e2 * e2;
-                }
+                primal_px(a, c, ix, iy, TVL1_F4_GET(crho[k], e), grad_of(ix, iy),
+                          last_col ? 0.f : TVL1_F4_GET(p11, e), (e == 0) ? l11 : TVL1_F4_GET(p11, (e + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(p12, e), TVL1_F4_GET(a12, e),
+                          last_col ? 0.f : TVL1_F4_GET(p21, e), (e == 0) ? l21 : TVL1_F4_GET(p21, (e + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(p22, e), TVL1_F4_GET(a22, e),
+                          P.l_t, P.theta, o1[e], o2[e]);
+                const float e1 = o1[e] - a, e2 = o2[e] - c;
+                const float sq = e1 * e1 + e2 * e2;
+                errp += (qok[k] && x0 + e < nx) ? sq : 0.f;
             }
             if (qok[k]) {
                 const float4 n1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
@@ -1107,18 +1136,11 @@ k_iterate_resident(const ResParams P)
                 const float c1 = TVL1_F4_GET(u1, e), c2 = TVL1_F4_GET(u2, e);
                 const float e1 = (e == 3) ? r1 : TVL1_F4_GET(u1, (e + 1) & 3);
                 const float e2 = (e == 3) ? r2 : TVL1_F4_GET(u2, (e + 1) & 3);
-                const float u1x = last_col ? 0.f : e1 - c1;
-                const float u2x = last_col ? 0.f : e2 - c2;
-                const float u1y = has_below ? TVL1_F4_GET(b1, e) - c1 : 0.f;
-                const float u2y = has_below ? TVL1_F4_GET(b2, e) - c2 : 0.f;
-                const float g1 = sqrtf(u1x * u1x + u1y * u1y);
-                const float g2 = sqrtf(u2x * u2x + u2y * u2y);
-                const float i1 = 1.0f / (1.0f + P.taut * g1);
-                const float i2 = 1.0f / (1.0f + P.taut * g2);
-                q11[e] = (TVL1_F4_GET(p11, e) + P.taut * u1x) * i1;
-                q12[e] = (TVL1_F4_GET(p12, e) + P.taut * u1y) * i1;
-                q21[e] = (TVL1_F4_GET(p21, e) + P.taut * u2x) * i2;
-                q22[e] = (TVL1_F4_GET(p22, e) + P.taut * u2y) * i2;
+                q11[e] = TVL1_F4_GET(p11, e); q12[e] = TVL1_F4_GET(p12, e);
+                q21[e] = TVL1_F4_GET(p21, e); q22[e] = TVL1_F4_GET(p22, e);
+                dual_px(last_col ? 0.f : e1 - c1, has_below ? TVL1_F4_GET(b1, e) - c1 : 0.f,
+                        last_col ? 0.f : e2 - c2, has_below ? TVL1_F4_GET(b2, e) - c2 : 0.f,
+                        P.taut, q11[e], q12[e], q21[e], q22[e]);
             }
             if (qok[k]) {
                 const float4 n12 = make_float4(q12[0], q12[1], q12[2], q12[3]);
