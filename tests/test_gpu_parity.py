@@ -166,7 +166,7 @@ def _iterate_inputs(shape, seed=8):
 @pytest.mark.parametrize("shape,cluster", [
     ((68, 120), 0), ((68, 120), 1), ((68, 120), 2), ((30, 40), 1), ((30, 40), 4), ((47, 61), 2),
     ((135, 240), 0), ((135, 240), 4), ((135, 240), 8), ((144, 240), 16), ((270, 480), 0), ((109, 256), 0),
-    ((17, 23), 16),
+    ((32, 23), 16),
 ])
 def test_iterate_resident_fixed_count(gpu, oracle_f64, shape, cluster):
     """The cluster-resident kernel (whole loop on chip, DSMEM halos) against src/tvl1flow.cpp:114-181
