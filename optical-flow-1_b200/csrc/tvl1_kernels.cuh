@@ -135,7 +135,10 @@ __global__ void k_minmax(const float *__restrict__ in0, const float *__restrict_
 //                       returns the centre tap exactly -> blur followed by [D*i, D*j] decimation)
 // One CTA produces a TW x TH output tile from a (D*TW+2r) x (D*TH+2r) input tile in shared memory.
 // z = image index in [0, nimg); pair (for min/max) = z % B.
-template <int D>
+// RT = compile-time radius (taps.size - 1) for the two windows the default parameters use
+// (sigma 0.8 -> 4, zoom sigma at zfactor 0.5 -> 5): weights live in registers and the tap loops
+// unroll; RT = 0 is the generic run-time radius.
+template <int D, int RT>
 __global__ void __launch_bounds__(256)
 k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__restrict__ out,
         int out_pitch, size_t out_stride, int nx, int ny, int onx, int ony, const GaussTaps taps,
@@ -143,13 +146,13 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
 {
     constexpr int TW = 64 / D, TH = 32 / D;        // output tile
     constexpr int IW = 64, IH = 32;                // input footprint without halo
-    constexpr int RMAX = kMaxTaps - 1;
+    constexpr int RMAX = RT > 0 ? RT : kMaxTaps - 1;
+    constexpr int NW = RT > 0 ? RT + 1 : kMaxTaps;
     __shared__ float s_in[(IH + 2 * RMAX)][IW + 2 * RMAX + 1];
     __shared__ float s_row[(IH + 2 * RMAX)][TW + 1];
-    __shared__ float s_w[kMaxTaps];
 
     const int tx = threadIdx.x, ty = threadIdx.y;  // block (32, 8)
-    const int r = taps.size - 1;
+    const int r = RT > 0 ? RT : taps.size - 1;
     const int z = blockIdx.z;
     const float *src = in + (size_t) z * in_stride;
     float *dst = out + (size_t) z * out_stride;
@@ -157,28 +160,38 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
     const int ix0 = ox0 * D - r, iy0 = oy0 * D - r;
     const int iw = IW + 2 * r - (D - 1), ih = IH + 2 * r - (D - 1);
 
-    if (ty == 0) {
+    float w[NW];
 #pragma unroll
-        for (int i = 0; i < kMaxTaps; i++)
-            if (tx == i) s_w[i] = taps.w[i];
-    }
-    float mn = 0.f, den = 0.f;
+    for (int i = 0; i < NW; i++) w[i] = taps.w[i];
+
+    // image_normalization_2 fused on load: (I - min) * (255 / den); the reference's
+    // "255*(I-min)/den" (src/utils.cpp:315-316) differs by one rounding
+    float mn = 0.f, scl = 1.f;
+    bool norm = false;
     if (mm) {
         mn = ord2f(mm[2 * (z % B)]);
-        den = ord2f(mm[2 * (z % B) + 1]) - mn;
+        const float den = ord2f(mm[2 * (z % B) + 1]) - mn;
+        norm = den > 0.f;
+        if (norm) scl = 255.0f / den;
     }
+    // tiles that do not touch the border skip the reflection arithmetic
+    const bool interior = ix0 >= 0 && iy0 >= 0 && ix0 + iw <= nx && iy0 + ih <= ny;
 
     for (int ly = ty; ly < ih; ly += 8) {
         int gy = iy0 + ly;
-        gy = gy < 0 ? -gy : (gy >= ny ? 2 * ny - 1 - gy : gy);
-        gy = clampi(gy, 0, ny - 1);   // only reachable for tiles hanging over the image edge
+        if (!interior) {
+            gy = gy < 0 ? -gy : (gy >= ny ? 2 * ny - 1 - gy : gy);
+            gy = clampi(gy, 0, ny - 1);   // only reachable for tiles hanging over the image edge
+        }
         const float *row = src + (size_t) gy * in_pitch;
         for (int lx = tx; lx < iw; lx += 32) {
             int gx = ix0 + lx;
-            gx = gx < 0 ? -gx : (gx >= nx ? 2 * nx - 1 - gx : gx);
-            gx = clampi(gx, 0, nx - 1);
+            if (!interior) {
+                gx = gx < 0 ? -gx : (gx >= nx ? 2 * nx - 1 - gx : gx);
+                gx = clampi(gx, 0, nx - 1);
+            }
             float v = __ldg(row + gx);
-            if (den > 0.f) v = 255.0f * (v - mn) / den;
+            if (norm) v = (v - mn) * scl;
             s_in[ly][lx] = v;
         }
     }
@@ -186,25 +199,38 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
 
     // row pass: every input row of the tile, output columns only
     for (int ly = ty; ly < ih; ly += 8) {
+#pragma unroll
         for (int ox = tx; ox < TW; ox += 32) {
-            const int c = ox * D + r;
-            float sum = s_w[0] * s_in[ly][c];
-            for (int j = 1; j <= r; j++) sum += s_w[j] * (s_in[ly][c - j] + s_in[ly][c + j]);
+            const float *c = &s_in[ly][ox * D + r];
+            float sum = w[0] * c[0];
+            if (RT > 0) {
+#pragma unroll
+                for (int j = 1; j <= RT; j++) sum += w[j] * (c[-j] + c[j]);
+            } else {
+                for (int j = 1; j <= r; j++) sum += taps.w[j] * (c[-j] + c[j]);
+            }
             s_row[ly][ox] = sum;
         }
     }
     __syncthreads();
 
     // column pass on output rows
+#pragma unroll
     for (int oy = ty; oy < TH; oy += 8) {
         const int gy = oy0 + oy;
         if (gy >= ony) break;
         const int c = oy * D + r;
+#pragma unroll
         for (int ox = tx; ox < TW; ox += 32) {
             const int gx = ox0 + ox;
             if (gx >= onx) break;
-            float sum = s_w[0] * s_row[c][ox];
-            for (int j = 1; j <= r; j++) sum += s_w[j] * (s_row[c - j][ox] + s_row[c + j][ox]);
+            float sum = w[0] * s_row[c][ox];
+            if (RT > 0) {
+#pragma unroll
+                for (int j = 1; j <= RT; j++) sum += w[j] * (s_row[c - j][ox] + s_row[c + j][ox]);
+            } else {
+                for (int j = 1; j <= r; j++) sum += taps.w[j] * (s_row[c - j][ox] + s_row[c + j][ox]);
+            }
             dst[(size_t) gy * out_pitch + gx] = sum;
         }
     }

@@ -330,15 +330,17 @@ int launch_gauss(tvl1_ctx *ctx, int D, const float *in, int in_pitch, size_t in_
                  const GaussTaps &taps, const unsigned int *mm, int B, int nimg)
 {
     cudaStream_t st = ctx->stream;
+    const int r = taps.size - 1;
+#define TVL1_GAUSS(D_, R_) k_gauss<D_, R_><<<g, dim3(32, 8), 0, st>>>(in, in_pitch, in_stride, out, out_pitch, \
+                                                                      out_stride, nx, ny, onx, ony, taps, mm, B)
     if (D == 1) {
         dim3 g(ceil_div(onx, 64), ceil_div(ony, 32), nimg);
-        k_gauss<1><<<g, dim3(32, 8), 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
-                                      onx, ony, taps, mm, B);
+        if (r == 4) TVL1_GAUSS(1, 4); else if (r == 5) TVL1_GAUSS(1, 5); else TVL1_GAUSS(1, 0);
     } else {
         dim3 g(ceil_div(onx, 32), ceil_div(ony, 16), nimg);
-        k_gauss<2><<<g, dim3(32, 8), 0, st>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, nx, ny,
-                                      onx, ony, taps, mm, B);
+        if (r == 5) TVL1_GAUSS(2, 5); else TVL1_GAUSS(2, 0);
     }
+#undef TVL1_GAUSS
     CKL(ctx);
     return TVL1_OK;
 }
@@ -365,8 +367,13 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
 
 int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
 {
-    dim3 g(ceil_div(P.lv.nx, 124), ceil_div(P.lv.ny, kIterR * kIterWY), B);
-    k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    if (P.lv.ny >= 512) {     // tall levels: longer strips, half the CTAs and half the halo rows
+        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(P.lv.ny, 2 * kIterR * kIterWY), B);
+        k_iterate_t1<2 * kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    } else {
+        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(P.lv.ny, kIterR * kIterWY), B);
+        k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
     return TVL1_OK;
 }
@@ -797,6 +804,51 @@ void add_stats(tvl1_stats &a, const tvl1_stats &b)
     }
 }
 
+// Runs `nchunks` chunks of work over one or two lanes.  Lane 0 is `ctx` on the calling thread; lane 1
+// is a private sibling context on the same GPU (own stream, workspace, solve graph) driven by a
+// second host thread.  The two lanes take alternate chunks and run concurrently on the GPU: the
+// copies of one chunk overlap the kernels of the other, and the sparse tail launches of one lane
+// (few pairs still iterating) are filled by the other lane's work.
+template <class Fn>
+int run_lanes(tvl1_ctx *ctx, int nchunks, Fn &&chunk_fn)
+{
+    tvl1_ctx *lanes[2] = { ctx, nullptr };
+    int nlanes = 1;
+    if (nchunks > 1 && ctx->two_lanes) {
+        if (!ctx->lane2) {
+            if (tvl1_create(ctx->device, &ctx->lane2) != TVL1_OK) {
+                ctx->err = std::string("second lane: ") + tvl1_last_error(nullptr);
+                return TVL1_ERR_CUDA;
+            }
+            ctx->lane2->two_lanes = false;
+        }
+        ctx->lane2->max_batch = ctx->max_batch;
+        ctx->lane2->profiling = ctx->profiling;
+        ctx->lane2->use_graph = ctx->use_graph;
+        ctx->lane2->use_resident = ctx->use_resident;
+        reset_stats(ctx->lane2);
+        lanes[1] = ctx->lane2;
+        nlanes = 2;
+    }
+    int rcs[2] = { TVL1_OK, TVL1_OK };
+    auto work = [&](int l) {
+        tvl1_ctx *c = lanes[l];
+        cudaSetDevice(c->device);
+        for (int k = l; k < nchunks && rcs[l] == TVL1_OK; k += nlanes) rcs[l] = chunk_fn(c, k);
+        resolve_events(c);
+    };
+    if (nlanes == 2) {
+        std::thread t(work, 1);
+        work(0);
+        t.join();
+        add_stats(ctx->stats, ctx->lane2->stats);
+        if (rcs[1] != TVL1_OK) { ctx->err = ctx->lane2->err; return rcs[1]; }
+    } else {
+        work(0);
+    }
+    return rcs[0];
+}
+
 // Host-buffer driver shared by the f32/f64, multiscale/single-scale entry points.  A batch larger
 // than max_batch is cut into chunks; two lanes (this context and a private sibling on the same
 // GPU, each with its own stream, workspace and host thread) take alternate chunks, so the H2D/D2H
@@ -813,53 +865,12 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     const int Bmax = std::min(npairs, ctx->max_batch);
     const int nchunks = ceil_div(npairs, Bmax);
     const int nstat = (multiscale ? prm->nscales : 1) * prm->warps;
-    tvl1_ctx *lanes[2] = { ctx, nullptr };
-    int nlanes = 1;
-    if (nchunks > 1 && ctx->two_lanes) {
-        if (!ctx->lane2) {
-            if (tvl1_create(ctx->device, &ctx->lane2) != TVL1_OK) {
-                ctx->err = std::string("second lane: ") + tvl1_last_error(nullptr);
-                return TVL1_ERR_CUDA;
-            }
-            ctx->lane2->two_lanes = false;
-        }
-        ctx->lane2->max_batch = ctx->max_batch;
-        ctx->lane2->profiling = ctx->profiling;
-        ctx->lane2->use_graph = ctx->use_graph;
-        reset_stats(ctx->lane2);
-        lanes[1] = ctx->lane2;
-        nlanes = 2;
-    }
-    for (int l = 0; l < nlanes; l++) {
-        tvl1_ctx *c = lanes[l];
-        const int rc = [&]() -> int {
-            tvl1_ctx *ctx = c;   // for CK
-            CK(cudaSetDevice(ctx->device));
-            return ensure_stage(ctx, (size_t) Bmax * n * sizeof(T), f64);
-        }();
-        if (rc != TVL1_OK) { if (c != ctx) ctx->err = c->err; return rc; }
-    }
-    int rcs[2] = { TVL1_OK, TVL1_OK };
-    auto work = [&](int l) {
-        tvl1_ctx *c = lanes[l];
-        cudaSetDevice(c->device);
-        for (int k = l; k < nchunks && rcs[l] == TVL1_OK; k += nlanes) {
-            const int first = k * Bmax, B = std::min(Bmax, npairs - first);
-            rcs[l] = solve_chunk<T>(c, first, B, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out,
-                                    multiscale, nstat);
-        }
-        resolve_events(c);
-    };
-    if (nlanes == 2) {
-        std::thread t(work, 1);
-        work(0);
-        t.join();
-        add_stats(ctx->stats, ctx->lane2->stats);
-        if (rcs[1] != TVL1_OK) { ctx->err = ctx->lane2->err; return rcs[1]; }
-    } else {
-        work(0);
-    }
-    return rcs[0];
+    return run_lanes(ctx, nchunks, [&](tvl1_ctx *c, int k) -> int {
+        tvl1_ctx *ctx = c;   // for CK / TRY
+        TRY(ensure_stage(ctx, (size_t) Bmax * n * sizeof(T), f64));
+        const int first = k * Bmax, B = std::min(Bmax, npairs - first);
+        return solve_chunk<T>(ctx, first, B, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, multiscale, nstat);
+    });
 }
 
 // ---- RAII device scratch for the per-kernel hooks -----------------------------------------------
@@ -1015,15 +1026,13 @@ int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const 
     const size_t n = (size_t) nx * ny;
     const int nstat = prm->nscales * prm->warps;
     const int Bmax = std::min(npairs, ctx->max_batch);
-    for (int first = 0; first < npairs; first += Bmax) {
-        const int B = std::min(Bmax, npairs - first);
+    return run_lanes(ctx, ceil_div(npairs, Bmax), [&](tvl1_ctx *c, int k) -> int {
+        const int first = k * Bmax, B = std::min(Bmax, npairs - first);
         const size_t off = (size_t) first * n;
-        TRY(run_multiscale(ctx, B, dI0 + off, dI1 + off, du1 + off, du2 + off, nx, ny, *prm,
-                           iters_out ? iters_out + (size_t) first * nstat : nullptr,
-                           errs_out ? errs_out + (size_t) first * nstat : nullptr));
-    }
-    resolve_events(ctx);
-    return TVL1_OK;
+        return run_multiscale(c, B, dI0 + off, dI1 + off, du1 + off, du2 + off, nx, ny, *prm,
+                              iters_out ? iters_out + (size_t) first * nstat : nullptr,
+                              errs_out ? errs_out + (size_t) first * nstat : nullptr);
+    });
 }
 
 int tvl1_single_scale_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2,
