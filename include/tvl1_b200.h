@@ -131,7 +131,9 @@ int tvl1_zoom_in_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, 
 int tvl1_warp_f32(tvl1_ctx *ctx, const float *I0, const float *I1, const float *u1, const float *u2,
                   int nx, int ny, float *I1wx, float *I1wy, float *rho_c, float *grad);
 /* exactly `iters` passes of the loop body (tvl1flow.cpp:114-181), no stopping test.
- * u1..p22 in/out; errs_out[iters] = mean squared update of each pass (may be NULL). */
+ * u1..p22 in/out; errs_out[iters] = mean squared update of each pass (may be NULL).  `grad` is
+ * accepted for symmetry with the reference's data flow but the kernel recomputes it as
+ * I1wx^2 + I1wy^2 (one plane less to read per iteration). */
 int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12, float *p21,
                      float *p22, const float *rho_c, const float *I1wx, const float *I1wy,
                      const float *grad, int nx, int ny, double tau, double lambda, double theta,

@@ -545,79 +545,86 @@ __device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, flo
                  ay[2] * (rowI[4] - rowI[2]) + ay[3] * (rowI[5] - rowI[3]));
 }
 
-// Shared-memory-staged gather: a CTA owns a 64x16 tile of output pixels.  The flow is smooth, so
-// the 6x6 neighbourhoods of all its sample points fall into a small bounding box of I1; the CTA
-// reduces that box (min/max of the integer sample positions of its valid pixels), stages it with
-// coalesced, index-clamped loads, and gathers from shared memory.  A tile whose box does not fit
-// (flow range > ~30 px inside one tile) gathers from global memory instead (same arithmetic).
-constexpr int kWarpTW = 64, kWarpTH = 16, kWarpBox = 5120;
+// Shared-memory-staged gather: a CTA owns a 64x16 tile of output pixels.  The box of I1 that covers
+// every 6x6 neighbourhood whose integer sample offset is within +-kWarpM pixels of its pixel (tile
+// grown by kWarpM+2 / kWarpM+3, x origin rounded down to a float4) is staged with cp.async
+// (16-byte copies for interior tiles, index-clamped 4-byte copies on the image border) WHILE the
+// flow and I0 of the tile are being loaded: one memory round trip per tile instead of two.
+// Pixels whose flow exceeds the margin gather from global memory instead (same arithmetic).
+constexpr int kWarpTW = 64, kWarpTH = 16, kWarpM = 8;
+constexpr int kWarpBX = 12;                                    // box starts kWarpBX columns left of the tile
+constexpr int kWarpBW = 88;                                    // >= kWarpBX + 64 + kWarpM + 3, multiple of 4
+constexpr int kWarpBY = kWarpM + 2;
+constexpr int kWarpBH = kWarpTH + 2 * kWarpM + 6;              // rows y0-M-2 .. y0+15+M+3
+
+__device__ __forceinline__ void cp_async4(float *dst, const float *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned int) __cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float *dst, const float *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned int) __cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 
 __global__ void __launch_bounds__(256, 4)
 k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_stride,
        const float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
-       const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv)
+       const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv, int write_grad)
 {
-    __shared__ float s_box[kWarpBox];
-    __shared__ int s_red[8][4];
+    __shared__ __align__(16) float s_box[kWarpBH * kWarpBW];
     const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
+    const int tid = ty * 32 + tx;
     const int b = blockIdx.z;
     const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
     const float *img1 = I1 + (size_t) b * img_stride;
     const float *u = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0;
     const int X0 = blockIdx.x * kWarpTW, Y0 = blockIdx.y * kWarpTH;
+    const int bx0 = X0 - kWarpBX, by0 = Y0 - kWarpBY;
 
+    // ---- stage the box (asynchronously) ---------------------------------------------------------
+    if (bx0 >= 0 && by0 >= 0 && bx0 + kWarpBW <= nx && by0 + kWarpBH <= ny) {
+        const float *src = img1 + (size_t) by0 * pitch + bx0;
+        for (int t = tid; t < kWarpBH * (kWarpBW / 4); t += 256) {
+            const int ly = t / (kWarpBW / 4), l4 = t - ly * (kWarpBW / 4);
+            cp_async16(s_box + ly * kWarpBW + l4 * 4, src + (size_t) ly * pitch + l4 * 4);
+        }
+    } else {
+        for (int ly = ty; ly < kWarpBH; ly += 8) {
+            const float *row = img1 + (size_t) clampi(by0 + ly, 0, ny - 1) * pitch;
+            for (int lx = tx; lx < kWarpBW; lx += 32)
+                cp_async4(s_box + ly * kWarpBW + lx, row + clampi(bx0 + lx, 0, nx - 1));
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---- flow, I0 and sample positions of this thread's four pixels ------------------------------
     float u1[4], u2[4], ftx[4], fty[4], i0v[4];
     int sx[4], sy[4];
     bool inside[4], valid[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { i0v[q] = 0.f; sx[q] = sy[q] = 0; ftx[q] = fty[q] = 0.f; }
-    int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
-#pragma unroll
     for (int q = 0; q < 4; q++) {
         const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
         inside[q] = j < nx && i < ny;
-        valid[q] = false;
-        u1[q] = u2[q] = 0.f;
+        u1[q] = u2[q] = i0v[q] = 0.f;
         if (inside[q]) {
             const size_t p = (size_t) i * pitch + j;
             u1[q] = __ldg(u + p);
             u2[q] = __ldg(u + field_stride + p);
             i0v[q] = __ldg(I0 + (size_t) b * img_stride + p);
-            const float fu = floorf(u1[q]), fv = floorf(u2[q]);
-            const float xf = (float) j + fu, yf = (float) i + fv;
-            valid[q] = xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
-            if (valid[q]) {
-                sx[q] = (int) xf; sy[q] = (int) yf;
-                ftx[q] = u1[q] - fu; fty[q] = u2[q] - fv;
-                bx0 = min(bx0, sx[q]); bx1 = max(bx1, sx[q]);
-                by0 = min(by0, sy[q]); by1 = max(by1, sy[q]);
-            }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-        bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-        by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-        by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    for (int q = 0; q < 4; q++) {
+        const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
+        const float fu = floorf(u1[q]), fv = floorf(u2[q]);
+        const float xf = (float) j + fu, yf = (float) i + fv;
+        valid[q] = inside[q] && xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
+        sx[q] = valid[q] ? (int) xf : 0;
+        sy[q] = valid[q] ? (int) yf : 0;
+        ftx[q] = u1[q] - fu;
+        fty[q] = u2[q] - fv;
     }
-    if (tx == 0) { s_red[ty][0] = bx0; s_red[ty][1] = bx1; s_red[ty][2] = by0; s_red[ty][3] = by1; }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        bx0 = min(bx0, s_red[w][0]); bx1 = max(bx1, s_red[w][1]);
-        by0 = min(by0, s_red[w][2]); by1 = max(by1, s_red[w][3]);
-    }
-    const bool any = bx1 >= bx0;
-    bx0 -= 2; by0 -= 2;
-    const int bw = any ? bx1 + 3 - bx0 + 1 : 0, bh = any ? by1 + 3 - by0 + 1 : 0;
-    const bool staged = any && (long long) bw * bh <= kWarpBox;
-    if (staged) {
-        for (int ly = ty; ly < bh; ly += 8) {
-            const float *row = img1 + (size_t) clampi(by0 + ly, 0, ny - 1) * pitch;
-            for (int lx = tx; lx < bw; lx += 32) s_box[ly * bw + lx] = __ldg(row + clampi(bx0 + lx, 0, nx - 1));
-        }
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
 #pragma unroll
@@ -627,9 +634,10 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
         const size_t p = (size_t) i * pitch + j;
         float w = 0.f, wx = 0.f, wy = 0.f;
         if (valid[q]) {
-            if (staged) {
-                const float *base = s_box + (sy[q] - 2 - by0) * bw + (sx[q] - 2 - bx0);
-                warp_gather([&](int r, int c) { return base[r * bw + c]; }, ftx[q], fty[q], w, wx, wy);
+            const int cx = sx[q] - 2 - bx0, cy = sy[q] - 2 - by0;       // box coordinates of tap (0,0)
+            if (cx >= 0 && cy >= 0 && cx + 6 <= kWarpBW && cy + 6 <= kWarpBH) {
+                const float *base = s_box + cy * kWarpBW + cx;
+                warp_gather([&](int r, int c) { return base[r * kWarpBW + c]; }, ftx[q], fty[q], w, wx, wy);
             } else {
                 const int x = sx[q], y = sy[q];
                 warp_gather([&](int r, int c) {
@@ -641,7 +649,7 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
         c[(size_t) C_IX * field_stride] = wx;
         c[(size_t) C_IY * field_stride] = wy;
         c[(size_t) C_RHO * field_stride] = w - wx * u1[q] - wy * u2[q] - i0v[q];
-        c[(size_t) C_GRAD * field_stride] = grad_of(wx, wy);
+        if (write_grad) c[(size_t) C_GRAD * field_stride] = grad_of(wx, wy);
     }
 }
 
@@ -685,7 +693,7 @@ struct IterParams {
 };
 
 struct Row4 {                    // one image row segment of 4 pixels, everything the update needs
-    float4 u1, u2, ix, iy, rho, grad, p11, p12, p21, p22;
+    float4 u1, u2, ix, iy, rho, p11, p12, p21, p22;      // |grad|^2 is recomputed from ix, iy (grad_of)
 };
 
 // Hardware approximations (MUFU.RCP / MUFU.RSQ based, <= 1-2 ulp): the IEEE-rounded division and
@@ -784,10 +792,9 @@ k_iterate_t1(const IterParams P)
                 r.ix = ldg4(cst + C_IX * fs + o);
                 r.iy = ldg4(cst + C_IY * fs + o);
                 r.rho = ldg4(cst + C_RHO * fs + o);
-                r.grad = ldg4(cst + C_GRAD * fs + o);
             } else {
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                r.u1 = r.u2 = r.p11 = r.p12 = r.p21 = r.p22 = r.ix = r.iy = r.rho = r.grad = z;
+                r.u1 = r.u2 = r.p11 = r.p12 = r.p21 = r.p22 = r.ix = r.iy = r.rho = z;
             }
         };
         // u_new of one row; a12/a22 = p12/p22 of the row above (0 on the first image row)
@@ -812,7 +819,7 @@ k_iterate_t1(const IterParams P)
                 // "+p2" on the last row, p[-1] = 0
                 const bool last_col = (x0 + k >= nx - 1);
                 primal_px(u1, u2, TVL1_F4_GET(r.ix, k), TVL1_F4_GET(r.iy, k), TVL1_F4_GET(r.rho, k),
-                          TVL1_F4_GET(r.grad, k),
+                          grad_of(TVL1_F4_GET(r.ix, k), TVL1_F4_GET(r.iy, k)),
                           last_col ? 0.f : TVL1_F4_GET(r.p11, k), (k == 0) ? l11 : TVL1_F4_GET(r.p11, (k + 3) & 3),
                           last_row ? 0.f : TVL1_F4_GET(r.p12, k), TVL1_F4_GET(a12, k),
                           last_col ? 0.f : TVL1_F4_GET(r.p21, k), (k == 0) ? l21 : TVL1_F4_GET(r.p21, (k + 3) & 3),

@@ -409,13 +409,13 @@ int launch_resident(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int sta
     return TVL1_OK;          // counted on the device like the streaming kernel
 }
 
-int launch_warp(tvl1_ctx *ctx, int s, int B)
+int launch_warp(tvl1_ctx *ctx, int s, int B, int write_grad = 0)
 {
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
     dim3 g(ceil_div(l.nx, kWarpTW), ceil_div(l.ny, kWarpTH), B);
     k_warp<<<g, dim3(32, 8), 0, ctx->stream>>>(w.I0(s), w.I1(s), w.plane(s), w.state, w.plane0,
-                                               w.field_stride, w.set_stride, w.ctl, w.consts, l);
+                                               w.field_stride, w.set_stride, w.ctl, w.consts, l, write_grad);
     CKL(ctx);
     ctx->stats.pixel_warps += (unsigned long long) B * l.nx * l.ny;
     return TVL1_OK;
@@ -1170,7 +1170,7 @@ int tvl1_warp_f32(tvl1_ctx *ctx, const float *I0, const float *I1, const float *
     k_import_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
                                              w.lv[0], buf + 2 * n, buf + 3 * n);
     CKL(ctx);
-    TRY(launch_warp(ctx, 0, 1));
+    TRY(launch_warp(ctx, 0, 1, 1));
     float *outs[4] = { I1wx, I1wy, rho_c, grad };
     const int which[4] = { C_IX, C_IY, C_RHO, C_GRAD };
     for (int k = 0; k < 4; k++) {
