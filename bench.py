@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--e2e-pairs", type=int, default=128, help="frame pairs per rank per e2e step")
     ap.add_argument("--e2e-max-batch", type=int, default=32,
                     help="lock-step chunk of the host-buffer path (chunks alternate between two lanes)")
+    ap.add_argument("--e2e-lanes", type=int, default=3)
     ap.add_argument("--nx", type=int, default=1920)
     ap.add_argument("--ny", type=int, default=1080)
     ap.add_argument("--max-batch", type=int, default=256, help="pairs advanced in lock-step")
@@ -291,6 +292,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     solver.close()
     solver = pkg.TVL1(device=local_rank, max_batch=args.e2e_max_batch, profiling=False)
+    solver.set_lanes(host_lanes=args.e2e_lanes)
     E = min(args.e2e_pairs, P)
     hI0 = torch.empty((E, ny, nx), dtype=torch.float32).pin_memory()
     hI1 = torch.empty_like(hI0).pin_memory()
@@ -319,7 +321,7 @@ def run_ours(args, rank, local_rank, world):
            "h2d_bytes_per_step": 2 * E * nx * ny * 4, "d2h_bytes_per_step": 2 * E * nx * ny * 4,
            "pairs_per_rank_per_step": E, "steps": e_steps, "ms_per_step": e_ms / e_steps,
            "api": "tvl1_solve_batch_f32 (host pinned fp32 in, host fp32 out)", "timer": "wall clock, max over ranks",
-           "lockstep_batch": args.e2e_max_batch, "lanes": 2 if E > args.e2e_max_batch else 1}
+           "lockstep_batch": args.e2e_max_batch, "lanes": min(args.e2e_lanes, -(-E // args.e2e_max_batch))}
     # the device-resident result must equal the host-path result for the same pairs
     same = bool(torch.equal(hu1, u1[:E].cpu()) and torch.equal(hu2, u2[:E].cpu()))
 

@@ -86,8 +86,11 @@ struct tvl1_ctx {
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
     SolveGraph sg;
-    tvl1_ctx *lane2 = nullptr;               // sibling context for copy/compute overlap (host-buffer batches)
-    bool two_lanes = true;
+    static constexpr int kMaxLanes = 4;
+    tvl1_ctx *sib[kMaxLanes - 1] = { nullptr, nullptr, nullptr };   // sibling contexts (extra lanes, same GPU)
+    int host_lanes = 3;                      // lanes used by the host-buffer batch entry points
+    int dev_lanes = 2;                       // lanes used by the device-buffer batch entry point
+    bool is_sibling = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<EventPair> ev_used;
     // staging for the host-buffer entry points
@@ -804,47 +807,48 @@ void add_stats(tvl1_stats &a, const tvl1_stats &b)
     }
 }
 
-// Runs `nchunks` chunks of work over one or two lanes.  Lane 0 is `ctx` on the calling thread; lane 1
-// is a private sibling context on the same GPU (own stream, workspace, solve graph) driven by a
-// second host thread.  The two lanes take alternate chunks and run concurrently on the GPU: the
+// Runs `nchunks` chunks of work over up to four lanes.  Lane 0 is `ctx` on the calling thread; the
+// others are private sibling contexts on the same GPU (own stream, workspace, solve graph), each
+// driven by its own host thread.  Lanes take chunks round-robin and run concurrently on the GPU: the
 // copies of one chunk overlap the kernels of the other, and the sparse tail launches of one lane
 // (few pairs still iterating) are filled by the other lane's work.
 template <class Fn>
-int run_lanes(tvl1_ctx *ctx, int nchunks, Fn &&chunk_fn)
+int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
 {
-    tvl1_ctx *lanes[2] = { ctx, nullptr };
+    tvl1_ctx *lanes[tvl1_ctx::kMaxLanes] = { ctx, nullptr, nullptr, nullptr };
     int nlanes = 1;
-    if (nchunks > 1 && ctx->two_lanes) {
-        if (!ctx->lane2) {
-            if (tvl1_create(ctx->device, &ctx->lane2) != TVL1_OK) {
-                ctx->err = std::string("second lane: ") + tvl1_last_error(nullptr);
+    if (!ctx->is_sibling)
+        nlanes = std::max(1, std::min(std::min(want_lanes, nchunks), (int) tvl1_ctx::kMaxLanes));
+    for (int l = 1; l < nlanes; l++) {
+        tvl1_ctx *&sb = ctx->sib[l - 1];
+        if (!sb) {
+            if (tvl1_create(ctx->device, &sb) != TVL1_OK) {
+                ctx->err = std::string("extra lane: ") + tvl1_last_error(nullptr);
                 return TVL1_ERR_CUDA;
             }
-            ctx->lane2->two_lanes = false;
+            sb->is_sibling = true;
         }
-        ctx->lane2->max_batch = ctx->max_batch;
-        ctx->lane2->profiling = ctx->profiling;
-        ctx->lane2->use_graph = ctx->use_graph;
-        ctx->lane2->use_resident = ctx->use_resident;
-        reset_stats(ctx->lane2);
-        lanes[1] = ctx->lane2;
-        nlanes = 2;
+        sb->max_batch = ctx->max_batch;
+        sb->profiling = ctx->profiling;
+        sb->use_graph = ctx->use_graph;
+        sb->use_resident = ctx->use_resident;
+        reset_stats(sb);
+        lanes[l] = sb;
     }
-    int rcs[2] = { TVL1_OK, TVL1_OK };
+    int rcs[tvl1_ctx::kMaxLanes] = { TVL1_OK, TVL1_OK, TVL1_OK, TVL1_OK };
     auto work = [&](int l) {
         tvl1_ctx *c = lanes[l];
         cudaSetDevice(c->device);
         for (int k = l; k < nchunks && rcs[l] == TVL1_OK; k += nlanes) rcs[l] = chunk_fn(c, k);
         resolve_events(c);
     };
-    if (nlanes == 2) {
-        std::thread t(work, 1);
-        work(0);
-        t.join();
-        add_stats(ctx->stats, ctx->lane2->stats);
-        if (rcs[1] != TVL1_OK) { ctx->err = ctx->lane2->err; return rcs[1]; }
-    } else {
-        work(0);
+    std::vector<std::thread> threads;
+    for (int l = 1; l < nlanes; l++) threads.emplace_back(work, l);
+    work(0);
+    for (auto &t : threads) t.join();
+    for (int l = 1; l < nlanes; l++) {
+        add_stats(ctx->stats, lanes[l]->stats);
+        if (rcs[l] != TVL1_OK && rcs[0] == TVL1_OK) { ctx->err = lanes[l]->err; rcs[0] = rcs[l]; }
     }
     return rcs[0];
 }
@@ -865,7 +869,7 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     const int Bmax = std::min(npairs, ctx->max_batch);
     const int nchunks = ceil_div(npairs, Bmax);
     const int nstat = (multiscale ? prm->nscales : 1) * prm->warps;
-    return run_lanes(ctx, nchunks, [&](tvl1_ctx *c, int k) -> int {
+    return run_lanes(ctx, nchunks, ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
         tvl1_ctx *ctx = c;   // for CK / TRY
         TRY(ensure_stage(ctx, (size_t) Bmax * n * sizeof(T), f64));
         const int first = k * Bmax, B = std::min(Bmax, npairs - first);
@@ -933,7 +937,7 @@ int tvl1_create(int device, tvl1_ctx **out)
 void tvl1_destroy(tvl1_ctx *ctx)
 {
     if (!ctx) return;
-    if (ctx->lane2) { tvl1_destroy(ctx->lane2); ctx->lane2 = nullptr; }
+    for (auto &sb : ctx->sib) { if (sb) tvl1_destroy(sb); sb = nullptr; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_graph(ctx->sg, ctx->ev_pool);
@@ -957,6 +961,15 @@ int tvl1_set_profiling(tvl1_ctx *ctx, int on)
 {
     if (!ctx) return TVL1_ERR_ARG;
     ctx->profiling = on != 0;
+    return TVL1_OK;
+}
+
+int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes)
+{
+    if (!ctx || host_lanes < 1 || dev_lanes < 1 || host_lanes > tvl1_ctx::kMaxLanes || dev_lanes > tvl1_ctx::kMaxLanes)
+        return TVL1_ERR_ARG;
+    ctx->host_lanes = host_lanes;
+    ctx->dev_lanes = dev_lanes;
     return TVL1_OK;
 }
 
@@ -1026,7 +1039,7 @@ int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const 
     const size_t n = (size_t) nx * ny;
     const int nstat = prm->nscales * prm->warps;
     const int Bmax = std::min(npairs, ctx->max_batch);
-    return run_lanes(ctx, ceil_div(npairs, Bmax), [&](tvl1_ctx *c, int k) -> int {
+    return run_lanes(ctx, ceil_div(npairs, Bmax), ctx->dev_lanes, [&](tvl1_ctx *c, int k) -> int {
         const int first = k * Bmax, B = std::min(Bmax, npairs - first);
         const size_t off = (size_t) first * n;
         return run_multiscale(c, B, dI0 + off, dI1 + off, du1 + off, du2 + off, nx, ny, *prm,

@@ -118,6 +118,9 @@ class TVL1:
     def set_profiling(self, on):
         self._ck(self.lib.tvl1_set_profiling(self.ctx, C.c_int(1 if on else 0)))
 
+    def set_lanes(self, host_lanes=3, dev_lanes=2):
+        self._ck(self.lib.tvl1_set_lanes(self.ctx, C.c_int(int(host_lanes)), C.c_int(int(dev_lanes))))
+
     def set_max_batch(self, pairs):
         self._ck(self.lib.tvl1_set_max_batch(self.ctx, C.c_int(int(pairs))))
 
