@@ -89,7 +89,7 @@ int tvl1_set_profiling(tvl1_ctx *ctx, int on);     /* bracket kernels with CUDA 
 int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs);  /* pairs advanced in lock-step per workspace (default 32) */
 /* Batches larger than max_batch are cut into chunks that up to 4 lanes (sibling contexts on the same
  * GPU, one host thread each) process concurrently: copies of one chunk overlap kernels of another.
- * host_lanes: host-buffer entry points (default 3); dev_lanes: device-buffer entry point (default 2). */
+ * host_lanes: host-buffer entry points (default 4); dev_lanes: device-buffer entry point (default 2). */
 int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes);
 int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out);
 void *tvl1_get_stream(const tvl1_ctx *ctx);        /* the cudaStream_t all work of this context is issued on */

@@ -88,7 +88,7 @@ struct tvl1_ctx {
     SolveGraph sg;
     static constexpr int kMaxLanes = 4;
     tvl1_ctx *sib[kMaxLanes - 1] = { nullptr, nullptr, nullptr };   // sibling contexts (extra lanes, same GPU)
-    int host_lanes = 3;                      // lanes used by the host-buffer batch entry points
+    int host_lanes = 4;                      // lanes used by the host-buffer batch entry points
     int dev_lanes = 2;                       // lanes used by the device-buffer batch entry point
     bool is_sibling = false;
     std::vector<cudaEvent_t> ev_pool;
