@@ -135,6 +135,7 @@ def cpu_sample(args, budget_s, max_pairs=4):
     import numpy as np
     from optical_flow_1_b200 import synth
     cpu, kind = cpu_solver()
+    cpu.set_threads(os.cpu_count() or 1)
     times = []
     t_all = time.perf_counter()
     for b in range(max_pairs):
@@ -159,6 +160,7 @@ def run_reference(args, rank, world):
     import numpy as np
     from optical_flow_1_b200 import synth
     cpu, kind = cpu_solver()
+    cpu.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; use every host core
     I0, I1 = synth.make_pair(args.nx, args.ny, seed=1234)
     I0, I1 = I0.astype(np.float64), I1.astype(np.float64)
     for _ in range(args.warmup):
@@ -196,30 +198,23 @@ def run_ours(args, rank, local_rank, world):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        pkg.shard.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return pkg.shard.max_over_ranks(x, dev)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return pkg.shard.sum_over_ranks(x, dev)
 
     nx, ny, P = args.nx, args.ny, args.pairs
     solver = pkg.TVL1(device=local_rank, max_batch=args.max_batch, profiling=True)
     stream = torch.cuda.ExternalStream(solver.stream(), device=dev)
 
-    # synthetic inputs generated straight into HBM; rank r uses seeds 1234 + r*P ...
-    I0, I1 = pkg.synth.make_batch_torch(P, nx, ny, seed=1234 + rank * P, device=dev)
+    # synthetic inputs generated straight into HBM; weak scaling: rank r holds pairs [r*P, (r+1)*P)
+    # of a world*P-pair job, pair b made from seed 1234 + b
+    first, _ = pkg.shard.shard_range(world * P, rank, world)
+    I0, I1 = pkg.synth.make_batch_torch(P, nx, ny, seed=pkg.shard.pair_seed(1234, first), device=dev)
     u1 = torch.empty_like(I0)
     u2 = torch.empty_like(I0)
     torch.cuda.synchronize()

@@ -6,4 +6,4 @@ __path__.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.absp
                                  "optical-flow-1_b200"))
 
 from .tvl1 import *  # noqa: F401,F403,E402
-from . import synth  # noqa: F401,E402
+from . import synth, shard  # noqa: F401,E402
