@@ -170,12 +170,16 @@ int iterate_parts(const Level &l)
 // Smallest cluster (1,2,4,8,16 CTAs) whose row bands fit one SM each: <= 2048 float4 groups per CTA
 // (512 threads x 4) and the six state planes of the band in <= 227 KB of shared memory.  Returns 0
 // when the level has to stream through HBM instead.
-int pick_cluster(tvl1_ctx *ctx, const Level &l, int *rows_out)
+int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
 {
     if (!ctx->use_resident) return 0;
     static bool attr_done[64] = { false };
+    int best = 0;
     for (int C = 1; C <= kResMaxCluster; C *= 2) {
         if (ctx->force_cluster && C != ctx->force_cluster) continue;
+        // a small batch cannot fill the GPU with minimal clusters: keep growing the cluster (shorter
+        // bands, shorter iterations) while all clusters of the batch still run concurrently
+        if (best && !ctx->force_cluster && B * C > ctx->sm_count) break;
         const int RB = ceil_div(l.ny, C);
         if ((C - 1) * RB >= l.ny) continue;                        // every CTA needs at least one row
         if (RB * (l.pitch / 4) > kResThreads * kResQuads) continue;
@@ -204,9 +208,10 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int *rows_out)
             continue;
         }
         *rows_out = RB;
-        return C;
+        best = C;
+        if (ctx->force_cluster) break;
     }
-    return 0;
+    return best;
 }
 
 int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride)
@@ -238,7 +243,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
         w.pyr_off[s] = off;
         off += 2 * (size_t) B * w.plane(s);
         parts = std::max(parts, iterate_parts(w.lv[s]));
-        w.res_cluster[s] = pick_cluster(ctx, w.lv[s], &w.res_rows[s]);
+        w.res_cluster[s] = pick_cluster(ctx, w.lv[s], B, &w.res_rows[s]);
     }
     w.plane0 = w.plane(0);
     w.field_stride = (size_t) B * w.plane0;

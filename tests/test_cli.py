@@ -1,0 +1,76 @@
+"""The reference's UNMODIFIED command-line program (src/tvl1flow_main.cpp) linked against
+libtvl1_b200.so (cli/tvl1flow) and, for A/B, against the reference's own CPU solver
+(cli/tvl1flow_ref); image IO through cli/iio_lite.cpp.  The .flo file is the only on-disk contract
+(src/iio.cpp:2754-2776)."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import _cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "cli", "tvl1flow")
+CLI_REF = os.path.join(ROOT, "cli", "tvl1flow_ref")
+
+
+def write_pgm(path, img):
+    img = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"P5\n# synthetic\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(img.tobytes())
+    return img
+
+
+def read_flo(path):
+    with open(path, "rb") as f:
+        assert f.read(4) == b"PIEH"
+        w, h = struct.unpack("<ii", f.read(8))
+        d = np.frombuffer(f.read(), np.float32).reshape(h, w, 2)
+    return d[..., 0], d[..., 1]
+
+
+def run_cli(exe, tmp, nx=96, ny=72, args=("0", "0.25", "0.15", "0.3", "3", "0.5", "3", "0.01", "1")):
+    I0, I1 = _cases.synth.make_pair(nx, ny, seed=77, scale=0.4)
+    q0 = write_pgm(tmp / "a.pgm", I0)
+    q1 = write_pgm(tmp / "b.pgm", I1)
+    out = tmp / ("out_%s.flo" % os.path.basename(exe))
+    p = subprocess.run([exe, str(tmp / "a.pgm"), str(tmp / "b.pgm"), str(out), *args],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    iters = [int(m) for m in re.findall(r"Warping: \d+, Iterations: (\d+), Error:", p.stderr)]
+    scales = re.findall(r"Scale (\d+): (\d+)x(\d+)", p.stderr)
+    return q0, q1, read_flo(out), iters, scales, p.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(CLI_REF), reason="cli/tvl1flow_ref not built (needs /root/reference)")
+def test_reference_cli_with_iio_lite_matches_oracle(tmp_path, oracle_f64):
+    """CPU: PGM in -> reference solver -> .flo out, through our IO shim, equals the oracle on the
+    same 8-bit images (validates iio_lite.cpp's readers and the .flo writer)."""
+    q0, q1, (u1, u2), iters, scales, err = run_cli(CLI_REF, tmp_path)
+    r1, r2, riters, _ = oracle_f64.multiscale(q0.astype(np.float64), q1.astype(np.float64),
+                                              nscales=3, zfactor=0.5, warps=3, eps=0.01)
+    assert iters == riters.ravel().tolist()
+    assert [(int(a), int(b), int(c)) for a, b, c in scales] == [(2, 24, 18), (1, 48, 36), (0, 96, 72)]
+    assert np.array_equal(u1, r1.astype(np.float32)) and np.array_equal(u2, r2.astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(CLI), reason="cli/tvl1flow not built")
+def test_cli_drop_in_on_gpu(tmp_path, oracle_f64):
+    """GPU: the same unmodified main() linked against libtvl1_b200.so; same verbose lines, same
+    iteration counts, flow within the north_star tolerance."""
+    q0, q1, (u1, u2), iters, scales, err = run_cli(CLI, tmp_path)
+    r1, r2, riters, _ = oracle_f64.multiscale(q0.astype(np.float64), q1.astype(np.float64),
+                                              nscales=3, zfactor=0.5, warps=3, eps=0.01)
+    assert iters == riters.ravel().tolist(), err
+    assert [(int(a), int(b), int(c)) for a, b, c in scales] == [(2, 24, 18), (1, 48, 36), (0, 96, 72)]
+    d = np.concatenate([np.abs(u1 - r1).ravel(), np.abs(u2 - r2).ravel()])
+    assert d.mean() <= 1e-3 and d.max() <= 1e-2
+    # the CLI clamps nscales by image size (tvl1flow_main.cpp:185-188) and warns about bad values
+    _, _, _, iters2, scales2, err2 = run_cli(CLI, tmp_path, args=("0", "0.9", "0.15", "0.3", "100", "0.5", "2", "0.01", "1"))
+    assert "tau changed to 0.25" in err2
+    assert len(scales2) == 3 and len(iters2) == 6
