@@ -115,6 +115,25 @@ int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const 
                              float *du1, float *du2, int nx, int ny, const tvl1_params *prm,
                              int *iters_out, double *errs_out);
 
+/* -- row-band mode: ONE image pair split over several GPUs ----------------------- */
+/* One context per rank/GPU.  Rank 0 makes an id (tvl1_band_unique_id), the caller distributes the
+ * TVL1_NCCL_ID_BYTES bytes to every rank by whatever means it has (torch.distributed broadcast, MPI,
+ * a file), every rank calls tvl1_band_init, then all ranks call tvl1_band_solve_* together with the
+ * same full images and parameters.  Levels with at least min_split_rows rows are cut into row bands
+ * whose 1-row halos (flow + dual variables) and error sum travel over NCCL every iteration; smaller
+ * levels are solved redundantly on every rank.  Every rank receives the full flow.  (A negative
+ * min_split_rows uses |min_split_rows| and takes the band code path even with a single rank.) */
+#define TVL1_NCCL_ID_BYTES 128
+int tvl1_band_unique_id(unsigned char *id_out /* [TVL1_NCCL_ID_BYTES] */);
+int tvl1_band_init(tvl1_ctx *ctx, int rank, int world, const unsigned char *id /* [TVL1_NCCL_ID_BYTES] */);
+int tvl1_band_solve_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2, int nx,
+                        int ny, const tvl1_params *prm, int min_split_rows, int *iters_out,
+                        double *errs_out);                                   /* HOST buffers */
+int tvl1_band_solve_dev_f32(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, float *du2,
+                            int nx, int ny, const tvl1_params *prm, int min_split_rows, int *iters_out,
+                            double *errs_out);                               /* DEVICE buffers */
+void tvl1_band_rows(int ny, int rank, int world, int *row_begin, int *row_end);  /* rows a rank owns */
+
 /* -- one level: Dual_TVL1_optic_flow (src/tvl1flow.cpp:46-212) ----------------------------- */
 /* u1,u2 are in/out (the initial flow is used, tvl1flow.cpp:94); nscales/zfactor of prm ignored;
  * iters_out/errs_out are [warps]. */

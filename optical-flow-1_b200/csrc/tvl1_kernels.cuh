@@ -293,7 +293,7 @@ constexpr int kZiTW = 64, kZiTH = 16, kZiCW = kZiTW + 8, kZiCH = kZiTH + 8;
 __global__ void __launch_bounds__(256)
 k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
                const PairCtl *__restrict__ ctl, Level coarse, Level fine, double fx, double fy,
-               float scale)
+               float scale, int row_begin, int row_end)
 {
     __shared__ float s_c[2][kZiCH][kZiCW];
     const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
@@ -301,8 +301,8 @@ k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, si
     const int cur = ctl[b].cur;
     const float *src = state + (size_t) cur * set_stride + (size_t) b * plane0;
     float *dst = state + (size_t) (cur ^ 1) * set_stride + (size_t) b * plane0;
-    const int X0 = blockIdx.x * kZiTW, Y0 = blockIdx.y * kZiTH;
-    const int X1 = min(X0 + kZiTW, fine.nx) - 1, Y1 = min(Y0 + kZiTH, fine.ny) - 1;
+    const int X0 = blockIdx.x * kZiTW, Y0 = row_begin + blockIdx.y * kZiTH;
+    const int X1 = min(X0 + kZiTW, fine.nx) - 1, Y1 = min(Y0 + kZiTH, row_end) - 1;
     // coarse footprint: taps x-1 .. x+2 around x = (int)(j1 / fx), monotone in j1
     const int xlo = (int) (X0 / fx) - 1, xhi = (int) (X1 / fx) + 2;
     const int ylo = (int) (Y0 / fy) - 1, yhi = (int) (Y1 / fy) + 2;
@@ -322,7 +322,7 @@ k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, si
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int j1 = X0 + tx + 32 * (q & 1), i1 = Y0 + ty + 8 * (q >> 1);
-        if (j1 >= fine.nx || i1 >= fine.ny) continue;
+        if (j1 >= fine.nx || i1 >= row_end) continue;
         const double j2 = j1 / fx, i2 = i1 / fy;
         const size_t o = (size_t) i1 * fine.pitch + j1;
         if (!staged) {
@@ -366,6 +366,28 @@ __global__ void k_zero_fields(float *__restrict__ state, size_t plane0, size_t f
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4;
          i += (size_t) gridDim.x * blockDim.x)
         dst[i] = z;
+}
+
+// Row-band mode (one image split over several GPUs): after the all-reduce of the per-rank sums every
+// rank applies the stopping rule of src/tvl1flow.cpp:113,162 to the same number.
+__global__ void k_band_decide(PairCtl *ctl, LoopCtl *loop, const double *band_sum, double npix, double eps2,
+                              int max_iter, int *stat_iters, double *stat_errs, int stat_slot,
+                              unsigned long long *px_iters, unsigned long long own_pixels)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || !ctl->active) return;
+    const double error = *band_sum / npix;
+    const int n = ctl->n + 1;
+    ctl->n = n;
+    ctl->err = error;
+    ctl->cur ^= 1;
+    atomicAdd(px_iters, own_pixels);
+    if (!(error > eps2 && n < max_iter)) {
+        ctl->active = 0;
+        stat_iters[stat_slot] = n;
+        stat_errs[stat_slot] = error;
+        loop->max_n = n;
+        loop->active_pairs = 0;
+    }
 }
 
 // start of a warp step: n = 0, error = INFINITY (src/tvl1flow.cpp:111-112)
@@ -569,7 +591,8 @@ __device__ __forceinline__ void cp_async16(float *dst, const float *src)
 __global__ void __launch_bounds__(256, 4)
 k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_stride,
        const float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
-       const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv, int write_grad)
+       const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv, int write_grad,
+       int row_begin, int row_end)
 {
     __shared__ __align__(16) float s_box[kWarpBH * kWarpBW];
     const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
@@ -578,7 +601,7 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
     const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
     const float *img1 = I1 + (size_t) b * img_stride;
     const float *u = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0;
-    const int X0 = blockIdx.x * kWarpTW, Y0 = blockIdx.y * kWarpTH;
+    const int X0 = blockIdx.x * kWarpTW, Y0 = row_begin + blockIdx.y * kWarpTH;
     const int bx0 = X0 - kWarpBX, by0 = Y0 - kWarpBY;
 
     // ---- stage the box (asynchronously) ---------------------------------------------------------
@@ -604,7 +627,7 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
-        inside[q] = j < nx && i < ny;
+        inside[q] = j < nx && i < row_end;
         u1[q] = u2[q] = i0v[q] = 0.f;
         if (inside[q]) {
             const size_t p = (size_t) i * pitch + j;
@@ -679,6 +702,9 @@ struct IterParams {
     LoopCtl *loop;
     cudaGraphConditionalHandle cond;   // while-node handle when launched from the solve graph, else 0
     int use_cond;
+    int row_begin, row_end;            // rows this launch owns (whole image: 0, ny; a row band otherwise)
+    double *band_sum;                  // row-band mode: the rank's raw sum of squared updates goes here
+                                       // and k_band_decide applies the stopping rule after the all-reduce
     int *stat_iters;             // [B][stat_stride]
     double *stat_errs;
     unsigned long long *px_iters;  // [level] pixel-iterations; [TVL1_MAX_LEVELS + level] launches
@@ -772,14 +798,14 @@ k_iterate_t1(const IterParams P)
     const size_t fs = P.field_stride;
 
     const int x0 = blockIdx.x * 124 + lane * 4;
-    const int ys = (blockIdx.y * WY + warp) * R;
-    const int ye = min(ys + R, ny);
+    const int ys = P.row_begin + (blockIdx.y * WY + warp) * R;
+    const int ye = min(ys + R, P.row_end);
     const bool in_alloc = x0 < pitch;               // float4 lies inside the row allocation
     const bool owner = in_alloc && lane < 31 && x0 < nx;
 
     float err = 0.f;
 
-    if (ys < ny) {                                  // warp-uniform
+    if (ys < P.row_end) {                           // warp-uniform
         auto load_row = [&](int y, Row4 &r) {
             if (in_alloc) {
                 const size_t o = (size_t) y * pitch + x0;
@@ -914,6 +940,11 @@ k_iterate_t1(const IterParams P)
     if (threadIdx.x == 0) {
         double tot = 0.0;
         for (int w = 0; w < WY; w++) tot += s_part[w];
+        if (P.band_sum) {            // row-band mode: the other ranks' rows are still missing
+            *P.band_sum = tot;
+            ctl->arrive = 0u;
+            return;
+        }
         const double error = tot / ((double) nx * (double) ny);   // src/tvl1flow.cpp:162
         const int n = ctl->n + 1;
         ctl->n = n;

@@ -7,11 +7,15 @@
 #include "../../include/tvl1_b200.h"
 #include "tvl1_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -48,6 +52,7 @@ struct Workspace {
     // cluster-resident iteration kernel: cluster size per level (0 = streaming kernel) and band height
     std::vector<int> res_cluster, res_rows;
     int resident_key = -1;
+    int row_pad = 1;
 
     size_t plane(int s) const { return (size_t) lv[s].pitch * lv[s].ny; }
     float *I0(int s) const { return pyr + pyr_off[s]; }
@@ -86,6 +91,11 @@ struct tvl1_ctx {
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
     SolveGraph sg;
+    // row-band mode (one image over several GPUs)
+    void *nccl_lib = nullptr;
+    void *nccl_comm = nullptr;
+    int band_rank = 0, band_world = 1;
+    double *d_band_sum = nullptr;
     static constexpr int kMaxLanes = 4;
     tvl1_ctx *sib[kMaxLanes - 1] = { nullptr, nullptr, nullptr };   // sibling contexts (extra lanes, same GPU)
     int host_lanes = 4;                      // lanes used by the host-buffer batch entry points
@@ -214,17 +224,20 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
     return best;
 }
 
-int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride)
+int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride,
+                     int row_pad = 1)
 {
     Workspace &w = ctx->ws;
     if (w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
-        w.stat_stride >= stat_stride && w.resident_key == (ctx->use_resident ? 1 + ctx->force_cluster : 0))
+        w.stat_stride >= stat_stride && w.resident_key == (ctx->use_resident ? 1 + ctx->force_cluster : 0) &&
+        w.row_pad == row_pad)
         return TVL1_OK;
     free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(w);
     w.nx = nx; w.ny = ny; w.nscales = nscales; w.zfactor = zfactor; w.B = B;
     w.stat_stride = stat_stride;
     w.resident_key = ctx->use_resident ? 1 + ctx->force_cluster : 0;
+    w.row_pad = row_pad;
     w.lv.resize(nscales);
     w.pyr_off.resize(nscales);
     w.res_cluster.assign(nscales, 0);
@@ -245,7 +258,8 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
         parts = std::max(parts, iterate_parts(w.lv[s]));
         w.res_cluster[s] = pick_cluster(ctx, w.lv[s], B, &w.res_rows[s]);
     }
-    w.plane0 = w.plane(0);
+    // row-band mode gathers equal-sized bands in place: round the rows of a plane up to a multiple of the rank count
+    w.plane0 = (size_t) w.lv[0].pitch * round_up(w.lv[0].ny, row_pad);
     w.field_stride = (size_t) B * w.plane0;
     w.set_stride = (size_t) F_COUNT * w.field_stride;
     w.parts_per_pair = parts;
@@ -360,6 +374,7 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
     IterParams P;
     P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
     P.loop = w.loop; P.cond = 0; P.use_cond = 0;
+    P.row_begin = 0; P.row_end = lv.ny; P.band_sum = nullptr;
     P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
     P.px_iters = w.counters;
     P.level = std::min(level, TVL1_MAX_LEVELS - 1);
@@ -375,11 +390,12 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
 
 int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
 {
-    if (P.lv.ny >= 512) {     // tall levels: longer strips, half the CTAs and half the halo rows
-        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(P.lv.ny, 2 * kIterR * kIterWY), B);
+    const int rows = P.row_end - P.row_begin;
+    if (rows >= 512) {        // tall levels: longer strips, half the CTAs and half the halo rows
+        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(rows, 2 * kIterR * kIterWY), B);
         k_iterate_t1<2 * kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else {
-        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(P.lv.ny, kIterR * kIterWY), B);
+        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(rows, kIterR * kIterWY), B);
         k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
@@ -417,15 +433,17 @@ int launch_resident(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int sta
     return TVL1_OK;          // counted on the device like the streaming kernel
 }
 
-int launch_warp(tvl1_ctx *ctx, int s, int B, int write_grad = 0)
+int launch_warp(tvl1_ctx *ctx, int s, int B, int write_grad = 0, int row_begin = 0, int row_end = -1)
 {
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
-    dim3 g(ceil_div(l.nx, kWarpTW), ceil_div(l.ny, kWarpTH), B);
+    if (row_end < 0) row_end = l.ny;
+    dim3 g(ceil_div(l.nx, kWarpTW), ceil_div(row_end - row_begin, kWarpTH), B);
     k_warp<<<g, dim3(32, 8), 0, ctx->stream>>>(w.I0(s), w.I1(s), w.plane(s), w.state, w.plane0,
-                                               w.field_stride, w.set_stride, w.ctl, w.consts, l, write_grad);
+                                               w.field_stride, w.set_stride, w.ctl, w.consts, l, write_grad,
+                                               row_begin, row_end);
     CKL(ctx);
-    ctx->stats.pixel_warps += (unsigned long long) B * l.nx * l.ny;
+    ctx->stats.pixel_warps += (unsigned long long) B * l.nx * (row_end - row_begin);
     return TVL1_OK;
 }
 
@@ -577,7 +595,7 @@ int enqueue_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool mu
         dim3 g(ceil_div(f.nx, kZiTW), ceil_div(f.ny, kZiTH), B);
         k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
                                                   c, f, (double) f.nx / c.nx, (double) f.ny / c.ny,
-                                                  (float) (1.0 / prm.zfactor));
+                                                  (float) (1.0 / prm.zfactor), 0, f.ny);
         CKL(ctx);
         k_flip_cur<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, B);
         CKL(ctx);
@@ -622,23 +640,18 @@ int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multis
     return TVL1_OK;
 }
 
-// Dual_TVL1_optic_flow_multiscale for B <= max_batch pairs, device-resident dense inputs/outputs.
-int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, float *du1, float *du2,
-                   int nx, int ny, const tvl1_params &prm, int *iters_out, double *errs_out)
+// Resets the per-solve device state and builds both image pyramids (src/tvl1flow.cpp:255-275).
+int build_pyramid(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, int nx, int ny, const tvl1_params &prm)
 {
-    const int ns = prm.nscales;
-    const int nstat = ns * prm.warps;
-    TRY(ensure_workspace(ctx, nx, ny, ns, prm.zfactor, B, nstat));
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
-
+    const int ns = prm.nscales;
     // validate the blur windows first: the reference throws before producing anything
     GaussTaps pre, zoom;
     TRY(check_sigma(ctx, TVL1_PRESMOOTHING_SIGMA, nx, pre));
     const double zsigma = TVL1_ZOOM_SIGMA_ZERO * std::sqrt(1.0 / (prm.zfactor * prm.zfactor) - 1.0);
     for (int s = 1; s < ns; s++) TRY(check_sigma(ctx, zsigma, w.lv[s - 1].nx, zoom));
 
-    Span total(ctx, 2);
     CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
@@ -670,8 +683,21 @@ int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, flo
             CKL(ctx);
         }
     }
+    return TVL1_OK;
+}
 
-    pyr.end();
+// Dual_TVL1_optic_flow_multiscale for B <= max_batch pairs, device-resident dense inputs/outputs.
+int run_multiscale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, float *du1, float *du2,
+                   int nx, int ny, const tvl1_params &prm, int *iters_out, double *errs_out)
+{
+    const int ns = prm.nscales;
+    const int nstat = ns * prm.warps;
+    TRY(ensure_workspace(ctx, nx, ny, ns, prm.zfactor, B, nstat));
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+
+    Span total(ctx, 2);
+    TRY(build_pyramid(ctx, B, dI0, dI1, nx, ny, prm));
     TRY(run_coarse_to_fine(ctx, B, prm, true));
     {
         Span ex(ctx, 5);
@@ -882,6 +908,233 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     });
 }
 
+
+// =================================================================================================
+// Row-band mode: ONE image pair split over the GPUs of a box (BASELINE configs[3..4]).
+// Every rank holds the full images and builds the full pyramids (cheap); coarse levels are solved
+// redundantly and identically by every rank; a level with at least `min_split_rows` rows is cut into
+// contiguous row bands.  Per primal-dual iteration of a split level a rank
+//   1. runs the fused iteration kernel on its own rows (halo rows are ordinary rows of its
+//      full-size planes),
+//   2. all-reduces the sum of squared updates (one double) and exchanges the 1-row halos with its
+//      band neighbours over NCCL send/recv (NVLink): row r0 of {u1,u2,p11,p12,p21,p22} goes up,
+//      row r1-1 of {p12,p22} goes down -- both ping-pong sets, so the exchange does not depend on
+//      the device-side parity,
+//   3. applies the stopping rule of src/tvl1flow.cpp:113 to the reduced error (k_band_decide), the
+//      same number on every rank.
+// After a split level the flow bands are all-gathered in place so that every rank can up-sample
+// (zoom_in) its band of the next level, and the caller of every rank receives the full flow.
+// NCCL is bound at run time (dlopen) so that the library has no link-time dependency on it.
+// =================================================================================================
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    void *lib = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+
+const char *load_nccl()
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mutex);
+    if (g_nccl.lib) return nullptr;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return "libnccl.so.2 not found";
+#define TVL1_SYM(field, name)                                                        \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));         \
+    if (!g_nccl.field) return "missing NCCL symbol " name
+    TVL1_SYM(GetUniqueId, "ncclGetUniqueId");
+    TVL1_SYM(CommInitRank, "ncclCommInitRank");
+    TVL1_SYM(CommDestroy, "ncclCommDestroy");
+    TVL1_SYM(Send, "ncclSend");
+    TVL1_SYM(Recv, "ncclRecv");
+    TVL1_SYM(AllReduce, "ncclAllReduce");
+    TVL1_SYM(AllGather, "ncclAllGather");
+    TVL1_SYM(GroupStart, "ncclGroupStart");
+    TVL1_SYM(GroupEnd, "ncclGroupEnd");
+    TVL1_SYM(GetErrorString, "ncclGetErrorString");
+#undef TVL1_SYM
+    g_nccl.lib = h;
+    return nullptr;
+}
+
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            ctx->err = std::string(#call " failed: ") + g_nccl.GetErrorString(r_);                 \
+            return TVL1_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+void band_rows(int ny, int rank, int world, int *r0, int *r1, int *rows_per)
+{
+    *rows_per = ceil_div(ny, world);
+    *r0 = std::min(ny, rank * *rows_per);
+    *r1 = std::min(ny, *r0 + *rows_per);
+}
+
+// all-reduce of the error sum + halo exchange of both ping-pong sets, one NCCL group
+int band_exchange(tvl1_ctx *ctx, int s, bool with_sum)
+{
+    const Workspace &w = ctx->ws;
+    const Level &l = w.lv[s];
+    ncclComm_t comm = (ncclComm_t) ctx->nccl_comm;
+    cudaStream_t st = ctx->stream;
+    int r0, r1, rows_per;
+    band_rows(l.ny, ctx->band_rank, ctx->band_world, &r0, &r1, &rows_per);
+    const int up = ctx->band_rank - 1, dn = ctx->band_rank + 1;
+    const bool has_up = up >= 0 && r0 > 0 && r0 < l.ny, has_dn = dn < ctx->band_world && r1 < l.ny && r1 > r0;
+    const size_t cnt = l.pitch;
+    auto row = [&](int set, int f, int y) { return w.state + (size_t) set * w.set_stride + (size_t) f * w.field_stride + (size_t) y * l.pitch; };
+    NK(g_nccl.GroupStart());
+    if (with_sum) NK(g_nccl.AllReduce(ctx->d_band_sum, ctx->d_band_sum, 1, ncclDouble, ncclSum, comm, st));
+    for (int set = 0; set < 2; set++) {
+        if (has_dn) {   // link (me, me+1): my last row of p12,p22 goes down; its first row of everything comes up
+            NK(g_nccl.Send(row(set, F_P12, r1 - 1), cnt, ncclFloat, dn, comm, st));
+            NK(g_nccl.Send(row(set, F_P22, r1 - 1), cnt, ncclFloat, dn, comm, st));
+            for (int f = 0; f < F_COUNT; f++) NK(g_nccl.Recv(row(set, f, r1), cnt, ncclFloat, dn, comm, st));
+        }
+        if (has_up) {   // link (me-1, me)
+            NK(g_nccl.Recv(row(set, F_P12, r0 - 1), cnt, ncclFloat, up, comm, st));
+            NK(g_nccl.Recv(row(set, F_P22, r0 - 1), cnt, ncclFloat, up, comm, st));
+            for (int f = 0; f < F_COUNT; f++) NK(g_nccl.Send(row(set, f, r0), cnt, ncclFloat, up, comm, st));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    return TVL1_OK;
+}
+
+int band_read_ctl(tvl1_ctx *ctx, PairCtl *out)
+{
+    CK(cudaMemcpyAsync(out, ctx->ws.ctl, sizeof(PairCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.host_syncs++;
+    return TVL1_OK;
+}
+
+// one split level: src/tvl1flow.cpp:46-212 on this rank's rows
+int band_level(tvl1_ctx *ctx, int s, const tvl1_params &prm, int stat_base, int &hint)
+{
+    const Workspace &w = ctx->ws;
+    const Level &l = w.lv[s];
+    cudaStream_t st = ctx->stream;
+    int r0, r1, rows_per;
+    band_rows(l.ny, ctx->band_rank, ctx->band_world, &r0, &r1, &rows_per);
+    TRY(launch_zero(ctx, s, 1, F_P11, 4));
+    for (int wi = 0; wi < prm.warps; wi++) {
+        if (r1 > r0) {
+            Span sp(ctx, 1);
+            TRY(launch_warp(ctx, s, 1, 0, r0, std::min(r1 + 1, l.ny)));   // + the halo row below
+        }
+        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.loop, 1);
+        CKL(ctx);
+        IterParams P = iter_params(ctx, l, prm, stat_base + wi, kMaxIterations, s);
+        P.row_begin = r0; P.row_end = r1; P.band_sum = ctx->d_band_sum;
+        int launched = 0, chunk = std::max(1, std::min(hint, P.max_iter));
+        while (launched < P.max_iter) {
+            const int k = std::min(chunk, P.max_iter - launched);
+            {
+                Span sp(ctx, 0, P.level);
+                for (int i = 0; i < k; i++) {
+                    CK(cudaMemsetAsync(ctx->d_band_sum, 0, sizeof(double), st));
+                    if (r1 > r0) TRY(launch_iterate(ctx, P, 1));
+                    TRY(band_exchange(ctx, s, true));
+                    k_band_decide<<<1, 32, 0, st>>>(w.ctl, w.loop, ctx->d_band_sum, (double) l.nx * (double) l.ny,
+                                                    P.eps2, P.max_iter, w.stat_iters, w.stat_errs, P.stat_slot,
+                                                    w.counters + P.level,
+                                                    (unsigned long long) l.nx * (unsigned long long) (r1 - r0));
+                    CKL(ctx);
+                }
+            }
+            launched += k;
+            CK(cudaMemcpyAsync(ctx->h_loop, w.loop, sizeof(LoopCtl), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ctx->stats.host_syncs++;
+            if (ctx->h_loop->active_pairs == 0) break;
+            chunk = std::max(1, hint / 8);
+        }
+        hint = std::max(1, ctx->h_loop->max_n);
+    }
+    return TVL1_OK;
+}
+
+int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, float *du2, int nx, int ny,
+             const tvl1_params &prm, int min_split_rows, int *iters_out, double *errs_out)
+{
+    const int ns = prm.nscales, nstat = ns * prm.warps, G = ctx->band_world;
+    TRY(ensure_workspace(ctx, nx, ny, ns, prm.zfactor, 1, nstat, G));
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    ncclComm_t comm = (ncclComm_t) ctx->nccl_comm;
+    // a negative threshold also splits on a single rank (one band = the whole level): the band code
+    // path without neighbours, used by the single-GPU tests
+    const bool force = min_split_rows < 0;
+    min_split_rows = std::max(std::abs(min_split_rows), 2 * G);
+    auto is_split = [&](int s) { return (G > 1 || force) && w.lv[s].ny >= min_split_rows; };
+    Span total(ctx, 2);
+    TRY(build_pyramid(ctx, 1, dI0, dI1, nx, ny, prm));
+    TRY(launch_zero(ctx, ns - 1, 1, F_U1, 2));
+    int hint = 16;
+    for (int s = ns - 1; s >= 0; s--) {
+        const int stat_base = (ns - 1 - s) * prm.warps;
+        if (is_split(s)) TRY(band_level(ctx, s, prm, stat_base, hint));
+        else TRY(run_level(ctx, s, 1, prm, stat_base, hint));      // replicated: identical on every rank
+        if (is_split(s)) {
+            // every rank gets the whole flow of this level (in place: band r sits at rows r*rows_per)
+            PairCtl c;
+            TRY(band_read_ctl(ctx, &c));
+            int r0, r1, rows_per;
+            band_rows(w.lv[s].ny, ctx->band_rank, G, &r0, &r1, &rows_per);
+            const size_t cnt = (size_t) rows_per * w.lv[s].pitch;
+            NK(g_nccl.GroupStart());
+            for (int f = F_U1; f <= F_U2; f++) {
+                float *plane = w.state + (size_t) c.cur * w.set_stride + (size_t) f * w.field_stride;
+                NK(g_nccl.AllGather(plane + (size_t) ctx->band_rank * cnt, plane, cnt, ncclFloat, comm, st));
+            }
+            NK(g_nccl.GroupEnd());
+        }
+        if (!s) break;
+        const Level &c = w.lv[s], &f = w.lv[s - 1];
+        int z0 = 0, z1 = f.ny;
+        if (is_split(s - 1)) {       // own rows plus both halo rows, straight from the full coarse flow
+            int r0, r1, rows_per;
+            band_rows(f.ny, ctx->band_rank, G, &r0, &r1, &rows_per);
+            z0 = std::max(r0 - 1, 0);
+            z1 = std::min(r1 + 1, f.ny);
+        }
+        if (z1 > z0) {
+            Span zs(ctx, 4);
+            dim3 g(ceil_div(f.nx, kZiTW), ceil_div(z1 - z0, kZiTH), 1);
+            k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                                      c, f, (double) f.nx / c.nx, (double) f.ny / c.ny,
+                                                      (float) (1.0 / prm.zfactor), z0, z1);
+            CKL(ctx);
+        }
+        k_flip_cur<<<1, 32, 0, st>>>(w.ctl, 1);
+        CKL(ctx);
+    }
+    {
+        Span ex(ctx, 5);
+        dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
+        k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                                 w.lv[0], du1, du2);
+        CKL(ctx);
+    }
+    total.end();
+    TRY(fetch_stats(ctx, 1, nstat, iters_out, errs_out));
+    return TVL1_OK;
+}
+
 // ---- RAII device scratch for the per-kernel hooks -----------------------------------------------
 struct Dev {
     std::vector<void *> ptrs;
@@ -945,6 +1198,8 @@ void tvl1_destroy(tvl1_ctx *ctx)
     for (auto &sb : ctx->sib) { if (sb) tvl1_destroy(sb); sb = nullptr; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t) ctx->nccl_comm);
+    cudaFree(ctx->d_band_sum);
     free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(ctx->ws);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->stage_in[i]); cudaFree(ctx->stage_out[i]); }
@@ -1063,6 +1318,77 @@ int tvl1_single_scale_f64(tvl1_ctx *ctx, const double *I0, const double *I1, dou
                           int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
 {
     return solve_host<double>(ctx, 1, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, false);
+}
+
+
+// ---- row-band mode ------------------------------------------------------------------------------
+
+int tvl1_band_unique_id(unsigned char *id_out)
+{
+    if (!id_out) return TVL1_ERR_ARG;
+    if (const char *e = load_nccl()) { g_create_error = e; return TVL1_ERR_CUDA; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return TVL1_ERR_CUDA; }
+    static_assert(sizeof(ncclUniqueId) <= TVL1_NCCL_ID_BYTES, "id buffer too small");
+    memset(id_out, 0, TVL1_NCCL_ID_BYTES);
+    memcpy(id_out, &id, sizeof id);
+    return TVL1_OK;
+}
+
+int tvl1_band_init(tvl1_ctx *ctx, int rank, int world, const unsigned char *id_bytes)
+{
+    if (!ctx || !id_bytes || world < 1 || rank < 0 || rank >= world) return fail_arg(ctx, "bad argument");
+    if (const char *e = load_nccl()) { ctx->err = e; return TVL1_ERR_CUDA; }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) { g_nccl.CommDestroy((ncclComm_t) ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclComm_t comm;
+    NK(g_nccl.CommInitRank(&comm, world, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->band_rank = rank;
+    ctx->band_world = world;
+    if (!ctx->d_band_sum) CK(cudaMalloc(&ctx->d_band_sum, sizeof(double)));
+    return TVL1_OK;
+}
+
+int tvl1_band_solve_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2, int nx,
+                        int ny, const tvl1_params *prm, int min_split_rows, int *iters_out, double *errs_out)
+{
+    TRY(check_common(ctx, I0, I1, u1, u2, nx, ny, prm, true));
+    if (!ctx->nccl_comm) return fail_arg(ctx, "tvl1_band_init has not been called on this context");
+    reset_stats(ctx);
+    const size_t n = (size_t) nx * ny;
+    TRY(ensure_stage(ctx, n * sizeof(float), false));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->stage_in[0], I0, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->stage_in[1], I1, n * 4, cudaMemcpyHostToDevice, st));
+    TRY(run_band(ctx, (const float *) ctx->stage_in[0], (const float *) ctx->stage_in[1],
+                 (float *) ctx->stage_out[0], (float *) ctx->stage_out[1], nx, ny, *prm, min_split_rows,
+                 iters_out, errs_out));
+    CK(cudaMemcpyAsync(u1, ctx->stage_out[0], n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(u2, ctx->stage_out[1], n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    resolve_events(ctx);
+    return TVL1_OK;
+}
+
+int tvl1_band_solve_dev_f32(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, float *du2,
+                            int nx, int ny, const tvl1_params *prm, int min_split_rows, int *iters_out,
+                            double *errs_out)
+{
+    TRY(check_common(ctx, dI0, dI1, du1, du2, nx, ny, prm, true));
+    if (!ctx->nccl_comm) return fail_arg(ctx, "tvl1_band_init has not been called on this context");
+    reset_stats(ctx);
+    TRY(run_band(ctx, dI0, dI1, du1, du2, nx, ny, *prm, min_split_rows, iters_out, errs_out));
+    resolve_events(ctx);
+    return TVL1_OK;
+}
+
+void tvl1_band_rows(int ny, int rank, int world, int *row_begin, int *row_end)
+{
+    int rp;
+    band_rows(ny, rank, world, row_begin, row_end, &rp);
 }
 
 // ---- hooks --------------------------------------------------------------------------------------

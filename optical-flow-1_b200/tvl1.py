@@ -218,6 +218,48 @@ class TVL1:
         self._ck(fn(self.ctx, C.c_int(npairs), C.c_void_p(pI0), C.c_void_p(pI1), C.c_void_p(pu1),
                     C.c_void_p(pu2), C.c_int(nx), C.c_int(ny), C.byref(prm), None, None))
 
+    # -- row-band mode: one image pair over several GPUs -------------------------------------------
+    def band_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        rc = self.lib.tvl1_band_unique_id(buf)
+        if rc:
+            raise TVL1Error(rc, self.lib.tvl1_last_error(None).decode())
+        return bytes(buf)
+
+    def band_init(self, rank, world, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.tvl1_band_init(self.ctx, C.c_int(rank), C.c_int(world), buf))
+
+    def band_rows(self, ny, rank, world):
+        a, b = C.c_int(), C.c_int()
+        self.lib.tvl1_band_rows(C.c_int(ny), C.c_int(rank), C.c_int(world), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def band_solve(self, I0, I1, min_split_rows=512, tau=0.25, lam=0.15, theta=0.3, nscales=5,
+                   zfactor=0.5, warps=5, eps=0.01):
+        """Collective over the ranks of band_init: same full (ny, nx) float32 images on every rank;
+        returns the full flow on every rank: (u1, u2, iters[nscales, warps], errs)."""
+        I0, I1 = self._f32(I0), self._f32(I1)
+        ny, nx = I0.shape
+        u1, u2 = np.empty_like(I0), np.empty_like(I0)
+        iters = np.zeros((nscales, warps), np.int32)
+        errs = np.zeros((nscales, warps), np.float64)
+        prm = self._params(tau, lam, theta, nscales, zfactor, warps, eps)
+        self._ck(self.lib.tvl1_band_solve_f32(self.ctx, _fp(I0), _fp(I1), _fp(u1), _fp(u2), C.c_int(nx),
+                                              C.c_int(ny), C.byref(prm), C.c_int(min_split_rows),
+                                              _fp(iters), _fp(errs)))
+        return u1, u2, iters, errs
+
+    def band_solve_device(self, dI0, dI1, du1, du2, nx, ny, min_split_rows=512, tau=0.25, lam=0.15,
+                          theta=0.3, nscales=5, zfactor=0.5, warps=5, eps=0.01):
+        prm = self._params(tau, lam, theta, nscales, zfactor, warps, eps)
+        iters = np.zeros((nscales, warps), np.int32)
+        errs = np.zeros((nscales, warps), np.float64)
+        self._ck(self.lib.tvl1_band_solve_dev_f32(self.ctx, C.c_void_p(dI0), C.c_void_p(dI1), C.c_void_p(du1),
+                                                  C.c_void_p(du2), C.c_int(nx), C.c_int(ny), C.byref(prm),
+                                                  C.c_int(min_split_rows), _fp(iters), _fp(errs)))
+        return iters, errs
+
     # -- per-kernel hooks ------------------------------------------------------------------------
     def zoom_size(self, nx, ny, factor):
         a, b = C.c_int(), C.c_int()

@@ -283,6 +283,22 @@ def test_batch_equals_individual_solves(gpu):
     assert np.array_equal(cu1, bu1) and np.array_equal(cu2, bu2) and np.array_equal(cit, bit)
 
 
+def test_band_code_path_single_rank(gpu, oracle_f64):
+    """Row-band mode with one rank (a band = the whole level, NCCL communicator of size 1): the
+    row-window kernels, the all-reduced stopping rule and the in-place all-gather must reproduce the
+    ordinary solve bit for bit."""
+    I0, I1 = _cases.synth.make_pair(200, 144, seed=31, scale=0.5)
+    kw = dict(nscales=3, warps=3, eps=0.01)
+    a = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    gpu.band_init(0, 1, gpu.band_unique_id())
+    b = gpu.band_solve(I0, I1, min_split_rows=-60, **kw)     # splits the 144- and 72-row levels
+    assert np.array_equal(a[2], b[2]), (a[2].tolist(), b[2].tolist())
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    r = oracle_f64.multiscale(I0, I1, **kw)
+    assert np.array_equal(b[2], r[2])
+    assert_flow_close(b[0], b[1], r[0], r[1], "band mode")
+
+
 # ---- BASELINE.json configs --------------------------------------------------------------------
 
 def reference_cpu():
