@@ -567,6 +567,17 @@ __device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, flo
                  ay[2] * (rowI[4] - rowI[2]) + ay[3] * (rowI[5] - rowI[3]));
 }
 
+// Rare path of k_warp: a pixel whose flow exceeds the staged margin gathers from global memory.
+__device__ __noinline__ void warp_gather_global(const float *__restrict__ img1, int pitch, int nx, int ny,
+                                                int x, int y, float tx, float ty, float *out3)
+{
+    float w, wx, wy;
+    warp_gather([&](int r, int c) {
+        return __ldg(img1 + clampi(y - 2 + r, 0, ny - 1) * pitch + clampi(x - 2 + c, 0, nx - 1));
+    }, tx, ty, w, wx, wy);
+    out3[0] = w; out3[1] = wx; out3[2] = wy;
+}
+
 // Shared-memory-staged gather: a CTA owns a 64x16 tile of output pixels.  The box of I1 that covers
 // every 6x6 neighbourhood whose integer sample offset is within +-kWarpM pixels of its pixel (tile
 // grown by kWarpM+2 / kWarpM+3, x origin rounded down to a float4) is staged with cp.async
@@ -599,21 +610,28 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
     const int tid = ty * 32 + tx;
     const int b = blockIdx.z;
     const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
+    // per-pair base pointers once (64-bit); every pixel access below is base + 32-bit offset
     const float *img1 = I1 + (size_t) b * img_stride;
-    const float *u = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0;
+    const float *img0 = I0 + (size_t) b * img_stride;
+    const float *pu1 = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0;
+    const float *pu2 = pu1 + field_stride;
+    float *cIx = consts + (size_t) C_IX * field_stride + (size_t) b * plane0;
+    float *cIy = consts + (size_t) C_IY * field_stride + (size_t) b * plane0;
+    float *cRho = consts + (size_t) C_RHO * field_stride + (size_t) b * plane0;
+    float *cGrad = consts + (size_t) C_GRAD * field_stride + (size_t) b * plane0;
     const int X0 = blockIdx.x * kWarpTW, Y0 = row_begin + blockIdx.y * kWarpTH;
     const int bx0 = X0 - kWarpBX, by0 = Y0 - kWarpBY;
 
     // ---- stage the box (asynchronously) ---------------------------------------------------------
     if (bx0 >= 0 && by0 >= 0 && bx0 + kWarpBW <= nx && by0 + kWarpBH <= ny) {
-        const float *src = img1 + (size_t) by0 * pitch + bx0;
+        const float *src = img1 + by0 * pitch + bx0;
         for (int t = tid; t < kWarpBH * (kWarpBW / 4); t += 256) {
             const int ly = t / (kWarpBW / 4), l4 = t - ly * (kWarpBW / 4);
-            cp_async16(s_box + ly * kWarpBW + l4 * 4, src + (size_t) ly * pitch + l4 * 4);
+            cp_async16(s_box + ly * kWarpBW + l4 * 4, src + ly * pitch + l4 * 4);
         }
     } else {
         for (int ly = ty; ly < kWarpBH; ly += 8) {
-            const float *row = img1 + (size_t) clampi(by0 + ly, 0, ny - 1) * pitch;
+            const float *row = img1 + clampi(by0 + ly, 0, ny - 1) * pitch;
             for (int lx = tx; lx < kWarpBW; lx += 32)
                 cp_async4(s_box + ly * kWarpBW + lx, row + clampi(bx0 + lx, 0, nx - 1));
         }
@@ -621,24 +639,26 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- flow, I0 and sample positions of this thread's four pixels ------------------------------
+    const int jj = X0 + tx, ii = Y0 + ty;
+    const int p00 = ii * pitch + jj;                 // pixel q sits at p00 + 32*(q&1) + 8*pitch*(q>>1)
     float u1[4], u2[4], ftx[4], fty[4], i0v[4];
     int sx[4], sy[4];
     bool inside[4], valid[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
+        const int j = jj + 32 * (q & 1), i = ii + 8 * (q >> 1);
+        const int p = p00 + 32 * (q & 1) + 8 * pitch * (q >> 1);
         inside[q] = j < nx && i < row_end;
         u1[q] = u2[q] = i0v[q] = 0.f;
         if (inside[q]) {
-            const size_t p = (size_t) i * pitch + j;
-            u1[q] = __ldg(u + p);
-            u2[q] = __ldg(u + field_stride + p);
-            i0v[q] = __ldg(I0 + (size_t) b * img_stride + p);
+            u1[q] = __ldg(pu1 + p);
+            u2[q] = __ldg(pu2 + p);
+            i0v[q] = __ldg(img0 + p);
         }
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
+        const int j = jj + 32 * (q & 1), i = ii + 8 * (q >> 1);
         const float fu = floorf(u1[q]), fv = floorf(u2[q]);
         const float xf = (float) j + fu, yf = (float) i + fv;
         valid[q] = inside[q] && xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
@@ -653,8 +673,7 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (!inside[q]) continue;
-        const int j = X0 + tx + 32 * (q & 1), i = Y0 + ty + 8 * (q >> 1);
-        const size_t p = (size_t) i * pitch + j;
+        const int p = p00 + 32 * (q & 1) + 8 * pitch * (q >> 1);
         float w = 0.f, wx = 0.f, wy = 0.f;
         if (valid[q]) {
             const int cx = sx[q] - 2 - bx0, cy = sy[q] - 2 - by0;       // box coordinates of tap (0,0)
@@ -662,17 +681,15 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
                 const float *base = s_box + cy * kWarpBW + cx;
                 warp_gather([&](int r, int c) { return base[r * kWarpBW + c]; }, ftx[q], fty[q], w, wx, wy);
             } else {
-                const int x = sx[q], y = sy[q];
-                warp_gather([&](int r, int c) {
-                    return __ldg(img1 + (size_t) clampi(y - 2 + r, 0, ny - 1) * pitch + clampi(x - 2 + c, 0, nx - 1));
-                }, ftx[q], fty[q], w, wx, wy);
+                float o3[3];
+                warp_gather_global(img1, pitch, nx, ny, sx[q], sy[q], ftx[q], fty[q], o3);
+                w = o3[0]; wx = o3[1]; wy = o3[2];
             }
         }
-        float *c = consts + (size_t) b * plane0 + p;
-        c[(size_t) C_IX * field_stride] = wx;
-        c[(size_t) C_IY * field_stride] = wy;
-        c[(size_t) C_RHO * field_stride] = w - wx * u1[q] - wy * u2[q] - i0v[q];
-        if (write_grad) c[(size_t) C_GRAD * field_stride] = grad_of(wx, wy);
+        cIx[p] = wx;
+        cIy[p] = wy;
+        cRho[p] = w - wx * u1[q] - wy * u2[q] - i0v[q];
+        if (write_grad) cGrad[p] = grad_of(wx, wy);
     }
 }
 
