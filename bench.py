@@ -289,6 +289,13 @@ def run_ours(args, rank, local_rank, world):
     solver = pkg.TVL1(device=local_rank, max_batch=args.e2e_max_batch, profiling=False)
     solver.set_lanes(host_lanes=args.e2e_lanes)
     E = min(args.e2e_pairs, P)
+    try:    # pinned host buffers of all ranks must stay a small part of the box's memory
+        import psutil
+        budget = 0.2 * psutil.virtual_memory().available / max(world, 1)
+        while E > args.e2e_max_batch and 4 * E * nx * ny * 4 > budget:
+            E //= 2
+    except ImportError:
+        pass
     hI0 = torch.empty((E, ny, nx), dtype=torch.float32).pin_memory()
     hI1 = torch.empty_like(hI0).pin_memory()
     hu1 = torch.empty_like(hI0).pin_memory()

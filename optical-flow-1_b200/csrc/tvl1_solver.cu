@@ -85,6 +85,7 @@ struct tvl1_ctx {
     tvl1_stats stats{};
     Workspace ws;
     LoopCtl *h_loop = nullptr;               // pinned
+    cudaEvent_t sync_event = nullptr;        // blocking-sync event: lane threads sleep instead of spinning
     cudaStream_t body_stream = nullptr;      // capture stream for while-node bodies
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
@@ -132,6 +133,15 @@ namespace {
         int rc_ = (expr);                                                                          \
         if (rc_ != TVL1_OK) return rc_;                                                            \
     } while (0)
+
+// Wait for the context's stream without spinning a host core (several lanes per GPU and several
+// ranks per box share the host CPUs).  Loop-control round trips keep using cudaStreamSynchronize.
+cudaError_t sleep_until_done(tvl1_ctx *ctx)
+{
+    cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->sync_event);
+}
 
 int fail_arg(tvl1_ctx *ctx, const char *msg)
 {
@@ -568,7 +578,7 @@ int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_ou
     if (errs_out)
         CK(cudaMemcpy2DAsync(errs_out, sizeof(double) * nstat, w.stat_errs, sizeof(double) * w.stat_stride,
                              sizeof(double) * nstat, B, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sleep_until_done(ctx));
     for (int l = 0; l < TVL1_MAX_LEVELS; l++) {
         ctx->stats.pixel_iterations += c[l];
         ctx->stats.level_pixel_iterations[l] += c[l];
@@ -634,7 +644,7 @@ int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multis
     ctx->stats.kernel_launches += sg.static_launches;
     ctx->stats.pixel_warps += sg.pixel_warps;
     if (!sg.events.empty()) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(sleep_until_done(ctx));
         for (const auto &p : sg.events) add_span_time(ctx, p);
     }
     return TVL1_OK;
@@ -820,7 +830,7 @@ int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1
     }
     CK(cudaMemcpyAsync(u1 + off, ctx->stage_out[0], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(u2 + off, ctx->stage_out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(sleep_until_done(ctx));
     return TVL1_OK;
 }
 
@@ -1180,6 +1190,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->body_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaMallocHost(&ctx->h_loop, sizeof(LoopCtl))) != cudaSuccess) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
         delete ctx;
@@ -1207,6 +1218,7 @@ void tvl1_destroy(tvl1_ctx *ctx)
     resolve_events(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->h_loop) cudaFreeHost(ctx->h_loop);
+    if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->body_stream) cudaStreamDestroy(ctx->body_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
