@@ -78,9 +78,11 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, enabled=True):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        if not enabled:
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "200"],
@@ -91,6 +93,8 @@ class ClockSampler:
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
+            self.f.close()
+            os.unlink(self.f.name)
             return out
         self.p.terminate()
         try:
@@ -183,6 +187,22 @@ def run_reference(args, rank, world):
     }))
 
 
+def pin_to_gpu_numa_node(index):
+    """Best effort: run this rank (and allocate its pinned host buffers) on the CPUs next to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # ---- our arm -------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -191,6 +211,7 @@ def run_ours(args, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the solver has no CPU fallback)")
+    pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -228,7 +249,7 @@ def run_ours(args, rank, local_rank, world):
         step_device()
 
     barrier()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))   # one poller per box: nvidia-smi queries perturb launches
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     acc = None

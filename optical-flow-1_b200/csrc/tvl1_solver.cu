@@ -86,6 +86,7 @@ struct tvl1_ctx {
     Workspace ws;
     LoopCtl *h_loop = nullptr;               // pinned
     cudaEvent_t sync_event = nullptr;        // blocking-sync event: lane threads sleep instead of spinning
+    bool blocking_wait = false;              // set while several lanes share the GPU
     cudaStream_t body_stream = nullptr;      // capture stream for while-node bodies
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
@@ -138,6 +139,7 @@ namespace {
 // ranks per box share the host CPUs).  Loop-control round trips keep using cudaStreamSynchronize.
 cudaError_t sleep_until_done(tvl1_ctx *ctx)
 {
+    if (!ctx->blocking_wait) return cudaStreamSynchronize(ctx->stream);   // single lane: lowest latency
     cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
     if (e != cudaSuccess) return e;
     return cudaEventSynchronize(ctx->sync_event);
@@ -876,6 +878,7 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
         reset_stats(sb);
         lanes[l] = sb;
     }
+    for (int l = 0; l < nlanes; l++) lanes[l]->blocking_wait = nlanes > 1;
     int rcs[tvl1_ctx::kMaxLanes] = { TVL1_OK, TVL1_OK, TVL1_OK, TVL1_OK };
     auto work = [&](int l) {
         tvl1_ctx *c = lanes[l];
