@@ -47,14 +47,40 @@ def main():
     t_band = time.perf_counter() - t
     st = g.stats()
 
+    # device-resident timings (no host copies): ordinary solve vs row bands
+    dI0, dI1 = torch.from_numpy(I0).cuda(), torch.from_numpy(I1).cuda()
+    du1, du2 = torch.empty_like(dI0), torch.empty_like(dI0)
+    ptrs = (dI0.data_ptr(), dI1.data_ptr(), du1.data_ptr(), du2.data_ptr())
+
+    def timed(fn, reps=3):
+        best = 1e9
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        return 1e3 * best
+
+    dev_solo = timed(lambda: g.solve_batch_device(*ptrs, 1, nx, ny, **kw))
+    dev_band = timed(lambda: g.band_solve_device(*ptrs, nx, ny, min_split_rows=min_rows, **kw))
+    big = max(min_rows, ny // 2 + 1)       # split the finest level only
+    dev_band_top = timed(lambda: g.band_solve_device(*ptrs, nx, ny, min_split_rows=big, **kw))
+    top_iters, _ = g.band_solve_device(*ptrs, nx, ny, min_split_rows=big, **kw)
+    same_top = bool(np.array_equal(top_iters, solo[2]) and np.array_equal(du1.cpu().numpy(), solo[0]))
+
     d = max(np.abs(solo[0] - band[0]).max(), np.abs(solo[1] - band[1]).max())
     same_iters = bool(np.array_equal(solo[2], band[2]))
     rows = [g.band_rows(ny, r, world) for r in range(world)]
     res = dict(rank=rank, world=world, nx=nx, ny=ny, params=kw, min_split_rows=min_rows, band_rows=rows,
                same_iteration_counts=same_iters, max_abs_flow_diff=float(d),
                solo_ms=1e3 * t_solo, band_ms=1e3 * t_band, host_syncs=st["host_syncs"],
+               device_resident_ms=dict(single_gpu=dev_solo, band_all_levels_ge_min_rows=dev_band,
+                                       band_finest_level_only=dev_band_top),
+               finest_only_matches_single_gpu=same_top,
                iterations_per_level=band[2].sum(axis=1).tolist())
-    ok = same_iters and d <= 1e-5
+    ok = same_iters and d <= 1e-5 and same_top
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:
