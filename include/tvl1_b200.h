@@ -133,6 +133,14 @@ int tvl1_band_solve_dev_f32(tvl1_ctx *ctx, const float *dI0, const float *dI1, f
                             int nx, int ny, const tvl1_params *prm, int min_split_rows, int *iters_out,
                             double *errs_out);                               /* DEVICE buffers */
 void tvl1_band_rows(int ny, int rank, int world, int *row_begin, int *row_end);  /* rows a rank owns */
+/* How the per-iteration halo rows and error sums travel.  Default (1): inside the iteration kernel,
+ * through peer memory mapped with CUDA IPC -- NVLink stores of the boundary rows plus an all-to-all
+ * of the per-rank sums in mailboxes; no NCCL call and no extra kernel per iteration.  0: one NCCL
+ * group (send/recv + all-reduce) per iteration (also the fallback when peer access is unavailable
+ * or the box has more than 8 ranks).  tvl1_band_exchange_mode returns the mode in effect (-1: no
+ * communicator yet). */
+int tvl1_band_set_exchange(tvl1_ctx *ctx, int use_nccl_per_iteration);
+int tvl1_band_exchange_mode(const tvl1_ctx *ctx);
 
 /* -- one level: Dual_TVL1_optic_flow (src/tvl1flow.cpp:46-212) ----------------------------- */
 /* u1,u2 are in/out (the initial flow is used, tvl1flow.cpp:94); nscales/zfactor of prm ignored;

@@ -711,6 +711,37 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
 // old values, hence ping-pong).  Per-CTA error partials are reduced in a fixed order by the last
 // CTA of each pair (deterministic, fp64), which also applies the stopping rule on the device.
 
+// Row-band mode over peer memory (NVLink): every rank owns one mailbox in its own HBM that all ranks
+// of the box map through CUDA IPC.  slot[e & 1][r] carries rank r's partial error sum of global
+// iteration (epoch) e; `epoch` counts the exchanges this rank has taken part in.
+constexpr int kMaxRanks = 8;
+struct BandMailbox {
+    double sum[2][kMaxRanks];
+    unsigned long long tag[2][kMaxRanks];
+    unsigned long long epoch;
+    int timed_out;
+    int pad;
+};
+
+struct BandPeers {
+    int enabled;                       // 0: not in peer-memory band mode
+    int rank, world;
+    float *up_state;                   // state base of rank-1 (same layout as ours), or null
+    float *dn_state;                   // state base of rank+1, or null
+    BandMailbox *box[kMaxRanks];       // box[r] = rank r's mailbox (box[rank] is local memory)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct IterParams {
     float *state;
     const float *consts;
@@ -722,6 +753,7 @@ struct IterParams {
     int row_begin, row_end;            // rows this launch owns (whole image: 0, ny; a row band otherwise)
     double *band_sum;                  // row-band mode: the rank's raw sum of squared updates goes here
                                        // and k_band_decide applies the stopping rule after the all-reduce
+    BandPeers peers;                   // row-band mode over peer memory: halos and error travel inside the kernel
     int *stat_iters;             // [B][stat_stride]
     double *stat_errs;
     unsigned long long *px_iters;  // [level] pixel-iterations; [TVL1_MAX_LEVELS + level] launches
@@ -907,6 +939,25 @@ k_iterate_t1(const IterParams P)
                 st4(sout + F_P12 * fs + o, make_float4(q12[0], q12[1], q12[2], q12[3]));
                 st4(sout + F_P21 * fs + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
                 st4(sout + F_P22 * fs + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
+                if (P.peers.enabled) {
+                    // my first row is the halo row below of the band above, my last row's p12/p22 the
+                    // halo above of the band below: same offsets in the neighbour's planes (NVLink stores)
+                    const size_t po = (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0 + o;
+                    if (y == P.row_begin && P.peers.up_state) {
+                        float *d = P.peers.up_state + po;
+                        st4(d + F_U1 * fs, uc1);
+                        st4(d + F_U2 * fs, uc2);
+                        st4(d + F_P11 * fs, make_float4(q11[0], q11[1], q11[2], q11[3]));
+                        st4(d + F_P12 * fs, make_float4(q12[0], q12[1], q12[2], q12[3]));
+                        st4(d + F_P21 * fs, make_float4(q21[0], q21[1], q21[2], q21[3]));
+                        st4(d + F_P22 * fs, make_float4(q22[0], q22[1], q22[2], q22[3]));
+                    }
+                    if (y == P.row_end - 1 && P.peers.dn_state) {
+                        float *d = P.peers.dn_state + po;
+                        st4(d + F_P12 * fs, make_float4(q12[0], q12[1], q12[2], q12[3]));
+                        st4(d + F_P22 * fs, make_float4(q22[0], q22[1], q22[2], q22[3]));
+                    }
+                }
             }
         };
 
@@ -940,7 +991,8 @@ k_iterate_t1(const IterParams P)
         double s = 0.0;
         for (int w = 0; w < WY; w++) s += s_part[w];
         P.partials[(size_t) b * P.parts_per_pair + blk] = s;
-        __threadfence();
+        if (P.peers.enabled) __threadfence_system();    // halo rows pushed to the neighbours are out
+        else __threadfence();
         const unsigned int t = atomicAdd(&ctl->arrive, 1u);
         s_last = (t == (unsigned int) nblk - 1u);
     }
@@ -962,13 +1014,37 @@ k_iterate_t1(const IterParams P)
             ctl->arrive = 0u;
             return;
         }
+        if (P.peers.enabled) {
+            // All-to-all of the per-rank sums through the mailboxes.  This is the one
+            // synchronisation point of an iteration: a rank publishes its sum only after all its
+            // CTAs (and their halo pushes) are done, and nobody leaves before it holds every sum,
+            // so the next launch finds its halo rows up to date.
+            BandMailbox *mine = P.peers.box[P.peers.rank];
+            const unsigned long long e = mine->epoch + 1;
+            const int par = (int) (e & 1);
+            for (int r = 0; r < P.peers.world; r++) {
+                BandMailbox *bx = P.peers.box[r];
+                bx->sum[par][P.peers.rank] = tot;
+                st_release_sys(&bx->tag[par][P.peers.rank], e);
+            }
+            double all = 0.0;
+            const long long t0 = clock64();
+            for (int r = 0; r < P.peers.world; r++) {        // fixed rank order: same bits everywhere
+                while (ld_acquire_sys(&mine->tag[par][r]) != e) {
+                    if (clock64() - t0 > (1ll << 33)) { mine->timed_out = 1; break; }   // ~4 s: never hang the GPU
+                }
+                all += *((volatile double *) &mine->sum[par][r]);
+            }
+            mine->epoch = e;
+            tot = all;
+        }
         const double error = tot / ((double) nx * (double) ny);   // src/tvl1flow.cpp:162
         const int n = ctl->n + 1;
         ctl->n = n;
         ctl->err = error;
         ctl->cur = cur ^ 1;
         ctl->arrive = 0u;
-        atomicAdd(P.px_iters + P.level, (unsigned long long) nx * (unsigned long long) ny);
+        atomicAdd(P.px_iters + P.level, (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
         if (!(error > P.eps2 && n < P.max_iter)) {                // src/tvl1flow.cpp:113
             ctl->active = 0;
             P.stat_iters[(size_t) b * P.stat_stride + P.stat_slot] = n;

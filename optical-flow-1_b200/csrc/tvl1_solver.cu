@@ -98,6 +98,14 @@ struct tvl1_ctx {
     void *nccl_comm = nullptr;
     int band_rank = 0, band_world = 1;
     double *d_band_sum = nullptr;
+    // ... over peer memory (CUDA IPC + NVLink): halos and error sums move inside the iteration kernel
+    bool p2p_ready = false;
+    bool band_use_nccl_per_iteration = false;   // TVL1_BAND_NCCL=1: the NCCL send/recv variant
+    BandMailbox *my_box = nullptr;
+    BandMailbox *boxes[kMaxRanks] = {};
+    float *peer_state[2] = { nullptr, nullptr };   // [0] rank-1, [1] rank+1
+    const float *p2p_state_key = nullptr;
+    unsigned char *d_handles = nullptr;            // [world][64] scratch for the handle all-gather
     static constexpr int kMaxLanes = 4;
     tvl1_ctx *sib[kMaxLanes - 1] = { nullptr, nullptr, nullptr };   // sibling contexts (extra lanes, same GPU)
     int host_lanes = 4;                      // lanes used by the host-buffer batch entry points
@@ -383,7 +391,7 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
                        int max_iter, int level = 0)
 {
     const Workspace &w = ctx->ws;
-    IterParams P;
+    IterParams P = {};
     P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
     P.loop = w.loop; P.cond = 0; P.use_cond = 0;
     P.row_begin = 0; P.row_end = lv.ny; P.band_sum = nullptr;
@@ -996,6 +1004,97 @@ void band_rows(int ny, int rank, int world, int *r0, int *r1, int *rows_per)
     *r1 = std::min(ny, *r0 + *rows_per);
 }
 
+
+// ---- peer-memory plumbing: CUDA IPC handles travel through one NCCL all-gather ------------------
+int exchange_ipc_handles(tvl1_ctx *ctx, void *dev_ptr, std::vector<cudaIpcMemHandle_t> &all)
+{
+    const int G = ctx->band_world;
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, dev_ptr));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+    CK(cudaMemcpyAsync(ctx->d_handles + 64 * ctx->band_rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    NK(g_nccl.AllGather(ctx->d_handles + 64 * ctx->band_rank, ctx->d_handles, 64, ncclChar,
+                        (ncclComm_t) ctx->nccl_comm, ctx->stream));
+    all.resize(G);
+    CK(cudaMemcpyAsync(all.data(), ctx->d_handles, 64 * G, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TVL1_OK;
+}
+
+void p2p_release_state(tvl1_ctx *ctx)
+{
+    for (float *&p : ctx->peer_state) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
+    ctx->p2p_state_key = nullptr;
+}
+
+int p2p_setup_mailboxes(tvl1_ctx *ctx)
+{
+    const int G = ctx->band_world, me = ctx->band_rank;
+    ctx->p2p_ready = false;
+    if (G > kMaxRanks) return TVL1_OK;                         // NCCL variant only
+    if (!ctx->d_handles) CK(cudaMalloc(&ctx->d_handles, 64 * kMaxRanks));
+    if (!ctx->my_box) CK(cudaMalloc(&ctx->my_box, 2 << 20));   // its own allocation: exported whole
+    CK(cudaMemsetAsync(ctx->my_box, 0, sizeof(BandMailbox), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all;
+    TRY(exchange_ipc_handles(ctx, ctx->my_box, all));
+    for (int r = 0; r < G; r++) {
+        if (r == me) { ctx->boxes[r] = ctx->my_box; continue; }
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return TVL1_OK;                                    // no peer access: stay on NCCL
+        }
+        ctx->boxes[r] = (BandMailbox *) p;
+    }
+    ctx->p2p_ready = true;
+    return TVL1_OK;
+}
+
+// (re)bind the neighbours' state buffers after the workspace was (re)allocated -- collective
+int p2p_bind_state(tvl1_ctx *ctx)
+{
+    if (!ctx->p2p_ready || ctx->p2p_state_key == ctx->ws.state) return TVL1_OK;
+    p2p_release_state(ctx);
+    std::vector<cudaIpcMemHandle_t> all;
+    TRY(exchange_ipc_handles(ctx, ctx->ws.state, all));
+    const int nb[2] = { ctx->band_rank - 1, ctx->band_rank + 1 };
+    for (int k = 0; k < 2; k++) {
+        if (nb[k] < 0 || nb[k] >= ctx->band_world) continue;
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, all[nb[k]], cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_state[k] = (float *) p;
+    }
+    ctx->p2p_state_key = ctx->ws.state;
+    return TVL1_OK;
+}
+
+// one split level with the exchange fused into the iteration kernel (no NCCL, no extra kernels)
+int band_level_p2p(tvl1_ctx *ctx, int s, const tvl1_params &prm, int stat_base, int &hint)
+{
+    const Workspace &w = ctx->ws;
+    const Level &l = w.lv[s];
+    int r0, r1, rows_per;
+    band_rows(l.ny, ctx->band_rank, ctx->band_world, &r0, &r1, &rows_per);
+    TRY(launch_zero(ctx, s, 1, F_P11, 4));
+    for (int wi = 0; wi < prm.warps; wi++) {
+        {
+            Span sp(ctx, 1);
+            TRY(launch_warp(ctx, s, 1, 0, r0, std::min(r1 + 1, l.ny)));   // + the halo row below
+        }
+        k_begin_warp<<<1, 32, 0, ctx->stream>>>(w.ctl, w.loop, 1);
+        CKL(ctx);
+        IterParams P = iter_params(ctx, l, prm, stat_base + wi, kMaxIterations, s);
+        P.row_begin = r0; P.row_end = r1;
+        P.peers.enabled = 1; P.peers.rank = ctx->band_rank; P.peers.world = ctx->band_world;
+        P.peers.up_state = r0 > 0 ? ctx->peer_state[0] : nullptr;
+        P.peers.dn_state = r1 < l.ny ? ctx->peer_state[1] : nullptr;
+        for (int r = 0; r < ctx->band_world; r++) P.peers.box[r] = ctx->boxes[r];
+        TRY(run_iterations(ctx, P, 1, hint));
+    }
+    return TVL1_OK;
+}
+
 // all-reduce of the error sum + halo exchange of both ping-pong sets, one NCCL group
 int band_exchange(tvl1_ctx *ctx, int s, bool with_sum)
 {
@@ -1089,6 +1188,8 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
     ncclComm_t comm = (ncclComm_t) ctx->nccl_comm;
+    const bool p2p = ctx->p2p_ready && !ctx->band_use_nccl_per_iteration;
+    if (p2p) TRY(p2p_bind_state(ctx));
     // a negative threshold also splits on a single rank (one band = the whole level): the band code
     // path without neighbours, used by the single-GPU tests
     const bool force = min_split_rows < 0;
@@ -1100,7 +1201,8 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
     int hint = 16;
     for (int s = ns - 1; s >= 0; s--) {
         const int stat_base = (ns - 1 - s) * prm.warps;
-        if (is_split(s)) TRY(band_level(ctx, s, prm, stat_base, hint));
+        if (is_split(s) && p2p) TRY(band_level_p2p(ctx, s, prm, stat_base, hint));
+        else if (is_split(s)) TRY(band_level(ctx, s, prm, stat_base, hint));
         else TRY(run_level(ctx, s, 1, prm, stat_base, hint));      // replicated: identical on every rank
         if (is_split(s)) {
             // every rank gets the whole flow of this level (in place: band r sits at rows r*rows_per)
@@ -1145,6 +1247,11 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
     }
     total.end();
     TRY(fetch_stats(ctx, 1, nstat, iters_out, errs_out));
+    if (p2p) {
+        int flag = 0;
+        CK(cudaMemcpy(&flag, &ctx->my_box->timed_out, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) { ctx->err = "row-band exchange timed out waiting for a peer rank"; return TVL1_ERR_CUDA; }
+    }
     return TVL1_OK;
 }
 
@@ -1212,6 +1319,11 @@ void tvl1_destroy(tvl1_ctx *ctx)
     for (auto &sb : ctx->sib) { if (sb) tvl1_destroy(sb); sb = nullptr; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    p2p_release_state(ctx);
+    for (int r = 0; r < kMaxRanks; r++)
+        if (ctx->boxes[r] && ctx->boxes[r] != ctx->my_box) cudaIpcCloseMemHandle(ctx->boxes[r]);
+    cudaFree(ctx->my_box);
+    cudaFree(ctx->d_handles);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t) ctx->nccl_comm);
     cudaFree(ctx->d_band_sum);
     free_graph(ctx->sg, ctx->ev_pool);
@@ -1364,6 +1476,9 @@ int tvl1_band_init(tvl1_ctx *ctx, int rank, int world, const unsigned char *id_b
     ctx->band_rank = rank;
     ctx->band_world = world;
     if (!ctx->d_band_sum) CK(cudaMalloc(&ctx->d_band_sum, sizeof(double)));
+    if (const char *e = std::getenv("TVL1_BAND_NCCL")) ctx->band_use_nccl_per_iteration = (e[0] == '1');
+    p2p_release_state(ctx);
+    TRY(p2p_setup_mailboxes(ctx));
     return TVL1_OK;
 }
 
@@ -1398,6 +1513,19 @@ int tvl1_band_solve_dev_f32(tvl1_ctx *ctx, const float *dI0, const float *dI1, f
     TRY(run_band(ctx, dI0, dI1, du1, du2, nx, ny, *prm, min_split_rows, iters_out, errs_out));
     resolve_events(ctx);
     return TVL1_OK;
+}
+
+int tvl1_band_set_exchange(tvl1_ctx *ctx, int use_nccl_per_iteration)
+{
+    if (!ctx) return TVL1_ERR_ARG;
+    ctx->band_use_nccl_per_iteration = use_nccl_per_iteration != 0;
+    return TVL1_OK;
+}
+
+int tvl1_band_exchange_mode(const tvl1_ctx *ctx)
+{
+    if (!ctx || !ctx->nccl_comm) return -1;
+    return (ctx->p2p_ready && !ctx->band_use_nccl_per_iteration) ? 1 : 0;
 }
 
 void tvl1_band_rows(int ny, int rank, int world, int *row_begin, int *row_end)

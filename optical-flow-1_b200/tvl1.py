@@ -230,6 +230,13 @@ class TVL1:
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._ck(self.lib.tvl1_band_init(self.ctx, C.c_int(rank), C.c_int(world), buf))
 
+    def band_set_exchange(self, mode):
+        """'peer' (default: NVLink stores + mailboxes inside the iteration kernel) or 'nccl'."""
+        self._ck(self.lib.tvl1_band_set_exchange(self.ctx, C.c_int(1 if mode == "nccl" else 0)))
+
+    def band_exchange_mode(self):
+        return {1: "peer", 0: "nccl", -1: None}[self.lib.tvl1_band_exchange_mode(self.ctx)]
+
     def band_rows(self, ny, rank, world):
         a, b = C.c_int(), C.c_int()
         self.lib.tvl1_band_rows(C.c_int(ny), C.c_int(rank), C.c_int(world), C.byref(a), C.byref(b))

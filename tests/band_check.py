@@ -64,11 +64,18 @@ def main():
         return 1e3 * best
 
     dev_solo = timed(lambda: g.solve_batch_device(*ptrs, 1, nx, ny, **kw))
-    dev_band = timed(lambda: g.band_solve_device(*ptrs, nx, ny, min_split_rows=min_rows, **kw))
     big = max(min_rows, ny // 2 + 1)       # split the finest level only
-    dev_band_top = timed(lambda: g.band_solve_device(*ptrs, nx, ny, min_split_rows=big, **kw))
-    top_iters, _ = g.band_solve_device(*ptrs, nx, ny, min_split_rows=big, **kw)
-    same_top = bool(np.array_equal(top_iters, solo[2]) and np.array_equal(du1.cpu().numpy(), solo[0]))
+    dev, same_top = {}, True
+    for mode in ("peer", "nccl"):
+        g.band_set_exchange(mode)
+        eff = g.band_exchange_mode()
+        dev[mode] = dict(mode_in_effect=eff,
+                         all_levels_ge_min_rows=timed(lambda: g.band_solve_device(*ptrs, nx, ny, min_split_rows=min_rows, **kw)),
+                         finest_level_only=timed(lambda: g.band_solve_device(*ptrs, nx, ny, min_split_rows=big, **kw)))
+        it, _ = g.band_solve_device(*ptrs, nx, ny, min_split_rows=min_rows, **kw)
+        same_top = same_top and bool(np.array_equal(it, solo[2]) and np.array_equal(du1.cpu().numpy(), solo[0])
+                                     and np.array_equal(du2.cpu().numpy(), solo[1]))
+    g.band_set_exchange("peer")
 
     d = max(np.abs(solo[0] - band[0]).max(), np.abs(solo[1] - band[1]).max())
     same_iters = bool(np.array_equal(solo[2], band[2]))
@@ -76,9 +83,8 @@ def main():
     res = dict(rank=rank, world=world, nx=nx, ny=ny, params=kw, min_split_rows=min_rows, band_rows=rows,
                same_iteration_counts=same_iters, max_abs_flow_diff=float(d),
                solo_ms=1e3 * t_solo, band_ms=1e3 * t_band, host_syncs=st["host_syncs"],
-               device_resident_ms=dict(single_gpu=dev_solo, band_all_levels_ge_min_rows=dev_band,
-                                       band_finest_level_only=dev_band_top),
-               finest_only_matches_single_gpu=same_top,
+               device_resident_ms=dict(single_gpu=dev_solo, band=dev),
+               both_exchange_modes_match_single_gpu=same_top, exchange_mode=g.band_exchange_mode(),
                iterations_per_level=band[2].sum(axis=1).tolist())
     ok = same_iters and d <= 1e-5 and same_top
     flags = [None] * world
