@@ -117,7 +117,7 @@ int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const 
 
 /* -- row-band mode: ONE image pair split over several GPUs ----------------------- */
 /* One context per rank/GPU.  Rank 0 makes an id (tvl1_band_unique_id), the caller distributes the
- * TVL1_NCCL_ID_BYTES bytes to every rank by whatever means it has (torch.distributed broadcast, MPI,
+ * TVL1_NCCL_ID_BYTES bytes to every rank by whatever means it has (a process-group broadcast, MPI,
  * a file), every rank calls tvl1_band_init, then all ranks call tvl1_band_solve_* together with the
  * same full images and parameters.  Levels with at least min_split_rows rows are cut into row bands
  * whose 1-row halos (flow + dual variables) and error sum travel over NCCL every iteration; smaller
