@@ -1031,7 +1031,8 @@ k_iterate_t1(const IterParams P)
             const long long t0 = clock64();
             for (int r = 0; r < P.peers.world; r++) {        // fixed rank order: same bits everywhere
                 while (ld_acquire_sys(&mine->tag[par][r]) != e) {
-                    if (clock64() - t0 > (1ll << 33)) { mine->timed_out = 1; break; }   // ~4 s: never hang the GPU
+                    // ~4 s in total, once: never hang the GPU on a rank that fell out of step
+                    if (mine->timed_out || clock64() - t0 > (1ll << 33)) { mine->timed_out = 1; break; }
                 }
                 all += *((volatile double *) &mine->sum[par][r]);
             }

@@ -111,6 +111,7 @@ struct tvl1_ctx {
     int host_lanes = 4;                      // lanes used by the host-buffer batch entry points
     int dev_lanes = 2;                       // lanes used by the device-buffer batch entry point
     bool is_sibling = false;
+    tvl1_ctx *band_ctx = nullptr;            // private context of the row-band mode
     std::vector<cudaEvent_t> ev_pool;
     std::vector<EventPair> ev_used;
     // staging for the host-buffer entry points
@@ -244,14 +245,20 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
     return best;
 }
 
+bool workspace_matches(const tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride,
+                       int row_pad)
+{
+    const Workspace &w = ctx->ws;
+    return w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
+           w.stat_stride >= stat_stride && w.resident_key == (ctx->use_resident ? 1 + ctx->force_cluster : 0) &&
+           w.row_pad == row_pad;
+}
+
 int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride,
                      int row_pad = 1)
 {
     Workspace &w = ctx->ws;
-    if (w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
-        w.stat_stride >= stat_stride && w.resident_key == (ctx->use_resident ? 1 + ctx->force_cluster : 0) &&
-        w.row_pad == row_pad)
-        return TVL1_OK;
+    if (workspace_matches(ctx, nx, ny, nscales, zfactor, B, stat_stride, row_pad)) return TVL1_OK;
     free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(w);
     w.nx = nx; w.ny = ny; w.nscales = nscales; w.zfactor = zfactor; w.B = B;
@@ -1054,8 +1061,7 @@ int p2p_setup_mailboxes(tvl1_ctx *ctx)
 // (re)bind the neighbours' state buffers after the workspace was (re)allocated -- collective
 int p2p_bind_state(tvl1_ctx *ctx)
 {
-    if (!ctx->p2p_ready || ctx->p2p_state_key == ctx->ws.state) return TVL1_OK;
-    p2p_release_state(ctx);
+    if (!ctx->p2p_ready || ctx->p2p_state_key != nullptr) return TVL1_OK;   // released <=> must (re)bind
     std::vector<cudaIpcMemHandle_t> all;
     TRY(exchange_ipc_handles(ctx, ctx->ws.state, all));
     const int nb[2] = { ctx->band_rank - 1, ctx->band_rank + 1 };
@@ -1184,12 +1190,20 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
              const tvl1_params &prm, int min_split_rows, int *iters_out, double *errs_out)
 {
     const int ns = prm.nscales, nstat = ns * prm.warps, G = ctx->band_world;
-    TRY(ensure_workspace(ctx, nx, ny, ns, prm.zfactor, 1, nstat, G));
-    Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
     ncclComm_t comm = (ncclComm_t) ctx->nccl_comm;
+    // This context's workspace is used by band solves only (see band_context), and those are
+    // collective: every rank takes the same (re)allocation decision here.  Before anybody frees a
+    // buffer that neighbours have mapped, all ranks drop their mappings and meet at a barrier.
+    if (!workspace_matches(ctx, nx, ny, ns, prm.zfactor, 1, nstat, G)) {
+        p2p_release_state(ctx);
+        NK(g_nccl.AllReduce(ctx->d_band_sum, ctx->d_band_sum, 1, ncclDouble, ncclSum, comm, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    TRY(ensure_workspace(ctx, nx, ny, ns, prm.zfactor, 1, nstat, G));
+    Workspace &w = ctx->ws;
     const bool p2p = ctx->p2p_ready && !ctx->band_use_nccl_per_iteration;
-    if (p2p) TRY(p2p_bind_state(ctx));
+    if (ctx->p2p_ready) TRY(p2p_bind_state(ctx));
     // a negative threshold also splits on a single rank (one band = the whole level): the band code
     // path without neighbours, used by the single-GPU tests
     const bool force = min_split_rows < 0;
@@ -1276,6 +1290,13 @@ struct Dev {
 // =================================================================================================
 extern "C" {
 
+static int band_init_impl(tvl1_ctx *ctx, int rank, int world, const unsigned char *id_bytes);
+static int band_solve_host_impl(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2, int nx,
+                                int ny, const tvl1_params *prm, int min_split_rows, int *iters_out, double *errs_out);
+static int band_solve_dev_impl(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, float *du2,
+                               int nx, int ny, const tvl1_params *prm, int min_split_rows, int *iters_out,
+                               double *errs_out);
+
 int tvl1_device_count(void)
 {
     int n = 0;
@@ -1317,6 +1338,7 @@ void tvl1_destroy(tvl1_ctx *ctx)
 {
     if (!ctx) return;
     for (auto &sb : ctx->sib) { if (sb) tvl1_destroy(sb); sb = nullptr; }
+    if (ctx->band_ctx) { tvl1_destroy(ctx->band_ctx); ctx->band_ctx = nullptr; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     p2p_release_state(ctx);
@@ -1462,9 +1484,41 @@ int tvl1_band_unique_id(unsigned char *id_out)
     return TVL1_OK;
 }
 
-int tvl1_band_init(tvl1_ctx *ctx, int rank, int world, const unsigned char *id_bytes)
+// Band solves run on a private sibling context: its workspace is (re)allocated only by collective
+// calls, so the ranks' decisions to re-export / re-map buffers can never diverge because one rank did
+// some single-GPU work in between.
+static tvl1_ctx *band_context(tvl1_ctx *ctx)
 {
-    if (!ctx || !id_bytes || world < 1 || rank < 0 || rank >= world) return fail_arg(ctx, "bad argument");
+    if (!ctx) return nullptr;
+    if (!ctx->band_ctx) {
+        if (tvl1_create(ctx->device, &ctx->band_ctx) != TVL1_OK) {
+            ctx->err = std::string("band context: ") + tvl1_last_error(nullptr);
+            return nullptr;
+        }
+        ctx->band_ctx->is_sibling = true;
+    }
+    ctx->band_ctx->profiling = ctx->profiling;
+    ctx->band_ctx->use_resident = ctx->use_resident;
+    return ctx->band_ctx;
+}
+
+static int band_return(tvl1_ctx *ctx, tvl1_ctx *bc, int rc)
+{
+    ctx->stats = bc->stats;
+    if (rc != TVL1_OK) ctx->err = bc->err;
+    return rc;
+}
+
+int tvl1_band_init(tvl1_ctx *outer, int rank, int world, const unsigned char *id_bytes)
+{
+    if (!outer || !id_bytes || world < 1 || rank < 0 || rank >= world) return fail_arg(outer, "bad argument");
+    tvl1_ctx *bc = band_context(outer);
+    if (!bc) return TVL1_ERR_CUDA;
+    return band_return(outer, bc, band_init_impl(bc, rank, world, id_bytes));
+}
+
+static int band_init_impl(tvl1_ctx *ctx, int rank, int world, const unsigned char *id_bytes)
+{
     if (const char *e = load_nccl()) { ctx->err = e; return TVL1_ERR_CUDA; }
     CK(cudaSetDevice(ctx->device));
     if (ctx->nccl_comm) { g_nccl.CommDestroy((ncclComm_t) ctx->nccl_comm); ctx->nccl_comm = nullptr; }
@@ -1482,8 +1536,16 @@ int tvl1_band_init(tvl1_ctx *ctx, int rank, int world, const unsigned char *id_b
     return TVL1_OK;
 }
 
-int tvl1_band_solve_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2, int nx,
+int tvl1_band_solve_f32(tvl1_ctx *outer, const float *I0, const float *I1, float *u1, float *u2, int nx,
                         int ny, const tvl1_params *prm, int min_split_rows, int *iters_out, double *errs_out)
+{
+    tvl1_ctx *bc = band_context(outer);
+    if (!bc) return outer ? TVL1_ERR_CUDA : TVL1_ERR_ARG;
+    return band_return(outer, bc, band_solve_host_impl(bc, I0, I1, u1, u2, nx, ny, prm, min_split_rows, iters_out, errs_out));
+}
+
+static int band_solve_host_impl(tvl1_ctx *ctx, const float *I0, const float *I1, float *u1, float *u2, int nx,
+                                int ny, const tvl1_params *prm, int min_split_rows, int *iters_out, double *errs_out)
 {
     TRY(check_common(ctx, I0, I1, u1, u2, nx, ny, prm, true));
     if (!ctx->nccl_comm) return fail_arg(ctx, "tvl1_band_init has not been called on this context");
@@ -1503,9 +1565,18 @@ int tvl1_band_solve_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *
     return TVL1_OK;
 }
 
-int tvl1_band_solve_dev_f32(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, float *du2,
+int tvl1_band_solve_dev_f32(tvl1_ctx *outer, const float *dI0, const float *dI1, float *du1, float *du2,
                             int nx, int ny, const tvl1_params *prm, int min_split_rows, int *iters_out,
                             double *errs_out)
+{
+    tvl1_ctx *bc = band_context(outer);
+    if (!bc) return outer ? TVL1_ERR_CUDA : TVL1_ERR_ARG;
+    return band_return(outer, bc, band_solve_dev_impl(bc, dI0, dI1, du1, du2, nx, ny, prm, min_split_rows, iters_out, errs_out));
+}
+
+static int band_solve_dev_impl(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, float *du2,
+                               int nx, int ny, const tvl1_params *prm, int min_split_rows, int *iters_out,
+                               double *errs_out)
 {
     TRY(check_common(ctx, dI0, dI1, du1, du2, nx, ny, prm, true));
     if (!ctx->nccl_comm) return fail_arg(ctx, "tvl1_band_init has not been called on this context");
@@ -1515,15 +1586,17 @@ int tvl1_band_solve_dev_f32(tvl1_ctx *ctx, const float *dI0, const float *dI1, f
     return TVL1_OK;
 }
 
-int tvl1_band_set_exchange(tvl1_ctx *ctx, int use_nccl_per_iteration)
+int tvl1_band_set_exchange(tvl1_ctx *outer, int use_nccl_per_iteration)
 {
+    tvl1_ctx *ctx = band_context(outer);
     if (!ctx) return TVL1_ERR_ARG;
     ctx->band_use_nccl_per_iteration = use_nccl_per_iteration != 0;
     return TVL1_OK;
 }
 
-int tvl1_band_exchange_mode(const tvl1_ctx *ctx)
+int tvl1_band_exchange_mode(const tvl1_ctx *outer)
 {
+    const tvl1_ctx *ctx = outer ? outer->band_ctx : nullptr;
     if (!ctx || !ctx->nccl_comm) return -1;
     return (ctx->p2p_ready && !ctx->band_use_nccl_per_iteration) ? 1 : 0;
 }
