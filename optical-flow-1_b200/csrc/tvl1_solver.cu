@@ -69,6 +69,7 @@ struct SolveGraph {
     cudaGraphExec_t exec = nullptr;
     tvl1_params prm{};
     bool multiscale = false, profiling = false;
+    long long variant = 0;
     unsigned long long static_launches = 0;   // kernel nodes outside the while bodies
     unsigned long long pixel_warps = 0;
     std::vector<EventPair> events;            // external event-record nodes (profiling)
@@ -93,6 +94,8 @@ struct tvl1_ctx {
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
     SolveGraph sg;
+    SolveGraph *cap = nullptr;               // graph being captured (profiling events attach to it)
+    SolveGraph level_sg[TVL1_MAX_LEVELS];    // row-band mode: one graph per pyramid level
     // row-band mode (one image over several GPUs)
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
@@ -260,6 +263,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     Workspace &w = ctx->ws;
     if (workspace_matches(ctx, nx, ny, nscales, zfactor, B, stat_stride, row_pad)) return TVL1_OK;
     free_graph(ctx->sg, ctx->ev_pool);
+    for (auto &g : ctx->level_sg) free_graph(g, ctx->ev_pool);
     free_workspace(w);
     w.nx = nx; w.ny = ny; w.nscales = nscales; w.zfactor = zfactor; w.B = B;
     w.stat_stride = stat_stride;
@@ -331,8 +335,8 @@ struct Span {
         EventPair p{ take_event(c), take_event(c), kind, level };
         if (c->capturing) {
             cudaEventRecordWithFlags(p.a, c->stream, cudaEventRecordExternal);
-            c->sg.events.push_back(p);
-            idx = (int) c->sg.events.size() - 1;
+            c->cap->events.push_back(p);
+            idx = (int) c->cap->events.size() - 1;
         } else {
             cudaEventRecord(p.a, c->stream);
             c->ev_used.push_back(p);
@@ -342,7 +346,7 @@ struct Span {
     void end()
     {
         if (idx < 0) return;
-        if (ctx->capturing) cudaEventRecordWithFlags(ctx->sg.events[idx].b, ctx->stream, cudaEventRecordExternal);
+        if (ctx->capturing) cudaEventRecordWithFlags(ctx->cap->events[idx].b, ctx->stream, cudaEventRecordExternal);
         else cudaEventRecord(ctx->ev_used[idx].b, ctx->stream);
         idx = -1;
     }
@@ -637,18 +641,23 @@ bool same_params(const tvl1_params &a, const tvl1_params &b)
            a.zfactor == b.zfactor && a.warps == b.warps && a.epsilon == b.epsilon;
 }
 
-int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multiscale)
+// Capture `enqueue` into `sg` (once per key) and replay it.  `variant` distinguishes the graphs a
+// context keeps (whole coarse-to-fine solve; one level of the row-band mode, ...).
+template <class Fn>
+int replay_graph(tvl1_ctx *ctx, SolveGraph &sg, const tvl1_params &prm, bool multiscale, long long variant,
+                 Fn &&enqueue)
 {
-    if (!ctx->use_graph) return enqueue_coarse_to_fine(ctx, B, prm, multiscale);
-    SolveGraph &sg = ctx->sg;
-    if (!sg.exec || !same_params(sg.prm, prm) || sg.multiscale != multiscale || sg.profiling != ctx->profiling) {
+    if (!sg.exec || !same_params(sg.prm, prm) || sg.multiscale != multiscale || sg.profiling != ctx->profiling ||
+        sg.variant != variant) {
         free_graph(sg, ctx->ev_pool);
-        sg.prm = prm; sg.multiscale = multiscale; sg.profiling = ctx->profiling;
+        sg.prm = prm; sg.multiscale = multiscale; sg.profiling = ctx->profiling; sg.variant = variant;
         const tvl1_stats keep = ctx->stats;
         CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
         ctx->capturing = true;
-        const int rc = enqueue_coarse_to_fine(ctx, B, prm, multiscale);
+        ctx->cap = &sg;
+        const int rc = enqueue();
         ctx->capturing = false;
+        ctx->cap = nullptr;
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &sg.graph);
         sg.static_launches = ctx->stats.kernel_launches - keep.kernel_launches;
         sg.pixel_warps = ctx->stats.pixel_warps - keep.pixel_warps;
@@ -665,6 +674,13 @@ int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multis
         for (const auto &p : sg.events) add_span_time(ctx, p);
     }
     return TVL1_OK;
+}
+
+int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multiscale)
+{
+    if (!ctx->use_graph) return enqueue_coarse_to_fine(ctx, B, prm, multiscale);
+    return replay_graph(ctx, ctx->sg, prm, multiscale, 0,
+                        [&]() { return enqueue_coarse_to_fine(ctx, B, prm, multiscale); });
 }
 
 // Resets the per-solve device state and builds both image pyramids (src/tvl1flow.cpp:255-275).
@@ -1030,6 +1046,7 @@ int exchange_ipc_handles(tvl1_ctx *ctx, void *dev_ptr, std::vector<cudaIpcMemHan
 
 void p2p_release_state(tvl1_ctx *ctx)
 {
+    for (auto &g : ctx->level_sg) free_graph(g, ctx->ev_pool);   // peer pointers are baked into them
     for (float *&p : ctx->peer_state) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
     ctx->p2p_state_key = nullptr;
 }
@@ -1215,9 +1232,24 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
     int hint = 16;
     for (int s = ns - 1; s >= 0; s--) {
         const int stat_base = (ns - 1 - s) * prm.warps;
-        if (is_split(s) && p2p) TRY(band_level_p2p(ctx, s, prm, stat_base, hint));
-        else if (is_split(s)) TRY(band_level(ctx, s, prm, stat_base, hint));
-        else TRY(run_level(ctx, s, 1, prm, stat_base, hint));      // replicated: identical on every rank
+        const int ls = std::min(s, TVL1_MAX_LEVELS - 1);
+        if (is_split(s) && !p2p) {
+            TRY(band_level(ctx, s, prm, stat_base, hint));         // NCCL calls per iteration: host-driven
+        } else if (ctx->use_graph && s < TVL1_MAX_LEVELS) {
+            // one graph per level (loops are conditional WHILE nodes; every rank replays the same
+            // number of iterations because every rank takes the same stop decision)
+            const long long variant = 1 + (is_split(s) ? 1 : 0) + 2ll * G + 64ll * ctx->band_rank + 4096ll * min_split_rows;
+            if (is_split(s))
+                TRY(replay_graph(ctx, ctx->level_sg[ls], prm, true, variant,
+                                 [&]() { int h = 16; return band_level_p2p(ctx, s, prm, stat_base, h); }));
+            else
+                TRY(replay_graph(ctx, ctx->level_sg[ls], prm, true, variant,
+                                 [&]() { int h = 16; return run_level(ctx, s, 1, prm, stat_base, h); }));
+        } else if (is_split(s)) {
+            TRY(band_level_p2p(ctx, s, prm, stat_base, hint));
+        } else {
+            TRY(run_level(ctx, s, 1, prm, stat_base, hint));       // replicated: identical on every rank
+        }
         if (is_split(s)) {
             // every rank gets the whole flow of this level (in place: band r sits at rows r*rows_per)
             PairCtl c;
@@ -1342,6 +1374,7 @@ void tvl1_destroy(tvl1_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     p2p_release_state(ctx);
+    for (auto &g : ctx->level_sg) free_graph(g, ctx->ev_pool);
     for (int r = 0; r < kMaxRanks; r++)
         if (ctx->boxes[r] && ctx->boxes[r] != ctx->my_box) cudaIpcCloseMemHandle(ctx->boxes[r]);
     cudaFree(ctx->my_box);
