@@ -243,6 +243,18 @@ __device__ __forceinline__ float cubic_cell(float v0, float v1, float v2, float 
                                            + t * (3.0f * (v1 - v2) + v3 - v0)));
 }
 
+// Catmull-Rom / Keys(a=-1/2) weights of the four taps at fraction t; algebraically the cubic of
+// src/bicubic_interpolation.cpp:108-123 written as a dot product so that one set of weights
+// serves I1, dI1/dx and dI1/dy.
+__device__ __forceinline__ void keys_weights(float t, float w[4])
+{
+    const float t2 = t * t, t3 = t2 * t;
+    w[0] = 0.5f * (-t + 2.0f * t2 - t3);
+    w[1] = 0.5f * (2.0f - 5.0f * t2 + 3.0f * t3);
+    w[2] = 0.5f * (t + 4.0f * t2 - 3.0f * t3);
+    w[3] = 0.5f * (t3 - t2);
+}
+
 // bicubic_interpolation_at with border_out = false and non-negative coordinates
 // (src/bicubic_interpolation.cpp:153-245): neighbours x-1,x,x+1,x+2 index-clamped (Neumann),
 // fractions relative to the (unclamped, since 0 <= uu < nx) base index; y first inside each
@@ -319,29 +331,48 @@ k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, si
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int j1 = X0 + tx + 32 * (q & 1), i1 = Y0 + ty + 8 * (q >> 1);
-        if (j1 >= fine.nx || i1 >= row_end) continue;
-        const double j2 = j1 / fx, i2 = i1 / fy;
-        const size_t o = (size_t) i1 * fine.pitch + j1;
-        if (!staged) {
+    if (!staged) {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            const int j1 = X0 + tx + 32 * (q & 1), i1 = Y0 + ty + 8 * (q >> 1);
+            if (j1 >= fine.nx || i1 >= row_end) continue;
+            const double j2 = j1 / fx, i2 = i1 / fy;
+            const size_t o = (size_t) i1 * fine.pitch + j1;
             dst[o] = bicubic_clamped(src, coarse.pitch, coarse.nx, coarse.ny, j2, i2) * scale;
             dst[field_stride + o] =
                 bicubic_clamped(src + field_stride, coarse.pitch, coarse.nx, coarse.ny, j2, i2) * scale;
-            continue;
         }
+        return;
+    }
+    // The sample grid is separable: a thread's four pixels share two column positions and two row
+    // positions; base indices and fractions come from the reference's fp64 division, the cubic is
+    // applied as Keys weights (same polynomial as cubic_cell, one set per column / row).
+    int cx[2], cy[2];
+    float wx[2][4], wy[2][4];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double j2 = (X0 + tx + 32 * k) / fx, i2 = (Y0 + ty + 8 * k) / fy;
         const int x = clampi((int) j2, 0, coarse.nx - 1), y = clampi((int) i2, 0, coarse.ny - 1);
-        const float fxr = (float) (j2 - x), fyr = (float) (i2 - y);
-        const int cx = x - 1 - xlo, cy = y - 1 - ylo;
+        keys_weights((float) (j2 - x), wx[k]);
+        keys_weights((float) (i2 - y), wy[k]);
+        cx[k] = x - 1 - xlo;
+        cy[k] = y - 1 - ylo;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int kx = q & 1, ky = q >> 1;
+        const int j1 = X0 + tx + 32 * kx, i1 = Y0 + ty + 8 * ky;
+        if (j1 >= fine.nx || i1 >= row_end) continue;
+        const int o = i1 * fine.pitch + j1;
 #pragma unroll
         for (int comp = 0; comp < 2; comp++) {
-            float col[4];
+            float acc = 0.f;
 #pragma unroll
-            for (int a = 0; a < 4; a++)
-                col[a] = cubic_cell(s_c[comp][cy][cx + a], s_c[comp][cy + 1][cx + a],
-                                    s_c[comp][cy + 2][cx + a], s_c[comp][cy + 3][cx + a], fyr);
-            dst[(size_t) comp * field_stride + o] = cubic_cell(col[0], col[1], col[2], col[3], fxr) * scale;
+            for (int r = 0; r < 4; r++) {
+                const float *row = &s_c[comp][cy[ky] + r][cx[kx]];
+                acc += wy[ky][r] * (wx[kx][0] * row[0] + wx[kx][1] * row[1] + wx[kx][2] * row[2] + wx[kx][3] * row[3]);
+            }
+            dst[(size_t) comp * field_stride + o] = acc * scale;
         }
     }
 }
@@ -510,18 +541,6 @@ __global__ void k_fill_bench(float *__restrict__ state, float *__restrict__ cons
 // ------------------------------------------------------------------------------------------------
 // (b) warp + precompute
 // ------------------------------------------------------------------------------------------------
-
-// Catmull-Rom / Keys(a=-1/2) weights of the four taps at fraction t; algebraically the cubic of
-// src/bicubic_interpolation.cpp:108-123 written as a dot product so that one set of weights
-// serves I1, dI1/dx and dI1/dy.
-__device__ __forceinline__ void keys_weights(float t, float w[4])
-{
-    const float t2 = t * t, t3 = t2 * t;
-    w[0] = 0.5f * (-t + 2.0f * t2 - t3);
-    w[1] = 0.5f * (2.0f - 5.0f * t2 + 3.0f * t3);
-    w[2] = 0.5f * (t + 4.0f * t2 - 3.0f * t3);
-    w[3] = 0.5f * (t3 - t2);
-}
 
 // One kernel for src/tvl1flow.cpp:84 and :94-109:
 //   centered_gradient(I1)                      src/operators.cpp:335-406
@@ -1174,22 +1193,19 @@ k_iterate_resident(const ResParams P)
         for (int i = tid; i < pitch; i += kResThreads) sP12[i] = sP22[i] = 0.f;     // p[-1] = 0
 
     // ---- per-thread pixel groups and their constants (registers) -------------------------------
-    int qoff[kResQuads];          // float offset of the group inside a band plane (row*pitch + x0)
-    int qx0[kResQuads], qrow[kResQuads];
-    bool qok[kResQuads];
+    // per group: band row (bits 16..30), first column (bits 0..15), valid (sign bit clear)
+    int qpos[kResQuads];
     float4 cix[kResQuads], ciy[kResQuads], crho[kResQuads];
 #pragma unroll
     for (int k = 0; k < kResQuads; k++) {
         const int q = tid + k * kResThreads;
-        qok[k] = q < nquads;
-        const int lr = qok[k] ? q / qpr : 0;
-        const int cq = qok[k] ? q - lr * qpr : 0;
-        qrow[k] = lr;
-        qx0[k] = cq * 4;
-        qoff[k] = lr * pitch + cq * 4;
+        const bool ok = q < nquads;
+        const int lr = ok ? q / qpr : 0;
+        const int cq = ok ? q - lr * qpr : 0;
+        qpos[k] = (lr << 16) | (cq * 4) | (ok ? 0 : (int) 0x80000000);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         cix[k] = ciy[k] = crho[k] = z;
-        if (qok[k]) {
+        if (ok) {
             const size_t o = (size_t) (r0 + lr) * pitch + cq * 4;
             cix[k] = ldg4(cst + C_IX * fs + o);
             ciy[k] = ldg4(cst + C_IY * fs + o);
@@ -1225,8 +1241,10 @@ k_iterate_resident(const ResParams P)
         float errp = 0.f;
 #pragma unroll
         for (int k = 0; k < kResQuads; k++) {
-            const int o = qoff[k], x0 = qx0[k];
-            const int gy = r0 + qrow[k];
+            const bool ok = qpos[k] >= 0;
+            const int lrow = (qpos[k] >> 16) & 0x7fff, x0 = qpos[k] & 0xffff;
+            const int o = lrow * pitch + x0;
+            const int gy = r0 + lrow;
             const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
             const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
             const float4 p12 = lds4(sP12 + o + pitch), p22 = lds4(sP22 + o + pitch);
@@ -1250,14 +1268,14 @@ k_iterate_resident(const ResParams P)
                           P.l_t, P.theta, o1[e], o2[e]);
                 const float e1 = o1[e] - a, e2 = o2[e] - c;
                 const float sq = e1 * e1 + e2 * e2;
-                errp += (qok[k] && x0 + e < nx) ? sq : 0.f;
+                errp += (ok && x0 + e < nx) ? sq : 0.f;
             }
-            if (qok[k]) {
+            if (ok) {
                 const float4 n1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
                 const float4 n2 = make_float4(o2[0], o2[1], o2[2], o2[3]);
                 st4(sU1 + o, n1);
                 st4(sU2 + o, n2);
-                if (qrow[k] == 0 && rank > 0) {     // my first row is the upper neighbour's row below
+                if (lrow == 0 && rank > 0) {     // my first row is the upper neighbour's row below
                     st4(upU1 + x0, n1);
                     st4(upU2 + x0, n2);
                 }
@@ -1277,8 +1295,10 @@ k_iterate_resident(const ResParams P)
         }
 #pragma unroll
         for (int k = 0; k < kResQuads; k++) {
-            const int o = qoff[k], x0 = qx0[k];
-            const int gy = r0 + qrow[k];
+            const bool ok = qpos[k] >= 0;
+            const int lrow = (qpos[k] >> 16) & 0x7fff, x0 = qpos[k] & 0xffff;
+            const int o = lrow * pitch + x0;
+            const int gy = r0 + lrow;
             const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
             const float4 b1 = lds4(sU1 + o + pitch), b2 = lds4(sU2 + o + pitch);
             float r1 = __shfl_down_sync(0xffffffffu, u1.x, 1);
@@ -1300,14 +1320,14 @@ k_iterate_resident(const ResParams P)
                         last_col ? 0.f : e2 - c2, has_below ? TVL1_F4_GET(b2, e) - c2 : 0.f,
                         P.taut, q11[e], q12[e], q21[e], q22[e]);
             }
-            if (qok[k]) {
+            if (ok) {
                 const float4 n12 = make_float4(q12[0], q12[1], q12[2], q12[3]);
                 const float4 n22 = make_float4(q22[0], q22[1], q22[2], q22[3]);
                 st4(sP11 + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
                 st4(sP21 + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
                 st4(sP12 + o + pitch, n12);
                 st4(sP22 + o + pitch, n22);
-                if (qrow[k] == rows - 1 && rank < C - 1) {   // my last row is the lower neighbour's row above
+                if (lrow == rows - 1 && rank < C - 1) {      // my last row is the lower neighbour's row above
                     st4(dnP12 + x0, n12);
                     st4(dnP22 + x0, n22);
                 }
