@@ -291,11 +291,15 @@ def run_ours(args, rank, local_rank, world):
         per_level.append({"level": l, "launches": acc["level_iterate_launches"][l], "ms": lms,
                           "GBps": ALGO_BYTES_PER_PIXEL_ITERATION * lpx / (lms / 1e3) / 1e9 if lms > 0 else None})
     roofline = {
-        "kernel": "k_iterate_t1 (fused TH + div + u update + grad + p update + stop test)",
+        "kernel": "fused primal-dual iteration (TH + div + u update + grad + p update + stop test): "
+                  "k_iterate_t1 streams the levels above 480x270 through HBM, k_iterate_resident keeps the "
+                  "smaller levels on chip (cluster + DSMEM); per_level shows each",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak if achieved else None,
         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
         "traffic_source": traffic.get("source") if traffic else None,
+        "traffic_launch": traffic.get("launch") if traffic else None,
+        "traffic_algorithmic_bytes_same_launch": traffic.get("algorithmic_bytes_same_launch") if traffic else None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_pixel_iteration": ALGO_BYTES_PER_PIXEL_ITERATION,
         "pixel_iterations": acc["pixel_iterations"], "launches": acc["iterate_launches"],
