@@ -114,6 +114,25 @@ def test_warp_precompute(gpu, oracle_f64, shape):
     assert np.allclose(got["grad"], ref["grad"], rtol=1e-4, atol=1e-4)
 
 
+def test_warp_precompute_large_flow_takes_the_global_gather_path(gpu, oracle_f64):
+    """Flows beyond the +-8 px box staged in shared memory (and a flow discontinuity inside one tile)
+    must give the same numbers through the out-of-line global gather."""
+    ny, nx = 96, 200
+    rs = np.random.RandomState(16)
+    yy, xx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    I1 = (128 + 60 * np.sin(0.11 * xx + 0.07 * yy) + 40 * np.cos(0.09 * yy - 0.03 * xx)).astype(np.float32)
+    I0 = (I1 + rs.uniform(-5, 5, I1.shape)).astype(np.float32)
+    u1 = rs.uniform(-40, 40, I1.shape).astype(np.float32)
+    u2 = rs.uniform(-25, 25, I1.shape).astype(np.float32)
+    u1[:, :100] = 3.25          # half of every tile row inside the margin, half far outside
+    got = gpu.warp_precompute(I0, I1, u1, u2)
+    ref = oracle_f64.warp_precompute(I0, I1, u1, u2)
+    assert np.abs(got["I1wx"] - ref["I1wx"]).max() < 2e-4
+    assert np.abs(got["I1wy"] - ref["I1wy"]).max() < 2e-4
+    assert np.abs(got["rho_c"] - ref["rho_c"]).max() < 2e-2      # |u| up to 40 multiplies the gradient error
+    assert np.array_equal(got["grad"] == 0, ref["grad"] == 0)
+
+
 @pytest.mark.parametrize("shape", [_cases.FUNC_SHAPE, (40, 128), (33, 250), (8, 124), (9, 125)])
 @pytest.mark.parametrize("iters", [1, 3])
 def test_iterate(gpu, oracle_f64, shape, iters):
@@ -243,6 +262,29 @@ def test_single_scale_entry(gpu, oracle_f64):
     r = oracle_f64.single_scale(I0, I1, u1, u2, warps=3, eps=0.01)
     assert np.array_equal(g[2], r[2]), (g[2], r[2])
     assert_flow_close(g[0], g[1], r[0], r[1], "single scale")
+
+
+def test_large_motion_solve(gpu, oracle_f64):
+    """A pair whose motion (about 12 px at the finest level) exceeds the warp kernel's staged margin:
+    the solver must still agree with the reference."""
+    I0, I1 = _cases.synth.make_pair(320, 240, seed=9, scale=4.0)
+    kw = dict(nscales=4, warps=4, eps=0.01)
+    u1, u2, iters, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    r1, r2, riters, _ = oracle_f64.multiscale(I0, I1, **kw)
+    assert np.abs(r1).max() > 8.5          # the case really leaves the margin
+    assert np.array_equal(iters, riters), (iters.tolist(), riters.tolist())
+    assert_flow_close(u1, u2, r1, r2, "large motion")
+
+
+def test_tiny_and_thin_images(gpu, oracle_f64):
+    """Levels narrower than one warp strip / one warp tile, heights below one strip."""
+    for (nx, ny, ns) in [(24, 40, 2), (125, 9, 1), (16, 16, 1), (300, 20, 2)]:
+        I0, I1 = _cases.synth.make_pair(nx, ny, seed=3, scale=0.2)
+        kw = dict(nscales=ns, warps=2, eps=0.01)
+        u1, u2, iters, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+        r1, r2, riters, _ = oracle_f64.multiscale(I0, I1, **kw)
+        assert np.array_equal(iters, riters), (nx, ny, iters.tolist(), riters.tolist())
+        assert_flow_close(u1, u2, r1, r2, "%dx%d" % (nx, ny))
 
 
 def test_eps_zero_runs_to_the_cap(gpu):
