@@ -236,6 +236,117 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
     }
 }
 
+// Register-marching variant of the separable blur for the windows the default parameters use
+// (R = 4: sigma 0.8; R = 5: zoom sigma at zfactor 0.5).  A thread owns 4 output columns and walks down
+// a strip of output rows: per input row it loads the 3D+2R+1 values its row pass needs (aligned float4
+// loads away from the left/right border), forms the 4 row-pass results, and keeps the last 2R+1 of
+// them in registers for the column pass -- no shared memory, every input element is read once per
+// strip (+2R halo rows).  Same boundary rule and summation order as k_gauss.
+template <int D, int R>
+__global__ void __launch_bounds__(128)
+k_gauss_march(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__restrict__ out,
+              int out_pitch, size_t out_stride, int nx, int ny, int onx, int ony, const GaussTaps taps,
+              const unsigned int *__restrict__ mm, int B)
+{
+    constexpr int S = 32;                         // output rows per strip
+    constexpr int W = 2 * R + 1;                  // window of row-pass results
+    constexpr int NIN = 3 * D + 2 * R + 1;        // input columns feeding 4 outputs
+    constexpr int OFF = (4 - (R % 4)) % 4;        // ix0 = 4*D*k - R  ->  aligned start is OFF columns earlier
+    constexpr int NV4 = (OFF + NIN + 3) / 4;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int z = blockIdx.z;
+    const int ox0 = (blockIdx.x * 32 + lane) * 4;
+    const int oy0 = (blockIdx.y * 4 + warp) * S;
+    if (oy0 >= ony || ox0 >= onx) return;
+    const int oy1 = min(oy0 + S, ony);
+    const float *src = in + (size_t) z * in_stride;
+    float *dst = out + (size_t) z * out_stride;
+    const int ix0 = ox0 * D - R;
+    const int ia = ix0 - OFF;
+    const bool fast = ia >= 0 && ia + 4 * NV4 <= nx && (in_pitch & 3) == 0 &&
+                      ((reinterpret_cast<size_t>(src) & 15) == 0);
+
+    float w[R + 1];
+#pragma unroll
+    for (int i = 0; i <= R; i++) w[i] = taps.w[i];
+    float mn = 0.f, scl = 1.f;
+    bool norm = false;
+    if (mm) {
+        mn = ord2f(mm[2 * (z % B)]);
+        const float den = ord2f(mm[2 * (z % B) + 1]) - mn;
+        norm = den > 0.f;
+        if (norm) scl = 255.0f / den;
+    }
+
+    float win[W][4];
+#pragma unroll
+    for (int u = 0; u < W; u++) win[u][0] = win[u][1] = win[u][2] = win[u][3] = 0.f;
+
+    const int iy_first = oy0 * D - R, iy_last = (oy1 - 1) * D + R;
+    for (int base = iy_first; base <= iy_last; base += W) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            const int iy = base + u;
+            if (iy > iy_last) break;
+            int gy = iy < 0 ? -iy : (iy >= ny ? 2 * ny - 1 - iy : iy);
+            gy = clampi(gy, 0, ny - 1);
+            const float *row = src + (size_t) gy * in_pitch;
+            float v[4 * NV4];
+            if (fast) {
+#pragma unroll
+                for (int q = 0; q < NV4; q++) {
+                    const float4 t = ldg4(row + ia + 4 * q);
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NIN; k++) {
+                    int gx = ix0 + k;
+                    gx = gx < 0 ? -gx : (gx >= nx ? 2 * nx - 1 - gx : gx);
+                    v[OFF + k] = __ldg(row + clampi(gx, 0, nx - 1));
+                }
+            }
+            if (norm) {
+#pragma unroll
+                for (int k = 0; k < NIN; k++) v[OFF + k] = (v[OFF + k] - mn) * scl;
+            }
+            // row pass at the four output columns (window slot u)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = OFF + R + k * D;
+                float sum = w[0] * v[c];
+#pragma unroll
+                for (int j = 1; j <= R; j++) sum += w[j] * (v[c - j] + v[c + j]);
+                win[u][k] = sum;
+            }
+            // the window now ends at input row iy: it is centred on row iy - R
+            const int cy = iy - R;
+            if (cy >= oy0 * D && (cy % D) == 0) {
+                const int oy = cy / D;
+                if (oy < oy1) {
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float sum = w[0] * win[(u + W - R) % W][k];
+#pragma unroll
+                        for (int j = 1; j <= R; j++)
+                            sum += w[j] * (win[(u + W - R - j) % W][k] + win[(u + W - R + j) % W][k]);
+                        o[k] = sum;
+                    }
+                    float *orow = dst + (size_t) oy * out_pitch + ox0;
+                    if (ox0 + 3 < onx && (out_pitch & 3) == 0 && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+                        st4(orow, make_float4(o[0], o[1], o[2], o[3]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (ox0 + k < onx) orow[k] = o[k];
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Keys cubic through v0..v3 at offset t from v1: src/bicubic_interpolation.cpp:108-123.
 __device__ __forceinline__ float cubic_cell(float v0, float v1, float v2, float v3, float t)
 {

@@ -386,14 +386,18 @@ int launch_gauss(tvl1_ctx *ctx, int D, const float *in, int in_pitch, size_t in_
     const int r = taps.size - 1;
 #define TVL1_GAUSS(D_, R_) k_gauss<D_, R_><<<g, dim3(32, 8), 0, st>>>(in, in_pitch, in_stride, out, out_pitch, \
                                                                       out_stride, nx, ny, onx, ony, taps, mm, B)
+#define TVL1_GAUSS_MARCH(D_, R_) k_gauss_march<D_, R_><<<gm, dim3(32, 4), 0, st>>>(in, in_pitch, in_stride, out, \
+                                                           out_pitch, out_stride, nx, ny, onx, ony, taps, mm, B)
+    const dim3 gm(ceil_div(onx, 128), ceil_div(ony, 128), nimg);   // marching kernel: 128 columns x 4 strips of 32 rows
     if (D == 1) {
         dim3 g(ceil_div(onx, 64), ceil_div(ony, 32), nimg);
-        if (r == 4) TVL1_GAUSS(1, 4); else if (r == 5) TVL1_GAUSS(1, 5); else TVL1_GAUSS(1, 0);
+        if (r == 4) TVL1_GAUSS_MARCH(1, 4); else if (r == 5) TVL1_GAUSS_MARCH(1, 5); else TVL1_GAUSS(1, 0);
     } else {
         dim3 g(ceil_div(onx, 32), ceil_div(ony, 16), nimg);
-        if (r == 5) TVL1_GAUSS(2, 5); else TVL1_GAUSS(2, 0);
+        if (r == 5) TVL1_GAUSS_MARCH(2, 5); else TVL1_GAUSS(2, 0);
     }
 #undef TVL1_GAUSS
+#undef TVL1_GAUSS_MARCH
     CKL(ctx);
     return TVL1_OK;
 }
