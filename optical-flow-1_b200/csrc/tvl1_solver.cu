@@ -1307,13 +1307,17 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
 
 // ---- RAII device scratch for the per-kernel hooks -----------------------------------------------
 struct Dev {
+    cudaStream_t st;
     std::vector<void *> ptrs;
-    ~Dev() { for (void *p : ptrs) cudaFree(p); }
+    explicit Dev(cudaStream_t s) : st(s) {}
+    ~Dev() { cudaStreamSynchronize(st); for (void *p : ptrs) cudaFree(p); }
     float *alloc(size_t floats)
     {
         void *p = nullptr;
         if (cudaMalloc(&p, std::max<size_t>(floats, 4) * sizeof(float)) != cudaSuccess) return nullptr;
-        cudaMemset(p, 0, std::max<size_t>(floats, 4) * sizeof(float));
+        // zero on the context's own (non-blocking) stream: a legacy-stream memset would not be ordered
+        // against the copies and kernels that follow
+        cudaMemsetAsync(p, 0, std::max<size_t>(floats, 4) * sizeof(float), st);
         ptrs.push_back(p);
         return (float *) p;
     }
@@ -1651,7 +1655,7 @@ int tvl1_normalize_f32(tvl1_ctx *ctx, const float *I0, const float *I1, float *I
 {
     if (!ctx || !I0 || !I1 || !I0n || !I1n || nx < 1 || ny < 1) return fail_arg(ctx, "bad argument");
     CK(cudaSetDevice(ctx->device));
-    Dev d;
+    Dev d(ctx->stream);
     const size_t n = (size_t) nx * ny;
     float *a = d.alloc(n), *b = d.alloc(n), *oa = d.alloc(n), *ob = d.alloc(n);
     unsigned int *mm = (unsigned int *) d.alloc(4);
@@ -1681,7 +1685,7 @@ int tvl1_gaussian_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny,
     CK(cudaSetDevice(ctx->device));
     GaussTaps taps;
     TRY(check_sigma(ctx, sigma, nx, taps));
-    Dev d;
+    Dev d(ctx->stream);
     const size_t n = (size_t) nx * ny;
     float *a = d.alloc(n), *o = d.alloc(n);
     if (!a || !o) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
@@ -1703,7 +1707,7 @@ int tvl1_zoom_out_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny,
     if (nxx < 1 || nyy < 1) return fail_arg(ctx, "zoomed image is empty");
     GaussTaps taps;
     TRY(check_sigma(ctx, TVL1_ZOOM_SIGMA_ZERO * std::sqrt(1.0 / (factor * factor) - 1.0), nx, taps));
-    Dev d;
+    Dev d(ctx->stream);
     const size_t n = (size_t) nx * ny, m = (size_t) nxx * nyy;
     float *a = d.alloc(n), *t = d.alloc(n), *o = d.alloc(m);
     if (!a || !t || !o) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
@@ -1727,7 +1731,7 @@ int tvl1_zoom_in_f32(tvl1_ctx *ctx, const float *I, float *out, int nx, int ny, 
 {
     if (!ctx || !I || !out || nx < 1 || ny < 1 || nxx < 1 || nyy < 1) return fail_arg(ctx, "bad argument");
     CK(cudaSetDevice(ctx->device));
-    Dev d;
+    Dev d(ctx->stream);
     const size_t n = (size_t) nx * ny, m = (size_t) nxx * nyy;
     float *a = d.alloc(n), *o = d.alloc(m);
     if (!a || !o) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
@@ -1752,7 +1756,7 @@ int tvl1_warp_f32(tvl1_ctx *ctx, const float *I0, const float *I1, const float *
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t) nx * ny;
-    Dev d;
+    Dev d(ctx->stream);
     float *buf = d.alloc(4 * n);
     if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     const float *src[4] = { I0, I1, u1, u2 };
@@ -1793,7 +1797,7 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t) nx * ny;
-    Dev d;
+    Dev d(ctx->stream);
     float *buf = d.alloc(n);
     if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
@@ -1858,7 +1862,7 @@ int tvl1_iterate_resident_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, f
     if (w.res_cluster[0] == 0) return fail_arg(ctx, "level does not fit the cluster-resident kernel with this cluster size");
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t) nx * ny;
-    Dev d;
+    Dev d(ctx->stream);
     float *buf = d.alloc(n);
     double *trace = (double *) d.alloc(2 * (size_t) max_iter);
     if (!buf || !trace) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
