@@ -43,10 +43,6 @@ struct PairCtl {
 struct LoopCtl {
     int active_pairs;     // pairs still iterating
     int max_n;            // largest iteration count among the pairs that already stopped
-    // work list of the streaming iteration kernel: list[parity] holds the pairs the next launch
-    // processes (n_list[parity] of them); pairs that go on are appended to list[parity ^ 1]
-    int parity;
-    int n_list[2];
 };
 
 struct GaussTaps {
@@ -516,12 +512,11 @@ __global__ void k_zero_fields(float *__restrict__ state, size_t plane0, size_t f
 
 // Row-band mode (one image split over several GPUs): after the all-reduce of the per-rank sums every
 // rank applies the stopping rule of src/tvl1flow.cpp:113,162 to the same number.
-__global__ void k_band_decide(PairCtl *ctl, LoopCtl *loop, int *list, int B, const double *band_sum, double npix,
-                              double eps2, int max_iter, int *stat_iters, double *stat_errs, int stat_slot,
+__global__ void k_band_decide(PairCtl *ctl, LoopCtl *loop, const double *band_sum, double npix, double eps2,
+                              int max_iter, int *stat_iters, double *stat_errs, int stat_slot,
                               unsigned long long *px_iters, unsigned long long own_pixels)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0 || !ctl->active) return;
-    const int nxt = loop->parity ^ 1;
     const double error = *band_sum / npix;
     const int n = ctl->n + 1;
     ctl->n = n;
@@ -534,14 +529,11 @@ __global__ void k_band_decide(PairCtl *ctl, LoopCtl *loop, int *list, int B, con
         stat_errs[stat_slot] = error;
         loop->max_n = n;
         loop->active_pairs = 0;
-    } else {
-        list[nxt * B] = 0;                 // the (single) pair goes on
-        loop->n_list[nxt] = 1;
     }
 }
 
 // start of a warp step: n = 0, error = INFINITY (src/tvl1flow.cpp:111-112)
-__global__ void k_begin_warp(PairCtl *ctl, LoopCtl *loop, int *list, int B)
+__global__ void k_begin_warp(PairCtl *ctl, LoopCtl *loop, int B)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) {
@@ -549,23 +541,8 @@ __global__ void k_begin_warp(PairCtl *ctl, LoopCtl *loop, int *list, int B)
         ctl[b].n = 0;
         ctl[b].arrive = 0u;
         ctl[b].err = INFINITY;
-        list[b] = b;                       // list[0] = every pair; k_iterate_advance makes it current
     }
-    if (b == 0) {
-        loop->active_pairs = B; loop->max_n = 0;
-        loop->parity = 1; loop->n_list[0] = B; loop->n_list[1] = 0;
-    }
-}
-
-// Runs between two launches of the streaming iteration kernel: the list the previous launch built
-// becomes the current one.  (A separate tiny launch, so that the kernel itself sees a frozen list.)
-__global__ void k_iterate_advance(LoopCtl *loop)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const int par = loop->parity ^ 1;
-        loop->parity = par;
-        loop->n_list[par ^ 1] = 0;
-    }
+    if (b == 0) { loop->active_pairs = B; loop->max_n = 0; }
 }
 
 __global__ void k_init_ctl(PairCtl *ctl, unsigned int *mm, int B)
@@ -901,8 +878,6 @@ struct IterParams {
     PairCtl *ctl;
     double *partials;            // [B][parts_per_pair]
     LoopCtl *loop;
-    int *list;                         // [2][batch] work lists of pair indices
-    int batch;
     cudaGraphConditionalHandle cond;   // while-node handle when launched from the solve graph, else 0
     int use_cond;
     int row_begin, row_end;            // rows this launch owns (whole image: 0, ny; a row band otherwise)
@@ -984,38 +959,25 @@ __device__ __forceinline__ void dual_px(float u1x, float u1y, float u2x, float u
 #define TVL1_F4_GET(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
 
 template <int R, int WY>
-__global__ void __launch_bounds__(32 * WY, 4)
+__global__ void __launch_bounds__(32 * WY)
 k_iterate_t1(const IterParams P)
 {
-    // Persistent CTAs: the grid is sized to the machine, and the (pair, tile) work items of the pairs
-    // that still iterate are dealt out round-robin, so a launch in which only a few pairs of the batch
-    // are left costs what those pairs cost.
-    __shared__ double s_part[32];
-    __shared__ int s_last;
+    const int b = blockIdx.z;
+    PairCtl *ctl = P.ctl + b;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && b == 0 && threadIdx.x == 0)
+        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
+    if (!ctl->active) return;                       // uniform for the whole CTA
+
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t fs = P.field_stride;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
-    const int par = P.loop->parity;
-    const int n_active = P.loop->n_list[par];
-    const int *work = P.list + par * P.batch;
-    const int tiles_x = (nx + 123) / 124;
-    const int tiles_y = (P.row_end - P.row_begin + R * WY - 1) / (R * WY);
-    const int nblk = tiles_x * tiles_y;
-    const long long n_items = (long long) n_active * nblk;
-
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int li = (int) (item / nblk), blk = (int) (item - (long long) li * nblk);
-    const int b = work[li];
-    const int tile_x = blk % tiles_x, tile_y = blk / tiles_x;
-    PairCtl *ctl = P.ctl + b;
     const int cur = ctl->cur;
     const float *sin = P.state + (size_t) cur * P.set_stride + (size_t) b * P.plane0;
     float *sout = P.state + (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0;
     const float *cst = P.consts + (size_t) b * P.plane0;
+    const size_t fs = P.field_stride;
 
-    const int x0 = tile_x * 124 + lane * 4;
-    const int ys = P.row_begin + (tile_y * WY + warp) * R;
+    const int x0 = blockIdx.x * 124 + lane * 4;
+    const int ys = P.row_begin + (blockIdx.y * WY + warp) * R;
     const int ye = min(ys + R, P.row_end);
     const bool in_alloc = x0 < pitch;               // float4 lies inside the row allocation
     const bool owner = in_alloc && lane < 31 && x0 < nx;
@@ -1148,10 +1110,13 @@ k_iterate_t1(const IterParams P)
     }
 
     // ---- error reduction: warp shuffle -> CTA -> fixed-order sum by the pair's last CTA ----
+    __shared__ double s_part[32];
+    __shared__ int s_last;
     double e = warp_sum((double) err);
-    __syncthreads();                                   // s_part / s_last of the previous item are free
     if (lane == 0) s_part[warp] = e;
     __syncthreads();
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < WY; w++) s += s_part[w];
@@ -1162,7 +1127,7 @@ k_iterate_t1(const IterParams P)
         s_last = (t == (unsigned int) nblk - 1u);
     }
     __syncthreads();
-    if (!s_last) continue;
+    if (!s_last) return;
 
     __threadfence();
     const volatile double *part = P.partials + (size_t) b * P.parts_per_pair;
@@ -1177,7 +1142,7 @@ k_iterate_t1(const IterParams P)
         if (P.band_sum) {            // row-band mode: the other ranks' rows are still missing
             *P.band_sum = tot;
             ctl->arrive = 0u;
-            continue;
+            return;
         }
         if (P.peers.enabled) {
             // All-to-all of the per-rank sums through the mailboxes.  This is the one
@@ -1219,12 +1184,8 @@ k_iterate_t1(const IterParams P)
             const int left = atomicSub(&P.loop->active_pairs, 1) - 1;
             // the last pair to stop ends the device-side while loop of the solve graph
             if (left == 0 && P.use_cond) cudaGraphSetConditional(P.cond, 0);
-        } else {
-            const int slot = atomicAdd(&P.loop->n_list[par ^ 1], 1);      // goes on: next launch's list
-            P.list[(par ^ 1) * P.batch + slot] = b;
         }
     }
-    }   // work items
 }
 
 

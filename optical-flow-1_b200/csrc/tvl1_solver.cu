@@ -43,7 +43,6 @@ struct Workspace {
     unsigned int *mm = nullptr;
     double *partials = nullptr;
     LoopCtl *loop = nullptr;
-    int *list = nullptr;                      // [2][B] work lists of the streaming iteration kernel
     int *stat_iters = nullptr;
     double *stat_errs = nullptr;
     unsigned long long *counters = nullptr;   // [level] pixel-iterations, [16 + level] iteration launches
@@ -192,7 +191,7 @@ void free_graph(SolveGraph &g, std::vector<cudaEvent_t> &pool)
 void free_workspace(Workspace &w)
 {
     cudaFree(w.pyr); cudaFree(w.state); cudaFree(w.consts); cudaFree(w.tmp); cudaFree(w.ctl);
-    cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.loop); cudaFree(w.list); cudaFree(w.stat_iters);
+    cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.loop); cudaFree(w.stat_iters);
     cudaFree(w.stat_errs); cudaFree(w.counters);
     w = Workspace();
 }
@@ -304,7 +303,6 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     CK(cudaMalloc(&w.mm, sizeof(unsigned int) * 2 * B));
     CK(cudaMalloc(&w.partials, sizeof(double) * (size_t) B * parts));
     CK(cudaMalloc(&w.loop, sizeof(LoopCtl)));
-    CK(cudaMalloc(&w.list, sizeof(int) * 2 * (size_t) B));
     CK(cudaMalloc(&w.stat_iters, sizeof(int) * (size_t) B * stat_stride));
     CK(cudaMalloc(&w.stat_errs, sizeof(double) * (size_t) B * stat_stride));
     CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS));
@@ -410,7 +408,7 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
     const Workspace &w = ctx->ws;
     IterParams P = {};
     P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
-    P.loop = w.loop; P.list = w.list; P.batch = w.B; P.cond = 0; P.use_cond = 0;
+    P.loop = w.loop; P.cond = 0; P.use_cond = 0;
     P.row_begin = 0; P.row_end = lv.ny; P.band_sum = nullptr;
     P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
     P.px_iters = w.counters;
@@ -427,24 +425,12 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
 
 int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
 {
-    // resident CTAs per SM of the two instantiations (queried once)
-    static int occ8 = 0, occ16 = 0;
-    if (!occ8) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, k_iterate_t1<kIterR, kIterWY>, 32 * kIterWY, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ16, k_iterate_t1<2 * kIterR, kIterWY>, 32 * kIterWY, 0);
-        occ8 = std::max(occ8, 1); occ16 = std::max(occ16, 1);
-    }
-    k_iterate_advance<<<1, 32, 0, ctx->stream>>>(P.loop);
-    CKL(ctx);
     const int rows = P.row_end - P.row_begin;
-    const int tiles_x = ceil_div(P.lv.nx, 124);
-    if (rows >= 512) {        // tall levels: longer strips, half the work items and half the halo rows
-        const long long items = (long long) tiles_x * ceil_div(rows, 2 * kIterR * kIterWY) * B;
-        const unsigned g = (unsigned) std::min<long long>(items, (long long) ctx->sm_count * occ16);
+    if (rows >= 512) {        // tall levels: longer strips, half the CTAs and half the halo rows
+        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(rows, 2 * kIterR * kIterWY), B);
         k_iterate_t1<2 * kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else {
-        const long long items = (long long) tiles_x * ceil_div(rows, kIterR * kIterWY) * B;
-        const unsigned g = (unsigned) std::min<long long>(items, (long long) ctx->sm_count * occ8);
+        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(rows, kIterR * kIterWY), B);
         k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
@@ -585,7 +571,7 @@ int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base
                                 prm.epsilon * prm.epsilon, nullptr));
             continue;
         }
-        k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.loop, w.list, B);   // :111-112
+        k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.loop, B);   // :111-112
         CKL(ctx);
         const IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations, s);
         TRY(run_iterations(ctx, P, B, chunk_hint));                         // :113-182
@@ -1123,7 +1109,7 @@ int band_level_p2p(tvl1_ctx *ctx, int s, const tvl1_params &prm, int stat_base, 
             Span sp(ctx, 1);
             TRY(launch_warp(ctx, s, 1, 0, r0, std::min(r1 + 1, l.ny)));   // + the halo row below
         }
-        k_begin_warp<<<1, 32, 0, ctx->stream>>>(w.ctl, w.loop, w.list, 1);
+        k_begin_warp<<<1, 32, 0, ctx->stream>>>(w.ctl, w.loop, 1);
         CKL(ctx);
         IterParams P = iter_params(ctx, l, prm, stat_base + wi, kMaxIterations, s);
         P.row_begin = r0; P.row_end = r1;
@@ -1189,7 +1175,7 @@ int band_level(tvl1_ctx *ctx, int s, const tvl1_params &prm, int stat_base, int 
             Span sp(ctx, 1);
             TRY(launch_warp(ctx, s, 1, 0, r0, std::min(r1 + 1, l.ny)));   // + the halo row below
         }
-        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.loop, w.list, 1);
+        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.loop, 1);
         CKL(ctx);
         IterParams P = iter_params(ctx, l, prm, stat_base + wi, kMaxIterations, s);
         P.row_begin = r0; P.row_end = r1; P.band_sum = ctx->d_band_sum;
@@ -1202,7 +1188,7 @@ int band_level(tvl1_ctx *ctx, int s, const tvl1_params &prm, int stat_base, int 
                     CK(cudaMemsetAsync(ctx->d_band_sum, 0, sizeof(double), st));
                     if (r1 > r0) TRY(launch_iterate(ctx, P, 1));
                     TRY(band_exchange(ctx, s, true));
-                    k_band_decide<<<1, 32, 0, st>>>(w.ctl, w.loop, w.list, w.B, ctx->d_band_sum, (double) l.nx * (double) l.ny,
+                    k_band_decide<<<1, 32, 0, st>>>(w.ctl, w.loop, ctx->d_band_sum, (double) l.nx * (double) l.ny,
                                                     P.eps2, P.max_iter, w.stat_iters, w.stat_errs, P.stat_slot,
                                                     w.counters + P.level,
                                                     (unsigned long long) l.nx * (unsigned long long) (r1 - r0));
@@ -1837,7 +1823,7 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
     prm.tau = tau; prm.lambda = lambda; prm.theta = theta; prm.epsilon = 0.0;
     int cur = 0;
     for (int k = 0; k < iters; k++) {
-        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.loop, w.list, 1);
+        k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.loop, 1);
         CKL(ctx);
         const IterParams P = iter_params(ctx, w.lv[0], prm, 0, 1);   // max_iter 1: record and stop
         TRY(launch_iterate(ctx, P, 1));
@@ -1929,7 +1915,7 @@ int tvl1_bench_iterate(tvl1_ctx *ctx, int npairs, int nx, int ny, int launches, 
     CKL(ctx);
     k_init_ctl<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.mm, npairs);
     CKL(ctx);
-    k_begin_warp<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.loop, w.list, npairs);
+    k_begin_warp<<<ceil_div(npairs, 128), 128, 0, st>>>(w.ctl, w.loop, npairs);
     CKL(ctx);
     tvl1_params prm;
     tvl1_default_params(&prm);
