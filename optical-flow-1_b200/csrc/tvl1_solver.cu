@@ -198,7 +198,7 @@ void free_workspace(Workspace &w)
 
 int iterate_parts(const Level &l)
 {
-    return ceil_div(l.nx, 124) * ceil_div(l.ny, kIterR * kIterWY);
+    return ceil_div(l.nx, 124) * ceil_div(l.ny, 4 * kIterWY);     // smallest strip height launch_iterate uses
 }
 
 // Smallest cluster (1,2,4,8,16 CTAs) whose row bands fit one SM each: <= 2048 float4 groups per CTA
@@ -425,13 +425,22 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
 
 int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
 {
+    // Strip height per warp: 16 rows (fewest CTAs, least halo traffic) when that still gives every SM
+    // a few CTAs, else 8, else 4 -- a single mid-size image is latency-bound on how many rows a warp
+    // walks, not on bytes.
     const int rows = P.row_end - P.row_begin;
-    if (rows >= 512) {        // tall levels: longer strips, half the CTAs and half the halo rows
-        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(rows, 2 * kIterR * kIterWY), B);
-        k_iterate_t1<2 * kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    const int tiles_x = ceil_div(P.lv.nx, 124);
+    const long long want = 4ll * ctx->sm_count;
+    auto ctas = [&](int R) { return (long long) tiles_x * ceil_div(rows, R * kIterWY) * B; };
+    if (ctas(16) >= want) {
+        dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), B);
+        k_iterate_t1<16, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    } else if (ctas(8) >= want) {
+        dim3 g(tiles_x, ceil_div(rows, 8 * kIterWY), B);
+        k_iterate_t1<8, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else {
-        dim3 g(ceil_div(P.lv.nx, 124), ceil_div(rows, kIterR * kIterWY), B);
-        k_iterate_t1<kIterR, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+        dim3 g(tiles_x, ceil_div(rows, 4 * kIterWY), B);
+        k_iterate_t1<4, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
     return TVL1_OK;
