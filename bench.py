@@ -308,6 +308,10 @@ def run_ours(args, rank, local_rank, world):
     }
     breakdown = {k: acc[k] / args.steps for k in ("total_ms", "iterate_ms", "warp_ms", "pyramid_ms",
                                                    "zoom_in_ms", "export_ms")}
+    # secondary kernels against the same roofline (canonical bytes of BASELINE.md section 3)
+    warp_gbs = 32 * acc["pixel_warps"] / (acc["warp_ms"] / 1e3) / 1e9 if acc["warp_ms"] > 0 else None
+    other = {"warp_precompute": {"algorithmic_bytes_per_pixel_warp": 32, "pixel_warps": acc["pixel_warps"],
+                                 "achieved_GBps": warp_gbs, "frac": warp_gbs / peak if warp_gbs else None}}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     solver.close()
@@ -367,6 +371,7 @@ def run_ours(args, rank, local_rank, world):
             "timer": {"device_ms_rank0": dev_ms, "wall_ms_rank0": wall_ms},
             "host_syncs_per_step": acc["host_syncs"] / args.steps,
             "device_ms_per_step_by_kernel_group": breakdown,
+            "other_kernels": other,
             "e2e_matches_device_path": same,
         }
         print(json.dumps(line))
