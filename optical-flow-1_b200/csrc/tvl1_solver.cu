@@ -122,6 +122,8 @@ struct tvl1_ctx {
     void *stage_out[2] = { nullptr, nullptr };
     float *stage_f32[4] = { nullptr, nullptr, nullptr, nullptr };
     size_t stage_bytes = 0, stage_f32_bytes = 0;
+    void *pipe_buf[2] = { nullptr, nullptr };      // pinned staging ring for pageable host buffers
+    cudaEvent_t pipe_ev[2] = { nullptr, nullptr };
     int sm_count = 148;
 };
 
@@ -830,6 +832,96 @@ int check_common(tvl1_ctx *ctx, const void *a, const void *b, const void *c, con
     return TVL1_OK;
 }
 
+// ---- pageable host memory <-> device through pinned staging ---------------------------------------
+// cudaMemcpyAsync from/to pageable memory is staged by the driver on one thread (6-12 GB/s here).  The
+// reference's callers hand us plain new[]/malloc buffers, fp64 at that, so the drop-in call was
+// dominated by those copies.  Instead: a few host threads copy (fp32) or convert (fp64 <-> fp32, halving
+// the PCIe bytes) slices into a double-buffered pinned ring while the previous slice is on the wire.
+constexpr size_t kPipeSlot = 8u << 20;      // bytes per pinned slot
+constexpr int kPipeThreads = 4;
+
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+template <class Fn>
+void parallel_slices(size_t n, Fn &&fn)
+{
+    const int nt = n >= (1u << 18) ? kPipeThreads : 1;
+    if (nt == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; t++) {
+        const size_t a = std::min(n, t * per), b = std::min(n, a + per);
+        if (b > a) th.emplace_back([&fn, a, b] { fn(a, b); });
+    }
+    fn(0, std::min(n, per));
+    for (auto &t : th) t.join();
+}
+
+int ensure_pipe(tvl1_ctx *ctx)
+{
+    for (int i = 0; i < 2; i++) {
+        if (!ctx->pipe_buf[i]) CK(cudaMallocHost(&ctx->pipe_buf[i], kPipeSlot));
+        if (!ctx->pipe_ev[i]) CK(cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+    }
+    return TVL1_OK;
+}
+
+// host (pageable, T) -> device fp32
+template <typename T>
+int upload_pageable(tvl1_ctx *ctx, float *dst, const T *src, size_t count)
+{
+    TRY(ensure_pipe(ctx));
+    const size_t per = kPipeSlot / sizeof(float);
+    int slot = 0;
+    for (size_t off = 0; off < count; off += per, slot ^= 1) {
+        const size_t n = std::min(per, count - off);
+        CK(cudaEventSynchronize(ctx->pipe_ev[slot]));         // the copy that last used this slot is done
+        float *pin = (float *) ctx->pipe_buf[slot];
+        const T *s = src + off;
+        parallel_slices(n, [pin, s](size_t a, size_t b) {
+            if (sizeof(T) == sizeof(float)) memcpy(pin + a, s + a, (b - a) * sizeof(float));
+            else for (size_t i = a; i < b; i++) pin[i] = (float) s[i];
+        });
+        CK(cudaMemcpyAsync(dst + off, pin, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->pipe_ev[slot], ctx->stream));
+    }
+    return TVL1_OK;
+}
+
+// device fp32 -> host (pageable, T); returns when the data is in `dst`
+template <typename T>
+int download_pageable(tvl1_ctx *ctx, T *dst, const float *src, size_t count)
+{
+    TRY(ensure_pipe(ctx));
+    const size_t per = kPipeSlot / sizeof(float);
+    size_t prev_off = 0, prev_n = 0;
+    int slot = 0;
+    auto drain = [&](int sl, size_t off, size_t n) -> int {
+        CK(cudaEventSynchronize(ctx->pipe_ev[sl]));
+        const float *pin = (const float *) ctx->pipe_buf[sl];
+        T *d = dst + off;
+        parallel_slices(n, [pin, d](size_t a, size_t b) {
+            if (sizeof(T) == sizeof(float)) memcpy(d + a, pin + a, (b - a) * sizeof(float));
+            else for (size_t i = a; i < b; i++) d[i] = (T) pin[i];
+        });
+        return TVL1_OK;
+    };
+    for (size_t off = 0; off < count; off += per, slot ^= 1) {
+        const size_t n = std::min(per, count - off);
+        CK(cudaMemcpyAsync(ctx->pipe_buf[slot], src + off, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->pipe_ev[slot], ctx->stream));
+        if (prev_n) TRY(drain(slot ^ 1, prev_off, prev_n));   // overlaps the copy just issued
+        prev_off = off; prev_n = n;
+    }
+    if (prev_n) TRY(drain(slot ^ 1, prev_off, prev_n));
+    return TVL1_OK;
+}
+
 // One chunk of <= max_batch pairs through one lane (context): H2D, solve, D2H, all on the lane's
 // stream.
 template <typename T>
@@ -840,42 +932,44 @@ int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1
     const size_t n = (size_t) nx * ny;
     cudaStream_t st = ctx->stream;
     const size_t cnt = (size_t) B * n, off = (size_t) first * n;
-    CK(cudaMemcpyAsync(ctx->stage_in[0], I0 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->stage_in[1], I1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-    float *d0, *d1, *o0, *o1;
     const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
-    if (f64) {
-        d0 = ctx->stage_f32[0]; d1 = ctx->stage_f32[1]; o0 = ctx->stage_f32[2]; o1 = ctx->stage_f32[3];
-        k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[0], d0, cnt);
-        CKL(ctx);
-        k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_in[1], d1, cnt);
-        CKL(ctx);
-    } else {
-        d0 = (float *) ctx->stage_in[0]; d1 = (float *) ctx->stage_in[1];
-        o0 = (float *) ctx->stage_out[0]; o1 = (float *) ctx->stage_out[1];
-    }
-    if (!multiscale) {   // u1,u2 are in/out: the initial flow is used (src/tvl1flow.cpp:94)
-        CK(cudaMemcpyAsync(ctx->stage_out[0], u1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->stage_out[1], u2 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+    // fp32 working buffers on the device
+    float *d0, *d1, *o0, *o1;
+    if (f64) { d0 = ctx->stage_f32[0]; d1 = ctx->stage_f32[1]; o0 = ctx->stage_f32[2]; o1 = ctx->stage_f32[3]; }
+    else { d0 = (float *) ctx->stage_in[0]; d1 = (float *) ctx->stage_in[1];
+           o0 = (float *) ctx->stage_out[0]; o1 = (float *) ctx->stage_out[1]; }
+    // host -> device: pinned buffers go straight over PCIe (fp64 is narrowed on the device), pageable
+    // buffers through the pinned staging ring (fp64 is narrowed on the host)
+    auto put = [&](const T *h, void *dev_T, float *dev_f32) -> int {
+        if (is_pageable(h)) return upload_pageable<T>(ctx, dev_f32, h, cnt);
+        CK(cudaMemcpyAsync(dev_T, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
         if (f64) {
-            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[0], o0, cnt);
-            CKL(ctx);
-            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) ctx->stage_out[1], o1, cnt);
+            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) dev_T, dev_f32, cnt);
             CKL(ctx);
         }
+        return TVL1_OK;
+    };
+    TRY(put(I0 + off, ctx->stage_in[0], d0));
+    TRY(put(I1 + off, ctx->stage_in[1], d1));
+    if (!multiscale) {   // u1,u2 are in/out: the initial flow is used (src/tvl1flow.cpp:94)
+        TRY(put(u1 + off, ctx->stage_out[0], o0));
+        TRY(put(u2 + off, ctx->stage_out[1], o1));
     }
     int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
     double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
     if (multiscale) TRY(run_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
     else TRY(run_single_scale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
-    if (f64) {
-        k_f32_to_f64<<<g, 256, 0, st>>>(o0, (double *) ctx->stage_out[0], cnt);
-        CKL(ctx);
-        k_f32_to_f64<<<g, 256, 0, st>>>(o1, (double *) ctx->stage_out[1], cnt);
-        CKL(ctx);
-    }
-    CK(cudaMemcpyAsync(u1 + off, ctx->stage_out[0], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(u2 + off, ctx->stage_out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+    auto get = [&](T *h, void *dev_T, const float *dev_f32) -> int {
+        if (is_pageable(h)) return download_pageable<T>(ctx, h, dev_f32, cnt);
+        if (f64) {
+            k_f32_to_f64<<<g, 256, 0, st>>>(dev_f32, (double *) dev_T, cnt);
+            CKL(ctx);
+        }
+        CK(cudaMemcpyAsync(h, f64 ? dev_T : (void *) dev_f32, cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+        return TVL1_OK;
+    };
+    TRY(get(u1 + off, ctx->stage_out[0], o0));
+    TRY(get(u2 + off, ctx->stage_out[1], o1));
     CK(sleep_until_done(ctx));
     return TVL1_OK;
 }
@@ -1404,6 +1498,10 @@ void tvl1_destroy(tvl1_ctx *ctx)
     for (int i = 0; i < 4; i++) cudaFree(ctx->stage_f32[i]);
     resolve_events(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->pipe_buf[i]) cudaFreeHost(ctx->pipe_buf[i]);
+        if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
+    }
     if (ctx->h_loop) cudaFreeHost(ctx->h_loop);
     if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->body_stream) cudaStreamDestroy(ctx->body_stream);
@@ -1603,13 +1701,19 @@ static int band_solve_host_impl(tvl1_ctx *ctx, const float *I0, const float *I1,
     const size_t n = (size_t) nx * ny;
     TRY(ensure_stage(ctx, n * sizeof(float), false));
     cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->stage_in[0], I0, n * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->stage_in[1], I1, n * 4, cudaMemcpyHostToDevice, st));
+    const float *in[2] = { I0, I1 };
+    for (int k = 0; k < 2; k++) {
+        if (is_pageable(in[k])) TRY(upload_pageable<float>(ctx, (float *) ctx->stage_in[k], in[k], n));
+        else CK(cudaMemcpyAsync(ctx->stage_in[k], in[k], n * 4, cudaMemcpyHostToDevice, st));
+    }
     TRY(run_band(ctx, (const float *) ctx->stage_in[0], (const float *) ctx->stage_in[1],
                  (float *) ctx->stage_out[0], (float *) ctx->stage_out[1], nx, ny, *prm, min_split_rows,
                  iters_out, errs_out));
-    CK(cudaMemcpyAsync(u1, ctx->stage_out[0], n * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(u2, ctx->stage_out[1], n * 4, cudaMemcpyDeviceToHost, st));
+    float *outp[2] = { u1, u2 };
+    for (int k = 0; k < 2; k++) {
+        if (is_pageable(outp[k])) TRY(download_pageable<float>(ctx, outp[k], (const float *) ctx->stage_out[k], n));
+        else CK(cudaMemcpyAsync(outp[k], ctx->stage_out[k], n * 4, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     resolve_events(ctx);
     return TVL1_OK;
