@@ -840,6 +840,14 @@ int check_common(tvl1_ctx *ctx, const void *a, const void *b, const void *c, con
 constexpr size_t kPipeSlot = 8u << 20;      // bytes per pinned slot
 constexpr int kPipeThreads = 4;
 
+// The ring pays off when it halves the bytes (fp64 callers) or for very large planes; small fp32
+// transfers stay on the driver's own staged copy (thread start-up would cost more than it saves).
+template <typename T>
+bool use_ring(size_t count)
+{
+    return sizeof(T) == 8 ? count >= (1u << 18) : count * sizeof(float) >= (64u << 20);
+}
+
 bool is_pageable(const void *p)
 {
     cudaPointerAttributes a;
@@ -941,7 +949,7 @@ int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1
     // host -> device: pinned buffers go straight over PCIe (fp64 is narrowed on the device), pageable
     // buffers through the pinned staging ring (fp64 is narrowed on the host)
     auto put = [&](const T *h, void *dev_T, float *dev_f32) -> int {
-        if (is_pageable(h)) return upload_pageable<T>(ctx, dev_f32, h, cnt);
+        if (use_ring<T>(cnt) && is_pageable(h)) return upload_pageable<T>(ctx, dev_f32, h, cnt);
         CK(cudaMemcpyAsync(dev_T, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
         if (f64) {
             k_f64_to_f32<<<g, 256, 0, st>>>((const double *) dev_T, dev_f32, cnt);
@@ -960,7 +968,7 @@ int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1
     if (multiscale) TRY(run_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
     else TRY(run_single_scale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
     auto get = [&](T *h, void *dev_T, const float *dev_f32) -> int {
-        if (is_pageable(h)) return download_pageable<T>(ctx, h, dev_f32, cnt);
+        if (use_ring<T>(cnt) && is_pageable(h)) return download_pageable<T>(ctx, h, dev_f32, cnt);
         if (f64) {
             k_f32_to_f64<<<g, 256, 0, st>>>(dev_f32, (double *) dev_T, cnt);
             CKL(ctx);
@@ -1703,7 +1711,7 @@ static int band_solve_host_impl(tvl1_ctx *ctx, const float *I0, const float *I1,
     cudaStream_t st = ctx->stream;
     const float *in[2] = { I0, I1 };
     for (int k = 0; k < 2; k++) {
-        if (is_pageable(in[k])) TRY(upload_pageable<float>(ctx, (float *) ctx->stage_in[k], in[k], n));
+        if (use_ring<float>(n) && is_pageable(in[k])) TRY(upload_pageable<float>(ctx, (float *) ctx->stage_in[k], in[k], n));
         else CK(cudaMemcpyAsync(ctx->stage_in[k], in[k], n * 4, cudaMemcpyHostToDevice, st));
     }
     TRY(run_band(ctx, (const float *) ctx->stage_in[0], (const float *) ctx->stage_in[1],
@@ -1711,7 +1719,7 @@ static int band_solve_host_impl(tvl1_ctx *ctx, const float *I0, const float *I1,
                  iters_out, errs_out));
     float *outp[2] = { u1, u2 };
     for (int k = 0; k < 2; k++) {
-        if (is_pageable(outp[k])) TRY(download_pageable<float>(ctx, outp[k], (const float *) ctx->stage_out[k], n));
+        if (use_ring<float>(n) && is_pageable(outp[k])) TRY(download_pageable<float>(ctx, outp[k], (const float *) ctx->stage_out[k], n));
         else CK(cudaMemcpyAsync(outp[k], ctx->stage_out[k], n * 4, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
