@@ -845,7 +845,7 @@ constexpr int kPipeThreads = 4;
 template <typename T>
 bool use_ring(size_t count)
 {
-    return sizeof(T) == 8 ? count >= (1u << 18) : count * sizeof(float) >= (64u << 20);
+    return sizeof(T) == 8 ? count >= (1u << 18) : count * sizeof(float) >= (24u << 20);
 }
 
 bool is_pageable(const void *p)
