@@ -34,7 +34,7 @@ int main(void)
     m1 /= (double) (nx - 32) * (ny - 32);
     m2 /= (double) (nx - 32) * (ny - 32);
     printf("mean flow (%.3f, %.3f), first-warp iterations %d\n", m1, m2, iters[0]);
-    p.nscales = 5;                                    /* level 3 is 12 px wide: narrower than the blur window */
+    p.nscales = 7;                                    /* level 5 is 3 px wide: narrower than the 6-tap zoom window */
     rc = tvl1_solve_f32(ctx, I0, I1, u1, u2, nx, ny, &p, NULL, NULL);
     if (rc != TVL1_ERR_SIGMA) { printf("expected TVL1_ERR_SIGMA, got %d\n", rc); return 1; }
     tvl1_destroy(ctx);
