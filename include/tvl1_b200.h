@@ -180,6 +180,17 @@ int tvl1_iterate_resident_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, f
                               int max_iter, int cluster, int *iters_out, double *errs_out,
                               int *cluster_out);
 
+/* The complete while loop of one warp step (src/tvl1flow.cpp:111-182) through the streaming kernels,
+ * driven from the host: temporal_blocking = 0 uses k_iterate_t1 only (one iteration per launch),
+ * 1 lets the device choose between k_iterate_t1 and the TMA-tiled k_iterate_tb (up to 4 iterations
+ * per launch, exact replay when a block overshoots the stopping point), 2 additionally starts with a
+ * full block.  epsilon < 0: run exactly max_iter iterations.  Outputs: iterations done, error of the
+ * last one, kernel launches (while-loop turns) it took. */
+int tvl1_iterate_loop_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12, float *p21,
+                          float *p22, const float *rho_c, const float *I1wx, const float *I1wy, int nx,
+                          int ny, double tau, double lambda, double theta, double epsilon, int max_iter,
+                          int temporal_blocking, int *iters_out, double *err_out, int *launches_out);
+
 /* -- bench hook: the fused iteration kernel alone on synthetic device-resident state -------- */
 /* Runs `launches` iteration launches over `npairs` pairs of nx*ny (state and constants are
  * seeded pseudo-random, resident in HBM) and returns the CUDA-event time of those launches. */

@@ -11,6 +11,7 @@
 //     {u1,u2,p11,p12,p21,p22}.  PairCtl[b].cur names the live set of pair b.
 //   * per-warp constants: consts[field][b][plane0], field in {I1wx, I1wy, rho_c, grad}.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <limits.h>
@@ -21,6 +22,7 @@ namespace tvl1 {
 constexpr int kMaxIterations = 300;       // src/tvl1flow.cpp:22
 constexpr float kGradIsZero = 1e-10f;     // src/tvl1flow.cpp:24
 constexpr int kStatLevels = 16;           // == TVL1_MAX_LEVELS
+constexpr int kTbT = 4;                   // iterations per launch of the temporally blocked kernel
 constexpr int kMaxTaps = 16;              // (int)(5*sigma)+1 <= 16  <=>  sigma < 3.2 (zfactor > 0.19)
 
 enum Field { F_U1 = 0, F_U2, F_P11, F_P12, F_P21, F_P22, F_COUNT };
@@ -37,6 +39,10 @@ struct PairCtl {
     int n;                // iterations done in the current warp step
     unsigned int arrive;  // CTA arrival counter (last-block election)
     double err;           // mean squared update of the last iteration
+    // temporal blocking (k_iterate_tb): iterations the next launch runs for this pair, and whether
+    // that launch is the exact replay of a block that overshot the stopping point
+    int nsteps;
+    int replay;
 };
 
 // Whole-batch loop state of the current warp step.
@@ -537,6 +543,11 @@ __global__ void k_begin_warp(PairCtl *ctl, LoopCtl *loop, int B)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) {
+        // first block of the warp step: as many iterations as the previous warp step of this pair
+        // suggests (it rarely needs more than its predecessor), 1 when that one stopped at once
+        const int n_old = ctl[b].n;
+        ctl[b].nsteps = n_old >= 2 * kTbT ? kTbT : (n_old >= 4 ? 2 : 1);
+        ctl[b].replay = 0;
         ctl[b].active = 1;
         ctl[b].n = 0;
         ctl[b].arrive = 0u;
@@ -550,6 +561,7 @@ __global__ void k_init_ctl(PairCtl *ctl, unsigned int *mm, int B)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) {
         ctl[b].cur = 0; ctl[b].active = 0; ctl[b].n = 0; ctl[b].arrive = 0u; ctl[b].err = 0.0;
+        ctl[b].nsteps = 1; ctl[b].replay = 0;
         mm[2 * b] = 0xffffffffu;
         mm[2 * b + 1] = 0u;
     }
@@ -880,6 +892,11 @@ struct IterParams {
     LoopCtl *loop;
     cudaGraphConditionalHandle cond;   // while-node handle when launched from the solve graph, else 0
     int use_cond;
+    double *tb_partials;               // [batch][tb_parts][kTbT] per-CTA error sums of k_iterate_tb
+    int tb_parts;
+    int batch;                         // pairs in the lock-step batch (plane index = field * batch + pair)
+    int tb;                            // 1: pairs whose next block has more than one iteration belong
+                                       // to k_iterate_tb; this kernel only takes the nsteps == 1 pairs
     int row_begin, row_end;            // rows this launch owns (whole image: 0, ny; a row band otherwise)
     double *band_sum;                  // row-band mode: the rank's raw sum of squared updates goes here
                                        // and k_band_decide applies the stopping rule after the all-reduce
@@ -896,6 +913,63 @@ struct IterParams {
     float l_t, theta, taut;
     double eps2;
 };
+
+// Stopping rule for a block of `ns` iterations of pair b that started at state set `cur`
+// (src/tvl1flow.cpp:113: stop after the first iteration whose mean squared update is <= eps^2, or at
+// the cap).  errs[t] = mean squared update of the block's iteration t.  With ns == 1 this is the plain
+// rule.  With ns > 1 (temporal blocking) the block may overshoot the stopping point; then nothing
+// is accepted -- the ping-pong set that still holds the block's start state stays current -- and the
+// pair is marked for an exact replay of t+1 iterations, after which it stops.  Otherwise the number
+// of iterations of the next block is predicted from the geometric decay of the error.
+__device__ __forceinline__ void decide_block(const IterParams &P, PairCtl *ctl, int b, int cur, int ns,
+                                             const double *errs, unsigned long long own_pixels)
+{
+    const int n0 = ctl->n;
+    int stop_at = -1;
+    if (ctl->replay) {
+        stop_at = ns - 1;                                   // the replay was sized to stop exactly here
+    } else {
+        for (int t = 0; t < ns; t++)
+            if (!(errs[t] > P.eps2 && n0 + t + 1 < P.max_iter)) { stop_at = t; break; }
+    }
+    ctl->arrive = 0u;
+    if (stop_at >= 0 && stop_at < ns - 1) {                 // overshoot: replay exactly stop_at+1 iterations
+        ctl->nsteps = stop_at + 1;
+        ctl->replay = 1;
+        return;
+    }
+    const double last = errs[ns - 1];
+    const double prev = ns >= 2 ? errs[ns - 2] : ctl->err;
+    const int n = n0 + ns;
+    ctl->n = n;
+    ctl->err = last;
+    ctl->cur = cur ^ 1;
+    ctl->replay = 0;
+    atomicAdd(P.px_iters + P.level, (unsigned long long) ns * own_pixels);
+    if (stop_at == ns - 1) {
+        ctl->active = 0;
+        ctl->nsteps = 1;
+        P.stat_iters[(size_t) b * P.stat_stride + P.stat_slot] = n;
+        P.stat_errs[(size_t) b * P.stat_stride + P.stat_slot] = last;
+        atomicMax(&P.loop->max_n, n);
+        const int left = atomicSub(&P.loop->active_pairs, 1) - 1;
+        // the last pair to stop ends the device-side while loop of the solve graph
+        if (left == 0 && P.use_cond) cudaGraphSetConditional(P.cond, 0);
+        return;
+    }
+    int next = 1;
+    if (P.tb) {
+        next = kTbT;
+        if (prev < INFINITY && last < prev && last > P.eps2) {
+            // error ~ last * r^k: iterations until it is below eps^2 (the decay usually slows down, so
+            // this under-estimates and a replay stays rare); keep one in hand
+            const double k = log(P.eps2 / last) / log(last / prev);
+            if (k < (double) (kTbT + 1)) next = max(1, (int) k - 1);
+        }
+        next = max(1, min(next, P.max_iter - n));
+    }
+    ctl->nsteps = next;
+}
 
 struct Row4 {                    // one image row segment of 4 pixels, everything the update needs
     float4 u1, u2, ix, iy, rho, p11, p12, p21, p22;      // |grad|^2 is recomputed from ix, iy (grad_of)
@@ -967,6 +1041,7 @@ k_iterate_t1(const IterParams P)
     if (blockIdx.x == 0 && blockIdx.y == 0 && b == 0 && threadIdx.x == 0)
         atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
     if (!ctl->active) return;                       // uniform for the whole CTA
+    if (P.tb && ctl->nsteps > 1) return;            // this pair's next block belongs to k_iterate_tb
 
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1170,24 +1245,10 @@ k_iterate_t1(const IterParams P)
             tot = all;
         }
         const double error = tot / ((double) nx * (double) ny);   // src/tvl1flow.cpp:162
-        const int n = ctl->n + 1;
-        ctl->n = n;
-        ctl->err = error;
-        ctl->cur = cur ^ 1;
-        ctl->arrive = 0u;
-        atomicAdd(P.px_iters + P.level, (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
-        if (!(error > P.eps2 && n < P.max_iter)) {                // src/tvl1flow.cpp:113
-            ctl->active = 0;
-            P.stat_iters[(size_t) b * P.stat_stride + P.stat_slot] = n;
-            P.stat_errs[(size_t) b * P.stat_stride + P.stat_slot] = error;
-            atomicMax(&P.loop->max_n, n);
-            const int left = atomicSub(&P.loop->active_pairs, 1) - 1;
-            // the last pair to stop ends the device-side while loop of the solve graph
-            if (left == 0 && P.use_cond) cudaGraphSetConditional(P.cond, 0);
-        }
+        decide_block(P, ctl, b, cur, 1, &error,
+                     (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // (c') cluster-resident iteration kernel: the whole while loop of one warp step on chip
@@ -1477,6 +1538,233 @@ k_iterate_resident(const ResParams P)
             if (b == 0) atomicAdd(P.counters + kStatLevels + P.level, 1ull);
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// (c'') temporally blocked streaming kernel: up to kTbT iterations per launch on 2-D TMA halo tiles
+// ------------------------------------------------------------------------------------------------
+//
+// For levels too large to stay on chip.  A CTA owns a 56x24 tile; one elected thread pulls the 64x32
+// box around it (halo kTbT on every side) of the six evolving planes and the three constant planes
+// into shared memory with nine `cp.async.bulk.tensor.3d` copies on one mbarrier (out-of-image parts
+// arrive as zeros, which is exactly the p[-1] = 0 rule of src/operators.cpp:35-78); then the CTA runs
+// `nsteps` (<= kTbT) complete iterations of src/tvl1flow.cpp:114-181 in place in shared memory -- the
+// region that is still exact shrinks by one pixel per side per iteration and ends at the owned tile
+// -- and writes the tile back with float4 stores.  HBM traffic per iteration: (9*1.52 + 6)/nsteps
+// planes instead of 15.  The error of every one of the nsteps iterations is reduced separately
+// (owned pixels only), so the last CTA of the pair can apply the stopping rule to each of them and
+// order an exact replay when the block overshot (decide_block).
+constexpr int kTbBW = 64, kTbBH = 32;                                  // box
+constexpr int kTbW = kTbBW - 2 * kTbT, kTbH = kTbBH - 2 * kTbT;        // owned tile: 56 x 24
+constexpr int kTbThreads = 256;
+constexpr int kTbPlane = kTbBW * kTbBH;
+constexpr int kTbPlanes = 9;
+constexpr size_t kTbSmemBytes = (size_t) kTbPlanes * kTbPlane * sizeof(float);
+
+struct TbMaps {
+    CUtensorMap state[2];      // dims (nx, ny, 6*B) of ping-pong set 0 / 1
+    CUtensorMap consts;        // dims (nx, ny, 4*B)
+};
+
+__device__ __forceinline__ void tma_load_3d(float *dst, const CUtensorMap *map, int x, int y, int z,
+                                            unsigned long long *mbar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z),
+                    "r"(smem_u32(mbar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kTbThreads, 2)
+k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
+{
+    extern __shared__ __align__(128) float tb_smem[];
+    __shared__ double s_err[kTbT][kTbThreads / 32];
+    __shared__ double s_tot[kTbT];
+    __shared__ unsigned long long mbar;
+    __shared__ int s_last;
+
+    const int b = blockIdx.z;
+    PairCtl *ctl = P.ctl + b;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && b == 0 && threadIdx.x == 0)
+        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
+    if (!ctl->active || ctl->nsteps <= 1) return;           // nsteps == 1 pairs belong to k_iterate_t1
+    const int ns = min(ctl->nsteps, kTbT);
+    const int cur = ctl->cur;
+    const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * kTbW - kTbT, Y0 = blockIdx.y * kTbH - kTbT;
+
+    float *sU1 = tb_smem, *sU2 = sU1 + kTbPlane, *sP11 = sU2 + kTbPlane, *sP12 = sP11 + kTbPlane,
+          *sP21 = sP12 + kTbPlane, *sP22 = sP21 + kTbPlane, *sIx = sP22 + kTbPlane, *sIy = sIx + kTbPlane,
+          *sRho = sIy + kTbPlane;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     :: "r"(smem_u32(&mbar)), "r"((unsigned int) kTbSmemBytes) : "memory");
+        const CUtensorMap *ms = &maps.state[cur];
+#pragma unroll
+        for (int f = 0; f < F_COUNT; f++)                   // smem plane order == enum Field
+            tma_load_3d(tb_smem + f * kTbPlane, ms, X0, Y0, f * P.batch + b, &mbar);
+        tma_load_3d(sIx, &maps.consts, X0, Y0, C_IX * P.batch + b, &mbar);
+        tma_load_3d(sIy, &maps.consts, X0, Y0, C_IY * P.batch + b, &mbar);
+        tma_load_3d(sRho, &maps.consts, X0, Y0, C_RHO * P.batch + b, &mbar);
+    }
+    {
+        unsigned int done = 0;
+        const long long t0 = clock64();
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+            if (!done && clock64() - t0 > (1ll << 31)) break;   // a bad descriptor must not hang the GPU
+        }
+    }
+
+    const int qx = tid & 15, ry = tid >> 4;                  // two groups of 4 pixels: rows ry and ry+16
+    const int bx0 = qx * 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int t = 0; t < ns; t++) {
+        // ---- phase A: thresholding, divergence, primal update, error ----------------------------
+        float errp = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int by = ry + 16 * k, o = by * kTbBW + bx0;
+            const int gy = Y0 + by;
+            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
+            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
+            const float4 p12 = lds4(sP12 + o), p22 = lds4(sP22 + o);
+            const float4 a12 = by > 0 ? lds4(sP12 + o - kTbBW) : zero4;
+            const float4 a22 = by > 0 ? lds4(sP22 + o - kTbBW) : zero4;
+            const float4 ix = lds4(sIx + o), iy = lds4(sIy + o), rc = lds4(sRho + o);
+            float l11 = __shfl_up_sync(0xffffffffu, p11.w, 1);
+            float l21 = __shfl_up_sync(0xffffffffu, p21.w, 1);
+            if (qx == 0) { l11 = 0.f; l21 = 0.f; }
+            const bool last_row = (gy == ny - 1);
+            const bool row_in = gy >= 0 && gy < ny;
+            const bool row_owned = by >= kTbT && by < kTbT + kTbH;
+            float o1[4], o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int gx = X0 + bx0 + e;
+                const bool in_img = row_in && gx >= 0 && gx < nx;
+                const bool last_col = gx >= nx - 1;
+                const float a = TVL1_F4_GET(u1, e), c = TVL1_F4_GET(u2, e);
+                const float gxv = TVL1_F4_GET(ix, e), gyv = TVL1_F4_GET(iy, e);
+                primal_px(a, c, gxv, gyv, TVL1_F4_GET(rc, e), grad_of(gxv, gyv),
+                          last_col ? 0.f : TVL1_F4_GET(p11, e), (e == 0) ? l11 : TVL1_F4_GET(p11, (e + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(p12, e), TVL1_F4_GET(a12, e),
+                          last_col ? 0.f : TVL1_F4_GET(p21, e), (e == 0) ? l21 : TVL1_F4_GET(p21, (e + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(p22, e), TVL1_F4_GET(a22, e),
+                          P.l_t, P.theta, o1[e], o2[e]);
+                if (!in_img) { o1[e] = a; o2[e] = c; }
+                const float e1 = o1[e] - a, e2 = o2[e] - c;
+                const bool owned = row_owned && in_img && bx0 + e >= kTbT && bx0 + e < kTbT + kTbW;
+                errp += owned ? (e1 * e1 + e2 * e2) : 0.f;
+            }
+            st4(sU1 + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
+            st4(sU2 + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        }
+        {
+            const double e = warp_sum((double) errp);
+            if (lane == 0) s_err[t][warp] = e;
+        }
+        __syncthreads();
+        // ---- phase B: forward gradient of u_new, dual update --------------------------------------
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int by = ry + 16 * k, o = by * kTbBW + bx0;
+            const int gy = Y0 + by;
+            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
+            const float4 b1 = by + 1 < kTbBH ? lds4(sU1 + o + kTbBW) : zero4;
+            const float4 b2 = by + 1 < kTbBH ? lds4(sU2 + o + kTbBW) : zero4;
+            float r1 = __shfl_down_sync(0xffffffffu, u1.x, 1);
+            float r2 = __shfl_down_sync(0xffffffffu, u2.x, 1);
+            if (qx == 15) { r1 = 0.f; r2 = 0.f; }
+            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
+            const float4 p12 = lds4(sP12 + o), p22 = lds4(sP22 + o);
+            const bool has_below = gy + 1 < ny;
+            const bool row_in = gy >= 0 && gy < ny;
+            float q11[4], q12[4], q21[4], q22[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int gx = X0 + bx0 + e;
+                const bool in_img = row_in && gx >= 0 && gx < nx;
+                const bool last_col = gx >= nx - 1;
+                const float c1 = TVL1_F4_GET(u1, e), c2 = TVL1_F4_GET(u2, e);
+                const float e1 = (e == 3) ? r1 : TVL1_F4_GET(u1, (e + 1) & 3);
+                const float e2 = (e == 3) ? r2 : TVL1_F4_GET(u2, (e + 1) & 3);
+                q11[e] = TVL1_F4_GET(p11, e); q12[e] = TVL1_F4_GET(p12, e);
+                q21[e] = TVL1_F4_GET(p21, e); q22[e] = TVL1_F4_GET(p22, e);
+                dual_px(last_col ? 0.f : e1 - c1, has_below ? TVL1_F4_GET(b1, e) - c1 : 0.f,
+                        last_col ? 0.f : e2 - c2, has_below ? TVL1_F4_GET(b2, e) - c2 : 0.f,
+                        P.taut, q11[e], q12[e], q21[e], q22[e]);
+                if (!in_img) { q11[e] = q12[e] = q21[e] = q22[e] = 0.f; }   // outside the image p stays 0
+            }
+            st4(sP11 + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
+            st4(sP12 + o, make_float4(q12[0], q12[1], q12[2], q12[3]));
+            st4(sP21 + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
+            st4(sP22 + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
+        }
+        __syncthreads();
+    }
+
+    // ---- write the owned tile to the other ping-pong set ------------------------------------------
+    {
+        float *gout = P.state + (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0;
+        const size_t fs = P.field_stride;
+        for (int idx = tid; idx < (kTbW / 4) * kTbH; idx += kTbThreads) {
+            const int row = idx / (kTbW / 4), q = idx - row * (kTbW / 4);
+            const int by = kTbT + row, bx = kTbT + 4 * q;
+            const int gy = Y0 + by, gx = X0 + bx;
+            if (gy >= ny || gx >= nx) continue;
+            const int so = by * kTbBW + bx;
+            const size_t go = (size_t) gy * pitch + gx;
+#pragma unroll
+            for (int f = 0; f < F_COUNT; f++) st4(gout + f * fs + go, lds4(tb_smem + f * kTbPlane + so));
+        }
+    }
+
+    // ---- per-iteration error sums: CTA -> fixed-order sum by the pair's last CTA -------------------
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    double *part = P.tb_partials + ((size_t) b * P.tb_parts) * kTbT;
+    if (tid == 0) {
+        for (int t = 0; t < ns; t++) {
+            double s = 0.0;
+            for (int w = 0; w < kTbThreads / 32; w++) s += s_err[t][w];
+            part[(size_t) blk * kTbT + t] = s;
+        }
+        __threadfence();
+        const unsigned int tk = atomicAdd(&ctl->arrive, 1u);
+        s_last = (tk == (unsigned int) nblk - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile double *vp = part;
+    for (int t = 0; t < ns; t++) {
+        double s = 0.0;
+        for (int i = tid; i < nblk; i += kTbThreads) s += vp[(size_t) i * kTbT + t];
+        s = warp_sum(s);
+        __syncthreads();
+        if (lane == 0) s_err[0][warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < kTbThreads / 32; w++) tot += s_err[0][w];
+            s_tot[t] = tot / ((double) nx * (double) ny);
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+        decide_block(P, ctl, b, cur, ns, s_tot, (unsigned long long) nx * (unsigned long long) ny);
 }
 
 } // namespace tvl1

@@ -42,6 +42,8 @@ struct Workspace {
     PairCtl *ctl = nullptr;
     unsigned int *mm = nullptr;
     double *partials = nullptr;
+    double *tb_partials = nullptr;            // [B][tb_parts][kTbT] (temporally blocked kernel)
+    int tb_parts = 0;
     LoopCtl *loop = nullptr;
     int *stat_iters = nullptr;
     double *stat_errs = nullptr;
@@ -91,6 +93,8 @@ struct tvl1_ctx {
     cudaStream_t body_stream = nullptr;      // capture stream for while-node bodies
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
+    bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
+    long long tb_max_pixels = 40ll << 20;    // ... which serves lock-step batches up to this many pixels per level
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
     SolveGraph sg;
@@ -193,7 +197,7 @@ void free_graph(SolveGraph &g, std::vector<cudaEvent_t> &pool)
 void free_workspace(Workspace &w)
 {
     cudaFree(w.pyr); cudaFree(w.state); cudaFree(w.consts); cudaFree(w.tmp); cudaFree(w.ctl);
-    cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.loop); cudaFree(w.stat_iters);
+    cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.loop); cudaFree(w.tb_partials); cudaFree(w.stat_iters);
     cudaFree(w.stat_errs); cudaFree(w.counters);
     w = Workspace();
 }
@@ -289,6 +293,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
         w.pyr_off[s] = off;
         off += 2 * (size_t) B * w.plane(s);
         parts = std::max(parts, iterate_parts(w.lv[s]));
+        w.tb_parts = std::max(w.tb_parts, ceil_div(cx, kTbW) * ceil_div(cy, kTbH));
         w.res_cluster[s] = pick_cluster(ctx, w.lv[s], B, &w.res_rows[s]);
     }
     // row-band mode gathers equal-sized bands in place: round the rows of a plane up to a multiple of the rank count
@@ -304,6 +309,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     CK(cudaMalloc(&w.ctl, sizeof(PairCtl) * B));
     CK(cudaMalloc(&w.mm, sizeof(unsigned int) * 2 * B));
     CK(cudaMalloc(&w.partials, sizeof(double) * (size_t) B * parts));
+    CK(cudaMalloc(&w.tb_partials, sizeof(double) * (size_t) B * w.tb_parts * kTbT));
     CK(cudaMalloc(&w.loop, sizeof(LoopCtl)));
     CK(cudaMalloc(&w.stat_iters, sizeof(int) * (size_t) B * stat_stride));
     CK(cudaMalloc(&w.stat_errs, sizeof(double) * (size_t) B * stat_stride));
@@ -411,6 +417,7 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
     IterParams P = {};
     P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
     P.loop = w.loop; P.cond = 0; P.use_cond = 0;
+    P.batch = w.B; P.tb_partials = w.tb_partials; P.tb_parts = w.tb_parts; P.tb = 0;
     P.row_begin = 0; P.row_end = lv.ny; P.band_sum = nullptr;
     P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
     P.px_iters = w.counters;
@@ -424,6 +431,9 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
     P.eps2 = prm.epsilon * prm.epsilon;                         // src/tvl1flow.cpp:113
     return P;
 }
+
+int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B);
+bool tb_usable(tvl1_ctx *ctx, const Level &l, int B);
 
 int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
 {
@@ -445,6 +455,76 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
         k_iterate_t1<4, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
+    if (P.tb) TRY(launch_iterate_tb(ctx, P, B));   // pairs whose next block has more than one iteration
+    return TVL1_OK;
+}
+
+
+// ---- TMA descriptors for the temporally blocked kernel ------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn) p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// planes[z][y][x] with row pitch `pitch` and plane stride `plane` (floats); box 64 x 32 x 1, zero fill
+bool make_plane_map(CUtensorMap *m, float *base, int nx, int ny, int nplanes, int pitch, size_t plane)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = { (cuuint64_t) nx, (cuuint64_t) ny, (cuuint64_t) nplanes };
+    const cuuint64_t strides[2] = { (cuuint64_t) pitch * sizeof(float), (cuuint64_t) plane * sizeof(float) };
+    const cuuint32_t box[3] = { kTbBW, kTbBH, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tb_usable(tvl1_ctx *ctx, const Level &l, int B)
+{
+    static bool attr = false;
+    if (!ctx->use_tb || !tensor_map_encoder()) return false;
+    if ((long long) B * l.nx * l.ny > ctx->tb_max_pixels) return false;     // big batches: empty launches cost more than they save
+    if (l.nx < kTbBW || l.ny < kTbBH) return false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_iterate_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTbSmemBytes) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr = true;
+    }
+    return true;
+}
+
+int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B)
+{
+    const Workspace &w = ctx->ws;
+    TbMaps maps;
+    bool ok = true;
+    for (int set = 0; set < 2; set++)
+        ok = ok && make_plane_map(&maps.state[set], w.state + (size_t) set * w.set_stride, P.lv.nx, P.lv.ny,
+                                  F_COUNT * B, P.lv.pitch, w.plane0);
+    ok = ok && make_plane_map(&maps.consts, w.consts, P.lv.nx, P.lv.ny, C_COUNT * B, P.lv.pitch, w.plane0);
+    if (!ok) { ctx->err = "cuTensorMapEncodeTiled failed"; return TVL1_ERR_CUDA; }
+    dim3 g(ceil_div(P.lv.nx, kTbW), ceil_div(P.lv.ny, kTbH), B);
+    k_iterate_tb<<<g, kTbThreads, kTbSmemBytes, ctx->stream>>>(maps, P);
+    CK(cudaGetLastError());
     return TVL1_OK;
 }
 
@@ -584,7 +664,8 @@ int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base
         }
         k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.loop, B);   // :111-112
         CKL(ctx);
-        const IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations, s);
+        IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations, s);
+        P.tb = tb_usable(ctx, w.lv[s], B) ? 1 : 0;
         TRY(run_iterations(ctx, P, B, chunk_hint));                         // :113-182
     }
     return TVL1_OK;
@@ -1481,6 +1562,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
+    if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
     *out = ctx;
     return TVL1_OK;
 }
@@ -2023,6 +2105,84 @@ int tvl1_iterate_resident_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, f
     }
     CK(cudaStreamSynchronize(st));
     return TVL1_OK;
+}
+
+int tvl1_iterate_loop_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12, float *p21,
+                          float *p22, const float *rho_c, const float *I1wx, const float *I1wy, int nx,
+                          int ny, double tau, double lambda, double theta, double epsilon, int max_iter,
+                          int temporal_blocking, int *iters_out, double *err_out, int *launches_out)
+{
+    if (!ctx || !u1 || !u2 || !p11 || !p12 || !p21 || !p22 || !rho_c || !I1wx || !I1wy || nx < 1 ||
+        ny < 1 || max_iter < 1)
+        return fail_arg(ctx, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const bool saved_res = ctx->use_resident;
+    ctx->use_resident = false;                               // this hook is about the streaming kernels
+    const int rc0 = ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1);
+    ctx->use_resident = saved_res;
+    TRY(rc0);
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t) nx * ny;
+    Dev d(ctx->stream);
+    float *buf = d.alloc(n);
+    if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
+    CKL(ctx);
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
+    float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
+    for (int f = 0; f < 6; f++) {
+        CK(cudaMemcpyAsync(buf, st_host[f], n * 4, cudaMemcpyHostToDevice, st));
+        k_pack<<<g, dim3(32, 8), 0, st>>>(buf, w.state + (size_t) f * w.field_stride, nx, ny, w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+    }
+    const float *c_host[3] = { I1wx, I1wy, rho_c };
+    for (int c = 0; c < 3; c++) {
+        CK(cudaMemcpyAsync(buf, c_host[c], n * 4, cudaMemcpyHostToDevice, st));
+        k_pack<<<g, dim3(32, 8), 0, st>>>(buf, w.consts + (size_t) c * w.field_stride, nx, ny, w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+    }
+    tvl1_params prm;
+    tvl1_default_params(&prm);
+    prm.tau = tau; prm.lambda = lambda; prm.theta = theta; prm.epsilon = epsilon < 0 ? 0.0 : epsilon;
+    k_begin_warp<<<1, 32, 0, st>>>(w.ctl, w.loop, 1);
+    CKL(ctx);
+    IterParams P = iter_params(ctx, w.lv[0], prm, 0, max_iter);
+    if (epsilon < 0) P.eps2 = -1.0;                          // never stop before max_iter
+    if (temporal_blocking) {
+        if (!tb_usable(ctx, w.lv[0], 1)) return fail_arg(ctx, "temporally blocked kernel not usable for this size");
+        P.tb = 1;
+        if (temporal_blocking > 1) {                          // force full blocks from the first launch on
+            PairCtl c;
+            CK(cudaMemcpyAsync(&c, w.ctl, sizeof c, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            c.nsteps = std::min(kTbT, max_iter);
+            CK(cudaMemcpyAsync(w.ctl, &c, sizeof c, cudaMemcpyHostToDevice, st));
+        }
+    }
+    int launches = 0;
+    for (;;) {
+        TRY(launch_iterate(ctx, P, 1));
+        launches++;
+        CK(cudaMemcpyAsync(ctx->h_loop, w.loop, sizeof(LoopCtl), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (ctx->h_loop->active_pairs == 0 || launches > 4 * max_iter + 8) break;
+    }
+    PairCtl c;
+    CK(cudaMemcpyAsync(&c, w.ctl, sizeof c, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (iters_out) *iters_out = c.n;
+    if (err_out) *err_out = c.err;
+    if (launches_out) *launches_out = launches;
+    for (int f = 0; f < 6; f++) {
+        k_unpack<<<g, dim3(32, 8), 0, st>>>(w.state + (size_t) c.cur * w.set_stride + (size_t) f * w.field_stride,
+                                            buf, nx, ny, w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+        CK(cudaMemcpyAsync(st_host[f], buf, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return c.active ? fail_arg(ctx, "iteration loop did not terminate") : TVL1_OK;
 }
 
 int tvl1_bench_iterate(tvl1_ctx *ctx, int npairs, int nx, int ny, int launches, double *ms_out)

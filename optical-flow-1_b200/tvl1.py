@@ -344,6 +344,20 @@ class TVL1:
             C.c_int(cluster), C.byref(n), _fp(errs), C.byref(c)))
         return (*st, n.value, errs[:n.value], c.value)
 
+    def iterate_loop(self, u1, u2, p11, p12, p21, p22, rho_c, I1wx, I1wy, tau, lam, theta, eps, max_iter,
+                     temporal_blocking=1):
+        """One warp step's while loop through the streaming kernels.  Returns
+        (u1,u2,p11,p12,p21,p22, n, last_error, launches)."""
+        st = [np.array(a, dtype=np.float32, order="C", copy=True) for a in (u1, u2, p11, p12, p21, p22)]
+        cs = [self._f32(a) for a in (rho_c, I1wx, I1wy)]
+        ny, nx = st[0].shape
+        n, launches, err = C.c_int(), C.c_int(), C.c_double()
+        self._ck(self.lib.tvl1_iterate_loop_f32(
+            self.ctx, *[_fp(a) for a in st], *[_fp(a) for a in cs], C.c_int(nx), C.c_int(ny),
+            C.c_double(tau), C.c_double(lam), C.c_double(theta), C.c_double(eps), C.c_int(max_iter),
+            C.c_int(temporal_blocking), C.byref(n), C.byref(err), C.byref(launches)))
+        return (*st, n.value, err.value, launches.value)
+
     def bench_iterate(self, npairs, nx, ny, launches):
         ms = C.c_double()
         self._ck(self.lib.tvl1_bench_iterate(self.ctx, C.c_int(npairs), C.c_int(nx), C.c_int(ny),

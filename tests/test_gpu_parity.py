@@ -230,6 +230,54 @@ def test_iterate_resident_stopping_rule(gpu, oracle_f64, cluster):
     assert got[6] == 37
 
 
+@pytest.mark.parametrize("shape", [(96, 128), (75, 131), (270, 480), (33, 70)])
+@pytest.mark.parametrize("iters", [4, 10, 13])
+def test_iterate_temporally_blocked_fixed_count(gpu, oracle_f64, shape, iters):
+    """k_iterate_tb (2-D TMA halo tiles, up to 4 iterations per launch in shared memory) against
+    src/tvl1flow.cpp:114-181 for a fixed number of passes; blocks of 4 plus a shorter last block."""
+    u1, u2, p, rho_c, ix, iy, grad = _iterate_inputs(shape, seed=21)
+    got = gpu.iterate_loop(u1, u2, *p, rho_c, ix, iy, 0.25, 0.15, 0.3, -1.0, iters, temporal_blocking=2)
+    ref = oracle_f64.iterate(u1, u2, *p, rho_c, ix, iy, grad, 0.25, 0.15, 0.3, iters)
+    assert got[6] == iters
+    assert got[8] == -(-iters // 4), "launches: %d" % got[8]          # ceil(iters / 4) blocks
+    for k, name in enumerate(("u1", "u2", "p11", "p12", "p21", "p22")):
+        assert np.abs(got[k] - ref[k]).max() < 2e-4 * iters, name
+    assert np.isclose(got[7], ref[6][-1], rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("eps", [0.05, 0.02])
+def test_iterate_loop_exact_stop(gpu, oracle_f64, mode, eps):
+    """Exact stopping under temporal blocking: whatever mix of single iterations, blocks and replays
+    the device chooses, the loop must end after the same iteration as the reference and leave the
+    same state (mode 2 starts with a full block of 4, which forces the overshoot / replay path when
+    the loop is short)."""
+    I0, I1 = _cases.synth.make_pair(200, 136, seed=5, scale=0.2)
+    z = np.zeros_like(I0)
+    c = oracle_f64.warp_precompute(I0, I1, z, z)
+    ref = oracle_f64.iterate(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], c["grad"], 0.25, 0.15, 0.3, 300)
+    n_ref = int(np.argmax(ref[6] <= eps * eps)) + 1 if np.any(ref[6] <= eps * eps) else 300
+    exact = oracle_f64.iterate(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], c["grad"], 0.25, 0.15, 0.3, n_ref)
+    got = gpu.iterate_loop(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, eps, 300, mode)
+    assert 1 < n_ref < 300
+    assert got[6] == n_ref, (got[6], n_ref, got[8])
+    for k in range(6):
+        assert np.abs(got[k] - exact[k]).max() < 2e-4 * n_ref
+    assert np.isclose(got[7], ref[6][n_ref - 1], rtol=1e-3)
+    if mode == 0:
+        assert got[8] == n_ref
+    else:
+        assert got[8] <= n_ref
+
+
+def test_iterate_loop_replay_on_immediate_stop(gpu, oracle_f64):
+    """A loop that stops after its first iteration although a block of 4 was started."""
+    shape = (64, 96)
+    z = np.zeros(shape, np.float32)
+    got = gpu.iterate_loop(z, z, z, z, z, z, z, z, z, 0.25, 0.15, 0.3, 0.01, 300, 2)   # zero update -> error 0
+    assert got[6] == 1 and got[7] == 0.0 and got[8] == 2       # block of 4 rejected, replay of 1 accepted
+
+
 # ---- the solver against the golden vectors of the unmodified reference --------------------------
 
 @pytest.mark.parametrize("name", sorted(_cases.SOLVER_CASES))
