@@ -958,9 +958,9 @@ __device__ __forceinline__ void decide_block(const IterParams &P, PairCtl *ctl, 
         return;
     }
     int next = 1;
-    if (P.tb) {
-        next = kTbT;
-        if (prev < INFINITY && last < prev && last > P.eps2) {
+    if (P.tb && prev < INFINITY) {          // no history yet (first iteration of the warp step): stay at 1
+        next = kTbT;                        // error not falling: far from the stopping point
+        if (last < prev && last > P.eps2) {
             // error ~ last * r^k: iterations until it is below eps^2 (the decay usually slows down, so
             // this under-estimates and a replay stays rare); keep one in hand
             const double k = log(P.eps2 / last) / log(last / prev);
