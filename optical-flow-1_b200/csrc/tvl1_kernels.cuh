@@ -1576,7 +1576,7 @@ __device__ __forceinline__ void tma_load_3d(float *dst, const CUtensorMap *map, 
                     "r"(smem_u32(mbar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kTbThreads, 2)
+__global__ void __launch_bounds__(kTbThreads, 3)
 k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
 {
     extern __shared__ __align__(128) float tb_smem[];
