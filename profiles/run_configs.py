@@ -20,7 +20,7 @@ kind = "reference" if available("reference", np.float64) else "port"
 cpu = CpuTvl1(kind, np.float64)
 cpu.set_threads(os.cpu_count() or 1)
 g = pkg.TVL1(0, profiling=True)
-print("| config | params | GPU device-resident ms | GPU host-buffer call ms (fp32 / fp64 drop-in) | CPU %s ms (%d threads) | speed-up (fp64 call) | iteration counts equal | mean / max |dflow| px | iterations per level (coarse->fine) | k_iterate_t1 GB/s (64 B/px-iter) |"
+print("| config | params | GPU device-resident ms | GPU host-buffer call ms (fp32 / fp64 drop-in) | CPU %s ms (%d threads) | speed-up (fp64 call) | iteration counts equal | mean / max |dflow| px | iterations per level (coarse->fine) | streaming iteration kernels (k_iterate_t1 + k_iterate_tb) GB/s at 64 B/px-iter |"
       % (kind, cpu.max_threads()))
 print("|---|---|---|---|---|---|---|---|---|---|")
 for idx in only:
