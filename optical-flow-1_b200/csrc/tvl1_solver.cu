@@ -218,8 +218,11 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
     for (int C = 1; C <= kResMaxCluster; C *= 2) {
         if (ctx->force_cluster && C != ctx->force_cluster) continue;
         // a small batch cannot fill the GPU with minimal clusters: keep growing the cluster (shorter
-        // bands, shorter iterations) while all clusters of the batch still run concurrently
-        if (best && !ctx->force_cluster && B * C > ctx->sm_count) break;
+        // bands, shorter iterations) while all clusters of the batch still run concurrently -- but
+        // only while a CTA still has real work: below ~2k pixels the two cluster barriers per
+        // iteration cost more than the band saves (a 1-CTA "cluster" only needs __syncthreads)
+        if (best && !ctx->force_cluster &&
+            (B * C > ctx->sm_count || (long long) *rows_out * l.pitch <= 2048)) break;
         const int RB = ceil_div(l.ny, C);
         if ((C - 1) * RB >= l.ny) continue;                        // every CTA needs at least one row
         if (RB * (l.pitch / 4) > kResThreads * kResQuads) continue;
