@@ -501,7 +501,8 @@ bool make_plane_map(CUtensorMap *m, float *base, int nx, int ny, int nplanes, in
 
 bool tb_usable(tvl1_ctx *ctx, const Level &l, int B)
 {
-    static bool attr = false;
+    static bool attr_done[64] = { false };      // function attributes are per device
+    bool &attr = attr_done[ctx->device & 63];
     if (!ctx->use_tb || !tensor_map_encoder()) return false;
     if ((long long) B * l.nx * l.ny > ctx->tb_max_pixels) return false;     // big batches: empty launches cost more than they save
     if (l.nx < kTbBW || l.ny < kTbBH) return false;
