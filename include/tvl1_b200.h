@@ -95,6 +95,11 @@ int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out);
 void *tvl1_get_stream(const tvl1_ctx *ctx);        /* the cudaStream_t all work of this context is issued on */
 void tvl1_default_params(tvl1_params *p);          /* tvl1flow_main.cpp:24-33 with nscales = 5 */
 
+/* The C++ drop-in symbols (Dual_TVL1_optic_flow_multiscale / Dual_TVL1_optic_flow) keep one context
+ * per calling host thread.  This selects the GPU for the calling thread (default: environment
+ * variable TVL1_DEVICE, else 0): one thread per GPU shards the frame pairs of a video. */
+void tvl1_dropin_set_device(int device);
+
 /* -- the solver: Dual_TVL1_optic_flow_multiscale (src/tvl1flow.cpp:219-328) ---------------- */
 /* HOST buffers.  iters_out / errs_out may be NULL; otherwise [nscales*warps] per pair, coarsest
  * level first, exactly the numbers the reference prints in verbose mode (tvl1flow.cpp:184-188). */

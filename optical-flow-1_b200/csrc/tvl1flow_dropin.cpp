@@ -31,19 +31,28 @@ namespace {
 
 struct ThreadCtx {
     tvl1_ctx *ctx = nullptr;
+    int device = -1;           // device the context was made for
     ~ThreadCtx() { tvl1_destroy(ctx); }
 };
 
-// one context per calling host thread: the reference is re-entrant, and batch sharding drives one
-// host thread per GPU (TVL1_DEVICE selects the device for the calling thread's first call).
+thread_local int t_device = -1;    // tvl1_dropin_set_device(); -1: TVL1_DEVICE or 0
+
+// One context per calling host thread: the reference is re-entrant, and batch sharding drives one
+// host thread per GPU.  The device is the one the thread chose with tvl1_dropin_set_device(), else
+// the process-wide TVL1_DEVICE, else 0.
 tvl1_ctx *thread_ctx()
 {
     static thread_local ThreadCtx tc;
-    if (!tc.ctx) {
-        int dev = 0;
+    int dev = t_device;
+    if (dev < 0) {
+        dev = 0;
         if (const char *e = std::getenv("TVL1_DEVICE")) dev = std::atoi(e);
+    }
+    if (tc.ctx && tc.device != dev) { tvl1_destroy(tc.ctx); tc.ctx = nullptr; }
+    if (!tc.ctx) {
         if (tvl1_create(dev, &tc.ctx) != TVL1_OK)
             throw std::runtime_error(std::string("tvl1_b200: ") + tvl1_last_error(nullptr));
+        tc.device = dev;
     }
     return tc.ctx;
 }
@@ -108,6 +117,9 @@ void single_scale(T *I0, T *I1, T *u1, T *u2, int nx, int ny, double tau, double
 }
 
 } // namespace
+
+// Selects the GPU for the calling thread's drop-in calls (declared in include/tvl1_b200.h).
+extern "C" void tvl1_dropin_set_device(int device) { t_device = device; }
 
 // ---- ofpix_t = double (reference as shipped) ----------------------------------------------------
 void Dual_TVL1_optic_flow_multiscale(double *I0, double *I1, double *u1, double *u2, const int nxx,

@@ -389,6 +389,44 @@ def test_band_code_path_single_rank(gpu, oracle_f64):
     assert_flow_close(b[0], b[1], r[0], r[1], "band mode")
 
 
+def test_dropin_symbols_from_threads(gpu):
+    """The reference's mangled C++ entry point (src/tvl1flow.h:56-70, ofpix_t = double) called from
+    two host threads at once, one context per thread (and one GPU per thread when there are two)."""
+    import ctypes as C
+    import threading
+    import torch
+    lib = C.CDLL(pkg.library_path())
+    fn = getattr(lib, "_Z31Dual_TVL1_optic_flow_multiscalePdS_S_S_iidddididb")
+    fn.restype = None
+    ndev = torch.cuda.device_count()
+    pairs = [_cases.synth.make_pair(120, 88, seed=60 + t, scale=0.4) for t in range(2)]
+    out, errors = [None, None], []
+
+    def work(t):
+        try:
+            lib.tvl1_dropin_set_device(C.c_int(t % ndev))
+            I0 = pairs[t][0].astype(np.float64)
+            I1 = pairs[t][1].astype(np.float64)
+            u = np.empty((2,) + I0.shape, np.float64)
+            p = lambda a: a.ctypes.data_as(C.c_void_p)
+            for _ in range(3):
+                fn(p(I0), p(I1), p(u[0]), C.c_void_p(u[1].ctypes.data), C.c_int(120), C.c_int(88), C.c_double(0.25),
+                   C.c_double(0.15), C.c_double(0.3), C.c_int(3), C.c_double(0.5), C.c_int(3), C.c_double(0.01),
+                   C.c_bool(False))
+            out[t] = u
+        except Exception as e:          # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    for t in range(2):
+        u1, u2, _, _ = gpu.Dual_TVL1_optic_flow_multiscale(pairs[t][0].astype(np.float64), pairs[t][1].astype(np.float64),
+                                                           nscales=3, warps=3, eps=0.01)
+        assert np.array_equal(out[t][0], u1) and np.array_equal(out[t][1], u2)
+
+
 # ---- BASELINE.json configs --------------------------------------------------------------------
 
 def reference_cpu():
