@@ -1576,6 +1576,106 @@ __device__ __forceinline__ void tma_load_3d(float *dst, const CUtensorMap *map, 
                     "r"(smem_u32(mbar)) : "memory");
 }
 
+// The iterations of k_iterate_tb on the shared-memory box.  INTERIOR = the box lies inside the image
+// and touches neither its last column nor its last row: all boundary predicates fold away.
+template <bool INTERIOR>
+__device__ __forceinline__ void tb_iterations(const IterParams &P, int ns, int X0, int Y0, int nx, int ny,
+                                              float *sU1, float *sU2, float *sP11, float *sP12, float *sP21,
+                                              float *sP22, const float *sIx, const float *sIy, const float *sRho,
+                                              double (*s_err)[kTbThreads / 32])
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qx = tid & 15, ry = tid >> 4;                  // two groups of 4 pixels: rows ry and ry+16
+    const int bx0 = qx * 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int t = 0; t < ns; t++) {
+        // ---- phase A: thresholding, divergence, primal update, error ----------------------------
+        float errp = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int by = ry + 16 * k, o = by * kTbBW + bx0;
+            const int gy = Y0 + by;
+            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
+            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
+            const float4 p12 = lds4(sP12 + o), p22 = lds4(sP22 + o);
+            const float4 a12 = by > 0 ? lds4(sP12 + o - kTbBW) : zero4;
+            const float4 a22 = by > 0 ? lds4(sP22 + o - kTbBW) : zero4;
+            const float4 ix = lds4(sIx + o), iy = lds4(sIy + o), rc = lds4(sRho + o);
+            float l11 = __shfl_up_sync(0xffffffffu, p11.w, 1);
+            float l21 = __shfl_up_sync(0xffffffffu, p21.w, 1);
+            if (qx == 0) { l11 = 0.f; l21 = 0.f; }
+            const bool last_row = !INTERIOR && (gy == ny - 1);
+            const bool row_in = INTERIOR || (gy >= 0 && gy < ny);
+            const bool row_owned = by >= kTbT && by < kTbT + kTbH;
+            float o1[4], o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int gx = X0 + bx0 + e;
+                const bool in_img = INTERIOR || (row_in && gx >= 0 && gx < nx);
+                const bool last_col = !INTERIOR && gx >= nx - 1;
+                const float a = TVL1_F4_GET(u1, e), c = TVL1_F4_GET(u2, e);
+                const float gxv = TVL1_F4_GET(ix, e), gyv = TVL1_F4_GET(iy, e);
+                primal_px(a, c, gxv, gyv, TVL1_F4_GET(rc, e), grad_of(gxv, gyv),
+                          last_col ? 0.f : TVL1_F4_GET(p11, e), (e == 0) ? l11 : TVL1_F4_GET(p11, (e + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(p12, e), TVL1_F4_GET(a12, e),
+                          last_col ? 0.f : TVL1_F4_GET(p21, e), (e == 0) ? l21 : TVL1_F4_GET(p21, (e + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(p22, e), TVL1_F4_GET(a22, e),
+                          P.l_t, P.theta, o1[e], o2[e]);
+                if (!in_img) { o1[e] = a; o2[e] = c; }
+                const float e1 = o1[e] - a, e2 = o2[e] - c;
+                const bool owned = row_owned && in_img && bx0 + e >= kTbT && bx0 + e < kTbT + kTbW;
+                errp += owned ? (e1 * e1 + e2 * e2) : 0.f;
+            }
+            st4(sU1 + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
+            st4(sU2 + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        }
+        {
+            const double e = warp_sum((double) errp);
+            if (lane == 0) s_err[t][warp] = e;
+        }
+        __syncthreads();
+        // ---- phase B: forward gradient of u_new, dual update --------------------------------------
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int by = ry + 16 * k, o = by * kTbBW + bx0;
+            const int gy = Y0 + by;
+            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
+            const float4 b1 = by + 1 < kTbBH ? lds4(sU1 + o + kTbBW) : zero4;
+            const float4 b2 = by + 1 < kTbBH ? lds4(sU2 + o + kTbBW) : zero4;
+            float r1 = __shfl_down_sync(0xffffffffu, u1.x, 1);
+            float r2 = __shfl_down_sync(0xffffffffu, u2.x, 1);
+            if (qx == 15) { r1 = 0.f; r2 = 0.f; }
+            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
+            const float4 p12 = lds4(sP12 + o), p22 = lds4(sP22 + o);
+            const bool has_below = INTERIOR || gy + 1 < ny;
+            const bool row_in = INTERIOR || (gy >= 0 && gy < ny);
+            float q11[4], q12[4], q21[4], q22[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int gx = X0 + bx0 + e;
+                const bool in_img = INTERIOR || (row_in && gx >= 0 && gx < nx);
+                const bool last_col = !INTERIOR && gx >= nx - 1;
+                const float c1 = TVL1_F4_GET(u1, e), c2 = TVL1_F4_GET(u2, e);
+                const float e1 = (e == 3) ? r1 : TVL1_F4_GET(u1, (e + 1) & 3);
+                const float e2 = (e == 3) ? r2 : TVL1_F4_GET(u2, (e + 1) & 3);
+                q11[e] = TVL1_F4_GET(p11, e); q12[e] = TVL1_F4_GET(p12, e);
+                q21[e] = TVL1_F4_GET(p21, e); q22[e] = TVL1_F4_GET(p22, e);
+                dual_px(last_col ? 0.f : e1 - c1, has_below ? TVL1_F4_GET(b1, e) - c1 : 0.f,
+                        last_col ? 0.f : e2 - c2, has_below ? TVL1_F4_GET(b2, e) - c2 : 0.f,
+                        P.taut, q11[e], q12[e], q21[e], q22[e]);
+                if (!in_img) { q11[e] = q12[e] = q21[e] = q22[e] = 0.f; }   // outside the image p stays 0
+            }
+            st4(sP11 + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
+            st4(sP12 + o, make_float4(q12[0], q12[1], q12[2], q12[3]));
+            st4(sP21 + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
+            st4(sP22 + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
+        }
+        __syncthreads();
+    }
+
+}
+
 __global__ void __launch_bounds__(kTbThreads, 3)
 k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
 {
@@ -1626,93 +1726,12 @@ k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
         }
     }
 
-    const int qx = tid & 15, ry = tid >> 4;                  // two groups of 4 pixels: rows ry and ry+16
-    const int bx0 = qx * 4;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int t = 0; t < ns; t++) {
-        // ---- phase A: thresholding, divergence, primal update, error ----------------------------
-        float errp = 0.f;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int by = ry + 16 * k, o = by * kTbBW + bx0;
-            const int gy = Y0 + by;
-            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
-            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
-            const float4 p12 = lds4(sP12 + o), p22 = lds4(sP22 + o);
-            const float4 a12 = by > 0 ? lds4(sP12 + o - kTbBW) : zero4;
-            const float4 a22 = by > 0 ? lds4(sP22 + o - kTbBW) : zero4;
-            const float4 ix = lds4(sIx + o), iy = lds4(sIy + o), rc = lds4(sRho + o);
-            float l11 = __shfl_up_sync(0xffffffffu, p11.w, 1);
-            float l21 = __shfl_up_sync(0xffffffffu, p21.w, 1);
-            if (qx == 0) { l11 = 0.f; l21 = 0.f; }
-            const bool last_row = (gy == ny - 1);
-            const bool row_in = gy >= 0 && gy < ny;
-            const bool row_owned = by >= kTbT && by < kTbT + kTbH;
-            float o1[4], o2[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int gx = X0 + bx0 + e;
-                const bool in_img = row_in && gx >= 0 && gx < nx;
-                const bool last_col = gx >= nx - 1;
-                const float a = TVL1_F4_GET(u1, e), c = TVL1_F4_GET(u2, e);
-                const float gxv = TVL1_F4_GET(ix, e), gyv = TVL1_F4_GET(iy, e);
-                primal_px(a, c, gxv, gyv, TVL1_F4_GET(rc, e), grad_of(gxv, gyv),
-                          last_col ? 0.f : TVL1_F4_GET(p11, e), (e == 0) ? l11 : TVL1_F4_GET(p11, (e + 3) & 3),
-                          last_row ? 0.f : TVL1_F4_GET(p12, e), TVL1_F4_GET(a12, e),
-                          last_col ? 0.f : TVL1_F4_GET(p21, e), (e == 0) ? l21 : TVL1_F4_GET(p21, (e + 3) & 3),
-                          last_row ? 0.f : TVL1_F4_GET(p22, e), TVL1_F4_GET(a22, e),
-                          P.l_t, P.theta, o1[e], o2[e]);
-                if (!in_img) { o1[e] = a; o2[e] = c; }
-                const float e1 = o1[e] - a, e2 = o2[e] - c;
-                const bool owned = row_owned && in_img && bx0 + e >= kTbT && bx0 + e < kTbT + kTbW;
-                errp += owned ? (e1 * e1 + e2 * e2) : 0.f;
-            }
-            st4(sU1 + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
-            st4(sU2 + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
-        }
-        {
-            const double e = warp_sum((double) errp);
-            if (lane == 0) s_err[t][warp] = e;
-        }
-        __syncthreads();
-        // ---- phase B: forward gradient of u_new, dual update --------------------------------------
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int by = ry + 16 * k, o = by * kTbBW + bx0;
-            const int gy = Y0 + by;
-            const float4 u1 = lds4(sU1 + o), u2 = lds4(sU2 + o);
-            const float4 b1 = by + 1 < kTbBH ? lds4(sU1 + o + kTbBW) : zero4;
-            const float4 b2 = by + 1 < kTbBH ? lds4(sU2 + o + kTbBW) : zero4;
-            float r1 = __shfl_down_sync(0xffffffffu, u1.x, 1);
-            float r2 = __shfl_down_sync(0xffffffffu, u2.x, 1);
-            if (qx == 15) { r1 = 0.f; r2 = 0.f; }
-            const float4 p11 = lds4(sP11 + o), p21 = lds4(sP21 + o);
-            const float4 p12 = lds4(sP12 + o), p22 = lds4(sP22 + o);
-            const bool has_below = gy + 1 < ny;
-            const bool row_in = gy >= 0 && gy < ny;
-            float q11[4], q12[4], q21[4], q22[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int gx = X0 + bx0 + e;
-                const bool in_img = row_in && gx >= 0 && gx < nx;
-                const bool last_col = gx >= nx - 1;
-                const float c1 = TVL1_F4_GET(u1, e), c2 = TVL1_F4_GET(u2, e);
-                const float e1 = (e == 3) ? r1 : TVL1_F4_GET(u1, (e + 1) & 3);
-                const float e2 = (e == 3) ? r2 : TVL1_F4_GET(u2, (e + 1) & 3);
-                q11[e] = TVL1_F4_GET(p11, e); q12[e] = TVL1_F4_GET(p12, e);
-                q21[e] = TVL1_F4_GET(p21, e); q22[e] = TVL1_F4_GET(p22, e);
-                dual_px(last_col ? 0.f : e1 - c1, has_below ? TVL1_F4_GET(b1, e) - c1 : 0.f,
-                        last_col ? 0.f : e2 - c2, has_below ? TVL1_F4_GET(b2, e) - c2 : 0.f,
-                        P.taut, q11[e], q12[e], q21[e], q22[e]);
-                if (!in_img) { q11[e] = q12[e] = q21[e] = q22[e] = 0.f; }   // outside the image p stays 0
-            }
-            st4(sP11 + o, make_float4(q11[0], q11[1], q11[2], q11[3]));
-            st4(sP12 + o, make_float4(q12[0], q12[1], q12[2], q12[3]));
-            st4(sP21 + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
-            st4(sP22 + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
-        }
-        __syncthreads();
+    {
+        const bool interior = X0 >= 0 && Y0 >= 0 && X0 + kTbBW < nx && Y0 + kTbBH < ny;   // CTA-uniform
+        if (interior)
+            tb_iterations<true>(P, ns, X0, Y0, nx, ny, sU1, sU2, sP11, sP12, sP21, sP22, sIx, sIy, sRho, s_err);
+        else
+            tb_iterations<false>(P, ns, X0, Y0, nx, ny, sU1, sU2, sP11, sP12, sP21, sP22, sIx, sIy, sRho, s_err);
     }
 
     // ---- write the owned tile to the other ping-pong set ------------------------------------------
