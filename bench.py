@@ -356,6 +356,32 @@ def run_ours(args, rank, local_rank, world):
     # the device-resident result must equal the host-path result for the same pairs
     same = bool(torch.equal(hu1, u1[:E].cpu()) and torch.equal(hu2, u2[:E].cpu()))
 
+    # the same through the fp64 entry point -- the element type of the reference's own ABI
+    # (ofpix_t = double): twice the PCIe bytes, narrowed / widened on the device
+    E64 = max(args.e2e_max_batch, E // 4)
+    dI0 = hI0[:E64].double().pin_memory()
+    dI1 = hI1[:E64].double().pin_memory()
+    du1 = torch.empty_like(dI0).pin_memory()
+    du2 = torch.empty_like(dI0).pin_memory()
+    del hI0, hI1
+
+    def step_host64():
+        solver.solve_batch_host_ptr(dI0.data_ptr(), dI1.data_ptr(), du1.data_ptr(), du2.data_ptr(),
+                                    E64, nx, ny, dtype="float64", **PARAMS)
+        return float(du1[0, ny // 2, nx // 2])
+
+    step_host64()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        step_host64()
+    torch.cuda.synchronize()
+    e64_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    same64 = bool(torch.equal(du1.float(), hu1[:E64]) and torch.equal(du2.float(), hu2[:E64]))
+    e2e["fp64_abi"] = {"value": world * E64 * 2 / (e64_ms / 1e3), "unit": UNIT, "pairs_per_rank_per_step": E64,
+                       "steps": 2, "h2d_bytes_per_step": 2 * E64 * nx * ny * 8, "d2h_bytes_per_step": 2 * E64 * nx * ny * 8,
+                       "api": "tvl1_solve_batch_f64 (host pinned fp64 in, host fp64 out)", "matches_fp32_path": same64}
+
     total_launches = sum_over_ranks(acc["kernel_launches"])
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
