@@ -269,6 +269,12 @@ def run_ours(args, rank, local_rank, world):
     clk = clocks.stop()
     ms = max_over_ranks(dev_ms)
     value = world * P * args.steps / (ms / 1e3)
+    per_rank_ms = [dev_ms]
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = dev_ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank_ms = [float(x) for x in t.tolist()]
 
     # roofline of the fused iteration kernel over the timed region (this rank)
     peaks = {}
@@ -394,7 +400,8 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config(args, world), "clocks": clk, "e2e": e2e,
             "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_base,
-            "timer": {"device_ms_rank0": dev_ms, "wall_ms_rank0": wall_ms},
+            "timer": {"device_ms_rank0": dev_ms, "wall_ms_rank0": wall_ms,
+                      "device_ms_per_rank": per_rank_ms},
             "host_syncs_per_step": acc["host_syncs"] / args.steps,
             "device_ms_per_step_by_kernel_group": breakdown,
             "other_kernels": other,
