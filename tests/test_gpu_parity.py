@@ -335,6 +335,35 @@ def test_tiny_and_thin_images(gpu, oracle_f64):
         assert_flow_close(u1, u2, r1, r2, "%dx%d" % (nx, ny))
 
 
+def _sweep_cases():
+    rs = np.random.RandomState(2026)
+    cases = []
+    for k in range(14):
+        nx, ny = int(rs.randint(48, 330)), int(rs.randint(40, 260))
+        zf = float(rs.choice([0.5, 0.5, 0.6, 0.7, 0.4, 0.8]))
+        ns = int(rs.randint(1, 5))
+        # the CLI's clamp keeps the coarsest level >= ~16 px (tvl1flow_main.cpp:185-188)
+        ns = min(ns, pkg.clamp_nscales(nx, ny, ns, zf))
+        cases.append(dict(nx=nx, ny=ny, seed=int(rs.randint(1, 10000)), scale=float(rs.uniform(0.1, 0.8)),
+                          kw=dict(tau=float(rs.choice([0.25, 0.2, 0.1])), lam=float(rs.choice([0.15, 0.05, 0.3])),
+                                  theta=float(rs.choice([0.3, 0.2, 0.5])), nscales=ns, zfactor=zf,
+                                  warps=int(rs.randint(1, 5)), eps=float(rs.choice([0.01, 0.02, 0.005])))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _sweep_cases(), ids=lambda c: "%dx%d_z%.1f_s%d_w%d" % (
+    c["nx"], c["ny"], c["kw"]["zfactor"], c["kw"]["nscales"], c["kw"]["warps"]))
+def test_random_parameter_sweep(gpu, oracle_f64, case):
+    """Seeded sweep over sizes (odd widths, non-multiples of 4), pyramid factors (general bicubic
+    zoom_out path, wider Gaussian windows), step sizes and thresholds: iteration counts and flow
+    against the oracle."""
+    I0, I1 = _cases.synth.make_pair(case["nx"], case["ny"], seed=case["seed"], scale=case["scale"])
+    u1, u2, iters, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **case["kw"])
+    r1, r2, riters, _ = oracle_f64.multiscale(I0, I1, **case["kw"])
+    assert np.array_equal(iters, riters), (iters.tolist(), riters.tolist())
+    assert_flow_close(u1, u2, r1, r2, str(case))
+
+
 def test_eps_zero_runs_to_the_cap(gpu):
     I0, I1 = _cases.synth.make_pair(48, 40, seed=3, scale=0.3)
     _, _, iters, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, nscales=2, warps=2, eps=0.0)
