@@ -13,6 +13,11 @@
 // and _Z20Dual_TVL1_optic_flowPdS_S_S_iidddidb.  The float overloads below cover a reference built
 // with OFPIX_DOUBLE commented out.  tvl1flow_main.cpp links against this object unchanged.
 //
+// The upstream IPOL C99 library the reference derives from has the same two functions with C linkage,
+// float pixels and float scalars (3rdparty/tvl1flow_3/tvl1flow_lib.c:45-59 and :299-314); C callers of
+// that library bind the unmangled names, exported at the end of this file.  (C++ allows one C-linkage
+// member in an overload set, and its parameter list differs from the float overloads above it.)
+//
 // Host C++ only: everything GPU goes through the C ABI of include/tvl1_b200.h.
 // Behaviour kept from the reference: void return, failures surface as exceptions
 // (std::runtime_error("GaussianSmooth: sigma too large") from src/operators.cpp:520-522), verbose mode
@@ -149,6 +154,25 @@ void Dual_TVL1_optic_flow_multiscale(float *I0, float *I1, float *u1, float *u2,
 void Dual_TVL1_optic_flow(float *I0, float *I1, float *u1, float *u2, const int nx, const int ny,
                           const double tau, const double lambda, const double theta, const int warps,
                           const double epsilon, const bool verbose)
+{
+    single_scale<float>(I0, I1, u1, u2, nx, ny, tau, lambda, theta, warps, epsilon, verbose);
+}
+
+// ---- upstream C99 library (3rdparty/tvl1flow_3/tvl1flow_lib.c): C linkage, float everywhere ------
+extern "C" void Dual_TVL1_optic_flow_multiscale(float *I0, float *I1, float *u1, float *u2,
+                                                const int nxx, const int nyy, const float tau,
+                                                const float lambda, const float theta,
+                                                const int nscales, const float zfactor,
+                                                const int warps, const float epsilon,
+                                                const bool verbose)
+{
+    multiscale<float>(I0, I1, u1, u2, nxx, nyy, tau, lambda, theta, nscales, zfactor, warps, epsilon, verbose);
+}
+
+extern "C" void Dual_TVL1_optic_flow(float *I0, float *I1, float *u1, float *u2, const int nx,
+                                     const int ny, const float tau, const float lambda,
+                                     const float theta, const int warps, const float epsilon,
+                                     const bool verbose)
 {
     single_scale<float>(I0, I1, u1, u2, nx, ny, tau, lambda, theta, warps, epsilon, verbose);
 }

@@ -216,3 +216,32 @@ class CpuTvl1:
         else:
             self._f("multiscale")(*base, C.c_int(0))
         return u1, u2, iters.reshape(nscales, warps), errs.reshape(nscales, warps)
+
+
+UPSTREAM_C99 = os.path.join(HERE, "_ref", "libtvl1flow3_c99.so")
+
+
+def upstream_c99_available():
+    return os.path.exists(UPSTREAM_C99)
+
+
+def c99_signature(lib):
+    """Declares the C-linkage prototypes of 3rdparty/tvl1flow_3/tvl1flow_lib.c:45-59 and :299-314 on
+    a loaded library (the upstream build, or the CUDA library that exports the same names)."""
+    vp, f, i, b = C.c_void_p, C.c_float, C.c_int, C.c_bool
+    lib.Dual_TVL1_optic_flow_multiscale.argtypes = [vp, vp, vp, vp, i, i, f, f, f, i, f, i, f, b]
+    lib.Dual_TVL1_optic_flow_multiscale.restype = None
+    lib.Dual_TVL1_optic_flow.argtypes = [vp, vp, vp, vp, i, i, f, f, f, i, f, b]
+    lib.Dual_TVL1_optic_flow.restype = None
+    return lib
+
+
+def c99_multiscale(lib, I0, I1, tau=0.25, lam=0.15, theta=0.3, nscales=5, zfactor=0.5, warps=5, eps=0.01):
+    """Calls lib's C-linkage Dual_TVL1_optic_flow_multiscale(float ...) and returns (u1, u2)."""
+    I0 = np.ascontiguousarray(I0, np.float32).copy()
+    I1 = np.ascontiguousarray(I1, np.float32).copy()
+    ny, nx = I0.shape
+    u = np.zeros((2, ny, nx), np.float32)
+    lib.Dual_TVL1_optic_flow_multiscale(I0.ctypes.data, I1.ctypes.data, u[0].ctypes.data, u[1].ctypes.data,
+                                        nx, ny, tau, lam, theta, nscales, zfactor, warps, eps, False)
+    return u[0], u[1]

@@ -20,6 +20,9 @@ MANGLED = [
     "_Z20Dual_TVL1_optic_flowPdS_S_S_iidddidb",
     "_Z31Dual_TVL1_optic_flow_multiscalePfS_S_S_iidddididb",
     "_Z20Dual_TVL1_optic_flowPfS_S_S_iidddidb",
+    # the upstream C99 library's C-linkage names (3rdparty/tvl1flow_3/tvl1flow_lib.c:45-59, :299-314)
+    "Dual_TVL1_optic_flow_multiscale",
+    "Dual_TVL1_optic_flow",
 ]
 
 

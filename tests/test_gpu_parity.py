@@ -456,6 +456,33 @@ def test_dropin_symbols_from_threads(gpu):
         assert np.array_equal(out[t][0], u1) and np.array_equal(out[t][1], u2)
 
 
+def test_upstream_c99_entry_points(gpu):
+    """The C-linkage, all-float names of the upstream library (3rdparty/tvl1flow_3/tvl1flow_lib.c:45-59,
+    :299-314) served by the same CUDA path: bit-identical to tvl1_solve_f32 / tvl1_single_scale_f32,
+    and within the flow tolerance of the upstream CPU build when that travelled with the snapshot."""
+    import ctypes as C
+    from oracle import loader
+    lib = loader.c99_signature(C.CDLL(pkg.library_path()))
+    I0, I1 = _cases.synth.make_pair(176, 132, seed=77, scale=0.6)
+    kw = dict(nscales=4, warps=4, eps=0.01)
+    u1, u2 = loader.c99_multiscale(lib, I0, I1, **kw)
+    g1, g2, _, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0.astype(np.float32), I1.astype(np.float32), **kw)
+    assert np.array_equal(u1, g1) and np.array_equal(u2, g2)
+    if loader.upstream_c99_available():
+        up = loader.c99_signature(C.CDLL(loader.UPSTREAM_C99))
+        r1, r2 = loader.c99_multiscale(up, I0, I1, **kw)
+        assert_flow_close(u1, u2, r1, r2, "upstream C99 build")
+    # one level: u1, u2 are the initial flow on entry
+    a = I0.astype(np.float32).copy()
+    b = I1.astype(np.float32).copy()
+    s = np.full((2,) + a.shape, 0.25, np.float32)
+    lib.Dual_TVL1_optic_flow(a.ctypes.data, b.ctypes.data, s[0].ctypes.data, s[1].ctypes.data,
+                             176, 132, 0.25, 0.15, 0.3, 3, 0.01, False)
+    h1, h2, _, _ = gpu.Dual_TVL1_optic_flow(a, b, np.full(a.shape, 0.25, np.float32),
+                                            np.full(a.shape, 0.25, np.float32), warps=3, eps=0.01)
+    assert np.array_equal(s[0], h1) and np.array_equal(s[1], h2)
+
+
 # ---- BASELINE.json configs --------------------------------------------------------------------
 
 def reference_cpu():

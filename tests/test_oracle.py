@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import _cases
+from oracle import loader
 from oracle.loader import CpuTvl1, available
 
 
@@ -91,3 +92,20 @@ def test_port_equals_compiled_reference(dt):
     rb = R.multiscale(I0, I1, nscales=3, warps=3)
     assert np.array_equal(ra[2], rb[2])
     assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+
+
+@pytest.mark.skipif(not (loader.upstream_c99_available() and available("reference", np.float32)),
+                    reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_upstream_c99_library_is_the_same_algorithm():
+    """The IPOL C99 library the reference derives from (3rdparty/tvl1flow_3/tvl1flow_lib.c, float, C
+    linkage) against the reference's C++ sources built with ofpix_t = float: same pyramid, same
+    stopping behaviour.  This is what lets one CUDA path serve both sets of entry points."""
+    import ctypes as C
+    up = loader.c99_signature(C.CDLL(loader.UPSTREAM_C99))
+    R = CpuTvl1("reference", np.float32)
+    for (nx, ny, ns, seed) in [(160, 120, 3, 1234), (211, 173, 4, 7)]:
+        I0, I1 = _cases.synth.make_pair(nx, ny, seed=seed)
+        u1, u2 = loader.c99_multiscale(up, I0, I1, nscales=ns)
+        r1, r2, _, _ = R.multiscale(I0.astype(np.float32), I1.astype(np.float32), nscales=ns)
+        d = np.abs(np.stack([u1 - r1, u2 - r2]))
+        assert d.mean() < 1e-4 and d.max() < 1e-2, (d.mean(), d.max())
