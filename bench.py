@@ -396,6 +396,41 @@ def run_ours(args, rank, local_rank, world):
                        "steps": 2, "h2d_bytes_per_step": 2 * E64 * nx * ny * 8, "d2h_bytes_per_step": 2 * E64 * nx * ny * 8,
                        "api": "tvl1_solve_batch_f64 (host pinned fp64 in, host fp64 out)", "matches_fp32_path": same64}
 
+    # video form: F consecutive frames -> F-1 flows, each frame uploaded once (tvl1_solve_sequence_f32),
+    # against the pairwise call on the same expanded pairs.  Frames alternate between the two images of
+    # pair 0 (forward / backward flow), so every pair has realistic motion.
+    del dI0, dI1, du1, du2
+    S = E64
+    hF = torch.empty((S + 1, ny, nx), dtype=torch.float32).pin_memory()
+    hF[0::2] = I0[0].cpu()
+    hF[1::2] = I1[0].cpu()
+    sA = hF[:-1].clone().pin_memory()
+    sB = hF[1:].clone().pin_memory()
+    su1 = torch.empty((S, ny, nx), dtype=torch.float32).pin_memory()
+    su2 = torch.empty_like(su1).pin_memory()
+    pu1 = torch.empty_like(su1).pin_memory()
+    pu2 = torch.empty_like(su1).pin_memory()
+
+    def time_host(fn, reps=2):
+        fn()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return max_over_ranks(1e3 * (time.perf_counter() - t)) / reps
+
+    seq_ms = time_host(lambda: solver.solve_sequence_host_ptr(hF.data_ptr(), su1.data_ptr(), su2.data_ptr(),
+                                                              S + 1, nx, ny, **PARAMS))
+    pair_ms = time_host(lambda: solver.solve_batch_host_ptr(sA.data_ptr(), sB.data_ptr(), pu1.data_ptr(),
+                                                            pu2.data_ptr(), S, nx, ny, dtype="float32", **PARAMS))
+    e2e["sequence"] = {"value": world * S / (seq_ms / 1e3), "unit": UNIT, "frames_per_rank_per_step": S + 1,
+                       "h2d_bytes_per_step": (S + 1) * nx * ny * 4, "d2h_bytes_per_step": 2 * S * nx * ny * 4,
+                       "api": "tvl1_solve_sequence_f32 (host pinned frames in, host fp32 flows out)",
+                       "pairwise_same_pairs": world * S / (pair_ms / 1e3),
+                       "matches_pairwise": bool(torch.equal(su1, pu1) and torch.equal(su2, pu2))}
+    del hF, sA, sB, su1, su2, pu1, pu2
+
     total_launches = sum_over_ranks(acc["kernel_launches"])
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -114,7 +114,17 @@ int tvl1_solve_batch_f32(tvl1_ctx *ctx, int npairs, const float *I0, const float
 int tvl1_solve_batch_f64(tvl1_ctx *ctx, int npairs, const double *I0, const double *I1, double *u1,
                          double *u2, int nx, int ny, const tvl1_params *prm, int *iters_out,
                          double *errs_out);
-/* Same, DEVICE buffers (dense, 16-byte aligned).  Work is issued on the context's stream and
+/* A frame sequence (video): nframes frames [nframes][ny][nx] in HOST memory give nframes-1 flows,
+ * pair b = (frame b, frame b+1), u1/u2 [nframes-1][ny][nx].  Same results as tvl1_solve_batch_* on
+ * the expanded pairs (each pair keeps its own joint normalisation, src/tvl1flow.cpp:255), but every
+ * frame crosses PCIe once instead of twice.  This is the batch/video mode of the CLI shell
+ * (src/tvl1flow_main.cpp:203-206 called in a loop over consecutive frames). */
+int tvl1_solve_sequence_f32(tvl1_ctx *ctx, int nframes, const float *frames, float *u1, float *u2,
+                            int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
+int tvl1_solve_sequence_f64(tvl1_ctx *ctx, int nframes, const double *frames, double *u1, double *u2,
+                            int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
+/* Same, DEVICE buffers (dense, 16-byte aligned).  A device-resident frame sequence is the call
+ * below with dI1 = dI0 + nx*ny (inputs are read-only and may overlap).   Work is issued on the context's stream and
  * complete on return.  iters_out / errs_out are HOST pointers. */
 int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const float *dI1,
                              float *du1, float *du2, int nx, int ny, const tvl1_params *prm,

@@ -1016,11 +1016,13 @@ int download_pageable(tvl1_ctx *ctx, T *dst, const float *src, size_t count)
 }
 
 // One chunk of <= max_batch pairs through one lane (context): H2D, solve, D2H, all on the lane's
-// stream.
+// stream.  I1 == nullptr selects the frame-sequence form: I0 holds consecutive frames, pair b is
+// (frame b, frame b+1), and the chunk's B+1 frames cross PCIe once.
 template <typename T>
 int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1, T *u2, int nx, int ny,
                 const tvl1_params *prm, int *iters_out, double *errs_out, bool multiscale, int nstat)
 {
+    const bool sequence = I1 == nullptr;
     const bool f64 = sizeof(T) == 8;
     const size_t n = (size_t) nx * ny;
     cudaStream_t st = ctx->stream;
@@ -1033,20 +1035,25 @@ int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1
            o0 = (float *) ctx->stage_out[0]; o1 = (float *) ctx->stage_out[1]; }
     // host -> device: pinned buffers go straight over PCIe (fp64 is narrowed on the device), pageable
     // buffers through the pinned staging ring (fp64 is narrowed on the host)
-    auto put = [&](const T *h, void *dev_T, float *dev_f32) -> int {
-        if (use_ring<T>(cnt) && is_pageable(h)) return upload_pageable<T>(ctx, dev_f32, h, cnt);
-        CK(cudaMemcpyAsync(dev_T, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+    auto put = [&](const T *h, void *dev_T, float *dev_f32, size_t count) -> int {
+        if (use_ring<T>(count) && is_pageable(h)) return upload_pageable<T>(ctx, dev_f32, h, count);
+        CK(cudaMemcpyAsync(dev_T, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
         if (f64) {
-            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) dev_T, dev_f32, cnt);
+            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) dev_T, dev_f32, count);
             CKL(ctx);
         }
         return TVL1_OK;
     };
-    TRY(put(I0 + off, ctx->stage_in[0], d0));
-    TRY(put(I1 + off, ctx->stage_in[1], d1));
+    if (sequence) {
+        TRY(put(I0 + off, ctx->stage_in[0], d0, cnt + n));
+        d1 = d0 + n;
+    } else {
+        TRY(put(I0 + off, ctx->stage_in[0], d0, cnt));
+        TRY(put(I1 + off, ctx->stage_in[1], d1, cnt));
+    }
     if (!multiscale) {   // u1,u2 are in/out: the initial flow is used (src/tvl1flow.cpp:94)
-        TRY(put(u1 + off, ctx->stage_out[0], o0));
-        TRY(put(u2 + off, ctx->stage_out[1], o1));
+        TRY(put(u1 + off, ctx->stage_out[0], o0, cnt));
+        TRY(put(u2 + off, ctx->stage_out[1], o1, cnt));
     }
     int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
     double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
@@ -1136,7 +1143,7 @@ template <typename T>
 int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2, int nx, int ny,
                const tvl1_params *prm, int *iters_out, double *errs_out, bool multiscale)
 {
-    TRY(check_common(ctx, I0, I1, u1, u2, nx, ny, prm, multiscale));
+    TRY(check_common(ctx, I0, I1 ? I1 : I0, u1, u2, nx, ny, prm, multiscale));
     if (npairs < 1) return fail_arg(ctx, "npairs must be >= 1");
     reset_stats(ctx);
     const bool f64 = sizeof(T) == 8;
@@ -1144,9 +1151,10 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     const int Bmax = std::min(npairs, ctx->max_batch);
     const int nchunks = ceil_div(npairs, Bmax);
     const int nstat = (multiscale ? prm->nscales : 1) * prm->warps;
+    const size_t stage_frames = (size_t) Bmax + (I1 ? 0 : 1);     // frame sequence: B+1 frames per chunk
     return run_lanes(ctx, nchunks, ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
         tvl1_ctx *ctx = c;   // for CK / TRY
-        TRY(ensure_stage(ctx, (size_t) Bmax * n * sizeof(T), f64));
+        TRY(ensure_stage(ctx, stage_frames * n * sizeof(T), f64));
         const int first = k * Bmax, B = std::min(Bmax, npairs - first);
         return solve_chunk<T>(ctx, first, B, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, multiscale, nstat);
     });
@@ -1679,6 +1687,20 @@ int tvl1_solve_batch_f64(tvl1_ctx *ctx, int npairs, const double *I0, const doub
                          double *errs_out)
 {
     return solve_host<double>(ctx, npairs, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int tvl1_solve_sequence_f32(tvl1_ctx *ctx, int nframes, const float *frames, float *u1, float *u2,
+                            int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    if (ctx && nframes < 2) return fail_arg(ctx, "a frame sequence needs at least 2 frames");
+    return solve_host<float>(ctx, nframes - 1, frames, nullptr, u1, u2, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int tvl1_solve_sequence_f64(tvl1_ctx *ctx, int nframes, const double *frames, double *u1, double *u2,
+                            int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    if (ctx && nframes < 2) return fail_arg(ctx, "a frame sequence needs at least 2 frames");
+    return solve_host<double>(ctx, nframes - 1, frames, nullptr, u1, u2, nx, ny, prm, iters_out, errs_out, true);
 }
 
 int tvl1_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI0, const float *dI1,

@@ -218,6 +218,35 @@ class TVL1:
         self._ck(fn(self.ctx, C.c_int(npairs), C.c_void_p(pI0), C.c_void_p(pI1), C.c_void_p(pu1),
                     C.c_void_p(pu2), C.c_int(nx), C.c_int(ny), C.byref(prm), None, None))
 
+    def solve_sequence(self, frames, tau=0.25, lam=0.15, theta=0.3, nscales=5, zfactor=0.5, warps=5,
+                       eps=0.01):
+        """A video: frames (F, ny, nx), float32 or float64 -> flows of the F-1 consecutive pairs,
+        (u1, u2, iters[F-1, nscales, warps], errs) -- the reference CLI's call
+        (src/tvl1flow_main.cpp:203-206) looped over consecutive frames, each frame uploaded once."""
+        frames = np.asarray(frames)
+        dt = np.float64 if frames.dtype == np.float64 else np.float32
+        frames = np.ascontiguousarray(frames, dt)
+        F, ny, nx = frames.shape
+        u1 = np.empty((max(F - 1, 0), ny, nx), dt)
+        u2 = np.empty_like(u1)
+        iters = np.zeros((max(F - 1, 0), nscales, warps), np.int32)
+        errs = np.zeros((max(F - 1, 0), nscales, warps), np.float64)
+        prm = self._params(tau, lam, theta, nscales, zfactor, warps, eps)
+        fn = self.lib.tvl1_solve_sequence_f64 if dt == np.float64 else self.lib.tvl1_solve_sequence_f32
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(fn(self.ctx, C.c_int(F), p(frames), p(u1), p(u2), C.c_int(nx), C.c_int(ny), C.byref(prm),
+                    iters.ctypes.data_as(C.POINTER(C.c_int)), errs.ctypes.data_as(C.POINTER(C.c_double))))
+        return u1, u2, iters, errs
+
+    def solve_sequence_host_ptr(self, pframes, pu1, pu2, nframes, nx, ny, dtype=np.float32, **kw):
+        """Frame sequence by raw host address (pinned buffers)."""
+        p = dict(PAR_DEFAULTS)
+        p.update(kw)
+        prm = self._params(p["tau"], p["lam"], p["theta"], p["nscales"], p["zfactor"], p["warps"], p["eps"])
+        fn = self.lib.tvl1_solve_sequence_f64 if np.dtype(dtype) == np.float64 else self.lib.tvl1_solve_sequence_f32
+        self._ck(fn(self.ctx, C.c_int(nframes), C.c_void_p(pframes), C.c_void_p(pu1), C.c_void_p(pu2),
+                    C.c_int(nx), C.c_int(ny), C.byref(prm), None, None))
+
     # -- row-band mode: one image pair over several GPUs -------------------------------------------
     def band_unique_id(self):
         buf = (C.c_ubyte * 128)()

@@ -74,3 +74,52 @@ def test_cli_drop_in_on_gpu(tmp_path, oracle_f64):
     _, _, _, iters2, scales2, err2 = run_cli(CLI, tmp_path, args=("0", "0.9", "0.15", "0.3", "100", "0.5", "2", "0.01", "1"))
     assert "tau changed to 0.25" in err2
     assert len(scales2) == 3 and len(iters2) == 6
+
+
+CLI_SEQ = os.path.join(ROOT, "cli", "tvl1flow_seq")
+
+
+def test_sequence_cli_usage_errors():
+    """CPU: argument handling of the video front end (no GPU work is reached)."""
+    if not os.path.exists(CLI_SEQ):
+        pytest.skip("cli/tvl1flow_seq not built")
+    p = subprocess.run([CLI_SEQ], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "usage:" in p.stderr
+    p = subprocess.run([CLI_SEQ, "-p", "a.pgm", "b.pgm", "c.pgm"], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "usage:" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(CLI) and os.path.exists(CLI_SEQ)), reason="cli not built")
+def test_sequence_cli_equals_pairwise_cli(tmp_path):
+    """GPU: four frames through tvl1flow_seq give the same three .flo files, byte for byte (the
+    reference main solves in double, the sequence front end in float: compare values, and iteration
+    counts), as three runs of the reference's two-image program."""
+    frames = []
+    for k in range(4):
+        I0, _ = _cases.synth.make_pair(96, 72, seed=5, scale=0.4)
+        write_pgm(tmp_path / ("f%d.pgm" % k), np.roll(I0, (k, 2 * k), axis=(0, 1)))
+        frames.append(str(tmp_path / ("f%d.pgm" % k)))
+    p = subprocess.run([CLI_SEQ, "-o", str(tmp_path / "seq_"), "-s", "3", "-w", "3", "-v", "-b", "2", *frames],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    seq_iters = [int(m) for m in re.findall(r"Warping: \d+, Iterations: (\d+), Error:", p.stderr)]
+    assert len(seq_iters) == 3 * 9
+    for k in range(3):
+        out = tmp_path / ("pair%d.flo" % k)
+        q = subprocess.run([CLI, frames[k], frames[k + 1], str(out), "0", "0.25", "0.15", "0.3", "3", "0.5", "3",
+                            "0.01", "1"], capture_output=True, text=True, timeout=300)
+        assert q.returncode == 0, q.stderr
+        iters = [int(m) for m in re.findall(r"Warping: \d+, Iterations: (\d+), Error:", q.stderr)]
+        assert iters == seq_iters[9 * k:9 * k + 9]
+        a1, a2 = read_flo(out)
+        b1, b2 = read_flo(tmp_path / ("seq_%04d.flo" % k))
+        assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+    # independent pairs: (f0 f1)(f2 f3)
+    p = subprocess.run([CLI_SEQ, "-p", "-o", str(tmp_path / "par_"), "-s", "3", "-w", "3", *frames],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    for k, src in ((0, 0), (1, 2)):
+        a1, a2 = read_flo(tmp_path / ("par_%04d.flo" % k))
+        b1, b2 = read_flo(tmp_path / ("seq_%04d.flo" % src))
+        assert np.array_equal(a1, b1) and np.array_equal(a2, b2)

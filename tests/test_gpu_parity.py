@@ -402,6 +402,27 @@ def test_batch_equals_individual_solves(gpu):
     assert np.array_equal(cu1, bu1) and np.array_equal(cu2, bu2) and np.array_equal(cit, bit)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_frame_sequence_equals_pairwise(gpu, dt):
+    """Video mode: F frames -> F-1 flows, each frame uploaded once; must equal the per-pair solves
+    bit for bit, also when the sequence is cut into chunks (the boundary frame is shared)."""
+    F = 6
+    base = [_cases.synth.make_pair(97, 61, seed=90 + k, scale=0.3)[0] for k in range(2)]
+    frames = np.stack([np.roll(base[k % 2], (k, 2 * k), axis=(0, 1)) for k in range(F)]).astype(dt)
+    kw = dict(nscales=3, warps=2, eps=0.01)
+    for mb in (32, 2):
+        gpu.set_max_batch(mb)
+        su1, su2, sit, _ = gpu.solve_sequence(frames, **kw)
+        assert su1.dtype == dt and su1.shape == (F - 1, 61, 97)
+        for b in range(F - 1):
+            u1, u2, it, _ = gpu.Dual_TVL1_optic_flow_multiscale(frames[b], frames[b + 1], **kw)
+            assert np.array_equal(it, sit[b])
+            assert np.array_equal(u1, su1[b]) and np.array_equal(u2, su2[b])
+    gpu.set_max_batch(32)
+    with pytest.raises(pkg.TVL1Error):
+        gpu.solve_sequence(frames[:1], **kw)
+
+
 def test_band_code_path_single_rank(gpu, oracle_f64):
     """Row-band mode with one rank (a band = the whole level, NCCL communicator of size 1): the
     row-window kernels, the all-reduced stopping rule and the in-place all-gather must reproduce the
