@@ -991,11 +991,15 @@ __device__ __forceinline__ float fast_sqrt(float x)
     return r;
 }
 
+// The per-pixel arithmetic below is written with explicit rounding intrinsics (never re-associated
+// or contracted differently by the compiler), so the streaming, temporally blocked and cluster-resident
+// kernels produce the same bits for the same input -- which kernel serves a level depends on the batch
+// size, and batching must not change the result.
 __device__ __forceinline__ float th_coeff(float rho, float grad, float l_t)
 {
     // src/tvl1flow.cpp:123-139: d = c * (I1wx, I1wy)
-    const float thr = l_t * grad;
-    const float q = -rho * fast_rcp(grad);          // unused (and possibly inf/nan) when grad ~ 0
+    const float thr = __fmul_rn(l_t, grad);
+    const float q = __fmul_rn(-rho, fast_rcp(grad));    // unused (and possibly inf/nan) when grad ~ 0
     return (rho < -thr) ? l_t : ((rho > thr) ? -l_t : ((grad < kGradIsZero) ? 0.f : q));
 }
 
@@ -1007,27 +1011,34 @@ __device__ __forceinline__ void primal_px(float u1, float u2, float ix, float iy
                                           float p21l, float p22c, float p22a, float l_t, float theta,
                                           float &o1, float &o2)
 {
-    const float rho = rho_c + (ix * u1 + iy * u2);
+    const float rho = __fadd_rn(rho_c, __fmaf_rn(ix, u1, __fmul_rn(iy, u2)));
     const float c = th_coeff(rho, grad, l_t);
-    const float v1 = u1 + c * ix, v2 = u2 + c * iy;
-    const float d1 = (p11c - p11l) + (p12c - p12a);
-    const float d2 = (p21c - p21l) + (p22c - p22a);
-    o1 = v1 + theta * d1;
-    o2 = v2 + theta * d2;
+    const float v1 = __fmaf_rn(c, ix, u1), v2 = __fmaf_rn(c, iy, u2);
+    const float d1 = __fadd_rn(__fsub_rn(p11c, p11l), __fsub_rn(p12c, p12a));
+    const float d2 = __fadd_rn(__fsub_rn(p21c, p21l), __fsub_rn(p22c, p22a));
+    o1 = __fmaf_rn(theta, d1, v1);
+    o2 = __fmaf_rn(theta, d2, v2);
+}
+
+// squared update of one pixel, the summand of the stopping test (:159-160)
+__device__ __forceinline__ float update_sq(float o1, float u1, float o2, float u2)
+{
+    const float e1 = __fsub_rn(o1, u1), e2 = __fsub_rn(o2, u2);
+    return __fmaf_rn(e1, e1, __fmul_rn(e2, e2));
 }
 
 // dual update of one pixel from the forward differences of u_new (:169-181)
 __device__ __forceinline__ void dual_px(float u1x, float u1y, float u2x, float u2y, float taut,
                                         float &p11, float &p12, float &p21, float &p22)
 {
-    const float g1 = fast_sqrt(u1x * u1x + u1y * u1y);
-    const float g2 = fast_sqrt(u2x * u2x + u2y * u2y);
-    const float i1 = fast_rcp(1.0f + taut * g1);
-    const float i2 = fast_rcp(1.0f + taut * g2);
-    p11 = (p11 + taut * u1x) * i1;
-    p12 = (p12 + taut * u1y) * i1;
-    p21 = (p21 + taut * u2x) * i2;
-    p22 = (p22 + taut * u2y) * i2;
+    const float g1 = fast_sqrt(__fmaf_rn(u1x, u1x, __fmul_rn(u1y, u1y)));
+    const float g2 = fast_sqrt(__fmaf_rn(u2x, u2x, __fmul_rn(u2y, u2y)));
+    const float i1 = fast_rcp(__fmaf_rn(taut, g1, 1.0f));
+    const float i2 = fast_rcp(__fmaf_rn(taut, g2, 1.0f));
+    p11 = __fmul_rn(__fmaf_rn(taut, u1x, p11), i1);
+    p12 = __fmul_rn(__fmaf_rn(taut, u1y, p12), i1);
+    p21 = __fmul_rn(__fmaf_rn(taut, u2x, p21), i2);
+    p22 = __fmul_rn(__fmaf_rn(taut, u2y, p22), i2);
 }
 
 #define TVL1_F4_GET(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
@@ -1105,9 +1116,8 @@ k_iterate_t1(const IterParams P)
                           last_col ? 0.f : TVL1_F4_GET(r.p21, k), (k == 0) ? l21 : TVL1_F4_GET(r.p21, (k + 3) & 3),
                           last_row ? 0.f : TVL1_F4_GET(r.p22, k), TVL1_F4_GET(a22, k),
                           P.l_t, P.theta, o1[k], o2[k]);
-                const float e1 = o1[k] - u1, e2 = o2[k] - u2;
-                const float sq = e1 * e1 + e2 * e2;
-                err += (tally && x0 + k < nx) ? sq : 0.f;
+                const float sq = update_sq(o1[k], u1, o2[k], u2);
+                err = __fadd_rn(err, (tally && x0 + k < nx) ? sq : 0.f);
             }
             n1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
             n2 = make_float4(o2[0], o2[1], o2[2], o2[3]);
@@ -1438,9 +1448,8 @@ k_iterate_resident(const ResParams P)
                           last_col ? 0.f : TVL1_F4_GET(p21, e), (e == 0) ? l21 : TVL1_F4_GET(p21, (e + 3) & 3),
                           last_row ? 0.f : TVL1_F4_GET(p22, e), TVL1_F4_GET(a22, e),
                           P.l_t, P.theta, o1[e], o2[e]);
-                const float e1 = o1[e] - a, e2 = o2[e] - c;
-                const float sq = e1 * e1 + e2 * e2;
-                errp += (ok && x0 + e < nx) ? sq : 0.f;
+                const float sq = update_sq(o1[e], a, o2[e], c);
+                errp = __fadd_rn(errp, (ok && x0 + e < nx) ? sq : 0.f);
             }
             if (ok) {
                 const float4 n1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
@@ -1623,9 +1632,8 @@ __device__ __forceinline__ void tb_iterations(const IterParams &P, int ns, int X
                           last_row ? 0.f : TVL1_F4_GET(p22, e), TVL1_F4_GET(a22, e),
                           P.l_t, P.theta, o1[e], o2[e]);
                 if (!in_img) { o1[e] = a; o2[e] = c; }
-                const float e1 = o1[e] - a, e2 = o2[e] - c;
                 const bool owned = row_owned && in_img && bx0 + e >= kTbT && bx0 + e < kTbT + kTbW;
-                errp += owned ? (e1 * e1 + e2 * e2) : 0.f;
+                errp = __fadd_rn(errp, owned ? update_sq(o1[e], a, o2[e], c) : 0.f);
             }
             st4(sU1 + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
             st4(sU2 + o, make_float4(o2[0], o2[1], o2[2], o2[3]));

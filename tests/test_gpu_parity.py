@@ -270,6 +270,45 @@ def test_iterate_loop_exact_stop(gpu, oracle_f64, mode, eps):
         assert got[8] <= n_ref
 
 
+def test_kernel_variants_agree_bitwise(oracle_f64):
+    """Which iteration kernel serves a level depends on level and batch size (streaming, temporally
+    blocked, cluster-resident); the flow must not: same bits from every combination."""
+    import os
+    I0, I1 = _cases.synth.make_pair(352, 264, seed=17, scale=0.6)
+    kw = dict(nscales=3, warps=3, eps=0.01)
+    saved = {k: os.environ.pop(k, None) for k in ("TVL1_NO_TB", "TVL1_NO_RESIDENT")}
+    results = []
+    try:
+        for env in ({}, {"TVL1_NO_TB": "1"}, {"TVL1_NO_RESIDENT": "1"}, {"TVL1_NO_TB": "1", "TVL1_NO_RESIDENT": "1"}):
+            for k in ("TVL1_NO_TB", "TVL1_NO_RESIDENT"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            g = pkg.TVL1(device=0)           # the switches are read when the context is made
+            results.append(g.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw))
+            g.close()
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    a = results[0]
+    for r in results[1:]:
+        assert np.array_equal(a[2], r[2])
+        assert np.array_equal(a[0], r[0]) and np.array_equal(a[1], r[1])
+
+
+def test_iterate_loop_variants_agree_bitwise(gpu, oracle_f64):
+    """Fixed 13 iterations on one level: single iterations (mode 0) against blocks of 4 (mode 2)."""
+    I0, I1 = _cases.synth.make_pair(200, 136, seed=5, scale=0.2)
+    z = np.zeros_like(I0)
+    c = oracle_f64.warp_precompute(I0, I1, z, z)
+    a = gpu.iterate_loop(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, -1.0, 13, 0)
+    b = gpu.iterate_loop(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, -1.0, 13, 2)
+    assert a[6] == b[6] == 13
+    for k in range(6):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_iterate_loop_replay_on_immediate_stop(gpu, oracle_f64):
     """A loop that stops after its first iteration although a block of 4 was started."""
     shape = (64, 96)
