@@ -1,6 +1,7 @@
-"""Whole 1080p solves under every combination of iteration kernels (default, no temporal blocking,\nno cluster-resident kernel): prints whether flows and iteration counts agree bitwise."""
+"""Whole 1080p solves under every combination of iteration kernels (default, no temporal blocking,
+no cluster-resident kernel): prints whether flows and iteration counts agree bitwise."""
 import os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import optical_flow_1_b200 as pkg
 P=16; nx,ny=1920,1080
