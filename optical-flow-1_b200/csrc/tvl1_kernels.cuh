@@ -1043,16 +1043,47 @@ __device__ __forceinline__ void dual_px(float u1x, float u1y, float u2x, float u
 
 #define TVL1_F4_GET(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
 
-template <int R, int WY>
-__global__ void __launch_bounds__(32 * WY)
-k_iterate_t1(const IterParams P)
+// Pair slots.  A lock-step batch keeps launching until its slowest pair has converged, so most launches
+// of a big batch find most pairs already inactive -- and a grid with one z-slice per pair would spend
+// the launch starting CTAs that exit at once (57 us for 256 x 272 empty CTAs, measured).  Instead
+// grid.z = Z <= B pair SLOTS: the CTA in slot z serves pairs z, z+Z, z+2Z, ...  Every lane tests one of
+// them, the ballot gives the CTA's work list, and the CTA walks the set bits.  `tb_kernel` selects
+// which of the two iteration kernels the pair's next block belongs to.
+// The work list lives in shared memory, not in registers: nothing of the loop stays live across
+// the (register-hungry) body.  The host sizes Z so that 32 * Z >= batch: one ballot covers the slot.
+template <class Body>
+__device__ __forceinline__ void for_each_pair_of_slot(const IterParams &P, bool tb_kernel, Body &&body)
 {
-    const int b = blockIdx.z;
+    __shared__ unsigned int s_todo;
+    {
+        const int mine = blockIdx.z + (threadIdx.x & 31) * gridDim.z;
+        bool take = false;
+        if (mine < P.batch) {
+            // a pair's control word changes only after ALL its CTAs, this one included, have arrived:
+            // every warp of the CTA reads the same values here
+            const PairCtl *c = P.ctl + mine;
+            const bool blocked = P.tb && c->nsteps > 1;
+            take = c->active && (blocked == tb_kernel);
+        }
+        const unsigned int todo = __ballot_sync(0xffffffffu, take);
+        if (todo == 0u) return;                      // the common case of a late launch
+        if (threadIdx.x == 0) s_todo = todo;
+    }
+    __syncthreads();
+    for (;;) {
+        const unsigned int todo = *(volatile unsigned int *) &s_todo;
+        if (todo == 0u) break;
+        body((int) blockIdx.z + (__ffs(todo) - 1) * (int) gridDim.z);
+        __syncthreads();                             // the pair's shared-memory scratch is free again
+        if (threadIdx.x == 0) { const unsigned int t = s_todo; s_todo = t & (t - 1u); }
+        __syncthreads();
+    }
+}
+
+template <int R, int WY>
+__device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b)
+{
     PairCtl *ctl = P.ctl + b;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && b == 0 && threadIdx.x == 0)
-        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
-    if (!ctl->active) return;                       // uniform for the whole CTA
-    if (P.tb && ctl->nsteps > 1) return;            // this pair's next block belongs to k_iterate_tb
 
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1258,6 +1289,15 @@ k_iterate_t1(const IterParams P)
         decide_block(P, ctl, b, cur, 1, &error,
                      (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
     }
+}
+
+template <int R, int WY>
+__global__ void __launch_bounds__(32 * WY)
+k_iterate_t1(const IterParams P)
+{
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
+    for_each_pair_of_slot(P, false, [&](int b) { iterate_t1_pair<R, WY>(P, b); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1684,20 +1724,13 @@ __device__ __forceinline__ void tb_iterations(const IterParams &P, int ns, int X
 
 }
 
-__global__ void __launch_bounds__(kTbThreads, 3)
-k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
+// One block of up to kTbT iterations of pair b on this CTA's tile.  `mbar` was initialised by the
+// kernel; `parity` is the phase this use of it completes.
+__device__ __forceinline__ void tb_pair(const TbMaps &maps, const IterParams &P, const int b, float *tb_smem,
+                                        double (*s_err)[kTbThreads / 32], double *s_tot,
+                                        unsigned long long &mbar, int &s_last, const unsigned int parity)
 {
-    extern __shared__ __align__(128) float tb_smem[];
-    __shared__ double s_err[kTbT][kTbThreads / 32];
-    __shared__ double s_tot[kTbT];
-    __shared__ unsigned long long mbar;
-    __shared__ int s_last;
-
-    const int b = blockIdx.z;
     PairCtl *ctl = P.ctl + b;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && b == 0 && threadIdx.x == 0)
-        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
-    if (!ctl->active || ctl->nsteps <= 1) return;           // nsteps == 1 pairs belong to k_iterate_t1
     const int ns = min(ctl->nsteps, kTbT);
     const int cur = ctl->cur;
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
@@ -1709,11 +1742,9 @@ k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
           *sRho = sIy + kTbPlane;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
+        // the previous pair's tile was read out of this memory with ordinary loads: order them
+        // before the TMA writes (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                      :: "r"(smem_u32(&mbar)), "r"((unsigned int) kTbSmemBytes) : "memory");
         const CUtensorMap *ms = &maps.state[cur];
@@ -1728,8 +1759,8 @@ k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
         unsigned int done = 0;
         const long long t0 = clock64();
         while (!done) {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(parity) : "memory");
             if (!done && clock64() - t0 > (1ll << 31)) break;   // a bad descriptor must not hang the GPU
         }
     }
@@ -1792,6 +1823,32 @@ k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
     __syncthreads();
     if (tid == 0)
         decide_block(P, ctl, b, cur, ns, s_tot, (unsigned long long) nx * (unsigned long long) ny);
+}
+
+__global__ void __launch_bounds__(kTbThreads, 3)
+k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
+{
+    extern __shared__ __align__(128) float tb_smem[];
+    __shared__ double s_err[kTbT][kTbThreads / 32];
+    __shared__ double s_tot[kTbT];
+    __shared__ unsigned long long mbar;
+    __shared__ int s_last;
+
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    __shared__ unsigned int s_parity;                // phase of the next use of mbar
+    if (threadIdx.x == 0) s_parity = 0u;
+    for_each_pair_of_slot(P, true, [&](int b) {      // (a barrier separates this from the first read)
+        const unsigned int parity = *(volatile unsigned int *) &s_parity;
+        tb_pair(maps, P, b, tb_smem, s_err, s_tot, mbar, s_last, parity);
+        __syncthreads();
+        if (threadIdx.x == 0) s_parity ^= 1u;
+    });
 }
 
 } // namespace tvl1

@@ -94,6 +94,7 @@ struct tvl1_ctx {
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
     bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
+    int slot_ctas = 32768;                   // CTAs a full iteration launch should have at least (TVL1_SLOT_CTAS)
     long long tb_max_pixels = 192ll << 20;   // ... which serves lock-step batches up to this many pixels per level
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
@@ -438,6 +439,15 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
 int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B);
 bool tb_usable(tvl1_ctx *ctx, const Level &l, int B);
 
+// grid.z of the iteration kernels: pair slots (see for_each_pair_of_slot).  Enough slots that a launch
+// with every pair active still has a few thousand CTAs, few enough that a launch with hardly any
+// active pair does not spend its time starting CTAs that exit at once.
+int pair_slots(const tvl1_ctx *ctx, int tiles, int B)
+{
+    // at least ceil(B / 32) slots: one ballot of the kernel covers a slot's pairs
+    return std::min(B, std::max(std::max(32, ceil_div(B, 32)), ceil_div(ctx->slot_ctas, std::max(tiles, 1))));
+}
+
 int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
 {
     // Strip height per warp: 16 rows (fewest CTAs, least halo traffic) when that still gives every SM
@@ -448,13 +458,16 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
     const long long want = 4ll * ctx->sm_count;
     auto ctas = [&](int R) { return (long long) tiles_x * ceil_div(rows, R * kIterWY) * B; };
     if (ctas(16) >= want) {
-        dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), B);
+        dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), 1);
+        g.z = pair_slots(ctx, g.x * g.y, B);
         k_iterate_t1<16, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else if (ctas(8) >= want) {
-        dim3 g(tiles_x, ceil_div(rows, 8 * kIterWY), B);
+        dim3 g(tiles_x, ceil_div(rows, 8 * kIterWY), 1);
+        g.z = pair_slots(ctx, g.x * g.y, B);
         k_iterate_t1<8, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else {
-        dim3 g(tiles_x, ceil_div(rows, 4 * kIterWY), B);
+        dim3 g(tiles_x, ceil_div(rows, 4 * kIterWY), 1);
+        g.z = pair_slots(ctx, g.x * g.y, B);
         k_iterate_t1<4, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
@@ -526,7 +539,8 @@ int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B)
                                   F_COUNT * B, P.lv.pitch, w.plane0);
     ok = ok && make_plane_map(&maps.consts, w.consts, P.lv.nx, P.lv.ny, C_COUNT * B, P.lv.pitch, w.plane0);
     if (!ok) { ctx->err = "cuTensorMapEncodeTiled failed"; return TVL1_ERR_CUDA; }
-    dim3 g(ceil_div(P.lv.nx, kTbW), ceil_div(P.lv.ny, kTbH), B);
+    dim3 g(ceil_div(P.lv.nx, kTbW), ceil_div(P.lv.ny, kTbH), 1);
+    g.z = pair_slots(ctx, g.x * g.y, B);
     k_iterate_tb<<<g, kTbThreads, kTbSmemBytes, ctx->stream>>>(maps, P);
     CK(cudaGetLastError());
     return TVL1_OK;
@@ -1575,6 +1589,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
+    if (const char *sc = std::getenv("TVL1_SLOT_CTAS")) ctx->slot_ctas = std::max(1, std::atoi(sc));
     if (const char *mp = std::getenv("TVL1_TB_MAX_MPIX")) ctx->tb_max_pixels = std::max(0ll, std::atoll(mp)) << 20;
     *out = ctx;
     return TVL1_OK;
