@@ -87,6 +87,7 @@ struct tvl1_ctx {
     int max_batch = 32;
     tvl1_stats stats{};
     Workspace ws;
+    Workspace ws_alt;                        // same image shape, other batch size (ragged last chunk)
     LoopCtl *h_loop = nullptr;               // pinned
     cudaEvent_t sync_event = nullptr;        // blocking-sync event: lane threads sleep instead of spinning
     bool blocking_wait = false;              // set while several lanes share the GPU
@@ -99,6 +100,7 @@ struct tvl1_ctx {
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
     SolveGraph sg;
+    SolveGraph sg_alt;                       // solve graph of ws_alt
     SolveGraph *cap = nullptr;               // graph being captured (profiling events attach to it)
     SolveGraph level_sg[TVL1_MAX_LEVELS];    // row-band mode: one graph per pyramid level
     // row-band mode (one image over several GPUs)
@@ -258,10 +260,9 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
     return best;
 }
 
-bool workspace_matches(const tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor, int B, int stat_stride,
-                       int row_pad)
+bool workspace_matches(const tvl1_ctx *ctx, const Workspace &w, int nx, int ny, int nscales, double zfactor, int B,
+                       int stat_stride, int row_pad)
 {
-    const Workspace &w = ctx->ws;
     return w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
            w.stat_stride >= stat_stride && w.resident_key == (ctx->use_resident ? 1 + ctx->force_cluster : 0) &&
            w.row_pad == row_pad;
@@ -271,7 +272,24 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
                      int row_pad = 1)
 {
     Workspace &w = ctx->ws;
-    if (workspace_matches(ctx, nx, ny, nscales, zfactor, B, stat_stride, row_pad)) return TVL1_OK;
+    if (workspace_matches(ctx, w, nx, ny, nscales, zfactor, B, stat_stride, row_pad)) return TVL1_OK;
+    // A batch that is not a multiple of the lock-step size alternates between two batch sizes (full
+    // chunks and the ragged last one): the displaced workspace and its solve graph are kept as the
+    // alternate, so neither is rebuilt call after call.  Only the batch size may differ, so at most
+    // one extra (smaller or equal) workspace of the same image shape is ever held.
+    if (!ctx->nccl_comm) {
+        if (workspace_matches(ctx, ctx->ws_alt, nx, ny, nscales, zfactor, B, stat_stride, row_pad)) {
+            std::swap(ctx->ws, ctx->ws_alt);
+            std::swap(ctx->sg, ctx->sg_alt);
+            return TVL1_OK;
+        }
+        free_graph(ctx->sg_alt, ctx->ev_pool);
+        free_workspace(ctx->ws_alt);
+        if (w.state && w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B != B) {
+            std::swap(ctx->ws, ctx->ws_alt);
+            std::swap(ctx->sg, ctx->sg_alt);
+        }
+    }
     free_graph(ctx->sg, ctx->ev_pool);
     for (auto &g : ctx->level_sg) free_graph(g, ctx->ev_pool);
     free_workspace(w);
@@ -1434,7 +1452,7 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
     // This context's workspace is used by band solves only (see band_context), and those are
     // collective: every rank takes the same (re)allocation decision here.  Before anybody frees a
     // buffer that neighbours have mapped, all ranks drop their mappings and meet at a barrier.
-    if (!workspace_matches(ctx, nx, ny, ns, prm.zfactor, 1, nstat, G)) {
+    if (!workspace_matches(ctx, ctx->ws, nx, ny, ns, prm.zfactor, 1, nstat, G)) {
         p2p_release_state(ctx);
         NK(g_nccl.AllReduce(ctx->d_band_sum, ctx->d_band_sum, 1, ncclDouble, ncclSum, comm, st));
         CK(cudaStreamSynchronize(st));
@@ -1612,6 +1630,8 @@ void tvl1_destroy(tvl1_ctx *ctx)
     cudaFree(ctx->d_band_sum);
     free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(ctx->ws);
+    free_graph(ctx->sg_alt, ctx->ev_pool);
+    free_workspace(ctx->ws_alt);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->stage_in[i]); cudaFree(ctx->stage_out[i]); }
     for (int i = 0; i < 4; i++) cudaFree(ctx->stage_f32[i]);
     resolve_events(ctx);

@@ -462,6 +462,27 @@ def test_frame_sequence_equals_pairwise(gpu, dt):
         gpu.solve_sequence(frames[:1], **kw)
 
 
+def test_ragged_batch_keeps_both_workspaces(gpu):
+    """A batch that is not a multiple of the lock-step size alternates between two batch sizes; the
+    displaced workspace and its solve graph are kept and swapped back in (profiles/run_e2e.py shows
+    the time this saves); results must not depend on which of the two a chunk ran in."""
+    pairs = [_cases.synth.make_pair(160, 120, seed=300 + b, scale=0.4) for b in range(7)]
+    I0 = np.stack([p[0] for p in pairs])
+    I1 = np.stack([p[1] for p in pairs])
+    kw = dict(nscales=3, warps=2, eps=0.01)
+    g = pkg.TVL1(device=0, max_batch=3)          # chunks of 3, 3, 1
+    g.set_lanes(host_lanes=1)
+    a = g.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    b = g.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    c = g.Dual_TVL1_optic_flow_multiscale(I0[:4], I1[:4], **kw)      # chunks of 3, 1 again
+    g.close()
+    assert np.array_equal(c[0], a[0][:4]) and np.array_equal(c[2], a[2][:4])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for k in range(7):
+        u1, u2, it, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0[k], I1[k], **kw)
+        assert np.array_equal(u1, a[0][k]) and np.array_equal(u2, a[1][k]) and np.array_equal(it, a[2][k])
+
+
 def test_band_code_path_single_rank(gpu, oracle_f64):
     """Row-band mode with one rank (a band = the whole level, NCCL communicator of size 1): the
     row-window kernels, the all-reduced stopping rule and the in-place all-gather must reproduce the
