@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="frame pairs per rank per step")
     ap.add_argument("--e2e-pairs", type=int, default=256, help="frame pairs per rank per e2e step")
-    ap.add_argument("--e2e-max-batch", type=int, default=32,
+    ap.add_argument("--e2e-max-batch", type=int, default=16,
                     help="lock-step chunk of the host-buffer path (chunks alternate between two lanes)")
     ap.add_argument("--e2e-lanes", type=int, default=4)
     ap.add_argument("--nx", type=int, default=1920)
@@ -372,7 +372,7 @@ def run_ours(args, rank, local_rank, world):
 
     # the same through the fp64 entry point -- the element type of the reference's own ABI
     # (ofpix_t = double): twice the PCIe bytes, narrowed / widened on the device
-    E64 = max(args.e2e_max_batch, E // 4)
+    E64 = max(4 * args.e2e_max_batch, E // 4)
     dI0 = hI0[:E64].double().pin_memory()
     dI1 = hI1[:E64].double().pin_memory()
     du1 = torch.empty_like(dI0).pin_memory()
