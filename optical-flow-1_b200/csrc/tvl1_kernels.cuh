@@ -830,7 +830,9 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
         }
         cIx[p] = wx;
         cIy[p] = wy;
-        cRho[p] = w - wx * u1[q] - wy * u2[q] - i0v[q];
+        // I1w - I0 first (nearly equal magnitudes: the difference is exact or close to it), then the two
+        // small products as FMAs: no rounding at the 0..255 scale of the images
+        cRho[p] = __fmaf_rn(-wy, u2[q], __fmaf_rn(-wx, u1[q], __fsub_rn(w, i0v[q])));
         if (write_grad) cGrad[p] = grad_of(wx, wy);
     }
 }
@@ -1011,7 +1013,7 @@ __device__ __forceinline__ void primal_px(float u1, float u2, float ix, float iy
                                           float p21l, float p22c, float p22a, float l_t, float theta,
                                           float &o1, float &o2)
 {
-    const float rho = __fadd_rn(rho_c, __fmaf_rn(ix, u1, __fmul_rn(iy, u2)));
+    const float rho = __fmaf_rn(ix, u1, __fmaf_rn(iy, u2, rho_c));      // two roundings
     const float c = th_coeff(rho, grad, l_t);
     const float v1 = __fmaf_rn(c, ix, u1), v2 = __fmaf_rn(c, iy, u2);
     const float d1 = __fadd_rn(__fsub_rn(p11c, p11l), __fsub_rn(p12c, p12a));
