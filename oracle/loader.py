@@ -217,6 +217,82 @@ class CpuTvl1:
             self._f("multiscale")(*base, C.c_int(0))
         return u1, u2, iters.reshape(nscales, warps), errs.reshape(nscales, warps)
 
+    # -- (d) pyramidal Horn-Schunck, src/horn_schunck_pyramidal.cpp ----------------------------------
+    # The reference's SOR sweep updates u, v in place under an OpenMP parallel-for (:148-158): only
+    # its one-thread result is well defined.  The reference back end is therefore run with one
+    # thread (and the previous thread count restored); the port is sequential by construction.
+    def hs_system(self, I1, I2w, I2wx, I2wy, u, v, alpha):
+        """src/horn_schunck_pyramidal.cpp:127-137 (port only) -> (Au, Av, Du, Dv, D)."""
+        assert self.kind == "port"
+        arrs = [self._arr(a) for a in (I1, I2w, I2wx, I2wy, u, v)]
+        outs = [np.empty_like(arrs[0]) for _ in range(5)]
+        self._f("hs_system")(*[self._p(a) for a in arrs], *[self._p(a) for a in outs],
+                             C.c_double(alpha * alpha), C.c_int(arrs[0].size))
+        return tuple(outs)
+
+    def hs_sor(self, Au, Av, Du, Dv, D, u, v, alpha, tol, maxiter):
+        """The SOR loop of one warp step, :139-231 (port only) -> (u, v, niter, error)."""
+        assert self.kind == "port"
+        cs = [self._arr(a) for a in (Au, Av, Du, Dv, D)]
+        u, v = self._arr(u).copy(), self._arr(v).copy()
+        ny, nx = u.shape
+        err = C.c_double()
+        f = self._f("hs_sor")
+        f.restype = C.c_int
+        n = f(*[self._p(a) for a in cs], self._p(u), self._p(v), C.c_double(alpha * alpha), C.c_int(nx),
+              C.c_int(ny), C.c_double(tol), C.c_int(maxiter), C.byref(err))
+        return u, v, int(n), err.value
+
+    def hs_single_scale(self, I1, I2, u, v, alpha=7.0, warps=10, tol=1e-4, maxiter=150):
+        """horn_schunck_optical_flow (u, v in/out) -> (u, v, iters[warps], errs[warps])."""
+        I1, I2 = self._arr(I1), self._arr(I2)
+        u, v = self._arr(u).copy(), self._arr(v).copy()
+        ny, nx = I1.shape
+        iters = np.zeros(warps, np.int32)
+        errs = np.zeros(warps, np.float64)
+        args = [self._p(I1), self._p(I2), self._p(u), self._p(v), C.c_int(nx), C.c_int(ny),
+                C.c_double(alpha), C.c_int(warps), C.c_double(tol), C.c_int(maxiter),
+                iters.ctypes.data_as(_c_int_p), errs.ctypes.data_as(_c_double_p)]
+        if self.kind == "port":
+            self._f("hs_single_scale")(*args)
+        else:
+            old = self.max_threads()
+            self.set_threads(1)
+            try:
+                n = self._f("hs_single_scale_iters")(*args, C.c_int(warps))
+            finally:
+                self.set_threads(old)
+            assert n == warps, n
+        return u, v, iters, errs
+
+    def hs_multiscale(self, I1, I2, alpha=7.0, nscales=5, zfactor=0.5, warps=10, tol=1e-4, maxiter=150,
+                      threads=1):
+        """horn_schunck_pyramidal -> (u, v, iters[nscales, warps], errs[nscales, warps]); row 0 is the
+        coarsest scale.  `threads` > 1 (reference back end only) runs the reference's racy parallel
+        sweep: used by the CPU baseline timing, never for parity."""
+        I1, I2 = self._arr(I1), self._arr(I2)
+        ny, nx = I1.shape
+        u = np.empty((ny, nx), self.dtype)
+        v = np.empty((ny, nx), self.dtype)
+        iters = np.zeros(nscales * warps, np.int32)
+        errs = np.zeros(nscales * warps, np.float64)
+        args = [self._p(I1), self._p(I2), self._p(u), self._p(v), C.c_int(nx), C.c_int(ny),
+                C.c_double(alpha), C.c_int(nscales), C.c_double(zfactor), C.c_int(warps), C.c_double(tol),
+                C.c_int(maxiter), iters.ctypes.data_as(_c_int_p), errs.ctypes.data_as(_c_double_p)]
+        if self.kind == "port":
+            rc = self._f("hs_multiscale")(*args)
+            if rc:
+                raise RuntimeError("GaussianSmooth: sigma too large")
+        else:
+            old = self.max_threads()
+            self.set_threads(threads)
+            try:
+                n = self._f("hs_multiscale_iters")(*args, C.c_int(iters.size))
+            finally:
+                self.set_threads(old)
+            assert n == iters.size, n
+        return u, v, iters.reshape(nscales, warps), errs.reshape(nscales, warps)
+
 
 UPSTREAM_C99 = os.path.join(HERE, "_ref", "libtvl1flow3_c99.so")
 

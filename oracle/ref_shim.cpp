@@ -13,6 +13,8 @@
 //   centered_gradient                 src/operators.h:93
 //   bicubic_interpolation_warp        src/bicubic_interpolation.h:45
 //   divergence / forward_gradient     src/operators.h:29,42
+//   horn_schunck_pyramidal            src/horn_schunck.h:35-48      
+//   horn_schunck_optical_flow         src/horn_schunck.h:15-26
 //
 // The pixel type is whatever `ofpix_t` the reference objects were built with
 // (double as shipped; float for the cross-check build, see oracle/Makefile).
@@ -31,6 +33,7 @@
 #include "bicubic_interpolation.h"
 #include "zoom.h"
 #include "utils.h"
+#include "horn_schunck.h"
 
 // Runs a callable with stderr redirected to a temp file and parses the reference's
 // "Warping: %d, Iterations: %d, Error: %f" lines (src/tvl1flow.cpp:185-187), which are
@@ -57,6 +60,12 @@ static int capture_iters(F &&call, int *iters, double *errs, int cap)
         if (sscanf(line, "Warping: %d, Iterations: %d, Error: %lf", &w, &it, &e) == 3) {
             if (n < cap) { if (iters) iters[n] = it; if (errs) errs[n] = e; }
             n++;
+        } else if (const char *h = strstr(line, "Iterations ")) {
+            // Horn-Schunck: "Warping %d:Iterations %d (%g)" (src/horn_schunck_pyramidal.cpp:118-120,233-235)
+            if (sscanf(h, "Iterations %d (%lf)", &it, &e) == 2) {
+                if (n < cap) { if (iters) iters[n] = it; if (errs) errs[n] = e; }
+                n++;
+            }
         }
     }
     if (f) fclose(f); else close(fd);
@@ -170,6 +179,31 @@ void ref_divergence(const ofpix_t *v1, const ofpix_t *v2, ofpix_t *div, int nx, 
 void ref_forward_gradient(const ofpix_t *f, ofpix_t *fx, ofpix_t *fy, int nx, int ny)
 {
     forward_gradient(f, fx, fy, nx, ny);
+}
+
+// ---- pyramidal Horn-Schunck (one thread: the reference's SOR sweep is only well defined then) ----
+int ref_hs_multiscale_iters(const ofpix_t *I1, const ofpix_t *I2, ofpix_t *u, ofpix_t *v, int nx, int ny,
+                            double alpha, int nscales, double zfactor, int warps, double TOL, int maxiter,
+                            int *iters, double *errs, int cap)
+{
+    return capture_iters([&] {
+        horn_schunck_pyramidal(I1, I2, u, v, nx, ny, alpha, nscales, zfactor, warps, TOL, maxiter, true);
+    }, iters, errs, cap);
+}
+
+int ref_hs_single_scale_iters(const ofpix_t *I1, const ofpix_t *I2, ofpix_t *u, ofpix_t *v, int nx, int ny,
+                              double alpha, int warps, double TOL, int maxiter, int *iters, double *errs,
+                              int cap)
+{
+    return capture_iters([&] {
+        horn_schunck_optical_flow(I1, I2, u, v, nx, ny, alpha, warps, TOL, maxiter, true);
+    }, iters, errs, cap);
+}
+
+void ref_hs_multiscale(const ofpix_t *I1, const ofpix_t *I2, ofpix_t *u, ofpix_t *v, int nx, int ny,
+                       double alpha, int nscales, double zfactor, int warps, double TOL, int maxiter)
+{
+    horn_schunck_pyramidal(I1, I2, u, v, nx, ny, alpha, nscales, zfactor, warps, TOL, maxiter, false);
 }
 
 } // extern "C"

@@ -523,3 +523,187 @@ int orc_multiscale(const PIX *I0, const PIX *I1, PIX *u1, PIX *u2, int nxx, int 
     free(I0s); free(I1s); free(u1s); free(u2s); free(nx); free(ny);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * (d) pyramidal Horn-Schunck: src/horn_schunck_pyramidal.cpp
+ *
+ * It shares the pyramid (a) and the warp (b) with TV-L1; only the inner SOR sweep is new.
+ * The reference runs the interior sweep under `#pragma omp parallel for` although it updates
+ * u, v in place (src/horn_schunck_pyramidal.cpp:148-158): with more than one thread the result
+ * depends on scheduling.  This restatement is the ONE-thread semantics (lexicographic
+ * Gauss-Seidel order), which is what tests pin against the reference run with one thread.
+ * ---------------------------------------------------------------------------------------- */
+#define ORC_HS_SOR_W 1.9                 /* src/horn_schunck_pyramidal.cpp:21 */
+#define ORC_HS_PRESMOOTHING_SIGMA 0.8    /* src/horn_schunck_pyramidal.cpp:22 */
+
+/* src/horn_schunck_pyramidal.cpp:31-71.  d[0..3] are the diagonal neighbours in the order the call
+ * site passes them (p1..p4), a[0..3] the axial ones (p5..p8). */
+static double orc_hs_sor_px(const PIX *Au, const PIX *Av, const PIX *Du, const PIX *Dv, const PIX *D,
+                            PIX *u, PIX *v, double al, int p, const int d[4], const int a[4])
+{
+    const double w = ORC_HS_SOR_W;
+    const double ula = 1. / 12. * (u[d[0]] + u[d[1]] + u[d[2]] + u[d[3]]) +
+                       1. / 6. * (u[a[0]] + u[a[1]] + u[a[2]] + u[a[3]]);
+    const double vla = 1. / 12. * (v[d[0]] + v[d[1]] + v[d[2]] + v[d[3]]) +
+                       1. / 6. * (v[a[0]] + v[a[1]] + v[a[2]] + v[a[3]]);
+    const PIX uk = u[p];
+    const PIX vk = v[p];
+    u[p] = (1.0 - w) * uk + w * (Au[p] - D[p] * v[p] + al * ula) / Du[p];
+    v[p] = (1.0 - w) * vk + w * (Av[p] - D[p] * u[p] + al * vla) / Dv[p];
+    return (u[p] - uk) * (u[p] - uk) + (v[p] - vk) * (v[p] - vk);
+}
+
+/* Neighbour indices of pixel (i, j): every call site of :147-228 passes the index-clamped
+ * 8-neighbourhood (up-left, up-right, down-left, down-right; up, left, down, right) -- except the
+ * bottom-right corner (:223-228), whose four diagonal arguments come in the order
+ * (left, self, up-left, up); the floating-point sum follows the argument order, so it is kept. */
+static double orc_hs_update(const PIX *Au, const PIX *Av, const PIX *Du, const PIX *Dv, const PIX *D,
+                            PIX *u, PIX *v, double al, int i, int j, int nx, int ny)
+{
+    const int im = orc_clampi(i - 1, ny), ip = orc_clampi(i + 1, ny);
+    const int jm = orc_clampi(j - 1, nx), jp = orc_clampi(j + 1, nx);
+    int d[4] = { im * nx + jm, im * nx + jp, ip * nx + jm, ip * nx + jp };
+    const int a[4] = { im * nx + j, i * nx + jm, ip * nx + j, i * nx + jp };
+    if (i == ny - 1 && j == nx - 1) {
+        const int k = i * nx + j;
+        d[0] = k - 1; d[1] = k; d[2] = k - nx - 1; d[3] = k - nx;
+    }
+    return orc_hs_sor_px(Au, Av, Du, Dv, D, u, v, al, i * nx + j, d, a);
+}
+
+/* One SOR sweep, src/horn_schunck_pyramidal.cpp:144-230: interior in row-major order, then first /
+ * last row interleaved per column, then first / last column interleaved per row, then the corners
+ * (UL, UR, BL, BR).  Returns sqrt(sum / size). */
+double orc_hs_sor_sweep(const PIX *Au, const PIX *Av, const PIX *Du, const PIX *Dv, const PIX *D,
+                        PIX *u, PIX *v, double alpha2, int nx, int ny)
+{
+    double error = 0;
+    for (int i = 1; i < ny - 1; i++)
+        for (int j = 1; j < nx - 1; j++)
+            error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, i, j, nx, ny);
+    for (int j = 1; j < nx - 1; j++) {
+        error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, 0, j, nx, ny);
+        error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, ny - 1, j, nx, ny);
+    }
+    for (int i = 1; i < ny - 1; i++) {
+        error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, i, 0, nx, ny);
+        error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, i, nx - 1, nx, ny);
+    }
+    error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, 0, 0, nx, ny);
+    error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, 0, nx - 1, nx, ny);
+    error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, ny - 1, 0, nx, ny);
+    error += orc_hs_update(Au, Av, Du, Dv, D, u, v, alpha2, ny - 1, nx - 1, nx, ny);
+    return sqrt(error / (nx * ny));
+}
+
+/* The constant parts of the linear system, src/horn_schunck_pyramidal.cpp:127-137. */
+void orc_hs_system(const PIX *I1, const PIX *I2w, const PIX *I2wx, const PIX *I2wy, const PIX *u,
+                   const PIX *v, PIX *Au, PIX *Av, PIX *Du, PIX *Dv, PIX *D, double alpha2, int size)
+{
+    for (int i = 0; i < size; i++) {
+        const double I2wl = I2wx[i] * u[i] + I2wy[i] * v[i];
+        const double dif = I1[i] - I2w[i] + I2wl;
+        Au[i] = dif * I2wx[i];
+        Av[i] = dif * I2wy[i];
+        Du[i] = I2wx[i] * I2wx[i] + alpha2;
+        Dv[i] = I2wy[i] * I2wy[i] + alpha2;
+        D[i] = I2wx[i] * I2wy[i];
+    }
+}
+
+/* The SOR loop of one warp step (:139-231) on a given system; u, v in/out.  Returns the number of
+ * sweeps; *err_out = the last sqrt(sum/size). */
+int orc_hs_sor(const PIX *Au, const PIX *Av, const PIX *Du, const PIX *Dv, const PIX *D, PIX *u, PIX *v,
+               double alpha2, int nx, int ny, double TOL, int maxiter, double *err_out)
+{
+    int niter = 0;
+    double error = 1000;
+    while (error > TOL && niter < maxiter) {
+        niter++;
+        error = orc_hs_sor_sweep(Au, Av, Du, Dv, D, u, v, alpha2, nx, ny);
+    }
+    if (err_out) *err_out = error;
+    return niter;
+}
+
+/* horn_schunck_optical_flow, src/horn_schunck_pyramidal.cpp:78-249.  iters/errs: `warps` entries
+ * (what the reference prints as "Iterations %d (%g)", :233-235), may be NULL. */
+void orc_hs_single_scale(const PIX *I1, const PIX *I2, PIX *u, PIX *v, int nx, int ny, double alpha,
+                         int warps, double TOL, int maxiter, int *iters, double *errs)
+{
+    const int size = nx * ny;
+    const double alpha2 = alpha * alpha;
+    PIX *buf = (PIX *) malloc(sizeof(PIX) * (size_t) size * 10);
+    PIX *I2x = buf, *I2y = buf + size, *I2w = buf + 2 * (size_t) size, *I2wx = buf + 3 * (size_t) size,
+        *I2wy = buf + 4 * (size_t) size, *Au = buf + 5 * (size_t) size, *Av = buf + 6 * (size_t) size,
+        *Du = buf + 7 * (size_t) size, *Dv = buf + 8 * (size_t) size, *D = buf + 9 * (size_t) size;
+    orc_centered_gradient(I2, I2x, I2y, nx, ny);                       /* :114 */
+    for (int n = 0; n < warps; n++) {                                  /* :117 */
+        orc_warp(I2, u, v, I2w, nx, ny, 1);                            /* :123-125 */
+        orc_warp(I2x, u, v, I2wx, nx, ny, 1);
+        orc_warp(I2y, u, v, I2wy, nx, ny, 1);
+        orc_hs_system(I1, I2w, I2wx, I2wy, u, v, Au, Av, Du, Dv, D, alpha2, size);
+        double error;
+        const int niter = orc_hs_sor(Au, Av, Du, Dv, D, u, v, alpha2, nx, ny, TOL, maxiter, &error);
+        if (iters) iters[n] = niter;
+        if (errs) errs[n] = error;
+    }
+    free(buf);
+}
+
+/* horn_schunck_pyramidal, src/horn_schunck_pyramidal.cpp:258-370.  iters/errs are [nscales*warps],
+ * coarsest scale first.  Returns 0, or 1 where the reference would throw from gaussian(). */
+int orc_hs_multiscale(const PIX *I1, const PIX *I2, PIX *u, PIX *v, int nx0, int ny0, double alpha,
+                      int nscales, double zfactor, int warps, double TOL, int maxiter, int *iters,
+                      double *errs)
+{
+    const int size = nx0 * ny0;
+    PIX **I1s = (PIX **) calloc(nscales, sizeof(PIX *));
+    PIX **I2s = (PIX **) calloc(nscales, sizeof(PIX *));
+    PIX **us = (PIX **) calloc(nscales, sizeof(PIX *));
+    PIX **vs = (PIX **) calloc(nscales, sizeof(PIX *));
+    int *nx = (int *) calloc(nscales, sizeof(int));
+    int *ny = (int *) calloc(nscales, sizeof(int));
+    int rc = 0, built = 1;
+
+    I1s[0] = (PIX *) malloc(sizeof(PIX) * size);
+    I2s[0] = (PIX *) malloc(sizeof(PIX) * size);
+    orc_normalize(I1, I2, I1s[0], I2s[0], size);                                  /* :293 */
+    rc |= orc_gaussian(I1s[0], nx0, ny0, ORC_HS_PRESMOOTHING_SIGMA);              /* :296 */
+    rc |= orc_gaussian(I2s[0], nx0, ny0, ORC_HS_PRESMOOTHING_SIGMA);              /* :297 */
+    us[0] = u; vs[0] = v; nx[0] = nx0; ny[0] = ny0;
+
+    for (int s = 1; s < nscales && !rc; s++) {                                    /* :305-317 */
+        orc_zoom_size(nx[s - 1], ny[s - 1], &nx[s], &ny[s], zfactor);
+        const size_t sizes = (size_t) nx[s] * ny[s];
+        I1s[s] = (PIX *) malloc(sizeof(PIX) * sizes);
+        I2s[s] = (PIX *) malloc(sizeof(PIX) * sizes);
+        us[s] = (PIX *) malloc(sizeof(PIX) * sizes);
+        vs[s] = (PIX *) malloc(sizeof(PIX) * sizes);
+        built = s + 1;
+        rc |= orc_zoom_out(I1s[s - 1], I1s[s], nx[s - 1], ny[s - 1], zfactor);
+        rc |= orc_zoom_out(I2s[s - 1], I2s[s], nx[s - 1], ny[s - 1], zfactor);
+    }
+
+    if (!rc) {
+        for (int i = 0; i < nx[nscales - 1] * ny[nscales - 1]; i++)              /* :320-323 */
+            us[nscales - 1][i] = vs[nscales - 1][i] = 0;
+        for (int s = nscales - 1; s >= 0; s--) {                                  /* :326-353 */
+            const int k = nscales - 1 - s;
+            orc_hs_single_scale(I1s[s], I2s[s], us[s], vs[s], nx[s], ny[s], alpha, warps, TOL, maxiter,
+                                iters ? iters + k * warps : 0, errs ? errs + k * warps : 0);
+            if (!s) break;
+            orc_zoom_in(us[s], us[s - 1], nx[s], ny[s], nx[s - 1], ny[s - 1]);
+            orc_zoom_in(vs[s], vs[s - 1], nx[s], ny[s], nx[s - 1], ny[s - 1]);
+            for (int i = 0; i < nx[s - 1] * ny[s - 1]; i++) {
+                us[s - 1][i] *= 1.0 / zfactor;
+                vs[s - 1][i] *= 1.0 / zfactor;
+            }
+        }
+    }
+
+    for (int i = 1; i < built; i++) { free(I1s[i]); free(I2s[i]); free(us[i]); free(vs[i]); }
+    free(I1s[0]); free(I2s[0]);
+    free(I1s); free(I2s); free(us); free(vs); free(nx); free(ny);
+    return rc;
+}

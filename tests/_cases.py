@@ -67,3 +67,36 @@ def solver_inputs(case):
 def run_solver_case(cpu, case):
     I0, I1 = solver_inputs(case)
     return cpu.multiscale(I0, I1, **case["kw"])
+
+
+# ---- pyramidal Horn-Schunck (src/horn_schunck_pyramidal.cpp), SURVEY.md section 8f-4 ----------
+HS_CASES = {
+    # default alpha / TOL of src/horn_schunck_pyramidal_main.cpp:25-30; fewer warps / sweeps so
+    # the fixtures stay small and fast
+    "hs_64x48": dict(nx=64, ny=48, seed=1234, scale=0.5,
+                     kw=dict(alpha=7.0, nscales=3, zfactor=0.5, warps=4, tol=1e-4, maxiter=60)),
+    "hs_61x47_z07": dict(nx=61, ny=47, seed=99, scale=0.4,
+                         kw=dict(alpha=15.0, nscales=3, zfactor=0.7, warps=3, tol=1e-3, maxiter=150)),
+    # loose TOL: every warp step stops on the tolerance, not on maxiter
+    "hs_96x64_tol": dict(nx=96, ny=64, seed=5, scale=0.5,
+                         kw=dict(alpha=7.0, nscales=2, zfactor=0.5, warps=3, tol=2e-2, maxiter=150)),
+}
+
+
+def run_hs_case(cpu, case):
+    I1, I2 = solver_inputs(case)
+    return cpu.hs_multiscale(I1, I2, **case["kw"])
+
+
+def hs_sor_inputs(nx=37, ny=29, seed=21):
+    """A seeded SOR system in the shape src/horn_schunck_pyramidal.cpp:127-137 produces (warped
+    gradients with exact zeros where the warp leaves the image, as border_out = true gives)."""
+    rs = np.random.RandomState(seed)
+    shape = (ny, nx)
+    ix = rs.uniform(-20, 20, shape)
+    iy = rs.uniform(-20, 20, shape)
+    out = rs.uniform(0, 1, shape) < 0.08
+    ix[out] = 0.0
+    iy[out] = 0.0
+    return dict(I1=rs.uniform(0, 255, shape), I2w=np.where(out, 0.0, rs.uniform(0, 255, shape)),
+                I2wx=ix, I2wy=iy, u=rs.uniform(-3, 3, shape), v=rs.uniform(-3, 3, shape))

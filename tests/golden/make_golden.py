@@ -37,6 +37,22 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
 
+    # pyramidal Horn-Schunck (src/horn_schunck_pyramidal.cpp), one thread: the reference's SOR sweep
+    # is an in-place update under an OpenMP parallel-for and only well defined then
+    hs = {}
+    for dt in (np.float64, np.float32):
+        R = CpuTvl1("reference", dt)
+        tag = "f64" if dt == np.float64 else "f32"
+        for name, case in _cases.HS_CASES.items():
+            u, v, iters, errs = _cases.run_hs_case(R, case)
+            hs["%s/%s/u" % (tag, name)] = u
+            hs["%s/%s/v" % (tag, name)] = v
+            hs["%s/%s/iters" % (tag, name)] = iters
+            hs["%s/%s/errs" % (tag, name)] = errs
+    path = os.path.join(ROOT, "tests", "golden", "hs_reference_vectors.npz")
+    np.savez_compressed(path, **hs)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(hs), "arrays")
+
 
 if __name__ == "__main__":
     main()
