@@ -1,0 +1,191 @@
+// TEST INFRASTRUCTURE.  CPU replay of the wavefront schedule of the Horn-Schunck SOR kernel.
+//
+// Includes the product's own per-thread step functions (optical-flow-1_b200/csrc/hs_sor_step.h, the
+// same text nvcc compiles into k_hs_sor) and drives them the way the kernel does -- a barrier per time
+// step, `nthreads` threads that each own rows tid, tid + nthreads, ..., asynchronous copies that land
+// at any time between their issue and the wait that covers them -- but lets the test choose the
+// adversary: the order in which the threads of a step run, whether fetches or updates of a step go
+// first, and when an asynchronous copy reads its source and writes its destination.
+// hs_emu_seq_sor is the sequential sweep (src/horn_schunck_pyramidal.cpp:144-230, the order of
+// oracle/tvl1_oracle.c) in the same fp32 arithmetic: the schedule is correct iff both agree bit for
+// bit under every adversary.
+#define HS_SOR_EMULATE 1
+#include "../../optical-flow-1_b200/csrc/hs_sor_step.h"
+
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+struct Pending { float *dst; const float *src; float value; int group; };
+
+struct EmuCp {
+    std::vector<Pending> q;
+    int group = 0;
+    int land = 0;          // 0: read + write at issue; 1: read at issue, write at completion; 2: both at completion
+    void cp4(float *dst, const float *src)
+    {
+        if (land == 0) { *dst = *src; return; }
+        q.push_back(Pending{ dst, src, *src, group });
+    }
+    void commit() { group++; }
+    // cp.async.wait_group n: at most the n most recently committed groups stay pending
+    void wait(int n)
+    {
+        size_t keep = 0;
+        for (size_t k = 0; k < q.size(); k++) {
+            if (q[k].group < group - n) *q[k].dst = (land == 1) ? q[k].value : *q[k].src;
+            else q[keep++] = q[k];
+        }
+        q.resize(keep);
+    }
+};
+
+struct Rng {
+    uint64_t s;
+    uint32_t next() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t) (s >> 33); }
+};
+
+void thread_order(std::vector<int> &ord, int mode, Rng &rng)
+{
+    const int n = (int) ord.size();
+    for (int k = 0; k < n; k++) ord[k] = k;
+    if (mode == 1) std::reverse(ord.begin(), ord.end());
+    if (mode == 2) for (int k = n - 1; k > 0; k--) std::swap(ord[k], ord[rng.next() % (k + 1)]);
+}
+
+void to_wave(const float *rm, float *w, int nx, int ny)
+{
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) w[hs::wave_index(i, j, nx, ny)] = rm[i * nx + j];
+}
+
+void from_wave(const float *w, float *rm, int nx, int ny)
+{
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) rm[i * nx + j] = w[hs::wave_index(i, j, nx, ny)];
+}
+
+// sequential update of pixel (i, j) on row-major planes, clamped neighbours (+ the BR corner's order)
+double seq_update(const float *ix, const float *iy, const float *rho, float *u, float *v, float alpha2,
+                  int i, int j, int nx, int ny)
+{
+    const int im = i > 0 ? i - 1 : 0, ip = i < ny - 1 ? i + 1 : ny - 1;
+    const int jm = j > 0 ? j - 1 : 0, jp = j < nx - 1 ? j + 1 : nx - 1;
+    int d0 = im * nx + jm, d1 = im * nx + jp, d2 = ip * nx + jm, d3 = ip * nx + jp;
+    const int a0 = im * nx + j, a1 = i * nx + jm, a2 = ip * nx + j, a3 = i * nx + jp, p = i * nx + j;
+    if (i == ny - 1 && j == nx - 1) { d0 = p - 1; d1 = p; d2 = p - nx - 1; d3 = p - nx; }
+    float un, vn;
+    const float e = hs::sor_px(ix[p], iy[p], rho[p], alpha2, u[d0], u[d1], u[d2], u[d3], u[a0], u[a1], u[a2],
+                               u[a3], v[d0], v[d1], v[d2], v[d3], v[a0], v[a1], v[a2], v[a3], u[p], v[p], &un,
+                               &vn);
+    u[p] = un;
+    v[p] = vn;
+    return (double) e;
+}
+
+} // namespace
+
+extern "C" {
+
+// The reference's loop (:139-231) in fp32 with the kernel's per-pixel arithmetic, strictly sequential.
+// u, v: row-major, in/out.  Returns the number of sweeps.
+int hs_emu_seq_sor(float *u, float *v, const float *ix, const float *iy, const float *rho, int nx, int ny,
+                   float alpha2, double tol, int maxiter, double *err_out)
+{
+    int niter = 0;
+    double error = 1000;
+    while (error > tol && niter < maxiter) {
+        niter++;
+        double e = 0;
+        for (int i = 1; i < ny - 1; i++)
+            for (int j = 1; j < nx - 1; j++) e += seq_update(ix, iy, rho, u, v, alpha2, i, j, nx, ny);
+        for (int j = 1; j < nx - 1; j++) {
+            e += seq_update(ix, iy, rho, u, v, alpha2, 0, j, nx, ny);
+            e += seq_update(ix, iy, rho, u, v, alpha2, ny - 1, j, nx, ny);
+        }
+        for (int i = 1; i < ny - 1; i++) {
+            e += seq_update(ix, iy, rho, u, v, alpha2, i, 0, nx, ny);
+            e += seq_update(ix, iy, rho, u, v, alpha2, i, nx - 1, nx, ny);
+        }
+        e += seq_update(ix, iy, rho, u, v, alpha2, 0, 0, nx, ny);
+        e += seq_update(ix, iy, rho, u, v, alpha2, 0, nx - 1, nx, ny);
+        e += seq_update(ix, iy, rho, u, v, alpha2, ny - 1, 0, nx, ny);
+        e += seq_update(ix, iy, rho, u, v, alpha2, ny - 1, nx - 1, nx, ny);
+        error = sqrt(e / (nx * ny));
+    }
+    if (err_out) *err_out = error;
+    return niter;
+}
+
+// The kernel's schedule.  order: 0 ascending thread ids, 1 descending, 2 shuffled per phase.
+// phase: 0 all fetches of a step then all updates, 1 per thread fetch + update, 2 all updates then
+// all fetches.  land: see EmuCp.  Returns the number of sweeps, or -1 for unsupported sizes.
+int hs_emu_wave_sor(float *u, float *v, const float *ix, const float *iy, const float *rho, int nx, int ny,
+                    float alpha2, double tol, int maxiter, int P, int nthreads, int order, int phase,
+                    int land, unsigned seed, double *err_out)
+{
+    if (nx < 3 || ny < 3 || P < 0 || P > hs::kMaxPrefetch || nthreads < 1) return -1;
+    const size_t n = (size_t) nx * ny;
+    std::vector<float> wu(n), wv(n), wix(n), wiy(n), wrho(n);
+    to_wave(u, wu.data(), nx, ny);
+    to_wave(v, wv.data(), nx, ny);
+    to_wave(ix, wix.data(), nx, ny);
+    to_wave(iy, wiy.data(), nx, ny);
+    to_wave(rho, wrho.data(), nx, ny);
+
+    hs::SorView V;
+    V.wu = wu.data(); V.wv = wv.data(); V.wix = wix.data(); V.wiy = wiy.data(); V.wrho = wrho.data();
+    V.nx = nx; V.ny = ny; V.alpha2 = alpha2;
+    V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = ny + 3;
+    // poison the rings: a read of a slot that was never fetched shows up as NaN in the result
+    std::vector<float> ring((size_t) (2 * V.S + 3 * V.CD) * V.rp, nanf(""));
+    V.ring_u = ring.data();
+    V.ring_v = V.ring_u + (size_t) V.S * V.rp;
+    V.cix = V.ring_v + (size_t) V.S * V.rp;
+    V.ciy = V.cix + (size_t) V.CD * V.rp;
+    V.crho = V.ciy + (size_t) V.CD * V.rp;
+
+    EmuCp cp;
+    cp.land = land;
+    Rng rng{ seed * 2654435761ull + 12345 };
+    std::vector<int> ord(nthreads);
+    int niter = 0;
+    double error = 1000;
+    while (error > tol && niter < maxiter) {
+        niter++;
+        std::vector<double> esum(nthreads, 0.0);
+        for (int t = hs::first_step(V); t <= hs::last_step(V); t++) {
+            cp.wait(P);                                     // cp.async.wait_group P; __syncthreads()
+            const hs::Step s = hs::make_step(V, t);
+            auto fetch = [&](int tid) { for (int i = tid; i < ny; i += nthreads) hs::issue_row(V, s, i, cp); };
+            auto update = [&](int tid) {
+                if (t >= 3) for (int i = tid; i < ny; i += nthreads) esum[tid] += hs::compute_row(V, s, i);
+            };
+            if (phase == 0) {
+                thread_order(ord, order, rng); for (int tid : ord) fetch(tid);
+                thread_order(ord, order, rng); for (int tid : ord) update(tid);
+            } else if (phase == 1) {
+                thread_order(ord, order, rng); for (int tid : ord) { fetch(tid); update(tid); }
+            } else {
+                thread_order(ord, order, rng); for (int tid : ord) update(tid);
+                thread_order(ord, order, rng); for (int tid : ord) fetch(tid);
+            }
+            cp.commit();                                    // one group per step (every thread commits)
+        }
+        cp.wait(0);                                         // cp.async.wait_group 0; __syncthreads()
+        double e = hs::corners(V);                          // thread 0
+        for (int tid = 0; tid < nthreads; tid++) e += esum[tid];
+        error = sqrt(e / (nx * ny));
+    }
+    from_wave(wu.data(), u, nx, ny);
+    from_wave(wv.data(), v, nx, ny);
+    if (err_out) *err_out = error;
+    return niter;
+}
+
+} // extern "C"
