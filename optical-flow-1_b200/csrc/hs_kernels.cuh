@@ -1,0 +1,206 @@
+// Device kernels of the pyramidal Horn-Schunck path (src/horn_schunck_pyramidal.cpp).
+// The pyramid, the warp (k_warp gives I2wx, I2wy and rho_c = -(I1 - I2w + I2wx u + I2wy v), which is
+// all the linear system of :127-137 is made of) and the flow up-sampling are the TV-L1 kernels of
+// tvl1_kernels.cuh; what is new is the SOR sweep.
+//
+//   k_hs_to_wave    row-major planes (u, v, I2wx, I2wy, rho_c) -> wave layout (hs_sor_step.h)
+//   k_hs_sor<P>     the whole `while (error > TOL && niter < maxiter)` loop of one warp step,
+//                   one CTA per frame pair, lexicographic Gauss-Seidel order kept exactly by a
+//                   wavefront schedule; no host round trip, no second launch
+//   k_hs_from_wave  wave layout (u, v) -> row-major planes
+#pragma once
+#include "hs_sor_step.h"
+#include "tvl1_kernels.cuh"
+
+namespace tvl1 {
+
+constexpr int kHsMaxThreads = 1024;
+constexpr size_t kHsSmemLimit = 227 * 1024;
+
+// Bytes of shared memory the rings of k_hs_sor<P> take for `rp` padded rows.
+__host__ __device__ inline size_t hs_ring_bytes(int P, int rp)
+{
+    return (size_t) (2 * (hs::kRingBase + P) + 3 * (P + 2)) * rp * sizeof(float);
+}
+
+struct HsSorParams {
+    float *state;                 // state[set][field][b][plane0]; the wave planes live in the idle set
+    size_t plane0, field_stride, set_stride;
+    const PairCtl *ctl;
+    int nx, ny, rp;
+    float alpha2;
+    double tol;
+    int max_iter;
+    int *stat_iters;
+    double *stat_errs;
+    int stat_stride, stat_slot;
+    unsigned long long *px_iters; // [level] pixel-iterations
+    int level;
+};
+
+// Tile transposes between the row-major pitched planes and the wave layout
+//   W[((j + 2i) mod nx) * ny + i] = plane[i * pitch + j].
+// A CTA moves a 32 x 32 tile of (wave column c, row i): row-major side coalesced along j (= c - 2i,
+// consecutive in c), wave side coalesced along i.
+__global__ void __launch_bounds__(256)
+k_hs_to_wave(float *__restrict__ state, const float *__restrict__ consts, size_t plane0, size_t field_stride,
+             size_t set_stride, const PairCtl *__restrict__ ctl, Level lv)
+{
+    __shared__ float tile[5][32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
+    const int b = blockIdx.z;
+    const int cur = ctl[b].cur;
+    const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
+    const int c0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const float *src[5];
+    src[0] = state + (size_t) cur * set_stride + (size_t) F_U1 * field_stride + (size_t) b * plane0;
+    src[1] = state + (size_t) cur * set_stride + (size_t) F_U2 * field_stride + (size_t) b * plane0;
+    src[2] = consts + (size_t) C_IX * field_stride + (size_t) b * plane0;
+    src[3] = consts + (size_t) C_IY * field_stride + (size_t) b * plane0;
+    src[4] = consts + (size_t) C_RHO * field_stride + (size_t) b * plane0;
+    float *dst = state + (size_t) (cur ^ 1) * set_stride + (size_t) b * plane0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = i0 + ty + 8 * r, c = c0 + tx;
+        if (i < ny && c < nx) {
+            const int j = hs::pmod(c - 2 * i, nx);
+            const int o = i * pitch + j;
+#pragma unroll
+            for (int k = 0; k < 5; k++) tile[k][ty + 8 * r][tx] = src[k][o];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int c = c0 + ty + 8 * r, i = i0 + tx;
+        if (i < ny && c < nx) {
+            const size_t o = (size_t) c * ny + i;
+#pragma unroll
+            for (int k = 0; k < 5; k++) dst[(size_t) k * field_stride + o] = tile[k][tx][ty + 8 * r];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_hs_from_wave(float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
+               const PairCtl *__restrict__ ctl, Level lv)
+{
+    __shared__ float tile[2][32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
+    const int b = blockIdx.z;
+    const int cur = ctl[b].cur;
+    const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
+    const int c0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const float *src = state + (size_t) (cur ^ 1) * set_stride + (size_t) b * plane0;
+    float *dst = state + (size_t) cur * set_stride + (size_t) b * plane0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int c = c0 + ty + 8 * r, i = i0 + tx;
+        if (i < ny && c < nx) {
+            const size_t o = (size_t) c * ny + i;
+            tile[0][ty + 8 * r][tx] = src[o];
+            tile[1][ty + 8 * r][tx] = src[field_stride + o];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = i0 + ty + 8 * r, c = c0 + tx;
+        if (i < ny && c < nx) {
+            const int j = hs::pmod(c - 2 * i, nx);
+            const int o = i * pitch + j;
+            dst[(size_t) F_U1 * field_stride + o] = tile[0][tx][ty + 8 * r];
+            dst[(size_t) F_U2 * field_stride + o] = tile[1][tx][ty + 8 * r];
+        }
+    }
+}
+
+struct HsCpAsync {
+    __device__ __forceinline__ void cp4(float *dst, const float *src) { cp_async4(dst, src); }
+};
+
+template <int N>
+__device__ __forceinline__ void hs_cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
+// One CTA per frame pair runs the complete SOR loop of a warp step (src/horn_schunck_pyramidal.cpp:
+// 139-231).  Thread tid owns rows tid, tid + blockDim.x, ...; a sweep is the time-step loop of
+// hs_sor_step.h with one __syncthreads per step; wave columns of u, v and of the coefficients are
+// fetched P steps ahead with cp.async into shared-memory rings.  The squared-update sum is reduced
+// in fp64 in a fixed order, so the stopping decision does not depend on scheduling.
+template <int P>
+__global__ void __launch_bounds__(kHsMaxThreads)
+k_hs_sor(HsSorParams A)
+{
+    extern __shared__ __align__(16) float hs_smem[];
+    __shared__ hs::Step s_step[2];
+    __shared__ double s_red[kHsMaxThreads / 32];
+    __shared__ double s_err;
+    __shared__ int s_go;
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int b = blockIdx.x;
+    const int nx = A.nx, ny = A.ny;
+    float *wave = A.state + (size_t) (A.ctl[b].cur ^ 1) * A.set_stride + (size_t) b * A.plane0;
+
+    hs::SorView V;
+    V.wu = wave;
+    V.wv = wave + A.field_stride;
+    V.wix = wave + 2 * A.field_stride;
+    V.wiy = wave + 3 * A.field_stride;
+    V.wrho = wave + 4 * A.field_stride;
+    V.nx = nx; V.ny = ny; V.alpha2 = A.alpha2;
+    V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = A.rp;
+    V.ring_u = hs_smem;
+    V.ring_v = V.ring_u + (size_t) V.S * V.rp;
+    V.cix = V.ring_v + (size_t) V.S * V.rp;
+    V.ciy = V.cix + (size_t) V.CD * V.rp;
+    V.crho = V.ciy + (size_t) V.CD * V.rp;
+
+    HsCpAsync cp;
+    const int t_first = hs::first_step(V), t_last = hs::last_step(V);
+    int niter = 0;
+    while (true) {
+        niter++;
+        double e = 0.0;
+        if (tid == 0) s_step[0] = hs::make_step(V, t_first);
+        for (int t = t_first, k = 0; t <= t_last; t++, k ^= 1) {
+            hs_cp_async_wait<P>();
+            __syncthreads();
+            const hs::Step &s = s_step[k];
+            if (tid == 0) {                      // next step's indices, published by the next barrier
+                hs::Step n = s;
+                hs::advance(V, n);
+                s_step[k ^ 1] = n;
+            }
+            for (int i = tid; i < ny; i += nthreads) hs::issue_row(V, s, i, cp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (t >= 3)
+                for (int i = tid; i < ny; i += nthreads) e += hs::compute_row(V, s, i);
+        }
+        hs_cp_async_wait<0>();
+        __syncthreads();
+        if (tid == 0) e += hs::corners(V);
+        e = warp_sum(e);
+        if ((tid & 31) == 0) s_red[tid >> 5] = e;
+        __syncthreads();
+        if (tid == 0) {
+            double sum = 0.0;
+            for (int w = 0; w < (nthreads + 31) / 32; w++) sum += s_red[w];
+            const double error = sqrt(sum / (double) (nx * ny));        // :230
+            s_err = error;
+            s_go = (error > A.tol && niter < A.max_iter) ? 1 : 0;       // :143
+        }
+        __syncthreads();
+        if (!s_go) break;
+    }
+    if (tid == 0) {
+        A.stat_iters[(size_t) b * A.stat_stride + A.stat_slot] = niter;
+        A.stat_errs[(size_t) b * A.stat_stride + A.stat_slot] = s_err;
+        atomicAdd(A.px_iters + A.level, (unsigned long long) niter * (unsigned long long) (nx * ny));
+    }
+}
+
+} // namespace tvl1

@@ -1,0 +1,322 @@
+// Host side of include/hs_b200.h: the coarse-to-fine driver (src/horn_schunck_pyramidal.cpp:258-370)
+// and the per-level driver (:78-249) of the pyramidal Horn-Schunck method on top of the TV-L1 path's
+// workspace, pyramid, warp and up-sampling kernels.  Included by tvl1_solver.cu (one translation unit,
+// the kernels are shared).
+#pragma once
+
+namespace {
+
+// Prefetch distance of k_hs_sor for a level: the largest P <= kMaxPrefetch whose rings fit one SM.
+int hs_pick_prefetch(int ny, int want)
+{
+    const int rp = round_up(ny, 32);
+    if (want >= 0 && want <= hs::kMaxPrefetch) return hs_ring_bytes(want, rp) <= kHsSmemLimit - 4096 ? want : -1;
+    for (int P = hs::kMaxPrefetch; P >= 0; P--)
+        if (hs_ring_bytes(P, rp) <= kHsSmemLimit - 4096) return P;
+    return -1;
+}
+
+int hs_check_level(tvl1_ctx *ctx, const Level &l)
+{
+    if (l.nx < 3 || l.ny < 3) return fail_arg(ctx, "Horn-Schunck: every pyramid level needs nx >= 3 and ny >= 3");
+    if (l.ny > HS_MAX_ROWS || hs_pick_prefetch(l.ny, -1) < 0)
+        return fail_arg(ctx, "Horn-Schunck: image has more rows than this build supports (HS_MAX_ROWS)");
+    return TVL1_OK;
+}
+
+template <int P>
+int hs_launch_sor_p(tvl1_ctx *ctx, const HsSorParams &A, int B, int threads, size_t smem)
+{
+    static bool attr_done[64] = { false };
+    if (!attr_done[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(k_hs_sor<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kHsSmemLimit - 4096)));
+        attr_done[ctx->device & 63] = true;
+    }
+    k_hs_sor<P><<<B, threads, smem, ctx->stream>>>(A);
+    CKL(ctx);
+    return TVL1_OK;
+}
+
+// The SOR loop of one warp step for every pair of the batch: one launch, one CTA per pair.
+int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_slot, int prefetch = -1)
+{
+    const Workspace &w = ctx->ws;
+    const Level &l = w.lv[s];
+    const int P = hs_pick_prefetch(l.ny, prefetch);
+    if (P < 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
+    HsSorParams A = {};
+    A.state = w.state; A.plane0 = w.plane0; A.field_stride = w.field_stride; A.set_stride = w.set_stride;
+    A.ctl = w.ctl;
+    A.nx = l.nx; A.ny = l.ny; A.rp = round_up(l.ny, 32);
+    A.alpha2 = (float) (prm.alpha * prm.alpha);                             // :99
+    A.tol = prm.tol; A.max_iter = prm.maxiter;
+    A.stat_iters = w.stat_iters; A.stat_errs = w.stat_errs;
+    A.stat_stride = w.stat_stride; A.stat_slot = stat_slot;
+    A.px_iters = w.counters; A.level = std::min(s, TVL1_MAX_LEVELS - 1);
+    // rows per thread as even as possible: ceil(ny / ceil(ny / 1024)) threads, whole warps
+    const int rows_per_thread = ceil_div(l.ny, kHsMaxThreads);
+    const int threads = std::min(kHsMaxThreads, round_up(ceil_div(l.ny, rows_per_thread), 32));
+    const size_t smem = hs_ring_bytes(P, A.rp);
+    switch (P) {
+    case 0: TRY(hs_launch_sor_p<0>(ctx, A, B, threads, smem)); break;
+    case 1: TRY(hs_launch_sor_p<1>(ctx, A, B, threads, smem)); break;
+    case 2: TRY(hs_launch_sor_p<2>(ctx, A, B, threads, smem)); break;
+    default: TRY(hs_launch_sor_p<3>(ctx, A, B, threads, smem)); break;
+    }
+    ctx->stats.iterate_launches++;
+    return TVL1_OK;
+}
+
+int hs_launch_to_wave(tvl1_ctx *ctx, int s, int B)
+{
+    const Workspace &w = ctx->ws;
+    const Level &l = w.lv[s];
+    dim3 g(ceil_div(l.nx, 32), ceil_div(l.ny, 32), B);
+    k_hs_to_wave<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.consts, w.plane0, w.field_stride, w.set_stride,
+                                                     w.ctl, l);
+    CKL(ctx);
+    return TVL1_OK;
+}
+
+int hs_launch_from_wave(tvl1_ctx *ctx, int s, int B)
+{
+    const Workspace &w = ctx->ws;
+    const Level &l = w.lv[s];
+    dim3 g(ceil_div(l.nx, 32), ceil_div(l.ny, 32), B);
+    k_hs_from_wave<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, l);
+    CKL(ctx);
+    return TVL1_OK;
+}
+
+// One pyramid level: horn_schunck_optical_flow, src/horn_schunck_pyramidal.cpp:78-249, for every pair.
+int hs_run_level(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_base)
+{
+    for (int wi = 0; wi < prm.warps; wi++) {                                // :117
+        {
+            Span sp(ctx, 1);
+            TRY(launch_warp(ctx, s, B));                                    // :114, :123-125, dif of :130
+        }
+        Span sp(ctx, 0, std::min(s, TVL1_MAX_LEVELS - 1));
+        TRY(hs_launch_to_wave(ctx, s, B));
+        TRY(hs_launch_sor(ctx, s, B, prm, stat_base + wi));                 // :127-137 (on the fly), :139-231
+        TRY(hs_launch_from_wave(ctx, s, B));
+    }
+    return TVL1_OK;
+}
+
+tvl1_params hs_as_tvl1(const hs_params &prm, bool multiscale)
+{
+    // the pyramid builder and the argument checks only look at nscales, zfactor and warps
+    tvl1_params t{ 0.25, 0.15, 0.3, multiscale ? prm.nscales : 1, multiscale ? prm.zfactor : 0.5, prm.warps, prm.tol };
+    return t;
+}
+
+int hs_check_params(tvl1_ctx *ctx, const hs_params *prm)
+{
+    if (!ctx) return TVL1_ERR_ARG;
+    if (!prm) return fail_arg(ctx, "null pointer argument");
+    if (!(prm->alpha > 0.0)) return fail_arg(ctx, "alpha must be positive");
+    if (prm->maxiter < 1) return fail_arg(ctx, "maxiter must be >= 1");
+    return TVL1_OK;
+}
+
+// horn_schunck_pyramidal for B <= max_batch pairs, device-resident dense inputs / outputs.
+int run_hs_multiscale(tvl1_ctx *ctx, int B, const float *dI1, const float *dI2, float *du, float *dv, int nx,
+                      int ny, const hs_params &prm, int *iters_out, double *errs_out)
+{
+    const int ns = prm.nscales;
+    const int nstat = ns * prm.warps;
+    const tvl1_params tp = hs_as_tvl1(prm, true);
+    TRY(ensure_workspace(ctx, nx, ny, ns, prm.zfactor, B, nstat));
+    Workspace &w = ctx->ws;
+    for (int s = 0; s < ns; s++) TRY(hs_check_level(ctx, w.lv[s]));
+    cudaStream_t st = ctx->stream;
+
+    Span total(ctx, 2);
+    TRY(build_pyramid(ctx, B, dI1, dI2, nx, ny, tp));                        // :293-317
+    TRY(launch_zero(ctx, ns - 1, B, F_U1, 2));                              // :320-323
+    for (int s = ns - 1; s >= 0; s--) {                                     // :326-353
+        TRY(hs_run_level(ctx, s, B, prm, (ns - 1 - s) * prm.warps));
+        if (!s) break;
+        const Level &c = w.lv[s], &f = w.lv[s - 1];
+        Span zs(ctx, 4);
+        dim3 g(ceil_div(f.nx, kZiTW), ceil_div(f.ny, kZiTH), B);
+        k_zoom_in_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, c, f,
+                                                  (double) f.nx / c.nx, (double) f.ny / c.ny,
+                                                  (float) (1.0 / prm.zfactor), 0, f.ny);   // :345-352
+        CKL(ctx);
+        k_flip_cur<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, B);
+        CKL(ctx);
+    }
+    {
+        Span ex(ctx, 5);
+        dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
+        k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0],
+                                                 du, dv);
+        CKL(ctx);
+    }
+    total.end();
+    TRY(fetch_stats(ctx, B, nstat, iters_out, errs_out));
+    return TVL1_OK;
+}
+
+// horn_schunck_optical_flow (one level, no normalisation / blur), device-resident dense buffers.
+int run_hs_single_scale(tvl1_ctx *ctx, int B, const float *dI1, const float *dI2, float *du, float *dv, int nx,
+                        int ny, const hs_params &prm, int *iters_out, double *errs_out)
+{
+    TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, B, prm.warps));
+    Workspace &w = ctx->ws;
+    TRY(hs_check_level(ctx, w.lv[0]));
+    cudaStream_t st = ctx->stream;
+    Span total(ctx, 2);
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
+    CKL(ctx);
+    dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
+    k_pack<<<g, dim3(32, 8), 0, st>>>(dI1, w.I0(0), nx, ny, w.lv[0].pitch, w.plane(0));
+    CKL(ctx);
+    k_pack<<<g, dim3(32, 8), 0, st>>>(dI2, w.I1(0), nx, ny, w.lv[0].pitch, w.plane(0));
+    CKL(ctx);
+    k_import_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0], du, dv);
+    CKL(ctx);
+    TRY(hs_run_level(ctx, 0, B, prm, 0));
+    k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0], du, dv);
+    CKL(ctx);
+    total.end();
+    TRY(fetch_stats(ctx, B, prm.warps, iters_out, errs_out));
+    return TVL1_OK;
+}
+
+template <typename T>
+int hs_solve_host(tvl1_ctx *ctx, int npairs, const T *I1, const T *I2, T *u, T *v, int nx, int ny,
+                  const hs_params *prm, int *iters_out, double *errs_out, bool multiscale)
+{
+    TRY(hs_check_params(ctx, prm));
+    const tvl1_params tp = hs_as_tvl1(*prm, multiscale);
+    ctx->hs_mode = true;
+    ctx->hs = *prm;
+    const int rc = solve_host<T>(ctx, npairs, I1, I2, u, v, nx, ny, &tp, iters_out, errs_out, multiscale);
+    ctx->hs_mode = false;
+    return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+void hs_default_params(hs_params *p)
+{
+    if (!p) return;
+    p->alpha = 7; p->nscales = 10; p->zfactor = 0.5; p->warps = 10; p->tol = 0.0001; p->maxiter = 150;
+}
+
+int hs_clamp_nscales(int nx, int ny, int nscales, double zfactor)
+{
+    const double N = 1 + std::log(std::hypot((double) nx, (double) ny) / 16) / std::log(1 / zfactor);
+    if (N < nscales) nscales = (int) N;
+    return nscales;
+}
+
+int hs_solve_f32(tvl1_ctx *ctx, const float *I1, const float *I2, float *u, float *v, int nx, int ny,
+                 const hs_params *prm, int *iters_out, double *errs_out)
+{
+    return hs_solve_host<float>(ctx, 1, I1, I2, u, v, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int hs_solve_f64(tvl1_ctx *ctx, const double *I1, const double *I2, double *u, double *v, int nx, int ny,
+                 const hs_params *prm, int *iters_out, double *errs_out)
+{
+    return hs_solve_host<double>(ctx, 1, I1, I2, u, v, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int hs_solve_batch_f32(tvl1_ctx *ctx, int npairs, const float *I1, const float *I2, float *u, float *v, int nx,
+                       int ny, const hs_params *prm, int *iters_out, double *errs_out)
+{
+    return hs_solve_host<float>(ctx, npairs, I1, I2, u, v, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int hs_solve_batch_dev_f32(tvl1_ctx *ctx, int npairs, const float *dI1, const float *dI2, float *du, float *dv,
+                           int nx, int ny, const hs_params *prm, int *iters_out, double *errs_out)
+{
+    TRY(hs_check_params(ctx, prm));
+    const tvl1_params tp = hs_as_tvl1(*prm, true);
+    TRY(check_common(ctx, dI1, dI2, du, dv, nx, ny, &tp, true));
+    if (npairs < 1) return fail_arg(ctx, "npairs must be >= 1");
+    reset_stats(ctx);
+    const hs_params hp = *prm;
+    const size_t n = (size_t) nx * ny;
+    const int nstat = hp.nscales * hp.warps;
+    const int Bmax = std::min(npairs, ctx->max_batch);
+    return run_lanes(ctx, ceil_div(npairs, Bmax), ctx->dev_lanes, [&](tvl1_ctx *c, int k) -> int {
+        const int first = k * Bmax, B = std::min(Bmax, npairs - first);
+        const size_t off = (size_t) first * n;
+        return run_hs_multiscale(c, B, dI1 + off, dI2 + off, du + off, dv + off, nx, ny, hp,
+                                 iters_out ? iters_out + (size_t) first * nstat : nullptr,
+                                 errs_out ? errs_out + (size_t) first * nstat : nullptr);
+    });
+}
+
+int hs_single_scale_f32(tvl1_ctx *ctx, const float *I1, const float *I2, float *u, float *v, int nx, int ny,
+                        const hs_params *prm, int *iters_out, double *errs_out)
+{
+    return hs_solve_host<float>(ctx, 1, I1, I2, u, v, nx, ny, prm, iters_out, errs_out, false);
+}
+
+int hs_single_scale_f64(tvl1_ctx *ctx, const double *I1, const double *I2, double *u, double *v, int nx, int ny,
+                        const hs_params *prm, int *iters_out, double *errs_out)
+{
+    return hs_solve_host<double>(ctx, 1, I1, I2, u, v, nx, ny, prm, iters_out, errs_out, false);
+}
+
+int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float *rho_c, float *u, float *v,
+               int nx, int ny, double alpha, double tol, int maxiter, int prefetch, int *niter_out,
+               double *err_out)
+{
+    if (!ctx) return TVL1_ERR_ARG;
+    if (!I2wx || !I2wy || !rho_c || !u || !v) return fail_arg(ctx, "null pointer argument");
+    if (!(alpha > 0.0) || maxiter < 1) return fail_arg(ctx, "alpha must be positive and maxiter >= 1");
+    if (prefetch > hs::kMaxPrefetch) return fail_arg(ctx, "prefetch must be -1 or 0..3");
+    CK(cudaSetDevice(ctx->device));
+    reset_stats(ctx);
+    TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1));
+    Workspace &w = ctx->ws;
+    TRY(hs_check_level(ctx, w.lv[0]));
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t) nx * ny;
+    Dev d(ctx->stream);
+    float *buf = d.alloc(5 * n);
+    if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
+    const float *src[5] = { u, v, I2wx, I2wy, rho_c };
+    for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(buf + k * n, src[k], n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
+    CKL(ctx);
+    const dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
+    // flow -> live set; I2wx, I2wy, rho_c -> the constant planes k_warp would have written
+    k_import_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0], buf,
+                                             buf + n);
+    CKL(ctx);
+    const int fields[3] = { C_IX, C_IY, C_RHO };
+    for (int k = 0; k < 3; k++) {
+        k_pack<<<g, dim3(32, 8), 0, st>>>(buf + (2 + k) * n, w.consts + (size_t) fields[k] * w.field_stride, nx, ny,
+                                          w.lv[0].pitch, w.plane0);
+        CKL(ctx);
+    }
+    hs_params prm{ alpha, 1, 0.5, 1, tol, maxiter };
+    TRY(hs_launch_to_wave(ctx, 0, 1));
+    TRY(hs_launch_sor(ctx, 0, 1, prm, 0, prefetch));
+    TRY(hs_launch_from_wave(ctx, 0, 1));
+    k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0], buf,
+                                             buf + n);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(u, buf, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(v, buf + n, n * 4, cudaMemcpyDeviceToHost, st));
+    int it = 0;
+    double er = 0;
+    TRY(fetch_stats(ctx, 1, 1, &it, &er));
+    if (niter_out) *niter_out = it;
+    if (err_out) *err_out = er;
+    return TVL1_OK;
+}
+
+} // extern "C"

@@ -33,6 +33,7 @@
 
 #if defined(__CUDACC__) && !defined(HS_SOR_EMULATE)
 #define HS_FN __device__ __forceinline__
+#define HS_FN_OUTLINE __device__ __noinline__
 #define hs_fma(a, b, c) __fmaf_rn((a), (b), (c))
 #define hs_mul(a, b) __fmul_rn((a), (b))
 #define hs_add(a, b) __fadd_rn((a), (b))
@@ -41,6 +42,7 @@
 #else
 #include <math.h>
 #define HS_FN static inline
+#define HS_FN_OUTLINE static
 #define hs_fma(a, b, c) fmaf((a), (b), (c))
 #define hs_mul(a, b) ((float) ((float) (a) * (float) (b)))
 #define hs_add(a, b) ((float) ((float) (a) + (float) (b)))
@@ -67,40 +69,67 @@ struct SorView {
     int S, CD, rp, P;                         // S = 8 + P, CD = P + 2, rp >= ny
 };
 
-// What one time step needs of the modular arithmetic, computed once per thread and step.
+// What one time step needs of the modular arithmetic, computed once per thread and step: make_step
+// does the divisions, advance() goes from step t to t + 1 with increments and wrap-arounds only.
 struct Step {
     int t;
-    int ld_ok, ld_a, ld_col, ld_slot;         // ring fetch of wave column a = t + 4 + P
-    int cf_ok, cf_t, cf_col, cf_slot;         // coefficient fetch for time t + 1 + P
-    int slot[7];                              // ring offsets of wave columns t-3 .. t+3
-    int wr_col;                               // global offset of wave column t
-    int cslot;                                // coefficient ring offset of time t
+    int ld_a, ld_m, ld_r;                     // ring fetch of wave column a = t + 4 + P: a mod nx, a mod S
+    int cf_t, cf_m, cf_r;                     // coefficient fetch for time t + 1 + P: mod nx, mod CD
+    int r0;                                   // (t - 3) mod S: ring slot of wave column t - 3
+    int wr_m;                                 // t mod nx: wave column the new values of this step go to
+    int c_r;                                  // t mod CD: coefficient ring slot of this step
+    int slot[7];                              // ring offsets (floats) of wave columns t-3 .. t+3
+    int ld_col, ld_slot, cf_col, cf_slot, wr_col, cslot;   // the same as float offsets
 };
 
+HS_FN int pmod(int x, int m) { const int r = x % m; return r < 0 ? r + m : r; }
 HS_FN int wave_index(int i, int j, int nx, int ny) { return ((j + 2 * i) % nx) * ny + i; }
+
+HS_FN void finish_step(const SorView &V, Step &s)
+{
+    for (int k = 0; k < 7; k++) {
+        int r = s.r0 + k;
+        if (r >= V.S) r -= V.S;
+        s.slot[k] = r * V.rp;
+    }
+    s.ld_col = s.ld_m * V.ny;
+    s.ld_slot = s.ld_r * V.rp;
+    s.cf_col = s.cf_m * V.ny;
+    s.cf_slot = s.cf_r * V.rp;
+    s.wr_col = s.wr_m * V.ny;
+    s.cslot = s.c_r * V.rp;
+}
 
 HS_FN Step make_step(const SorView &V, int t)
 {
     Step s;
     s.t = t;
     s.ld_a = t + 4 + V.P;
-    s.ld_ok = s.ld_a >= 0;
-    s.ld_col = s.ld_ok ? (s.ld_a % V.nx) * V.ny : 0;
-    s.ld_slot = s.ld_ok ? (s.ld_a % V.S) * V.rp : 0;
+    s.ld_m = pmod(s.ld_a, V.nx);
+    s.ld_r = pmod(s.ld_a, V.S);
     s.cf_t = t + 1 + V.P;
-    s.cf_ok = s.cf_t >= 3;
-    s.cf_col = s.cf_ok ? (s.cf_t % V.nx) * V.ny : 0;
-    s.cf_slot = s.cf_ok ? (s.cf_t % V.CD) * V.rp : 0;
-    if (t >= 3) {
-        for (int k = 0; k < 7; k++) s.slot[k] = ((t - 3 + k) % V.S) * V.rp;
-        s.wr_col = (t % V.nx) * V.ny;
-        s.cslot = (t % V.CD) * V.rp;
-    } else {
-        for (int k = 0; k < 7; k++) s.slot[k] = 0;
-        s.wr_col = 0;
-        s.cslot = 0;
-    }
+    s.cf_m = pmod(s.cf_t, V.nx);
+    s.cf_r = pmod(s.cf_t, V.CD);
+    s.r0 = pmod(t - 3, V.S);
+    s.wr_m = pmod(t, V.nx);
+    s.c_r = pmod(t, V.CD);
+    finish_step(V, s);
     return s;
+}
+
+HS_FN void advance(const SorView &V, Step &s)
+{
+    s.t++;
+    s.ld_a++;
+    s.cf_t++;
+    if (++s.ld_m == V.nx) s.ld_m = 0;
+    if (++s.ld_r == V.S) s.ld_r = 0;
+    if (++s.cf_m == V.nx) s.cf_m = 0;
+    if (++s.cf_r == V.CD) s.cf_r = 0;
+    if (++s.r0 == V.S) s.r0 = 0;
+    if (++s.wr_m == V.nx) s.wr_m = 0;
+    if (++s.c_r == V.CD) s.c_r = 0;
+    finish_step(V, s);
 }
 
 // One SOR update, src/horn_schunck_pyramidal.cpp:31-71.  d* = diagonal neighbours in the order the
@@ -130,7 +159,7 @@ HS_FN float sor_px(float ix, float iy, float rho, float alpha2, float ud0, float
 // Border pixel (i, j) through global memory: index-clamped 8-neighbourhood, which is what every
 // border call site of :160-228 passes -- except the bottom-right corner (:223-228), whose diagonal
 // arguments come in the order (left, self, up-left, up); floating-point sums follow that order.
-HS_FN float update_global(const SorView &V, int i, int j)
+HS_FN_OUTLINE float update_global(const SorView &V, int i, int j)
 {
     const int nx = V.nx, ny = V.ny;
     const int im = i > 0 ? i - 1 : 0, ip = i < ny - 1 ? i + 1 : ny - 1;
@@ -157,14 +186,14 @@ HS_FN float update_global(const SorView &V, int i, int j)
 template <class Cp>
 HS_FN void issue_row(const SorView &V, const Step &s, int i, Cp &cp)
 {
-    if (s.ld_ok) {
+    {
         const int j = s.ld_a - 2 * i;
         if (j >= 0 && j <= V.nx - 1) {
             cp.cp4(V.ring_u + s.ld_slot + i, V.wu + s.ld_col + i);
             cp.cp4(V.ring_v + s.ld_slot + i, V.wv + s.ld_col + i);
         }
     }
-    if (s.cf_ok && i >= 1) {
+    if (i >= 1) {
         const int j = s.cf_t - 2 * i;
         if (j >= 1 && j <= V.nx - 2) {
             cp.cp4(V.cix + s.cf_slot + i, V.wix + s.cf_col + i);

@@ -5,7 +5,9 @@
 // device per pair.  The host only decides how many launches to enqueue before it looks at the
 // "pairs still iterating" counter again.
 #include "../../include/tvl1_b200.h"
+#include "../../include/hs_b200.h"
 #include "tvl1_kernels.cuh"
+#include "hs_kernels.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -132,6 +134,10 @@ struct tvl1_ctx {
     void *pipe_buf[2] = { nullptr, nullptr };      // pinned staging ring for pageable host buffers
     cudaEvent_t pipe_ev[2] = { nullptr, nullptr };
     int sm_count = 148;
+    // Horn-Schunck entry points (include/hs_b200.h) reuse the host-buffer drivers below: while hs_mode
+    // is set, a chunk is solved by run_hs_multiscale / run_hs_single_scale with these parameters
+    bool hs_mode = false;
+    hs_params hs{};
 };
 
 namespace {
@@ -1047,6 +1053,11 @@ int download_pageable(tvl1_ctx *ctx, T *dst, const float *src, size_t count)
     return TVL1_OK;
 }
 
+int run_hs_multiscale(tvl1_ctx *ctx, int B, const float *dI1, const float *dI2, float *du, float *dv, int nx,
+                      int ny, const hs_params &prm, int *iters_out, double *errs_out);
+int run_hs_single_scale(tvl1_ctx *ctx, int B, const float *dI1, const float *dI2, float *du, float *dv, int nx,
+                        int ny, const hs_params &prm, int *iters_out, double *errs_out);
+
 // One chunk of <= max_batch pairs through one lane (context): H2D, solve, D2H, all on the lane's
 // stream.  I1 == nullptr selects the frame-sequence form: I0 holds consecutive frames, pair b is
 // (frame b, frame b+1), and the chunk's B+1 frames cross PCIe once.
@@ -1089,7 +1100,10 @@ int solve_chunk(tvl1_ctx *ctx, int first, int B, const T *I0, const T *I1, T *u1
     }
     int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
     double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
-    if (multiscale) TRY(run_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
+    if (ctx->hs_mode) {
+        if (multiscale) TRY(run_hs_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, ctx->hs, it, er));
+        else TRY(run_hs_single_scale(ctx, B, d0, d1, o0, o1, nx, ny, ctx->hs, it, er));
+    } else if (multiscale) TRY(run_multiscale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
     else TRY(run_single_scale(ctx, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
     auto get = [&](T *h, void *dev_T, const float *dev_f32) -> int {
         if (use_ring<T>(cnt) && is_pageable(h)) return download_pageable<T>(ctx, h, dev_f32, cnt);
@@ -1145,6 +1159,8 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
         sb->profiling = ctx->profiling;
         sb->use_graph = ctx->use_graph;
         sb->use_resident = ctx->use_resident;
+        sb->hs_mode = ctx->hs_mode;
+        sb->hs = ctx->hs;
         reset_stats(sb);
         lanes[l] = sb;
     }
@@ -1560,6 +1576,8 @@ struct Dev {
 };
 
 } // namespace
+
+#include "hs_solver.cuh"
 
 // =================================================================================================
 // C ABI

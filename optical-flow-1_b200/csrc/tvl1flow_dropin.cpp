@@ -25,6 +25,7 @@
 // (:185-187) on stderr; I0/I1 are not modified; u1/u2 are fully overwritten (multiscale) or
 // used as the initial flow (single level).
 #include "../../include/tvl1_b200.h"
+#include "../../include/hs_b200.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -121,6 +122,68 @@ void single_scale(T *I0, T *I1, T *u1, T *u2, int nx, int ny, double tau, double
     if (verbose) print_level(warps, iters.data(), errs.data());
 }
 
+// ---- pyramidal Horn-Schunck (src/horn_schunck.h:15-48) -------------------------------------------
+// Verbose output as the reference prints it: the parameter banners (src/horn_schunck_pyramidal.cpp:
+// 92-96, :274-278), "Scale: %d %dx%d" (:328) and, per warp, "Warping %d:" + "Iterations %d (%g)"
+// (:118-120, :233-235).
+void hs_print_level(int nx, int ny, double alpha, int warps, double TOL, int maxiter, const int *iters,
+                    const double *errs)
+{
+    fprintf(stderr, "Single-scale Horn-Schunck of a %dx%d image\n\ta=%g nw=%d eps=%g mi=%d v=%d\n", nx, ny,
+            alpha, warps, TOL, maxiter, 1);
+    for (int w = 0; w < warps; w++) fprintf(stderr, "Warping %d:Iterations %d (%g)\n", w, iters[w], errs[w]);
+}
+
+template <typename T>
+void hs_pyramidal(const T *I1, const T *I2, T *u, T *v, int nx, int ny, double alpha, int nscales, double zfactor,
+                  int warps, double TOL, int maxiter, bool verbose)
+{
+    tvl1_ctx *ctx = thread_ctx();
+    hs_params p{ alpha, nscales, zfactor, warps, TOL, maxiter };
+    std::vector<int> iters((size_t) nscales * warps);
+    std::vector<double> errs((size_t) nscales * warps);
+    if (verbose)
+        fprintf(stderr, "Multiscale Horn-Schunck of a %dx%d pair\n\ta=%g ns=%d zf=%g nw=%d eps=%g mi=%d\n", nx, ny,
+                alpha, nscales, zfactor, warps, TOL, maxiter);
+    int rc;
+    if (sizeof(T) == 8)
+        rc = hs_solve_f64(ctx, (const double *) I1, (const double *) I2, (double *) u, (double *) v, nx, ny, &p,
+                          iters.data(), errs.data());
+    else
+        rc = hs_solve_f32(ctx, (const float *) I1, (const float *) I2, (float *) u, (float *) v, nx, ny, &p,
+                          iters.data(), errs.data());
+    if (rc != TVL1_OK) raise(ctx, rc);
+    if (verbose) {
+        std::vector<int> sx(nscales), sy(nscales);
+        sx[0] = nx; sy[0] = ny;
+        for (int s = 1; s < nscales; s++) tvl1_zoom_size(sx[s - 1], sy[s - 1], &sx[s], &sy[s], zfactor);
+        for (int s = nscales - 1; s >= 0; s--) {
+            fprintf(stderr, "Scale: %d %dx%d\n", s, sx[s], sy[s]);
+            const size_t k = (size_t) (nscales - 1 - s) * warps;
+            hs_print_level(sx[s], sy[s], alpha, warps, TOL, maxiter, iters.data() + k, errs.data() + k);
+        }
+    }
+}
+
+template <typename T>
+void hs_one_level(const T *I1, const T *I2, T *u, T *v, int nx, int ny, double alpha, int warps, double TOL,
+                  int maxiter, bool verbose)
+{
+    tvl1_ctx *ctx = thread_ctx();
+    hs_params p{ alpha, 1, 0.5, warps, TOL, maxiter };
+    std::vector<int> iters(warps);
+    std::vector<double> errs(warps);
+    int rc;
+    if (sizeof(T) == 8)
+        rc = hs_single_scale_f64(ctx, (const double *) I1, (const double *) I2, (double *) u, (double *) v, nx, ny,
+                                 &p, iters.data(), errs.data());
+    else
+        rc = hs_single_scale_f32(ctx, (const float *) I1, (const float *) I2, (float *) u, (float *) v, nx, ny, &p,
+                                 iters.data(), errs.data());
+    if (rc != TVL1_OK) raise(ctx, rc);
+    if (verbose) hs_print_level(nx, ny, alpha, warps, TOL, maxiter, iters.data(), errs.data());
+}
+
 } // namespace
 
 // Selects the GPU for the calling thread's drop-in calls (declared in include/tvl1_b200.h).
@@ -175,4 +238,34 @@ extern "C" void Dual_TVL1_optic_flow(float *I0, float *I1, float *u1, float *u2,
                                      const bool verbose)
 {
     single_scale<float>(I0, I1, u1, u2, nx, ny, tau, lambda, theta, warps, epsilon, verbose);
+}
+
+// ---- pyramidal Horn-Schunck: src/horn_schunck.h:15-48, ofpix_t = double (as shipped) and float ------
+// _Z22horn_schunck_pyramidalPKdS0_PdS1_iidididib, _Z25horn_schunck_optical_flowPKdS0_PdS1_iididib
+void horn_schunck_pyramidal(const double *I1, const double *I2, double *u, double *v, const int nx, const int ny,
+                            const double alpha, const int nscales, const double zfactor, const int warps,
+                            const double TOL, const int maxiter, const bool verbose)
+{
+    hs_pyramidal<double>(I1, I2, u, v, nx, ny, alpha, nscales, zfactor, warps, TOL, maxiter, verbose);
+}
+
+void horn_schunck_optical_flow(const double *I1, const double *I2, double *u, double *v, const int nx,
+                               const int ny, const double alpha, const int warps, const double TOL,
+                               const int maxiter, const bool verbose)
+{
+    hs_one_level<double>(I1, I2, u, v, nx, ny, alpha, warps, TOL, maxiter, verbose);
+}
+
+void horn_schunck_pyramidal(const float *I1, const float *I2, float *u, float *v, const int nx, const int ny,
+                            const double alpha, const int nscales, const double zfactor, const int warps,
+                            const double TOL, const int maxiter, const bool verbose)
+{
+    hs_pyramidal<float>(I1, I2, u, v, nx, ny, alpha, nscales, zfactor, warps, TOL, maxiter, verbose);
+}
+
+void horn_schunck_optical_flow(const float *I1, const float *I2, float *u, float *v, const int nx, const int ny,
+                               const double alpha, const int warps, const double TOL, const int maxiter,
+                               const bool verbose)
+{
+    hs_one_level<float>(I1, I2, u, v, nx, ny, alpha, warps, TOL, maxiter, verbose);
 }

@@ -159,9 +159,10 @@ int hs_emu_wave_sor(float *u, float *v, const float *ix, const float *iy, const 
     while (error > tol && niter < maxiter) {
         niter++;
         std::vector<double> esum(nthreads, 0.0);
-        for (int t = hs::first_step(V); t <= hs::last_step(V); t++) {
+        hs::Step s = hs::make_step(V, hs::first_step(V));
+        for (int t = hs::first_step(V); t <= hs::last_step(V); t++, hs::advance(V, s)) {
             cp.wait(P);                                     // cp.async.wait_group P; __syncthreads()
-            const hs::Step s = hs::make_step(V, t);
+            if (memcmp(&s, &(const hs::Step &) hs::make_step(V, t), sizeof s) != 0) return -2;
             auto fetch = [&](int tid) { for (int i = tid; i < ny; i += nthreads) hs::issue_row(V, s, i, cp); };
             auto update = [&](int tid) {
                 if (t >= 3) for (int i = tid; i < ny; i += nthreads) esum[tid] += hs::compute_row(V, s, i);

@@ -13,6 +13,7 @@ import optical_flow_1_b200 as pkg
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "tvl1_b200.h")
+HS_HEADER = os.path.join(ROOT, "include", "hs_b200.h")
 
 # src/tvl1flow.h:36-70 with ofpix_t = double (src/of.h:4-10), and the float variant
 MANGLED = [
@@ -23,6 +24,12 @@ MANGLED = [
     # the upstream C99 library's C-linkage names (3rdparty/tvl1flow_3/tvl1flow_lib.c:45-59, :299-314)
     "Dual_TVL1_optic_flow_multiscale",
     "Dual_TVL1_optic_flow",
+    # src/horn_schunck.h:15-48 with ofpix_t = double (the names `nm` shows on the compiled reference,
+    # oracle/_ref/libof_ref_f64.so) and the float variant
+    "_Z22horn_schunck_pyramidalPKdS0_PdS1_iidididib",
+    "_Z25horn_schunck_optical_flowPKdS0_PdS1_iididib",
+    "_Z22horn_schunck_pyramidalPKfS0_PfS1_iidididib",
+    "_Z25horn_schunck_optical_flowPKfS0_PfS1_iididib",
 ]
 
 
@@ -34,9 +41,12 @@ def lib():
 
 
 def declared_functions():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(tvl1_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for path, prefix in ((HEADER, "tvl1_"), (HS_HEADER, "hs_")):
+        src = open(path).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names.update(re.findall(r"\b(%s[a-z0-9_]+)\s*\(" % prefix, src))
+    return sorted(names)
 
 
 def test_header_declares_the_expected_surface():
@@ -44,7 +54,10 @@ def test_header_declares_the_expected_surface():
     for must in ("tvl1_create", "tvl1_destroy", "tvl1_solve_f32", "tvl1_solve_f64",
                  "tvl1_solve_batch_f32", "tvl1_solve_batch_f64", "tvl1_solve_batch_dev_f32",
                  "tvl1_single_scale_f32", "tvl1_single_scale_f64", "tvl1_warp_f32",
-                 "tvl1_iterate_f32", "tvl1_gaussian_f32", "tvl1_zoom_out_f32", "tvl1_zoom_in_f32"):
+                 "tvl1_iterate_f32", "tvl1_gaussian_f32", "tvl1_zoom_out_f32", "tvl1_zoom_in_f32",
+                 "hs_solve_f32", "hs_solve_f64", "hs_solve_batch_f32", "hs_solve_batch_dev_f32",
+                 "hs_single_scale_f32", "hs_single_scale_f64", "hs_sor_f32", "hs_default_params",
+                 "hs_clamp_nscales"):
         assert must in names
 
 
@@ -59,8 +72,34 @@ def test_library_exports_reference_cxx_symbols(lib):
 
 
 def test_no_torch_types_in_the_abi():
-    src = open(HEADER).read()
-    assert "torch" not in src.lower() and "at::" not in src and "c10::" not in src
+    for path in (HEADER, HS_HEADER):
+        src = open(path).read()
+        assert "torch" not in src.lower() and "at::" not in src and "c10::" not in src
+
+
+def test_reference_mangled_names_are_those_of_the_compiled_reference():
+    """The drop-in names above are not hand-mangled: they are what the unmodified reference objects
+    export (present where oracle/_ref was built)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libof_ref_f64.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run(["nm", "-D", "--defined-only", ref], capture_output=True, text=True).stdout
+    for name in MANGLED:
+        if "Pd" in name:
+            assert name in out, name
+
+
+def test_hs_default_params_and_nscales_rule(lib):
+    p = pkg.HsParams()
+    lib.hs_default_params(C.byref(p))
+    # src/horn_schunck_pyramidal_main.cpp:25-30
+    assert (p.alpha, p.nscales, p.zfactor, p.warps, p.tol, p.maxiter) == (7.0, 10, 0.5, 10, 1e-4, 150)
+    lib.hs_clamp_nscales.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
+    # src/horn_schunck_pyramidal_main.cpp:136-143
+    for nx, ny, ns, zf in [(640, 480, 10, 0.5), (1920, 1080, 10, 0.5), (64, 48, 10, 0.5), (640, 480, 3, 0.5),
+                           (1024, 436, 10, 0.7)]:
+        assert lib.hs_clamp_nscales(nx, ny, ns, zf) == pkg.hs_clamp_nscales(nx, ny, ns, zf)
+    assert pkg.hs_clamp_nscales(640, 480, 10, 0.5) == 6
 
 
 def test_zoom_size_matches_oracle(lib, oracle_f64):

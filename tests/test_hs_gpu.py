@@ -1,0 +1,199 @@
+"""GPU parity tests of the pyramidal Horn-Schunck path (include/hs_b200.h) through the C ABI.
+
+* the SOR kernel against the sequential lexicographic sweep in the same fp32 arithmetic: BIT-EXACT
+  (the wavefront schedule must not change a single neighbour value);
+* the solver against the committed golden vectors of the unmodified reference (one thread) and
+  against the oracle: identical sweep counts per (level, warp), flow within the tolerance
+  BASELINE.json's north_star states for the fp32 path (mean |d| <= 1e-3 px, max |d| <= 1e-2 px);
+* batch = individual solves bit for bit; fp64 entry point and the reference's mangled C++ symbols.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import _cases
+import _hs_emu
+import optical_flow_1_b200 as pkg
+from oracle.loader import CpuTvl1, available
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MEAN_TOL = 1e-3
+MAX_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    g = pkg.HornSchunck(device=0)
+    yield g
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def hs_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "hs_reference_vectors.npz"))
+
+
+def assert_flow_close(u, v, ru, rv, what=""):
+    d = np.concatenate([np.abs(u.astype(np.float64) - ru).ravel(), np.abs(v.astype(np.float64) - rv).ravel()])
+    assert d.mean() <= MEAN_TOL and d.max() <= MAX_TOL, "%s mean|d|=%g max|d|=%g" % (what, d.mean(), d.max())
+
+
+# ---- the SOR kernel -----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("nx,ny", [(3, 3), (4, 3), (3, 9), (9, 3), (5, 7), (37, 29), (64, 48), (131, 70), (33, 200)])
+@pytest.mark.parametrize("prefetch", [-1, 0, 1, 2, 3])
+def test_sor_kernel_is_the_sequential_sweep_bitwise(gpu, nx, ny, prefetch):
+    ix, iy, rho, u, v, _ = _hs_emu.system(nx, ny, seed=nx * 100 + ny)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, 0.0, 7)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=0.0, maxiter=7, prefetch=prefetch)
+    assert gn == rn == 7
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv), (np.abs(gu - ru).max(), np.abs(gv - rv).max())
+    assert abs(gerr - rerr) <= 1e-9 * max(1.0, rerr)
+
+
+def test_sor_kernel_rows_beyond_one_thread_each(gpu):
+    """More rows than threads of a CTA (1024): threads own rows tid and tid + blockDim."""
+    nx, ny = 40, 1100
+    ix, iy, rho, u, v, _ = _hs_emu.system(nx, ny, seed=9)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, 0.0, 3)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=0.0, maxiter=3)
+    assert gn == rn
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv)
+
+
+@pytest.mark.parametrize("tol", [1e-1, 1e-2, 1e-3])
+def test_sor_kernel_stops_like_the_reference_loop(gpu, oracle_f64, tol):
+    """while (error > TOL && niter < maxiter), src/horn_schunck_pyramidal.cpp:143: same sweep count as the
+    sequential fp32 loop and as the fp64 oracle, flow at fp32 rounding level of the oracle's."""
+    ix, iy, rho, u, v, x = _hs_emu.system(96, 80, seed=3)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, tol, 150)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=tol, maxiter=150)
+    assert 1 < rn < 150 and gn == rn
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv)
+    assert gerr <= tol
+    sysm = oracle_f64.hs_system(x["I1"], x["I2w"], x["I2wx"], x["I2wy"], x["u"], x["v"], 7.0)
+    ou, ov, on, oerr = oracle_f64.hs_sor(*sysm, x["u"], x["v"], 7.0, tol=tol, maxiter=150)
+    assert on == gn
+    assert np.abs(gu - ou).max() < 5e-4 and np.abs(gv - ov).max() < 5e-4
+
+
+def test_sor_kernel_rejects_unsupported_sizes(gpu):
+    z = np.zeros((2, 8), np.float32)
+    with pytest.raises(pkg.TVL1Error) as e:
+        gpu.sor(z, z, z, z, z)
+    assert e.value.code == 3
+
+
+# ---- the solver ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", sorted(_cases.HS_CASES))
+def test_hs_solver_matches_golden(gpu, hs_golden, name):
+    case = _cases.HS_CASES[name]
+    I1, I2 = _cases.solver_inputs(case)
+    u, v, iters, errs = gpu.horn_schunck_pyramidal(I1.astype(np.float32), I2.astype(np.float32), **case["kw"])
+    pre = "f64/%s/" % name
+    assert np.array_equal(iters, hs_golden[pre + "iters"]), (iters, hs_golden[pre + "iters"])
+    assert_flow_close(u, v, hs_golden[pre + "u"], hs_golden[pre + "v"], name)
+    assert np.allclose(errs, hs_golden[pre + "errs"], rtol=2e-2, atol=1e-6)
+
+
+def test_hs_single_scale_matches_oracle(gpu, oracle_f64):
+    I1, I2 = _cases.synth.make_pair(72, 56, seed=21, scale=0.3)
+    rs = np.random.RandomState(1)
+    u0 = rs.uniform(-0.5, 0.5, I1.shape)
+    v0 = rs.uniform(-0.5, 0.5, I1.shape)
+    ru, rv, rit, rerr = oracle_f64.hs_single_scale(I1, I2, u0, v0, alpha=7.0, warps=3, tol=1e-3, maxiter=100)
+    u, v, it, err = gpu.horn_schunck_optical_flow(I1.astype(np.float32), I2.astype(np.float32), u0, v0, alpha=7.0,
+                                                  warps=3, tol=1e-3, maxiter=100)
+    assert np.array_equal(it, rit), (it, rit)
+    assert_flow_close(u, v, ru, rv, "single scale")
+
+
+def test_hs_batch_equals_individual_solves(gpu):
+    kw = dict(alpha=7.0, nscales=3, zfactor=0.5, warps=3, tol=1e-3, maxiter=40)
+    pairs = [_cases.synth.make_pair(80, 60, seed=50 + b, scale=0.4) for b in range(5)]
+    I1 = np.stack([p[0] for p in pairs]).astype(np.float32)
+    I2 = np.stack([p[1] for p in pairs]).astype(np.float32)
+    bu, bv, bit, berr = gpu.horn_schunck_pyramidal(I1, I2, **kw)
+    for b in range(5):
+        u, v, it, err = gpu.horn_schunck_pyramidal(I1[b], I2[b], **kw)
+        assert np.array_equal(it, bit[b])
+        assert np.array_equal(u, bu[b]) and np.array_equal(v, bv[b])
+    # chunks smaller than the batch (lanes, ragged last chunk) give the same bits
+    gpu.set_max_batch(2)
+    try:
+        cu, cv, cit, _ = gpu.horn_schunck_pyramidal(I1, I2, **kw)
+    finally:
+        gpu.set_max_batch(32)
+    assert np.array_equal(cit, bit) and np.array_equal(cu, bu) and np.array_equal(cv, bv)
+
+
+def test_hs_after_tvl1_on_the_same_context(gpu):
+    """Both solvers share a context's workspace: alternating them must not leak state."""
+    I1, I2 = _cases.synth.make_pair(64, 48, seed=1234, scale=0.5)
+    I1, I2 = I1.astype(np.float32), I2.astype(np.float32)
+    kw = dict(alpha=7.0, nscales=3, zfactor=0.5, warps=2, tol=1e-3, maxiter=30)
+    a = gpu.horn_schunck_pyramidal(I1, I2, **kw)
+    t = gpu.Dual_TVL1_optic_flow_multiscale(I1, I2, nscales=3, warps=2)
+    b = gpu.horn_schunck_pyramidal(I1, I2, **kw)
+    t2 = gpu.Dual_TVL1_optic_flow_multiscale(I1, I2, nscales=3, warps=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(t[0], t2[0]) and np.array_equal(t[2], t2[2])
+
+
+@pytest.mark.skipif(not available("reference", np.float64), reason="oracle/_ref not built")
+def test_hs_vga_default_parameters_against_the_compiled_reference(gpu):
+    """640x480 with the CLI's defaults (src/horn_schunck_pyramidal_main.cpp:25-30, nscales clamped by
+    :136-143) against the unmodified reference run with one thread."""
+    nx, ny = 640, 480
+    I1, I2 = _cases.synth.make_pair(nx, ny, seed=1234)
+    kw = dict(pkg.HS_DEFAULTS)
+    kw["nscales"] = pkg.hs_clamp_nscales(nx, ny, kw["nscales"], kw["zfactor"])
+    R = CpuTvl1("reference", np.float64)
+    ru, rv, rit, rerr = R.hs_multiscale(I1, I2, **kw)
+    u, v, it, err = gpu.horn_schunck_pyramidal(I1.astype(np.float32), I2.astype(np.float32), **kw)
+    assert np.array_equal(it, rit), (it - rit)
+    assert_flow_close(u, v, ru, rv, "640x480")
+    st = gpu.stats()
+    assert st["iterate_launches"] == kw["nscales"] * kw["warps"]
+    assert st["pixel_iterations"] > 0
+
+
+def test_hs_f64_entry_point_and_dropin_symbols(gpu):
+    """The reference's own C++ symbols (src/horn_schunck.h:15-48, ofpix_t = double) exported by the CUDA
+    library: same result as the C ABI's fp64 entry point, which is the fp32 path behind conversions."""
+    I1, I2 = _cases.synth.make_pair(64, 48, seed=1234, scale=0.5)
+    kw = dict(alpha=7.0, nscales=3, zfactor=0.5, warps=3, tol=1e-3, maxiter=40)
+    u32, v32, it32, _ = gpu.horn_schunck_pyramidal(I1.astype(np.float32), I2.astype(np.float32), **kw)
+    u64, v64, it64, _ = gpu.horn_schunck_pyramidal(I1, I2, **kw)
+    assert np.array_equal(it32, it64)
+    assert np.array_equal(u64.astype(np.float32), u32) and np.array_equal(v64.astype(np.float32), v32)
+    lib = C.CDLL(pkg.library_path())
+    fn = getattr(lib, "_Z22horn_schunck_pyramidalPKdS0_PdS1_iidididib")
+    fn.restype = None
+    fn.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_double,
+                                      C.c_int, C.c_bool]
+    a, b = np.ascontiguousarray(I1, np.float64), np.ascontiguousarray(I2, np.float64)
+    u, v = np.empty_like(a), np.empty_like(a)
+    fn(a.ctypes.data, b.ctypes.data, u.ctypes.data, v.ctypes.data, 64, 48, 7.0, 3, 0.5, 3, 1e-3, 40, False)
+    assert np.array_equal(u, u64) and np.array_equal(v, v64)
+    one = getattr(lib, "_Z25horn_schunck_optical_flowPKdS0_PdS1_iididib")
+    one.restype = None
+    one.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_bool]
+    u1 = np.zeros_like(a)
+    v1 = np.zeros_like(a)
+    one(a.ctypes.data, b.ctypes.data, u1.ctypes.data, v1.ctypes.data, 64, 48, 7.0, 2, 1e-3, 30, False)
+    g = gpu.horn_schunck_optical_flow(a, b, np.zeros_like(a), np.zeros_like(a), alpha=7.0, warps=2, tol=1e-3,
+                                      maxiter=30)
+    assert np.array_equal(u1, g[0]) and np.array_equal(v1, g[1])
+
+
+def test_hs_rejects_levels_the_sweep_cannot_run(gpu):
+    I = np.random.RandomState(0).uniform(0, 255, (40, 40)).astype(np.float32)
+    with pytest.raises(pkg.TVL1Error) as e:       # 40 -> 20 -> 10 -> 5 -> 3 -> 2: the last level is 2 wide
+        gpu.horn_schunck_pyramidal(I, I, nscales=6, warps=1, maxiter=2)
+    assert e.value.code in (2, 3)

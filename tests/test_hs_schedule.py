@@ -8,75 +8,27 @@ and the moment an asynchronous copy reads and lands.  The schedule is correct if
 the sequential lexicographic sweep of src/horn_schunck_pyramidal.cpp:144-230 bit for bit in every case.
 A second test ties that sequential fp32 sweep to the fp64 oracle.
 """
-import ctypes as C
-import os
-import subprocess
-
 import numpy as np
 import pytest
 
-import _cases
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "tests", "c", "hs_schedule_emu.cpp")
-HDR = os.path.join(ROOT, "optical-flow-1_b200", "csrc", "hs_sor_step.h")
-
-
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("hs_emu") / "libhs_emu.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra", "-Werror",
-                    "-shared", "-o", so, SRC, "-lm"], check=True)
-    lib = C.CDLL(so)
-    vp, i, f, d = C.c_void_p, C.c_int, C.c_float, C.c_double
-    lib.hs_emu_seq_sor.argtypes = [vp, vp, vp, vp, vp, i, i, f, d, i, C.POINTER(d)]
-    lib.hs_emu_seq_sor.restype = i
-    lib.hs_emu_wave_sor.argtypes = [vp, vp, vp, vp, vp, i, i, f, d, i, i, i, i, i, i, C.c_uint, C.POINTER(d)]
-    lib.hs_emu_wave_sor.restype = i
-    return lib
-
-
-def system(nx, ny, seed):
-    """Stored planes of the kernel: I2wx, I2wy, rho_c (= -dif) and a start flow, fp32."""
-    x = _cases.hs_sor_inputs(nx, ny, seed)
-    rho = -(x["I1"] - x["I2w"] + x["I2wx"] * x["u"] + x["I2wy"] * x["v"])
-    f = lambda a: np.ascontiguousarray(a, np.float32)
-    return f(x["I2wx"]), f(x["I2wy"]), f(rho), f(x["u"]), f(x["v"]), x
-
-
-def run_seq(emu, ix, iy, rho, u, v, alpha, tol, maxiter):
-    u, v = u.copy(), v.copy()
-    ny, nx = u.shape
-    err = C.c_double()
-    n = emu.hs_emu_seq_sor(u.ctypes.data, v.ctypes.data, ix.ctypes.data, iy.ctypes.data, rho.ctypes.data,
-                           nx, ny, alpha * alpha, tol, maxiter, C.byref(err))
-    return u, v, n, err.value
-
-
-def run_wave(emu, ix, iy, rho, u, v, alpha, tol, maxiter, P, nthreads, order, phase, land, seed=1):
-    u, v = u.copy(), v.copy()
-    ny, nx = u.shape
-    err = C.c_double()
-    n = emu.hs_emu_wave_sor(u.ctypes.data, v.ctypes.data, ix.ctypes.data, iy.ctypes.data, rho.ctypes.data,
-                            nx, ny, alpha * alpha, tol, maxiter, P, nthreads, order, phase, land, seed,
-                            C.byref(err))
-    return u, v, n, err.value
+import _hs_emu
+from _hs_emu import run_seq, run_wave, system
 
 
 SHAPES = [(3, 3), (4, 3), (3, 4), (5, 3), (3, 9), (9, 3), (4, 4), (5, 7), (8, 5), (12, 9), (37, 29), (64, 48), (23, 70)]
 
 
 @pytest.mark.parametrize("nx,ny", SHAPES)
-def test_wave_schedule_equals_sequential_sweep(emu, nx, ny):
+def test_wave_schedule_equals_sequential_sweep(nx, ny):
     ix, iy, rho, u, v, _ = system(nx, ny, seed=nx * 100 + ny)
-    ref = run_seq(emu, ix, iy, rho, u, v, 7.0, 0.0, 5)
+    ref = run_seq(ix, iy, rho, u, v, 7.0, 0.0, 5)
     assert ref[2] == 5 and np.isfinite(ref[0]).all()
     for P in range(4):
         for nthreads in sorted({1, 2, 3, max(1, ny // 2), ny, ny + 5}):
             for order in range(3):
                 for phase in range(3):
                     for land in range(3):
-                        got = run_wave(emu, ix, iy, rho, u, v, 7.0, 0.0, 5, P, nthreads, order, phase, land,
+                        got = run_wave(ix, iy, rho, u, v, 7.0, 0.0, 5, P, nthreads, order, phase, land,
                                        seed=P * 7 + order)
                         key = (P, nthreads, order, phase, land)
                         assert got[2] == ref[2], key
@@ -84,29 +36,29 @@ def test_wave_schedule_equals_sequential_sweep(emu, nx, ny):
                         assert abs(got[3] - ref[3]) <= 1e-12 * max(1.0, ref[3]), key
 
 
-def test_wave_schedule_stops_like_the_sequential_loop(emu):
+def test_wave_schedule_stops_like_the_sequential_loop():
     ix, iy, rho, u, v, _ = system(48, 40, seed=3)
     for tol in (1e-1, 1e-2, 1e-3):
-        ref = run_seq(emu, ix, iy, rho, u, v, 7.0, tol, 150)
-        got = run_wave(emu, ix, iy, rho, u, v, 7.0, tol, 150, 2, 16, 2, 1, 2)
+        ref = run_seq(ix, iy, rho, u, v, 7.0, tol, 150)
+        got = run_wave(ix, iy, rho, u, v, 7.0, tol, 150, 2, 16, 2, 1, 2)
         assert 1 < ref[2] < 150
         assert got[2] == ref[2]
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
 
 
-def test_unsupported_sizes_are_refused(emu):
+def test_unsupported_sizes_are_refused():
     ix, iy, rho, u, v, _ = system(5, 5, seed=1)
-    assert run_wave(emu, ix[:2], iy[:2], rho[:2], u[:2], v[:2], 7.0, 0.0, 1, 1, 4, 0, 0, 0)[2] == -1
+    assert run_wave(ix[:2], iy[:2], rho[:2], u[:2], v[:2], 7.0, 0.0, 1, 1, 4, 0, 0, 0)[2] == -1
 
 
 @pytest.mark.parametrize("nx,ny", [(37, 29), (64, 48)])
-def test_fp32_sequential_sweep_tracks_the_fp64_oracle(emu, oracle_f64, nx, ny):
+def test_fp32_sequential_sweep_tracks_the_fp64_oracle(oracle_f64, nx, ny):
     """The kernel's arithmetic (fp32, system formed from I2wx, I2wy, rho_c on the fly) against the
     oracle's (fp64, stored Au, Av, Du, Dv, D): same sweep, differences at fp32 rounding level."""
     ix, iy, rho, u, v, x = system(nx, ny, seed=11)
     sysm = oracle_f64.hs_system(x["I1"], x["I2w"], x["I2wx"], x["I2wy"], x["u"], x["v"], 7.0)
     ou, ov, on, oerr = oracle_f64.hs_sor(*sysm, x["u"], x["v"], 7.0, tol=1e-3, maxiter=150)
-    su, sv, sn, serr = run_seq(emu, ix, iy, rho, u, v, 7.0, 1e-3, 150)
+    su, sv, sn, serr = run_seq(ix, iy, rho, u, v, 7.0, 1e-3, 150)
     assert sn == on
     assert np.abs(su - ou).max() < 2e-4 and np.abs(sv - ov).max() < 2e-4
     assert abs(serr - oerr) < 1e-5
