@@ -25,7 +25,7 @@ __host__ __device__ inline size_t hs_ring_bytes(int P, int rp)
 
 struct HsSorParams {
     float *state;                 // state[set][field][b][plane0]; the wave planes live in the idle set
-    size_t plane0, field_stride, set_stride;
+    size_t plane0, set_stride;
     const PairCtl *ctl;
     int nx, ny, rp;
     float alpha2;
@@ -37,6 +37,14 @@ struct HsSorParams {
     unsigned long long *px_iters; // [level] pixel-iterations
     int level;
 };
+
+// Where the wave planes of pair b live: the idle ping-pong set of the state buffer (6 B plane0 floats),
+// re-partitioned per pair as [b][6 * plane0]:  (u, v) interleaved [2n] | (I2wx, I2wy) interleaved [2n] |
+// rho_c [n],  n = nx * ny <= plane0.
+__device__ __forceinline__ float *hs_wave_base(float *state, size_t set_stride, size_t plane0, int cur, int b)
+{
+    return state + (size_t) (cur ^ 1) * set_stride + (size_t) b * 6 * plane0;
+}
 
 // Tile transposes between the row-major pitched planes and the wave layout
 //   W[((j + 2i) mod nx) * ny + i] = plane[i * pitch + j].
@@ -58,7 +66,11 @@ k_hs_to_wave(float *__restrict__ state, const float *__restrict__ consts, size_t
     src[2] = consts + (size_t) C_IX * field_stride + (size_t) b * plane0;
     src[3] = consts + (size_t) C_IY * field_stride + (size_t) b * plane0;
     src[4] = consts + (size_t) C_RHO * field_stride + (size_t) b * plane0;
-    float *dst = state + (size_t) (cur ^ 1) * set_stride + (size_t) b * plane0;
+    const size_t n = (size_t) nx * ny;
+    float *base = hs_wave_base(state, set_stride, plane0, cur, b);
+    float2 *wuv = reinterpret_cast<float2 *>(base);
+    float2 *wxy = reinterpret_cast<float2 *>(base + 2 * n);
+    float *wrho = base + 4 * n;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int i = i0 + ty + 8 * r, c = c0 + tx;
@@ -75,8 +87,9 @@ k_hs_to_wave(float *__restrict__ state, const float *__restrict__ consts, size_t
         const int c = c0 + ty + 8 * r, i = i0 + tx;
         if (i < ny && c < nx) {
             const size_t o = (size_t) c * ny + i;
-#pragma unroll
-            for (int k = 0; k < 5; k++) dst[(size_t) k * field_stride + o] = tile[k][tx][ty + 8 * r];
+            wuv[o] = make_float2(tile[0][tx][ty + 8 * r], tile[1][tx][ty + 8 * r]);
+            wxy[o] = make_float2(tile[2][tx][ty + 8 * r], tile[3][tx][ty + 8 * r]);
+            wrho[o] = tile[4][tx][ty + 8 * r];
         }
     }
 }
@@ -91,15 +104,15 @@ k_hs_from_wave(float *__restrict__ state, size_t plane0, size_t field_stride, si
     const int cur = ctl[b].cur;
     const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
     const int c0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
-    const float *src = state + (size_t) (cur ^ 1) * set_stride + (size_t) b * plane0;
+    const float2 *wuv = reinterpret_cast<const float2 *>(hs_wave_base(state, set_stride, plane0, cur, b));
     float *dst = state + (size_t) cur * set_stride + (size_t) b * plane0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int c = c0 + ty + 8 * r, i = i0 + tx;
         if (i < ny && c < nx) {
-            const size_t o = (size_t) c * ny + i;
-            tile[0][ty + 8 * r][tx] = src[o];
-            tile[1][ty + 8 * r][tx] = src[field_stride + o];
+            const float2 uv = wuv[(size_t) c * ny + i];
+            tile[0][ty + 8 * r][tx] = uv.x;
+            tile[1][ty + 8 * r][tx] = uv.y;
         }
     }
     __syncthreads();
@@ -115,8 +128,14 @@ k_hs_from_wave(float *__restrict__ state, size_t plane0, size_t field_stride, si
     }
 }
 
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned int) __cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 struct HsCpAsync {
     __device__ __forceinline__ void cp4(float *dst, const float *src) { cp_async4(dst, src); }
+    __device__ __forceinline__ void cp8(float2 *dst, const float2 *src) { cp_async8(dst, src); }
 };
 
 template <int N>
@@ -135,7 +154,6 @@ __global__ void __launch_bounds__(kHsMaxThreads)
 k_hs_sor(HsSorParams A)
 {
     extern __shared__ __align__(16) float hs_smem[];
-    __shared__ hs::Step s_step[2];
     __shared__ double s_red[kHsMaxThreads / 32];
     __shared__ double s_err;
     __shared__ int s_go;
@@ -143,21 +161,18 @@ k_hs_sor(HsSorParams A)
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int b = blockIdx.x;
     const int nx = A.nx, ny = A.ny;
-    float *wave = A.state + (size_t) (A.ctl[b].cur ^ 1) * A.set_stride + (size_t) b * A.plane0;
+    float *wave = hs_wave_base(A.state, A.set_stride, A.plane0, A.ctl[b].cur, b);
+    const size_t n = (size_t) nx * ny;
 
     hs::SorView V;
-    V.wu = wave;
-    V.wv = wave + A.field_stride;
-    V.wix = wave + 2 * A.field_stride;
-    V.wiy = wave + 3 * A.field_stride;
-    V.wrho = wave + 4 * A.field_stride;
+    V.wuv = reinterpret_cast<float2 *>(wave);
+    V.wxy = reinterpret_cast<const float2 *>(wave + 2 * n);
+    V.wrho = wave + 4 * n;
     V.nx = nx; V.ny = ny; V.alpha2 = A.alpha2;
     V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = A.rp;
-    V.ring_u = hs_smem;
-    V.ring_v = V.ring_u + (size_t) V.S * V.rp;
-    V.cix = V.ring_v + (size_t) V.S * V.rp;
-    V.ciy = V.cix + (size_t) V.CD * V.rp;
-    V.crho = V.ciy + (size_t) V.CD * V.rp;
+    V.ring_uv = reinterpret_cast<float2 *>(hs_smem);
+    V.cxy = V.ring_uv + (size_t) V.S * V.rp;
+    V.crho = reinterpret_cast<float *>(V.cxy + (size_t) V.CD * V.rp);
 
     HsCpAsync cp;
     const int t_first = hs::first_step(V), t_last = hs::last_step(V);
@@ -165,16 +180,10 @@ k_hs_sor(HsSorParams A)
     while (true) {
         niter++;
         double e = 0.0;
-        if (tid == 0) s_step[0] = hs::make_step(V, t_first);
-        for (int t = t_first, k = 0; t <= t_last; t++, k ^= 1) {
+        hs::Step s = hs::make_step(V, t_first);
+        for (int t = t_first; t <= t_last; t++, hs::advance(V, s)) {
             hs_cp_async_wait<P>();
             __syncthreads();
-            const hs::Step &s = s_step[k];
-            if (tid == 0) {                      // next step's indices, published by the next barrier
-                hs::Step n = s;
-                hs::advance(V, n);
-                s_step[k ^ 1] = n;
-            }
             for (int i = tid; i < ny; i += nthreads) hs::issue_row(V, s, i, cp);
             asm volatile("cp.async.commit_group;" ::: "memory");
             if (t >= 3)

@@ -42,10 +42,12 @@ int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_sl
 {
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
+    if (prefetch < 0)
+        if (const char *e = std::getenv("HS_PREFETCH")) prefetch = std::atoi(e);   // measurements (profiles/run_hs.py)
     const int P = hs_pick_prefetch(l.ny, prefetch);
     if (P < 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
     HsSorParams A = {};
-    A.state = w.state; A.plane0 = w.plane0; A.field_stride = w.field_stride; A.set_stride = w.set_stride;
+    A.state = w.state; A.plane0 = w.plane0; A.set_stride = w.set_stride;
     A.ctl = w.ctl;
     A.nx = l.nx; A.ny = l.ny; A.rp = round_up(l.ny, 32);
     A.alpha2 = (float) (prm.alpha * prm.alpha);                             // :99

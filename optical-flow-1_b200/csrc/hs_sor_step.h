@@ -19,12 +19,15 @@
 // adversarial thread orders and copy-landing times and compares it bit for bit with the sequential
 // sweep).
 //
-// Storage: the five planes the sweep touches (u, v, I2wx, I2wy, rho_c) are kept in a *wave layout*,
+// Storage: the five planes the sweep touches are kept in a *wave layout*,
 //   element (i, j)  at  W[((j + 2i) mod nx) * ny + i],
 // so that the pixels of one time step are contiguous in i: every access of a step is coalesced.
+// u and v are interleaved (one 8-byte element per pixel), so are I2wx and I2wy; rho_c is a plane of its
+// own: 28 bytes per pixel and sweep, moved by three asynchronous copies, one 8-byte store and nine
+// 8-byte shared-memory loads.
 // A ring of S = 8 + P wave columns of u and v lives in shared memory (columns t-3 .. t+4+P at step t;
-// column a is fetched with cp.async at step a-4-P, P steps before its first use), and a ring of P + 2
-// coefficient columns.  Border pixels are rare and go through global memory.
+// column a is fetched with cp.async at step a-4-P and is complete P steps later, one step before its
+// first use), and a ring of P + 2 coefficient columns.  Border pixels are rare and go through global memory.
 //
 // This header is compiled twice: by nvcc into the kernel, and by g++ into the schedule emulator of
 // the tests (HS_SOR_EMULATE).  Arithmetic uses explicitly rounded fp32 operations in both, so the two
@@ -39,8 +42,10 @@
 #define hs_add(a, b) __fadd_rn((a), (b))
 #define hs_sub(a, b) __fsub_rn((a), (b))
 #define hs_div(a, b) __fdiv_rn((a), (b))
+namespace hs { typedef float2 F2; }
 #else
 #include <math.h>
+namespace hs { struct F2 { float x, y; }; }
 #define HS_FN static inline
 #define HS_FN_OUTLINE static
 #define hs_fma(a, b, c) fmaf((a), (b), (c))
@@ -60,76 +65,52 @@ constexpr int kRingBase = 8;                  // wave columns t-3 .. t+4 are liv
 constexpr int kMaxPrefetch = 3;
 
 struct SorView {
-    float *wu, *wv;                           // flow, wave layout, updated in place
-    const float *wix, *wiy, *wrho;            // I2wx, I2wy and rho_c = -(I1 - I2w + I2wx u + I2wy v), wave layout
+    F2 *wuv;                                  // flow (u, v), wave layout, updated in place
+    const F2 *wxy;                            // (I2wx, I2wy), wave layout
+    const float *wrho;                        // rho_c = -(I1 - I2w + I2wx u + I2wy v), wave layout
     int nx, ny;
     float alpha2;
-    float *ring_u, *ring_v;                   // [S][rp]
-    float *cix, *ciy, *crho;                  // [CD][rp]
+    F2 *ring_uv;                              // [S][rp]
+    F2 *cxy;                                  // [CD][rp]
+    float *crho;                              // [CD][rp]
     int S, CD, rp, P;                         // S = 8 + P, CD = P + 2, rp >= ny
 };
 
-// What one time step needs of the modular arithmetic, computed once per thread and step: make_step
-// does the divisions, advance() goes from step t to t + 1 with increments and wrap-arounds only.
+// The modular counters of a time step.  Every thread keeps its own copy in registers: make_step does
+// the divisions once per sweep, advance() goes from step t to t + 1 with increments and wrap-arounds.
 struct Step {
     int t;
-    int ld_a, ld_m, ld_r;                     // ring fetch of wave column a = t + 4 + P: a mod nx, a mod S
-    int cf_t, cf_m, cf_r;                     // coefficient fetch for time t + 1 + P: mod nx, mod CD
     int r0;                                   // (t - 3) mod S: ring slot of wave column t - 3
-    int wr_m;                                 // t mod nx: wave column the new values of this step go to
     int c_r;                                  // t mod CD: coefficient ring slot of this step
-    int slot[7];                              // ring offsets (floats) of wave columns t-3 .. t+3
-    int ld_col, ld_slot, cf_col, cf_slot, wr_col, cslot;   // the same as float offsets
+    int wr_m;                                 // t mod nx: wave column the new values of this step go to
+    int ld_m;                                 // (t + 4 + P) mod nx: wave column fetched into the ring at this step
+    int cf_m;                                 // (t + 1 + P) mod nx: wave column of the coefficients fetched
 };
 
 HS_FN int pmod(int x, int m) { const int r = x % m; return r < 0 ? r + m : r; }
+HS_FN int wrap(int x, int m) { return x >= m ? x - m : x; }      // for 0 <= x < 2m
 HS_FN int wave_index(int i, int j, int nx, int ny) { return ((j + 2 * i) % nx) * ny + i; }
-
-HS_FN void finish_step(const SorView &V, Step &s)
-{
-    for (int k = 0; k < 7; k++) {
-        int r = s.r0 + k;
-        if (r >= V.S) r -= V.S;
-        s.slot[k] = r * V.rp;
-    }
-    s.ld_col = s.ld_m * V.ny;
-    s.ld_slot = s.ld_r * V.rp;
-    s.cf_col = s.cf_m * V.ny;
-    s.cf_slot = s.cf_r * V.rp;
-    s.wr_col = s.wr_m * V.ny;
-    s.cslot = s.c_r * V.rp;
-}
 
 HS_FN Step make_step(const SorView &V, int t)
 {
     Step s;
     s.t = t;
-    s.ld_a = t + 4 + V.P;
-    s.ld_m = pmod(s.ld_a, V.nx);
-    s.ld_r = pmod(s.ld_a, V.S);
-    s.cf_t = t + 1 + V.P;
-    s.cf_m = pmod(s.cf_t, V.nx);
-    s.cf_r = pmod(s.cf_t, V.CD);
     s.r0 = pmod(t - 3, V.S);
-    s.wr_m = pmod(t, V.nx);
     s.c_r = pmod(t, V.CD);
-    finish_step(V, s);
+    s.wr_m = pmod(t, V.nx);
+    s.ld_m = pmod(t + 4 + V.P, V.nx);
+    s.cf_m = pmod(t + 1 + V.P, V.nx);
     return s;
 }
 
 HS_FN void advance(const SorView &V, Step &s)
 {
     s.t++;
-    s.ld_a++;
-    s.cf_t++;
-    if (++s.ld_m == V.nx) s.ld_m = 0;
-    if (++s.ld_r == V.S) s.ld_r = 0;
-    if (++s.cf_m == V.nx) s.cf_m = 0;
-    if (++s.cf_r == V.CD) s.cf_r = 0;
-    if (++s.r0 == V.S) s.r0 = 0;
-    if (++s.wr_m == V.nx) s.wr_m = 0;
-    if (++s.c_r == V.CD) s.c_r = 0;
-    finish_step(V, s);
+    s.r0 = wrap(s.r0 + 1, V.S);
+    s.c_r = wrap(s.c_r + 1, V.CD);
+    s.wr_m = wrap(s.wr_m + 1, V.nx);
+    s.ld_m = wrap(s.ld_m + 1, V.nx);
+    s.cf_m = wrap(s.cf_m + 1, V.nx);
 }
 
 // One SOR update, src/horn_schunck_pyramidal.cpp:31-71.  d* = diagonal neighbours in the order the
@@ -159,9 +140,10 @@ HS_FN float sor_px(float ix, float iy, float rho, float alpha2, float ud0, float
 // Border pixel (i, j) through global memory: index-clamped 8-neighbourhood, which is what every
 // border call site of :160-228 passes -- except the bottom-right corner (:223-228), whose diagonal
 // arguments come in the order (left, self, up-left, up); floating-point sums follow that order.
-HS_FN_OUTLINE float update_global(const SorView &V, int i, int j)
+// (Arguments by value: the caller's SorView stays in registers.)
+HS_FN_OUTLINE float update_global_px(F2 *wuv, const F2 *wxy, const float *wrho, int nx, int ny, float alpha2,
+                                     int i, int j)
 {
-    const int nx = V.nx, ny = V.ny;
     const int im = i > 0 ? i - 1 : 0, ip = i < ny - 1 ? i + 1 : ny - 1;
     const int jm = j > 0 ? j - 1 : 0, jp = j < nx - 1 ? j + 1 : nx - 1;
     int d0 = wave_index(im, jm, nx, ny), d1 = wave_index(im, jp, nx, ny);
@@ -172,33 +154,41 @@ HS_FN_OUTLINE float update_global(const SorView &V, int i, int j)
     if (i == ny - 1 && j == nx - 1) {
         d0 = a1; d1 = p; d2 = wave_index(im, jm, nx, ny); d3 = a0;
     }
-    float un, vn;
-    const float e = sor_px(V.wix[p], V.wiy[p], V.wrho[p], V.alpha2, V.wu[d0], V.wu[d1], V.wu[d2], V.wu[d3],
-                           V.wu[a0], V.wu[a1], V.wu[a2], V.wu[a3], V.wv[d0], V.wv[d1], V.wv[d2], V.wv[d3],
-                           V.wv[a0], V.wv[a1], V.wv[a2], V.wv[a3], V.wu[p], V.wv[p], &un, &vn);
-    V.wu[p] = un;
-    V.wv[p] = vn;
+    const F2 D0 = wuv[d0], D1 = wuv[d1], D2 = wuv[d2], D3 = wuv[d3];
+    const F2 A0 = wuv[a0], A1 = wuv[a1], A2 = wuv[a2], A3 = wuv[a3];
+    const F2 c = wuv[p], g = wxy[p];
+    F2 n;
+    const float e = sor_px(g.x, g.y, wrho[p], alpha2, D0.x, D1.x, D2.x, D3.x, A0.x, A1.x, A2.x, A3.x,
+                           D0.y, D1.y, D2.y, D3.y, A0.y, A1.y, A2.y, A3.y, c.x, c.y, &n.x, &n.y);
+    wuv[p] = n;
     return e;
 }
 
-// Fetches of row i at one step.  `Cp::cp4(dst, src)` is a 4-byte asynchronous global -> shared copy
-// (cp.async in the kernel, a queued copy in the emulator).
+HS_FN float update_global(const SorView &V, int i, int j)
+{
+    return update_global_px(V.wuv, V.wxy, V.wrho, V.nx, V.ny, V.alpha2, i, j);
+}
+
+// Fetches of row i at one step.  `Cp::cp8(dst, src)` / `Cp::cp4(dst, src)` are 8- and 4-byte asynchronous
+// global -> shared copies (cp.async in the kernel, queued copies in the emulator).
 template <class Cp>
 HS_FN void issue_row(const SorView &V, const Step &s, int i, Cp &cp)
 {
     {
-        const int j = s.ld_a - 2 * i;
+        // wave column a = t + 4 + P goes to the ring slot of column t - 4 (S = 8 + P), whose last reader
+        // was step t - 1
+        const int j = s.t + 4 + V.P - 2 * i;
         if (j >= 0 && j <= V.nx - 1) {
-            cp.cp4(V.ring_u + s.ld_slot + i, V.wu + s.ld_col + i);
-            cp.cp4(V.ring_v + s.ld_slot + i, V.wv + s.ld_col + i);
+            cp.cp8(V.ring_uv + wrap(s.r0 + V.S - 1, V.S) * V.rp + i, V.wuv + s.ld_m * V.ny + i);
         }
     }
     if (i >= 1) {
-        const int j = s.cf_t - 2 * i;
+        // coefficients of time t + 1 + P go to the slot of time t - 1 (CD = P + 2)
+        const int j = s.t + 1 + V.P - 2 * i;
         if (j >= 1 && j <= V.nx - 2) {
-            cp.cp4(V.cix + s.cf_slot + i, V.wix + s.cf_col + i);
-            cp.cp4(V.ciy + s.cf_slot + i, V.wiy + s.cf_col + i);
-            cp.cp4(V.crho + s.cf_slot + i, V.wrho + s.cf_col + i);
+            const int slot = wrap(s.c_r + V.CD - 1, V.CD) * V.rp + i, col = s.cf_m * V.ny + i;
+            cp.cp8(V.cxy + slot, V.wxy + col);
+            cp.cp4(V.crho + slot, V.wrho + col);
         }
     }
 }
@@ -211,24 +201,20 @@ HS_FN double compute_row(const SorView &V, const Step &s, int i)
     double e = 0.0;
     if (i >= 1 && j >= 1 && j <= nx - 2) {
         // interior row, or the last row (its lower neighbours clamp onto the row itself)
-        const float *ru = V.ring_u, *rv = V.ring_v;
-        const float u_ul = ru[s.slot[0] + i - 1], u_up = ru[s.slot[1] + i - 1], u_ur = ru[s.slot[2] + i - 1];
-        const float v_ul = rv[s.slot[0] + i - 1], v_up = rv[s.slot[1] + i - 1], v_ur = rv[s.slot[2] + i - 1];
-        const float u_l = ru[s.slot[2] + i], u_c = ru[s.slot[3] + i], u_r = ru[s.slot[4] + i];
-        const float v_l = rv[s.slot[2] + i], v_c = rv[s.slot[3] + i], v_r = rv[s.slot[4] + i];
-        float u_dl = u_l, u_d = u_c, u_dr = u_r, v_dl = v_l, v_d = v_c, v_dr = v_r;
-        if (i < ny - 1) {
-            u_dl = ru[s.slot[4] + i + 1]; u_d = ru[s.slot[5] + i + 1]; u_dr = ru[s.slot[6] + i + 1];
-            v_dl = rv[s.slot[4] + i + 1]; v_d = rv[s.slot[5] + i + 1]; v_dr = rv[s.slot[6] + i + 1];
-        }
-        float un, vn;
-        e += (double) sor_px(V.cix[s.cslot + i], V.ciy[s.cslot + i], V.crho[s.cslot + i], V.alpha2,
-                             u_ul, u_ur, u_dl, u_dr, u_up, u_l, u_d, u_r,
-                             v_ul, v_ur, v_dl, v_dr, v_up, v_l, v_d, v_r, u_c, v_c, &un, &vn);
-        V.ring_u[s.slot[3] + i] = un;
-        V.ring_v[s.slot[3] + i] = vn;
-        V.wu[s.wr_col + i] = un;
-        V.wv[s.wr_col + i] = vn;
+        const F2 *ring = V.ring_uv + i;
+        int so[7];                                // ring offsets of wave columns t-3 .. t+3
+        for (int k = 0; k < 7; k++) so[k] = wrap(s.r0 + k, V.S) * V.rp;
+        const F2 ul = ring[so[0] - 1], up = ring[so[1] - 1], ur = ring[so[2] - 1];
+        const F2 l = ring[so[2]], c = ring[so[3]], r = ring[so[4]];
+        F2 dl = l, d = c, dr = r;
+        if (i < ny - 1) { dl = ring[so[4] + 1]; d = ring[so[5] + 1]; dr = ring[so[6] + 1]; }
+        const int cslot = s.c_r * V.rp + i;
+        const F2 g = V.cxy[cslot];
+        F2 n;
+        e += (double) sor_px(g.x, g.y, V.crho[cslot], V.alpha2, ul.x, ur.x, dl.x, dr.x, up.x, l.x, d.x, r.x,
+                             ul.y, ur.y, dl.y, dr.y, up.y, l.y, d.y, r.y, c.x, c.y, &n.x, &n.y);
+        V.ring_uv[so[3] + i] = n;
+        V.wuv[s.wr_m * V.ny + i] = n;
     }
     if (i >= 1 && i <= ny - 2) {
         if (j == 4) e += (double) update_global(V, i, 0);

@@ -36,7 +36,7 @@ for rep in range(2):
                                      want_iters=True, **kw)
     st = g.stats()
 sweep_bytes = 28.0 * st["pixel_iterations"]
-res = dict(npairs=npairs, nx=nx, ny=ny, params=kw, total_ms=st["total_ms"], sor_ms=st["iterate_ms"],
+res = dict(prefetch_env=os.environ.get('HS_PREFETCH'), npairs=npairs, nx=nx, ny=ny, params=kw, total_ms=st["total_ms"], sor_ms=st["iterate_ms"],
            warp_ms=st["warp_ms"], pyramid_ms=st["pyramid_ms"], zoom_in_ms=st["zoom_in_ms"],
            kernel_launches=st["kernel_launches"], sor_launches=st["iterate_launches"],
            pixel_sweeps=st["pixel_iterations"], pairs_per_s=npairs / (st["total_ms"] * 1e-3),

@@ -21,24 +21,28 @@
 
 namespace {
 
-struct Pending { float *dst; const float *src; float value; int group; };
+struct Pending { float *dst; const float *src; float value[2]; int n; int group; };
 
 struct EmuCp {
     std::vector<Pending> q;
     int group = 0;
     int land = 0;          // 0: read + write at issue; 1: read at issue, write at completion; 2: both at completion
-    void cp4(float *dst, const float *src)
+    void copy(float *dst, const float *src, int n)
     {
-        if (land == 0) { *dst = *src; return; }
-        q.push_back(Pending{ dst, src, *src, group });
+        if (land == 0) { for (int k = 0; k < n; k++) dst[k] = src[k]; return; }
+        Pending p{ dst, src, { src[0], n > 1 ? src[1] : 0.f }, n, group };
+        q.push_back(p);
     }
+    void cp4(float *dst, const float *src) { copy(dst, src, 1); }
+    void cp8(hs::F2 *dst, const hs::F2 *src) { copy(&dst->x, &src->x, 2); }
     void commit() { group++; }
     // cp.async.wait_group n: at most the n most recently committed groups stay pending
     void wait(int n)
     {
         size_t keep = 0;
         for (size_t k = 0; k < q.size(); k++) {
-            if (q[k].group < group - n) *q[k].dst = (land == 1) ? q[k].value : *q[k].src;
+            if (q[k].group < group - n)
+                for (int c = 0; c < q[k].n; c++) q[k].dst[c] = (land == 1) ? q[k].value[c] : q[k].src[c];
             else q[keep++] = q[k];
         }
         q.resize(keep);
@@ -56,18 +60,6 @@ void thread_order(std::vector<int> &ord, int mode, Rng &rng)
     for (int k = 0; k < n; k++) ord[k] = k;
     if (mode == 1) std::reverse(ord.begin(), ord.end());
     if (mode == 2) for (int k = n - 1; k > 0; k--) std::swap(ord[k], ord[rng.next() % (k + 1)]);
-}
-
-void to_wave(const float *rm, float *w, int nx, int ny)
-{
-    for (int i = 0; i < ny; i++)
-        for (int j = 0; j < nx; j++) w[hs::wave_index(i, j, nx, ny)] = rm[i * nx + j];
-}
-
-void from_wave(const float *w, float *rm, int nx, int ny)
-{
-    for (int i = 0; i < ny; i++)
-        for (int j = 0; j < nx; j++) rm[i * nx + j] = w[hs::wave_index(i, j, nx, ny)];
 }
 
 // sequential update of pixel (i, j) on row-major planes, clamped neighbours (+ the BR corner's order)
@@ -131,24 +123,26 @@ int hs_emu_wave_sor(float *u, float *v, const float *ix, const float *iy, const 
 {
     if (nx < 3 || ny < 3 || P < 0 || P > hs::kMaxPrefetch || nthreads < 1) return -1;
     const size_t n = (size_t) nx * ny;
-    std::vector<float> wu(n), wv(n), wix(n), wiy(n), wrho(n);
-    to_wave(u, wu.data(), nx, ny);
-    to_wave(v, wv.data(), nx, ny);
-    to_wave(ix, wix.data(), nx, ny);
-    to_wave(iy, wiy.data(), nx, ny);
-    to_wave(rho, wrho.data(), nx, ny);
+    std::vector<hs::F2> wuv(n), wxy(n);
+    std::vector<float> wrho(n);
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) {
+            const int w = hs::wave_index(i, j, nx, ny), p = i * nx + j;
+            wuv[w].x = u[p]; wuv[w].y = v[p];
+            wxy[w].x = ix[p]; wxy[w].y = iy[p];
+            wrho[w] = rho[p];
+        }
 
     hs::SorView V;
-    V.wu = wu.data(); V.wv = wv.data(); V.wix = wix.data(); V.wiy = wiy.data(); V.wrho = wrho.data();
+    V.wuv = wuv.data(); V.wxy = wxy.data(); V.wrho = wrho.data();
     V.nx = nx; V.ny = ny; V.alpha2 = alpha2;
     V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = ny + 3;
     // poison the rings: a read of a slot that was never fetched shows up as NaN in the result
-    std::vector<float> ring((size_t) (2 * V.S + 3 * V.CD) * V.rp, nanf(""));
-    V.ring_u = ring.data();
-    V.ring_v = V.ring_u + (size_t) V.S * V.rp;
-    V.cix = V.ring_v + (size_t) V.S * V.rp;
-    V.ciy = V.cix + (size_t) V.CD * V.rp;
-    V.crho = V.ciy + (size_t) V.CD * V.rp;
+    std::vector<hs::F2> ring((size_t) (V.S + V.CD) * V.rp, hs::F2{ nanf(""), nanf("") });
+    std::vector<float> ring_rho((size_t) V.CD * V.rp, nanf(""));
+    V.ring_uv = ring.data();
+    V.cxy = V.ring_uv + (size_t) V.S * V.rp;
+    V.crho = ring_rho.data();
 
     EmuCp cp;
     cp.land = land;
@@ -162,7 +156,8 @@ int hs_emu_wave_sor(float *u, float *v, const float *ix, const float *iy, const 
         hs::Step s = hs::make_step(V, hs::first_step(V));
         for (int t = hs::first_step(V); t <= hs::last_step(V); t++, hs::advance(V, s)) {
             cp.wait(P);                                     // cp.async.wait_group P; __syncthreads()
-            if (memcmp(&s, &(const hs::Step &) hs::make_step(V, t), sizeof s) != 0) return -2;
+            const hs::Step chk = hs::make_step(V, t);       // advance() must agree with the closed form
+            if (memcmp(&s, &chk, sizeof s) != 0) return -2;
             auto fetch = [&](int tid) { for (int i = tid; i < ny; i += nthreads) hs::issue_row(V, s, i, cp); };
             auto update = [&](int tid) {
                 if (t >= 3) for (int i = tid; i < ny; i += nthreads) esum[tid] += hs::compute_row(V, s, i);
@@ -183,8 +178,12 @@ int hs_emu_wave_sor(float *u, float *v, const float *ix, const float *iy, const 
         for (int tid = 0; tid < nthreads; tid++) e += esum[tid];
         error = sqrt(e / (nx * ny));
     }
-    from_wave(wu.data(), u, nx, ny);
-    from_wave(wv.data(), v, nx, ny);
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) {
+            const int w = hs::wave_index(i, j, nx, ny), p = i * nx + j;
+            u[p] = wuv[w].x;
+            v[p] = wuv[w].y;
+        }
     if (err_out) *err_out = error;
     return niter;
 }
