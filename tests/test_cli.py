@@ -123,3 +123,52 @@ def test_sequence_cli_equals_pairwise_cli(tmp_path):
         a1, a2 = read_flo(tmp_path / ("par_%04d.flo" % k))
         b1, b2 = read_flo(tmp_path / ("seq_%04d.flo" % src))
         assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+
+
+# ---- the reference's Horn-Schunck program (src/horn_schunck_pyramidal_main.cpp), unmodified -------
+HS_CLI = os.path.join(ROOT, "cli", "horn_schunck_pyramidal")
+HS_CLI_REF = os.path.join(ROOT, "cli", "horn_schunck_pyramidal_ref")
+# argv of :88-105: outfile nproc alpha nscales zfactor nwarps TOL maxiter verbose
+HS_ARGS = ("1", "7", "3", "0.5", "3", "0.001", "60", "1")
+
+
+def run_hs_cli(exe, tmp, nx=96, ny=72, args=HS_ARGS):
+    I1, I2 = _cases.synth.make_pair(nx, ny, seed=77, scale=0.4)
+    q1 = write_pgm(tmp / "a.pgm", I1)
+    q2 = write_pgm(tmp / "b.pgm", I2)
+    out = tmp / ("hs_%s.flo" % os.path.basename(exe))
+    p = subprocess.run([exe, str(tmp / "a.pgm"), str(tmp / "b.pgm"), str(out), *args],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    iters = [int(m) for m in re.findall(r"Iterations (\d+) \(", p.stderr)]
+    scales = re.findall(r"Scale: (\d+) (\d+)x(\d+)", p.stderr)
+    return q1, q2, read_flo(out), iters, scales, p.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(HS_CLI_REF), reason="cli/horn_schunck_pyramidal_ref not built")
+def test_reference_hs_cli_with_iio_lite_matches_oracle(tmp_path, oracle_f64):
+    """CPU: the reference's Horn-Schunck program (one thread: argv nproc = 1) through our IO shim equals
+    the oracle on the same 8-bit images."""
+    q1, q2, (u, v), iters, scales, err = run_hs_cli(HS_CLI_REF, tmp_path)
+    ru, rv, rit, _ = oracle_f64.hs_multiscale(q1.astype(np.float64), q2.astype(np.float64), alpha=7.0, nscales=3,
+                                              zfactor=0.5, warps=3, tol=1e-3, maxiter=60)
+    assert iters == rit.ravel().tolist()
+    assert [(int(a), int(b), int(c)) for a, b, c in scales] == [(2, 24, 18), (1, 48, 36), (0, 96, 72)]
+    assert np.array_equal(u, ru.astype(np.float32)) and np.array_equal(v, rv.astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(HS_CLI), reason="cli/horn_schunck_pyramidal not built")
+def test_hs_cli_drop_in_on_gpu(tmp_path, oracle_f64):
+    """GPU: the same unmodified main() linked against libtvl1_b200.so: same verbose lines, same sweep
+    counts, flow within the tolerance; and the CLI's nscales clamp (main.cpp:136-143) still applies."""
+    q1, q2, (u, v), iters, scales, err = run_hs_cli(HS_CLI, tmp_path)
+    ru, rv, rit, _ = oracle_f64.hs_multiscale(q1.astype(np.float64), q2.astype(np.float64), alpha=7.0, nscales=3,
+                                              zfactor=0.5, warps=3, tol=1e-3, maxiter=60)
+    assert iters == rit.ravel().tolist(), err
+    assert [(int(a), int(b), int(c)) for a, b, c in scales] == [(2, 24, 18), (1, 48, 36), (0, 96, 72)]
+    assert "Multiscale Horn-Schunck of a 96x72 pair" in err and "Single-scale Horn-Schunck of a 24x18 image" in err
+    d = np.concatenate([np.abs(u - ru).ravel(), np.abs(v - rv).ravel()])
+    assert d.mean() <= 1e-3 and d.max() <= 1e-2
+    _, _, _, iters2, scales2, _ = run_hs_cli(HS_CLI, tmp_path, args=("1", "7", "10", "0.5", "2", "0.001", "20", "1"))
+    assert len(scales2) == 3 and len(iters2) == 6       # 96x72: N = 1 + log2(120 / 16) = 3.9 -> 3 levels
