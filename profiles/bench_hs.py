@@ -9,7 +9,11 @@ bench.py's contract: batch of synthetic 1920x1080 pairs, the CLI's default param
   cpu_baseline the unmodified reference (oracle/_ref) with ONE thread -- the only thread count for which
                its result is defined -- on one pair of the workload
 
-    python profiles/bench_hs.py [--pairs 296] [--steps 1] [--warmup 1] [--e2e-pairs 74] [--no-cpu]
+    python profiles/bench_hs.py [--pairs 296] [--steps 1] [--warmup 1] [--e2e-pairs 296] [--no-cpu]
+                                [--skip-device] [--e2e-warmup 1]
+
+A solve takes about as long for 37 pairs as for 296 (one CTA per pair, up to two per SM), so the e2e
+leg must carry the whole batch too: 4 lanes x 74 pairs.
 """
 import argparse
 import json
@@ -26,10 +30,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=296)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=1)
-ap.add_argument("--e2e-pairs", type=int, default=74)
+ap.add_argument("--e2e-pairs", type=int, default=296)
 ap.add_argument("--nx", type=int, default=1920)
 ap.add_argument("--ny", type=int, default=1080)
 ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--skip-device", action="store_true", help="only the e2e (host-buffer) leg")
+ap.add_argument("--e2e-warmup", type=int, default=1)
 args = ap.parse_args()
 nx, ny, P = args.nx, args.ny, args.pairs
 kw = dict(pkg.HS_DEFAULTS)
@@ -53,39 +59,42 @@ def solve():
                                    want_iters=True, **kw)
 
 
-for _ in range(args.warmup):
-    solve()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-sor_ms = px = launches = sor_launches = 0
-with torch.cuda.stream(stream):
-    e0.record()
-    for _ in range(args.steps):
-        it, er = solve()
-        st = g.stats()
-        sor_ms += st["iterate_ms"]; px += st["pixel_iterations"]
-        launches += st["kernel_launches"]; sor_launches += st["iterate_launches"]
-    e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / args.steps
-line = {
-    "metric": "Horn-Schunck 1080p frame-pairs/sec", "value": P / (ms * 1e-3), "unit": "frame-pairs/s",
-    "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-    "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": "batch of %d synthetic %dx%d frame pairs, pyramidal Horn-Schunck, CLI default parameters"
-                           % (P, nx, ny), "params": kw, "lockstep_batch": P,
-               "l2": "inputs and solver state exceed the 126 MB L2; no explicit flush"},
-    "gpu_launches": launches,
-    "sweeps_per_warp_step_mean": float(it.mean()), "sweeps_per_warp_step_max": int(it.max()),
-    "roofline": {"kernel": "k_hs_sor (+ k_hs_to_wave / k_hs_from_wave once per warp step)", "bound": "hbm",
-                 "achieved": 28.0 * px / (sor_ms * 1e-3) / 1e9 if sor_ms else None, "peak": peak, "unit": "GB/s",
-                 "frac": (28.0 * px / (sor_ms * 1e-3) / 1e9 / peak) if sor_ms else None,
-                 "algorithmic_bytes_per_pixel_sweep": 28, "pixel_sweeps": px, "launches": sor_launches,
-                 "kernel_ms": sor_ms, "kernel_share_of_step": sor_ms / (ms * args.steps),
-                 "traffic": 17529608000, "traffic_source": "profiles/r1h_hs_sor_full.csv (148 pairs, finest level, "
-                 "2 sweeps: 17.19 GB algorithmic)",
-                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6556.5"},
-}
+line = {}
+it = None
+if not args.skip_device:
+    for _ in range(args.warmup):
+        solve()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sor_ms = px = launches = sor_launches = 0
+    with torch.cuda.stream(stream):
+        e0.record()
+        for _ in range(args.steps):
+            it, er = solve()
+            st = g.stats()
+            sor_ms += st["iterate_ms"]; px += st["pixel_iterations"]
+            launches += st["kernel_launches"]; sor_launches += st["iterate_launches"]
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    line = {
+        "metric": "Horn-Schunck 1080p frame-pairs/sec", "value": P / (ms * 1e-3), "unit": "frame-pairs/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch of %d synthetic %dx%d frame pairs, pyramidal Horn-Schunck, CLI default parameters"
+                               % (P, nx, ny), "params": kw, "lockstep_batch": P,
+                   "l2": "inputs and solver state exceed the 126 MB L2; no explicit flush"},
+        "gpu_launches": launches,
+        "sweeps_per_warp_step_mean": float(it.mean()), "sweeps_per_warp_step_max": int(it.max()),
+        "roofline": {"kernel": "k_hs_sor (+ k_hs_to_wave / k_hs_from_wave once per warp step)", "bound": "hbm",
+                     "achieved": 28.0 * px / (sor_ms * 1e-3) / 1e9 if sor_ms else None, "peak": peak, "unit": "GB/s",
+                     "frac": (28.0 * px / (sor_ms * 1e-3) / 1e9 / peak) if sor_ms else None,
+                     "algorithmic_bytes_per_pixel_sweep": 28, "pixel_sweeps": px, "launches": sor_launches,
+                     "kernel_ms": sor_ms, "kernel_share_of_step": sor_ms / (ms * args.steps),
+                     "traffic": 17529608000, "traffic_source": "profiles/r1h_hs_sor_full.csv (148 pairs, finest level, "
+                     "2 sweeps: 17.19 GB algorithmic)",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6556.5"},
+    }
 
 # e2e: pinned host buffers through the public batch call
 E = min(args.e2e_pairs, P)
@@ -95,7 +104,7 @@ hu = torch.empty_like(hI1).pin_memory()
 hv = torch.empty_like(hI1).pin_memory()
 hI1.copy_(I1[:E]); hI2.copy_(I2[:E])
 torch.cuda.synchronize()
-h = pkg.HornSchunck(0, max_batch=max(1, E // 2))
+h = pkg.HornSchunck(0, max_batch=max(1, (E + 3) // 4))     # 4 lanes
 import ctypes as C
 prm = h._hs_params(kw["alpha"], kw["nscales"], kw["zfactor"], kw["warps"], kw["tol"], kw["maxiter"])
 
@@ -106,16 +115,19 @@ def host_solve():
                                    C.byref(prm), None, None))
 
 
-host_solve()
+for _ in range(args.e2e_warmup):
+    host_solve()
 t0 = time.perf_counter()
 host_solve()
 dt = time.perf_counter() - t0
-same = bool(torch.equal(hu, u[:E].cpu()) and torch.equal(hv, v[:E].cpu()))
+same = None if args.skip_device else bool(torch.equal(hu, u[:E].cpu()) and torch.equal(hv, v[:E].cpu()))
 line["e2e"] = {"value": E / dt, "unit": "frame-pairs/s", "pairs_per_step": E, "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": 2 * E * nx * ny * 4, "d2h_bytes_per_step": 2 * E * nx * ny * 4,
-               "api": "hs_solve_batch_f32 (host pinned fp32 in, host fp32 out)", "matches_device_path": same}
+               "api": "hs_solve_batch_f32 (host pinned fp32 in, host fp32 out)", "matches_device_path": same,
+               "warmup": args.e2e_warmup, "lanes": 4, "lockstep_batch": max(1, (E + 3) // 4),
+               "finite": bool(torch.isfinite(hu).all() and torch.isfinite(hv).all())}
 
-if not args.no_cpu:
+if not args.no_cpu and not args.skip_device:
     from oracle.loader import CpuTvl1, available
     kind = "reference" if available("reference", np.float64) else "port"
     cpu = CpuTvl1(kind, np.float64)
