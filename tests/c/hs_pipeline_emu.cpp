@@ -42,12 +42,12 @@ struct Rng {
 };
 
 struct Pipe {
-    int nx, ny, L, K, maxiter;
+    int nx, ny, L, K, D, maxiter;      // D: sweeps whose error partials are kept (rows run up to (2ny+nx)/L sweeps ahead)
     float alpha2;
     const float *ix, *iy, *rho;
     float *u, *v;
     std::vector<float> snap_u[2], snap_v[2];
-    std::vector<double> part;          // [4][ny + 1] squared-update partial sums per (sweep mod 4, row); slot ny = corners
+    std::vector<double> part;          // [D][ny + 1] squared-update partial sums per (sweep mod D, row)
     bool account;                      // speculative phase: keep errors and snapshots
     int limit;                         // sweeps 0 .. limit-1 may be started
 
@@ -66,7 +66,7 @@ struct Pipe {
         u[p] = un;
         v[p] = vn;
         if (account) {
-            part[(size_t) (n & 3) * (ny + 1) + part_row] += (double) e;
+            part[(size_t) (n % D) * (ny + 1) + part_row] += (double) e;
             if ((n + 1) % K == 0) {                     // sweep n+1 (1-based) is a snapshot sweep
                 const int q = ((n + 1) / K) & 1;
                 snap_u[q][p] = un;
@@ -109,8 +109,9 @@ struct Pipe {
             if (j == nx) update(i, nx - 1, n, i);
         }
     }
-    void part_reset(int n, int row) { if (account) part[(size_t) (n & 3) * (ny + 1) + row] = 0.0; }
-    int t_done(int n) const { return n * L + 2 * ny + nx - 2; }      // the BR corner of sweep n
+    void part_reset(int n, int row) { if (account) part[(size_t) (n % D) * (ny + 1) + row] = 0.0; }
+    // last update of sweep n: the BR corner, or (3-row images) the UL corner at n*L + 8
+    int t_done(int n) const { return n * L + std::max(8, 2 * ny + nx - 2); }
 };
 
 void thread_order(std::vector<int> &ord, int mode, Rng &rng)
@@ -139,7 +140,8 @@ int hs_emu_pipe_sor(float *u, float *v, const float *ix, const float *iy, const 
     P.ix = ix; P.iy = iy; P.rho = rho; P.u = u; P.v = v;
     const size_t n = (size_t) nx * ny;
     for (int q = 0; q < 2; q++) { P.snap_u[q].assign(u, u + n); P.snap_v[q].assign(v, v + n); }
-    P.part.assign((size_t) 4 * (ny + 1), 0.0);
+    P.D = (2 * ny + nx) / P.L + 3;
+    P.part.assign((size_t) P.D * (ny + 1), 0.0);
     P.account = true;
     P.limit = maxiter;
 
@@ -157,7 +159,7 @@ int hs_emu_pipe_sor(float *u, float *v, const float *ix, const float *iy, const 
         step(T);                                            // one barrier per step
         if (T == P.t_done(decided)) {
             double e = 0;
-            for (int r = 0; r <= ny; r++) e += P.part[(size_t) (decided & 3) * (ny + 1) + r];   // fixed order
+            for (int r = 0; r <= ny; r++) e += P.part[(size_t) (decided % P.D) * (ny + 1) + r];   // fixed order
             error = sqrt(e / (nx * ny));
             niter = ++decided;
             if (!(error > tol && niter < maxiter)) break;
