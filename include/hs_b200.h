@@ -20,8 +20,9 @@
  * result is only defined with one thread.  This implementation reproduces the ONE-thread order
  * exactly (every pixel reads the same mix of new and old neighbour values), in fp32.
  *
- * Limits of this build: every pyramid level needs nx >= 3, ny >= 3 and ny <= HS_MAX_ROWS (the sweep of
- * one frame pair keeps a ring of wave columns of u and v in the shared memory of one SM).
+ * Limits of this build: every pyramid level needs nx >= 3 and ny >= 3.  Up to about HS_MAX_ROWS rows the
+ * sweep of a frame pair keeps its ring of wave columns in the shared memory of one SM; taller levels keep
+ * it in global memory (same schedule, same result, slower) and then need nx >= 24.
  */
 #ifndef HS_B200_H
 #define HS_B200_H
@@ -34,7 +35,7 @@ extern "C" {
 
 #define HS_SOR_EXTRAPOLATION_PARAMETER 1.9   /* src/horn_schunck_pyramidal.cpp:21 */
 #define HS_INPUT_PRESMOOTHING_SIGMA 0.8      /* src/horn_schunck_pyramidal.cpp:22 */
-#define HS_MAX_ROWS 2560                     /* rows of the largest level k_hs_sor accepts */
+#define HS_MAX_ROWS 2560                     /* rows up to which the rings of k_hs_sor live in shared memory */
 
 /* Solver parameters: the reference's own set (src/horn_schunck.h:35-48), same meaning and order. */
 typedef struct hs_params {
@@ -77,7 +78,8 @@ int hs_single_scale_f64(tvl1_ctx *ctx, const double *I1, const double *I2, doubl
  * warped gradients and rho_c = -(I1 - I2w + I2wx*u + I2wy*v) what the warp kernel stores
  * (src/horn_schunck_pyramidal.cpp:127-137 in terms of these: Au = -rho_c*I2wx, Du = I2wx^2 + alpha^2,
  * D = I2wx*I2wy).  u, v in/out.  prefetch = -1 picks the prefetch distance automatically, 0..3 forces
- * it.  Outputs: sweeps done and the last sqrt(mean squared update). */
+ * it, -2 forces the rings into global memory (the path of levels with more than ~HS_MAX_ROWS rows).
+ * Outputs: sweeps done and the last sqrt(mean squared update). */
 int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float *rho_c, float *u, float *v,
                int nx, int ny, double alpha, double tol, int maxiter, int prefetch, int *niter_out,
                double *err_out);

@@ -12,6 +12,8 @@
 #include "hs_sor_step.h"
 #include "tvl1_kernels.cuh"
 
+#include <type_traits>
+
 namespace tvl1 {
 
 constexpr int kHsMaxThreads = 1024;
@@ -137,6 +139,17 @@ struct HsCpAsync {
     __device__ __forceinline__ void cp4(float *dst, const float *src) { cp_async4(dst, src); }
     __device__ __forceinline__ void cp8(float2 *dst, const float2 *src) { cp_async8(dst, src); }
 };
+// Rings in global memory (images with more rows than one SM's shared memory can ring-buffer): plain
+// copies, ordered by the per-step barrier like everything else the threads of a CTA exchange.
+struct HsCpSync {
+    __device__ __forceinline__ void cp4(float *dst, const float *src) { *dst = *src; }
+    __device__ __forceinline__ void cp8(float2 *dst, const float2 *src) { *dst = *src; }
+};
+
+// Floats of ring storage a pair needs when the rings live in global memory (P = 0), and where they
+// start inside the pair's wave region (after the 5n floats of the wave planes, 16-byte aligned).
+__host__ __device__ inline size_t hs_global_ring_floats(int rp) { return (size_t) (2 * hs::kRingBase + 3 * 2) * rp; }
+__host__ __device__ inline size_t hs_global_ring_offset(size_t n) { return (5 * n + 3) / 4 * 4; }
 
 template <int N>
 __device__ __forceinline__ void hs_cp_async_wait()
@@ -149,7 +162,9 @@ __device__ __forceinline__ void hs_cp_async_wait()
 // hs_sor_step.h with one __syncthreads per step; wave columns of u, v and of the coefficients are
 // fetched P steps ahead with cp.async into shared-memory rings.  The squared-update sum is reduced
 // in fp64 in a fixed order, so the stopping decision does not depend on scheduling.
-template <int P>
+// GLOBAL_RING (with P = 0): the rings live in the pair's wave region in global memory instead -- the
+// same schedule for images whose rows do not fit the shared-memory rings (ny > HS_MAX_ROWS).
+template <int P, bool GLOBAL_RING>
 __global__ void __launch_bounds__(kHsMaxThreads)
 k_hs_sor(HsSorParams A)
 {
@@ -170,11 +185,11 @@ k_hs_sor(HsSorParams A)
     V.wrho = wave + 4 * n;
     V.nx = nx; V.ny = ny; V.alpha2 = A.alpha2;
     V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = A.rp;
-    V.ring_uv = reinterpret_cast<float2 *>(hs_smem);
+    V.ring_uv = reinterpret_cast<float2 *>(GLOBAL_RING ? wave + hs_global_ring_offset(n) : hs_smem);
     V.cxy = V.ring_uv + (size_t) V.S * V.rp;
     V.crho = reinterpret_cast<float *>(V.cxy + (size_t) V.CD * V.rp);
 
-    HsCpAsync cp;
+    typename std::conditional<GLOBAL_RING, HsCpSync, HsCpAsync>::type cp;
     const int t_first = hs::first_step(V), t_last = hs::last_step(V);
     int niter = 0;
     while (true) {

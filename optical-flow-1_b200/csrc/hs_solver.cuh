@@ -24,36 +24,51 @@ int hs_pick_prefetch(int ny, int want)
     return -1;
 }
 
+// Levels whose rows do not fit the shared-memory rings keep the rings in the pair's wave region in
+// global memory (k_hs_sor<0, true>): needs 22 floats per (padded) row behind the 5n floats of the planes.
+bool hs_global_ring_fits(const Workspace &w, const Level &l)
+{
+    const size_t n = (size_t) l.nx * l.ny;
+    return hs_global_ring_offset(n) + hs_global_ring_floats(round_up(l.ny, 32)) <= 6 * w.plane0;
+}
+
 int hs_check_level(tvl1_ctx *ctx, const Level &l)
 {
     if (l.nx < 3 || l.ny < 3) return fail_arg(ctx, "Horn-Schunck: every pyramid level needs nx >= 3 and ny >= 3");
-    if (l.ny > HS_MAX_ROWS || hs_pick_prefetch(l.ny, -1) < 0)
-        return fail_arg(ctx, "Horn-Schunck: image has more rows than this build supports (HS_MAX_ROWS)");
+    if (hs_pick_prefetch(l.ny, -1) < 0 && !hs_global_ring_fits(ctx->ws, l))
+        return fail_arg(ctx, "Horn-Schunck: image too tall and narrow (more than HS_MAX_ROWS rows need nx >= 24)");
     return TVL1_OK;
 }
 
-template <int P>
+template <int P, bool G>
 int hs_launch_sor_p(tvl1_ctx *ctx, const HsSorParams &A, int B, int threads, size_t smem)
 {
     static bool attr_done[64] = { false };
-    if (!attr_done[ctx->device & 63]) {
-        CK(cudaFuncSetAttribute(k_hs_sor<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kHsSmemOneCta));
+    if (!G && !attr_done[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(k_hs_sor<P, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kHsSmemOneCta));
         attr_done[ctx->device & 63] = true;
     }
-    k_hs_sor<P><<<B, threads, smem, ctx->stream>>>(A);
+    k_hs_sor<P, G><<<B, threads, G ? 0 : smem, ctx->stream>>>(A);
     CKL(ctx);
     return TVL1_OK;
 }
+
+constexpr int kHsForceGlobalRing = -2;     // hs_sor_f32(prefetch = -2): tests force the global-memory rings
 
 // The SOR loop of one warp step for every pair of the batch: one launch, one CTA per pair.
 int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_slot, int prefetch = -1)
 {
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
-    if (prefetch < 0)
+    if (prefetch == -1)
         if (const char *e = std::getenv("HS_PREFETCH")) prefetch = std::atoi(e);   // measurements (profiles/run_hs.py)
-    const int P = hs_pick_prefetch(l.ny, prefetch);
-    if (P < 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
+    int P = prefetch == kHsForceGlobalRing ? -1 : hs_pick_prefetch(l.ny, prefetch);
+    const bool global_ring = P < 0;
+    if (global_ring) {
+        if (prefetch >= 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
+        if (!hs_global_ring_fits(w, l)) return fail_arg(ctx, "Horn-Schunck: no room for the rings in global memory");
+        P = 0;
+    }
     HsSorParams A = {};
     A.state = w.state; A.plane0 = w.plane0; A.set_stride = w.set_stride;
     A.ctl = w.ctl;
@@ -67,11 +82,12 @@ int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_sl
     const int rows_per_thread = ceil_div(l.ny, kHsMaxThreads);
     const int threads = std::min(kHsMaxThreads, round_up(ceil_div(l.ny, rows_per_thread), 32));
     const size_t smem = hs_ring_bytes(P, A.rp);
-    switch (P) {
-    case 0: TRY(hs_launch_sor_p<0>(ctx, A, B, threads, smem)); break;
-    case 1: TRY(hs_launch_sor_p<1>(ctx, A, B, threads, smem)); break;
-    case 2: TRY(hs_launch_sor_p<2>(ctx, A, B, threads, smem)); break;
-    default: TRY(hs_launch_sor_p<3>(ctx, A, B, threads, smem)); break;
+    if (global_ring) TRY((hs_launch_sor_p<0, true>(ctx, A, B, threads, 0)));
+    else switch (P) {
+    case 0: TRY((hs_launch_sor_p<0, false>(ctx, A, B, threads, smem))); break;
+    case 1: TRY((hs_launch_sor_p<1, false>(ctx, A, B, threads, smem))); break;
+    case 2: TRY((hs_launch_sor_p<2, false>(ctx, A, B, threads, smem))); break;
+    default: TRY((hs_launch_sor_p<3, false>(ctx, A, B, threads, smem))); break;
     }
     ctx->stats.iterate_launches++;
     return TVL1_OK;
@@ -285,7 +301,7 @@ int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float 
     if (!ctx) return TVL1_ERR_ARG;
     if (!I2wx || !I2wy || !rho_c || !u || !v) return fail_arg(ctx, "null pointer argument");
     if (!(alpha > 0.0) || maxiter < 1) return fail_arg(ctx, "alpha must be positive and maxiter >= 1");
-    if (prefetch > hs::kMaxPrefetch) return fail_arg(ctx, "prefetch must be -1 or 0..3");
+    if (prefetch > hs::kMaxPrefetch || prefetch < kHsForceGlobalRing) return fail_arg(ctx, "prefetch must be -2, -1 or 0..3");
     CK(cudaSetDevice(ctx->device));
     reset_stats(ctx);
     TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1));

@@ -81,6 +81,18 @@ def test_sor_kernel_stops_like_the_reference_loop(gpu, oracle_f64, tol):
     assert np.abs(gu - ou).max() < 5e-4 and np.abs(gv - ov).max() < 5e-4
 
 
+@pytest.mark.parametrize("nx,ny,prefetch", [(37, 29, -2), (64, 48, -2), (131, 70, -2), (24, 3000, -1), (40, 2700, -1)])
+def test_sor_kernel_with_rings_in_global_memory(gpu, nx, ny, prefetch):
+    """Images with more rows than the shared-memory rings hold (ny > ~2590) keep the rings in global memory:
+    same schedule, same bits.  prefetch = -2 forces that path on small images."""
+    ix, iy, rho, u, v, _ = _hs_emu.system(nx, ny, seed=nx + ny)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, 0.0, 4)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=0.0, maxiter=4, prefetch=prefetch)
+    assert gn == rn == 4
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv)
+    assert abs(gerr - rerr) <= 1e-9 * max(1.0, rerr)
+
+
 def test_sor_kernel_rejects_unsupported_sizes(gpu):
     z = np.zeros((2, 8), np.float32)
     with pytest.raises(pkg.TVL1Error) as e:
