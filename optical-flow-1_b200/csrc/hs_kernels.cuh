@@ -10,6 +10,7 @@
 //   k_hs_from_wave  wave layout (u, v) -> row-major planes
 #pragma once
 #include "hs_sor_step.h"
+#include "hs_sor_pipe.h"
 #include "tvl1_kernels.cuh"
 
 #include <type_traits>
@@ -38,6 +39,13 @@ struct HsSorParams {
     int stat_stride, stat_slot;
     unsigned long long *px_iters; // [level] pixel-iterations
     int level;
+    // pipelined kernel only (k_hs_sor_pipe): wave period, snapshot period, error depth, snapshot planes
+    // (2 x 2 L ny floats per pair) and per-row error sums (D x rp doubles per pair)
+    int L, K, D;
+    float *snap;
+    size_t snap_stride;
+    double *part;
+    size_t part_stride;
 };
 
 // Where the wave planes of pair b live: the idle ping-pong set of the state buffer (6 B plane0 floats),
@@ -49,12 +57,14 @@ __device__ __forceinline__ float *hs_wave_base(float *state, size_t set_stride, 
 }
 
 // Tile transposes between the row-major pitched planes and the wave layout
-//   W[((j + 2i) mod nx) * ny + i] = plane[i * pitch + j].
+//   W[((j + 2i) mod M) * ny + i] = plane[i * pitch + j],   M = nx (k_hs_sor) or L (k_hs_sor_pipe).
 // A CTA moves a 32 x 32 tile of (wave column c, row i): row-major side coalesced along j (= c - 2i,
-// consecutive in c), wave side coalesced along i.
+// consecutive in c), wave side coalesced along i.  snap (pipelined kernel): the initial flow is also
+// the snapshot of "sweep 0".
 __global__ void __launch_bounds__(256)
 k_hs_to_wave(float *__restrict__ state, const float *__restrict__ consts, size_t plane0, size_t field_stride,
-             size_t set_stride, const PairCtl *__restrict__ ctl, Level lv)
+             size_t set_stride, const PairCtl *__restrict__ ctl, Level lv, int mod, float *__restrict__ snap,
+             size_t snap_stride)
 {
     __shared__ float tile[5][32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
@@ -68,28 +78,33 @@ k_hs_to_wave(float *__restrict__ state, const float *__restrict__ consts, size_t
     src[2] = consts + (size_t) C_IX * field_stride + (size_t) b * plane0;
     src[3] = consts + (size_t) C_IY * field_stride + (size_t) b * plane0;
     src[4] = consts + (size_t) C_RHO * field_stride + (size_t) b * plane0;
-    const size_t n = (size_t) nx * ny;
+    const size_t n = (size_t) mod * ny;
     float *base = hs_wave_base(state, set_stride, plane0, cur, b);
     float2 *wuv = reinterpret_cast<float2 *>(base);
     float2 *wxy = reinterpret_cast<float2 *>(base + 2 * n);
     float *wrho = base + 4 * n;
+    float2 *snap0 = snap ? reinterpret_cast<float2 *>(snap + (size_t) b * snap_stride) : nullptr;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int i = i0 + ty + 8 * r, c = c0 + tx;
-        if (i < ny && c < nx) {
-            const int j = hs::pmod(c - 2 * i, nx);
-            const int o = i * pitch + j;
+        if (i < ny && c < mod) {
+            const int j = hs::pmod(c - 2 * i, mod);
+            if (j < nx) {
+                const int o = i * pitch + j;
 #pragma unroll
-            for (int k = 0; k < 5; k++) tile[k][ty + 8 * r][tx] = src[k][o];
+                for (int k = 0; k < 5; k++) tile[k][ty + 8 * r][tx] = src[k][o];
+            }
         }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int c = c0 + ty + 8 * r, i = i0 + tx;
-        if (i < ny && c < nx) {
+        if (i < ny && c < mod && hs::pmod(c - 2 * i, mod) < nx) {
             const size_t o = (size_t) c * ny + i;
-            wuv[o] = make_float2(tile[0][tx][ty + 8 * r], tile[1][tx][ty + 8 * r]);
+            const float2 uv = make_float2(tile[0][tx][ty + 8 * r], tile[1][tx][ty + 8 * r]);
+            wuv[o] = uv;
+            if (snap0) snap0[o] = uv;
             wxy[o] = make_float2(tile[2][tx][ty + 8 * r], tile[3][tx][ty + 8 * r]);
             wrho[o] = tile[4][tx][ty + 8 * r];
         }
@@ -98,7 +113,7 @@ k_hs_to_wave(float *__restrict__ state, const float *__restrict__ consts, size_t
 
 __global__ void __launch_bounds__(256)
 k_hs_from_wave(float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
-               const PairCtl *__restrict__ ctl, Level lv)
+               const PairCtl *__restrict__ ctl, Level lv, int mod)
 {
     __shared__ float tile[2][32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
@@ -111,7 +126,7 @@ k_hs_from_wave(float *__restrict__ state, size_t plane0, size_t field_stride, si
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int c = c0 + ty + 8 * r, i = i0 + tx;
-        if (i < ny && c < nx) {
+        if (i < ny && c < mod && hs::pmod(c - 2 * i, mod) < nx) {
             const float2 uv = wuv[(size_t) c * ny + i];
             tile[0][ty + 8 * r][tx] = uv.x;
             tile[1][ty + 8 * r][tx] = uv.y;
@@ -121,11 +136,13 @@ k_hs_from_wave(float *__restrict__ state, size_t plane0, size_t field_stride, si
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int i = i0 + ty + 8 * r, c = c0 + tx;
-        if (i < ny && c < nx) {
-            const int j = hs::pmod(c - 2 * i, nx);
-            const int o = i * pitch + j;
-            dst[(size_t) F_U1 * field_stride + o] = tile[0][tx][ty + 8 * r];
-            dst[(size_t) F_U2 * field_stride + o] = tile[1][tx][ty + 8 * r];
+        if (i < ny && c < mod) {
+            const int j = hs::pmod(c - 2 * i, mod);
+            if (j < nx) {
+                const int o = i * pitch + j;
+                dst[(size_t) F_U1 * field_stride + o] = tile[0][tx][ty + 8 * r];
+                dst[(size_t) F_U2 * field_stride + o] = tile[1][tx][ty + 8 * r];
+            }
         }
     }
 }
@@ -219,6 +236,126 @@ k_hs_sor(HsSorParams A)
         }
         __syncthreads();
         if (!s_go) break;
+    }
+    if (tid == 0) {
+        A.stat_iters[(size_t) b * A.stat_stride + A.stat_slot] = niter;
+        A.stat_errs[(size_t) b * A.stat_stride + A.stat_slot] = s_err;
+        atomicAdd(A.px_iters + A.level, (unsigned long long) niter * (unsigned long long) (nx * ny));
+    }
+}
+
+// The pipelined form of k_hs_sor (hs_sor_pipe.h): sweep n of row i at time n*L + 2i + j, so that all rows
+// work all the time (a row of k_hs_sor works nx of 2*ny + nx steps).  Speculative phase with per-row error
+// sums (decided one barrier after a sweep completes, by warp 0 in a fixed order) and snapshots of every
+// K-th sweep; on a stop by TOL the snapshot is restored and the remaining sweeps are replayed with a
+// known count.  Dynamic shared memory: the rings of k_hs_sor<P> followed by rp doubles (running error
+// sum of each row's current sweep).
+template <int P>
+__global__ void __launch_bounds__(kHsMaxThreads)
+k_hs_sor_pipe(HsSorParams A)
+{
+    extern __shared__ __align__(16) float hs_smem[];
+    __shared__ double s_err;
+    __shared__ int s_go;
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int b = blockIdx.x;
+    const int nx = A.nx, ny = A.ny, L = A.L;
+    float *wave = hs_wave_base(A.state, A.set_stride, A.plane0, A.ctl[b].cur, b);
+    const size_t n = (size_t) L * ny;
+
+    hs::PipeView V;
+    V.wuv = reinterpret_cast<float2 *>(wave);
+    V.wxy = reinterpret_cast<const float2 *>(wave + 2 * n);
+    V.wrho = wave + 4 * n;
+    V.snap0 = reinterpret_cast<float2 *>(A.snap + (size_t) b * A.snap_stride);
+    V.snap1 = V.snap0 + n;
+    V.part = A.part + (size_t) b * A.part_stride;
+    V.nx = nx; V.ny = ny; V.L = L; V.K = A.K; V.D = A.D; V.alpha2 = A.alpha2;
+    V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = A.rp;
+    V.ring_uv = reinterpret_cast<float2 *>(hs_smem);
+    V.cxy = V.ring_uv + (size_t) V.S * V.rp;
+    V.crho = reinterpret_cast<float *>(V.cxy + (size_t) V.CD * V.rp);
+    V.esum = reinterpret_cast<double *>(V.crho + (size_t) V.CD * V.rp);
+    V.limit = A.max_iter;
+    V.account = 1;
+
+    for (int i = tid; i < V.rp; i += nthreads) V.esum[i] = 0.0;
+    __syncthreads();
+
+    HsCpAsync cp;
+    const int T_first = -4 - P;
+    // row positions without divisions: this thread's first row, the others 2*nthreads further back each
+    const int step_dn = (2 * nthreads) / L, step_dj = (2 * nthreads) % L;
+    int niter = 0;
+    {   // speculative phase
+        int decided = 0, t_dec = hs::pipe_t_done(0, L, nx, ny) + 1;
+        hs::PipeStep s = hs::pipe_make_step(V, T_first);
+        hs::RowPos base = hs::pipe_pos(T_first - 2 * tid, L);
+        for (int T = T_first;; T++, hs::pipe_advance(V, s)) {
+            hs_cp_async_wait<P>();
+            __syncthreads();
+            if (T == t_dec) {
+                if (tid < 32) {
+                    double e = 0.0;
+                    const double *row = V.part + (size_t) (decided % V.D) * V.rp;
+                    for (int r = tid; r < ny; r += 32) e += row[r];
+                    e = warp_sum(e);
+                    if (tid == 0) {
+                        const double error = sqrt(e / (double) (nx * ny));                 // :230
+                        s_err = error;
+                        s_go = (error > A.tol && decided + 1 < A.max_iter) ? 1 : 0;        // :143
+                    }
+                }
+                __syncthreads();
+                niter = ++decided;
+                if (!s_go) break;
+                t_dec += L;
+            }
+            hs::RowPos p = base;
+            for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L))
+                hs::pipe_issue_row(V, s, i, p, cp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (T >= 1) {
+                p = base;
+                for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L))
+                    hs::pipe_compute_row(V, s, i, p);
+            }
+            base = hs::pipe_pos_add(base, 1, L);
+        }
+        hs_cp_async_wait<0>();
+        __syncthreads();
+    }
+    if (niter < A.max_iter) {
+        // stopped by TOL: the upper rows ran ahead.  Restore the snapshot at or before sweep niter, replay.
+        const int m = (niter / V.K) * V.K;
+        const float2 *src = ((niter / V.K) & 1) ? V.snap1 : V.snap0;
+        for (size_t k = tid; k < n; k += nthreads) V.wuv[k] = src[k];
+        __syncthreads();
+        const int rep = niter - m;
+        if (rep > 0) {
+            V.limit = rep;
+            V.account = 0;
+            const int T_last = hs::pipe_t_done(rep - 1, L, nx, ny);
+            hs::PipeStep s = hs::pipe_make_step(V, T_first);
+            hs::RowPos base = hs::pipe_pos(T_first - 2 * tid, L);
+            for (int T = T_first; T <= T_last; T++, hs::pipe_advance(V, s)) {
+                hs_cp_async_wait<P>();
+                __syncthreads();
+                hs::RowPos p = base;
+                for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L))
+                    hs::pipe_issue_row(V, s, i, p, cp);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (T >= 1) {
+                    p = base;
+                    for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L))
+                        hs::pipe_compute_row(V, s, i, p);
+                }
+                base = hs::pipe_pos_add(base, 1, L);
+            }
+            hs_cp_async_wait<0>();
+            __syncthreads();
+        }
     }
     if (tid == 0) {
         A.stat_iters[(size_t) b * A.stat_stride + A.stat_slot] = niter;

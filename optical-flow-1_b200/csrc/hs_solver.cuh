@@ -53,21 +53,89 @@ int hs_launch_sor_p(tvl1_ctx *ctx, const HsSorParams &A, int B, int threads, siz
     return TVL1_OK;
 }
 
-constexpr int kHsForceGlobalRing = -2;     // hs_sor_f32(prefetch = -2): tests force the global-memory rings
+template <int P>
+int hs_launch_pipe_p(tvl1_ctx *ctx, const HsSorParams &A, int B, int threads, size_t smem)
+{
+    static bool attr_done[64] = { false };
+    if (!attr_done[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(k_hs_sor_pipe<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kHsSmemOneCta));
+        attr_done[ctx->device & 63] = true;
+    }
+    k_hs_sor_pipe<P><<<B, threads, smem, ctx->stream>>>(A);
+    CKL(ctx);
+    return TVL1_OK;
+}
+
+// hs_sor_f32(prefetch = ...): tests force a kernel variant
+constexpr int kHsForceGlobalRing = -2;     // rings in global memory
+constexpr int kHsForcePipelined = -3;      // pipelined sweeps (k_hs_sor_pipe)
+
+// ---- pipelined sweeps (k_hs_sor_pipe, hs_sor_pipe.h) ------------------------------------------------
+// Shared memory of a CTA: the rings plus one double per (padded) row.
+size_t hs_pipe_smem(int P, int rp) { return hs_ring_bytes(P, rp) + sizeof(double) * rp; }
+
+int hs_pipe_prefetch(int ny, int want)
+{
+    const int rp = round_up(ny, 32);
+    if (want >= 0 && want <= hs::kMaxPrefetch) return hs_pipe_smem(want, rp) <= kHsSmemOneCta ? want : -1;
+    if (hs_pipe_smem(1, rp) <= kHsSmemTwoCtas) return 1;
+    if (hs_pipe_smem(0, rp) <= kHsSmemTwoCtas) return 0;
+    if (hs_pipe_smem(1, rp) <= kHsSmemOneCta) return 1;
+    if (hs_pipe_smem(0, rp) <= kHsSmemOneCta) return 0;
+    return -1;
+}
+
+// Can level l run pipelined?  Its wave planes have period L = nx + 2 (5 L ny floats) and must fit the
+// pair's region of the idle ping-pong set; the rings must fit one SM.
+bool hs_pipe_fits(const Workspace &w, const Level &l)
+{
+    const int L = hs::pipe_period(l.nx);
+    return l.nx >= 17 && (size_t) 5 * L * l.ny <= 6 * w.plane0 && hs_pipe_prefetch(l.ny, -1) >= 0;
+}
+
+// HS_PIPELINE=1 selects the pipelined kernel wherever it fits (default: the one-sweep kernel).
+bool hs_pipe_enabled()
+{
+    const char *e = std::getenv("HS_PIPELINE");
+    return e && std::atoi(e) != 0;
+}
+
+bool hs_level_pipelined(const tvl1_ctx *ctx, const Level &l, int prefetch)
+{
+    if (prefetch == kHsForcePipelined) return true;
+    if (prefetch != -1) return false;
+    return hs_pipe_enabled() && hs_pipe_fits(ctx->ws, l);
+}
+
+// Snapshot planes (2 x float2 x L ny per pair) and error sums (D x rp doubles per pair) for the largest level.
+int hs_ensure_pipe_buffers(tvl1_ctx *ctx)
+{
+    Workspace &w = ctx->ws;
+    size_t snap = 0, part = 0;
+    for (const Level &l : w.lv) {
+        const int L = hs::pipe_period(l.nx);
+        snap = std::max(snap, (size_t) 4 * L * l.ny);
+        part = std::max(part, (size_t) hs::pipe_error_depth(L, l.nx, l.ny) * round_up(l.ny, 32));
+    }
+    if (w.hs_snap && w.hs_snap_stride >= snap && w.hs_part_stride >= part) return TVL1_OK;
+    cudaFree(w.hs_snap); cudaFree(w.hs_part);
+    w.hs_snap = nullptr; w.hs_part = nullptr;
+    CK(cudaMalloc(&w.hs_snap, sizeof(float) * snap * w.B));
+    CK(cudaMalloc(&w.hs_part, sizeof(double) * part * w.B));
+    w.hs_snap_stride = snap; w.hs_part_stride = part;
+    return TVL1_OK;
+}
 
 // The SOR loop of one warp step for every pair of the batch: one launch, one CTA per pair.
 int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_slot, int prefetch = -1)
 {
-    const Workspace &w = ctx->ws;
+    Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
-    if (prefetch == -1)
-        if (const char *e = std::getenv("HS_PREFETCH")) prefetch = std::atoi(e);   // measurements (profiles/run_hs.py)
-    int P = prefetch == kHsForceGlobalRing ? -1 : hs_pick_prefetch(l.ny, prefetch);
-    const bool global_ring = P < 0;
-    if (global_ring) {
-        if (prefetch >= 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
-        if (!hs_global_ring_fits(w, l)) return fail_arg(ctx, "Horn-Schunck: no room for the rings in global memory");
-        P = 0;
+    const bool pipe = hs_level_pipelined(ctx, l, prefetch);
+    int want = prefetch;
+    if (want < 0) {
+        want = -1;
+        if (const char *e = std::getenv("HS_PREFETCH")) want = std::atoi(e);       // measurements (profiles/run_hs.py)
     }
     HsSorParams A = {};
     A.state = w.state; A.plane0 = w.plane0; A.set_stride = w.set_stride;
@@ -81,6 +149,35 @@ int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_sl
     // rows per thread as even as possible: ceil(ny / ceil(ny / 1024)) threads, whole warps
     const int rows_per_thread = ceil_div(l.ny, kHsMaxThreads);
     const int threads = std::min(kHsMaxThreads, round_up(ceil_div(l.ny, rows_per_thread), 32));
+    if (pipe) {
+        if (!hs_pipe_fits(w, l)) return fail_arg(ctx, "Horn-Schunck: level does not fit the pipelined kernel");
+        const int P = hs_pipe_prefetch(l.ny, want);
+        if (P < 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
+        TRY(hs_ensure_pipe_buffers(ctx));
+        A.L = hs::pipe_period(l.nx);
+        int K = 8;
+        if (const char *e = std::getenv("HS_SNAP_K")) K = std::max(1, std::atoi(e));
+        A.K = hs::pipe_snapshot_period(K, A.L, l.nx, l.ny);
+        A.D = hs::pipe_error_depth(A.L, l.nx, l.ny);
+        A.snap = w.hs_snap; A.snap_stride = w.hs_snap_stride;
+        A.part = w.hs_part; A.part_stride = w.hs_part_stride;
+        const size_t smem = hs_pipe_smem(P, A.rp);
+        switch (P) {
+        case 0: TRY(hs_launch_pipe_p<0>(ctx, A, B, threads, smem)); break;
+        case 1: TRY(hs_launch_pipe_p<1>(ctx, A, B, threads, smem)); break;
+        case 2: TRY(hs_launch_pipe_p<2>(ctx, A, B, threads, smem)); break;
+        default: TRY(hs_launch_pipe_p<3>(ctx, A, B, threads, smem)); break;
+        }
+        ctx->stats.iterate_launches++;
+        return TVL1_OK;
+    }
+    int P = prefetch == kHsForceGlobalRing ? -1 : hs_pick_prefetch(l.ny, want);
+    const bool global_ring = P < 0;
+    if (global_ring) {
+        if (want >= 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
+        if (!hs_global_ring_fits(w, l)) return fail_arg(ctx, "Horn-Schunck: no room for the rings in global memory");
+        P = 0;
+    }
     const size_t smem = hs_ring_bytes(P, A.rp);
     if (global_ring) TRY((hs_launch_sor_p<0, true>(ctx, A, B, threads, 0)));
     else switch (P) {
@@ -93,23 +190,28 @@ int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_sl
     return TVL1_OK;
 }
 
-int hs_launch_to_wave(tvl1_ctx *ctx, int s, int B)
+// pipe: wave planes with period L (and the initial snapshot) for k_hs_sor_pipe, else period nx
+int hs_launch_to_wave(tvl1_ctx *ctx, int s, int B, bool pipe)
 {
+    if (pipe) TRY(hs_ensure_pipe_buffers(ctx));
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
-    dim3 g(ceil_div(l.nx, 32), ceil_div(l.ny, 32), B);
+    const int mod = pipe ? hs::pipe_period(l.nx) : l.nx;
+    dim3 g(ceil_div(mod, 32), ceil_div(l.ny, 32), B);
     k_hs_to_wave<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.consts, w.plane0, w.field_stride, w.set_stride,
-                                                     w.ctl, l);
+                                                     w.ctl, l, mod, pipe ? w.hs_snap : nullptr, w.hs_snap_stride);
     CKL(ctx);
     return TVL1_OK;
 }
 
-int hs_launch_from_wave(tvl1_ctx *ctx, int s, int B)
+int hs_launch_from_wave(tvl1_ctx *ctx, int s, int B, bool pipe)
 {
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
-    dim3 g(ceil_div(l.nx, 32), ceil_div(l.ny, 32), B);
-    k_hs_from_wave<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, l);
+    const int mod = pipe ? hs::pipe_period(l.nx) : l.nx;
+    dim3 g(ceil_div(mod, 32), ceil_div(l.ny, 32), B);
+    k_hs_from_wave<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, l,
+                                                       mod);
     CKL(ctx);
     return TVL1_OK;
 }
@@ -123,9 +225,10 @@ int hs_run_level(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_bas
             TRY(launch_warp(ctx, s, B));                                    // :114, :123-125, dif of :130
         }
         Span sp(ctx, 0, std::min(s, TVL1_MAX_LEVELS - 1));
-        TRY(hs_launch_to_wave(ctx, s, B));
+        const bool pipe = hs_level_pipelined(ctx, ctx->ws.lv[s], -1);
+        TRY(hs_launch_to_wave(ctx, s, B, pipe));
         TRY(hs_launch_sor(ctx, s, B, prm, stat_base + wi));                 // :127-137 (on the fly), :139-231
-        TRY(hs_launch_from_wave(ctx, s, B));
+        TRY(hs_launch_from_wave(ctx, s, B, pipe));
     }
     return TVL1_OK;
 }
@@ -301,7 +404,7 @@ int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float 
     if (!ctx) return TVL1_ERR_ARG;
     if (!I2wx || !I2wy || !rho_c || !u || !v) return fail_arg(ctx, "null pointer argument");
     if (!(alpha > 0.0) || maxiter < 1) return fail_arg(ctx, "alpha must be positive and maxiter >= 1");
-    if (prefetch > hs::kMaxPrefetch || prefetch < kHsForceGlobalRing) return fail_arg(ctx, "prefetch must be -2, -1 or 0..3");
+    if (prefetch > hs::kMaxPrefetch || prefetch < kHsForcePipelined) return fail_arg(ctx, "prefetch must be -3 .. 3");
     CK(cudaSetDevice(ctx->device));
     reset_stats(ctx);
     TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1));
@@ -329,9 +432,11 @@ int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float 
         CKL(ctx);
     }
     hs_params prm{ alpha, 1, 0.5, 1, tol, maxiter };
-    TRY(hs_launch_to_wave(ctx, 0, 1));
+    const bool pipe = hs_level_pipelined(ctx, w.lv[0], prefetch);
+    if (pipe && !hs_pipe_fits(w, w.lv[0])) return fail_arg(ctx, "Horn-Schunck: level does not fit the pipelined kernel");
+    TRY(hs_launch_to_wave(ctx, 0, 1, pipe));
     TRY(hs_launch_sor(ctx, 0, 1, prm, 0, prefetch));
-    TRY(hs_launch_from_wave(ctx, 0, 1));
+    TRY(hs_launch_from_wave(ctx, 0, 1, pipe));
     k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0], buf,
                                              buf + n);
     CKL(ctx);

@@ -37,6 +37,7 @@
 #if defined(__CUDACC__) && !defined(HS_SOR_EMULATE)
 #define HS_FN __device__ __forceinline__
 #define HS_FN_OUTLINE __device__ __noinline__
+#define HS_HD __host__ __device__ __forceinline__
 #define hs_fma(a, b, c) __fmaf_rn((a), (b), (c))
 #define hs_mul(a, b) __fmul_rn((a), (b))
 #define hs_add(a, b) __fadd_rn((a), (b))
@@ -48,6 +49,7 @@ namespace hs { typedef float2 F2; }
 namespace hs { struct F2 { float x, y; }; }
 #define HS_FN static inline
 #define HS_FN_OUTLINE static
+#define HS_HD static inline
 #define hs_fma(a, b, c) fmaf((a), (b), (c))
 #define hs_mul(a, b) ((float) ((float) (a) * (float) (b)))
 #define hs_add(a, b) ((float) ((float) (a) + (float) (b)))

@@ -57,6 +57,10 @@ struct Workspace {
     std::vector<int> res_cluster, res_rows;
     int resident_key = -1;
     int row_pad = 1;
+    // pipelined Horn-Schunck kernel (hs_solver.cuh): snapshot planes and per-row error sums, allocated on first use
+    float *hs_snap = nullptr;
+    double *hs_part = nullptr;
+    size_t hs_snap_stride = 0, hs_part_stride = 0;
 
     size_t plane(int s) const { return (size_t) lv[s].pitch * lv[s].ny; }
     float *I0(int s) const { return pyr + pyr_off[s]; }
@@ -207,7 +211,7 @@ void free_workspace(Workspace &w)
 {
     cudaFree(w.pyr); cudaFree(w.state); cudaFree(w.consts); cudaFree(w.tmp); cudaFree(w.ctl);
     cudaFree(w.mm); cudaFree(w.partials); cudaFree(w.loop); cudaFree(w.tb_partials); cudaFree(w.stat_iters);
-    cudaFree(w.stat_errs); cudaFree(w.counters);
+    cudaFree(w.stat_errs); cudaFree(w.counters); cudaFree(w.hs_snap); cudaFree(w.hs_part);
     w = Workspace();
 }
 

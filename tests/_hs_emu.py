@@ -27,6 +27,9 @@ def load():
         lib.hs_emu_seq_sor.restype = i
         lib.hs_emu_wave_sor.argtypes = [vp, vp, vp, vp, vp, i, i, f, d_, i, i, i, i, i, i, C.c_uint, C.POINTER(d_)]
         lib.hs_emu_wave_sor.restype = i
+        lib.hs_emu_pipe_wave_sor.argtypes = [vp, vp, vp, vp, vp, i, i, f, d_, i, i, i, i, i, i, i, C.c_uint,
+                                             C.POINTER(d_), C.POINTER(i)]
+        lib.hs_emu_pipe_wave_sor.restype = i
         _lib = lib
     return _lib
 
@@ -61,3 +64,16 @@ def run_wave(ix, iy, rho, u, v, alpha, tol, maxiter, P, nthreads, order, phase, 
                             nx, ny, alpha * alpha, tol, maxiter, P, nthreads, order, phase, land, seed,
                             C.byref(err))
     return u, v, n, err.value
+
+
+def run_pipe_wave(ix, iy, rho, u, v, alpha, tol, maxiter, K, P, nthreads, order, phase, land, seed=1):
+    """The PIPELINED schedule of k_hs_sor_pipe (hs_sor_pipe.h) replayed on the CPU -> (u, v, sweeps, error,
+    sweeps replayed after a restore)."""
+    emu = load()
+    u, v = u.copy(), v.copy()
+    ny, nx = u.shape
+    err, rep = C.c_double(), C.c_int()
+    n = emu.hs_emu_pipe_wave_sor(u.ctypes.data, v.ctypes.data, ix.ctypes.data, iy.ctypes.data, rho.ctypes.data,
+                                 nx, ny, alpha * alpha, tol, maxiter, K, P, nthreads, order, phase, land, seed,
+                                 C.byref(err), C.byref(rep))
+    return u, v, n, err.value, rep.value

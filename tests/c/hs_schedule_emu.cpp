@@ -11,6 +11,7 @@
 // bit under every adversary.
 #define HS_SOR_EMULATE 1
 #include "../../optical-flow-1_b200/csrc/hs_sor_step.h"
+#include "../../optical-flow-1_b200/csrc/hs_sor_pipe.h"
 
 #include <stdint.h>
 #include <stdlib.h>
@@ -185,6 +186,130 @@ int hs_emu_wave_sor(float *u, float *v, const float *ix, const float *iy, const 
             v[p] = wuv[w].y;
         }
     if (err_out) *err_out = error;
+    return niter;
+}
+
+// The PIPELINED schedule (hs_sor_pipe.h) driven like k_hs_sor_pipe: speculative phase with error
+// accounting and snapshots, decision one barrier after a sweep completes, restore + replay on a stop by
+// TOL.  Same adversary as hs_emu_wave_sor.  *replayed: sweeps re-run after the restore.
+int hs_emu_pipe_wave_sor(float *u, float *v, const float *ix, const float *iy, const float *rho, int nx, int ny,
+                         float alpha2, double tol, int maxiter, int K, int P, int nthreads, int order, int phase,
+                         int land, unsigned seed, double *err_out, int *replayed)
+{
+    if (nx < 3 || ny < 3 || P < 0 || P > hs::kMaxPrefetch || nthreads < 1 || maxiter < 1) return -1;
+    const int L = hs::pipe_period(nx);
+    const size_t n = (size_t) L * ny;
+    std::vector<hs::F2> wuv(n, hs::F2{ nanf(""), nanf("") }), wxy(n, hs::F2{ nanf(""), nanf("") });
+    std::vector<float> wrho(n, nanf(""));
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) {
+            const int w = hs::pipe_wave_index(i, j, L, ny), p = i * nx + j;
+            wuv[w].x = u[p]; wuv[w].y = v[p];
+            wxy[w].x = ix[p]; wxy[w].y = iy[p];
+            wrho[w] = rho[p];
+        }
+    std::vector<hs::F2> snap0(wuv), snap1(wuv);
+
+    hs::PipeView V;
+    V.wuv = wuv.data(); V.wxy = wxy.data(); V.wrho = wrho.data();
+    V.snap0 = snap0.data(); V.snap1 = snap1.data();
+    V.nx = nx; V.ny = ny; V.L = L; V.alpha2 = alpha2;
+    V.K = hs::pipe_snapshot_period(K, L, nx, ny);
+    V.D = hs::pipe_error_depth(L, nx, ny);
+    V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = ny + 3;
+    std::vector<double> part((size_t) V.D * V.rp, nan("")), esum(V.rp, 0.0);
+    V.part = part.data(); V.esum = esum.data();
+    std::vector<hs::F2> ring((size_t) (V.S + V.CD) * V.rp, hs::F2{ nanf(""), nanf("") });
+    std::vector<float> ring_rho((size_t) V.CD * V.rp, nanf(""));
+    V.ring_uv = ring.data();
+    V.cxy = V.ring_uv + (size_t) V.S * V.rp;
+    V.crho = ring_rho.data();
+
+    EmuCp cp;
+    cp.land = land;
+    Rng rng{ seed * 2654435761ull + 4711 };
+    std::vector<int> ord(nthreads);
+    const int T_first = -4 - P;
+    // per-thread row positions, advanced like the kernel does (no division in the time loop)
+    std::vector<hs::RowPos> base(nthreads);
+    const int step_dn = (2 * nthreads) / L, step_dj = (2 * nthreads) % L;
+    auto reset_positions = [&]() { for (int tid = 0; tid < nthreads; tid++) base[tid] = hs::pipe_pos(T_first - 2 * tid, L); };
+    auto step = [&](const hs::PipeStep &s) {
+        auto fetch = [&](int tid) {
+            hs::RowPos p = base[tid];
+            for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L)) {
+                const hs::RowPos chk = hs::pipe_pos(s.T - 2 * i, L);
+                if (chk.n != p.n || chk.j != p.j) abort();
+                hs::pipe_issue_row(V, s, i, p, cp);
+            }
+        };
+        auto update = [&](int tid) {
+            hs::RowPos p = base[tid];
+            if (s.T >= 1)
+                for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L))
+                    hs::pipe_compute_row(V, s, i, p);
+        };
+        if (phase == 0) {
+            thread_order(ord, order, rng); for (int tid : ord) fetch(tid);
+            thread_order(ord, order, rng); for (int tid : ord) update(tid);
+        } else if (phase == 1) {
+            thread_order(ord, order, rng); for (int tid : ord) { fetch(tid); update(tid); }
+        } else {
+            thread_order(ord, order, rng); for (int tid : ord) update(tid);
+            thread_order(ord, order, rng); for (int tid : ord) fetch(tid);
+        }
+        cp.commit();
+        for (int tid = 0; tid < nthreads; tid++) base[tid] = hs::pipe_pos_add(base[tid], 1, L);
+    };
+
+    // speculative phase
+    V.limit = maxiter;
+    V.account = 1;
+    reset_positions();
+    int decided = 0, niter = 0;
+    double error = 1000;
+    hs::PipeStep s = hs::pipe_make_step(V, T_first);
+    for (int T = T_first;; T++, hs::pipe_advance(V, s)) {
+        cp.wait(P);                                         // cp.async.wait_group P; __syncthreads()
+        const hs::PipeStep chk = hs::pipe_make_step(V, T);
+        if (memcmp(&s, &chk, sizeof s) != 0) return -2;
+        if (T == hs::pipe_t_done(decided, L, nx, ny) + 1) {
+            double e = 0;
+            for (int r = 0; r < ny; r++) e += part[(size_t) (decided % V.D) * V.rp + r];   // fixed order
+            error = sqrt(e / (nx * ny));
+            niter = ++decided;
+            if (!(error > tol && niter < maxiter)) break;   // (an extra barrier in the kernel)
+        }
+        step(s);
+    }
+    cp.wait(0);
+    int rep = 0;
+    if (niter < maxiter) {
+        const int m = (niter / V.K) * V.K;
+        const std::vector<hs::F2> &src = ((niter / V.K) & 1) ? snap1 : snap0;
+        std::copy(src.begin(), src.end(), wuv.begin());
+        rep = niter - m;
+        if (rep > 0) {
+            V.limit = rep;
+            V.account = 0;
+            std::fill(ring.begin(), ring.end(), hs::F2{ nanf(""), nanf("") });
+            reset_positions();
+            hs::PipeStep r = hs::pipe_make_step(V, T_first);
+            for (int T = T_first; T <= hs::pipe_t_done(rep - 1, L, nx, ny); T++, hs::pipe_advance(V, r)) {
+                cp.wait(P);
+                step(r);
+            }
+            cp.wait(0);
+        }
+    }
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) {
+            const int w = hs::pipe_wave_index(i, j, L, ny), p = i * nx + j;
+            u[p] = wuv[w].x;
+            v[p] = wuv[w].y;
+        }
+    if (err_out) *err_out = error;
+    if (replayed) *replayed = rep;
     return niter;
 }
 

@@ -93,6 +93,39 @@ def test_sor_kernel_with_rings_in_global_memory(gpu, nx, ny, prefetch):
     assert abs(gerr - rerr) <= 1e-9 * max(1.0, rerr)
 
 
+# ---- the pipelined kernel (k_hs_sor_pipe; prefetch = -3 forces it through the hook) -------------------
+
+@pytest.mark.parametrize("nx,ny,sweeps", [(37, 29, 7), (64, 48, 7), (131, 70, 5), (33, 200, 5), (40, 1100, 3), (17, 3, 9),
+                                          (1920, 1080, 3)])
+def test_pipelined_sor_kernel_is_the_sequential_sweep_bitwise(gpu, nx, ny, sweeps):
+    ix, iy, rho, u, v, _ = _hs_emu.system(nx, ny, seed=nx * 100 + ny)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, 0.0, sweeps)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=0.0, maxiter=sweeps, prefetch=-3)
+    assert gn == rn == sweeps
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv), (np.abs(gu - ru).max(), np.abs(gv - rv).max())
+    assert abs(gerr - rerr) <= 1e-9 * max(1.0, rerr)
+
+
+@pytest.mark.parametrize("nx,ny", [(96, 80), (64, 300)])
+@pytest.mark.parametrize("tol", [1e-1, 1e-2, 1e-3])
+def test_pipelined_sor_kernel_stops_exactly(gpu, nx, ny, tol):
+    """A stop by TOL: the upper rows had run ahead; snapshot restore + replay give the sequential loop's
+    state and sweep count bit for bit."""
+    ix, iy, rho, u, v, _ = _hs_emu.system(nx, ny, seed=3)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, tol, 150)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=tol, maxiter=150, prefetch=-3)
+    assert 1 < rn < 150 and gn == rn
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv)
+    assert abs(gerr - rerr) <= 1e-9 * max(1.0, rerr)
+
+
+def test_pipelined_sor_kernel_refuses_narrow_levels(gpu):
+    ix, iy, rho, u, v, _ = _hs_emu.system(9, 12, seed=1)
+    with pytest.raises(pkg.TVL1Error) as e:
+        gpu.sor(ix, iy, rho, u, v, prefetch=-3)
+    assert e.value.code == 3
+
+
 def test_sor_kernel_rejects_unsupported_sizes(gpu):
     z = np.zeros((2, 8), np.float32)
     with pytest.raises(pkg.TVL1Error) as e:

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import _hs_emu
-from _hs_emu import run_seq, run_wave, system
+from _hs_emu import run_pipe_wave, run_seq, run_wave, system
 
 
 SHAPES = [(3, 3), (4, 3), (3, 4), (5, 3), (3, 9), (9, 3), (4, 4), (5, 7), (8, 5), (12, 9), (37, 29), (64, 48), (23, 70)]
@@ -62,3 +62,42 @@ def test_fp32_sequential_sweep_tracks_the_fp64_oracle(oracle_f64, nx, ny):
     assert sn == on
     assert np.abs(su - ou).max() < 2e-4 and np.abs(sv - ov).max() < 2e-4
     assert abs(serr - oerr) < 1e-5
+
+
+# ---- the pipelined schedule (hs_sor_pipe.h) ------------------------------------------------------
+
+@pytest.mark.parametrize("nx,ny", SHAPES + [(70, 23)])
+def test_pipelined_schedule_equals_sequential_loop_fixed_count(nx, ny):
+    ix, iy, rho, u, v, _ = system(nx, ny, seed=nx * 100 + ny)
+    for maxiter in (1, 2, 7):
+        ref = run_seq(ix, iy, rho, u, v, 7.0, 0.0, maxiter)
+        for P in (0, 1, 3):
+            for nthreads in sorted({1, 3, ny, ny + 5}):
+                for order in range(3):
+                    for phase in range(3):
+                        for land in range(3):
+                            got = run_pipe_wave(ix, iy, rho, u, v, 7.0, 0.0, maxiter, 4, P, nthreads, order, phase,
+                                                land, seed=P * 7 + order)
+                            key = (maxiter, P, nthreads, order, phase, land)
+                            assert got[2] == ref[2] == maxiter, key
+                            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), key
+                            assert abs(got[3] - ref[3]) <= 1e-12 * max(1.0, ref[3]), key
+                            assert got[4] == 0, key
+
+
+@pytest.mark.parametrize("nx,ny", [(12, 9), (37, 29), (64, 48), (23, 70), (70, 23)])
+@pytest.mark.parametrize("K", [1, 4, 8])
+def test_pipelined_schedule_stops_exactly_where_the_sequential_loop_stops(nx, ny, K):
+    ix, iy, rho, u, v, _ = system(nx, ny, seed=7 * nx + ny)
+    seen = set()
+    for tol in (3e-1, 1e-1, 3e-2, 1e-2, 3e-3, 1e-3):
+        ref = run_seq(ix, iy, rho, u, v, 7.0, tol, 150)
+        if ref[2] in seen:
+            continue
+        seen.add(ref[2])
+        for order, phase, land in ((0, 0, 0), (1, 2, 1), (2, 1, 2), (2, 0, 2)):
+            got = run_pipe_wave(ix, iy, rho, u, v, 7.0, tol, 150, K, 1 + order, max(1, ny // 2), order, phase, land)
+            assert got[2] == ref[2], (tol, order, got[2], ref[2])
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), (tol, order)
+            assert abs(got[3] - ref[3]) <= 1e-12 * max(1.0, ref[3])
+    assert len(seen) >= 3
