@@ -93,11 +93,12 @@ bool hs_pipe_fits(const Workspace &w, const Level &l)
     return l.nx >= 17 && (size_t) 5 * L * l.ny <= 6 * w.plane0 && hs_pipe_prefetch(l.ny, -1) >= 0;
 }
 
-// HS_PIPELINE=1 selects the pipelined kernel wherever it fits (default: the one-sweep kernel).
+// The pipelined kernel serves every level it fits; HS_PIPELINE=0 keeps the one-sweep kernel everywhere
+// (A/B measurements -- both give the bits of the sequential sweep).
 bool hs_pipe_enabled()
 {
     const char *e = std::getenv("HS_PIPELINE");
-    return e && std::atoi(e) != 0;
+    return !e || std::atoi(e) != 0;
 }
 
 bool hs_level_pipelined(const tvl1_ctx *ctx, const Level &l, int prefetch)
