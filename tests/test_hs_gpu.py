@@ -1,7 +1,8 @@
 """GPU parity tests of the pyramidal Horn-Schunck path (include/hs_b200.h) through the C ABI.
 
-* the SOR kernel against the sequential lexicographic sweep in the same fp32 arithmetic: BIT-EXACT
-  (the wavefront schedule must not change a single neighbour value);
+* the SOR kernels (one-sweep, pipelined, rings in global memory) against the sequential lexicographic
+  sweep in the same fp32 arithmetic: BIT-EXACT (the wavefront schedules must not change a single
+  neighbour value, nor the sweep at which the loop stops);
 * the solver against the committed golden vectors of the unmodified reference (one thread) and
   against the oracle: identical sweep counts per (level, warp), flow within the tolerance
   BASELINE.json's north_star states for the fp32 path (mean |d| <= 1e-3 px, max |d| <= 1e-2 px);
