@@ -101,11 +101,68 @@ bool hs_pipe_enabled()
     return !e || std::atoi(e) != 0;
 }
 
-bool hs_level_pipelined(const tvl1_ctx *ctx, const Level &l, int prefetch)
+int hs_threads(const Level &l)
+{
+    // rows per thread as even as possible: ceil(ny / ceil(ny / 1024)) threads, whole warps
+    const int rows_per_thread = ceil_div(l.ny, kHsMaxThreads);
+    return std::min(kHsMaxThreads, round_up(ceil_div(l.ny, rows_per_thread), 32));
+}
+
+// CTAs of a kernel variant one SM holds (registers, shared memory, threads), 0 if unknown.
+template <class K>
+int hs_ctas_per_sm(K kernel, int threads, size_t smem)
+{
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kHsSmemOneCta) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb;
+}
+
+int hs_ctas_per_sm_one(int P, int threads, size_t smem)
+{
+    switch (P) {
+    case 0: return hs_ctas_per_sm(k_hs_sor<0, false>, threads, smem);
+    case 1: return hs_ctas_per_sm(k_hs_sor<1, false>, threads, smem);
+    case 2: return hs_ctas_per_sm(k_hs_sor<2, false>, threads, smem);
+    default: return hs_ctas_per_sm(k_hs_sor<3, false>, threads, smem);
+    }
+}
+
+int hs_ctas_per_sm_pipe(int P, int threads, size_t smem)
+{
+    switch (P) {
+    case 0: return hs_ctas_per_sm(k_hs_sor_pipe<0>, threads, smem);
+    case 1: return hs_ctas_per_sm(k_hs_sor_pipe<1>, threads, smem);
+    case 2: return hs_ctas_per_sm(k_hs_sor_pipe<2>, threads, smem);
+    default: return hs_ctas_per_sm(k_hs_sor_pipe<3>, threads, smem);
+    }
+}
+
+// Which SOR kernel serves level l for a batch of B pairs.  Measured on 1920x1080:
+// the pipelined kernel is 1.2x faster CTA for CTA, but it needs 64 registers per thread, so at 544
+// threads only ONE of its CTAs fits an SM where TWO of the one-sweep kernel do -- and two resident pairs
+// per SM are worth 1.47x.  So: pipelined, unless the batch needs more CTAs than the pipelined kernel can
+// keep resident while the one-sweep kernel could hold more per SM.  (Both give the same bits.)
+bool hs_level_pipelined(tvl1_ctx *ctx, const Level &l, int B, int prefetch)
 {
     if (prefetch == kHsForcePipelined) return true;
     if (prefetch != -1) return false;
-    return hs_pipe_enabled() && hs_pipe_fits(ctx->ws, l);
+    if (!hs_pipe_enabled() || !hs_pipe_fits(ctx->ws, l)) return false;
+    const int P_one = hs_pick_prefetch(l.ny, -1);
+    if (P_one < 0) return true;                       // the one-sweep kernel would need its rings in global memory
+    const int threads = hs_threads(l), rp = round_up(l.ny, 32);
+    const int P_pipe = hs_pipe_prefetch(l.ny, -1);
+    const int nb_pipe = hs_ctas_per_sm_pipe(P_pipe, threads, hs_pipe_smem(P_pipe, rp));
+    if (nb_pipe < 1 || B <= nb_pipe * ctx->sm_count) return true;
+    const int nb_one = hs_ctas_per_sm_one(P_one, threads, hs_ring_bytes(P_one, rp));
+    return nb_one <= nb_pipe;
 }
 
 // Snapshot planes (2 x float2 x L ny per pair) and error sums (D x rp doubles per pair) for the largest level.
@@ -128,11 +185,10 @@ int hs_ensure_pipe_buffers(tvl1_ctx *ctx)
 }
 
 // The SOR loop of one warp step for every pair of the batch: one launch, one CTA per pair.
-int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_slot, int prefetch = -1)
+int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_slot, bool pipe, int prefetch = -1)
 {
     Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
-    const bool pipe = hs_level_pipelined(ctx, l, prefetch);
     int want = prefetch;
     if (want < 0) {
         want = -1;
@@ -147,9 +203,7 @@ int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_sl
     A.stat_iters = w.stat_iters; A.stat_errs = w.stat_errs;
     A.stat_stride = w.stat_stride; A.stat_slot = stat_slot;
     A.px_iters = w.counters; A.level = std::min(s, TVL1_MAX_LEVELS - 1);
-    // rows per thread as even as possible: ceil(ny / ceil(ny / 1024)) threads, whole warps
-    const int rows_per_thread = ceil_div(l.ny, kHsMaxThreads);
-    const int threads = std::min(kHsMaxThreads, round_up(ceil_div(l.ny, rows_per_thread), 32));
+    const int threads = hs_threads(l);
     if (pipe) {
         if (!hs_pipe_fits(w, l)) return fail_arg(ctx, "Horn-Schunck: level does not fit the pipelined kernel");
         const int P = hs_pipe_prefetch(l.ny, want);
@@ -226,9 +280,9 @@ int hs_run_level(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_bas
             TRY(launch_warp(ctx, s, B));                                    // :114, :123-125, dif of :130
         }
         Span sp(ctx, 0, std::min(s, TVL1_MAX_LEVELS - 1));
-        const bool pipe = hs_level_pipelined(ctx, ctx->ws.lv[s], -1);
+        const bool pipe = hs_level_pipelined(ctx, ctx->ws.lv[s], B, -1);
         TRY(hs_launch_to_wave(ctx, s, B, pipe));
-        TRY(hs_launch_sor(ctx, s, B, prm, stat_base + wi));                 // :127-137 (on the fly), :139-231
+        TRY(hs_launch_sor(ctx, s, B, prm, stat_base + wi, pipe));           // :127-137 (on the fly), :139-231
         TRY(hs_launch_from_wave(ctx, s, B, pipe));
     }
     return TVL1_OK;
@@ -433,10 +487,10 @@ int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float 
         CKL(ctx);
     }
     hs_params prm{ alpha, 1, 0.5, 1, tol, maxiter };
-    const bool pipe = hs_level_pipelined(ctx, w.lv[0], prefetch);
+    const bool pipe = hs_level_pipelined(ctx, w.lv[0], 1, prefetch);
     if (pipe && !hs_pipe_fits(w, w.lv[0])) return fail_arg(ctx, "Horn-Schunck: level does not fit the pipelined kernel");
     TRY(hs_launch_to_wave(ctx, 0, 1, pipe));
-    TRY(hs_launch_sor(ctx, 0, 1, prm, 0, prefetch));
+    TRY(hs_launch_sor(ctx, 0, 1, prm, 0, pipe, prefetch));
     TRY(hs_launch_from_wave(ctx, 0, 1, pipe));
     k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0], buf,
                                              buf + n);
