@@ -1,7 +1,10 @@
-"""Design prototype ("Next for this kernel"): the PIPELINED Horn-Schunck SOR
-schedule -- sweep n of row i at time n*L + 2i + j with L = nx + 2, so that all rows work all the time --
-with snapshot + replay for the exact stopping rule, modelled on the CPU (tests/c/hs_pipeline_emu.cpp)
-and compared bit for bit with the sequential sweep, sweep count included.  Not yet a kernel."""
+"""Design prototypes of Horn-Schunck SOR schedules, modelled on plain arrays on the
+CPU and compared bit for bit with the sequential sweep, sweep count included:
+
+* tests/c/hs_pipeline_emu.cpp -- PIPELINED sweeps: sweep n of row i at time n*L + 2i + j with L = nx + 2, all
+  rows busy all the time, snapshot + replay for the exact stopping rule.  Built since: k_hs_sor_pipe.
+* tests/c/hs_pairs_emu.cpp -- the next step, not yet a kernel: TWO columns per thread-step on top of it
+  (pair c = columns 2c, 2c+1 at time n*L + 2i + c)."""
 import ctypes as C
 import os
 import subprocess
@@ -13,29 +16,32 @@ import pytest
 import _hs_emu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "tests", "c", "hs_pipeline_emu.cpp")
 
 
-@pytest.fixture(scope="module")
-def pipe():
-    so = os.path.join(tempfile.mkdtemp(prefix="hs_pipe_"), "libhs_pipe.so")
+SOURCES = {"hs_emu_pipe_sor": "hs_pipeline_emu.cpp", "hs_emu_pairs_sor": "hs_pairs_emu.cpp"}
+
+
+@pytest.fixture(scope="module", params=sorted(SOURCES))
+def pipe(request):
+    """The model under test: (library, entry point)."""
+    name = request.param
+    so = os.path.join(tempfile.mkdtemp(prefix="hs_pipe_"), "lib%s.so" % name)
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra", "-Werror", "-shared",
-                    "-o", so, SRC, "-lm"], check=True)
+                    "-o", so, os.path.join(ROOT, "tests", "c", SOURCES[name]), "-lm"], check=True)
     lib = C.CDLL(so)
     vp, i, f, d = C.c_void_p, C.c_int, C.c_float, C.c_double
-    lib.hs_emu_pipe_sor.argtypes = [vp, vp, vp, vp, vp, i, i, f, d, i, i, i, i, C.c_uint, C.POINTER(d),
-                                    C.POINTER(i), C.POINTER(i)]
-    lib.hs_emu_pipe_sor.restype = i
-    return lib
+    fn = getattr(lib, name)
+    fn.argtypes = [vp, vp, vp, vp, vp, i, i, f, d, i, i, i, i, C.c_uint, C.POINTER(d), C.POINTER(i), C.POINTER(i)]
+    fn.restype = i
+    return fn
 
 
-def run_pipe(lib, ix, iy, rho, u, v, alpha, tol, maxiter, K, nthreads, order, seed=1):
+def run_pipe(fn, ix, iy, rho, u, v, alpha, tol, maxiter, K, nthreads, order, seed=1):
     u, v = u.copy(), v.copy()
     ny, nx = u.shape
     err, rep, spec = C.c_double(), C.c_int(), C.c_int()
-    n = lib.hs_emu_pipe_sor(u.ctypes.data, v.ctypes.data, ix.ctypes.data, iy.ctypes.data, rho.ctypes.data, nx, ny,
-                            alpha * alpha, tol, maxiter, K, nthreads, order, seed, C.byref(err), C.byref(rep),
-                            C.byref(spec))
+    n = fn(u.ctypes.data, v.ctypes.data, ix.ctypes.data, iy.ctypes.data, rho.ctypes.data, nx, ny, alpha * alpha, tol,
+           maxiter, K, nthreads, order, seed, C.byref(err), C.byref(rep), C.byref(spec))
     return u, v, n, err.value, rep.value, spec.value
 
 
@@ -77,5 +83,5 @@ def test_pipelined_sweeps_stop_exactly_where_the_sequential_loop_stops(pipe, nx,
             assert abs(got[3] - ref[3]) <= 1e-12 * max(1.0, ref[3])
             if ref[2] < 150:
                 assert got[5] >= 1                     # speculative sweeps had been started ...
-                assert got[4] < max(K, (2 * ny + nx) // max(nx + 2, 8) + 2)     # ... and at most K-1 were replayed
+                assert got[4] < max(K, (2 * ny + nx) // 8 + 2)     # ... and fewer than a snapshot period were replayed
     assert len(seen) >= 3
