@@ -79,7 +79,8 @@ int hs_single_scale_f64(tvl1_ctx *ctx, const double *I1, const double *I2, doubl
  * (src/horn_schunck_pyramidal.cpp:127-137 in terms of these: Au = -rho_c*I2wx, Du = I2wx^2 + alpha^2,
  * D = I2wx*I2wy).  u, v in/out.  prefetch = -1 picks the prefetch distance automatically, 0..3 forces
  * it (one-sweep kernel), -2 forces the rings into global memory (the path of levels with more than
- * ~HS_MAX_ROWS rows), -3 forces the pipelined kernel (the default wherever a level fits it).
+ * ~HS_MAX_ROWS rows), -3 forces the pipelined kernel (the default wherever a level fits it), -4 the
+ * experimental two-columns-per-step kernel (not yet validated on a GPU; never selected by default).
  * Outputs: sweeps done and the last sqrt(mean squared update). */
 int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float *rho_c, float *u, float *v,
                int nx, int ny, double alpha, double tol, int maxiter, int prefetch, int *niter_out,

@@ -69,6 +69,9 @@ int hs_launch_pipe_p(tvl1_ctx *ctx, const HsSorParams &A, int B, int threads, si
 // hs_sor_f32(prefetch = ...): tests force a kernel variant
 constexpr int kHsForceGlobalRing = -2;     // rings in global memory
 constexpr int kHsForcePipelined = -3;      // pipelined sweeps (k_hs_sor_pipe)
+constexpr int kHsForcePairs = -4;          // pipelined sweeps, two columns per thread-step (k_hs_sor_pairs, experimental)
+
+enum HsKernel { HS_ONE_SWEEP = 0, HS_PIPELINED = 1, HS_PAIRS = 2 };
 
 // ---- pipelined sweeps (k_hs_sor_pipe, hs_sor_pipe.h) ------------------------------------------------
 // Shared memory of a CTA: the rings plus one double per (padded) row.
@@ -91,6 +94,41 @@ bool hs_pipe_fits(const Workspace &w, const Level &l)
 {
     const int L = hs::pipe_period(l.nx);
     return l.nx >= 17 && (size_t) 5 * L * l.ny <= 6 * w.plane0 && hs_pipe_prefetch(l.ny, -1) >= 0;
+}
+
+// ---- two columns per thread-step (k_hs_sor_pairs; EXPERIMENTAL: not yet run on a GPU, HS_PAIRS=1 only) ----
+int hs_pairs_prefetch(int ny, int want)
+{
+    const int rp = round_up(ny, 32);
+    if (want >= 0 && want <= hs::kMaxPrefetch) return hs_pairs_smem(want, rp) <= kHsSmemOneCta ? want : -1;
+    if (hs_pairs_smem(1, rp) <= kHsSmemOneCta) return 1;
+    if (hs_pairs_smem(0, rp) <= kHsSmemOneCta) return 0;
+    return -1;
+}
+
+bool hs_pairs_fits(const Workspace &w, const Level &l)
+{
+    const int L = hs::pairs_period(l.nx);
+    return l.nx >= 32 && (size_t) 10 * L * l.ny <= 6 * w.plane0 && hs_pairs_prefetch(l.ny, -1) >= 0;
+}
+
+bool hs_pairs_enabled()
+{
+    const char *e = std::getenv("HS_PAIRS");
+    return e && std::atoi(e) != 0;
+}
+
+template <int P>
+int hs_launch_pairs_p(tvl1_ctx *ctx, const HsSorParams &A, int B, int threads, size_t smem)
+{
+    static bool attr_done[64] = { false };
+    if (!attr_done[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(k_hs_sor_pairs<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kHsSmemOneCta));
+        attr_done[ctx->device & 63] = true;
+    }
+    k_hs_sor_pairs<P><<<B, threads, smem, ctx->stream>>>(A);
+    CKL(ctx);
+    return TVL1_OK;
 }
 
 // The pipelined kernel serves every level it fits; HS_PIPELINE=0 keeps the one-sweep kernel everywhere
@@ -150,6 +188,15 @@ int hs_ctas_per_sm_pipe(int P, int threads, size_t smem)
 // threads only ONE of its CTAs fits an SM where TWO of the one-sweep kernel do -- and two resident pairs
 // per SM are worth 1.47x.  So: pipelined, unless the batch needs more CTAs than the pipelined kernel can
 // keep resident while the one-sweep kernel could hold more per SM.  (Both give the same bits.)
+bool hs_level_pipelined(tvl1_ctx *ctx, const Level &l, int B, int prefetch);
+
+HsKernel hs_level_kernel(tvl1_ctx *ctx, const Level &l, int B, int prefetch)
+{
+    if (prefetch == kHsForcePairs) return HS_PAIRS;
+    if (prefetch == -1 && hs_pairs_enabled() && hs_pairs_fits(ctx->ws, l)) return HS_PAIRS;
+    return hs_level_pipelined(ctx, l, B, prefetch) ? HS_PIPELINED : HS_ONE_SWEEP;
+}
+
 bool hs_level_pipelined(tvl1_ctx *ctx, const Level &l, int B, int prefetch)
 {
     if (prefetch == kHsForcePipelined) return true;
@@ -172,8 +219,10 @@ int hs_ensure_pipe_buffers(tvl1_ctx *ctx)
     size_t snap = 0, part = 0;
     for (const Level &l : w.lv) {
         const int L = hs::pipe_period(l.nx);
-        snap = std::max(snap, (size_t) 4 * L * l.ny);
-        part = std::max(part, (size_t) hs::pipe_error_depth(L, l.nx, l.ny) * round_up(l.ny, 32));
+        const int Lp = hs::pairs_period(l.nx);
+        snap = std::max(snap, std::max((size_t) 4 * L * l.ny, (size_t) 8 * Lp * l.ny));
+        part = std::max(part, (size_t) std::max(hs::pipe_error_depth(L, l.nx, l.ny),
+                                                hs::pairs_error_depth(Lp, l.nx, l.ny)) * round_up(l.ny, 32));
     }
     if (w.hs_snap && w.hs_snap_stride >= snap && w.hs_part_stride >= part) return TVL1_OK;
     cudaFree(w.hs_snap); cudaFree(w.hs_part);
@@ -185,7 +234,7 @@ int hs_ensure_pipe_buffers(tvl1_ctx *ctx)
 }
 
 // The SOR loop of one warp step for every pair of the batch: one launch, one CTA per pair.
-int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_slot, bool pipe, int prefetch = -1)
+int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_slot, HsKernel kern, int prefetch = -1)
 {
     Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
@@ -204,6 +253,29 @@ int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_sl
     A.stat_stride = w.stat_stride; A.stat_slot = stat_slot;
     A.px_iters = w.counters; A.level = std::min(s, TVL1_MAX_LEVELS - 1);
     const int threads = hs_threads(l);
+    const bool pipe = kern == HS_PIPELINED;
+    if (kern == HS_PAIRS) {
+        if (!hs_pairs_fits(w, l)) return fail_arg(ctx, "Horn-Schunck: level does not fit the two-column kernel");
+        const int P = hs_pairs_prefetch(l.ny, want);
+        if (P < 0) return fail_arg(ctx, "Horn-Schunck: prefetch distance does not fit shared memory");
+        TRY(hs_ensure_pipe_buffers(ctx));
+        A.L = hs::pairs_period(l.nx);
+        int K = 8;
+        if (const char *e = std::getenv("HS_SNAP_K")) K = std::max(1, std::atoi(e));
+        A.K = hs::pairs_snapshot_period(K, A.L, l.nx, l.ny);
+        A.D = hs::pairs_error_depth(A.L, l.nx, l.ny);
+        A.snap = w.hs_snap; A.snap_stride = w.hs_snap_stride;
+        A.part = w.hs_part; A.part_stride = w.hs_part_stride;
+        const size_t smem = hs_pairs_smem(P, A.rp);
+        switch (P) {
+        case 0: TRY(hs_launch_pairs_p<0>(ctx, A, B, threads, smem)); break;
+        case 1: TRY(hs_launch_pairs_p<1>(ctx, A, B, threads, smem)); break;
+        case 2: TRY(hs_launch_pairs_p<2>(ctx, A, B, threads, smem)); break;
+        default: TRY(hs_launch_pairs_p<3>(ctx, A, B, threads, smem)); break;
+        }
+        ctx->stats.iterate_launches++;
+        return TVL1_OK;
+    }
     if (pipe) {
         if (!hs_pipe_fits(w, l)) return fail_arg(ctx, "Horn-Schunck: level does not fit the pipelined kernel");
         const int P = hs_pipe_prefetch(l.ny, want);
@@ -245,12 +317,22 @@ int hs_launch_sor(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_sl
     return TVL1_OK;
 }
 
-// pipe: wave planes with period L (and the initial snapshot) for k_hs_sor_pipe, else period nx
-int hs_launch_to_wave(tvl1_ctx *ctx, int s, int B, bool pipe)
+// wave planes with period L (and the initial snapshot) for k_hs_sor_pipe, pair planes for k_hs_sor_pairs,
+// else period nx
+int hs_launch_to_wave(tvl1_ctx *ctx, int s, int B, HsKernel kern)
 {
-    if (pipe) TRY(hs_ensure_pipe_buffers(ctx));
+    const bool pipe = kern == HS_PIPELINED;
+    if (kern != HS_ONE_SWEEP) TRY(hs_ensure_pipe_buffers(ctx));
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
+    if (kern == HS_PAIRS) {
+        const int L = hs::pairs_period(l.nx);
+        dim3 g(ceil_div(L, 32), ceil_div(l.ny, 32), B);
+        k_hs_to_wave_pairs<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.consts, w.plane0, w.field_stride,
+                                                               w.set_stride, w.ctl, l, L, w.hs_snap, w.hs_snap_stride);
+        CKL(ctx);
+        return TVL1_OK;
+    }
     const int mod = pipe ? hs::pipe_period(l.nx) : l.nx;
     dim3 g(ceil_div(mod, 32), ceil_div(l.ny, 32), B);
     k_hs_to_wave<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.consts, w.plane0, w.field_stride, w.set_stride,
@@ -259,10 +341,19 @@ int hs_launch_to_wave(tvl1_ctx *ctx, int s, int B, bool pipe)
     return TVL1_OK;
 }
 
-int hs_launch_from_wave(tvl1_ctx *ctx, int s, int B, bool pipe)
+int hs_launch_from_wave(tvl1_ctx *ctx, int s, int B, HsKernel kern)
 {
+    const bool pipe = kern == HS_PIPELINED;
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
+    if (kern == HS_PAIRS) {
+        const int L = hs::pairs_period(l.nx);
+        dim3 g(ceil_div(L, 32), ceil_div(l.ny, 32), B);
+        k_hs_from_wave_pairs<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl,
+                                                                 l, L);
+        CKL(ctx);
+        return TVL1_OK;
+    }
     const int mod = pipe ? hs::pipe_period(l.nx) : l.nx;
     dim3 g(ceil_div(mod, 32), ceil_div(l.ny, 32), B);
     k_hs_from_wave<<<g, dim3(32, 8), 0, ctx->stream>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, l,
@@ -280,10 +371,10 @@ int hs_run_level(tvl1_ctx *ctx, int s, int B, const hs_params &prm, int stat_bas
             TRY(launch_warp(ctx, s, B));                                    // :114, :123-125, dif of :130
         }
         Span sp(ctx, 0, std::min(s, TVL1_MAX_LEVELS - 1));
-        const bool pipe = hs_level_pipelined(ctx, ctx->ws.lv[s], B, -1);
-        TRY(hs_launch_to_wave(ctx, s, B, pipe));
-        TRY(hs_launch_sor(ctx, s, B, prm, stat_base + wi, pipe));           // :127-137 (on the fly), :139-231
-        TRY(hs_launch_from_wave(ctx, s, B, pipe));
+        const HsKernel kern = hs_level_kernel(ctx, ctx->ws.lv[s], B, -1);
+        TRY(hs_launch_to_wave(ctx, s, B, kern));
+        TRY(hs_launch_sor(ctx, s, B, prm, stat_base + wi, kern));           // :127-137 (on the fly), :139-231
+        TRY(hs_launch_from_wave(ctx, s, B, kern));
     }
     return TVL1_OK;
 }
@@ -459,7 +550,7 @@ int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float 
     if (!ctx) return TVL1_ERR_ARG;
     if (!I2wx || !I2wy || !rho_c || !u || !v) return fail_arg(ctx, "null pointer argument");
     if (!(alpha > 0.0) || maxiter < 1) return fail_arg(ctx, "alpha must be positive and maxiter >= 1");
-    if (prefetch > hs::kMaxPrefetch || prefetch < kHsForcePipelined) return fail_arg(ctx, "prefetch must be -3 .. 3");
+    if (prefetch > hs::kMaxPrefetch || prefetch < kHsForcePairs) return fail_arg(ctx, "prefetch must be -4 .. 3");
     CK(cudaSetDevice(ctx->device));
     reset_stats(ctx);
     TRY(ensure_workspace(ctx, nx, ny, 1, 0.5, 1, 1));
@@ -487,11 +578,14 @@ int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float 
         CKL(ctx);
     }
     hs_params prm{ alpha, 1, 0.5, 1, tol, maxiter };
-    const bool pipe = hs_level_pipelined(ctx, w.lv[0], 1, prefetch);
-    if (pipe && !hs_pipe_fits(w, w.lv[0])) return fail_arg(ctx, "Horn-Schunck: level does not fit the pipelined kernel");
-    TRY(hs_launch_to_wave(ctx, 0, 1, pipe));
-    TRY(hs_launch_sor(ctx, 0, 1, prm, 0, pipe, prefetch));
-    TRY(hs_launch_from_wave(ctx, 0, 1, pipe));
+    const HsKernel kern = hs_level_kernel(ctx, w.lv[0], 1, prefetch);
+    if (kern == HS_PIPELINED && !hs_pipe_fits(w, w.lv[0]))
+        return fail_arg(ctx, "Horn-Schunck: level does not fit the pipelined kernel");
+    if (kern == HS_PAIRS && !hs_pairs_fits(w, w.lv[0]))
+        return fail_arg(ctx, "Horn-Schunck: level does not fit the two-column kernel");
+    TRY(hs_launch_to_wave(ctx, 0, 1, kern));
+    TRY(hs_launch_sor(ctx, 0, 1, prm, 0, kern, prefetch));
+    TRY(hs_launch_from_wave(ctx, 0, 1, kern));
     k_export_flow<<<g, dim3(32, 8), 0, st>>>(w.state, w.plane0, w.field_stride, w.set_stride, w.ctl, w.lv[0], buf,
                                              buf + n);
     CKL(ctx);

@@ -30,6 +30,8 @@ def load():
         lib.hs_emu_pipe_wave_sor.argtypes = [vp, vp, vp, vp, vp, i, i, f, d_, i, i, i, i, i, i, i, C.c_uint,
                                              C.POINTER(d_), C.POINTER(i)]
         lib.hs_emu_pipe_wave_sor.restype = i
+        lib.hs_emu_pairs_wave_sor.argtypes = lib.hs_emu_pipe_wave_sor.argtypes
+        lib.hs_emu_pairs_wave_sor.restype = i
         _lib = lib
     return _lib
 
@@ -66,14 +68,15 @@ def run_wave(ix, iy, rho, u, v, alpha, tol, maxiter, P, nthreads, order, phase, 
     return u, v, n, err.value
 
 
-def run_pipe_wave(ix, iy, rho, u, v, alpha, tol, maxiter, K, P, nthreads, order, phase, land, seed=1):
-    """The PIPELINED schedule of k_hs_sor_pipe (hs_sor_pipe.h) replayed on the CPU -> (u, v, sweeps, error,
-    sweeps replayed after a restore)."""
+def run_pipe_wave(ix, iy, rho, u, v, alpha, tol, maxiter, K, P, nthreads, order, phase, land, seed=1, pairs=False):
+    """The PIPELINED schedule of k_hs_sor_pipe (hs_sor_pipe.h), or with pairs=True the two-columns-per-step
+    schedule of hs_sor_pairs.h, replayed on the CPU -> (u, v, sweeps, error, sweeps replayed after a restore)."""
     emu = load()
     u, v = u.copy(), v.copy()
     ny, nx = u.shape
     err, rep = C.c_double(), C.c_int()
-    n = emu.hs_emu_pipe_wave_sor(u.ctypes.data, v.ctypes.data, ix.ctypes.data, iy.ctypes.data, rho.ctypes.data,
+    fn = emu.hs_emu_pairs_wave_sor if pairs else emu.hs_emu_pipe_wave_sor
+    n = fn(u.ctypes.data, v.ctypes.data, ix.ctypes.data, iy.ctypes.data, rho.ctypes.data,
                                  nx, ny, alpha * alpha, tol, maxiter, K, P, nthreads, order, phase, land, seed,
                                  C.byref(err), C.byref(rep))
     return u, v, n, err.value, rep.value

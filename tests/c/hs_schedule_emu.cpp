@@ -12,6 +12,7 @@
 #define HS_SOR_EMULATE 1
 #include "../../optical-flow-1_b200/csrc/hs_sor_step.h"
 #include "../../optical-flow-1_b200/csrc/hs_sor_pipe.h"
+#include "../../optical-flow-1_b200/csrc/hs_sor_pairs.h"
 
 #include <stdint.h>
 #include <stdlib.h>
@@ -22,7 +23,7 @@
 
 namespace {
 
-struct Pending { float *dst; const float *src; float value[2]; int n; int group; };
+struct Pending { float *dst; const float *src; float value[4]; int n; int group; };
 
 struct EmuCp {
     std::vector<Pending> q;
@@ -31,11 +32,13 @@ struct EmuCp {
     void copy(float *dst, const float *src, int n)
     {
         if (land == 0) { for (int k = 0; k < n; k++) dst[k] = src[k]; return; }
-        Pending p{ dst, src, { src[0], n > 1 ? src[1] : 0.f }, n, group };
+        Pending p{ dst, src, { 0.f, 0.f, 0.f, 0.f }, n, group };
+        for (int k = 0; k < n; k++) p.value[k] = src[k];
         q.push_back(p);
     }
     void cp4(float *dst, const float *src) { copy(dst, src, 1); }
     void cp8(hs::F2 *dst, const hs::F2 *src) { copy(&dst->x, &src->x, 2); }
+    void cp16(hs::F4 *dst, const hs::F4 *src) { copy(&dst->x, &src->x, 4); }
     void commit() { group++; }
     // cp.async.wait_group n: at most the n most recently committed groups stay pending
     void wait(int n)
@@ -307,6 +310,126 @@ int hs_emu_pipe_wave_sor(float *u, float *v, const float *ix, const float *iy, c
             const int w = hs::pipe_wave_index(i, j, L, ny), p = i * nx + j;
             u[p] = wuv[w].x;
             v[p] = wuv[w].y;
+        }
+    if (err_out) *err_out = error;
+    if (replayed) *replayed = rep;
+    return niter;
+}
+
+// The two-columns-per-step schedule (hs_sor_pairs.h), driven exactly like hs_emu_pipe_wave_sor.
+int hs_emu_pairs_wave_sor(float *u, float *v, const float *ix, const float *iy, const float *rho, int nx, int ny,
+                          float alpha2, double tol, int maxiter, int K, int P, int nthreads, int order, int phase,
+                          int land, unsigned seed, double *err_out, int *replayed)
+{
+    if (nx < 3 || ny < 3 || P < 0 || P > hs::kMaxPrefetch || nthreads < 1 || maxiter < 1) return -1;
+    const int L = hs::pairs_period(nx);
+    const size_t n = (size_t) L * ny;
+    const float qn = nanf("");
+    std::vector<hs::F4> wuv(n, hs::F4{ qn, qn, qn, qn }), wxy(n, hs::F4{ qn, qn, qn, qn });
+    std::vector<hs::F2> wrho(n, hs::F2{ qn, qn });
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) {
+            const int w = hs::pairs_px_index(i, j, L, ny), p = i * nx + j;
+            ((hs::F2 *) wuv.data())[w] = hs::F2{ u[p], v[p] };
+            ((hs::F2 *) wxy.data())[w] = hs::F2{ ix[p], iy[p] };
+            ((float *) wrho.data())[w] = rho[p];
+        }
+    std::vector<hs::F4> snap0(wuv), snap1(wuv);
+
+    hs::PairsView V;
+    V.wuv = wuv.data(); V.wxy = wxy.data(); V.wrho = wrho.data();
+    V.snap0 = snap0.data(); V.snap1 = snap1.data();
+    V.nx = nx; V.ny = ny; V.L = L; V.alpha2 = alpha2;
+    V.cl = hs::pairs_cl(nx); V.cn = hs::pairs_cn(nx);
+    V.K = hs::pairs_snapshot_period(K, L, nx, ny);
+    V.D = hs::pairs_error_depth(L, nx, ny);
+    V.P = P; V.S = hs::kRingBase + P; V.CD = P + 2; V.rp = ny + 3;
+    std::vector<double> part((size_t) V.D * V.rp, nan("")), esum(V.rp, 0.0);
+    V.part = part.data(); V.esum = esum.data();
+    std::vector<hs::F4> ring((size_t) (V.S + V.CD) * V.rp, hs::F4{ qn, qn, qn, qn });
+    std::vector<hs::F2> ring_rho((size_t) V.CD * V.rp, hs::F2{ qn, qn });
+    V.ring_uv = ring.data();
+    V.cxy = V.ring_uv + (size_t) V.S * V.rp;
+    V.crho = ring_rho.data();
+    // PipeStep / pipe_make_step only use S, CD, L, P of the view
+    hs::PipeView W;
+    W.S = V.S; W.CD = V.CD; W.L = V.L; W.P = V.P;
+
+    EmuCp cp;
+    cp.land = land;
+    Rng rng{ seed * 2654435761ull + 1234567 };
+    std::vector<int> ord(nthreads);
+    const int T_first = -4 - P;
+    std::vector<hs::RowPos> base(nthreads);
+    const int step_dn = (2 * nthreads) / L, step_dj = (2 * nthreads) % L;
+    auto reset_positions = [&]() { for (int tid = 0; tid < nthreads; tid++) base[tid] = hs::pipe_pos(T_first - 2 * tid, L); };
+    auto step = [&](const hs::PipeStep &s) {
+        auto fetch = [&](int tid) {
+            hs::RowPos p = base[tid];
+            for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L))
+                hs::pairs_issue_row(V, s, i, p, cp);
+        };
+        auto update = [&](int tid) {
+            hs::RowPos p = base[tid];
+            if (s.T >= 0)
+                for (int i = tid; i < ny; i += nthreads, p = hs::pipe_pos_sub(p, step_dn, step_dj, L))
+                    hs::pairs_compute_row(V, s, i, p);
+        };
+        if (phase == 0) {
+            thread_order(ord, order, rng); for (int tid : ord) fetch(tid);
+            thread_order(ord, order, rng); for (int tid : ord) update(tid);
+        } else if (phase == 1) {
+            thread_order(ord, order, rng); for (int tid : ord) { fetch(tid); update(tid); }
+        } else {
+            thread_order(ord, order, rng); for (int tid : ord) update(tid);
+            thread_order(ord, order, rng); for (int tid : ord) fetch(tid);
+        }
+        cp.commit();
+        for (int tid = 0; tid < nthreads; tid++) base[tid] = hs::pipe_pos_add(base[tid], 1, L);
+    };
+
+    V.limit = maxiter;
+    V.account = 1;
+    reset_positions();
+    int decided = 0, niter = 0;
+    double error = 1000;
+    hs::PipeStep s = hs::pipe_make_step(W, T_first);
+    for (int T = T_first;; T++, hs::pipe_advance(W, s)) {
+        cp.wait(P);
+        if (T == hs::pairs_t_done(decided, L, nx, ny) + 1) {
+            double e = 0;
+            for (int r = 0; r < ny; r++) e += part[(size_t) (decided % V.D) * V.rp + r];
+            error = sqrt(e / (nx * ny));
+            niter = ++decided;
+            if (!(error > tol && niter < maxiter)) break;
+        }
+        step(s);
+    }
+    cp.wait(0);
+    int rep = 0;
+    if (niter < maxiter) {
+        const int m = (niter / V.K) * V.K;
+        const std::vector<hs::F4> &src = ((niter / V.K) & 1) ? snap1 : snap0;
+        std::copy(src.begin(), src.end(), wuv.begin());
+        rep = niter - m;
+        if (rep > 0) {
+            V.limit = rep;
+            V.account = 0;
+            std::fill(ring.begin(), ring.end(), hs::F4{ qn, qn, qn, qn });
+            reset_positions();
+            hs::PipeStep r = hs::pipe_make_step(W, T_first);
+            for (int T = T_first; T <= hs::pairs_t_done(rep - 1, L, nx, ny); T++, hs::pipe_advance(W, r)) {
+                cp.wait(P);
+                step(r);
+            }
+            cp.wait(0);
+        }
+    }
+    for (int i = 0; i < ny; i++)
+        for (int j = 0; j < nx; j++) {
+            const hs::F2 uv = ((const hs::F2 *) wuv.data())[hs::pairs_px_index(i, j, L, ny)];
+            u[i * nx + j] = uv.x;
+            v[i * nx + j] = uv.y;
         }
     if (err_out) *err_out = error;
     if (replayed) *replayed = rep;

@@ -101,3 +101,43 @@ def test_pipelined_schedule_stops_exactly_where_the_sequential_loop_stops(nx, ny
             assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), (tol, order)
             assert abs(got[3] - ref[3]) <= 1e-12 * max(1.0, ref[3])
     assert len(seen) >= 3
+
+
+# ---- two columns per thread-step (hs_sor_pairs.h; not yet a kernel) ------------------------------
+
+@pytest.mark.parametrize("nx,ny", SHAPES + [(70, 23), (6, 5), (7, 6)])
+def test_pairs_schedule_equals_sequential_loop_fixed_count(nx, ny):
+    ix, iy, rho, u, v, _ = system(nx, ny, seed=nx * 100 + ny)
+    for maxiter in (1, 2, 7):
+        ref = run_seq(ix, iy, rho, u, v, 7.0, 0.0, maxiter)
+        for P in (0, 1, 3):
+            for nthreads in sorted({1, 3, ny, ny + 5}):
+                for order in range(3):
+                    for phase in range(3):
+                        for land in range(3):
+                            got = run_pipe_wave(ix, iy, rho, u, v, 7.0, 0.0, maxiter, 4, P, nthreads, order, phase,
+                                                land, seed=P * 7 + order, pairs=True)
+                            key = (maxiter, P, nthreads, order, phase, land)
+                            assert got[2] == ref[2] == maxiter, key
+                            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), key
+                            assert abs(got[3] - ref[3]) <= 1e-12 * max(1.0, ref[3]), key
+                            assert got[4] == 0, key
+
+
+@pytest.mark.parametrize("nx,ny", [(12, 9), (37, 29), (64, 48), (23, 70), (70, 23)])
+@pytest.mark.parametrize("K", [1, 4, 8])
+def test_pairs_schedule_stops_exactly_where_the_sequential_loop_stops(nx, ny, K):
+    ix, iy, rho, u, v, _ = system(nx, ny, seed=7 * nx + ny)
+    seen = set()
+    for tol in (3e-1, 1e-1, 3e-2, 1e-2, 3e-3, 1e-3):
+        ref = run_seq(ix, iy, rho, u, v, 7.0, tol, 150)
+        if ref[2] in seen:
+            continue
+        seen.add(ref[2])
+        for order, phase, land in ((0, 0, 0), (1, 2, 1), (2, 1, 2), (2, 0, 2)):
+            got = run_pipe_wave(ix, iy, rho, u, v, 7.0, tol, 150, K, 1 + order, max(1, ny // 2), order, phase, land,
+                                pairs=True)
+            assert got[2] == ref[2], (tol, order, got[2], ref[2])
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), (tol, order)
+            assert abs(got[3] - ref[3]) <= 1e-12 * max(1.0, ref[3])
+    assert len(seen) >= 3
