@@ -97,8 +97,14 @@ int main(int argc, char **argv)
     int nx = 0, ny = 0;
     std::vector<float> frames;
     for (size_t k = 0; k < files.size(); k++) {
-        int w, h;
+        int w = 0, h = 0;
         float *img = iio_read_image_float(files[k], &w, &h);
+        if (!img || w < 1 || h < 1) {
+            // iio_lite reads binary/ASCII PGM (P5/P2) and PFM only; the reference's iio also takes PNG/JPEG/TIFF
+            fprintf(stderr, "ERROR: cannot read image '%s' (supported: PGM P2/P5, PFM)\n", files[k]);
+            free(img);
+            return EXIT_FAILURE;
+        }
         if (k == 0) { nx = w; ny = h; frames.resize(files.size() * (size_t) nx * ny); }
         if (w != nx || h != ny) {
             fprintf(stderr, "ERROR: input images size mismatch %dx%d != %dx%d\n", nx, ny, w, h);

@@ -132,6 +132,13 @@ __global__ void k_minmax(const float *__restrict__ in0, const float *__restrict_
     }
 }
 
+// One pixel of image_normalization_2: 255*(I-min)/den evaluated left to right as the reference does
+// (src/utils.cpp:315-316), every step IEEE-rounded and never contracted.
+__device__ __forceinline__ float normalize_px(float v, float mn, float den)
+{
+    return __fdiv_rn(__fmul_rn(255.0f, __fsub_rn(v, mn)), den);
+}
+
 // Separable Gaussian with the reference's boundary rule, optionally fused with the [0,255]
 // normalisation on load and with a decimation by D on store.
 //   gaussian            src/operators.cpp:506-624  (rows then columns, reflecting boundary:
@@ -170,15 +177,14 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
 #pragma unroll
     for (int i = 0; i < NW; i++) w[i] = taps.w[i];
 
-    // image_normalization_2 fused on load: (I - min) * (255 / den); the reference's
-    // "255*(I-min)/den" (src/utils.cpp:315-316) differs by one rounding
-    float mn = 0.f, scl = 1.f;
+    // image_normalization_2 fused on load, in the reference's own operation order
+    // 255*(I-min)/den (src/utils.cpp:315-316): subtract, multiply, IEEE-rounded divide
+    float mn = 0.f, den = 1.f;
     bool norm = false;
     if (mm) {
         mn = ord2f(mm[2 * (z % B)]);
-        const float den = ord2f(mm[2 * (z % B) + 1]) - mn;
+        den = ord2f(mm[2 * (z % B) + 1]) - mn;
         norm = den > 0.f;
-        if (norm) scl = 255.0f / den;
     }
     // tiles that do not touch the border skip the reflection arithmetic
     const bool interior = ix0 >= 0 && iy0 >= 0 && ix0 + iw <= nx && iy0 + ih <= ny;
@@ -197,7 +203,7 @@ k_gauss(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__r
                 gx = clampi(gx, 0, nx - 1);
             }
             float v = __ldg(row + gx);
-            if (norm) v = (v - mn) * scl;
+            if (norm) v = normalize_px(v, mn, den);
             s_in[ly][lx] = v;
         }
     }
@@ -275,13 +281,12 @@ k_gauss_march(const float *__restrict__ in, int in_pitch, size_t in_stride, floa
     float w[R + 1];
 #pragma unroll
     for (int i = 0; i <= R; i++) w[i] = taps.w[i];
-    float mn = 0.f, scl = 1.f;
+    float mn = 0.f, den = 1.f;
     bool norm = false;
     if (mm) {
         mn = ord2f(mm[2 * (z % B)]);
-        const float den = ord2f(mm[2 * (z % B) + 1]) - mn;
+        den = ord2f(mm[2 * (z % B) + 1]) - mn;
         norm = den > 0.f;
-        if (norm) scl = 255.0f / den;
     }
 
     float win[W][4];
@@ -314,7 +319,7 @@ k_gauss_march(const float *__restrict__ in, int in_pitch, size_t in_stride, floa
             }
             if (norm) {
 #pragma unroll
-                for (int k = 0; k < NIN; k++) v[OFF + k] = (v[OFF + k] - mn) * scl;
+                for (int k = 0; k < NIN; k++) v[OFF + k] = normalize_px(v[OFF + k], mn, den);
             }
             // row pass at the four output columns (window slot u)
 #pragma unroll
@@ -860,7 +865,7 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
 // iteration (epoch) e; `epoch` counts the exchanges this rank has taken part in.
 constexpr int kMaxRanks = 8;
 struct BandMailbox {
-    double sum[2][kMaxRanks];
+    double sum[2][kMaxRanks][kTbT];    // up to kTbT sums per exchange (one per iteration of a block)
     unsigned long long tag[2][kMaxRanks];
     unsigned long long epoch;
     int timed_out;
@@ -870,6 +875,7 @@ struct BandMailbox {
 struct BandPeers {
     int enabled;                       // 0: not in peer-memory band mode
     int rank, world;
+    int halo;                          // rows a band keeps current beyond each of its edges (kTbT, or 1)
     float *up_state;                   // state base of rank-1 (same layout as ours), or null
     float *dn_state;                   // state base of rank+1, or null
     BandMailbox *box[kMaxRanks];       // box[r] = rank r's mailbox (box[rank] is local memory)
@@ -886,6 +892,33 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// All-to-all of `ns` per-rank partial sums through the mailboxes; called by ONE thread per rank and
+// exchange.  vals[t] goes in, the sum over ranks (fixed rank order: same bits everywhere) comes back.
+// This is the one synchronisation point of a band iteration / block: a rank publishes only after all
+// its CTAs (and their halo pushes, fenced at system scope) are done, and nobody leaves before it holds
+// every rank's sums, so the next launch finds its halo rows up to date.
+__device__ __forceinline__ void band_all_to_all(const BandPeers &pp, double *vals, int ns)
+{
+    BandMailbox *mine = pp.box[pp.rank];
+    const unsigned long long e = mine->epoch + 1;
+    const int par = (int) (e & 1);
+    for (int r = 0; r < pp.world; r++) {
+        BandMailbox *bx = pp.box[r];
+        for (int t = 0; t < ns; t++) bx->sum[par][pp.rank][t] = vals[t];
+        st_release_sys(&bx->tag[par][pp.rank], e);
+    }
+    for (int t = 0; t < ns; t++) vals[t] = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < pp.world; r++) {
+        while (ld_acquire_sys(&mine->tag[par][r]) != e) {
+            // ~4 s in total, once: never hang the GPU on a rank that fell out of step
+            if (mine->timed_out || clock64() - t0 > (1ll << 33)) { mine->timed_out = 1; break; }
+        }
+        for (int t = 0; t < ns; t++) vals[t] += *((volatile double *) &mine->sum[par][r][t]);
+    }
+    mine->epoch = e;
+}
+
 struct IterParams {
     float *state;
     const float *consts;
@@ -894,6 +927,10 @@ struct IterParams {
     LoopCtl *loop;
     cudaGraphConditionalHandle cond;   // while-node handle when launched from the solve graph, else 0
     int use_cond;
+    // two-phase loop of big lock-step batches: the first while node (wide grid) ends as soon as no more
+    // than bulk_min pairs still iterate, the second (narrow grid) when none does
+    cudaGraphConditionalHandle cond_bulk;
+    int bulk_min;                      // -1: single-phase loop
     double *tb_partials;               // [batch][tb_parts][kTbT] per-CTA error sums of k_iterate_tb
     int tb_parts;
     int batch;                         // pairs in the lock-step batch (plane index = field * batch + pair)
@@ -956,7 +993,10 @@ __device__ __forceinline__ void decide_block(const IterParams &P, PairCtl *ctl, 
         atomicMax(&P.loop->max_n, n);
         const int left = atomicSub(&P.loop->active_pairs, 1) - 1;
         // the last pair to stop ends the device-side while loop of the solve graph
-        if (left == 0 && P.use_cond) cudaGraphSetConditional(P.cond, 0);
+        if (P.use_cond) {
+            if (left == P.bulk_min) cudaGraphSetConditional(P.cond_bulk, 0);
+            if (left == 0) cudaGraphSetConditional(P.cond, 0);
+        }
         return;
     }
     int next = 1;
@@ -1188,22 +1228,25 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
                 st4(sout + F_P21 * fs + o, make_float4(q21[0], q21[1], q21[2], q21[3]));
                 st4(sout + F_P22 * fs + o, make_float4(q22[0], q22[1], q22[2], q22[3]));
                 if (P.peers.enabled) {
-                    // my first row is the halo row below of the band above, my last row's p12/p22 the
+                    // my first `halo` rows are the halo below of the band above, my last `halo` rows the
                     // halo above of the band below: same offsets in the neighbour's planes (NVLink stores)
                     const size_t po = (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0 + o;
-                    if (y == P.row_begin && P.peers.up_state) {
-                        float *d = P.peers.up_state + po;
-                        st4(d + F_U1 * fs, uc1);
-                        st4(d + F_U2 * fs, uc2);
-                        st4(d + F_P11 * fs, make_float4(q11[0], q11[1], q11[2], q11[3]));
-                        st4(d + F_P12 * fs, make_float4(q12[0], q12[1], q12[2], q12[3]));
-                        st4(d + F_P21 * fs, make_float4(q21[0], q21[1], q21[2], q21[3]));
-                        st4(d + F_P22 * fs, make_float4(q22[0], q22[1], q22[2], q22[3]));
-                    }
-                    if (y == P.row_end - 1 && P.peers.dn_state) {
-                        float *d = P.peers.dn_state + po;
-                        st4(d + F_P12 * fs, make_float4(q12[0], q12[1], q12[2], q12[3]));
-                        st4(d + F_P22 * fs, make_float4(q22[0], q22[1], q22[2], q22[3]));
+                    float *d = nullptr;
+                    if (y < P.row_begin + P.peers.halo) d = P.peers.up_state;
+                    else if (y >= P.row_end - P.peers.halo) d = P.peers.dn_state;
+                    // (a band shorter than 2*halo rows sends its overlap both ways)
+                    float *d2 = (y < P.row_begin + P.peers.halo && y >= P.row_end - P.peers.halo) ? P.peers.dn_state : nullptr;
+#pragma unroll 1
+                    for (int k2 = 0; k2 < 2; k2++) {
+                        float *dd = k2 ? d2 : d;
+                        if (!dd) continue;
+                        dd += po;
+                        st4(dd + F_U1 * fs, uc1);
+                        st4(dd + F_U2 * fs, uc2);
+                        st4(dd + F_P11 * fs, make_float4(q11[0], q11[1], q11[2], q11[3]));
+                        st4(dd + F_P12 * fs, make_float4(q12[0], q12[1], q12[2], q12[3]));
+                        st4(dd + F_P21 * fs, make_float4(q21[0], q21[1], q21[2], q21[3]));
+                        st4(dd + F_P22 * fs, make_float4(q22[0], q22[1], q22[2], q22[3]));
                     }
                 }
             }
@@ -1262,31 +1305,7 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
             ctl->arrive = 0u;
             return;
         }
-        if (P.peers.enabled) {
-            // All-to-all of the per-rank sums through the mailboxes.  This is the one
-            // synchronisation point of an iteration: a rank publishes its sum only after all its
-            // CTAs (and their halo pushes) are done, and nobody leaves before it holds every sum,
-            // so the next launch finds its halo rows up to date.
-            BandMailbox *mine = P.peers.box[P.peers.rank];
-            const unsigned long long e = mine->epoch + 1;
-            const int par = (int) (e & 1);
-            for (int r = 0; r < P.peers.world; r++) {
-                BandMailbox *bx = P.peers.box[r];
-                bx->sum[par][P.peers.rank] = tot;
-                st_release_sys(&bx->tag[par][P.peers.rank], e);
-            }
-            double all = 0.0;
-            const long long t0 = clock64();
-            for (int r = 0; r < P.peers.world; r++) {        // fixed rank order: same bits everywhere
-                while (ld_acquire_sys(&mine->tag[par][r]) != e) {
-                    // ~4 s in total, once: never hang the GPU on a rank that fell out of step
-                    if (mine->timed_out || clock64() - t0 > (1ll << 33)) { mine->timed_out = 1; break; }
-                }
-                all += *((volatile double *) &mine->sum[par][r]);
-            }
-            mine->epoch = e;
-            tot = all;
-        }
+        if (P.peers.enabled) band_all_to_all(P.peers, &tot, 1);
         const double error = tot / ((double) nx * (double) ny);   // src/tvl1flow.cpp:162
         decide_block(P, ctl, b, cur, 1, &error,
                      (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
@@ -1300,6 +1319,56 @@ k_iterate_t1(const IterParams P)
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
         atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
     for_each_pair_of_slot(P, false, [&](int b) { iterate_t1_pair<R, WY>(P, b); });
+}
+
+// Row-band mode over peer memory: barrier of all ranks through the mailboxes (start of a solve: no rank
+// may push halos into a neighbour that is still reading the previous solve's result).
+__global__ void k_band_barrier(BandPeers pp)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double none = 0.0;
+        band_all_to_all(pp, &none, 0);
+    }
+}
+
+// Row-band mode over peer memory: all-gather of the flow after a split level.  Every rank stores its
+// band of u1, u2 (live set) into the same rows of every other rank's planes (NVLink stores), then the
+// ranks meet at a mailbox barrier, so when this kernel has finished on a rank that rank holds the whole
+// flow of the level.  No NCCL call, no host round trip.
+struct GatherParams {
+    float *state[kMaxRanks];           // state base of every rank (state[rank] = ours)
+    BandPeers peers;
+    const PairCtl *ctl;
+    unsigned int *ticket;              // zeroed; left zeroed
+    size_t set_stride, field_stride;
+    int pitch, row_begin, row_end;
+};
+
+__global__ void __launch_bounds__(256)
+k_band_allgather(const GatherParams G)
+{
+    const size_t set_off = (size_t) G.ctl->cur * G.set_stride;
+    const size_t first = (size_t) G.row_begin * G.pitch;
+    const size_t n4 = (size_t) (G.row_end - G.row_begin) * G.pitch / 4;
+    const float *mine = G.state[G.peers.rank] + set_off + first;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n4; i += (size_t) gridDim.x * blockDim.x) {
+        const size_t f = i / n4, k = i - f * n4;                     // field F_U1 / F_U2, float4 index
+        const size_t o = f * G.field_stride + 4 * k;
+        const float4 v = ldg4(mine + o);
+        for (int r = 0; r < G.peers.world; r++)
+            if (r != G.peers.rank) st4(G.state[r] + set_off + first + o, v);
+    }
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(G.ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence_system();
+        *G.ticket = 0u;
+        double none = 0.0;
+        band_all_to_all(G.peers, &none, 0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1631,7 +1700,7 @@ __device__ __forceinline__ void tma_load_3d(float *dst, const CUtensorMap *map, 
 // and touches neither its last column nor its last row: all boundary predicates fold away.
 template <bool INTERIOR>
 __device__ __forceinline__ void tb_iterations(const IterParams &P, int ns, int X0, int Y0, int nx, int ny,
-                                              float *sU1, float *sU2, float *sP11, float *sP12, float *sP21,
+                                              int own_rows, float *sU1, float *sU2, float *sP11, float *sP12, float *sP21,
                                               float *sP22, const float *sIx, const float *sIy, const float *sRho,
                                               double (*s_err)[kTbThreads / 32])
 {
@@ -1658,7 +1727,7 @@ __device__ __forceinline__ void tb_iterations(const IterParams &P, int ns, int X
             if (qx == 0) { l11 = 0.f; l21 = 0.f; }
             const bool last_row = !INTERIOR && (gy == ny - 1);
             const bool row_in = INTERIOR || (gy >= 0 && gy < ny);
-            const bool row_owned = by >= kTbT && by < kTbT + kTbH;
+            const bool row_owned = by >= kTbT && by < kTbT + own_rows;   // (a row band may end inside the tile)
             float o1[4], o2[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
@@ -1737,7 +1806,9 @@ __device__ __forceinline__ void tb_pair(const TbMaps &maps, const IterParams &P,
     const int cur = ctl->cur;
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int X0 = blockIdx.x * kTbW - kTbT, Y0 = blockIdx.y * kTbH - kTbT;
+    // tiles cover the rows this launch owns (the whole image, or this rank's row band)
+    const int X0 = blockIdx.x * kTbW - kTbT, Y0 = P.row_begin + blockIdx.y * kTbH - kTbT;
+    const int own_rows = min(kTbH, P.row_end - (Y0 + kTbT));
 
     float *sU1 = tb_smem, *sU2 = sU1 + kTbPlane, *sP11 = sU2 + kTbPlane, *sP12 = sP11 + kTbPlane,
           *sP21 = sP12 + kTbPlane, *sP22 = sP21 + kTbPlane, *sIx = sP22 + kTbPlane, *sIy = sIx + kTbPlane,
@@ -1770,9 +1841,9 @@ __device__ __forceinline__ void tb_pair(const TbMaps &maps, const IterParams &P,
     {
         const bool interior = X0 >= 0 && Y0 >= 0 && X0 + kTbBW < nx && Y0 + kTbBH < ny;   // CTA-uniform
         if (interior)
-            tb_iterations<true>(P, ns, X0, Y0, nx, ny, sU1, sU2, sP11, sP12, sP21, sP22, sIx, sIy, sRho, s_err);
+            tb_iterations<true>(P, ns, X0, Y0, nx, ny, own_rows, sU1, sU2, sP11, sP12, sP21, sP22, sIx, sIy, sRho, s_err);
         else
-            tb_iterations<false>(P, ns, X0, Y0, nx, ny, sU1, sU2, sP11, sP12, sP21, sP22, sIx, sIy, sRho, s_err);
+            tb_iterations<false>(P, ns, X0, Y0, nx, ny, own_rows, sU1, sU2, sP11, sP12, sP21, sP22, sIx, sIy, sRho, s_err);
     }
 
     // ---- write the owned tile to the other ping-pong set ------------------------------------------
@@ -1783,11 +1854,24 @@ __device__ __forceinline__ void tb_pair(const TbMaps &maps, const IterParams &P,
             const int row = idx / (kTbW / 4), q = idx - row * (kTbW / 4);
             const int by = kTbT + row, bx = kTbT + 4 * q;
             const int gy = Y0 + by, gx = X0 + bx;
-            if (gy >= ny || gx >= nx) continue;
+            if (row >= own_rows || gx >= nx) continue;
             const int so = by * kTbBW + bx;
             const size_t go = (size_t) gy * pitch + gx;
 #pragma unroll
             for (int f = 0; f < F_COUNT; f++) st4(gout + f * fs + go, lds4(tb_smem + f * kTbPlane + so));
+            if (P.peers.enabled) {
+                // rows within `halo` of a band edge are the neighbour's halo rows: the same values go to
+                // the same offsets of its planes (NVLink stores), see iterate_t1_pair
+                const size_t po = (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0 + go;
+                if (gy < P.row_begin + P.peers.halo && P.peers.up_state) {
+#pragma unroll
+                    for (int f = 0; f < F_COUNT; f++) st4(P.peers.up_state + po + f * fs, lds4(tb_smem + f * kTbPlane + so));
+                }
+                if (gy >= P.row_end - P.peers.halo && P.peers.dn_state) {
+#pragma unroll
+                    for (int f = 0; f < F_COUNT; f++) st4(P.peers.dn_state + po + f * fs, lds4(tb_smem + f * kTbPlane + so));
+                }
+            }
         }
     }
 
@@ -1801,7 +1885,8 @@ __device__ __forceinline__ void tb_pair(const TbMaps &maps, const IterParams &P,
             for (int w = 0; w < kTbThreads / 32; w++) s += s_err[t][w];
             part[(size_t) blk * kTbT + t] = s;
         }
-        __threadfence();
+        if (P.peers.enabled) __threadfence_system();    // halo rows pushed to the neighbours are out
+        else __threadfence();
         const unsigned int tk = atomicAdd(&ctl->arrive, 1u);
         s_last = (tk == (unsigned int) nblk - 1u);
     }
@@ -1819,12 +1904,16 @@ __device__ __forceinline__ void tb_pair(const TbMaps &maps, const IterParams &P,
         if (tid == 0) {
             double tot = 0.0;
             for (int w = 0; w < kTbThreads / 32; w++) tot += s_err[0][w];
-            s_tot[t] = tot / ((double) nx * (double) ny);
+            s_tot[t] = tot;
         }
     }
     __syncthreads();
-    if (tid == 0)
-        decide_block(P, ctl, b, cur, ns, s_tot, (unsigned long long) nx * (unsigned long long) ny);
+    if (tid == 0) {
+        if (P.peers.enabled) band_all_to_all(P.peers, s_tot, ns);     // the other bands' sums of this block
+        for (int t = 0; t < ns; t++) s_tot[t] /= (double) nx * (double) ny;
+        decide_block(P, ctl, b, cur, ns, s_tot,
+                     (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
+    }
 }
 
 __global__ void __launch_bounds__(kTbThreads, 3)

@@ -102,6 +102,9 @@ struct tvl1_ctx {
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
     bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
     int slot_ctas = 32768;                   // CTAs a full iteration launch should have at least (TVL1_SLOT_CTAS)
+    int tail_pairs = 16;                     // lock-step batches: once this few pairs still iterate, the loop goes on
+                                             // with narrow launches of tail_slot_ctas CTAs (TVL1_TAIL_PAIRS, 0 = off)
+    int tail_slot_ctas = 2048;               // (TVL1_TAIL_SLOT_CTAS)
     long long tb_max_pixels = 192ll << 20;   // ... which serves lock-step batches up to this many pixels per level
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
@@ -114,12 +117,14 @@ struct tvl1_ctx {
     void *nccl_comm = nullptr;
     int band_rank = 0, band_world = 1;
     double *d_band_sum = nullptr;
+    double *d_agree = nullptr;
     // ... over peer memory (CUDA IPC + NVLink): halos and error sums move inside the iteration kernel
     bool p2p_ready = false;
     bool band_use_nccl_per_iteration = false;   // TVL1_BAND_NCCL=1: the NCCL send/recv variant
     BandMailbox *my_box = nullptr;
     BandMailbox *boxes[kMaxRanks] = {};
-    float *peer_state[2] = { nullptr, nullptr };   // [0] rank-1, [1] rank+1
+    float *peer_state[kMaxRanks] = {};             // every rank's state buffer ([band_rank] = our own)
+    unsigned int *d_gather_ticket = nullptr;       // arrival counter of k_band_allgather
     const float *p2p_state_key = nullptr;
     unsigned char *d_handles = nullptr;            // [world][64] scratch for the handle all-gather
     static constexpr int kMaxLanes = 4;
@@ -464,19 +469,21 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
     return P;
 }
 
-int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B);
+int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B, bool tail);
 bool tb_usable(tvl1_ctx *ctx, const Level &l, int B);
 
 // grid.z of the iteration kernels: pair slots (see for_each_pair_of_slot).  Enough slots that a launch
 // with every pair active still has a few thousand CTAs, few enough that a launch with hardly any
 // active pair does not spend its time starting CTAs that exit at once.
-int pair_slots(const tvl1_ctx *ctx, int tiles, int B)
+int pair_slots(const tvl1_ctx *ctx, int tiles, int B, bool tail = false)
 {
     // at least ceil(B / 32) slots: one ballot of the kernel covers a slot's pairs
+    if (tail) return std::min(B, std::max(ceil_div(B, 32), ceil_div(ctx->tail_slot_ctas, std::max(tiles, 1))));
     return std::min(B, std::max(std::max(32, ceil_div(B, 32)), ceil_div(ctx->slot_ctas, std::max(tiles, 1))));
 }
 
-int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
+// `tail`: narrow launch for the late iterations of a lock-step batch, when only a few pairs are left
+int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B, bool tail = false)
 {
     // Strip height per warp: 16 rows (fewest CTAs, least halo traffic) when that still gives every SM
     // a few CTAs, else 8, else 4 -- a single mid-size image is latency-bound on how many rows a warp
@@ -487,19 +494,19 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B)
     auto ctas = [&](int R) { return (long long) tiles_x * ceil_div(rows, R * kIterWY) * B; };
     if (ctas(16) >= want) {
         dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), 1);
-        g.z = pair_slots(ctx, g.x * g.y, B);
+        g.z = pair_slots(ctx, g.x * g.y, B, tail);
         k_iterate_t1<16, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else if (ctas(8) >= want) {
         dim3 g(tiles_x, ceil_div(rows, 8 * kIterWY), 1);
-        g.z = pair_slots(ctx, g.x * g.y, B);
+        g.z = pair_slots(ctx, g.x * g.y, B, tail);
         k_iterate_t1<8, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else {
         dim3 g(tiles_x, ceil_div(rows, 4 * kIterWY), 1);
-        g.z = pair_slots(ctx, g.x * g.y, B);
+        g.z = pair_slots(ctx, g.x * g.y, B, tail);
         k_iterate_t1<4, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
-    if (P.tb) TRY(launch_iterate_tb(ctx, P, B));   // pairs whose next block has more than one iteration
+    if (P.tb) TRY(launch_iterate_tb(ctx, P, B, tail));   // pairs whose next block has more than one iteration
     return TVL1_OK;
 }
 
@@ -557,7 +564,7 @@ bool tb_usable(tvl1_ctx *ctx, const Level &l, int B)
     return true;
 }
 
-int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B)
+int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B, bool tail)
 {
     const Workspace &w = ctx->ws;
     TbMaps maps;
@@ -567,8 +574,8 @@ int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B)
                                   F_COUNT * B, P.lv.pitch, w.plane0);
     ok = ok && make_plane_map(&maps.consts, w.consts, P.lv.nx, P.lv.ny, C_COUNT * B, P.lv.pitch, w.plane0);
     if (!ok) { ctx->err = "cuTensorMapEncodeTiled failed"; return TVL1_ERR_CUDA; }
-    dim3 g(ceil_div(P.lv.nx, kTbW), ceil_div(P.lv.ny, kTbH), 1);
-    g.z = pair_slots(ctx, g.x * g.y, B);
+    dim3 g(ceil_div(P.lv.nx, kTbW), ceil_div(P.row_end - P.row_begin, kTbH), 1);
+    g.z = pair_slots(ctx, g.x * g.y, B, tail);
     k_iterate_tb<<<g, kTbThreads, kTbSmemBytes, ctx->stream>>>(maps, P);
     CK(cudaGetLastError());
     return TVL1_OK;
@@ -633,15 +640,13 @@ int launch_zero(tvl1_ctx *ctx, int s, int B, int first_field, int nfields)
 // The while loop of src/tvl1flow.cpp:113 for the whole batch, as a conditional WHILE node of the
 // solve graph: the body is one launch of the fused iteration kernel; the kernel clears the
 // condition when the last pair stops.  (default launch value 1 => at least one iteration)
-int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
+int add_while_node(tvl1_ctx *ctx, const IterParams &P, int B, cudaGraphConditionalHandle h, bool tail)
 {
     cudaStreamCaptureStatus status;
     cudaGraph_t g = nullptr;
     const cudaGraphNode_t *deps = nullptr;
     size_t ndeps = 0;
     CK(cudaStreamGetCaptureInfo_v2(ctx->stream, &status, nullptr, &g, &deps, &ndeps));
-    cudaGraphConditionalHandle h;
-    CK(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
     cudaGraphNodeParams np = { cudaGraphNodeTypeConditional };
     np.type = cudaGraphNodeTypeConditional;
     np.conditional.handle = h;
@@ -651,16 +656,41 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
     CK(cudaGraphAddNode(&node, g, deps, ndeps, &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
     CK(cudaStreamBeginCaptureToGraph(ctx->body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-    P.cond = h;
-    P.use_cond = 1;
     std::swap(ctx->stream, ctx->body_stream);
-    const int rc = launch_iterate(ctx, P, B);
+    const int rc = launch_iterate(ctx, P, B, tail);
     std::swap(ctx->stream, ctx->body_stream);
     cudaGraph_t ended = nullptr;
     CK(cudaStreamEndCapture(ctx->body_stream, &ended));
     TRY(rc);
     CK(cudaStreamUpdateCaptureDependencies(ctx->stream, &node, 1, cudaStreamSetCaptureDependencies));
     return TVL1_OK;
+}
+
+int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
+{
+    cudaStreamCaptureStatus status;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamGetCaptureInfo_v2(ctx->stream, &status, nullptr, &g, nullptr, nullptr));
+    cudaGraphConditionalHandle h_all, h_bulk = 0;
+    CK(cudaGraphConditionalHandleCreate(&h_all, g, 1, cudaGraphCondAssignDefault));
+    P.cond = h_all;
+    P.use_cond = 1;
+    P.cond_bulk = 0;
+    P.bulk_min = -1;
+    // A big lock-step batch launches until its slowest pair has converged, and most of those launches
+    // find only a few pairs still active.  Two while nodes in sequence: wide launches (full-size grid)
+    // while more than tail_pairs pairs iterate, then narrow ones (a tenth of the CTAs: a launch with
+    // little work costs what it does, not what it takes to start and retire 32k empty CTAs).  The
+    // active count only falls within a warp step, so the second loop never has to hand back.
+    const bool two_phase = ctx->tail_pairs > 0 && B > 2 * ctx->tail_pairs && !P.peers.enabled;
+    if (two_phase) {
+        CK(cudaGraphConditionalHandleCreate(&h_bulk, g, 1, cudaGraphCondAssignDefault));
+        P.cond_bulk = h_bulk;
+        P.bulk_min = ctx->tail_pairs;
+        TRY(add_while_node(ctx, P, B, h_bulk, false));
+        return add_while_node(ctx, P, B, h_all, true);
+    }
+    return add_while_node(ctx, P, B, h_all, false);
 }
 
 // Host-driven variant of the same loop (TVL1_NO_GRAPH=1, and the per-kernel hooks): enqueue a
@@ -927,7 +957,10 @@ int run_single_scale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, f
 int ensure_stage(tvl1_ctx *ctx, size_t bytes_each, bool need_f32)
 {
     if (ctx->stage_bytes < bytes_each) {
-        for (int i = 0; i < 2; i++) { cudaFree(ctx->stage_in[i]); cudaFree(ctx->stage_out[i]); }
+        for (int i = 0; i < 2; i++) {
+            cudaFree(ctx->stage_in[i]); ctx->stage_in[i] = nullptr;
+            cudaFree(ctx->stage_out[i]); ctx->stage_out[i] = nullptr;
+        }
         ctx->stage_bytes = 0;
         for (int i = 0; i < 2; i++) {
             CK(cudaMalloc(&ctx->stage_in[i], bytes_each));
@@ -936,7 +969,7 @@ int ensure_stage(tvl1_ctx *ctx, size_t bytes_each, bool need_f32)
         ctx->stage_bytes = bytes_each;
     }
     if (need_f32 && ctx->stage_f32_bytes < bytes_each / 2) {
-        for (int i = 0; i < 4; i++) cudaFree(ctx->stage_f32[i]);
+        for (int i = 0; i < 4; i++) { cudaFree(ctx->stage_f32[i]); ctx->stage_f32[i] = nullptr; }
         ctx->stage_f32_bytes = 0;
         for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->stage_f32[i], bytes_each / 2));
         ctx->stage_f32_bytes = bytes_each / 2;
@@ -1288,6 +1321,19 @@ void band_rows(int ny, int rank, int world, int *r0, int *r1, int *rows_per)
 }
 
 
+// Sum of a few host doubles over the ranks of the band communicator (collective; used to take
+// identical decisions on every rank).
+int agree_sum(tvl1_ctx *ctx, double *vals, int n)
+{
+    if (n > 8) return fail_arg(ctx, "agree_sum: too many values");
+    if (!ctx->d_agree) CK(cudaMalloc(&ctx->d_agree, 8 * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->d_agree, vals, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NK(g_nccl.AllReduce(ctx->d_agree, ctx->d_agree, n, ncclDouble, ncclSum, (ncclComm_t) ctx->nccl_comm, ctx->stream));
+    CK(cudaMemcpyAsync(vals, ctx->d_agree, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TVL1_OK;
+}
+
 // ---- peer-memory plumbing: CUDA IPC handles travel through one NCCL all-gather ------------------
 int exchange_ipc_handles(tvl1_ctx *ctx, void *dev_ptr, std::vector<cudaIpcMemHandle_t> &all)
 {
@@ -1307,7 +1353,10 @@ int exchange_ipc_handles(tvl1_ctx *ctx, void *dev_ptr, std::vector<cudaIpcMemHan
 void p2p_release_state(tvl1_ctx *ctx)
 {
     for (auto &g : ctx->level_sg) free_graph(g, ctx->ev_pool);   // peer pointers are baked into them
-    for (float *&p : ctx->peer_state) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
+    for (int r = 0; r < kMaxRanks; r++) {
+        if (ctx->peer_state[r] && r != ctx->band_rank) cudaIpcCloseMemHandle(ctx->peer_state[r]);
+        ctx->peer_state[r] = nullptr;
+    }
     ctx->p2p_state_key = nullptr;
 }
 
@@ -1320,16 +1369,39 @@ int p2p_setup_mailboxes(tvl1_ctx *ctx)
     if (!ctx->my_box) CK(cudaMalloc(&ctx->my_box, 2 << 20));   // its own allocation: exported whole
     CK(cudaMemsetAsync(ctx->my_box, 0, sizeof(BandMailbox), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->d_gather_ticket) {
+        CK(cudaMalloc(&ctx->d_gather_ticket, sizeof(unsigned int)));
+        CK(cudaMemsetAsync(ctx->d_gather_ticket, 0, sizeof(unsigned int), ctx->stream));
+    }
+    for (int r = 0; r < kMaxRanks; r++) {                      // mappings of an earlier tvl1_band_init
+        if (ctx->boxes[r] && ctx->boxes[r] != ctx->my_box) cudaIpcCloseMemHandle(ctx->boxes[r]);
+        ctx->boxes[r] = nullptr;
+    }
     std::vector<cudaIpcMemHandle_t> all;
     TRY(exchange_ipc_handles(ctx, ctx->my_box, all));
-    for (int r = 0; r < G; r++) {
+    bool ok = true;
+    for (int r = 0; r < G && ok; r++) {
         if (r == me) { ctx->boxes[r] = ctx->my_box; continue; }
         void *p = nullptr;
         if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
             cudaGetLastError();
-            return TVL1_OK;                                    // no peer access: stay on NCCL
+            ok = false;                                        // no peer access from this rank
+            break;
         }
         ctx->boxes[r] = (BandMailbox *) p;
+    }
+    // The ranks must agree: one rank on the mailboxes while another waits in NCCL would hang the job.
+    // Peer memory is used only if EVERY rank mapped every mailbox; the NCCL-per-iteration switch is
+    // taken if ANY rank asks for it.
+    double flags[2] = { ok ? 0.0 : 1.0, ctx->band_use_nccl_per_iteration ? 1.0 : 0.0 };
+    TRY(agree_sum(ctx, flags, 2));
+    ctx->band_use_nccl_per_iteration = flags[1] > 0.0;
+    if (flags[0] > 0.0) {                                      // somebody failed: everybody stays on NCCL
+        for (int r = 0; r < kMaxRanks; r++) {
+            if (ctx->boxes[r] && ctx->boxes[r] != ctx->my_box) cudaIpcCloseMemHandle(ctx->boxes[r]);
+            ctx->boxes[r] = nullptr;
+        }
+        return TVL1_OK;
     }
     ctx->p2p_ready = true;
     return TVL1_OK;
@@ -1341,40 +1413,64 @@ int p2p_bind_state(tvl1_ctx *ctx)
     if (!ctx->p2p_ready || ctx->p2p_state_key != nullptr) return TVL1_OK;   // released <=> must (re)bind
     std::vector<cudaIpcMemHandle_t> all;
     TRY(exchange_ipc_handles(ctx, ctx->ws.state, all));
-    const int nb[2] = { ctx->band_rank - 1, ctx->band_rank + 1 };
-    for (int k = 0; k < 2; k++) {
-        if (nb[k] < 0 || nb[k] >= ctx->band_world) continue;
+    for (int r = 0; r < ctx->band_world; r++) {     // neighbours for the halos, everybody for the all-gather
+        if (r == ctx->band_rank) { ctx->peer_state[r] = ctx->ws.state; continue; }
         void *p = nullptr;
-        CK(cudaIpcOpenMemHandle(&p, all[nb[k]], cudaIpcMemLazyEnablePeerAccess));
-        ctx->peer_state[k] = (float *) p;
+        CK(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_state[r] = (float *) p;
     }
     ctx->p2p_state_key = ctx->ws.state;
     return TVL1_OK;
 }
 
-// one split level with the exchange fused into the iteration kernel (no NCCL, no extra kernels)
+BandPeers band_peers(const tvl1_ctx *ctx, const Level &l, int r0, int r1)
+{
+    BandPeers pp = {};
+    pp.enabled = 1; pp.rank = ctx->band_rank; pp.world = ctx->band_world;
+    pp.halo = kTbT;
+    pp.up_state = (r0 > 0 && ctx->band_rank > 0) ? ctx->peer_state[ctx->band_rank - 1] : nullptr;
+    pp.dn_state = (r1 < l.ny && ctx->band_rank + 1 < ctx->band_world) ? ctx->peer_state[ctx->band_rank + 1] : nullptr;
+    for (int r = 0; r < ctx->band_world; r++) pp.box[r] = ctx->boxes[r];
+    return pp;
+}
+
+// One split level with the exchange fused into the iteration kernels (no NCCL, no extra kernels, no
+// host round trip).  A band keeps kTbT rows beyond each of its edges current -- pushed by the
+// neighbours after every accepted iteration / block of iterations -- so the temporally blocked kernel
+// runs inside the bands exactly as on one GPU (T-row halos every T iterations), and the
+// constants of those rows are computed locally (the warp is per-pixel work on replicated pyramids).
+// The level ends with the all-gather of the flow through peer memory.
 int band_level_p2p(tvl1_ctx *ctx, int s, const tvl1_params &prm, int stat_base, int &hint)
 {
     const Workspace &w = ctx->ws;
     const Level &l = w.lv[s];
     int r0, r1, rows_per;
     band_rows(l.ny, ctx->band_rank, ctx->band_world, &r0, &r1, &rows_per);
+    const BandPeers pp = band_peers(ctx, l, r0, r1);
+    const int h0 = std::max(r0 - pp.halo, 0), h1 = std::min(r1 + pp.halo, l.ny);
     TRY(launch_zero(ctx, s, 1, F_P11, 4));
     for (int wi = 0; wi < prm.warps; wi++) {
         {
             Span sp(ctx, 1);
-            TRY(launch_warp(ctx, s, 1, 0, r0, std::min(r1 + 1, l.ny)));   // + the halo row below
+            TRY(launch_warp(ctx, s, 1, 0, h0, h1));                     // own rows + both halos
         }
         k_begin_warp<<<1, 32, 0, ctx->stream>>>(w.ctl, w.loop, 1);
         CKL(ctx);
         IterParams P = iter_params(ctx, l, prm, stat_base + wi, kMaxIterations, s);
         P.row_begin = r0; P.row_end = r1;
-        P.peers.enabled = 1; P.peers.rank = ctx->band_rank; P.peers.world = ctx->band_world;
-        P.peers.up_state = r0 > 0 ? ctx->peer_state[0] : nullptr;
-        P.peers.dn_state = r1 < l.ny ? ctx->peer_state[1] : nullptr;
-        for (int r = 0; r < ctx->band_world; r++) P.peers.box[r] = ctx->boxes[r];
+        P.peers = pp;
+        P.tb = (r1 - r0 >= kTbBH && tb_usable(ctx, l, 1)) ? 1 : 0;
         TRY(run_iterations(ctx, P, 1, hint));
     }
+    GatherParams G = {};
+    for (int r = 0; r < ctx->band_world; r++) G.state[r] = ctx->peer_state[r];
+    G.peers = pp; G.ctl = w.ctl; G.ticket = ctx->d_gather_ticket;
+    G.set_stride = w.set_stride; G.field_stride = w.field_stride;
+    G.pitch = l.pitch; G.row_begin = r0; G.row_end = r1;
+    const size_t n4 = (size_t) (r1 - r0) * l.pitch / 4;
+    const int blocks = (int) std::min<size_t>(std::max<size_t>((2 * n4 + 1023) / 1024, 1), (size_t) 4 * ctx->sm_count);
+    k_band_allgather<<<blocks, 256, 0, ctx->stream>>>(G);
+    CKL(ctx);
     return TVL1_OK;
 }
 
@@ -1484,9 +1580,22 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
     // a negative threshold also splits on a single rank (one band = the whole level): the band code
     // path without neighbours, used by the single-GPU tests
     const bool force = min_split_rows < 0;
-    min_split_rows = std::max(std::abs(min_split_rows), 2 * G);
-    auto is_split = [&](int s) { return (G > 1 || force) && w.lv[s].ny >= min_split_rows; };
+    const int halo = p2p ? kTbT : 1;
+    min_split_rows = std::max(std::abs(min_split_rows), 2 * halo * G);
+    // every band, the last (shortest) one included, must hold at least `halo` rows
+    auto is_split = [&](int s) {
+        const int ny_s = w.lv[s].ny;
+        return (G > 1 || force) && ny_s >= min_split_rows && ny_s - (G - 1) * ceil_div(ny_s, G) >= halo;
+    };
     Span total(ctx, 2);
+    if (p2p && G > 1) {
+        // nobody pushes halos into a rank that is still reading the previous solve's result
+        BandPeers pp = {};
+        pp.enabled = 1; pp.rank = ctx->band_rank; pp.world = G;
+        for (int r = 0; r < G; r++) pp.box[r] = ctx->boxes[r];
+        k_band_barrier<<<1, 32, 0, st>>>(pp);
+        CKL(ctx);
+    }
     TRY(build_pyramid(ctx, 1, dI0, dI1, nx, ny, prm));
     TRY(launch_zero(ctx, ns - 1, 1, F_U1, 2));
     int hint = 16;
@@ -1510,8 +1619,9 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
         } else {
             TRY(run_level(ctx, s, 1, prm, stat_base, hint));       // replicated: identical on every rank
         }
-        if (is_split(s)) {
+        if (is_split(s) && !p2p) {
             // every rank gets the whole flow of this level (in place: band r sits at rows r*rows_per)
+            // -- the peer-memory path has done this on the device (k_band_allgather)
             PairCtl c;
             TRY(band_read_ctl(ctx, &c));
             int r0, r1, rows_per;
@@ -1530,8 +1640,8 @@ int run_band(tvl1_ctx *ctx, const float *dI0, const float *dI1, float *du1, floa
         if (is_split(s - 1)) {       // own rows plus both halo rows, straight from the full coarse flow
             int r0, r1, rows_per;
             band_rows(f.ny, ctx->band_rank, G, &r0, &r1, &rows_per);
-            z0 = std::max(r0 - 1, 0);
-            z1 = std::min(r1 + 1, f.ny);
+            z0 = std::max(r0 - halo, 0);
+            z1 = std::min(r1 + halo, f.ny);
         }
         if (z1 > z0) {
             Span zs(ctx, 4);
@@ -1622,6 +1732,10 @@ int tvl1_create(int device, tvl1_ctx **out)
         (e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaMallocHost(&ctx->h_loop, sizeof(LoopCtl))) != cudaSuccess) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        if (ctx->h_loop) cudaFreeHost(ctx->h_loop);
+        if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
+        if (ctx->body_stream) cudaStreamDestroy(ctx->body_stream);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return TVL1_ERR_CUDA;
     }
@@ -1630,6 +1744,8 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
     if (const char *sc = std::getenv("TVL1_SLOT_CTAS")) ctx->slot_ctas = std::max(1, std::atoi(sc));
+    if (const char *tp = std::getenv("TVL1_TAIL_PAIRS")) ctx->tail_pairs = std::max(0, std::atoi(tp));
+    if (const char *tc = std::getenv("TVL1_TAIL_SLOT_CTAS")) ctx->tail_slot_ctas = std::max(1, std::atoi(tc));
     if (const char *mp = std::getenv("TVL1_TB_MAX_MPIX")) ctx->tb_max_pixels = std::max(0ll, std::atoll(mp)) << 20;
     *out = ctx;
     return TVL1_OK;
@@ -1650,6 +1766,8 @@ void tvl1_destroy(tvl1_ctx *ctx)
     cudaFree(ctx->d_handles);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t) ctx->nccl_comm);
     cudaFree(ctx->d_band_sum);
+    cudaFree(ctx->d_agree);
+    cudaFree(ctx->d_gather_ticket);
     free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(ctx->ws);
     free_graph(ctx->sg_alt, ctx->ev_pool);
@@ -1918,7 +2036,13 @@ int tvl1_band_set_exchange(tvl1_ctx *outer, int use_nccl_per_iteration)
 {
     tvl1_ctx *ctx = band_context(outer);
     if (!ctx) return TVL1_ERR_ARG;
-    ctx->band_use_nccl_per_iteration = use_nccl_per_iteration != 0;
+    if (!ctx->nccl_comm) return fail_arg(outer, "tvl1_band_init has not been called on this context");
+    // collective: NCCL per iteration is used if any rank asks for it (ranks in different modes would hang)
+    CK(cudaSetDevice(ctx->device));
+    double want = use_nccl_per_iteration != 0 ? 1.0 : 0.0;
+    const int rc = agree_sum(ctx, &want, 1);
+    if (rc != TVL1_OK) { outer->err = ctx->err; return rc; }
+    ctx->band_use_nccl_per_iteration = want > 0.0;
     return TVL1_OK;
 }
 

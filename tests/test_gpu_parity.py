@@ -17,6 +17,8 @@ from oracle.loader import CpuTvl1, available
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 MEAN_TOL = 1e-3
 MAX_TOL = 1e-2
 
@@ -499,6 +501,64 @@ def test_band_code_path_single_rank(gpu, oracle_f64):
     r = oracle_f64.multiscale(I0, I1, **kw)
     assert np.array_equal(b[2], r[2])
     assert_flow_close(b[0], b[1], r[0], r[1], "band mode")
+
+
+def test_band_code_path_single_rank_temporal_blocking(gpu):
+    """Same with levels large enough for the temporally blocked kernel inside the band (tile grid
+    anchored at the band, T-row halo logic, error sums through the mailbox), at a tight epsilon so
+    that blocks of 4 iterations, predicted short blocks and exact replays all occur; also the NCCL
+    exchange mode on the same context."""
+    I0, I1 = _cases.synth.make_pair(320, 264, seed=32, scale=0.5)
+    kw = dict(nscales=3, warps=3, eps=0.002)
+    a = gpu.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    gpu.band_init(0, 1, gpu.band_unique_id())
+    assert gpu.band_exchange_mode() == "peer"
+    for mode in ("peer", "nccl", "peer"):
+        gpu.band_set_exchange(mode)
+        assert gpu.band_exchange_mode() == mode
+        b = gpu.band_solve(I0, I1, min_split_rows=-100, **kw)    # splits the 264- and 132-row levels
+        assert np.array_equal(a[2], b[2]), (mode, a[2].tolist(), b[2].tolist())
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), mode
+    assert gpu.stats()["host_syncs"] == 0          # peer mode: the whole solve without a host round trip
+    assert a[2].max() > 8                           # long enough loops for multi-iteration blocks
+
+
+def _run_band_check(world, *args, timeout=600):
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "band_check.py")] + [str(a) for a in args]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and line, (r.returncode, r.stdout[-2000:], r.stderr[-3000:])
+    import json
+    return json.loads(line[-1])
+
+
+@pytest.mark.parametrize("case", ["small", "4k"])
+def test_row_bands_over_all_gpus_of_the_box(case):
+    """SURVEY 8e row 2 / BASELINE configs[3]: one image pair split into row bands over
+    min(device_count, 8) GPUs, one process per GPU under torch.distributed.run.  Every rank must get
+    the single-GPU flow bit for bit with identical iteration counts, in both exchange modes (peer
+    memory fused into the iteration kernels; NCCL send/recv + all-reduce per iteration).  Skipped on a
+    one-GPU box (the single-rank tests above cover the code path there)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = min(n, 8)
+    if case == "small":
+        res = _run_band_check(world, 1024, 768, 4, 3, 0.01, 96)
+    else:
+        res = _run_band_check(world, 3840, 2160, 6, 10, 0.001, 512)
+    assert res["all_ranks_ok"] and res["same_iteration_counts"] and res["both_exchange_modes_match_single_gpu"], res
+    assert res["max_abs_flow_diff"] == 0.0, res
 
 
 def test_dropin_symbols_from_threads(gpu):
