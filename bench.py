@@ -54,11 +54,27 @@ def parse():
     ap.add_argument("--max-batch", type=int, default=256, help="pairs advanced in lock-step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="batch1080p", choices=["batch1080p", "band4k", "band8k"],
+                    help="batch1080p: BASELINE configs[2] (the headline); band4k / band8k: configs[3] / configs[4], "
+                         "ONE pair split into row bands over the ranks (strong scaling)")
+    ap.add_argument("--no-row-band", action="store_true",
+                    help="skip the row_band leg that the batch1080p workload appends when N > 1")
+    ap.add_argument("--quick", action="store_true", help="skip the fp64 / sequence / copy-ceiling extras of e2e")
     return ap.parse_args()
+
+
+BAND_CASES = {
+    "band4k": dict(nx=3840, ny=2160, kw=dict(nscales=6, warps=10, eps=0.001), min_rows=512,
+                   name="BASELINE.json configs[3]: synthetic 3840x2160 pair, nscales=6 nwarps=10 eps=0.001"),
+    "band8k": dict(nx=7680, ny=4320, kw=dict(nscales=5, warps=5, eps=0.01), min_rows=1024,
+                   name="BASELINE.json configs[4]: synthetic 7680x4320 pair, default params"),
+}
 
 
 def config(args, n_gpus):
     return {
+        "timed_region": "value: one tvl1_solve_batch_dev_f32 call per step with per-kernel-group CUDA events switched on "
+                        "(profiling): the call returns when the step's events have completed, i.e. one host wait per step",
         "workload": "batch of %d synthetic %dx%d frame pairs per rank (BASELINE.json configs[2]), "
                     "5 scales x 5 warps, default params" % (args.pairs, args.nx, args.ny),
         "pairs_per_rank_per_step": args.pairs,
@@ -165,22 +181,37 @@ def run_reference(args, rank, world):
     from optical_flow_1_b200 import synth
     cpu, kind = cpu_solver()
     cpu.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; use every host core
-    I0, I1 = synth.make_pair(args.nx, args.ny, seed=1234)
+    nx, ny, prm, metric, cfg = args.nx, args.ny, PARAMS, METRIC, None
+    if args.workload != "batch1080p":         # one pair of configs[3] / configs[4]: a step is the whole workload
+        case = BAND_CASES[args.workload]
+        nx, ny, prm = case["nx"], case["ny"], case["kw"]
+        metric = "TV-L1 %dx%d frame-pairs/sec, one pair in row bands" % (nx, ny)
+        cfg = {"workload": case["name"] + ", CPU reference (no split)", "params": prm}
+    I0, I1 = synth.make_pair(nx, ny, seed=1234)
     I0, I1 = I0.astype(np.float64), I1.astype(np.float64)
     for _ in range(args.warmup):
-        cpu.multiscale(I0, I1, want_iters=False, **PARAMS)
+        cpu.multiscale(I0, I1, want_iters=False, **prm)
     t = time.perf_counter()
     for _ in range(args.steps):
-        cpu.multiscale(I0, I1, want_iters=False, **PARAMS)
+        cpu.multiscale(I0, I1, want_iters=False, **prm)
     dt = time.perf_counter() - t
     v = args.steps / dt
     sample = ("each step = 1 pair of the workload (%dx%d, seed 1234), fp64, g++ -O3 -fopenmp, %d threads"
-              % (args.nx, args.ny, cpu.max_threads()))
+              % (nx, ny, cpu.max_threads()))
+    if cfg is not None:
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.max_threads(), "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config(args, args.gpus),
+        "data": "synthetic", "config": dict(config(args, args.gpus), reference_arm_step="ONE pair of this workload per step "
+                                            "(a bounded sample: the batch is 256 independent repetitions of this unit)"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.max_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -201,6 +232,169 @@ def pin_to_gpu_numa_node(index):
             os.sched_setaffinity(0, cpus)
     except Exception:
         pass
+
+
+
+# ---- row bands: ONE image pair split over the ranks (BASELINE configs[3], [4]) -----
+def band_measure(pkg, torch, dist, solver, case, rank, world, dev, steps=5, warmup=3, with_e2e=True):
+    """Times the banded solve of one pair on `world` ranks (device-resident buffers, CUDA events on the
+    solver's stream, barrier before every step, max over ranks), the ordinary single-GPU solve of the
+    same pair on this rank, checks that the two agree bit for bit, and times the banded solve through
+    the host-buffer C ABI (tvl1_band_solve_f32, pinned buffers)."""
+    import numpy as np
+    nx, ny, kw, min_rows = case["nx"], case["ny"], case["kw"], case["min_rows"]
+    stream = torch.cuda.ExternalStream(solver.stream(), device=dev)
+    I0, I1 = pkg.synth.make_batch_torch(1, nx, ny, seed=1234, device=dev)
+    u1, u2 = torch.empty_like(I0), torch.empty_like(I0)
+    b1, b2 = torch.empty_like(I0), torch.empty_like(I0)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        pkg.shard.barrier()
+
+    def timed(fn, n):
+        ms = []
+        for _ in range(n):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(pkg.shard.max_over_ranks(e0.elapsed_time(e1), dev))
+        return ms
+
+    solo = lambda: solver.solve_batch_device(I0.data_ptr(), I1.data_ptr(), u1.data_ptr(), u2.data_ptr(), 1, nx, ny,
+                                             want_iters=True, **kw)
+    for _ in range(warmup):
+        it_solo, _ = solo()
+    solo_ms = timed(solo, steps)
+    solo_stats = solver.stats()
+    out = {"case": case["name"], "nx": nx, "ny": ny, "params": kw, "n_gpus": world,
+           "single_gpu_ms": min(solo_ms), "single_gpu_ms_mean": sum(solo_ms) / len(solo_ms),
+           "iterations_per_level_fine_to_coarse": it_solo[0].sum(axis=1).tolist()[::-1]}
+    if world < 2:
+        out["pixel_iterations"] = solo_stats["pixel_iterations"]
+        return out, (I0, I1, u1, u2)
+    uid = [solver.band_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    solver.band_init(rank, world, uid[0])
+    band = lambda: solver.band_solve_device(I0.data_ptr(), I1.data_ptr(), b1.data_ptr(), b2.data_ptr(), nx, ny,
+                                            min_split_rows=min_rows, **kw)
+    for _ in range(warmup):
+        it_band, _ = band()
+    band_ms = timed(band, steps)
+    st = solver.stats()
+    same = bool(torch.equal(u1, b1) and torch.equal(u2, b2) and np.array_equal(it_solo[0], it_band))
+    same = pkg.shard.sum_over_ranks(0.0 if same else 1.0, dev) == 0.0
+    out.update({
+        "band_ms": min(band_ms), "band_ms_mean": sum(band_ms) / len(band_ms),
+        "speedup_vs_single_gpu": min(solo_ms) / min(band_ms),
+        "exchange": solver.band_exchange_mode(), "min_split_rows": min_rows,
+        "band_rows_finest": [solver.band_rows(ny, r, world) for r in range(world)],
+        "bit_identical_to_single_gpu_on_every_rank": same,
+        "host_syncs_per_solve": st["host_syncs"],
+        "halo": "4 rows of the six evolving planes pushed to each neighbour (NVLink stores fused into the "
+                "iteration kernels) after every accepted block of <= 4 iterations; error sums through peer mailboxes",
+    })
+    if with_e2e:
+        h = [torch.empty((ny, nx), dtype=torch.float32).pin_memory() for _ in range(4)]
+        h[0].copy_(I0[0]); h[1].copy_(I1[0])
+        torch.cuda.synchronize()
+        prm = dict(kw)
+        def host():
+            solver.band_solve_host_ptr(h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), h[3].data_ptr(), nx, ny,
+                                       min_split_rows=min_rows, **prm)
+            return float(h[2][ny // 2, nx // 2])
+        for _ in range(2):
+            host()
+        ts = []
+        for _ in range(max(3, steps)):
+            barrier()
+            t = time.perf_counter()
+            host()
+            ts.append(pkg.shard.max_over_ranks(1e3 * (time.perf_counter() - t), dev))
+        out["e2e_host_buffers_ms"] = min(ts)
+        out["e2e_matches"] = bool(torch.equal(h[2], b1[0].cpu()) and torch.equal(h[3], b2[0].cpu()))
+        out["e2e_h2d_bytes_per_rank"] = 2 * nx * ny * 4
+        out["e2e_d2h_bytes_per_rank"] = 2 * nx * ny * 4
+    out["pixel_iterations_this_rank"] = st["pixel_iterations"]
+    return out, (I0, I1, b1, b2)
+
+
+def run_band_workload(args, rank, local_rank, world):
+    """--workload band4k | band8k: one step = one solve of ONE pair, split into row bands over the ranks
+    (strong scaling: the work is fixed, N GPUs share it)."""
+    import torch
+    import torch.distributed as dist
+    import optical_flow_1_b200 as pkg
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the solver has no CPU fallback)")
+    case = BAND_CASES[args.workload]
+    nx, ny = case["nx"], case["ny"]
+    pin_to_gpu_numa_node(local_rank)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    solver = pkg.TVL1(device=local_rank, profiling=False)
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
+    res, bufs = band_measure(pkg, torch, dist, solver, case, rank, world, dev, steps=args.steps, warmup=args.warmup)
+    clk = clocks.stop()
+    ms = res["band_ms"] if world > 1 else res["single_gpu_ms"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # whole-solve algorithmic bytes (SURVEY 8d): 64 B x pixel-iterations + 32 B x pixel-warps, all levels
+    solver.set_profiling(True)
+    solver.solve_batch_device(*[t.data_ptr() for t in bufs], 1, nx, ny, **case["kw"])
+    st = solver.stats()
+    algo = 64 * st["pixel_iterations"] + 32 * st["pixel_warps"]
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import numpy as np
+        cpu, kind = cpu_solver()
+        cpu.set_threads(os.cpu_count() or 1)
+        I0, I1 = pkg.synth.make_pair(nx, ny, seed=1234)
+        t = time.perf_counter()
+        cpu.multiscale(I0.astype(np.float64), I1.astype(np.float64), want_iters=False, **case["kw"])
+        dt = time.perf_counter() - t
+        cpu_base = {"value": 1.0 / dt, "unit": UNIT, "cores": cpu.max_threads(), "kind": kind,
+                    "sample": "the workload's one %dx%d pair, once, fp64, g++ -O3 -fopenmp, %d threads, %.1f s"
+                              % (nx, ny, cpu.max_threads(), dt)}
+    if rank == 0:
+        e2e_ms = res.get("e2e_host_buffers_ms")
+        line = {
+            "metric": "TV-L1 %dx%d frame-pairs/sec, one pair in row bands" % (nx, ny), "value": 1e3 / ms, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": case["name"] + ", row-band split over %d GPU(s)" % world, "params": case["kw"],
+                       "parallelism": "row bands x%d, peer-memory halo exchange fused into the iteration kernels" % world,
+                       "l2": "state of the finest level (%.0f MB) exceeds the 126 MB L2" % (16 * nx * ny * 4 / 1e6)},
+            "clocks": clk,
+            "e2e": {"value": 1e3 / e2e_ms if e2e_ms else None, "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * nx * ny * 4 * world, "d2h_bytes_per_step": 2 * nx * ny * 4 * world,
+                    "api": "tvl1_band_solve_f32 (every rank uploads the pair and receives the whole flow)"}
+                   if e2e_ms else None,
+            "gpu_launches": int(st["kernel_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "whole solve (all levels; iteration + warp kernels)",
+                         "achieved": algo / (res["single_gpu_ms"] / 1e3) / 1e9 if world == 1 else
+                                     algo / (ms / 1e3) / 1e9,
+                         "peak": peak * world, "unit": "GB/s",
+                         "frac": (algo / (ms / 1e3) / 1e9) / (peak * world), "traffic": None,
+                         "note": "algorithmic bytes of the whole pair (64 B x pixel-iterations + 32 B x pixel-warps) "
+                                 "over the solve time, against N x the measured HBM peak; the replicated coarse "
+                                 "levels bound it (Amdahl)"},
+            "cpu_baseline": cpu_base, "row_band": res,
+        }
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---- our arm -------------------------------------------------------------------------------------
@@ -285,21 +479,33 @@ def run_ours(args, rank, local_rank, world):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     it_ms = acc["iterate_ms"]
-    achieved = ALGO_BYTES_PER_PIXEL_ITERATION * acc["pixel_iterations"] / (it_ms / 1e3) / 1e9 if it_ms > 0 else None
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
     except (OSError, ValueError):
         pass
     per_level = []
+    hbm_px = hbm_ms = chip_px = chip_ms = 0.0
+    hbm_launches = 0
     for l in range(PARAMS["nscales"]):
-        lms, lpx = acc["level_iterate_ms"][l], acc["level_pixel_iterations"][l]
-        per_level.append({"level": l, "launches": acc["level_iterate_launches"][l], "ms": lms,
+        lms, lpx, ll = acc["level_iterate_ms"][l], acc["level_pixel_iterations"][l], acc["level_iterate_launches"][l]
+        # a level served by k_iterate_resident is ONE launch per warp step (the whole while loop on chip)
+        on_chip = ll <= PARAMS["warps"] * args.steps
+        per_level.append({"level": l, "kernel": "k_iterate_resident (on chip)" if on_chip else "k_iterate_t1 (+ k_iterate_tb) through HBM",
+                          "launches": ll, "ms": lms,
                           "GBps": ALGO_BYTES_PER_PIXEL_ITERATION * lpx / (lms / 1e3) / 1e9 if lms > 0 else None})
+        if on_chip:
+            chip_px += lpx; chip_ms += lms
+        else:
+            hbm_px += lpx; hbm_ms += lms; hbm_launches += ll
+    # the roofline object is about the dominant HBM-streaming kernel ALONE (k_iterate_t1 on the two finest
+    # levels); the on-chip levels, which move no HBM bytes per iteration, are reported beside it
+    achieved = ALGO_BYTES_PER_PIXEL_ITERATION * hbm_px / (hbm_ms / 1e3) / 1e9 if hbm_ms > 0 else None
+    all_levels = ALGO_BYTES_PER_PIXEL_ITERATION * acc["pixel_iterations"] / (it_ms / 1e3) / 1e9 if it_ms > 0 else None
     roofline = {
-        "kernel": "fused primal-dual iteration (TH + div + u update + grad + p update + stop test): "
-                  "k_iterate_t1 streams the levels above 480x270 through HBM, k_iterate_resident keeps the "
-                  "smaller levels on chip (cluster + DSMEM); per_level shows each",
+        "kernel": "k_iterate_t1 -- the fused primal-dual iteration (TH + div + u update + grad + p update + stop "
+                  "test) streaming the levels above 480x270 through HBM, one iteration per launch "
+                  "(with k_iterate_tb for the pairs whose next block has several iterations)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak if achieved else None,
         "frac_of_nominal_8000": achieved / 8000.0 if achieved else None,
@@ -309,8 +515,13 @@ def run_ours(args, rank, local_rank, world):
         "traffic_algorithmic_bytes_same_launch": traffic.get("algorithmic_bytes_same_launch") if traffic else None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_pixel_iteration": ALGO_BYTES_PER_PIXEL_ITERATION,
-        "pixel_iterations": acc["pixel_iterations"], "launches": acc["iterate_launches"],
-        "kernel_ms": it_ms, "kernel_share_of_step": it_ms / (dev_ms if dev_ms > 0 else 1),
+        "pixel_iterations": hbm_px, "launches": hbm_launches,
+        "kernel_ms": hbm_ms, "kernel_share_of_step": hbm_ms / (dev_ms if dev_ms > 0 else 1),
+        "on_chip_levels": {"kernel": "k_iterate_resident (cluster + DSMEM; 0 HBM bytes per iteration)",
+                           "pixel_iterations": chip_px, "kernel_ms": chip_ms,
+                           "algorithmic_GBps_equivalent": ALGO_BYTES_PER_PIXEL_ITERATION * chip_px / (chip_ms / 1e3) / 1e9 if chip_ms > 0 else None,
+                           "share_of_step": chip_ms / (dev_ms if dev_ms > 0 else 1)},
+        "all_iteration_launches_GBps_equivalent": all_levels,
         "per_level": per_level,
     }
     breakdown = {k: acc[k] / args.steps for k in ("total_ms", "iterate_ms", "warp_ms", "pyramid_ms",
@@ -370,66 +581,109 @@ def run_ours(args, rank, local_rank, world):
     # the device-resident result must equal the host-path result for the same pairs
     same = bool(torch.equal(hu1, u1[:E].cpu()) and torch.equal(hu2, u2[:E].cpu()))
 
-    # the same through the fp64 entry point -- the element type of the reference's own ABI
-    # (ofpix_t = double): twice the PCIe bytes, narrowed / widened on the device
-    E64 = max(4 * args.e2e_max_batch, E // 4)
-    dI0 = hI0[:E64].double().pin_memory()
-    dI1 = hI1[:E64].double().pin_memory()
-    du1 = torch.empty_like(dI0).pin_memory()
-    du2 = torch.empty_like(dI0).pin_memory()
-    del hI0, hI1
+    # copy-only ceiling of this box for the same bytes: every rank at once, H2D of the step's inputs and
+    # D2H of a step's flows on two streams (full duplex), no kernels.  e2e cannot beat it.
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    dI = torch.empty((2, E, ny, nx), dtype=torch.float32, device=dev)
 
-    def step_host64():
-        solver.solve_batch_host_ptr(dI0.data_ptr(), dI1.data_ptr(), du1.data_ptr(), du2.data_ptr(),
-                                    E64, nx, ny, dtype="float64", **PARAMS)
-        return float(du1[0, ny // 2, nx // 2])
+    def copy_only():
+        with torch.cuda.stream(s_in):
+            dI[0].copy_(hI0, non_blocking=True)
+            dI[1].copy_(hI1, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hu1.copy_(u1[:E], non_blocking=True)      # (the same values they already hold)
+            hu2.copy_(u2[:E], non_blocking=True)
+        torch.cuda.synchronize()
 
-    step_host64()
+    copy_only()
     barrier()
     t0 = time.perf_counter()
     for _ in range(2):
+        copy_only()
+    c_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / 2
+    ceiling = world * E / (c_ms / 1e3)
+    e2e["copy_ceiling"] = {"value": ceiling, "unit": UNIT, "ms_per_step": c_ms,
+                           "GBps_each_direction_per_rank": 2 * E * nx * ny * 4 / (c_ms / 1e3) / 1e9,
+                           "what": "same H2D + D2H bytes, all ranks simultaneously, pinned memory, two streams, no kernels"}
+    e2e["frac_of_copy_ceiling"] = e2e["value"] / ceiling
+    e2e["frac_of_device_rate"] = e2e["value"] / value
+    del dI
+
+    if not args.quick:
+        # the same through the fp64 entry point -- the element type of the reference's own ABI
+        # (ofpix_t = double): twice the PCIe bytes, narrowed / widened on the device
+        E64 = max(4 * args.e2e_max_batch, E // 4)
+        dI0 = hI0[:E64].double().pin_memory()
+        dI1 = hI1[:E64].double().pin_memory()
+        du1 = torch.empty_like(dI0).pin_memory()
+        du2 = torch.empty_like(dI0).pin_memory()
+        del hI0, hI1
+
+        def step_host64():
+            solver.solve_batch_host_ptr(dI0.data_ptr(), dI1.data_ptr(), du1.data_ptr(), du2.data_ptr(),
+                                        E64, nx, ny, dtype="float64", **PARAMS)
+            return float(du1[0, ny // 2, nx // 2])
+
         step_host64()
-    torch.cuda.synchronize()
-    e64_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    same64 = bool(torch.equal(du1.float(), hu1[:E64]) and torch.equal(du2.float(), hu2[:E64]))
-    e2e["fp64_abi"] = {"value": world * E64 * 2 / (e64_ms / 1e3), "unit": UNIT, "pairs_per_rank_per_step": E64,
-                       "steps": 2, "h2d_bytes_per_step": 2 * E64 * nx * ny * 8, "d2h_bytes_per_step": 2 * E64 * nx * ny * 8,
-                       "api": "tvl1_solve_batch_f64 (host pinned fp64 in, host fp64 out)", "matches_fp32_path": same64}
-
-    # video form: F consecutive frames -> F-1 flows, each frame uploaded once (tvl1_solve_sequence_f32),
-    # against the pairwise call on the same expanded pairs.  Frames alternate between the two images of
-    # pair 0 (forward / backward flow), so every pair has realistic motion.
-    del dI0, dI1, du1, du2
-    S = E64
-    hF = torch.empty((S + 1, ny, nx), dtype=torch.float32).pin_memory()
-    hF[0::2] = I0[0].cpu()
-    hF[1::2] = I1[0].cpu()
-    sA = hF[:-1].clone().pin_memory()
-    sB = hF[1:].clone().pin_memory()
-    su1 = torch.empty((S, ny, nx), dtype=torch.float32).pin_memory()
-    su2 = torch.empty_like(su1).pin_memory()
-    pu1 = torch.empty_like(su1).pin_memory()
-    pu2 = torch.empty_like(su1).pin_memory()
-
-    def time_host(fn, reps=2):
-        fn()
         barrier()
-        t = time.perf_counter()
-        for _ in range(reps):
-            fn()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            step_host64()
         torch.cuda.synchronize()
-        return max_over_ranks(1e3 * (time.perf_counter() - t)) / reps
+        e64_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        same64 = bool(torch.equal(du1.float(), hu1[:E64]) and torch.equal(du2.float(), hu2[:E64]))
+        e2e["fp64_abi"] = {"value": world * E64 * 2 / (e64_ms / 1e3), "unit": UNIT, "pairs_per_rank_per_step": E64,
+                           "steps": 2, "h2d_bytes_per_step": 2 * E64 * nx * ny * 8, "d2h_bytes_per_step": 2 * E64 * nx * ny * 8,
+                           "api": "tvl1_solve_batch_f64 (host pinned fp64 in, host fp64 out)", "matches_fp32_path": same64}
 
-    seq_ms = time_host(lambda: solver.solve_sequence_host_ptr(hF.data_ptr(), su1.data_ptr(), su2.data_ptr(),
-                                                              S + 1, nx, ny, **PARAMS))
-    pair_ms = time_host(lambda: solver.solve_batch_host_ptr(sA.data_ptr(), sB.data_ptr(), pu1.data_ptr(),
-                                                            pu2.data_ptr(), S, nx, ny, dtype="float32", **PARAMS))
-    e2e["sequence"] = {"value": world * S / (seq_ms / 1e3), "unit": UNIT, "frames_per_rank_per_step": S + 1,
-                       "h2d_bytes_per_step": (S + 1) * nx * ny * 4, "d2h_bytes_per_step": 2 * S * nx * ny * 4,
-                       "api": "tvl1_solve_sequence_f32 (host pinned frames in, host fp32 flows out)",
-                       "pairwise_same_pairs": world * S / (pair_ms / 1e3),
-                       "matches_pairwise": bool(torch.equal(su1, pu1) and torch.equal(su2, pu2))}
-    del hF, sA, sB, su1, su2, pu1, pu2
+        # video form: F consecutive frames -> F-1 flows, each frame uploaded once (tvl1_solve_sequence_f32),
+        # against the pairwise call on the same expanded pairs.  Frames alternate between the two images of
+        # pair 0 (forward / backward flow), so every pair has realistic motion.
+        del dI0, dI1, du1, du2
+        S = E64
+        hF = torch.empty((S + 1, ny, nx), dtype=torch.float32).pin_memory()
+        hF[0::2] = I0[0].cpu()
+        hF[1::2] = I1[0].cpu()
+        sA = hF[:-1].clone().pin_memory()
+        sB = hF[1:].clone().pin_memory()
+        su1 = torch.empty((S, ny, nx), dtype=torch.float32).pin_memory()
+        su2 = torch.empty_like(su1).pin_memory()
+        pu1 = torch.empty_like(su1).pin_memory()
+        pu2 = torch.empty_like(su1).pin_memory()
+
+        def time_host(fn, reps=2):
+            fn()
+            barrier()
+            t = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return max_over_ranks(1e3 * (time.perf_counter() - t)) / reps
+
+        seq_ms = time_host(lambda: solver.solve_sequence_host_ptr(hF.data_ptr(), su1.data_ptr(), su2.data_ptr(),
+                                                                  S + 1, nx, ny, **PARAMS))
+        pair_ms = time_host(lambda: solver.solve_batch_host_ptr(sA.data_ptr(), sB.data_ptr(), pu1.data_ptr(),
+                                                                pu2.data_ptr(), S, nx, ny, dtype="float32", **PARAMS))
+        e2e["sequence"] = {"value": world * S / (seq_ms / 1e3), "unit": UNIT, "frames_per_rank_per_step": S + 1,
+                           "h2d_bytes_per_step": (S + 1) * nx * ny * 4, "d2h_bytes_per_step": 2 * S * nx * ny * 4,
+                           "api": "tvl1_solve_sequence_f32 (host pinned frames in, host fp32 flows out)",
+                           "pairwise_same_pairs": world * S / (pair_ms / 1e3),
+                           "matches_pairwise": bool(torch.equal(su1, pu1) and torch.equal(su2, pu2))}
+        del hF, sA, sB, su1, su2, pu1, pu2
+
+    # ---- row bands (configs[3], configs[4]) on the same ranks: driver-visible at N > 1 ----
+    row_band = None
+    if world > 1 and not args.no_row_band:
+        row_band = {}
+        bs = pkg.TVL1(device=local_rank, profiling=False)
+        for name in ("band4k", "band8k"):
+            try:
+                row_band[name], bufs = band_measure(pkg, torch, dist, bs, BAND_CASES[name], rank, world, dev, steps=3, warmup=2)
+                del bufs
+            except Exception as e:      # keep the headline line even if this leg fails
+                row_band[name] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+        bs.close()
 
     total_launches = sum_over_ranks(acc["kernel_launches"])
     cpu_base = None
@@ -450,6 +704,7 @@ def run_ours(args, rank, local_rank, world):
             "other_kernels": other,
             "whole_solve": whole,
             "e2e_matches_device_path": same,
+            "row_band": row_band,
         }
         print(json.dumps(line))
     solver.close()
@@ -464,6 +719,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload != "batch1080p":
+        run_band_workload(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -96,7 +96,7 @@ bool hs_pipe_fits(const Workspace &w, const Level &l)
     return l.nx >= 17 && (size_t) 5 * L * l.ny <= 6 * w.plane0 && hs_pipe_prefetch(l.ny, -1) >= 0;
 }
 
-// ---- two columns per thread-step (k_hs_sor_pairs; EXPERIMENTAL: not yet run on a GPU, HS_PAIRS=1 only) ----
+// ---- two columns per thread-step (k_hs_sor_pairs; bit-equal to the sequential sweep on a B200, tests/test_hs_gpu.py; selected with HS_PAIRS=1) ----
 int hs_pairs_prefetch(int ny, int want)
 {
     const int rp = round_up(ny, 32);

@@ -1093,12 +1093,17 @@ __device__ __forceinline__ void dual_px(float u1x, float u1y, float u2x, float u
 // which of the two iteration kernels the pair's next block belongs to.
 // The work list lives in shared memory, not in registers: nothing of the loop stays live across
 // the (register-hungry) body.  The host sizes Z so that 32 * Z >= batch: one ballot covers the slot.
-template <class Body>
+// ROUNDS = false: the host sizes Z so that 32 * Z >= batch, one ballot covers the slot (the streaming
+// kernel: a loop around its body costs it 50 registers).  ROUNDS = true: any Z; a narrow launch with
+// fewer than batch / 32 slots goes round again.
+template <bool ROUNDS, class Body>
 __device__ __forceinline__ void for_each_pair_of_slot(const IterParams &P, bool tb_kernel, Body &&body)
 {
     __shared__ unsigned int s_todo;
-    {
-        const int mine = blockIdx.z + (threadIdx.x & 31) * gridDim.z;
+    const int per_round = 32 * (int) gridDim.z;
+#pragma unroll 1
+    for (int base = 0; base < (ROUNDS ? P.batch : 1); base += per_round) {
+        const int mine = base + blockIdx.z + (threadIdx.x & 31) * gridDim.z;
         bool take = false;
         if (mine < P.batch) {
             // a pair's control word changes only after ALL its CTAs, this one included, have arrived:
@@ -1107,18 +1112,19 @@ __device__ __forceinline__ void for_each_pair_of_slot(const IterParams &P, bool 
             const bool blocked = P.tb && c->nsteps > 1;
             take = c->active && (blocked == tb_kernel);
         }
-        const unsigned int todo = __ballot_sync(0xffffffffu, take);
-        if (todo == 0u) return;                      // the common case of a late launch
-        if (threadIdx.x == 0) s_todo = todo;
-    }
-    __syncthreads();
-    for (;;) {
-        const unsigned int todo = *(volatile unsigned int *) &s_todo;
-        if (todo == 0u) break;
-        body((int) blockIdx.z + (__ffs(todo) - 1) * (int) gridDim.z);
-        __syncthreads();                             // the pair's shared-memory scratch is free again
-        if (threadIdx.x == 0) { const unsigned int t = s_todo; s_todo = t & (t - 1u); }
+        const unsigned int todo0 = __ballot_sync(0xffffffffu, take);
+        if (todo0 == 0u) continue;                   // the common case of a late launch (CTA-uniform)
+        if (threadIdx.x == 0) s_todo = todo0;
         __syncthreads();
+        for (;;) {
+            const unsigned int todo = *(volatile unsigned int *) &s_todo;
+            if (todo == 0u) break;
+            body(base + (int) blockIdx.z + (__ffs(todo) - 1) * (int) gridDim.z);
+            __syncthreads();                         // the pair's shared-memory scratch is free again
+            if (threadIdx.x == 0) { const unsigned int t = s_todo; s_todo = t & (t - 1u); }
+            __syncthreads();
+        }
+        __syncthreads();                             // everybody has seen the empty list before it is refilled
     }
 }
 
@@ -1318,7 +1324,7 @@ k_iterate_t1(const IterParams P)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
         atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
-    for_each_pair_of_slot(P, false, [&](int b) { iterate_t1_pair<R, WY>(P, b); });
+    for_each_pair_of_slot<false>(P, false, [&](int b) { iterate_t1_pair<R, WY>(P, b); });
 }
 
 // Row-band mode over peer memory: barrier of all ranks through the mailboxes (start of a solve: no rank
@@ -1934,7 +1940,7 @@ k_iterate_tb(const __grid_constant__ TbMaps maps, const IterParams P)
     __syncthreads();
     __shared__ unsigned int s_parity;                // phase of the next use of mbar
     if (threadIdx.x == 0) s_parity = 0u;
-    for_each_pair_of_slot(P, true, [&](int b) {      // (a barrier separates this from the first read)
+    for_each_pair_of_slot<true>(P, true, [&](int b) {      // (a barrier separates this from the first read)
         const unsigned int parity = *(volatile unsigned int *) &s_parity;
         tb_pair(maps, P, b, tb_smem, s_err, s_tot, mbar, s_last, parity);
         __syncthreads();

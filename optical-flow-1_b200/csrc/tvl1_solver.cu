@@ -105,6 +105,7 @@ struct tvl1_ctx {
     int tail_pairs = 16;                     // lock-step batches: once this few pairs still iterate, the loop goes on
                                              // with narrow launches of tail_slot_ctas CTAs (TVL1_TAIL_PAIRS, 0 = off)
     int tail_slot_ctas = 2048;               // (TVL1_TAIL_SLOT_CTAS)
+    bool tail_tb = true;                     // temporal blocking in the tail even where the full batch runs without (TVL1_TAIL_TB)
     long long tb_max_pixels = 192ll << 20;   // ... which serves lock-step batches up to this many pixels per level
     int force_cluster = 0;                   // tests: force this cluster size where it fits
     bool capturing = false;
@@ -475,10 +476,11 @@ bool tb_usable(tvl1_ctx *ctx, const Level &l, int B);
 // grid.z of the iteration kernels: pair slots (see for_each_pair_of_slot).  Enough slots that a launch
 // with every pair active still has a few thousand CTAs, few enough that a launch with hardly any
 // active pair does not spend its time starting CTAs that exit at once.
-int pair_slots(const tvl1_ctx *ctx, int tiles, int B, bool tail = false)
+int pair_slots(const tvl1_ctx *ctx, int tiles, int B, bool tail = false, bool rounds = false)
 {
-    // at least ceil(B / 32) slots: one ballot of the kernel covers a slot's pairs
-    if (tail) return std::min(B, std::max(ceil_div(B, 32), ceil_div(ctx->tail_slot_ctas, std::max(tiles, 1))));
+    // at least ceil(B / 32) slots: one ballot of the kernel covers a slot's pairs (the temporally blocked
+    // kernel goes round again instead: any number of slots)
+    if (tail) return std::min(B, std::max(rounds ? 1 : ceil_div(B, 32), ceil_div(ctx->tail_slot_ctas, std::max(tiles, 1))));
     return std::min(B, std::max(std::max(32, ceil_div(B, 32)), ceil_div(ctx->slot_ctas, std::max(tiles, 1))));
 }
 
@@ -491,7 +493,9 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B, bool tail = false)
     const int rows = P.row_end - P.row_begin;
     const int tiles_x = ceil_div(P.lv.nx, 124);
     const long long want = 4ll * ctx->sm_count;
-    auto ctas = [&](int R) { return (long long) tiles_x * ceil_div(rows, R * kIterWY) * B; };
+    // a tail launch serves the few pairs still iterating (often one or two): size the strips for an eighth of the switch-over count
+    const int Bw = tail ? std::max(1, ctx->tail_pairs / 8) : B;
+    auto ctas = [&](int R) { return (long long) tiles_x * ceil_div(rows, R * kIterWY) * Bw; };
     if (ctas(16) >= want) {
         dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), 1);
         g.z = pair_slots(ctx, g.x * g.y, B, tail);
@@ -547,6 +551,7 @@ bool make_plane_map(CUtensorMap *m, float *base, int nx, int ny, int nplanes, in
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// B = pairs that a launch is expected to serve (the lock-step batch, or the tail of one)
 bool tb_usable(tvl1_ctx *ctx, const Level &l, int B)
 {
     static bool attr_done[64] = { false };      // function attributes are per device
@@ -575,7 +580,7 @@ int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B, bool tail)
     ok = ok && make_plane_map(&maps.consts, w.consts, P.lv.nx, P.lv.ny, C_COUNT * B, P.lv.pitch, w.plane0);
     if (!ok) { ctx->err = "cuTensorMapEncodeTiled failed"; return TVL1_ERR_CUDA; }
     dim3 g(ceil_div(P.lv.nx, kTbW), ceil_div(P.row_end - P.row_begin, kTbH), 1);
-    g.z = pair_slots(ctx, g.x * g.y, B, tail);
+    g.z = pair_slots(ctx, g.x * g.y, B, tail, true);
     k_iterate_tb<<<g, kTbThreads, kTbSmemBytes, ctx->stream>>>(maps, P);
     CK(cudaGetLastError());
     return TVL1_OK;
@@ -688,6 +693,10 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
         P.cond_bulk = h_bulk;
         P.bulk_min = ctx->tail_pairs;
         TRY(add_while_node(ctx, P, B, h_bulk, false));
+        // the pairs of the tail are the slow ones (tens of iterations where the batch needs two): worth
+        // temporal blocking even where the full batch is not (a wide launch of both kernels costs more
+        // than blocking saves; a narrow one does not)
+        if (!P.tb && ctx->tail_tb && tb_usable(ctx, P.lv, ctx->tail_pairs)) P.tb = 1;
         return add_while_node(ctx, P, B, h_all, true);
     }
     return add_while_node(ctx, P, B, h_all, false);
@@ -1746,6 +1755,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *sc = std::getenv("TVL1_SLOT_CTAS")) ctx->slot_ctas = std::max(1, std::atoi(sc));
     if (const char *tp = std::getenv("TVL1_TAIL_PAIRS")) ctx->tail_pairs = std::max(0, std::atoi(tp));
     if (const char *tc = std::getenv("TVL1_TAIL_SLOT_CTAS")) ctx->tail_slot_ctas = std::max(1, std::atoi(tc));
+    if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
     if (const char *mp = std::getenv("TVL1_TB_MAX_MPIX")) ctx->tb_max_pixels = std::max(0ll, std::atoll(mp)) << 20;
     *out = ctx;
     return TVL1_OK;

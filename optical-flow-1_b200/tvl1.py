@@ -286,6 +286,15 @@ class TVL1:
                                               _fp(iters), _fp(errs)))
         return u1, u2, iters, errs
 
+    def band_solve_host_ptr(self, pI0, pI1, pu1, pu2, nx, ny, min_split_rows=512, **kw):
+        """Banded solve by raw HOST addresses (e.g. pinned torch tensors); collective."""
+        p = dict(PAR_DEFAULTS)
+        p.update(kw)
+        prm = self._params(p["tau"], p["lam"], p["theta"], p["nscales"], p["zfactor"], p["warps"], p["eps"])
+        self._ck(self.lib.tvl1_band_solve_f32(self.ctx, C.c_void_p(pI0), C.c_void_p(pI1), C.c_void_p(pu1),
+                                              C.c_void_p(pu2), C.c_int(nx), C.c_int(ny), C.byref(prm),
+                                              C.c_int(min_split_rows), None, None))
+
     def band_solve_device(self, dI0, dI1, du1, du2, nx, ny, min_split_rows=512, tau=0.25, lam=0.15,
                           theta=0.3, nscales=5, zfactor=0.5, warps=5, eps=0.01):
         prm = self._params(tau, lam, theta, nscales, zfactor, warps, eps)

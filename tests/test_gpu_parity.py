@@ -699,11 +699,11 @@ def test_8k_vs_reference(gpu):
 
 def test_4k_vs_reference(gpu):
     """configs[3]: 3840x2160, 6 scales x 10 warps, eps 0.001 (60 warp steps of up to 300 iterations;
-    about 12 s of CPU reference).  Iteration counts and the mean bound hold as everywhere else.  The
-    max bound holds except at the edge of the moving disc, where the problem is ill-conditioned in
-    fp32: at most 3 pixels of 8.3 M may exceed 1e-2 px, none 2e-2 px -- the reference's OWN float build
-    differs from its fp64 build by 9e-2 px there and exceeds 1e-2 at 33 pixels (profiles/diff_4k.py);
-    when that build travelled with the snapshot the test also checks that the CUDA path is the closer one."""
+    about 12 s of CPU reference).  Iteration counts, the mean bound and the max bound all hold: measured
+    max 7.4e-3 px at one pixel on the edge of the moving disc (row 712, col 1520), where the problem is
+    ill-conditioned in fp32 -- the reference's OWN float build differs from its fp64 build by 9.4e-2 px
+    there and exceeds 1e-2 at 33 pixels (profiles/diff_4k.py, profiles/r2a_diff_4k.txt); when that build
+    travelled with the snapshot the test also checks that the CUDA path is the closer one."""
     cpu, kind = reference_cpu()
     cpu.set_threads(os.cpu_count() or 1)
     I0, I1 = _cases.synth.make_pair(3840, 2160, seed=1234)
@@ -715,7 +715,7 @@ def test_4k_vs_reference(gpu):
           % (kind, d.mean(), d.max(), int((d > MAX_TOL).sum()), iters.sum(axis=1).tolist()))
     assert np.array_equal(iters, riters), (iters.tolist(), riters.tolist())
     assert d.mean() <= MEAN_TOL
-    assert int((d > MAX_TOL).sum()) <= 3 and d.max() <= 2e-2
+    assert d.max() <= MAX_TOL
     if available("reference", np.float32):
         c32 = CpuTvl1("reference", np.float32)
         c32.set_threads(os.cpu_count() or 1)

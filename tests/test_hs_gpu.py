@@ -202,7 +202,14 @@ def test_hs_vga_default_parameters_against_the_compiled_reference(gpu):
     R = CpuTvl1("reference", np.float64)
     ru, rv, rit, rerr = R.hs_multiscale(I1, I2, **kw)
     u, v, it, err = gpu.horn_schunck_pyramidal(I1.astype(np.float32), I2.astype(np.float32), **kw)
-    assert np.array_equal(it, rit), (it - rit)
+    # 60 warp steps at TOL = 1e-4, where the update norm falls by well under a percent per sweep: a
+    # rounding-sized perturbation can move a stopping sweep by one.  The reference's own float build
+    # differs from its fp64 build at 1 of these 60 steps (profiles/r1i_hs_reference_float_vs_double.txt);
+    # the CUDA path is held to the same: at most 2 steps, by at most 2 sweeps -- and to the flow tolerance.
+    diff = it - rit
+    print("640x480 HS: warp steps with a different sweep count: %d of %d, max |d sweeps| %d"
+          % (int((diff != 0).sum()), diff.size, int(np.abs(diff).max())))
+    assert int((diff != 0).sum()) <= 2 and np.abs(diff).max() <= 2, diff.tolist()
     assert_flow_close(u, v, ru, rv, "640x480")
     st = gpu.stats()
     assert st["iterate_launches"] == kw["nscales"] * kw["warps"]
@@ -284,3 +291,34 @@ def test_hs_1080p_against_the_reference(gpu):
     assert_flow_close(u, v, ru, rv, "1080p")
     assert np.abs(it - rit).max() <= 1, (it - rit)          # sweep counts: see the printed parity table
     assert (it != rit).sum() <= 2, (it - rit)
+
+
+# ---- k_hs_sor_pairs: pipelined sweeps, two columns per thread-step (csrc/hs_sor_pairs.h) ----------------
+# First run on a B200 in round 2 (profiles/r2a: 12 of 12 bit-equal); hook code prefetch = -4 forces it.
+@pytest.mark.parametrize("nx,ny,sweeps", [(37, 29, 7), (64, 48, 7), (131, 70, 5), (33, 200, 5), (40, 1100, 3),
+                                          (1920, 1080, 3)])
+def test_pairs_kernel_is_the_sequential_sweep_bitwise(gpu, nx, ny, sweeps):
+    ix, iy, rho, u, v, _ = _hs_emu.system(nx, ny, seed=nx * 100 + ny)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, 0.0, sweeps)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=0.0, maxiter=sweeps, prefetch=-4)
+    assert gn == rn == sweeps
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv), (np.abs(gu - ru).max(), np.abs(gv - rv).max())
+    assert abs(gerr - rerr) <= 1e-9 * max(1.0, rerr)
+
+
+@pytest.mark.parametrize("nx,ny", [(96, 80), (64, 300)])
+@pytest.mark.parametrize("tol", [1e-1, 1e-2, 1e-3])
+def test_pairs_kernel_stops_exactly(gpu, nx, ny, tol):
+    ix, iy, rho, u, v, _ = _hs_emu.system(nx, ny, seed=3)
+    ru, rv, rn, rerr = _hs_emu.run_seq(ix, iy, rho, u, v, 7.0, tol, 150)
+    gu, gv, gn, gerr = gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=tol, maxiter=150, prefetch=-4)
+    assert 1 < rn < 150 and gn == rn
+    assert np.array_equal(gu, ru) and np.array_equal(gv, rv)
+    assert abs(gerr - rerr) <= 1e-9 * max(1.0, rerr)
+
+
+def test_pairs_kernel_rejects_levels_it_cannot_hold(gpu):
+    """Too few rows for the two-column schedule: the hook refuses (the solver never selects it there)."""
+    ix, iy, rho, u, v, _ = _hs_emu.system(32, 3, seed=1)
+    with pytest.raises(pkg.TVL1Error):
+        gpu.sor(ix, iy, rho, u, v, alpha=7.0, tol=0.0, maxiter=3, prefetch=-4)
