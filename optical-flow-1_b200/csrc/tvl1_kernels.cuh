@@ -71,6 +71,19 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi)
 {
     return min(max(v, lo), hi);
 }
+__device__ __forceinline__ unsigned int smem_u32(const void *p)
+{
+    return (unsigned int) __cvta_generic_to_shared(p);
+}
+// one box of a 3-D tensor map -> shared memory, completion on an mbarrier (SASS: UTMALDG.3D)
+__device__ __forceinline__ void tma_load_3d(float *dst, const CUtensorMap *map, int x, int y, int z,
+                                            unsigned long long *mbar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z),
+                    "r"(smem_u32(mbar)) : "memory");
+}
 // order-preserving float <-> uint map for atomicMin/atomicMax
 __device__ __forceinline__ unsigned int f2ord(float f)
 {
@@ -688,35 +701,53 @@ __device__ __forceinline__ float grad_of(float ix, float iy)
 }
 
 // `fetch(r, c)` returns I1 at row y-2+r, column x-2+c with index clamping already applied.
+// Keys (a = -1/2) weights built from the partition of unity and the first moment: 10 operations, and
+// sum(w) == 1 up to one rounding.
+__device__ __forceinline__ void keys_weights_pu(float t, float w[4])
+{
+    const float s = 1.0f - t;
+    const float h = -0.5f * t * s;          // -t(1-t)/2
+    w[0] = h * s;                           // -t(1-t)^2/2
+    w[3] = h * t;                           // -t^2(1-t)/2
+    w[2] = fmaf(-2.0f, w[3], t + w[0]);     // first moment: -w0 + w2 + 2 w3 = t
+    w[1] = ((1.0f - w[0]) - w[2]) - w[3];
+}
+
 template <class Fetch>
 __device__ __forceinline__ void warp_gather(Fetch fetch, float tx, float ty, float &w, float &wx, float &wy)
 {
     float ax[4], ay[4];
-    keys_weights(tx, ax);
-    keys_weights(ty, ay);
-    // x-derivative taps: sum_a ax[a] * (c[a+3] - c[a+1]) regrouped per column
-    const float d0 = -ax[0], d1 = -ax[1], d2 = ax[0] - ax[2], d3 = ax[1] - ax[3], d4 = ax[2], d5 = ax[3];
-    float rowI[6];   // x-interpolated I1 on rows y-2 .. y+3
+    keys_weights_pu(tx, ax);
+    keys_weights_pu(ty, ay);
+    const float d2 = ax[0] - ax[2], d3 = ax[1] - ax[3];
+    float rowI[6];
     float accx = 0.f;
 #pragma unroll
     for (int r = 0; r < 6; r++) {
         const float c1 = fetch(r, 1), c2 = fetch(r, 2), c3 = fetch(r, 3), c4 = fetch(r, 4);
-        rowI[r] = ax[0] * c1 + ax[1] * c2 + ax[2] * c3 + ax[3] * c4;
+        rowI[r] = fmaf(ax[3], c4, fmaf(ax[2], c3, fmaf(ax[1], c2, ax[0] * c1)));
         if (r >= 1 && r <= 4) {
             const float c0 = fetch(r, 0), c5 = fetch(r, 5);
-            const float dxr = d0 * c0 + d1 * c1 + d2 * c2 + d3 * c3 + d4 * c4 + d5 * c5;
-            accx += ay[r - 1] * dxr;
+            float dxr = ax[3] * c5;
+            dxr = fmaf(ax[2], c4, dxr);
+            dxr = fmaf(d3, c3, dxr);
+            dxr = fmaf(d2, c2, dxr);
+            dxr = fmaf(-ax[1], c1, dxr);
+            dxr = fmaf(-ax[0], c0, dxr);
+            accx = fmaf(ay[r - 1], dxr, accx);
         }
     }
-    w = ay[0] * rowI[1] + ay[1] * rowI[2] + ay[2] * rowI[3] + ay[3] * rowI[4];
+    w = fmaf(ay[3], rowI[4], fmaf(ay[2], rowI[3], fmaf(ay[1], rowI[2], ay[0] * rowI[1])));
     wx = 0.5f * accx;
-    wy = 0.5f * (ay[0] * (rowI[2] - rowI[0]) + ay[1] * (rowI[3] - rowI[1]) +
-                 ay[2] * (rowI[4] - rowI[2]) + ay[3] * (rowI[5] - rowI[3]));
+    float a = ay[0] * (rowI[2] - rowI[0]);
+    a = fmaf(ay[1], rowI[3] - rowI[1], a);
+    a = fmaf(ay[2], rowI[4] - rowI[2], a);
+    a = fmaf(ay[3], rowI[5] - rowI[3], a);
+    wy = 0.5f * a;
 }
 
-// Rare path of k_warp: a pixel whose flow exceeds the staged margin gathers from global memory.
 __device__ __noinline__ void warp_gather_global(const float *__restrict__ img1, int pitch, int nx, int ny,
-                                                int x, int y, float tx, float ty, float *out3)
+                                                 int x, int y, float tx, float ty, float *out3)
 {
     float w, wx, wy;
     warp_gather([&](int r, int c) {
@@ -747,30 +778,33 @@ __device__ __forceinline__ void cp_async16(float *dst, const float *src)
 }
 
 __global__ void __launch_bounds__(256, 4)
-k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_stride,
-       const float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
-       const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv, int write_grad,
-       int row_begin, int row_end)
+k_warp(const __grid_constant__ CUtensorMap map_i1, const int use_tma,
+        const float *__restrict__ I0, const float *__restrict__ I1, size_t img_stride,
+        const float *__restrict__ state, size_t plane0, size_t field_stride, size_t set_stride,
+        const PairCtl *__restrict__ ctl, float *__restrict__ consts, Level lv, int write_grad,
+        int row_begin, int row_end)
 {
-    __shared__ __align__(16) float s_box[kWarpBH * kWarpBW];
+    __shared__ __align__(128) float s_box[kWarpBH * kWarpBW];
+    __shared__ unsigned long long mbar;
     const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
     const int tid = ty * 32 + tx;
     const int b = blockIdx.z;
     const int nx = lv.nx, ny = lv.ny, pitch = lv.pitch;
-    // per-pair base pointers once (64-bit); every pixel access below is base + 32-bit offset
-    const float *img1 = I1 + (size_t) b * img_stride;
-    const float *img0 = I0 + (size_t) b * img_stride;
-    const float *pu1 = state + (size_t) ctl[b].cur * set_stride + (size_t) b * plane0;
-    const float *pu2 = pu1 + field_stride;
-    float *cIx = consts + (size_t) C_IX * field_stride + (size_t) b * plane0;
-    float *cIy = consts + (size_t) C_IY * field_stride + (size_t) b * plane0;
-    float *cRho = consts + (size_t) C_RHO * field_stride + (size_t) b * plane0;
-    float *cGrad = consts + (size_t) C_GRAD * field_stride + (size_t) b * plane0;
     const int X0 = blockIdx.x * kWarpTW, Y0 = row_begin + blockIdx.y * kWarpTH;
     const int bx0 = X0 - kWarpBX, by0 = Y0 - kWarpBY;
+    const float *img1 = I1 + (size_t) b * img_stride;
 
-    // ---- stage the box (asynchronously) ---------------------------------------------------------
-    if (bx0 >= 0 && by0 >= 0 && bx0 + kWarpBW <= nx && by0 + kWarpBH <= ny) {
+    const bool box_inside = bx0 >= 0 && by0 >= 0 && bx0 + kWarpBW <= nx && by0 + kWarpBH <= ny;
+    const bool tma = use_tma && box_inside;          // CTA-uniform
+    if (tma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         :: "r"(smem_u32(&mbar)), "r"((unsigned int) (kWarpBH * kWarpBW * sizeof(float))) : "memory");
+            tma_load_3d(s_box, &map_i1, bx0, by0, b, &mbar);
+        }
+    } else if (box_inside) {
         const float *src = img1 + by0 * pitch + bx0;
         for (int t = tid; t < kWarpBH * (kWarpBW / 4); t += 256) {
             const int ly = t / (kWarpBW / 4), l4 = t - ly * (kWarpBW / 4);
@@ -785,60 +819,61 @@ k_warp(const float *__restrict__ I0, const float *__restrict__ I1, size_t img_st
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 
-    // ---- flow, I0 and sample positions of this thread's four pixels ------------------------------
+    // ---- flow and I0 of this thread's four pixels: (jj, ii), (jj+32, ii), (jj, ii+8), (jj+32, ii+8) ----
     const int jj = X0 + tx, ii = Y0 + ty;
-    const int p00 = ii * pitch + jj;                 // pixel q sits at p00 + 32*(q&1) + 8*pitch*(q>>1)
-    float u1[4], u2[4], ftx[4], fty[4], i0v[4];
-    int sx[4], sy[4];
-    bool inside[4], valid[4];
+    const size_t pair_off = (size_t) b * plane0;
+    const float *pu1 = state + (size_t) ctl[b].cur * set_stride + pair_off + (size_t) ii * pitch + jj;
+    const float *pu2 = pu1 + field_stride;
+    const float *pi0 = I0 + (size_t) b * img_stride + (size_t) ii * pitch + jj;
+    const bool full = X0 + kWarpTW <= nx && Y0 + kWarpTH <= row_end;      // CTA-uniform: no pixel outside
+    const int dn = 8 * pitch;
+    float u1[4], u2[4], i0v[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int j = jj + 32 * (q & 1), i = ii + 8 * (q >> 1);
-        const int p = p00 + 32 * (q & 1) + 8 * pitch * (q >> 1);
-        inside[q] = j < nx && i < row_end;
-        u1[q] = u2[q] = i0v[q] = 0.f;
-        if (inside[q]) {
-            u1[q] = __ldg(pu1 + p);
-            u2[q] = __ldg(pu2 + p);
-            i0v[q] = __ldg(img0 + p);
-        }
+        const int o = 32 * (q & 1) + dn * (q >> 1);
+        const bool in = full || (jj + 32 * (q & 1) < nx && ii + 8 * (q >> 1) < row_end);
+        u1[q] = in ? __ldg(pu1 + o) : 0.f;
+        u2[q] = in ? __ldg(pu2 + o) : 0.f;
+        i0v[q] = in ? __ldg(pi0 + o) : 0.f;
     }
+    if (tma) {
+        __syncthreads();                 // the barrier word is initialised before anybody polls it
+        unsigned int done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+    } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+
+    float *cIx = consts + (size_t) C_IX * field_stride + pair_off + (size_t) ii * pitch + jj;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int j = jj + 32 * (q & 1), i = ii + 8 * (q >> 1);
+        if (!full && !(j < nx && i < row_end)) continue;
         const float fu = floorf(u1[q]), fv = floorf(u2[q]);
         const float xf = (float) j + fu, yf = (float) i + fv;
-        valid[q] = inside[q] && xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
-        sx[q] = valid[q] ? (int) xf : 0;
-        sy[q] = valid[q] ? (int) yf : 0;
-        ftx[q] = u1[q] - fu;
-        fty[q] = u2[q] - fv;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        if (!inside[q]) continue;
-        const int p = p00 + 32 * (q & 1) + 8 * pitch * (q >> 1);
+        const bool valid = xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
         float w = 0.f, wx = 0.f, wy = 0.f;
-        if (valid[q]) {
-            const int cx = sx[q] - 2 - bx0, cy = sy[q] - 2 - by0;       // box coordinates of tap (0,0)
-            if (cx >= 0 && cy >= 0 && cx + 6 <= kWarpBW && cy + 6 <= kWarpBH) {
+        if (valid) {
+            const int sx = (int) xf, sy = (int) yf;
+            const float ftx = u1[q] - fu, fty = u2[q] - fv;
+            const int cx = sx - 2 - bx0, cy = sy - 2 - by0;       // box coordinates of tap (0,0)
+            if ((unsigned) cx <= (unsigned) (kWarpBW - 6) && (unsigned) cy <= (unsigned) (kWarpBH - 6)) {
                 const float *base = s_box + cy * kWarpBW + cx;
-                warp_gather([&](int r, int c) { return base[r * kWarpBW + c]; }, ftx[q], fty[q], w, wx, wy);
+                warp_gather([&](int r, int c) { return base[r * kWarpBW + c]; }, ftx, fty, w, wx, wy);
             } else {
                 float o3[3];
-                warp_gather_global(img1, pitch, nx, ny, sx[q], sy[q], ftx[q], fty[q], o3);
+                warp_gather_global(img1, pitch, nx, ny, sx, sy, ftx, fty, o3);
                 w = o3[0]; wx = o3[1]; wy = o3[2];
             }
         }
-        cIx[p] = wx;
-        cIy[p] = wy;
-        // I1w - I0 first (nearly equal magnitudes: the difference is exact or close to it), then the two
-        // small products as FMAs: no rounding at the 0..255 scale of the images
-        cRho[p] = __fmaf_rn(-wy, u2[q], __fmaf_rn(-wx, u1[q], __fsub_rn(w, i0v[q])));
-        if (write_grad) cGrad[p] = grad_of(wx, wy);
+        const int o = 32 * (q & 1) + dn * (q >> 1);
+        cIx[o] = wx;
+        cIx[field_stride + o] = wy;                 // C_IY
+        cIx[2 * field_stride + o] = __fmaf_rn(-wy, u2[q], __fmaf_rn(-wx, u1[q], __fsub_rn(w, i0v[q])));   // C_RHO
+        if (write_grad) cIx[3 * field_stride + o] = grad_of(wx, wy);
     }
 }
 
@@ -1425,10 +1460,6 @@ __host__ __device__ inline size_t resident_smem_bytes(int pitch, int rows_per_ct
     return (size_t) pitch * (6 * rows_per_cta + 4) * sizeof(float) + (2 * kResMaxCluster) * sizeof(double) + 16;
 }
 
-__device__ __forceinline__ unsigned int smem_u32(const void *p)
-{
-    return (unsigned int) __cvta_generic_to_shared(p);
-}
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
 __global__ void __launch_bounds__(kResThreads, 1)
@@ -1692,15 +1723,6 @@ struct TbMaps {
     CUtensorMap state[2];      // dims (nx, ny, 6*B) of ping-pong set 0 / 1
     CUtensorMap consts;        // dims (nx, ny, 4*B)
 };
-
-__device__ __forceinline__ void tma_load_3d(float *dst, const CUtensorMap *map, int x, int y, int z,
-                                            unsigned long long *mbar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-                 "[%0], [%1, {%2, %3, %4}], [%5];"
-                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z),
-                    "r"(smem_u32(mbar)) : "memory");
-}
 
 // The iterations of k_iterate_tb on the shared-memory box.  INTERIOR = the box lies inside the image
 // and touches neither its last column nor its last row: all boundary predicates fold away.

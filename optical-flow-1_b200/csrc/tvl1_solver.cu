@@ -101,6 +101,7 @@ struct tvl1_ctx {
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
     bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
+    bool warp_tma = true;                    // TVL1_WARP_TMA=0: stage the warp kernel's box with cp.async only
     int slot_ctas = 32768;                   // CTAs a full iteration launch should have at least (TVL1_SLOT_CTAS)
     int tail_pairs = 16;                     // lock-step batches: once this few pairs still iterate, the loop goes on
                                              // with narrow launches of tail_slot_ctas CTAs (TVL1_TAIL_PAIRS, 0 = off)
@@ -537,16 +538,17 @@ EncodeTiledFn tensor_map_encoder()
     return fn;
 }
 
-// planes[z][y][x] with row pitch `pitch` and plane stride `plane` (floats); box 64 x 32 x 1, zero fill
-bool make_plane_map(CUtensorMap *m, float *base, int nx, int ny, int nplanes, int pitch, size_t plane)
+// planes[z][y][x] with row pitch `pitch` and plane stride `plane` (floats); box bw x bh x 1, zero fill
+bool make_plane_map(CUtensorMap *m, const float *base, int nx, int ny, int nplanes, int pitch, size_t plane,
+                    int bw = kTbBW, int bh = kTbBH)
 {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint64_t dims[3] = { (cuuint64_t) nx, (cuuint64_t) ny, (cuuint64_t) nplanes };
     const cuuint64_t strides[2] = { (cuuint64_t) pitch * sizeof(float), (cuuint64_t) plane * sizeof(float) };
-    const cuuint32_t box[3] = { kTbBW, kTbBH, 1 };
+    const cuuint32_t box[3] = { (cuuint32_t) bw, (cuuint32_t) bh, 1 };
     const cuuint32_t estr[3] = { 1, 1, 1 };
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -623,7 +625,12 @@ int launch_warp(tvl1_ctx *ctx, int s, int B, int write_grad = 0, int row_begin =
     const Level &l = w.lv[s];
     if (row_end < 0) row_end = l.ny;
     dim3 g(ceil_div(l.nx, kWarpTW), ceil_div(row_end - row_begin, kWarpTH), B);
-    k_warp<<<g, dim3(32, 8), 0, ctx->stream>>>(w.I0(s), w.I1(s), w.plane(s), w.state, w.plane0,
+    // interior tiles pull their box of I1 with one TMA copy: a 3-D tensor map (nx, ny, pair) of the level
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    const int use_tma = ctx->warp_tma && l.nx >= kWarpBW && l.ny >= kWarpBH &&
+                        make_plane_map(&map, w.I1(s), l.nx, l.ny, B, l.pitch, w.plane(s), kWarpBW, kWarpBH) ? 1 : 0;
+    k_warp<<<g, dim3(32, 8), 0, ctx->stream>>>(map, use_tma, w.I0(s), w.I1(s), w.plane(s), w.state, w.plane0,
                                                w.field_stride, w.set_stride, w.ctl, w.consts, l, write_grad,
                                                row_begin, row_end);
     CKL(ctx);
@@ -1292,8 +1299,14 @@ const char *load_nccl()
 {
     std::lock_guard<std::mutex> lk(g_nccl_mutex);
     if (g_nccl.lib) return nullptr;
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    // The NCCL the process already uses comes first (a host program or torch.distributed has usually
+    // loaded one; a second copy of another version under the same soname would break whoever binds
+    // later), then an explicit path (TVL1_NCCL_LIB), then the system library.  Never RTLD_GLOBAL: our
+    // symbols are looked up with dlsym and nobody else should resolve against what we happened to load.
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) if (const char *path = std::getenv("TVL1_NCCL_LIB")) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!h) return "libnccl.so.2 not found";
 #define TVL1_SYM(field, name)                                                        \
     g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));         \
@@ -1752,6 +1765,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
+    if (const char *wt = std::getenv("TVL1_WARP_TMA")) ctx->warp_tma = !(wt[0] == '0');
     if (const char *sc = std::getenv("TVL1_SLOT_CTAS")) ctx->slot_ctas = std::max(1, std::atoi(sc));
     if (const char *tp = std::getenv("TVL1_TAIL_PAIRS")) ctx->tail_pairs = std::max(0, std::atoi(tp));
     if (const char *tc = std::getenv("TVL1_TAIL_SLOT_CTAS")) ctx->tail_slot_ctas = std::max(1, std::atoi(tc));

@@ -248,7 +248,19 @@ class TVL1:
                     C.c_int(nx), C.c_int(ny), C.byref(prm), None, None))
 
     # -- row-band mode: one image pair over several GPUs -------------------------------------------
+    @staticmethod
+    def _prefer_torch_nccl():
+        """The library binds NCCL at run time and takes the copy the process has already loaded.  In a
+        Python process that copy should be torch's own (torch.distributed is the plumbing around the band
+        mode): import torch first, so that a later `import torch` does not find an older system libnccl
+        under the same soname."""
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+
     def band_unique_id(self):
+        self._prefer_torch_nccl()
         buf = (C.c_ubyte * 128)()
         rc = self.lib.tvl1_band_unique_id(buf)
         if rc:
@@ -256,6 +268,7 @@ class TVL1:
         return bytes(buf)
 
     def band_init(self, rank, world, unique_id):
+        self._prefer_torch_nccl()
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._ck(self.lib.tvl1_band_init(self.ctx, C.c_int(rank), C.c_int(world), buf))
 
