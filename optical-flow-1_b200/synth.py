@@ -51,6 +51,20 @@ def make_pair(nx, ny, seed=1234, scale=1.0):
     return I0.astype(np.float32), I1.astype(np.float32)
 
 
+def make_triple(nx, ny, seed=1234, scale=1.0):
+    """numpy float32 (I_1, I0, I1): the texture one step back, now and one step ahead along the same
+    two motions -- the three frames src/tvl1occflow.cpp takes (previous, source, target)."""
+    Y, X = np.meshgrid(np.arange(ny, dtype=np.float64), np.arange(nx, dtype=np.float64),
+                       indexing="ij")
+    disc = (X - 0.5 * nx) ** 2 + (Y - 0.5 * ny) ** 2 < (0.25 * ny) ** 2
+    dx = np.where(disc, DISC_MOTION[0], BG_MOTION[0]) * scale
+    dy = np.where(disc, DISC_MOTION[1], BG_MOTION[1]) * scale
+    I_1 = _texture(np, X + dx, Y + dy, seed)
+    I0 = _texture(np, X, Y, seed)
+    I1 = _texture(np, X - dx, Y - dy, seed)
+    return I_1.astype(np.float32), I0.astype(np.float32), I1.astype(np.float32)
+
+
 def make_batch_torch(npairs, nx, ny, seed=1234, device="cuda"):
     """torch float32 (I0[npairs, ny, nx], I1[...]) on `device`; pair b uses seed + b."""
     import torch

@@ -321,3 +321,77 @@ def c99_multiscale(lib, I0, I1, tau=0.25, lam=0.15, theta=0.3, nscales=5, zfacto
     lib.Dual_TVL1_optic_flow_multiscale(I0.ctypes.data, I1.ctypes.data, u[0].ctypes.data, u[1].ctypes.data,
                                         nx, ny, tau, lam, theta, nscales, zfactor, warps, eps, False)
     return u[0], u[1]
+
+
+# ---- TV-L1 with occlusions -----------------------------------------------------------
+OCC_DEFAULTS = dict(lam=0.15, alpha=0.01, beta=0.15, theta=0.3, nscales=5, zfactor=0.5, warps=2, eps=0.01)
+
+
+def occ_available(kind, dtype=np.float64):
+    suffix = "f64" if np.dtype(dtype) == np.float64 else "f32"
+    if kind == "port":
+        return os.path.exists(os.path.join(HERE, "libtvl1_oracle_%s.so" % suffix))
+    return os.path.exists(os.path.join(HERE, "_ref", "libocc_ref_%s.so" % suffix))
+
+
+class CpuOcc:
+    """src/tvl1occflow*.cpp on the CPU: the C restatement (``port``, oracle/tvl1_oracle.c section (e)) or the
+    unmodified reference objects behind oracle/occ_ref_shim.cpp (``reference``; zero-filling new[], see
+    that file).  Images are (ny, nx) arrays; I_1 = frame before I0, filtI0 = the image g is taken from."""
+
+    def __init__(self, kind="port", dtype=np.float64):
+        assert kind in ("port", "reference")
+        self.kind, self.dtype = kind, np.dtype(dtype)
+        suffix = "f64" if self.dtype == np.float64 else "f32"
+        path = (os.path.join(HERE, "libtvl1_oracle_%s.so" % suffix) if kind == "port"
+                else os.path.join(HERE, "_ref", "libocc_ref_%s.so" % suffix))
+        if not os.path.exists(path):
+            build(ref=(kind == "reference"))
+        self.lib = C.CDLL(path)
+        self.pfx = "orc_occ_" if kind == "port" else "occ_ref_"
+        if kind == "reference":
+            assert self.lib.occ_ref_sizeof_pix() == self.dtype.itemsize
+            assert self.lib.occ_ref_new_is_zeroing() == 1
+        else:
+            assert self.lib.orc_sizeof_pix() == self.dtype.itemsize
+
+    def _arr(self, a):
+        return np.ascontiguousarray(a, dtype=self.dtype)
+
+    _p = staticmethod(lambda a: a.ctypes.data_as(C.c_void_p))
+
+    def set_threads(self, n):
+        (self.lib.orc_set_threads if self.kind == "port" else self.lib.occ_ref_set_threads)(C.c_int(int(n)))
+
+    def multiscale(self, I_1, I0, I1, filtI0=None, lam=0.15, alpha=0.01, beta=0.15, theta=0.3, nscales=5,
+                   zfactor=0.5, warps=2, eps=0.01):
+        """-> (u1, u2, chi, iters[nscales, warps] coarsest level first, errs)."""
+        I_1, I0, I1 = self._arr(I_1), self._arr(I0), self._arr(I1)
+        f = self._arr(I0 if filtI0 is None else filtI0)
+        ny, nx = I0.shape
+        u1, u2, chi = (np.zeros_like(I0) for _ in range(3))
+        it = np.zeros((nscales, warps), np.int32)
+        er = np.zeros((nscales, warps), np.float64)
+        rc = getattr(self.lib, self.pfx + "multiscale")(
+            self._p(I_1), self._p(I0), self._p(I1), self._p(f), self._p(u1), self._p(u2), self._p(chi),
+            C.c_int(nx), C.c_int(ny), C.c_double(lam), C.c_double(alpha), C.c_double(beta), C.c_double(theta),
+            C.c_int(nscales), C.c_double(zfactor), C.c_int(warps), C.c_double(eps), self._p(it), self._p(er))
+        if self.kind == "port" and rc:
+            raise RuntimeError("GaussianSmooth: sigma too large")
+        return u1, u2, chi, it, er
+
+    def rof_box(self, u, f, p1, p2, g, lam, omega=1.25, niter=10):
+        """Scalar_ROF_BoxCellCentered -> (u, p1, p2) after niter sweeps."""
+        u, p1, p2 = self._arr(u).copy(), self._arr(p1).copy(), self._arr(p2).copy()
+        f, g = self._arr(f), self._arr(g)
+        ny, nx = u.shape
+        getattr(self.lib, self.pfx + "rof_box")(self._p(u), self._p(f), self._p(p1), self._p(p2), self._p(g),
+                                                C.c_double(lam), C.c_double(omega), C.c_int(nx), C.c_int(ny),
+                                                C.c_int(niter))
+        return u, p1, p2
+
+    def median3(self, a):
+        a = self._arr(a).copy()
+        ny, nx = a.shape
+        (self.lib.orc_median3 if self.kind == "port" else self.lib.occ_ref_median3)(self._p(a), C.c_int(nx), C.c_int(ny))
+        return a

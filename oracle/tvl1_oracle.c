@@ -28,9 +28,11 @@
 typedef float PIX;
 /* the reference is C++: hypot(float, float) resolves to the float overload (src/tvl1flow.cpp:172) */
 #define ORC_HYPOT(a, b) hypotf((a), (b))
+#define ORC_SQRT_PIX(a) sqrtf(a)
 #else
 typedef double PIX;
 #define ORC_HYPOT(a, b) hypot((a), (b))
+#define ORC_SQRT_PIX(a) sqrt(a)
 #endif
 
 #define ORC_MAX_ITERATIONS 300      /* src/tvl1flow.cpp:22 */
@@ -705,5 +707,421 @@ int orc_hs_multiscale(const PIX *I1, const PIX *I2, PIX *u, PIX *v, int nx0, int
     for (int i = 1; i < built; i++) { free(I1s[i]); free(I2s[i]); free(us[i]); free(vs[i]); }
     free(I1s[0]); free(I2s[0]);
     free(I1s); free(I2s); free(us); free(vs); free(nx); free(ny);
+    return rc;
+}
+
+/* ==========================================================================================
+ * (e) TV-L1 with occlusion detection: src/tvl1occflow.cpp,
+ *     src/tvl1occflow_solvers.cpp, src/tvl1occflow_tv_rof_box.cpp, me_median_filtering of src/utils.cpp
+ *
+ * DEFINED BEHAVIOUR.  The reference keeps the dual variables of Solver_wrt_u (p11..p22) and of
+ * Solver_wrt_chi (eta1, eta2) in function-level statics that are re-created whenever the image width
+ * changes (src/tvl1occflow_solvers.cpp:163-186, :241-253); eta1/eta2 are then READ UNINITIALISED
+ * (:262, the file's own #warning).  What a fresh process computes de facto -- large new[] blocks come
+ * from zero pages -- is: p and eta start from zero at every pyramid level.  That is the behaviour
+ * restated here, and the compiled reference is pinned to it by building it with a zero-filling
+ * operator new[] (oracle/occ_ref_shim.cpp; the reference sources stay untouched).
+ * Consecutive levels always differ in width, so "re-created when nx changes" == "per level".
+ * ========================================================================================== */
+#define ORC_OCC_EXT_MAX_ITERATIONS 20    /* src/tvl1occflow_constants.h:25 */
+#define ORC_OCC_OMEGA 1.25               /* :26 */
+#define ORC_OCC_IS_ZERO 1E-10            /* :28 */
+#define ORC_OCC_THR_CHI 0.75             /* :29 */
+#define ORC_OCC_MAX_ITERATIONS_CHI 100   /* :30 */
+#define ORC_OCC_PRESMOOTHING_SIGMA 0.8   /* :31 */
+#define ORC_OCC_G_FACTOR 0.05            /* :35 (G_CHOICE 2) */
+#define ORC_OCC_MAX_ITERATIONS_U 10      /* :37 */
+#define ORC_OCC_TAU_ETA 0.15             /* :38 */
+#define ORC_OCC_TAU_CHI 0.15             /* :39 */
+
+/* me_median_filtering, src/utils.cpp:151-213, window 3: median of the 3x3 neighbourhood with the
+ * symmetric boundary x<0 -> -x-1, x>=n -> 2n-x-1. */
+void orc_median3(PIX *in, int nx, int ny)
+{
+    PIX *out = (PIX *) malloc(sizeof(PIX) * (size_t) nx * ny);
+    #pragma omp parallel for
+    for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+            PIX v[9];
+            int n = 0;
+            for (int yy = y - 1; yy <= y + 1; yy++)
+                for (int xx = x - 1; xx <= x + 1; xx++) {
+                    int x0 = xx, y0 = yy;
+                    if (x0 < 0) x0 = -x0 - 1;
+                    if (x0 >= nx) x0 = 2 * nx - x0 - 1;
+                    if (y0 < 0) y0 = -y0 - 1;
+                    if (y0 >= ny) y0 = 2 * ny - y0 - 1;
+                    v[n++] = in[y0 * nx + x0];
+                }
+            for (int a = 1; a < 9; a++) {            /* insertion sort: the median is order-independent */
+                const PIX t = v[a];
+                int b = a - 1;
+                while (b >= 0 && v[b] > t) { v[b + 1] = v[b]; b--; }
+                v[b + 1] = t;
+            }
+            out[y * nx + x] = v[4];
+        }
+    memcpy(in, out, sizeof(PIX) * (size_t) nx * ny);
+    free(out);
+}
+
+/* choosed_g with G_CHOICE 2, src/tvl1occflow.cpp:100-136: g = 1 / (1 + G_FACTOR |grad I|). */
+void orc_occ_g(const PIX *I, PIX *g, int nx, int ny)
+{
+    const int size = nx * ny;
+    PIX *Ix = (PIX *) malloc(sizeof(PIX) * size), *Iy = (PIX *) malloc(sizeof(PIX) * size);
+    orc_centered_gradient(I, Ix, Iy, nx, ny);
+    for (int i = 0; i < size; i++) {
+        /* C++ overload resolution in the reference: sqrt of an ofpix_t expression is computed in ofpix_t */
+        const double gggrad = ORC_SQRT_PIX(Ix[i] * Ix[i] + Iy[i] * Iy[i]);
+        const double aux = 1. + ORC_OCC_G_FACTOR * gggrad;
+        g[i] = 1. / aux;
+    }
+    free(Ix); free(Iy);
+}
+
+/* Solver_wrt_v, src/tvl1occflow_solvers.cpp:54-148. */
+void orc_occ_solver_v(const PIX *u1, const PIX *u2, PIX *v1, PIX *v2, const PIX *chi, const PIX *I1wx,
+                      const PIX *I1wy, const PIX *I_1wx, const PIX *I_1wy, const PIX *rho1_c,
+                      const PIX *rho3_c, PIX *Vfwd_1, PIX *Vfwd_2, PIX *Vbck_1, PIX *Vbck_2, const PIX *grad1,
+                      const PIX *grad3, double alpha, double theta, double lambda, int size)
+{
+    const double l_t = lambda * theta;
+    const double _1pat = 1. + alpha * theta;
+    const double at_d_1pat = alpha * theta / _1pat;
+    const double lt_d_1pat = 2. * lambda * theta / _1pat;
+    for (int i = 0; i < size; i++) {
+        double d1 = 0, d2 = 0;
+        const double rho1 = rho1_c[i] + (I1wx[i] * u1[i] + I1wy[i] * u2[i]);
+        if (rho1 < -l_t * grad1[i]) { d1 = l_t * I1wx[i]; d2 = l_t * I1wy[i]; }
+        else if (rho1 > l_t * grad1[i]) { d1 = -l_t * I1wx[i]; d2 = -l_t * I1wy[i]; }
+        else if (grad1[i] < ORC_OCC_IS_ZERO) { d1 = d2 = 0; }
+        else { d1 = -rho1 * I1wx[i] / grad1[i]; d2 = -rho1 * I1wy[i] / grad1[i]; }
+        Vfwd_1[i] = u1[i] + d1;
+        Vfwd_2[i] = u2[i] + d2;
+
+        const double rho3 = rho3_c[i] - (I_1wx[i] * u1[i] + I_1wy[i] * u2[i]);
+        const double A = rho3 + at_d_1pat * (I_1wx[i] * u1[i] + I_1wy[i] * u2[i]);
+        if (A < -lt_d_1pat * grad3[i]) {
+            d1 = -lt_d_1pat * I_1wx[i]; d2 = -lt_d_1pat * I_1wy[i];
+            Vbck_1[i] = (u1[i] / _1pat) + d1; Vbck_2[i] = (u2[i] / _1pat) + d2;
+        } else if (A > lt_d_1pat * grad3[i]) {
+            d1 = lt_d_1pat * I_1wx[i]; d2 = lt_d_1pat * I_1wy[i];
+            Vbck_1[i] = (u1[i] / _1pat) + d1; Vbck_2[i] = (u2[i] / _1pat) + d2;
+        } else {
+            if (grad3[i] < ORC_OCC_IS_ZERO) { d1 = d2 = 0; }
+            else { d1 = rho3 * I_1wx[i] / grad3[i]; d2 = rho3 * I_1wy[i] / grad3[i]; }
+            Vbck_1[i] = u1[i] + d1; Vbck_2[i] = u2[i] + d2;
+        }
+        if (chi[i] < ORC_OCC_THR_CHI) { v1[i] = Vfwd_1[i]; v2[i] = Vfwd_2[i]; }
+        else { v1[i] = Vbck_1[i]; v2[i] = Vbck_2[i]; }
+    }
+}
+
+/* Scalar_ROF_BoxCellCentered, src/tvl1occflow_tv_rof_box.cpp:25-645, restated on compact arrays.
+ * The reference works on a (2nx+1) x (2ny+1) staggered grid whose only live unknowns are the dual values
+ * on the SOUTH and EAST side of every cell: pS[i][j] (its initialP1) and pE[i][j] (its initialP2); a
+ * cell's NORTH side is the south side of the cell above, its WEST side the east side of the cell to the
+ * left, and sides on the image border are never updated (north / west: 0; south of the last row / east
+ * of the last column: whatever pS / pE hold there).  One sweep = alfa = |grad u| / (lambda g) per cell
+ * (:186-202), then a Gauss-Seidel pass over the cells in row-major order, each cell re-solving the
+ * 2x2 / 3x3 / 4x4 system of its own sides with relaxation omega (corner :206-247 / :304-331 / :452-481
+ * / :527-554, edge :250-301 / :334-383 / :486-524 / :484-..., interior :385-482), then
+ * u = lambda f + lambda (pS - pN + pE - pW) (:557-585).  Every expression keeps the reference's
+ * association order (double build bit-exact). */
+#define OCC_PS(i, j) ((i) < 0 ? (PIX) 0 : pS[(i) * nx + (j)])
+#define OCC_PE(i, j) ((j) < 0 ? (PIX) 0 : pE[(i) * nx + (j)])
+void orc_occ_rof_box(PIX *u, const PIX *f, PIX *pS, PIX *pE, const PIX *g, double lambda, double omega,
+                     int nx, int ny, int nIter)
+{
+    const int size = nx * ny;
+    PIX *ux = (PIX *) malloc(sizeof(PIX) * size), *uy = (PIX *) malloc(sizeof(PIX) * size);
+    PIX *al = (PIX *) malloc(sizeof(PIX) * size);
+    for (int iter = 1; iter <= nIter; iter++) {
+        orc_forward_gradient(u, ux, uy, nx, ny);
+        /* the reference's OWN hypot, src/tvl1occflow_tv_rof_box.cpp:15-20: sqrt(x*x + y*y) in double, not libm's */
+        for (int k = 0; k < size; k++) {
+            const double x = ux[k], y = uy[k];
+            al[k] = sqrt(x * x + y * y) / (lambda * g[k]);
+        }
+        for (int i = 0; i < ny; i++)
+            for (int j = 0; j < nx; j++) {
+                const int hasW = j > 0, hasN = i > 0, hasS = i < ny - 1, hasE = j < nx - 1;
+                const int c = i * nx + j;
+                /* beta of each side present (0 otherwise): -2 - alfa of the cell that owns the side.  Operand
+                 * types as in the reference: beta[], stgGrid_P and stgGrid_F are ofpix_t, the free terms double */
+                const PIX b0 = hasW ? -2 - al[c - 1] : 0, b1 = hasN ? -2 - al[c - nx] : 0;
+                const PIX b2 = hasS ? -2 - al[c] : 0, b3 = hasE ? -2 - al[c] : 0;
+                /* side values of the neighbours (staggered names of the reference in comments) */
+                double W = 0, N = 0, S = 0, E = 0;
+                const int n_edge = !hasN && hasW && hasE;       /* north side, not a corner: F comes first */
+                if (hasW) {
+                    const PIX jm3 = OCC_PE(i, j - 2), ip1_jm2 = pS[c - 1], im1_jm2 = OCC_PS(i - 1, j - 1);
+                    const PIX Fw = f[c] - f[c - 1];
+                    W = n_edge ? -Fw - jm3 + ip1_jm2 - im1_jm2 : -jm3 + ip1_jm2 - im1_jm2 - Fw;
+                }
+                if (hasN) {
+                    const PIX im3 = OCC_PS(i - 2, j), im2_jp1 = pE[c - nx], im2_jm1 = OCC_PE(i - 1, j - 1);
+                    const PIX Fn = f[c] - f[c - nx];
+                    N = -im3 + im2_jp1 - im2_jm1 - Fn;
+                }
+                if (hasS) {
+                    const PIX ip3 = pS[c + nx], ip2_jp1 = pE[c + nx], ip2_jm1 = OCC_PE(i + 1, j - 1);
+                    const PIX Fs = f[c + nx] - f[c];
+                    S = n_edge ? -Fs - ip3 - ip2_jp1 + ip2_jm1 : -ip3 - ip2_jp1 + ip2_jm1 - Fs;
+                }
+                if (hasE) {
+                    const PIX jp3 = pE[c + 1], ip1_jp2 = pS[c + 1], im1_jp2 = OCC_PS(i - 1, j + 1);
+                    const PIX Fe = f[c + 1] - f[c];
+                    E = n_edge ? -Fe - jp3 - ip1_jp2 + im1_jp2 : -jp3 - ip1_jp2 + im1_jp2 - Fe;
+                }
+                PIX *qW = hasW ? &pE[c - 1] : 0, *qN = hasN ? &pS[c - nx] : 0, *qS = &pS[c], *qE = &pE[c];
+                double den;
+#define OCC_RELAX(q, num) (*(q) = (1 - omega) * *(q) + omega * (num) / den)
+                if (hasW && hasN && hasS && hasE) {                              /* :385-482, Gauss elimination */
+                    const double a = 1 / b0;
+                    const double b = -(b0 + 1) / (b0 * b1 - 1);
+                    const double alf = 1 + a;
+                    const double gam = -a + b * alf;
+                    const double x = N + a * W;
+                    const double y = -a * W + b * x;
+                    const double cc = (1 - gam) / (b2 + gam);
+                    *qE = (1 - omega) * *qE + omega * (E + y + cc * (S + y)) / (b3 + gam + cc * (gam - 1));
+                    *qS = (1 - omega) * *qS + omega * (S + y + *qE * (1 - gam)) / (b2 + gam);
+                    *qN = (1 - omega) * *qN + omega * (x - alf * (*qE + *qS)) / (b1 - a);
+                    *qW = (1 - omega) * *qW + omega * (W + *qN - *qS - *qE) / (b0);
+                } else if (!hasN && !hasW) {                                      /* NW corner :206-247 */
+                    den = b2 * b3 - 1;
+                    OCC_RELAX(qS, S * b3 + E);
+                    OCC_RELAX(qE, E * b2 + S);
+                } else if (!hasN && !hasE) {                                      /* NE corner :304-331 */
+                    den = b0 * b2 - 1;
+                    OCC_RELAX(qW, W * b2 - S);
+                    OCC_RELAX(qS, S * b0 - W);
+                } else if (!hasN) {                                               /* north side :250-301 */
+                    den = b0 * b2 * b3 - b0 - b2 - b3 - 2;
+                    OCC_RELAX(qW, W * b2 * b3 - E * b2 - S * b3 - W - E - S);
+                    OCC_RELAX(qS, S * b0 * b3 - W * b3 + E * b0 - W + E - S);
+                    OCC_RELAX(qE, E * b0 * b2 - W * b2 + S * b0 - W - E + S);
+                } else if (!hasS && !hasW) {                                      /* SW corner */
+                    den = b3 * b1 - 1;
+                    OCC_RELAX(qN, b3 * N - E);
+                    OCC_RELAX(qE, b1 * E - N);
+                } else if (!hasS && !hasE) {                                      /* SE corner */
+                    den = b0 * b1 - 1;
+                    OCC_RELAX(qW, W * b1 + N);
+                    OCC_RELAX(qN, N * b0 + W);
+                } else if (!hasS) {                                               /* south side */
+                    den = b0 * b1 * b3 - b0 - b1 - b3 - 2;
+                    OCC_RELAX(qW, W * b1 * b3 - E + N - E * b1 - W + N * b3);
+                    OCC_RELAX(qN, N * b0 * b3 + W - E - N - E * b0 + W * b3);
+                    OCC_RELAX(qE, E * b0 * b1 - N - W - W * b1 - N * b0 - E);
+                } else if (!hasW) {                                               /* west side :334-383 */
+                    den = b1 * b2 * b3 - (b1 + b2 + b3) - 2;
+                    OCC_RELAX(qN, b2 * b3 * N - E * b2 - S * b3 - N - S - E);
+                    OCC_RELAX(qS, b1 * b3 * S + E * b1 - N * b3 - N - S + E);
+                    OCC_RELAX(qE, b1 * b2 * E - N * b2 + S * b1 - N + S - E);
+                } else {                                                          /* east side */
+                    den = (b0 * b1 * b2) + (-b0 - b1 - b2 - 2);
+                    OCC_RELAX(qW, W * b1 * b2 - S + N - S * b1 - W + N * b2);
+                    OCC_RELAX(qN, N * b0 * b2 + W - S - N - S * b0 + W * b2);
+                    OCC_RELAX(qS, S * b0 * b1 - N - W - W * b1 - N * b0 - S);
+                }
+#undef OCC_RELAX
+            }
+        for (int i = 0; i < ny; i++)
+            for (int j = 0; j < nx; j++) {
+                const int c = i * nx + j;
+                u[c] = lambda * f[c] + lambda * (pS[c] - OCC_PS(i - 1, j) + pE[c] - OCC_PE(i, j - 1));
+            }
+    }
+    free(ux); free(uy); free(al);
+}
+#undef OCC_PS
+#undef OCC_PE
+
+/* Solver_wrt_u, src/tvl1occflow_solvers.cpp:150-213 (p = the level's persistent dual variables). */
+void orc_occ_solver_u(PIX *u1, PIX *u2, const PIX *v1, const PIX *v2, const PIX *chi, const PIX *g,
+                      PIX *p11, PIX *p12, PIX *p21, PIX *p22, double theta, double beta, int nx, int ny)
+{
+    const int size = nx * ny;
+    PIX *chix = (PIX *) malloc(sizeof(PIX) * size), *chiy = (PIX *) malloc(sizeof(PIX) * size);
+    PIX *f1 = (PIX *) malloc(sizeof(PIX) * size), *f2 = (PIX *) malloc(sizeof(PIX) * size);
+    orc_forward_gradient(chi, chix, chiy, nx, ny);
+    for (int i = 0; i < size; i++) {
+        f1[i] = v1[i] / theta + beta * chix[i];
+        f2[i] = v2[i] / theta + beta * chiy[i];
+        u1[i] = v1[i] + theta * beta * chix[i];
+        u2[i] = v2[i] + theta * beta * chiy[i];
+    }
+    orc_occ_rof_box(u1, f1, p11, p12, g, theta, ORC_OCC_OMEGA, nx, ny, ORC_OCC_MAX_ITERATIONS_U);
+    orc_occ_rof_box(u2, f2, p21, p22, g, theta, ORC_OCC_OMEGA, nx, ny, ORC_OCC_MAX_ITERATIONS_U);
+    free(chix); free(chiy); free(f1); free(f2);
+}
+
+/* Solver_wrt_chi, src/tvl1occflow_solvers.cpp:215-338 (eta = the level's persistent dual variable). */
+void orc_occ_solver_chi(const PIX *u1, const PIX *u2, PIX *chi, const PIX *I1wx, const PIX *I1wy,
+                        const PIX *I_1wx, const PIX *I_1wy, const PIX *rho1_c, const PIX *rho3_c,
+                        const PIX *Vfwd_1, const PIX *Vfwd_2, const PIX *Vbck_1, const PIX *Vbck_2, const PIX *g,
+                        PIX *eta1, PIX *eta2, double lambda, double theta, double alpha, double beta,
+                        double tau_chi, double tau_eta, int nx, int ny, int niter)
+{
+    const int size = nx * ny;
+    PIX *chix = (PIX *) malloc(sizeof(PIX) * size), *chiy = (PIX *) malloc(sizeof(PIX) * size);
+    PIX *geta1 = (PIX *) malloc(sizeof(PIX) * size), *geta2 = (PIX *) malloc(sizeof(PIX) * size);
+    PIX *div_eta = (PIX *) malloc(sizeof(PIX) * size), *div_u = (PIX *) malloc(sizeof(PIX) * size);
+    for (int n_chi = 0; n_chi < niter; n_chi++) {
+        orc_forward_gradient(chi, chix, chiy, nx, ny);
+        for (int i = 0; i < size; i++) {
+            eta1[i] = eta1[i] + tau_eta * g[i] * chix[i];
+            eta2[i] = eta2[i] + tau_eta * g[i] * chiy[i];
+        }
+        for (int j = 0; j < size; j++) {                                  /* project, :33-52 */
+            const double norm2 = eta1[j] * eta1[j] + eta2[j] * eta2[j];
+            if (norm2 < ORC_OCC_IS_ZERO) { eta1[j] = 0.0; eta2[j] = 0.0; }
+            else { const double norm = sqrt(norm2); eta1[j] = eta1[j] / norm; eta2[j] = eta2[j] / norm; }
+        }
+        for (int i = 0; i < size; i++) { geta1[i] = g[i] * eta1[i]; geta2[i] = g[i] * eta2[i]; }
+        orc_divergence(geta1, geta2, div_eta, nx, ny);
+        orc_divergence(u1, u2, div_u, nx, ny);
+        for (int i = 0; i < size; i++) {
+            const double rho1 = rho1_c[i] + (I1wx[i] * Vfwd_1[i] + I1wy[i] * Vfwd_2[i]);
+            const double abs_rho1 = (rho1 < 0.) ? -rho1 : rho1;
+            const double rho3 = rho3_c[i] - (I_1wx[i] * Vbck_1[i] + I_1wy[i] * Vbck_2[i]);
+            const double abs_rho3 = (rho3 < 0.) ? -rho3 : rho3;
+            double F, G;
+            if (chi[i] < 0.5) {
+                F = -lambda * abs_rho1;
+                G = -(0.5 / theta) * ((Vfwd_1[i] - u1[i]) * (Vfwd_1[i] - u1[i]) + (Vfwd_2[i] - u2[i]) * (Vfwd_2[i] - u2[i]));
+            } else {
+                F = lambda * abs_rho3;
+                G = (0.5 / theta) * ((Vbck_1[i] - u1[i]) * (Vbck_1[i] - u1[i]) + (Vbck_2[i] - u2[i]) * (Vbck_2[i] - u2[i]))
+                    + alpha * theta * (Vbck_1[i] * Vbck_1[i] + Vbck_2[i] * Vbck_2[i]);
+            }
+            chi[i] = chi[i] + tau_chi * (div_eta[i] - F - G - beta * div_u[i]);
+            if (chi[i] > 1.) chi[i] = 1.;
+            else if (chi[i] < 0.) chi[i] = 0.;
+        }
+    }
+    free(chix); free(chiy); free(geta1); free(geta2); free(div_eta); free(div_u);
+}
+
+/* Dual_TVL1_optic_flow of src/tvl1occflow.cpp:144-330: one level.  iters/errs: [warps]. */
+void orc_occ_single_scale(const PIX *I_1, const PIX *I0, const PIX *I1, const PIX *filtI0, PIX *u1, PIX *u2,
+                          PIX *chi, int nx, int ny, double lambda, double alpha, double beta, double theta,
+                          int warps, double epsilon, int *iters, double *errs)
+{
+    const int size = nx * ny;
+    PIX *buf = (PIX *) calloc((size_t) 30 * size, sizeof(PIX));
+    PIX *I1x = buf, *I1y = buf + size, *I1w = buf + 2 * size, *I1wx = buf + 3 * size, *I1wy = buf + 4 * size;
+    PIX *I_1x = buf + 5 * size, *I_1y = buf + 6 * size, *I_1w = buf + 7 * size, *I_1wx = buf + 8 * size;
+    PIX *I_1wy = buf + 9 * size, *rho1_c = buf + 10 * size, *rho3_c = buf + 11 * size, *v1 = buf + 12 * size;
+    PIX *v2 = buf + 13 * size, *v11 = buf + 14 * size, *v12 = buf + 15 * size, *v31 = buf + 16 * size;
+    PIX *v32 = buf + 17 * size, *gp1 = buf + 18 * size, *gp2 = buf + 19 * size, *grad1 = buf + 20 * size;
+    PIX *grad3 = buf + 21 * size, *g = buf + 22 * size, *u1prev = buf + 23 * size, *u2prev = buf + 24 * size;
+    PIX *p11 = buf + 25 * size, *p12 = buf + 26 * size, *p21 = buf + 27 * size, *p22 = buf + 28 * size;
+    PIX *eta = (PIX *) calloc((size_t) 2 * size, sizeof(PIX));          /* zero at every level, see the header */
+
+    orc_occ_g(filtI0, g, nx, ny);                                        /* :205 */
+    orc_centered_gradient(I1, I1x, I1y, nx, ny);                         /* :207-208 */
+    orc_centered_gradient(I_1, I_1x, I_1y, nx, ny);
+    for (int i = 0; i < size; i++) { u1prev[i] = u1[i]; u2prev[i] = u2[i]; }   /* :211-224 (the rest is zero) */
+
+    for (int w = 0; w < warps; w++) {
+        orc_warp(I1, u1, u2, I1w, nx, ny, 0);                            /* :232-234; border_out defaults to false here */
+        orc_warp(I1x, u1, u2, I1wx, nx, ny, 0);
+        orc_warp(I1y, u1, u2, I1wy, nx, ny, 0);
+        for (int i = 0; i < size; i++) { gp1[i] = -u1[i]; gp2[i] = -u2[i]; }    /* :237-241 */
+        orc_warp(I_1, gp1, gp2, I_1w, nx, ny, 0);                        /* :243-245 */
+        orc_warp(I_1x, gp1, gp2, I_1wx, nx, ny, 0);
+        orc_warp(I_1y, gp1, gp2, I_1wy, nx, ny, 0);
+        for (int i = 0; i < size; i++) {                                 /* :250-270 */
+            double Ix2 = I1wx[i] * I1wx[i], Iy2 = I1wy[i] * I1wy[i];
+            grad1[i] = (Ix2 + Iy2);
+            Ix2 = I_1wx[i] * I_1wx[i]; Iy2 = I_1wy[i] * I_1wy[i];
+            grad3[i] = (Ix2 + Iy2);
+            rho1_c[i] = (I1w[i] - I1wx[i] * u1[i] - I1wy[i] * u2[i] - I0[i]);
+            rho3_c[i] = (I_1w[i] + I_1wx[i] * u1[i] + I_1wy[i] * u2[i] - I0[i]);
+        }
+        int n = 0;
+        double error = INFINITY;
+        while (error > epsilon && n < ORC_OCC_EXT_MAX_ITERATIONS) {      /* :277: epsilon, not epsilon^2 */
+            n++;
+            orc_occ_solver_v(u1, u2, v1, v2, chi, I1wx, I1wy, I_1wx, I_1wy, rho1_c, rho3_c, v11, v12, v31, v32,
+                             grad1, grad3, alpha, theta, lambda, size);
+            orc_occ_solver_u(u1, u2, v1, v2, chi, g, p11, p12, p21, p22, theta, beta, nx, ny);
+            orc_median3(u1, nx, ny);                                     /* :292-293 */
+            orc_median3(u2, nx, ny);
+            orc_occ_solver_chi(u1, u2, chi, I1wx, I1wy, I_1wx, I_1wy, rho1_c, rho3_c, v11, v12, v31, v32, g,
+                               eta, eta + size, lambda, theta, alpha, beta, ORC_OCC_TAU_CHI, ORC_OCC_TAU_ETA,
+                               nx, ny, ORC_OCC_MAX_ITERATIONS_CHI);
+            error = 0.0;                                                 /* L2error, :70-88 */
+            for (int i = 0; i < size; i++) {
+                error += (u1[i] - u1prev[i]) * (u1[i] - u1prev[i]) + (u2[i] - u2prev[i]) * (u2[i] - u2prev[i]);
+                u1prev[i] = u1[i];
+                u2prev[i] = u2[i];
+            }
+            error /= size;
+        }
+        if (iters) iters[w] = n;
+        if (errs) errs[w] = error;
+    }
+    free(buf); free(eta);
+}
+
+/* Dual_TVL1_optic_flow_multiscale of src/tvl1occflow.cpp:335-482.  The result of image_normalization_4
+ * (:379-380) is overwritten by the raw images two lines later (:383-388): the pyramid is built from the
+ * UN-normalised inputs, so it is here.  chi is thresholded at THR_CHI at the end (:459).
+ * iters/errs: [nscales][warps], coarsest level first. */
+int orc_occ_multiscale(const PIX *I_1, const PIX *I0, const PIX *I1, const PIX *filtI0, PIX *u1, PIX *u2,
+                       PIX *chi, int nxx, int nyy, double lambda, double alpha, double beta, double theta,
+                       int nscales, double zfactor, int warps, double epsilon, int *iters, double *errs)
+{
+    const int size = nxx * nyy;
+    PIX **im[4], **us[3];
+    int *nx = (int *) calloc(nscales, sizeof(int)), *ny = (int *) calloc(nscales, sizeof(int));
+    int rc = 0;
+    const PIX *src[4] = { I_1, I0, I1, filtI0 };
+    for (int k = 0; k < 4; k++) im[k] = (PIX **) calloc(nscales, sizeof(PIX *));
+    for (int k = 0; k < 3; k++) us[k] = (PIX **) calloc(nscales, sizeof(PIX *));
+    us[0][0] = u1; us[1][0] = u2; us[2][0] = chi;
+    nx[0] = nxx; ny[0] = nyy;
+    for (int k = 0; k < 4; k++) {
+        im[k][0] = (PIX *) malloc(sizeof(PIX) * size);
+        memcpy(im[k][0], src[k], sizeof(PIX) * size);
+    }
+    for (int i = 0; i < size; i++) u1[i] = u2[i] = chi[i] = 0.0;
+    for (int k = 0; k < 4 && !rc; k++) rc |= orc_gaussian(im[k][0], nxx, nyy, ORC_OCC_PRESMOOTHING_SIGMA);
+    int built = 1;
+    for (int s = 1; s < nscales && !rc; s++) {
+        orc_zoom_size(nx[s - 1], ny[s - 1], &nx[s], &ny[s], zfactor);
+        const size_t sizes = (size_t) nx[s] * ny[s];
+        for (int k = 0; k < 4; k++) im[k][s] = (PIX *) malloc(sizeof(PIX) * sizes);
+        for (int k = 0; k < 3; k++) us[k][s] = (PIX *) calloc(sizes, sizeof(PIX));
+        built = s + 1;
+        for (int k = 0; k < 4 && !rc; k++) rc |= orc_zoom_out(im[k][s - 1], im[k][s], nx[s - 1], ny[s - 1], zfactor);
+    }
+    for (int s = nscales - 1; s >= 0 && !rc; s--) {
+        const int k = nscales - 1 - s;
+        orc_occ_single_scale(im[0][s], im[1][s], im[2][s], im[3][s], us[0][s], us[1][s], us[2][s], nx[s], ny[s],
+                             lambda, alpha, beta, theta, warps, epsilon, iters ? iters + k * warps : 0,
+                             errs ? errs + k * warps : 0);
+        if (s) {
+            for (int c = 0; c < 3; c++) orc_zoom_in(us[c][s], us[c][s - 1], nx[s], ny[s], nx[s - 1], ny[s - 1]);
+            for (int i = 0; i < nx[s - 1] * ny[s - 1]; i++) {
+                us[0][s - 1][i] *= (double) 1.0 / zfactor;
+                us[1][s - 1][i] *= (double) 1.0 / zfactor;
+            }
+        } else {
+            for (int i = 0; i < size; i++) chi[i] = (chi[i] > ORC_OCC_THR_CHI);
+        }
+    }
+    for (int s = 0; s < built; s++) {
+        for (int k = 0; k < 4; k++) free(im[k][s]);
+        if (s) for (int k = 0; k < 3; k++) free(us[k][s]);
+    }
+    for (int k = 0; k < 4; k++) free(im[k]);
+    for (int k = 0; k < 3; k++) free(us[k]);
+    free(nx); free(ny);
     return rc;
 }

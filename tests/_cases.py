@@ -100,3 +100,25 @@ def hs_sor_inputs(nx=37, ny=29, seed=21):
     iy[out] = 0.0
     return dict(I1=rs.uniform(0, 255, shape), I2w=np.where(out, 0.0, rs.uniform(0, 255, shape)),
                 I2wx=ix, I2wy=iy, u=rs.uniform(-3, 3, shape), v=rs.uniform(-3, 3, shape))
+
+
+# ---- TV-L1 with occlusions: src/tvl1occflow.cpp -----------------------------------------
+OCC_CASES = {
+    # CLI defaults of src/tvl1occflow_constants.h:14-23 (nscales clamped by image size as the CLI does)
+    "occ_64x48": dict(nx=64, ny=48, seed=1234, scale=0.5,
+                      kw=dict(lam=0.15, alpha=0.01, beta=0.15, theta=0.3, nscales=2, zfactor=0.5, warps=2, eps=0.01)),
+    "occ_96x80_tight": dict(nx=96, ny=80, seed=7, scale=0.5,
+                            kw=dict(lam=0.15, alpha=0.01, beta=0.15, theta=0.3, nscales=3, zfactor=0.5, warps=3, eps=0.002)),
+    "occ_61x47_z07": dict(nx=61, ny=47, seed=99, scale=0.4,
+                          kw=dict(lam=0.2, alpha=0.02, beta=0.1, theta=0.25, nscales=2, zfactor=0.7, warps=2, eps=0.005)),
+}
+
+
+def occ_inputs(case):
+    I_1, I0, I1 = synth.make_triple(case["nx"], case["ny"], seed=case["seed"], scale=case["scale"])
+    return I_1, I0, I1
+
+
+def run_occ_case(cpu, case):
+    I_1, I0, I1 = occ_inputs(case)
+    return cpu.multiscale(I_1, I0, I1, None, **case["kw"])

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from oracle.loader import CpuTvl1, build  # noqa: E402
+from oracle.loader import CpuOcc, CpuTvl1, build  # noqa: E402
 import _cases  # noqa: E402
 
 
@@ -52,6 +52,23 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "hs_reference_vectors.npz")
     np.savez_compressed(path, **hs)
     print("wrote", path, os.path.getsize(path), "bytes,", len(hs), "arrays")
+
+    # TV-L1 with occlusions (src/tvl1occflow.cpp), reference built with the zero-filling new[] of
+    # oracle/occ_ref_shim.cpp (the one defined reading of its uninitialised eta1/eta2)
+    occ = {}
+    for dt in (np.float64, np.float32):
+        R = CpuOcc("reference", dt)
+        R.set_threads(1)
+        tag = "f64" if dt == np.float64 else "f32"
+        for name, case in _cases.OCC_CASES.items():
+            u1, u2, chi, iters, errs = _cases.run_occ_case(R, case)
+            occ["%s/%s/u1" % (tag, name)] = u1
+            occ["%s/%s/u2" % (tag, name)] = u2
+            occ["%s/%s/chi" % (tag, name)] = chi.astype(np.uint8)
+            occ["%s/%s/iters" % (tag, name)] = iters
+    path = os.path.join(ROOT, "tests", "golden", "occ_reference_vectors.npz")
+    np.savez_compressed(path, **occ)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(occ), "arrays")
 
 
 if __name__ == "__main__":
