@@ -1,0 +1,624 @@
+// CUDA kernels of the TV-L1 + occlusions solver (include/occ_b200.h).
+//
+// IEEE fp64 throughout, reference association order, no fused multiply-adds: this header is only
+// included by occ_solver.cu, which is compiled with -fmad=false (the reference is built for baseline
+// x86-64, which has no FMA; fp64 division and square root are correctly rounded on both sides).  Every
+// kernel below restates one loop nest of the reference (cited at the kernel) as one thread per pixel;
+// the only loop whose ORDER matters, the Gauss-Seidel pass of the box relaxation, keeps its data
+// dependences on a wavefront (k_occ_rof_gs).
+//
+// Batch layout: a "plane" is a dense [ny][nx] array of double; a batch of B triples keeps plane b of a
+// field at field + b * N (N = nx * ny); fields that come in groups ([k][B][N]) say so.  ctl[b].active
+// gates every kernel of the outer loop: a triple that met its stopping rule costs nothing afterwards.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace occ {
+
+struct TripleCtl {
+    int active;        // still inside the while of src/tvl1occflow.cpp:277
+    int n;             // outer iterations of the current warp step
+    double error;      // last L2error
+};
+
+struct GaussTaps {
+    int size;          // taps = radius + 1
+    double B[40];
+};
+
+constexpr int kErrThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------
+// pyramid: gaussian (src/operators.cpp:506-624), zoom_out / zoom_in (src/zoom.cpp:41-78, :132-155)
+// ---------------------------------------------------------------------------------------------------
+
+// reflecting pad of src/operators.cpp:557-562: x = -k -> I[k]; x = n-1+k -> I[n-k]
+__device__ __forceinline__ int gauss_reflect(int x, int n)
+{
+    if (x < 0) x = -x;
+    else if (x >= n) x = 2 * n - 1 - x;
+    return x < 0 ? 0 : (x >= n ? n - 1 : x);     // only for lines shorter than the window (undefined upstream)
+}
+
+// One pass along x (DIR 0) or y (DIR 1); sum order of :573-576.
+template <int DIR>
+__global__ void __launch_bounds__(256) k_occ_gauss_pass(const double *__restrict__ in, double *__restrict__ out,
+                                                    int nx, int ny, GaussTaps t)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t N = (size_t) nx * ny;
+    const double *src = in + blockIdx.z * N;
+    const int n = DIR ? ny : nx, c = DIR ? i : j;
+    auto at = [&](int x) { x = gauss_reflect(x, n); return DIR ? src[(size_t) x * nx + j] : src[(size_t) i * nx + x]; };
+    double sum = t.B[0] * at(c);
+    for (int k = 1; k < t.size; k++) sum += t.B[k] * (at(c - k) + at(c + k));
+    out[blockIdx.z * N + (size_t) i * nx + j] = sum;
+}
+
+// src/bicubic_interpolation.cpp:108-123
+__device__ __forceinline__ double cubic(double v0, double v1, double v2, double v3, double x)
+{
+    return v1 + 0.5 * x * (v2 - v0 + x * (2.0 * v0 - 5.0 * v1 + 4.0 * v2 - v3 + x * (3.0 * (v1 - v2) + v3 - v0)));
+}
+
+// Index part of src/bicubic_interpolation.cpp:153-245 (BOUNDARY_CONDITION 0 = neumann, :24-39), shared by
+// every plane sampled at the same position.  The "minus" row uses sx (:173, upstream quirk, kept).
+struct BicubicPos {
+    int xs[4], ys[4];
+    double fx, fy;
+    bool out;
+};
+
+__device__ __forceinline__ int neumann(int x, int n, bool &out)
+{
+    if (x < 0) { x = 0; out = true; }
+    else if (x >= n) { x = n - 1; out = true; }
+    return x;
+}
+
+__device__ __forceinline__ BicubicPos bicubic_pos(double uu, double vv, int nx, int ny)
+{
+    BicubicPos p;
+    const int sx = (uu < 0) ? -1 : 1, sy = (vv < 0) ? -1 : 1;
+    p.out = false;
+    const int x = neumann((int) uu, nx, p.out), y = neumann((int) vv, ny, p.out);
+    p.xs[0] = neumann((int) uu - sx, nx, p.out);
+    p.ys[0] = neumann((int) vv - sx, ny, p.out);
+    p.xs[1] = x;
+    p.ys[1] = y;
+    p.xs[2] = neumann((int) uu + sx, nx, p.out);
+    p.ys[2] = neumann((int) vv + sy, ny, p.out);
+    p.xs[3] = neumann((int) uu + 2 * sx, nx, p.out);
+    p.ys[3] = neumann((int) vv + 2 * sy, ny, p.out);
+    p.fx = uu - x;
+    p.fy = vv - y;
+    return p;
+}
+
+// along y inside each of the four x-columns first, then along x (:137-144, :236-240); border_out = false
+__device__ __forceinline__ double bicubic_eval(const double *__restrict__ in, const BicubicPos &p, int nx)
+{
+    double col[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+        col[a] = cubic(in[p.xs[a] + (size_t) nx * p.ys[0]], in[p.xs[a] + (size_t) nx * p.ys[1]],
+                       in[p.xs[a] + (size_t) nx * p.ys[2]], in[p.xs[a] + (size_t) nx * p.ys[3]], p.fy);
+    return cubic(col[0], col[1], col[2], col[3], p.fx);
+}
+
+// zoom_out's sampling loop (src/zoom.cpp:67-75) on the blurred copy, and zoom_in (:143-153) with the
+// "*= 1 / zfactor" of src/tvl1occflow.cpp:447-451 applied to the stored value (mul = 0: none).
+__global__ void __launch_bounds__(256) k_occ_resample(const double *__restrict__ in, double *__restrict__ out, int nx,
+                                                  int ny, int nxx, int nyy, double fx, double fy, double mul)
+{
+    const int j1 = blockIdx.x * 32 + threadIdx.x, i1 = blockIdx.y * 8 + threadIdx.y;
+    if (j1 >= nxx || i1 >= nyy) return;
+    const double i2 = i1 / fy, j2 = j1 / fx;
+    const BicubicPos p = bicubic_pos(j2, i2, nx, ny);
+    double v = bicubic_eval(in + blockIdx.z * (size_t) nx * ny, p, nx);
+    if (mul != 0.0) v = v * mul;
+    out[blockIdx.z * (size_t) nxx * nyy + (size_t) i1 * nxx + j1] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per level: g, image gradients; per warp step: the six warps and the constants of the outer loop
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
+
+// centered_gradient (src/operators.cpp:335-406) of I1 and I_1, and choosed_g with G_CHOICE 2
+// (src/tvl1occflow.cpp:100-136): g = 1 / (1 + G_FACTOR |grad filtI0|).
+__global__ void __launch_bounds__(256) k_occ_level_setup(const double *__restrict__ I1, const double *__restrict__ Im1,
+                                                     const double *__restrict__ filt, double *__restrict__ I1x,
+                                                     double *__restrict__ I1y, double *__restrict__ Im1x,
+                                                     double *__restrict__ Im1y, double *__restrict__ g, int nx, int ny,
+                                                     double g_factor)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t o = blockIdx.z * (size_t) nx * ny;
+    const int k = i * nx + j;
+    const int l = i * nx + clampi(j - 1, nx), r = i * nx + clampi(j + 1, nx);
+    const int u = clampi(i - 1, ny) * nx + j, d = clampi(i + 1, ny) * nx + j;
+    I1x[o + k] = 0.5 * (I1[o + r] - I1[o + l]);
+    I1y[o + k] = 0.5 * (I1[o + d] - I1[o + u]);
+    Im1x[o + k] = 0.5 * (Im1[o + r] - Im1[o + l]);
+    Im1y[o + k] = 0.5 * (Im1[o + d] - Im1[o + u]);
+    const double gx = 0.5 * (filt[o + r] - filt[o + l]), gy = 0.5 * (filt[o + d] - filt[o + u]);
+    const double gggrad = sqrt(gx * gx + gy * gy);
+    const double aux = 1. + g_factor * gggrad;
+    g[o + k] = 1. / aux;
+}
+
+// src/tvl1occflow.cpp:232-270: I1, I1x, I1y sampled at x + u, I_1, I_1x, I_1y at x - u (border_out = false),
+// grad1 / grad3, rho1_c / rho3_c.  I1w and I_1w are consumed here.
+__global__ void __launch_bounds__(256) k_occ_warp(const double *__restrict__ I0, const double *__restrict__ I1,
+                                              const double *__restrict__ I1x, const double *__restrict__ I1y,
+                                              const double *__restrict__ Im1, const double *__restrict__ Im1x,
+                                              const double *__restrict__ Im1y, const double *__restrict__ u1,
+                                              const double *__restrict__ u2, double *__restrict__ I1wx,
+                                              double *__restrict__ I1wy, double *__restrict__ Im1wx,
+                                              double *__restrict__ Im1wy, double *__restrict__ rho1_c,
+                                              double *__restrict__ rho3_c, double *__restrict__ grad1,
+                                              double *__restrict__ grad3, int nx, int ny)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t o = blockIdx.z * (size_t) nx * ny;
+    const size_t p = o + (size_t) i * nx + j;
+    const double a = u1[p], b = u2[p];
+    const BicubicPos f = bicubic_pos(j + a, i + b, nx, ny);
+    const double w = bicubic_eval(I1 + o, f, nx), wx = bicubic_eval(I1x + o, f, nx), wy = bicubic_eval(I1y + o, f, nx);
+    const BicubicPos q = bicubic_pos(j + (-a), i + (-b), nx, ny);
+    const double m = bicubic_eval(Im1 + o, q, nx), mx = bicubic_eval(Im1x + o, q, nx), my = bicubic_eval(Im1y + o, q, nx);
+    I1wx[p] = wx;
+    I1wy[p] = wy;
+    Im1wx[p] = mx;
+    Im1wy[p] = my;
+    double Ix2 = wx * wx, Iy2 = wy * wy;
+    grad1[p] = Ix2 + Iy2;
+    Ix2 = mx * mx;
+    Iy2 = my * my;
+    grad3[p] = Ix2 + Iy2;
+    rho1_c[p] = w - wx * a - wy * b - I0[p];
+    rho3_c[p] = m + mx * a + my * b - I0[p];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// outer loop, step 1: Solver_wrt_v (src/tvl1occflow_solvers.cpp:54-148), and the prologue of
+// Solver_wrt_u (:188-203): f = v / theta + beta grad(chi), u = v + theta beta grad(chi).
+// U and F are [2][B][N] (component, triple).
+// ---------------------------------------------------------------------------------------------------
+struct VParams {
+    double l_t, one_pat, at_d_1pat, lt_d_1pat, theta, beta, is_zero, thr_chi;
+};
+
+__global__ void __launch_bounds__(256) k_occ_solver_v(const TripleCtl *__restrict__ ctl, double *__restrict__ U,
+                                                  double *__restrict__ F, const double *__restrict__ chi,
+                                                  const double *__restrict__ I1wx, const double *__restrict__ I1wy,
+                                                  const double *__restrict__ Im1wx, const double *__restrict__ Im1wy,
+                                                  const double *__restrict__ rho1_c, const double *__restrict__ rho3_c,
+                                                  const double *__restrict__ grad1, const double *__restrict__ grad3,
+                                                  double *__restrict__ Vfwd, double *__restrict__ Vbck, int nx, int ny,
+                                                  int B, VParams P)
+{
+    const int b = blockIdx.z;
+    if (!ctl[b].active) return;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t N = (size_t) nx * ny, BN = (size_t) B * N;
+    const size_t p = b * N + (size_t) i * nx + j;
+    const double a = U[p], c = U[BN + p];
+    const double wx = I1wx[p], wy = I1wy[p], mx = Im1wx[p], my = Im1wy[p], g1 = grad1[p], g3 = grad3[p];
+    double d1, d2;
+    const double rho1 = rho1_c[p] + (wx * a + wy * c);
+    if (rho1 < -P.l_t * g1) { d1 = P.l_t * wx; d2 = P.l_t * wy; }
+    else if (rho1 > P.l_t * g1) { d1 = -P.l_t * wx; d2 = -P.l_t * wy; }
+    else if (g1 < P.is_zero) { d1 = d2 = 0; }
+    else { d1 = -rho1 * wx / g1; d2 = -rho1 * wy / g1; }
+    const double vf1 = a + d1, vf2 = c + d2;
+    Vfwd[p] = vf1;
+    Vfwd[BN + p] = vf2;
+
+    double vb1, vb2;
+    const double rho3 = rho3_c[p] - (mx * a + my * c);
+    const double A = rho3 + P.at_d_1pat * (mx * a + my * c);
+    if (A < -P.lt_d_1pat * g3) {
+        d1 = -P.lt_d_1pat * mx; d2 = -P.lt_d_1pat * my;
+        vb1 = (a / P.one_pat) + d1; vb2 = (c / P.one_pat) + d2;
+    } else if (A > P.lt_d_1pat * g3) {
+        d1 = P.lt_d_1pat * mx; d2 = P.lt_d_1pat * my;
+        vb1 = (a / P.one_pat) + d1; vb2 = (c / P.one_pat) + d2;
+    } else {
+        if (g3 < P.is_zero) { d1 = d2 = 0; }
+        else { d1 = rho3 * mx / g3; d2 = rho3 * my / g3; }
+        vb1 = a + d1; vb2 = c + d2;
+    }
+    Vbck[p] = vb1;
+    Vbck[BN + p] = vb2;
+    const double x = chi[p];
+    const double v1 = (x < P.thr_chi) ? vf1 : vb1, v2 = (x < P.thr_chi) ? vf2 : vb2;
+    // forward_gradient of chi (src/operators.cpp:86-125)
+    const double chix = (j < nx - 1) ? chi[p + 1] - x : 0, chiy = (i < ny - 1) ? chi[p + nx] - x : 0;
+    F[p] = v1 / P.theta + P.beta * chix;
+    F[BN + p] = v2 / P.theta + P.beta * chiy;
+    U[p] = v1 + P.theta * P.beta * chix;
+    U[BN + p] = v2 + P.theta * P.beta * chiy;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// outer loop, step 2: Scalar_ROF_BoxCellCentered (src/tvl1occflow_tv_rof_box.cpp:25-645) on the 2B
+// planes (component k of triple b = problem q = k * B + b): U, F, AL are [2][B][N]; P is [4][B][N] =
+// p11, p12, p21, p22, the dual values on the SOUTH (2k) and EAST (2k + 1) side of every cell.
+// ---------------------------------------------------------------------------------------------------
+
+// alfa = |grad u| / (lambda g), :186-202, with the reference's own hypot (:15-20).  g is [B][N].
+__global__ void __launch_bounds__(256) k_occ_rof_alfa(const TripleCtl *__restrict__ ctl, const double *__restrict__ U,
+                                                  const double *__restrict__ g, double *__restrict__ AL, int nx,
+                                                  int ny, int B, double lambda)
+{
+    const int q = blockIdx.z, b = q % B;
+    if (ctl && !ctl[b].active) return;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t N = (size_t) nx * ny;
+    const size_t c = (size_t) i * nx + j;
+    const double *u = U + q * N;
+    const double x = (j < nx - 1) ? u[c + 1] - u[c] : 0, y = (i < ny - 1) ? u[c + nx] - u[c] : 0;
+    AL[q * N + c] = sqrt(x * x + y * y) / (lambda * g[b * N + c]);
+}
+
+// One cell of the Gauss-Seidel pass: re-solves the 2x2 / 3x3 / 4x4 system of the cell's own sides with
+// relaxation omega (corner :206-247 / :304-331 / ..., edge :250-301 / :334-383 / ..., interior :385-482).
+// pS / pE are read and written through ordinary (coherent) accesses: other threads of the CTA wrote the
+// values this cell needs at earlier wavefront steps.
+__device__ __forceinline__ void rof_cell(int i, int j, int nx, int ny, double *pS, double *pE,
+                                         const double *__restrict__ f, const double *__restrict__ al, double omega)
+{
+    const bool hasW = j > 0, hasN = i > 0, hasS = i < ny - 1, hasE = j < nx - 1;
+    const int c = i * nx + j;
+#define PS_(ii, jj) ((ii) < 0 ? 0.0 : pS[(ii) * nx + (jj)])
+#define PE_(ii, jj) ((jj) < 0 ? 0.0 : pE[(ii) * nx + (jj)])
+    const double b0 = hasW ? -2 - al[c - 1] : 0, b1 = hasN ? -2 - al[c - nx] : 0;
+    const double b2 = hasS ? -2 - al[c] : 0, b3 = hasE ? -2 - al[c] : 0;
+    double W = 0, N = 0, S = 0, E = 0;
+    const bool n_edge = !hasN && hasW && hasE;
+    const double fc = f[c];
+    if (hasW) {
+        const double jm3 = PE_(i, j - 2), ip1_jm2 = pS[c - 1], im1_jm2 = PS_(i - 1, j - 1);
+        const double Fw = fc - f[c - 1];
+        W = n_edge ? -Fw - jm3 + ip1_jm2 - im1_jm2 : -jm3 + ip1_jm2 - im1_jm2 - Fw;
+    }
+    if (hasN) {
+        const double im3 = PS_(i - 2, j), im2_jp1 = pE[c - nx], im2_jm1 = PE_(i - 1, j - 1);
+        const double Fn = fc - f[c - nx];
+        N = -im3 + im2_jp1 - im2_jm1 - Fn;
+    }
+    if (hasS) {
+        const double ip3 = pS[c + nx], ip2_jp1 = pE[c + nx], ip2_jm1 = PE_(i + 1, j - 1);
+        const double Fs = f[c + nx] - fc;
+        S = n_edge ? -Fs - ip3 - ip2_jp1 + ip2_jm1 : -ip3 - ip2_jp1 + ip2_jm1 - Fs;
+    }
+    if (hasE) {
+        const double jp3 = pE[c + 1], ip1_jp2 = pS[c + 1], im1_jp2 = PS_(i - 1, j + 1);
+        const double Fe = f[c + 1] - fc;
+        E = n_edge ? -Fe - jp3 - ip1_jp2 + im1_jp2 : -jp3 - ip1_jp2 + im1_jp2 - Fe;
+    }
+#undef PS_
+#undef PE_
+    double *qW = pE + c - 1, *qN = pS + c - nx, *qS = pS + c, *qE = pE + c;
+    double den;
+#define RELAX_(q, num) (*(q) = (1 - omega) * *(q) + omega * (num) / den)
+    if (hasW && hasN && hasS && hasE) {
+        const double a = 1 / b0;
+        const double b = -(b0 + 1) / (b0 * b1 - 1);
+        const double alf = 1 + a;
+        const double gam = -a + b * alf;
+        const double x = N + a * W;
+        const double y = -a * W + b * x;
+        const double cc = (1 - gam) / (b2 + gam);
+        const double e = (1 - omega) * *qE + omega * (E + y + cc * (S + y)) / (b3 + gam + cc * (gam - 1));
+        *qE = e;
+        const double s = (1 - omega) * *qS + omega * (S + y + e * (1 - gam)) / (b2 + gam);
+        *qS = s;
+        const double n = (1 - omega) * *qN + omega * (x - alf * (e + s)) / (b1 - a);
+        *qN = n;
+        *qW = (1 - omega) * *qW + omega * (W + n - s - e) / (b0);
+    } else if (!hasN && !hasW) {
+        den = b2 * b3 - 1;
+        RELAX_(qS, S * b3 + E);
+        RELAX_(qE, E * b2 + S);
+    } else if (!hasN && !hasE) {
+        den = b0 * b2 - 1;
+        RELAX_(qW, W * b2 - S);
+        RELAX_(qS, S * b0 - W);
+    } else if (!hasN) {
+        den = b0 * b2 * b3 - b0 - b2 - b3 - 2;
+        RELAX_(qW, W * b2 * b3 - E * b2 - S * b3 - W - E - S);
+        RELAX_(qS, S * b0 * b3 - W * b3 + E * b0 - W + E - S);
+        RELAX_(qE, E * b0 * b2 - W * b2 + S * b0 - W - E + S);
+    } else if (!hasS && !hasW) {
+        den = b3 * b1 - 1;
+        RELAX_(qN, b3 * N - E);
+        RELAX_(qE, b1 * E - N);
+    } else if (!hasS && !hasE) {
+        den = b0 * b1 - 1;
+        RELAX_(qW, W * b1 + N);
+        RELAX_(qN, N * b0 + W);
+    } else if (!hasS) {
+        den = b0 * b1 * b3 - b0 - b1 - b3 - 2;
+        RELAX_(qW, W * b1 * b3 - E + N - E * b1 - W + N * b3);
+        RELAX_(qN, N * b0 * b3 + W - E - N - E * b0 + W * b3);
+        RELAX_(qE, E * b0 * b1 - N - W - W * b1 - N * b0 - E);
+    } else if (!hasW) {
+        den = b1 * b2 * b3 - (b1 + b2 + b3) - 2;
+        RELAX_(qN, b2 * b3 * N - E * b2 - S * b3 - N - S - E);
+        RELAX_(qS, b1 * b3 * S + E * b1 - N * b3 - N - S + E);
+        RELAX_(qE, b1 * b2 * E - N * b2 + S * b1 - N + S - E);
+    } else {
+        den = (b0 * b1 * b2) + (-b0 - b1 - b2 - 2);
+        RELAX_(qW, W * b1 * b2 - S + N - S * b1 - W + N * b2);
+        RELAX_(qN, N * b0 * b2 + W - S - N - S * b0 + W * b2);
+        RELAX_(qS, S * b0 * b1 - N - W - W * b1 - N * b0 - S);
+    }
+#undef RELAX_
+}
+
+// The Gauss-Seidel pass of one sweep, one CTA per plane.  The reference visits the cells in row-major
+// order; cell (i, j) reads sides written by (i, j-1) and (i-1, j+1) (and cells before them) and must see
+// the OLD sides of (i, j+1), (i+1, j-1) and later cells.  Step t = 2i + j keeps exactly that: both
+// predecessors run at t - 1, both successors at t + 1, and the cells of one step -- (i, j) and
+// (i-1, j+2), ... -- touch disjoint sides.  Thread r owns rows r, r + blockDim.x, ...; one barrier per step.
+__global__ void __launch_bounds__(1024) k_occ_rof_gs(const TripleCtl *__restrict__ ctl, double *P,
+                                                 const double *__restrict__ F, const double *__restrict__ AL, int nx,
+                                                 int ny, int B, double omega)
+{
+    const int q = blockIdx.x, k = q / B, b = q % B;
+    if (ctl && !ctl[b].active) return;
+    const size_t N = (size_t) nx * ny;
+    double *pS = P + ((size_t) (2 * k) * B + b) * N, *pE = P + ((size_t) (2 * k + 1) * B + b) * N;
+    const double *f = F + q * N, *al = AL + q * N;
+    const int steps = 2 * (ny - 1) + nx;
+    for (int t = 0; t < steps; t++) {
+        for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+            const int j = t - 2 * i;
+            if (j < 0) break;
+            if (j < nx) rof_cell(i, j, nx, ny, pS, pE, f, al, omega);
+        }
+        __syncthreads();
+    }
+}
+
+// u = lambda f + lambda (pS - pN + pE - pW), :557-585
+__global__ void __launch_bounds__(256) k_occ_rof_u(const TripleCtl *__restrict__ ctl, double *__restrict__ U,
+                                               const double *__restrict__ F, const double *__restrict__ P, int nx,
+                                               int ny, int B, double lambda)
+{
+    const int q = blockIdx.z, k = q / B, b = q % B;
+    if (ctl && !ctl[b].active) return;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t N = (size_t) nx * ny;
+    const size_t c = (size_t) i * nx + j;
+    const double *pS = P + ((size_t) (2 * k) * B + b) * N, *pE = P + ((size_t) (2 * k + 1) * B + b) * N;
+    const double pn = i > 0 ? pS[c - nx] : 0.0, pw = j > 0 ? pE[c - 1] : 0.0;
+    U[q * N + c] = lambda * F[q * N + c] + lambda * (pS[c] - pn + pE[c] - pw);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// outer loop: me_median_filtering, window 3 (src/utils.cpp:151-213), symmetric boundary.  in / out [2][B][N].
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_occ_median3(const TripleCtl *__restrict__ ctl, const double *__restrict__ in,
+                                                 double *__restrict__ out, int nx, int ny, int B)
+{
+    const int q = blockIdx.z, b = q % B;
+    if (ctl && !ctl[b].active) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    const size_t N = (size_t) nx * ny;
+    const double *src = in + q * N;
+    double v[9];
+    int n = 0;
+#pragma unroll
+    for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+        for (int xx = -1; xx <= 1; xx++) {
+            int x0 = x + xx, y0 = y + yy;
+            if (x0 < 0) x0 = -x0 - 1;
+            if (x0 >= nx) x0 = 2 * nx - x0 - 1;
+            if (y0 < 0) y0 = -y0 - 1;
+            if (y0 >= ny) y0 = 2 * ny - y0 - 1;
+            v[n++] = src[(size_t) y0 * nx + x0];
+        }
+    // the reference's insertion sort (:196-206) as adjacent exchanges on strict ">": stable, so even the
+    // sign of a zero among equal values comes out as upstream
+#pragma unroll
+    for (int a = 1; a < 9; a++)
+#pragma unroll
+        for (int k = a - 1; k >= 0; k--) {
+            const double lo = v[k], hi = v[k + 1];
+            const bool sw = lo > hi;
+            v[k] = sw ? hi : lo;
+            v[k + 1] = sw ? lo : hi;
+        }
+    out[q * N + (size_t) y * nx + x] = v[4];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// outer loop, step 3: Solver_wrt_chi (src/tvl1occflow_solvers.cpp:215-338).  Everything that does not
+// change during its 100 iterations is formed once (k_occ_chi_setup): F and G of both branches of :300-318
+// and beta div(u); an iteration is the dual step + projection (k_occ_chi_eta, :262-268 and :33-52) and the
+// primal step (k_occ_chi_update, :270-325).  C is [5][B][N] = F0, G0, F1, G1, beta div u; ETA is [2][B][N].
+// ---------------------------------------------------------------------------------------------------
+
+// divergence (src/operators.cpp:35-78) with its per-case association order; a(x) / b(x) give v1 / v2
+template <class A1, class A2>
+__device__ __forceinline__ double divergence_at(int i, int j, int nx, int ny, A1 v1, A2 v2)
+{
+    const int p = i * nx + j;
+    if (i > 0 && i < ny - 1 && j > 0 && j < nx - 1) {
+        const double v1x = v1(p) - v1(p - 1);
+        const double v2y = v2(p) - v2(p - nx);
+        return v1x + v2y;
+    }
+    double a = 0;
+    bool first = true;
+    if (j < nx - 1) { a = v1(p); first = false; }
+    if (j > 0) { a = first ? -v1(p - 1) : a - v1(p - 1); first = false; }
+    if (i < ny - 1) { a = first ? v2(p) : a + v2(p); first = false; }
+    if (i > 0) { a = first ? -v2(p - nx) : a - v2(p - nx); first = false; }
+    return a;
+}
+
+struct ChiParams {
+    double lambda, half_over_theta, alpha_theta, beta, tau_chi, tau_eta, is_zero;
+};
+
+__global__ void __launch_bounds__(256) k_occ_chi_setup(const TripleCtl *__restrict__ ctl, const double *__restrict__ U,
+                                                   const double *__restrict__ I1wx, const double *__restrict__ I1wy,
+                                                   const double *__restrict__ Im1wx, const double *__restrict__ Im1wy,
+                                                   const double *__restrict__ rho1_c, const double *__restrict__ rho3_c,
+                                                   const double *__restrict__ Vfwd, const double *__restrict__ Vbck,
+                                                   double *__restrict__ C, int nx, int ny, int B, ChiParams P)
+{
+    const int b = blockIdx.z;
+    if (!ctl[b].active) return;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t N = (size_t) nx * ny, BN = (size_t) B * N;
+    const size_t p = b * N + (size_t) i * nx + j;
+    const double *u1 = U + b * N, *u2 = U + BN + b * N;
+    const double a = U[p], c = U[BN + p];
+    const double vf1 = Vfwd[p], vf2 = Vfwd[BN + p], vb1 = Vbck[p], vb2 = Vbck[BN + p];
+    const double rho1 = rho1_c[p] + (I1wx[p] * vf1 + I1wy[p] * vf2);
+    const double abs_rho1 = (rho1 < 0.) ? -rho1 : rho1;
+    const double rho3 = rho3_c[p] - (Im1wx[p] * vb1 + Im1wy[p] * vb2);
+    const double abs_rho3 = (rho3 < 0.) ? -rho3 : rho3;
+    C[p] = -P.lambda * abs_rho1;
+    C[BN + p] = -P.half_over_theta * ((vf1 - a) * (vf1 - a) + (vf2 - c) * (vf2 - c));
+    C[2 * BN + p] = P.lambda * abs_rho3;
+    C[3 * BN + p] = P.half_over_theta * ((vb1 - a) * (vb1 - a) + (vb2 - c) * (vb2 - c))
+                    + P.alpha_theta * (vb1 * vb1 + vb2 * vb2);
+    const double div_u = divergence_at(i, j, nx, ny, [&](int x) { return u1[x]; }, [&](int x) { return u2[x]; });
+    C[4 * BN + p] = P.beta * div_u;
+}
+
+__global__ void __launch_bounds__(256) k_occ_chi_eta(const TripleCtl *__restrict__ ctl, const double *__restrict__ chi,
+                                                 const double *__restrict__ g, double *__restrict__ ETA, int nx,
+                                                 int ny, int B, ChiParams P)
+{
+    const int b = blockIdx.z;
+    if (!ctl[b].active) return;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t N = (size_t) nx * ny, BN = (size_t) B * N;
+    const size_t p = b * N + (size_t) i * nx + j;
+    const double x = chi[p], gg = g[p];
+    const double chix = (j < nx - 1) ? chi[p + 1] - x : 0, chiy = (i < ny - 1) ? chi[p + nx] - x : 0;
+    double e1 = ETA[p] + P.tau_eta * gg * chix;
+    double e2 = ETA[BN + p] + P.tau_eta * gg * chiy;
+    const double norm2 = e1 * e1 + e2 * e2;
+    if (norm2 < P.is_zero) { e1 = 0.0; e2 = 0.0; }
+    else { const double norm = sqrt(norm2); e1 = e1 / norm; e2 = e2 / norm; }
+    ETA[p] = e1;
+    ETA[BN + p] = e2;
+}
+
+__global__ void __launch_bounds__(256) k_occ_chi_update(const TripleCtl *__restrict__ ctl, double *__restrict__ chi,
+                                                    const double *__restrict__ g, const double *__restrict__ ETA,
+                                                    const double *__restrict__ C, int nx, int ny, int B, ChiParams P)
+{
+    const int b = blockIdx.z;
+    if (!ctl[b].active) return;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const size_t N = (size_t) nx * ny, BN = (size_t) B * N;
+    const size_t p = b * N + (size_t) i * nx + j;
+    const double *gb = g + b * N, *e1 = ETA + b * N, *e2 = ETA + BN + b * N;
+    const double div_eta = divergence_at(i, j, nx, ny, [&](int x) { return gb[x] * e1[x]; },
+                                         [&](int x) { return gb[x] * e2[x]; });
+    double x = chi[p];
+    const int br = (x < 0.5) ? 0 : 2;
+    const double Fv = C[br * BN + p], Gv = C[(br + 1) * BN + p];
+    x = x + P.tau_chi * (div_eta - Fv - Gv - C[4 * BN + p]);
+    if (x > 1.) x = 1.;
+    else if (x < 0.) x = 0.;
+    chi[p] = x;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// outer loop: L2error (src/tvl1occflow.cpp:70-88) and the while test of :277.  Fixed-order fp64 sums:
+// per-CTA partials, then one thread per triple adds them in index order (the reference adds the pixels
+// in index order; the sums agree to rounding and only gate the loop).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kErrThreads) k_occ_error_partial(const TripleCtl *__restrict__ ctl,
+                                                               const double *__restrict__ U, double *__restrict__ Uprev,
+                                                               double *__restrict__ partials, int N, int B, int parts)
+{
+    const int b = blockIdx.y;
+    if (!ctl[b].active) return;
+    const size_t BN = (size_t) B * N;
+    const int per = (N + parts - 1) / parts;
+    const int lo = blockIdx.x * per, hi = min(N, lo + per);
+    double s = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += kErrThreads) {
+        const size_t p = (size_t) b * N + i;
+        const double a = U[p], c = U[BN + p];
+        const double da = a - Uprev[p], dc = c - Uprev[BN + p];
+        s += da * da + dc * dc;
+        Uprev[p] = a;
+        Uprev[BN + p] = c;
+    }
+    __shared__ double sh[kErrThreads];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = kErrThreads / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[(size_t) b * parts + blockIdx.x] = sh[0];
+}
+
+__global__ void k_occ_error_decide(TripleCtl *ctl, const double *__restrict__ partials, int N, int B, int parts,
+                               double epsilon, int max_outer, int *n_active)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || !ctl[b].active) return;
+    double s = 0;
+    for (int k = 0; k < parts; k++) s += partials[(size_t) b * parts + k];
+    const double error = s / N;
+    const int n = ctl[b].n + 1;
+    ctl[b].n = n;
+    ctl[b].error = error;
+    if (!(error > epsilon && n < max_outer)) ctl[b].active = 0;
+    else atomicAdd(n_active, 1);
+}
+
+// start of a warp step: n = 0, error = INFINITY (:275-276); end: counts out (:305-309)
+__global__ void k_occ_ctl_begin(TripleCtl *ctl, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ctl[b].active = 1;
+    ctl[b].n = 0;
+    ctl[b].error = __longlong_as_double(0x7ff0000000000000ll);
+}
+
+__global__ void k_occ_ctl_end(const TripleCtl *__restrict__ ctl, int B, int *iters, double *errs, int slot, int stride)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    iters[(size_t) b * stride + slot] = ctl[b].n;
+    errs[(size_t) b * stride + slot] = ctl[b].error;
+}
+
+// chi = (chi > THR_CHI), src/tvl1occflow.cpp:459 and :46-57
+__global__ void __launch_bounds__(256) k_occ_threshold(double *__restrict__ chi, size_t count, double thr)
+{
+    const size_t p = (size_t) blockIdx.x * 256 + threadIdx.x;
+    if (p < count) chi[p] = (chi[p] > thr) ? 1.0 : 0.0;
+}
+
+} // namespace occ

@@ -26,6 +26,7 @@
 // used as the initial flow (single level).
 #include "../../include/tvl1_b200.h"
 #include "../../include/hs_b200.h"
+#include "../../include/occ_b200.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -268,4 +269,78 @@ void horn_schunck_optical_flow(const float *I1, const float *I2, float *u, float
                                const bool verbose)
 {
     hs_one_level<float>(I1, I2, u, v, nx, ny, alpha, warps, TOL, maxiter, verbose);
+}
+
+// ---- TV-L1 with occlusions: src/tvl1occflow.h:63-79 and :111-129, ofpix_t = double (as shipped) -------
+// _Z31Dual_TVL1_optic_flow_multiscalePdS_S_S_S_S_S_iiddddididb, _Z20Dual_TVL1_optic_flowPdS_S_S_S_S_S_iidddd idb:
+// the seven-plane overloads of the TV-L1 names above.  Verbose mode prints what the reference prints:
+// "verbose" on stdout once per level (src/tvl1occflow.cpp:192-194) and "Warping: %d, Iterations: %d,
+// Error: %e" on stderr (:292-296).  The occlusion solver computes in fp64 (include/occ_b200.h).
+namespace {
+
+struct OccThreadCtx {
+    occ_ctx *ctx = nullptr;
+    int device = -1;
+    ~OccThreadCtx() { occ_destroy(ctx); }
+};
+
+occ_ctx *occ_thread_ctx()
+{
+    static thread_local OccThreadCtx tc;
+    int dev = t_device;
+    if (dev < 0) {
+        dev = 0;
+        if (const char *e = std::getenv("TVL1_DEVICE")) dev = std::atoi(e);
+    }
+    if (tc.ctx && tc.device != dev) { occ_destroy(tc.ctx); tc.ctx = nullptr; }
+    if (!tc.ctx) {
+        if (occ_create(dev, &tc.ctx) != OCC_OK)
+            throw std::runtime_error(std::string("occ_b200: ") + occ_last_error(nullptr));
+        tc.device = dev;
+    }
+    return tc.ctx;
+}
+
+[[noreturn]] void occ_raise(occ_ctx *ctx, int rc)
+{
+    if (rc == OCC_ERR_SIGMA) throw std::runtime_error("GaussianSmooth: sigma too large");
+    throw std::runtime_error(std::string("occ_b200: ") + occ_last_error(ctx));
+}
+
+void occ_print_level(int warps, const int *iters, const double *errs)
+{
+    printf("verbose\n");
+    fflush(stdout);
+    for (int w = 0; w < warps; w++)
+        fprintf(stderr, "Warping: %d, Iterations: %d, Error: %e\n", w, iters[w], errs[w]);
+}
+
+} // namespace
+
+void Dual_TVL1_optic_flow_multiscale(double *I_1, double *I0, double *I1, double *filtI0, double *u1, double *u2,
+                                     double *chi, const int nxx, const int nyy, const double lambda,
+                                     const double alpha, const double beta, const double theta, const int nscales,
+                                     const double zfactor, const int warps, const double epsilon, const bool verbose)
+{
+    occ_ctx *ctx = occ_thread_ctx();
+    occ_params p{ lambda, alpha, beta, theta, nscales, zfactor, warps, epsilon };
+    std::vector<int> iters((size_t) nscales * warps);
+    std::vector<double> errs((size_t) nscales * warps);
+    const int rc = occ_solve_f64(ctx, I_1, I0, I1, filtI0, u1, u2, chi, nxx, nyy, &p, iters.data(), errs.data());
+    if (rc != OCC_OK) occ_raise(ctx, rc);
+    if (verbose)
+        for (int k = 0; k < nscales; k++) occ_print_level(warps, iters.data() + (size_t) k * warps, errs.data() + (size_t) k * warps);
+}
+
+void Dual_TVL1_optic_flow(double *I_1, double *I0, double *I1, double *filtI0, double *u1, double *u2, double *chi,
+                          const int nx, const int ny, const double lambda, const double alpha, const double beta,
+                          const double theta, const int warps, const double epsilon, const bool verbose)
+{
+    occ_ctx *ctx = occ_thread_ctx();
+    occ_params p{ lambda, alpha, beta, theta, 1, 0.5, warps, epsilon };
+    std::vector<int> iters(warps);
+    std::vector<double> errs(warps);
+    const int rc = occ_single_scale_f64(ctx, I_1, I0, I1, filtI0, u1, u2, chi, nx, ny, &p, iters.data(), errs.data());
+    if (rc != OCC_OK) occ_raise(ctx, rc);
+    if (verbose) occ_print_level(warps, iters.data(), errs.data());
 }

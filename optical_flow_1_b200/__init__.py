@@ -7,4 +7,5 @@ __path__.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.absp
 
 from .tvl1 import *  # noqa: F401,F403,E402
 from .hs import *  # noqa: F401,F403,E402
+from .occ import *  # noqa: F401,F403,E402
 from . import synth, shard  # noqa: F401,E402

@@ -380,6 +380,23 @@ class CpuOcc:
             raise RuntimeError("GaussianSmooth: sigma too large")
         return u1, u2, chi, it, er
 
+    def single_scale(self, I_1, I0, I1, filtI0, u1, u2, chi, lam=0.15, alpha=0.01, beta=0.15, theta=0.3, warps=2,
+                     eps=0.01):
+        """Dual_TVL1_optic_flow of src/tvl1occflow.cpp:144-330 (restatement only): one level from the given
+        flow and occlusion map -> (u1, u2, chi, iters[warps], errs[warps])."""
+        assert self.kind == "port"
+        I_1, I0, I1 = self._arr(I_1), self._arr(I0), self._arr(I1)
+        f = self._arr(I0 if filtI0 is None else filtI0)
+        u1, u2, chi = self._arr(u1).copy(), self._arr(u2).copy(), self._arr(chi).copy()
+        ny, nx = I0.shape
+        it = np.zeros(warps, np.int32)
+        er = np.zeros(warps, np.float64)
+        self.lib.orc_occ_single_scale(self._p(I_1), self._p(I0), self._p(I1), self._p(f), self._p(u1), self._p(u2),
+                                      self._p(chi), C.c_int(nx), C.c_int(ny), C.c_double(lam), C.c_double(alpha),
+                                      C.c_double(beta), C.c_double(theta), C.c_int(warps), C.c_double(eps),
+                                      self._p(it), self._p(er))
+        return u1, u2, chi, it, er
+
     def rof_box(self, u, f, p1, p2, g, lam, omega=1.25, niter=10):
         """Scalar_ROF_BoxCellCentered -> (u, p1, p2) after niter sweeps."""
         u, p1, p2 = self._arr(u).copy(), self._arr(p1).copy(), self._arr(p2).copy()
