@@ -54,9 +54,11 @@ def parse():
     ap.add_argument("--max-batch", type=int, default=256, help="pairs advanced in lock-step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="batch1080p", choices=["batch1080p", "band4k", "band8k"],
+    ap.add_argument("--workload", default="batch1080p", choices=["batch1080p", "band4k", "band8k", "occ"],
                     help="batch1080p: BASELINE configs[2] (the headline); band4k / band8k: configs[3] / configs[4], "
-                         "ONE pair split into row bands over the ranks (strong scaling)")
+                         "ONE pair split into row bands over the ranks (strong scaling); occ: the occlusion solver "
+                         "(SURVEY 8f-3) on a batch of 640x480 frame triples per rank")
+    ap.add_argument("--triples", type=int, default=64, help="occ workload: frame triples per rank per step")
     ap.add_argument("--no-row-band", action="store_true",
                     help="skip the row_band leg that the batch1080p workload appends when N > 1")
     ap.add_argument("--quick", action="store_true", help="skip the fp64 / sequence / copy-ceiling extras of e2e")
@@ -397,6 +399,187 @@ def run_band_workload(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ---- TV-L1 with occlusions ------------------------------------------------------------------
+OCC_CASE = dict(nx=640, ny=480, kw=dict(lam=0.15, alpha=0.01, beta=0.15, theta=0.3, nscales=5, zfactor=0.5, warps=2, eps=0.01),
+                name="batch of synthetic 640x480 frame triples (BASELINE.json configs[0]'s shape), CLI defaults of "
+                     "src/tvl1occflow_constants.h:14-23 (5 scales by the CLI's size rule, 2 warps)")
+OCC_UNIT = "frame-triples/s"
+OCC_METRIC = "TV-L1 with occlusions, 640x480 frame-triples/sec"
+
+
+def occ_cpu(args, budget_s, max_triples=3):
+    """The reference's own CPU solver (oracle/_ref behind the zero-filling new[] shim, else the C
+    restatement) on whole triples of the same workload, all host threads."""
+    import numpy as np
+    from oracle.loader import CpuOcc, occ_available
+    from optical_flow_1_b200 import synth
+    kind = "reference" if occ_available("reference", np.float64) else "port"
+    cpu = CpuOcc(kind, np.float64)
+    threads = os.cpu_count() or 1
+    cpu.set_threads(threads)
+    times = []
+    t_all = time.perf_counter()
+    for b in range(max_triples):
+        T = synth.make_triple(OCC_CASE["nx"], OCC_CASE["ny"], seed=1234 + b)
+        t = time.perf_counter()
+        cpu.multiscale(T[0], T[1], T[2], None, **OCC_CASE["kw"])
+        times.append(time.perf_counter() - t)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    return {"value": len(times) / sum(times), "unit": OCC_UNIT, "cores": threads, "kind": kind,
+            "sample": "%d of the workload's triples (seeds 1234..), 7-plane Dual_TVL1_optic_flow_multiscale in fp64, "
+                      "g++ -O3 -fopenmp, %d threads (its box relaxation is serial code), %.1f s"
+                      % (len(times), threads, sum(times))}
+
+
+def run_occ_reference(args, rank):
+    if rank != 0:
+        return
+    b = occ_cpu(args, 1e9, max_triples=args.warmup)          # warm-up steps
+    import numpy as np
+    from oracle.loader import CpuOcc, occ_available
+    from optical_flow_1_b200 import synth
+    kind = "reference" if occ_available("reference", np.float64) else "port"
+    cpu = CpuOcc(kind, np.float64)
+    cpu.set_threads(os.cpu_count() or 1)
+    T = synth.make_triple(OCC_CASE["nx"], OCC_CASE["ny"], seed=1234)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.multiscale(T[0], T[1], T[2], None, **OCC_CASE["kw"])
+    dt = time.perf_counter() - t
+    v = args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": OCC_METRIC, "value": v, "unit": OCC_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": OCC_CASE["name"], "params": OCC_CASE["kw"], "reference_arm_step": "ONE triple per step"},
+        "cpu_baseline": dict(b, value=v, sample="each step = 1 triple of the workload (seed 1234)"),
+        "e2e": {"value": v, "unit": OCC_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_occ_workload(args, rank, local_rank, world):
+    """--workload occ: one step = one occ_solve_batch_dev_f64 call on `--triples` frame triples per rank
+    (triples are independent: batch-sharded over the ranks, no collective)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import optical_flow_1_b200 as pkg
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the solver has no CPU fallback)")
+    nx, ny, kw, B = OCC_CASE["nx"], OCC_CASE["ny"], OCC_CASE["kw"], args.triples
+    pin_to_gpu_numa_node(local_rank)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    solver = pkg.TVL1Occ(device=local_rank, profiling=True, max_batch=args.triples)
+    trip = [pkg.synth.make_triple(nx, ny, seed=1234 + rank * B + b) for b in range(B)]
+    host = [np.stack([t[k] for t in trip]).astype(np.float64) for k in range(3)]
+    dI = [torch.from_numpy(h).to(dev) for h in host]
+    dO = [torch.empty_like(dI[0]) for _ in range(3)]
+    ptrs = [t.data_ptr() for t in dI] + [0] + [t.data_ptr() for t in dO]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return solver.solve_batch_device(*ptrs, B, nx, ny, want_iters=True, **kw)
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
+    acc = None
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        iters, _ = step()
+        st = solver.stats()
+        acc = st if acc is None else {k: acc[k] + st[k] for k in st}
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    ms = torch.tensor([1e3 * wall / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    # e2e: host buffers (pinned) through occ_solve_batch_f64, H2D of the three frames and D2H of flow + map inside
+    hp = [torch.from_numpy(h).pin_memory() for h in host]
+    ho = [torch.empty_like(hp[0]).pin_memory() for _ in range(3)]
+    it_e = np.zeros((B, kw["nscales"], kw["warps"]), np.int32)
+    prm = pkg.OccParams(kw["lam"], kw["alpha"], kw["beta"], kw["theta"], kw["nscales"], kw["zfactor"], kw["warps"], kw["eps"])
+    import ctypes as C
+
+    def e2e_step():
+        rc = solver.lib.occ_solve_batch_f64(solver.ctx, C.c_int(B), C.c_void_p(hp[0].data_ptr()), C.c_void_p(hp[1].data_ptr()),
+                                            C.c_void_p(hp[2].data_ptr()), None, C.c_void_p(ho[0].data_ptr()),
+                                            C.c_void_p(ho[1].data_ptr()), C.c_void_p(ho[2].data_ptr()), C.c_int(nx),
+                                            C.c_int(ny), C.byref(prm), it_e.ctypes.data_as(C.c_void_p), None)
+        solver._ck(rc)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(1, min(args.steps, 3))
+    for _ in range(e_steps):
+        e2e_step()
+    barrier()
+    e_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e_ms = float(e_ms.item())
+    same = bool(np.array_equal(it_e, iters) and torch.equal(ho[0].to(dev), dO[0]) and torch.equal(ho[2].to(dev), dO[2]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cpu_base = occ_cpu(args, args.cpu_seconds) if (rank == 0 and not args.no_cpu_baseline) else None
+    if rank == 0:
+        chi_bytes = 80.0 * acc["chi_pixel_iterations"]
+        chi_gbps = chi_bytes / (acc["ms_chi"] / 1e3) / 1e9 if acc["ms_chi"] else None
+        line = {
+            "metric": OCC_METRIC, "value": B * world * 1e3 / ms, "unit": OCC_UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": OCC_CASE["name"], "params": kw, "triples_per_rank_per_step": B,
+                       "global_triples_per_step": B * world, "parallelism": "batch-sharded x%d, no collective" % world,
+                       "l2": "state of one step (%.1f GB per rank) exceeds the 126 MB L2; no explicit flush"
+                             % (B * 47 * nx * ny * 8 / 1e9),
+                       "timed_region": "value: wall clock around the steps (the outer loop reads one counter per outer "
+                                       "iteration back), max over ranks"},
+            "clocks": clk,
+            "e2e": {"value": B * world * 1e3 / e_ms, "unit": OCC_UNIT, "ms_per_step": e_ms,
+                    "h2d_bytes_per_step": 3 * B * nx * ny * 8 * world, "d2h_bytes_per_step": 3 * B * nx * ny * 8 * world,
+                    "api": "occ_solve_batch_f64 (host pinned fp64 frames in, flow + occlusion map out)",
+                    "matches_device_path": same},
+            "gpu_launches": int(acc["kernel_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_occ_chi_eta + k_occ_chi_update: one primal-dual iteration of the "
+                         "occlusion map (Solver_wrt_chi), 100 per outer iteration",
+                         "achieved": chi_gbps, "peak": peak, "unit": "GB/s", "frac": chi_gbps / peak if chi_gbps else None,
+                         "traffic": None, "algorithmic_bytes_per_pixel_iteration": 80,
+                         "what": "fp64: read chi, eta1, eta2, g, F, G, beta div u; write chi, eta1, eta2",
+                         "pixel_iterations": acc["chi_pixel_iterations"], "kernel_ms": acc["ms_chi"],
+                         "kernel_share_of_step": acc["ms_chi"] / acc["ms_total"] if acc["ms_total"] else None},
+            "box_relaxation": {"kernel": "k_occ_rof_gs (wavefront Gauss-Seidel, latency-bound: one CTA per plane)",
+                               "cell_updates": acc["box_cell_updates"], "ms": acc["ms_box"],
+                               "cell_updates_per_s": acc["box_cell_updates"] / (acc["ms_box"] / 1e3) if acc["ms_box"] else None,
+                               "share_of_step": acc["ms_box"] / acc["ms_total"] if acc["ms_total"] else None},
+            "device_ms_per_step_by_kernel_group": {k: acc[k] / args.steps for k in
+                                                   ("ms_total", "ms_pyramid", "ms_warp", "ms_box", "ms_chi", "ms_other")},
+            "outer_iterations_per_triple": acc["outer_iterations"] / args.steps / B,
+            "host_syncs_per_step": acc["host_syncs"] / args.steps,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---- our arm -------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -717,7 +900,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
+    if args.workload == "occ":
+        run_occ_reference(args, rank) if args.impl == "reference" else run_occ_workload(args, rank, local_rank, world)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     elif args.workload != "batch1080p":
         run_band_workload(args, rank, local_rank, world)

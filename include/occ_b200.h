@@ -89,6 +89,7 @@ int occ_create(int device, occ_ctx **out);
 void occ_destroy(occ_ctx *ctx);
 const char *occ_last_error(const occ_ctx *ctx);     /* ctx may be NULL: error of the last failed occ_create */
 int occ_set_profiling(occ_ctx *ctx, int on);        /* CUDA events around the kernel groups (adds syncs) */
+int occ_set_max_batch(occ_ctx *ctx, int triples);   /* triples advanced in lock-step (default 64; OCC_MAX_BATCH) */
 int occ_get_stats(const occ_ctx *ctx, occ_stats *out);   /* of the last solve */
 void *occ_get_stream(const occ_ctx *ctx);
 

@@ -349,6 +349,7 @@ int run_level(occ_ctx *ctx, int s, const occ_params &prm, int stat_base)
             k_occ_ctl_begin<<<ctl_blocks, 128, 0, st>>>(w.ctl, B);
             CKL();
         }
+        int active_now = B;
         for (int n = 0; n < OCC_EXT_MAX_ITERATIONS; n++) {
             {
                 Scope sc(ctx, G_OTHER);
@@ -393,7 +394,10 @@ int run_level(occ_ctx *ctx, int s, const occ_params &prm, int stat_base)
             }
             CK(cudaStreamSynchronize(st));
             ctx->stats.host_syncs++;
-            if (*ctx->h_n_active == 0) break;
+            ctx->stats.box_cell_updates += (unsigned long long) active_now * 2 * N * OCC_MAX_ITERATIONS_U;
+            ctx->stats.chi_pixel_iterations += (unsigned long long) active_now * N * OCC_MAX_ITERATIONS_CHI;
+            active_now = *ctx->h_n_active;
+            if (active_now == 0) break;
         }
         k_occ_ctl_end<<<ctl_blocks, 128, 0, st>>>(w.ctl, B, w.stat_iters, w.stat_errs, stat_base + wp, w.stat_stride);
         CKL();
@@ -648,6 +652,13 @@ int occ_set_profiling(occ_ctx *ctx, int on)
 {
     if (!ctx) return OCC_ERR_ARG;
     ctx->profiling = on != 0;
+    return OCC_OK;
+}
+
+int occ_set_max_batch(occ_ctx *ctx, int triples)
+{
+    if (!ctx || triples < 1) return OCC_ERR_ARG;
+    ctx->max_batch = triples;
     return OCC_OK;
 }
 

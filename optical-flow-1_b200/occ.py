@@ -49,7 +49,7 @@ def occ_clamp_nscales(nx, ny, nscales, zfactor):
 class TVL1Occ:
     """One solver context = one GPU + one stream."""
 
-    def __init__(self, device=0, profiling=False):
+    def __init__(self, device=0, profiling=False, max_batch=None):
         self.lib = _load()
         self.lib.occ_last_error.restype = C.c_char_p
         self.lib.occ_last_error.argtypes = [C.c_void_p]
@@ -62,6 +62,8 @@ class TVL1Occ:
         self.device = device
         if profiling:
             self.lib.occ_set_profiling(self.ctx, C.c_int(1))
+        if max_batch:
+            self.lib.occ_set_max_batch(self.ctx, C.c_int(int(max_batch)))
 
     def close(self):
         if getattr(self, "ctx", None):

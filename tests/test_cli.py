@@ -172,3 +172,74 @@ def test_hs_cli_drop_in_on_gpu(tmp_path, oracle_f64):
     assert d.mean() <= 1e-3 and d.max() <= 1e-2
     _, _, _, iters2, scales2, _ = run_hs_cli(HS_CLI, tmp_path, args=("1", "7", "10", "0.5", "2", "0.001", "20", "1"))
     assert len(scales2) == 3 and len(iters2) == 6       # 96x72: N = 1 + log2(120 / 16) = 3.9 -> 3 levels
+
+
+# ---- TV-L1 with occlusions: the reference's unmodified src/tvl1occflow_main.cpp ---------------------------
+OCC_CLI = os.path.join(ROOT, "cli", "tvl1occflow")
+OCC_CLI_REF = os.path.join(ROOT, "cli", "tvl1occflow_ref")
+
+
+def read_png_grey8(path):
+    """Reads back the 8-bit grey PNG iio_lite.cpp writes (any zlib stream, filter 0 rows)."""
+    import zlib
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(b):
+        n, typ = struct.unpack(">I4s", b[pos:pos + 8])
+        body = b[pos + 8:pos + 8 + n]
+        assert zlib.crc32(typ + body) == struct.unpack(">I", b[pos + 8 + n:pos + 12 + n])[0]
+        if typ == b"IHDR":
+            w, h, depth, colour = struct.unpack(">IIBB", body[:10])
+            assert (depth, colour) == (8, 0)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, w + 1)
+    assert not raw[:, 0].any()
+    return raw[:, 1:]
+
+
+def run_occ_cli(exe, tmp, nx=112, ny=80):
+    I_1, I0, I1 = _cases.synth.make_triple(nx, ny, seed=31, scale=0.5)
+    q = [write_pgm(tmp / ("f%d.pgm" % k), im) for k, im in enumerate((I_1, I0, I1))]
+    flo, occ = tmp / ("occ_%s.flo" % os.path.basename(exe)), tmp / ("occ_%s.png" % os.path.basename(exe))
+    # I_1 I0 I1 filtI0 out occ nproc lambda alpha beta theta nscales zfactor nwarps epsilon verbose
+    args = [str(tmp / "f0.pgm"), str(tmp / "f1.pgm"), str(tmp / "f2.pgm"), str(tmp / "f1.pgm"), str(flo), str(occ),
+            "1", "0.15", "0.01", "0.15", "0.3", "100", "0.5", "2", "0.01", "1"]
+    p = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    iters = [int(m) for m in re.findall(r"Warping: \d+, Iterations: (\d+), Error:", p.stderr)]
+    return q, read_flo(flo), read_png_grey8(occ), iters, p.stderr
+
+
+def occ_expected(q, nx=112, ny=80):
+    from oracle.loader import CpuOcc
+    P = CpuOcc("port", np.float64)
+    P.set_threads(1)
+    nscales = int(np.floor(np.log(np.float32(min(nx, ny)) / 16.0) / np.log(1. / 0.5))) + 1   # main.cpp:191-196
+    return P.multiscale(q[0], q[1], q[2], None, nscales=nscales, zfactor=0.5, warps=2, eps=0.01), nscales
+
+
+@pytest.mark.skipif(not os.path.exists(OCC_CLI_REF), reason="cli/tvl1occflow_ref not built (needs /root/reference)")
+def test_reference_occ_cli_with_iio_lite_matches_oracle(tmp_path):
+    """CPU: three PGM frames -> the reference's occlusion solver (zero-filling new[]) -> .flo + occlusion PNG
+    through our IO shim: equal to the oracle on the same 8-bit frames."""
+    q, (u1, u2), occ, iters, err = run_occ_cli(OCC_CLI_REF, tmp_path)
+    (r1, r2, rchi, riters, _), nscales = occ_expected(q)
+    assert nscales == 3 and iters == riters.ravel().tolist(), err
+    assert np.array_equal(u1, r1.astype(np.float32)) and np.array_equal(u2, r2.astype(np.float32))
+    assert np.array_equal(occ, (rchi * 255).astype(np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(OCC_CLI), reason="cli/tvl1occflow not built")
+def test_occ_cli_drop_in_on_gpu(tmp_path):
+    """GPU: the same unmodified main() linked against libtvl1_b200.so: same verbose lines and iteration
+    counts, the .flo file and the occlusion map IDENTICAL to the reference's (fp64 path, bit-exact)."""
+    q, (u1, u2), occ, iters, err = run_occ_cli(OCC_CLI, tmp_path)
+    (r1, r2, rchi, riters, _), _ = occ_expected(q)
+    assert iters == riters.ravel().tolist(), err
+    assert np.array_equal(u1, r1.astype(np.float32)) and np.array_equal(u2, r2.astype(np.float32))
+    assert np.array_equal(occ, (rchi * 255).astype(np.uint8))
+    assert 0 < occ.astype(bool).sum() < occ.size
