@@ -66,7 +66,7 @@ def parse():
 
 
 BAND_CASES = {
-    "band4k": dict(nx=3840, ny=2160, kw=dict(nscales=6, warps=10, eps=0.001), min_rows=512,
+    "band4k": dict(nx=3840, ny=2160, kw=dict(nscales=6, warps=10, eps=0.001), min_rows=1024,
                    name="BASELINE.json configs[3]: synthetic 3840x2160 pair, nscales=6 nwarps=10 eps=0.001"),
     "band8k": dict(nx=7680, ny=4320, kw=dict(nscales=5, warps=5, eps=0.01), min_rows=1024,
                    name="BASELINE.json configs[4]: synthetic 7680x4320 pair, default params"),

@@ -13,6 +13,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -132,6 +133,8 @@ struct tvl1_ctx {
     static constexpr int kMaxLanes = 4;
     tvl1_ctx *sib[kMaxLanes - 1] = { nullptr, nullptr, nullptr };   // sibling contexts (extra lanes, same GPU)
     int host_lanes = 4;                      // lanes used by the host-buffer batch entry points
+    int short_div = 4;                       // host-buffer batches: first / last chunks of max_batch / short_div pairs
+                                             // (TVL1_SHORT_DIV, 0 or 1 = all chunks equal)
     int dev_lanes = 2;                       // lanes used by the device-buffer batch entry point
     bool is_sibling = false;
     tvl1_ctx *band_ctx = nullptr;            // private context of the row-band mode
@@ -1219,10 +1222,12 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
     }
     for (int l = 0; l < nlanes; l++) lanes[l]->blocking_wait = nlanes > 1;
     int rcs[tvl1_ctx::kMaxLanes] = { TVL1_OK, TVL1_OK, TVL1_OK, TVL1_OK };
+    std::atomic<int> next{0};
     auto work = [&](int l) {
         tvl1_ctx *c = lanes[l];
         cudaSetDevice(c->device);
-        for (int k = l; k < nchunks && rcs[l] == TVL1_OK; k += nlanes) rcs[l] = chunk_fn(c, k);
+        // chunks are taken from a shared queue in order (their sizes may differ, see chunk_schedule)
+        for (int k = next++; k < nchunks && rcs[l] == TVL1_OK; k = next++) rcs[l] = chunk_fn(c, k);
         resolve_events(c);
     };
     std::vector<std::thread> threads;
@@ -1234,6 +1239,30 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
         if (rcs[l] != TVL1_OK && rcs[0] == TVL1_OK) { ctx->err = lanes[l]->err; rcs[0] = rcs[l]; }
     }
     return rcs[0];
+}
+
+// Cuts a host-buffer batch into lock-step chunks.  The pipeline of a call cannot start computing before
+// its first chunk has arrived and cannot finish before its last chunk has been downloaded, and towards
+// the end the lanes run out of work at different times; so when there are enough chunks the first and
+// the last ones (one per lane) are SHORT (Bmax / short_div pairs), the ones in between full.  Only two
+// chunk sizes occur (plus at most one ragged remainder), which is what a lane keeps workspaces for.
+void chunk_schedule(const tvl1_ctx *ctx, int npairs, int Bmax, int lanes, std::vector<std::pair<int, int>> &out)
+{
+    const int div = ctx->short_div;
+    const int small = div > 1 ? Bmax / div : 0;
+    const int nlanes = std::max(1, std::min(lanes, (int) tvl1_ctx::kMaxLanes));
+    int first = 0;
+    auto push = [&](int b) { out.emplace_back(first, b); first += b; };
+    if (small >= 1 && npairs >= 2 * nlanes * small + 2 * nlanes * Bmax) {
+        for (int l = 0; l < nlanes; l++) push(small);
+        int rest = npairs - first - nlanes * small;
+        while (rest >= Bmax) { push(Bmax); rest -= Bmax; }
+        while (rest >= small) { push(small); rest -= small; }
+        if (rest > 0) push(rest);
+        for (int l = 0; l < nlanes; l++) push(small);
+    } else {
+        while (first < npairs) push(std::min(Bmax, npairs - first));
+    }
 }
 
 // Host-buffer driver shared by the f32/f64, multiscale/single-scale entry points.  A batch larger
@@ -1250,14 +1279,15 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     const bool f64 = sizeof(T) == 8;
     const size_t n = (size_t) nx * ny;
     const int Bmax = std::min(npairs, ctx->max_batch);
-    const int nchunks = ceil_div(npairs, Bmax);
     const int nstat = (multiscale ? prm->nscales : 1) * prm->warps;
     const size_t stage_frames = (size_t) Bmax + (I1 ? 0 : 1);     // frame sequence: B+1 frames per chunk
-    return run_lanes(ctx, nchunks, ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
+    std::vector<std::pair<int, int>> chunks;                      // (first pair, pairs)
+    chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
+    return run_lanes(ctx, (int) chunks.size(), ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
         tvl1_ctx *ctx = c;   // for CK / TRY
         TRY(ensure_stage(ctx, stage_frames * n * sizeof(T), f64));
-        const int first = k * Bmax, B = std::min(Bmax, npairs - first);
-        return solve_chunk<T>(ctx, first, B, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out, multiscale, nstat);
+        return solve_chunk<T>(ctx, chunks[k].first, chunks[k].second, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out,
+                              multiscale, nstat);
     });
 }
 
@@ -1770,6 +1800,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *tp = std::getenv("TVL1_TAIL_PAIRS")) ctx->tail_pairs = std::max(0, std::atoi(tp));
     if (const char *tc = std::getenv("TVL1_TAIL_SLOT_CTAS")) ctx->tail_slot_ctas = std::max(1, std::atoi(tc));
     if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
+    if (const char *sd = std::getenv("TVL1_SHORT_DIV")) ctx->short_div = std::max(0, std::atoi(sd));
     if (const char *mp = std::getenv("TVL1_TB_MAX_MPIX")) ctx->tb_max_pixels = std::max(0ll, std::atoll(mp)) << 20;
     *out = ctx;
     return TVL1_OK;
