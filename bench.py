@@ -58,7 +58,7 @@ def parse():
                     help="batch1080p: BASELINE configs[2] (the headline); band4k / band8k: configs[3] / configs[4], "
                          "ONE pair split into row bands over the ranks (strong scaling); occ: the occlusion solver "
                          "(SURVEY 8f-3) on a batch of 640x480 frame triples per rank")
-    ap.add_argument("--triples", type=int, default=64, help="occ workload: frame triples per rank per step")
+    ap.add_argument("--triples", type=int, default=148, help="occ workload: frame triples per rank per step")
     ap.add_argument("--no-row-band", action="store_true",
                     help="skip the row_band leg that the batch1080p workload appends when N > 1")
     ap.add_argument("--quick", action="store_true", help="skip the fp64 / sequence / copy-ceiling extras of e2e")

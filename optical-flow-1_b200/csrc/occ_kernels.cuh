@@ -548,6 +548,73 @@ __global__ void __launch_bounds__(256) k_occ_chi_update(const TripleCtl *__restr
     chi[p] = x;
 }
 
+// Both steps of one iteration in one pass (the default; the two kernels above are the A/B reference and
+// give the same bits): a CTA owns a 32 x 16 tile, projects the dual variable on the tile plus the column
+// to its left and the row above it (the values the divergence at its own pixels reads), keeps g * eta in
+// shared memory and updates chi.  chi and eta are read from one buffer and written to another (a
+// neighbouring tile still needs the old values): 100 iterations end in the buffer they started from.
+constexpr int kChiTW = 32, kChiTH = 16;
+
+__global__ void __launch_bounds__(256) k_occ_chi_fused(const TripleCtl *__restrict__ ctl, const double *__restrict__ chi_in,
+                                                       double *__restrict__ chi_out, const double *__restrict__ g,
+                                                       const double *__restrict__ eta_in, double *__restrict__ eta_out,
+                                                       const double *__restrict__ C, int nx, int ny, int B, ChiParams P)
+{
+    const int b = blockIdx.z;
+    if (!ctl[b].active) return;
+    __shared__ double s1[kChiTH + 1][kChiTW + 1], s2[kChiTH + 1][kChiTW + 1];     // g * eta1, g * eta2 at (y0-1.., x0-1..)
+    const size_t N = (size_t) nx * ny, BN = (size_t) B * N;
+    const size_t o = b * N;
+    const int x0 = blockIdx.x * kChiTW, y0 = blockIdx.y * kChiTH;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int k = tid; k < (kChiTH + 1) * (kChiTW + 1); k += 256) {
+        const int ly = k / (kChiTW + 1), lx = k - ly * (kChiTW + 1);
+        const int i = y0 - 1 + ly, j = x0 - 1 + lx;
+        if (i < 0 || j < 0 || i >= ny || j >= nx) continue;
+        const size_t p = o + (size_t) i * nx + j;
+        const double x = chi_in[p], gg = g[p];
+        const double chix = (j < nx - 1) ? chi_in[p + 1] - x : 0, chiy = (i < ny - 1) ? chi_in[p + nx] - x : 0;
+        double e1 = eta_in[p] + P.tau_eta * gg * chix;
+        double e2 = eta_in[BN + p] + P.tau_eta * gg * chiy;
+        const double norm2 = e1 * e1 + e2 * e2;
+        if (norm2 < P.is_zero) { e1 = 0.0; e2 = 0.0; }
+        else { const double norm = sqrt(norm2); e1 = e1 / norm; e2 = e2 / norm; }
+        if (ly && lx) { eta_out[p] = e1; eta_out[BN + p] = e2; }
+        s1[ly][lx] = gg * e1;
+        s2[ly][lx] = gg * e2;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kChiTH / 8; r++) {
+        const int ly = threadIdx.y + 8 * r + 1, lx = threadIdx.x + 1;
+        const int i = y0 + ly - 1, j = x0 + lx - 1;
+        if (i >= ny || j >= nx) continue;
+        const size_t p = o + (size_t) i * nx + j;
+        // divergence (src/operators.cpp:35-78) of (g eta1, g eta2), per-case association order
+        double div_eta;
+        if (i > 0 && i < ny - 1 && j > 0 && j < nx - 1) {
+            const double v1x = s1[ly][lx] - s1[ly][lx - 1];
+            const double v2y = s2[ly][lx] - s2[ly - 1][lx];
+            div_eta = v1x + v2y;
+        } else {
+            double a = 0;
+            bool first = true;
+            if (j < nx - 1) { a = s1[ly][lx]; first = false; }
+            if (j > 0) { a = first ? -s1[ly][lx - 1] : a - s1[ly][lx - 1]; first = false; }
+            if (i < ny - 1) { a = first ? s2[ly][lx] : a + s2[ly][lx]; first = false; }
+            if (i > 0) { a = first ? -s2[ly - 1][lx] : a - s2[ly - 1][lx]; first = false; }
+            div_eta = a;
+        }
+        double x = chi_in[p];
+        const int br = (x < 0.5) ? 0 : 2;
+        const double Fv = C[br * BN + p], Gv = C[(br + 1) * BN + p];
+        x = x + P.tau_chi * (div_eta - Fv - Gv - C[4 * BN + p]);
+        if (x > 1.) x = 1.;
+        else if (x < 0.) x = 0.;
+        chi_out[p] = x;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // outer loop: L2error (src/tvl1occflow.cpp:70-88) and the while test of :277.  Fixed-order fp64 sums:
 // per-CTA partials, then one thread per triple adds them in index order (the reference adds the pixels

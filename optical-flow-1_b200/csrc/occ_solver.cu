@@ -61,6 +61,7 @@ struct occ_ctx {
     std::string err;
     bool profiling = false;
     int max_batch = 64;
+    bool chi_fused = true;           // OCC_CHI_FUSED=0: the two-kernel form of the occlusion-map iteration (A/B)
     int sm_count = 148;
     occ_stats stats{};
     Workspace ws;
@@ -374,11 +375,23 @@ int run_level(occ_ctx *ctx, int s, const occ_params &prm, int stat_base)
                 k_occ_chi_setup<<<gB, kBlock2d, 0, st>>>(w.ctl, U, I1wx, I1wy, Im1wx, Im1wy, rho1, rho3, w.Vfwd, w.Vbck, w.C,
                                                      nx, ny, B, cp);
                 CKL();
-                for (int k = 0; k < OCC_MAX_ITERATIONS_CHI; k++) {
-                    k_occ_chi_eta<<<gB, kBlock2d, 0, st>>>(w.ctl, chi, w.g, w.ETA, nx, ny, B, cp);
-                    CKL();
-                    k_occ_chi_update<<<gB, kBlock2d, 0, st>>>(w.ctl, chi, w.g, w.ETA, w.C, nx, ny, B, cp);
-                    CKL();
+                if (ctx->chi_fused) {
+                    // ping-pong between (chi, ETA) and (tmpU, AL), both free here; an even count ends where it began
+                    static_assert(OCC_MAX_ITERATIONS_CHI % 2 == 0, "the fused occlusion-map loop ping-pongs");
+                    const dim3 gF(ceil_div(nx, kChiTW), ceil_div(ny, kChiTH), B);
+                    for (int k = 0; k < OCC_MAX_ITERATIONS_CHI; k += 2) {
+                        k_occ_chi_fused<<<gF, kBlock2d, 0, st>>>(w.ctl, chi, w.tmpU, w.g, w.ETA, w.AL, w.C, nx, ny, B, cp);
+                        CKL();
+                        k_occ_chi_fused<<<gF, kBlock2d, 0, st>>>(w.ctl, w.tmpU, chi, w.g, w.AL, w.ETA, w.C, nx, ny, B, cp);
+                        CKL();
+                    }
+                } else {
+                    for (int k = 0; k < OCC_MAX_ITERATIONS_CHI; k++) {
+                        k_occ_chi_eta<<<gB, kBlock2d, 0, st>>>(w.ctl, chi, w.g, w.ETA, nx, ny, B, cp);
+                        CKL();
+                        k_occ_chi_update<<<gB, kBlock2d, 0, st>>>(w.ctl, chi, w.g, w.ETA, w.C, nx, ny, B, cp);
+                        CKL();
+                    }
                 }
             }
             {
@@ -628,6 +641,7 @@ int occ_create(int device, occ_ctx **out)
     if ((e = cudaMallocHost(&ctx->h_n_active, sizeof(int))) != cudaSuccess) return fail("cudaMallocHost", e);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *s = getenv("OCC_MAX_BATCH")) ctx->max_batch = std::max(1, atoi(s));
+    if (const char *s = getenv("OCC_CHI_FUSED")) ctx->chi_fused = s[0] != '0';
     *out = ctx;
     return OCC_OK;
 }

@@ -110,6 +110,8 @@ struct tvl1_ctx {
     bool tail_tb = true;                     // temporal blocking in the tail even where the full batch runs without (TVL1_TAIL_TB)
     long long tb_max_pixels = 192ll << 20;   // ... which serves lock-step batches up to this many pixels per level
     int force_cluster = 0;                   // tests: force this cluster size where it fits
+    bool shared_gpu = false;                 // set while several lanes run chunks concurrently on this GPU
+    bool tb_when_shared = false;             // TVL1_TB_SHARED=1: temporal blocking also then (A/B)
     bool capturing = false;
     SolveGraph sg;
     SolveGraph sg_alt;                       // solve graph of ws_alt
@@ -133,7 +135,7 @@ struct tvl1_ctx {
     static constexpr int kMaxLanes = 4;
     tvl1_ctx *sib[kMaxLanes - 1] = { nullptr, nullptr, nullptr };   // sibling contexts (extra lanes, same GPU)
     int host_lanes = 4;                      // lanes used by the host-buffer batch entry points
-    int short_div = 4;                       // host-buffer batches: first / last chunks of max_batch / short_div pairs
+    int short_div = 2;                       // host-buffer batches: first / last chunks of max_batch / short_div pairs
                                              // (TVL1_SHORT_DIV, 0 or 1 = all chunks equal)
     int dev_lanes = 2;                       // lanes used by the device-buffer batch entry point
     bool is_sibling = false;
@@ -562,7 +564,13 @@ bool tb_usable(tvl1_ctx *ctx, const Level &l, int B)
     static bool attr_done[64] = { false };      // function attributes are per device
     bool &attr = attr_done[ctx->device & 63];
     if (!ctx->use_tb || !tensor_map_encoder()) return false;
-    if ((long long) B * l.nx * l.ny > ctx->tb_max_pixels) return false;     // big batches: empty launches cost more than they save
+    // The blocked kernel trades HBM traffic for instruction issue and shared-memory wavefronts: it wins
+    // while the launch leaves the GPU under-used (single images, small batches), and loses to the
+    // streaming kernel once the SMs are saturated anyway -- by a big lock-step batch, or by the other
+    // lanes of a chunked batch (measured, profiles/r2g_chunks.txt: 16 pairs x 4 lanes 178.9 -> 165.7 ms,
+    // 64 x 4 lanes 163.7 -> 157.0 ms per 256 x 1080p without it).
+    if (ctx->shared_gpu && !ctx->tb_when_shared) return false;
+    if ((long long) B * l.nx * l.ny > ctx->tb_max_pixels) return false;
     if (l.nx < kTbBW || l.ny < kTbBH) return false;
     if (!attr) {
         if (cudaFuncSetAttribute(k_iterate_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTbSmemBytes) != cudaSuccess) {
@@ -870,7 +878,8 @@ int replay_graph(tvl1_ctx *ctx, SolveGraph &sg, const tvl1_params &prm, bool mul
 int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multiscale)
 {
     if (!ctx->use_graph) return enqueue_coarse_to_fine(ctx, B, prm, multiscale);
-    return replay_graph(ctx, ctx->sg, prm, multiscale, 0,
+    // (the kernel choice depends on whether other lanes share the GPU: tb_usable)
+    return replay_graph(ctx, ctx->sg, prm, multiscale, ctx->shared_gpu ? 1 : 0,
                         [&]() { return enqueue_coarse_to_fine(ctx, B, prm, multiscale); });
 }
 
@@ -1220,7 +1229,7 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
         reset_stats(sb);
         lanes[l] = sb;
     }
-    for (int l = 0; l < nlanes; l++) lanes[l]->blocking_wait = nlanes > 1;
+    for (int l = 0; l < nlanes; l++) lanes[l]->blocking_wait = lanes[l]->shared_gpu = nlanes > 1;
     int rcs[tvl1_ctx::kMaxLanes] = { TVL1_OK, TVL1_OK, TVL1_OK, TVL1_OK };
     std::atomic<int> next{0};
     auto work = [&](int l) {
@@ -1253,7 +1262,7 @@ void chunk_schedule(const tvl1_ctx *ctx, int npairs, int Bmax, int lanes, std::v
     const int nlanes = std::max(1, std::min(lanes, (int) tvl1_ctx::kMaxLanes));
     int first = 0;
     auto push = [&](int b) { out.emplace_back(first, b); first += b; };
-    if (small >= 1 && npairs >= 2 * nlanes * small + 2 * nlanes * Bmax) {
+    if (small >= 1 && npairs >= 2 * nlanes * small + nlanes * Bmax) {
         for (int l = 0; l < nlanes; l++) push(small);
         int rest = npairs - first - nlanes * small;
         while (rest >= Bmax) { push(Bmax); rest -= Bmax; }
@@ -1800,6 +1809,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *tp = std::getenv("TVL1_TAIL_PAIRS")) ctx->tail_pairs = std::max(0, std::atoi(tp));
     if (const char *tc = std::getenv("TVL1_TAIL_SLOT_CTAS")) ctx->tail_slot_ctas = std::max(1, std::atoi(tc));
     if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
+    if (const char *ts = std::getenv("TVL1_TB_SHARED")) ctx->tb_when_shared = ts[0] == '1';
     if (const char *sd = std::getenv("TVL1_SHORT_DIV")) ctx->short_div = std::max(0, std::atoi(sd));
     if (const char *mp = std::getenv("TVL1_TB_MAX_MPIX")) ctx->tb_max_pixels = std::max(0ll, std::atoll(mp)) << 20;
     *out = ctx;
