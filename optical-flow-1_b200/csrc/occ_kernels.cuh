@@ -270,6 +270,11 @@ __global__ void __launch_bounds__(256) k_occ_rof_alfa(const TripleCtl *__restric
     AL[q * N + c] = sqrt(x * x + y * y) / (lambda * g[b * N + c]);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 // One cell of the Gauss-Seidel pass: re-solves the 2x2 / 3x3 / 4x4 system of the cell's own sides with
 // relaxation omega (corner :206-247 / :304-331 / ..., edge :250-301 / :334-383 / ..., interior :385-482).
 // pS / pE are read and written through ordinary (coherent) accesses: other threads of the CTA wrote the
@@ -381,11 +386,27 @@ __global__ void __launch_bounds__(1024) k_occ_rof_gs(const TripleCtl *__restrict
     double *pS = P + ((size_t) (2 * k) * B + b) * N, *pE = P + ((size_t) (2 * k + 1) * B + b) * N;
     const double *f = F + q * N, *al = AL + q * N;
     const int steps = 2 * (ny - 1) + nx;
+    // The pass is a chain of dependent steps, so a step must not wait for DRAM: what the cell kPf columns
+    // ahead will read of f, alfa (read-only) and of the sides nobody has touched yet in this sweep (its own
+    // and the row below) is pulled into L2 now.  Sectors hold four doubles: one request per array and row
+    // every fourth column.
+    constexpr int kPf = 8;
     for (int t = 0; t < steps; t++) {
         for (int i = threadIdx.x; i < ny; i += blockDim.x) {
             const int j = t - 2 * i;
             if (j < 0) break;
-            if (j < nx) rof_cell(i, j, nx, ny, pS, pE, f, al, omega);
+            if (j < nx) {
+                const int jp = j + kPf;
+                if ((j & 3) == 0 && jp < nx) {
+                    const int c = i * nx + jp;
+                    prefetch_l2(f + c);
+                    prefetch_l2(al + c);
+                    prefetch_l2(pS + c);
+                    prefetch_l2(pE + c);
+                    if (i + 1 < ny) { prefetch_l2(f + c + nx); prefetch_l2(pS + c + nx); prefetch_l2(pE + c + nx); }
+                }
+                rof_cell(i, j, nx, ny, pS, pE, f, al, omega);
+            }
         }
         __syncthreads();
     }

@@ -371,6 +371,124 @@ k_gauss_march(const float *__restrict__ in, int in_pitch, size_t in_stride, floa
     }
 }
 
+// Same marching blur with the row-pass inputs shared through warp shuffles (round 2).  A lane loads only
+// ITS OWN 4*D input columns of a row (D aligned float4 loads), normalises them once, and takes the R
+// columns to its left and the R-D+1 to its right from its lane neighbours: one load and -- on the
+// normalising pass -- one IEEE division per input element instead of three (k_gauss_march reads and
+// normalises the 3D+2R+1 columns behind its four outputs itself, so neighbouring lanes repeat each
+// other's work).  Lanes 0 and 31 of a warp only load (their outputs belong to the neighbouring warps): a
+// warp produces 30 x 4 output columns.  Same boundary rule, same summation order, same bits.
+// Requires R <= 4*D and R-D+1 <= 4*D (the default windows: D=1,R=4 and D=2,R=5).
+template <int D, int R>
+__global__ void __launch_bounds__(128)
+k_gauss_shfl(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__restrict__ out,
+             int out_pitch, size_t out_stride, int nx, int ny, int onx, int ony, const GaussTaps taps,
+             const unsigned int *__restrict__ mm, int B)
+{
+    constexpr int S = 32;                         // output rows per strip
+    constexpr int W = 2 * R + 1;                  // window of row-pass results
+    constexpr int OWN = 4 * D;                    // input columns a lane loads
+    constexpr int NR = R - D + 1;                 // columns taken from the right neighbour
+    static_assert(R <= OWN && NR <= OWN && NR >= 0, "window does not fit the neighbours' blocks");
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int z = blockIdx.z;
+    const int grp = blockIdx.x * 30 + lane - 1;   // column group of this lane (outputs 4*grp .. 4*grp+3)
+    const int ox0 = grp * 4;
+    const int oy0 = (blockIdx.y * 4 + warp) * S;
+    if (oy0 >= ony || blockIdx.x * 120 >= onx) return;          // warp-uniform
+    const int oy1 = min(oy0 + S, ony);
+    const float *src = in + (size_t) z * in_stride;
+    float *dst = out + (size_t) z * out_stride;
+    const int ix0 = grp * OWN;                    // first own input column (may be < 0 or >= nx: reflected)
+    const bool fast = ix0 >= 0 && ix0 + OWN <= nx && (in_pitch & 3) == 0 &&
+                      ((reinterpret_cast<size_t>(src) & 15) == 0);
+    const bool writer = lane >= 1 && lane <= 30 && ox0 < onx;
+
+    float w[R + 1];
+#pragma unroll
+    for (int i = 0; i <= R; i++) w[i] = taps.w[i];
+    float mn = 0.f, den = 1.f;
+    bool norm = false;
+    if (mm) {
+        mn = ord2f(mm[2 * (z % B)]);
+        den = ord2f(mm[2 * (z % B) + 1]) - mn;
+        norm = den > 0.f;
+    }
+
+    float win[W][4];
+#pragma unroll
+    for (int u = 0; u < W; u++) win[u][0] = win[u][1] = win[u][2] = win[u][3] = 0.f;
+
+    const int iy_first = oy0 * D - R, iy_last = (oy1 - 1) * D + R;
+    for (int base = iy_first; base <= iy_last; base += W) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            const int iy = base + u;
+            if (iy > iy_last) break;
+            int gy = iy < 0 ? -iy : (iy >= ny ? 2 * ny - 1 - iy : iy);
+            gy = clampi(gy, 0, ny - 1);
+            const float *row = src + (size_t) gy * in_pitch;
+            // v[R .. R+OWN) = own columns, v[0 .. R) from the left neighbour, v[R+OWN .. R+OWN+NR) from the right
+            float v[R + OWN + NR];
+            if (fast) {
+#pragma unroll
+                for (int q = 0; q < D; q++) {
+                    const float4 t = ldg4(row + ix0 + 4 * q);
+                    v[R + 4 * q] = t.x; v[R + 4 * q + 1] = t.y; v[R + 4 * q + 2] = t.z; v[R + 4 * q + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < OWN; k++) {
+                    int gx = ix0 + k;
+                    gx = gx < 0 ? -gx : (gx >= nx ? 2 * nx - 1 - gx : gx);
+                    v[R + k] = __ldg(row + clampi(gx, 0, nx - 1));
+                }
+            }
+            if (norm) {
+#pragma unroll
+                for (int k = 0; k < OWN; k++) v[R + k] = normalize_px(v[R + k], mn, den);
+            }
+#pragma unroll
+            for (int m = 0; m < R; m++) v[m] = __shfl_up_sync(0xffffffffu, v[R + OWN - R + m], 1);
+#pragma unroll
+            for (int m = 0; m < NR; m++) v[R + OWN + m] = __shfl_down_sync(0xffffffffu, v[R + m], 1);
+            // row pass at the four output columns (window slot u)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = R + k * D;
+                float sum = w[0] * v[c];
+#pragma unroll
+                for (int j = 1; j <= R; j++) sum += w[j] * (v[c - j] + v[c + j]);
+                win[u][k] = sum;
+            }
+            // the window now ends at input row iy: it is centred on row iy - R
+            const int cy = iy - R;
+            if (cy >= oy0 * D && (cy % D) == 0) {
+                const int oy = cy / D;
+                if (oy < oy1 && writer) {
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float sum = w[0] * win[(u + W - R) % W][k];
+#pragma unroll
+                        for (int j = 1; j <= R; j++)
+                            sum += w[j] * (win[(u + W - R - j) % W][k] + win[(u + W - R + j) % W][k]);
+                        o[k] = sum;
+                    }
+                    float *orow = dst + (size_t) oy * out_pitch + ox0;
+                    if (ox0 + 3 < onx && (out_pitch & 3) == 0 && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+                        st4(orow, make_float4(o[0], o[1], o[2], o[3]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (ox0 + k < onx) orow[k] = o[k];
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Keys cubic through v0..v3 at offset t from v1: src/bicubic_interpolation.cpp:108-123.
 __device__ __forceinline__ float cubic_cell(float v0, float v1, float v2, float v3, float t)
 {
@@ -443,6 +561,7 @@ k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, si
                float scale, int row_begin, int row_end)
 {
     __shared__ float s_c[2][kZiCH][kZiCW];
+    __shared__ float s_h[2][kZiCH][kZiTW];          // rows of the footprint interpolated to the fine columns
     const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
     const int b = blockIdx.z;
     const int cur = ctl[b].cur;
@@ -450,9 +569,14 @@ k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, si
     float *dst = state + (size_t) (cur ^ 1) * set_stride + (size_t) b * plane0;
     const int X0 = blockIdx.x * kZiTW, Y0 = row_begin + blockIdx.y * kZiTH;
     const int X1 = min(X0 + kZiTW, fine.nx) - 1, Y1 = min(Y0 + kZiTH, row_end) - 1;
+    // sample coordinate j1 / f in fp64 as the reference forms it; for f == 2 (every level pair of even size
+    // at zfactor 0.5) the product with 0.5 is the same number without the division
+    const bool hx = fx == 2.0, hy = fy == 2.0;
+    auto pos_x = [&](int j1) { return hx ? j1 * 0.5 : j1 / fx; };
+    auto pos_y = [&](int i1) { return hy ? i1 * 0.5 : i1 / fy; };
     // coarse footprint: taps x-1 .. x+2 around x = (int)(j1 / fx), monotone in j1
-    const int xlo = (int) (X0 / fx) - 1, xhi = (int) (X1 / fx) + 2;
-    const int ylo = (int) (Y0 / fy) - 1, yhi = (int) (Y1 / fy) + 2;
+    const int xlo = (int) pos_x(X0) - 1, xhi = (int) pos_x(X1) + 2;
+    const int ylo = (int) pos_y(Y0) - 1, yhi = (int) pos_y(Y1) + 2;
     const int cw = xhi - xlo + 1, ch = yhi - ylo + 1;
     const bool staged = (cw <= kZiCW) && (ch <= kZiCH);   // always true when fx, fy >= 1
     if (staged) {
@@ -480,19 +604,33 @@ k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, si
         return;
     }
     // The sample grid is separable: a thread's four pixels share two column positions and two row
-    // positions; base indices and fractions come from the reference's fp64 division, the cubic is
-    // applied as Keys weights (same polynomial as cubic_cell, one set per column / row).
+    // positions; base indices and fractions come from the reference's fp64 coordinate, the cubic is
+    // applied as Keys weights (same polynomial as cubic_cell, one set per column / row).  Round 2: the
+    // horizontal interpolation of a footprint row is formed ONCE per fine column (s_h) instead of once per
+    // fine pixel and tap row -- the same products and sums in the same order, 2.4x fewer shared-memory loads.
     int cx[2], cy[2];
     float wx[2][4], wy[2][4];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const double j2 = (X0 + tx + 32 * k) / fx, i2 = (Y0 + ty + 8 * k) / fy;
+        const double j2 = pos_x(X0 + tx + 32 * k), i2 = pos_y(Y0 + ty + 8 * k);
         const int x = clampi((int) j2, 0, coarse.nx - 1), y = clampi((int) i2, 0, coarse.ny - 1);
         keys_weights((float) (j2 - x), wx[k]);
         keys_weights((float) (i2 - y), wy[k]);
-        cx[k] = x - 1 - xlo;
-        cy[k] = y - 1 - ylo;
+        cx[k] = min(x - 1 - xlo, kZiCW - 4);         // (columns beyond the image: never stored)
+        cy[k] = min(y - 1 - ylo, kZiCH - 4);
     }
+    for (int ly = ty; ly < ch; ly += 8) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+#pragma unroll
+            for (int comp = 0; comp < 2; comp++) {
+                const float *row = &s_c[comp][ly][cx[k]];
+                s_h[comp][ly][tx + 32 * k] =
+                    fmaf(wx[k][3], row[3], fmaf(wx[k][2], row[2], fmaf(wx[k][1], row[1], wx[k][0] * row[0])));
+            }
+        }
+    }
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int kx = q & 1, ky = q >> 1;
@@ -503,10 +641,7 @@ k_zoom_in_flow(float *__restrict__ state, size_t plane0, size_t field_stride, si
         for (int comp = 0; comp < 2; comp++) {
             float acc = 0.f;
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const float *row = &s_c[comp][cy[ky] + r][cx[kx]];
-                acc += wy[ky][r] * (wx[kx][0] * row[0] + wx[kx][1] * row[1] + wx[kx][2] * row[2] + wx[kx][3] * row[3]);
-            }
+            for (int r = 0; r < 4; r++) acc = fmaf(wy[ky][r], s_h[comp][cy[ky] + r][tx + 32 * kx], acc);
             dst[(size_t) comp * field_stride + o] = acc * scale;
         }
     }

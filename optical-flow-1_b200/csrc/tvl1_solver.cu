@@ -102,6 +102,7 @@ struct tvl1_ctx {
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
     bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
+    bool gauss_shfl = true;                  // TVL1_GAUSS_SHFL=0: the marching blur that loads its own row inputs (A/B)
     bool warp_tma = true;                    // TVL1_WARP_TMA=0: stage the warp kernel's box with cp.async only
     int slot_ctas = 32768;                   // CTAs a full iteration launch should have at least (TVL1_SLOT_CTAS)
     int tail_pairs = 16;                     // lock-step batches: once this few pairs still iterate, the loop goes on
@@ -440,16 +441,24 @@ int launch_gauss(tvl1_ctx *ctx, int D, const float *in, int in_pitch, size_t in_
                                                                       out_stride, nx, ny, onx, ony, taps, mm, B)
 #define TVL1_GAUSS_MARCH(D_, R_) k_gauss_march<D_, R_><<<gm, dim3(32, 4), 0, st>>>(in, in_pitch, in_stride, out, \
                                                            out_pitch, out_stride, nx, ny, onx, ony, taps, mm, B)
+#define TVL1_GAUSS_SHFL(D_, R_) k_gauss_shfl<D_, R_><<<gs, dim3(32, 4), 0, st>>>(in, in_pitch, in_stride, out, \
+                                                           out_pitch, out_stride, nx, ny, onx, ony, taps, mm, B)
     const dim3 gm(ceil_div(onx, 128), ceil_div(ony, 128), nimg);   // marching kernel: 128 columns x 4 strips of 32 rows
+    const dim3 gs(ceil_div(onx, 120), ceil_div(ony, 128), nimg);   // ... with shuffled row inputs: 120 columns per warp
+    const bool shfl = ctx->gauss_shfl;
     if (D == 1) {
         dim3 g(ceil_div(onx, 64), ceil_div(ony, 32), nimg);
-        if (r == 4) TVL1_GAUSS_MARCH(1, 4); else if (r == 5) TVL1_GAUSS_MARCH(1, 5); else TVL1_GAUSS(1, 0);
+        if (r == 4) { if (shfl) TVL1_GAUSS_SHFL(1, 4); else TVL1_GAUSS_MARCH(1, 4); }
+        else if (r == 5) TVL1_GAUSS_MARCH(1, 5);
+        else TVL1_GAUSS(1, 0);
     } else {
         dim3 g(ceil_div(onx, 32), ceil_div(ony, 16), nimg);
-        if (r == 5) TVL1_GAUSS_MARCH(2, 5); else TVL1_GAUSS(2, 0);
+        if (r == 5) { if (shfl) TVL1_GAUSS_SHFL(2, 5); else TVL1_GAUSS_MARCH(2, 5); }
+        else TVL1_GAUSS(2, 0);
     }
 #undef TVL1_GAUSS
 #undef TVL1_GAUSS_MARCH
+#undef TVL1_GAUSS_SHFL
     CKL(ctx);
     return TVL1_OK;
 }
@@ -1804,6 +1813,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
+    if (const char *gs = std::getenv("TVL1_GAUSS_SHFL")) ctx->gauss_shfl = !(gs[0] == '0');
     if (const char *wt = std::getenv("TVL1_WARP_TMA")) ctx->warp_tma = !(wt[0] == '0');
     if (const char *sc = std::getenv("TVL1_SLOT_CTAS")) ctx->slot_ctas = std::max(1, std::atoi(sc));
     if (const char *tp = std::getenv("TVL1_TAIL_PAIRS")) ctx->tail_pairs = std::max(0, std::atoi(tp));

@@ -83,6 +83,28 @@ def test_zoom_out(gpu, oracle_f64, factor, shape):
     assert np.abs(got - ref).max() < 5e-4
 
 
+@pytest.mark.parametrize("shape", [(1080, 1920), (436, 1024), (55, 109), (47, 61), (70, 131), (33, 240), (130, 122)])
+def test_gaussian_kernel_variants_agree_bitwise(shape, monkeypatch):
+    """The marching blur with shuffled row inputs (k_gauss_shfl, the default) against the one that loads its
+    own inputs (k_gauss_march): blur, decimating blur (zoom_out at 0.5) and the normalising blur inside a
+    solve -- identical bits, at sizes with ragged last groups, odd widths and fewer columns than a warp."""
+    rs = np.random.RandomState(shape[0] + shape[1])
+    I = rs.uniform(0, 255, shape).astype(np.float32)
+    J = rs.uniform(10, 200, shape).astype(np.float32)
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TVL1_GAUSS_SHFL", flag)
+        g = pkg.TVL1(device=0)
+        res = [g.gaussian(I, _cases.SIGMA_PRE), g.zoom_out(I, 0.5)]
+        if shape[0] >= 47:
+            u1, u2, it, _ = g.Dual_TVL1_optic_flow_multiscale(I, J, nscales=2, warps=1, eps=0.05)
+            res += [u1, u2, it]
+        out.append(res)
+        g.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
 def test_zoom_in(gpu, oracle_f64):
     I = np.random.RandomState(5).uniform(-8, 8, (27, 35)).astype(np.float32)
     for (nxx, nyy) in [(70, 54), (71, 53), (69, 55), (50, 38)]:
