@@ -54,10 +54,11 @@ def parse():
     ap.add_argument("--max-batch", type=int, default=256, help="pairs advanced in lock-step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="batch1080p", choices=["batch1080p", "band4k", "band8k", "occ"],
+    ap.add_argument("--workload", default="batch1080p", choices=["batch1080p", "band4k", "band8k", "occ", "hs"],
                     help="batch1080p: BASELINE configs[2] (the headline); band4k / band8k: configs[3] / configs[4], "
                          "ONE pair split into row bands over the ranks (strong scaling); occ: the occlusion solver "
-                         "(SURVEY 8f-3) on a batch of 640x480 frame triples per rank")
+                         "(SURVEY 8f-3) on a batch of 640x480 frame triples per rank; hs: pyramidal Horn-Schunck (SURVEY 8f-4) on "
+                         "296 x 1080p pairs, one GPU (profiles/bench_hs.py, same JSON contract)")
     ap.add_argument("--triples", type=int, default=148, help="occ workload: frame triples per rank per step")
     ap.add_argument("--no-row-band", action="store_true",
                     help="skip the row_band leg that the batch1080p workload appends when N > 1")
@@ -900,6 +901,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "hs":
+        # the Horn-Schunck bench line lives in profiles/bench_hs.py (one GPU; the reference's sweep is only
+        # defined for one thread, so its CPU leg is the one-thread reference)
+        if rank == 0:
+            os.execv(sys.executable, [sys.executable, os.path.join(ROOT, "profiles", "bench_hs.py"), "--steps",
+                                      str(args.steps), "--warmup", str(args.warmup)]
+                     + (["--no-cpu"] if args.no_cpu_baseline else []))
+        return
     if args.workload == "occ":
         run_occ_reference(args, rank) if args.impl == "reference" else run_occ_workload(args, rank, local_rank, world)
     elif args.impl == "reference":
