@@ -549,7 +549,7 @@ def run_occ_workload(args, rank, local_rank, world):
             "config": {"workload": OCC_CASE["name"], "params": kw, "triples_per_rank_per_step": B,
                        "global_triples_per_step": B * world, "parallelism": "batch-sharded x%d, no collective" % world,
                        "l2": "state of one step (%.1f GB per rank) exceeds the 126 MB L2; no explicit flush"
-                             % (B * 47 * nx * ny * 8 / 1e9),
+                             % (B * 65 * nx * ny * 8 / 1e9),
                        "timed_region": "value: wall clock around the steps (the outer loop reads one counter per outer "
                                        "iteration back), max over ranks"},
             "clocks": clk,

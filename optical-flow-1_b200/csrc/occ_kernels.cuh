@@ -270,6 +270,42 @@ __global__ void __launch_bounds__(256) k_occ_rof_alfa(const TripleCtl *__restric
     AL[q * N + c] = sqrt(x * x + y * y) / (lambda * g[b * N + c]);
 }
 
+// The 4x4 system of an interior cell (:385-482) is eliminated with coefficients that depend on alfa only,
+// not on the sides: a, b, alf, gam, c and the three denominators.  They hold three of the seven divisions of
+// a cell and sit on no dependence chain, so they are formed here, one thread per cell, and the serial
+// Gauss-Seidel pass only reads them: K is [2B][N][kRofK] = a, b, alf, gam, c, b3 + gam + c (gam - 1),
+// b2 + gam, b1 - a, b0 (same expressions, same bits).  Border cells keep working from alfa.
+constexpr int kRofK = 9;
+
+__global__ void __launch_bounds__(256) k_occ_rof_coef(const TripleCtl *__restrict__ ctl, const double *__restrict__ AL,
+                                                      double *__restrict__ K, int nx, int ny, int B)
+{
+    const int q = blockIdx.z, bb = q % B;
+    if (ctl && !ctl[bb].active) return;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (j < 1 || i < 1 || j >= nx - 1 || i >= ny - 1) return;
+    const size_t N = (size_t) nx * ny;
+    const size_t c = (size_t) i * nx + j;
+    const double *al = AL + q * N;
+    const double b0 = -2 - al[c - 1], b1 = -2 - al[c - nx];
+    const double b2 = -2 - al[c], b3 = -2 - al[c];
+    const double a = 1 / b0;
+    const double b = -(b0 + 1) / (b0 * b1 - 1);
+    const double alf = 1 + a;
+    const double gam = -a + b * alf;
+    const double cc = (1 - gam) / (b2 + gam);
+    double *k = K + (q * N + c) * kRofK;
+    k[0] = a;
+    k[1] = b;
+    k[2] = alf;
+    k[3] = gam;
+    k[4] = cc;
+    k[5] = b3 + gam + cc * (gam - 1);
+    k[6] = b2 + gam;
+    k[7] = b1 - a;
+    k[8] = b0;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
@@ -280,14 +316,19 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 // pS / pE are read and written through ordinary (coherent) accesses: other threads of the CTA wrote the
 // values this cell needs at earlier wavefront steps.
 __device__ __forceinline__ void rof_cell(int i, int j, int nx, int ny, double *pS, double *pE,
-                                         const double *__restrict__ f, const double *__restrict__ al, double omega)
+                                         const double *__restrict__ f, const double *__restrict__ al,
+                                         const double *__restrict__ K, double omega)
 {
     const bool hasW = j > 0, hasN = i > 0, hasS = i < ny - 1, hasE = j < nx - 1;
+    const bool interior = hasW && hasN && hasS && hasE;
     const int c = i * nx + j;
 #define PS_(ii, jj) ((ii) < 0 ? 0.0 : pS[(ii) * nx + (jj)])
 #define PE_(ii, jj) ((jj) < 0 ? 0.0 : pE[(ii) * nx + (jj)])
-    const double b0 = hasW ? -2 - al[c - 1] : 0, b1 = hasN ? -2 - al[c - nx] : 0;
-    const double b2 = hasS ? -2 - al[c] : 0, b3 = hasE ? -2 - al[c] : 0;
+    double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    if (!interior) {
+        b0 = hasW ? -2 - al[c - 1] : 0; b1 = hasN ? -2 - al[c - nx] : 0;
+        b2 = hasS ? -2 - al[c] : 0; b3 = hasE ? -2 - al[c] : 0;
+    }
     double W = 0, N = 0, S = 0, E = 0;
     const bool n_edge = !hasN && hasW && hasE;
     const double fc = f[c];
@@ -316,21 +357,18 @@ __device__ __forceinline__ void rof_cell(int i, int j, int nx, int ny, double *p
     double *qW = pE + c - 1, *qN = pS + c - nx, *qS = pS + c, *qE = pE + c;
     double den;
 #define RELAX_(q, num) (*(q) = (1 - omega) * *(q) + omega * (num) / den)
-    if (hasW && hasN && hasS && hasE) {
-        const double a = 1 / b0;
-        const double b = -(b0 + 1) / (b0 * b1 - 1);
-        const double alf = 1 + a;
-        const double gam = -a + b * alf;
+    if (interior) {
+        const double *k = K + (size_t) c * kRofK;
+        const double a = k[0], b = k[1], alf = k[2], gam = k[3], cc = k[4];
         const double x = N + a * W;
         const double y = -a * W + b * x;
-        const double cc = (1 - gam) / (b2 + gam);
-        const double e = (1 - omega) * *qE + omega * (E + y + cc * (S + y)) / (b3 + gam + cc * (gam - 1));
+        const double e = (1 - omega) * *qE + omega * (E + y + cc * (S + y)) / k[5];
         *qE = e;
-        const double s = (1 - omega) * *qS + omega * (S + y + e * (1 - gam)) / (b2 + gam);
+        const double s = (1 - omega) * *qS + omega * (S + y + e * (1 - gam)) / k[6];
         *qS = s;
-        const double n = (1 - omega) * *qN + omega * (x - alf * (e + s)) / (b1 - a);
+        const double n = (1 - omega) * *qN + omega * (x - alf * (e + s)) / k[7];
         *qN = n;
-        *qW = (1 - omega) * *qW + omega * (W + n - s - e) / (b0);
+        *qW = (1 - omega) * *qW + omega * (W + n - s - e) / k[8];
     } else if (!hasN && !hasW) {
         den = b2 * b3 - 1;
         RELAX_(qS, S * b3 + E);
@@ -377,14 +415,14 @@ __device__ __forceinline__ void rof_cell(int i, int j, int nx, int ny, double *p
 // predecessors run at t - 1, both successors at t + 1, and the cells of one step -- (i, j) and
 // (i-1, j+2), ... -- touch disjoint sides.  Thread r owns rows r, r + blockDim.x, ...; one barrier per step.
 __global__ void __launch_bounds__(1024) k_occ_rof_gs(const TripleCtl *__restrict__ ctl, double *P,
-                                                 const double *__restrict__ F, const double *__restrict__ AL, int nx,
-                                                 int ny, int B, double omega)
+                                                 const double *__restrict__ F, const double *__restrict__ AL,
+                                                 const double *__restrict__ Kc, int nx, int ny, int B, double omega)
 {
     const int q = blockIdx.x, k = q / B, b = q % B;
     if (ctl && !ctl[b].active) return;
     const size_t N = (size_t) nx * ny;
     double *pS = P + ((size_t) (2 * k) * B + b) * N, *pE = P + ((size_t) (2 * k + 1) * B + b) * N;
-    const double *f = F + q * N, *al = AL + q * N;
+    const double *f = F + q * N, *al = AL + q * N, *K = Kc + q * N * kRofK;
     const int steps = 2 * (ny - 1) + nx;
     // The pass is a chain of dependent steps, so a step must not wait for DRAM: what the cell kPf columns
     // ahead will read of f, alfa (read-only) and of the sides nobody has touched yet in this sweep (its own
@@ -405,7 +443,8 @@ __global__ void __launch_bounds__(1024) k_occ_rof_gs(const TripleCtl *__restrict
                     prefetch_l2(pE + c);
                     if (i + 1 < ny) { prefetch_l2(f + c + nx); prefetch_l2(pS + c + nx); prefetch_l2(pE + c + nx); }
                 }
-                rof_cell(i, j, nx, ny, pS, pE, f, al, omega);
+                if (jp < nx) { prefetch_l2(K + (size_t) (i * nx + jp) * kRofK); prefetch_l2(K + (size_t) (i * nx + jp) * kRofK + 8); }
+                rof_cell(i, j, nx, ny, pS, pE, f, al, K, omega);
             }
         }
         __syncthreads();

@@ -41,7 +41,7 @@ struct Workspace {
     double *Ig = nullptr;             // [4][B][N]  I1x, I1y, I_1x, I_1y
     double *Wc = nullptr;             // [8][B][N]  I1wx, I1wy, I_1wx, I_1wy, rho1_c, rho3_c, grad1, grad3
     double *g = nullptr, *F = nullptr, *AL = nullptr, *P = nullptr, *ETA = nullptr, *Vfwd = nullptr,
-           *Vbck = nullptr, *C = nullptr, *Uprev = nullptr, *tmpU = nullptr;
+           *Vbck = nullptr, *C = nullptr, *Uprev = nullptr, *tmpU = nullptr, *K = nullptr;
     TripleCtl *ctl = nullptr;
     double *partials = nullptr;
     int parts = 0;
@@ -152,7 +152,7 @@ int ensure_workspace(occ_ctx *ctx, int nx, int ny, int nscales, double zfactor, 
     for (auto &l : w.lv) SN += l.N;
     const size_t N0 = w.lv[0].N, BN0 = (size_t) B * N0;
     const int n_im = filt_alias ? 3 : 4;
-    const size_t total = (size_t) B * SN * (n_im + 3) + BN0 * (4 + 8 + 1 + 2 + 2 + 4 + 2 + 2 + 2 + 5 + 2 + 2);
+    const size_t total = (size_t) B * SN * (n_im + 3) + BN0 * (4 + 8 + 1 + 2 + 2 + 4 + 2 + 2 + 2 + 5 + 2 + 2 + 2 * kRofK);
     CK(cudaMalloc(&w.pool, total * sizeof(double)));
     w.pool_doubles = total;
     double *p = w.pool;
@@ -178,6 +178,7 @@ int ensure_workspace(occ_ctx *ctx, int nx, int ny, int nscales, double zfactor, 
     w.C = take(5 * BN0);
     w.Uprev = take(2 * BN0);
     w.tmpU = take(2 * BN0);
+    w.K = take(2 * kRofK * BN0);
     w.parts = std::max(1, std::min(64, (int) (N0 / 4096)));
     CK(cudaMalloc(&w.ctl, sizeof(TripleCtl) * B));
     CK(cudaMalloc(&w.partials, sizeof(double) * B * w.parts));
@@ -275,12 +276,14 @@ int rof_threads(int ny) { return std::max(32, std::min(1024, ceil_div(ny, 32) * 
 
 // Scalar_ROF_BoxCellCentered on `planes` problems (2B inside the solver, 1 for the hook)
 int rof_box(occ_ctx *ctx, const TripleCtl *ctl, double *U, const double *F, double *P, const double *g, double *AL,
-            int nx, int ny, int B, int planes, double lambda, double omega, int niter)
+            double *K, int nx, int ny, int B, int planes, double lambda, double omega, int niter)
 {
     for (int it = 0; it < niter; it++) {
         k_occ_rof_alfa<<<grid2d(nx, ny, planes), kBlock2d, 0, ctx->stream>>>(ctl, U, g, AL, nx, ny, B, lambda);
         CKL();
-        k_occ_rof_gs<<<planes, rof_threads(ny), 0, ctx->stream>>>(ctl, P, F, AL, nx, ny, B, omega);
+        k_occ_rof_coef<<<grid2d(nx, ny, planes), kBlock2d, 0, ctx->stream>>>(ctl, AL, K, nx, ny, B);
+        CKL();
+        k_occ_rof_gs<<<planes, rof_threads(ny), 0, ctx->stream>>>(ctl, P, F, AL, K, nx, ny, B, omega);
         CKL();
         k_occ_rof_u<<<grid2d(nx, ny, planes), kBlock2d, 0, ctx->stream>>>(ctl, U, F, P, nx, ny, B, lambda);
         CKL();
@@ -360,7 +363,7 @@ int run_level(occ_ctx *ctx, int s, const occ_params &prm, int stat_base)
             }
             {
                 Scope sc(ctx, G_BOX);
-                TRY(rof_box(ctx, w.ctl, U, w.F, w.P, w.g, w.AL, nx, ny, B, 2 * B, prm.theta, OCC_OMEGA,
+                TRY(rof_box(ctx, w.ctl, U, w.F, w.P, w.g, w.AL, w.K, nx, ny, B, 2 * B, prm.theta, OCC_OMEGA,
                             OCC_MAX_ITERATIONS_U));
             }
             {
@@ -737,15 +740,15 @@ int occ_rof_box_f64(occ_ctx *ctx, double *u, const double *f, double *p1, double
     CK(cudaSetDevice(ctx->device));
     ctx->stats = occ_stats{};
     const size_t N = (size_t) nx * ny;
-    TRY(ensure_stage(ctx, 6 * N));
+    TRY(ensure_stage(ctx, (6 + kRofK) * N));
     cudaStream_t st = ctx->stream;
-    double *dU = ctx->stage, *dF = dU + N, *dP = dF + N, *dG = dP + 2 * N, *dAL = dG + N;
+    double *dU = ctx->stage, *dF = dU + N, *dP = dF + N, *dG = dP + 2 * N, *dAL = dG + N, *dK = dAL + N;
     CK(cudaMemcpyAsync(dU, u, N * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dF, f, N * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dP, p1, N * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dP + N, p2, N * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dG, g, N * sizeof(double), cudaMemcpyHostToDevice, st));
-    TRY(rof_box(ctx, nullptr, dU, dF, dP, dG, dAL, nx, ny, 1, 1, lambda, omega, niter));
+    TRY(rof_box(ctx, nullptr, dU, dF, dP, dG, dAL, dK, nx, ny, 1, 1, lambda, omega, niter));
     CK(cudaMemcpyAsync(u, dU, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(p1, dP, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(p2, dP + N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
