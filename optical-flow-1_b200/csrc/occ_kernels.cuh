@@ -270,40 +270,100 @@ __global__ void __launch_bounds__(256) k_occ_rof_alfa(const TripleCtl *__restric
     AL[q * N + c] = sqrt(x * x + y * y) / (lambda * g[b * N + c]);
 }
 
+// ---- wave layout ------------------------------------------------------------------------------------
+// The Gauss-Seidel pass below runs cell (i, j) at step t = 2i + j, thread = row.  In row-major planes the
+// cells of one step lie nx - 2 elements apart: every load of a warp touches 32 different sectors, and the
+// pass is bound by L1 sector throughput (ncu: ~1.5 us per step, prefetching changed nothing).  In the WAVE
+// layout   W[((j + 2i) mod nx) * ny + i]   the cells of a step are contiguous in i, and so are all their
+// neighbours ((i+di, j+dj) lives in wave column t + dj + 2di, row i + di): every access of a step is
+// coalesced.  j -> (j + 2i) mod nx is a permutation for fixed i, so a wave plane has exactly nx * ny
+// elements.  The dual variables stay in this layout for a whole pyramid level; f, alfa and the
+// coefficients are brought into it by 32 x 32 tile transposes.
+__device__ __forceinline__ int wmod(int x, int m)
+{
+    x %= m;
+    return x < 0 ? x + m : x;
+}
+
+// Tile transposes between row-major planes and the wave layout, planes [z][N]; a CTA moves a 32 x 32 tile of
+// (wave column c, row i): the row-major side is coalesced along j (= c - 2i mod nx, consecutive in c), the
+// wave side along i.
+template <bool TO_WAVE>
+__global__ void __launch_bounds__(256) k_occ_wave_transpose(const TripleCtl *__restrict__ ctl, const double *__restrict__ in,
+                                                            double *__restrict__ out, int nx, int ny, int B)
+{
+    __shared__ double tile[32][33];
+    const int z = blockIdx.z;
+    if (ctl && !ctl[z % B].active) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
+    const int c0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const size_t N = (size_t) nx * ny;
+    const double *src = in + z * N;
+    double *dst = out + z * N;
+    if (TO_WAVE) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = i0 + ty + 8 * r, c = c0 + tx;
+            if (i < ny && c < nx) tile[ty + 8 * r][tx] = src[(size_t) i * nx + wmod(c - 2 * i, nx)];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int c = c0 + ty + 8 * r, i = i0 + tx;
+            if (i < ny && c < nx) dst[(size_t) c * ny + i] = tile[tx][ty + 8 * r];
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int c = c0 + ty + 8 * r, i = i0 + tx;
+            if (i < ny && c < nx) tile[tx][ty + 8 * r] = src[(size_t) c * ny + i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = i0 + ty + 8 * r, c = c0 + tx;
+            if (i < ny && c < nx) dst[(size_t) i * nx + wmod(c - 2 * i, nx)] = tile[ty + 8 * r][tx];
+        }
+    }
+}
+
 // The 4x4 system of an interior cell (:385-482) is eliminated with coefficients that depend on alfa only,
 // not on the sides: a, b, alf, gam, c and the three denominators.  They hold three of the seven divisions of
 // a cell and sit on no dependence chain, so they are formed here, one thread per cell, and the serial
-// Gauss-Seidel pass only reads them: K is [2B][N][kRofK] = a, b, alf, gam, c, b3 + gam + c (gam - 1),
-// b2 + gam, b1 - a, b0 (same expressions, same bits).  Border cells keep working from alfa.
+// Gauss-Seidel pass only reads them: K is [2B][kRofK][N] in the wave layout = a, b, alf, gam, c,
+// b3 + gam + c (gam - 1), b2 + gam, b1 - a, b0 (same expressions, same bits).  Border cells keep working
+// from alfa.  ALW = alfa in the wave layout; thread (i, c): i along x, so every access is coalesced.
 constexpr int kRofK = 9;
 
-__global__ void __launch_bounds__(256) k_occ_rof_coef(const TripleCtl *__restrict__ ctl, const double *__restrict__ AL,
+__global__ void __launch_bounds__(256) k_occ_rof_coef(const TripleCtl *__restrict__ ctl, const double *__restrict__ ALW,
                                                       double *__restrict__ K, int nx, int ny, int B)
 {
     const int q = blockIdx.z, bb = q % B;
     if (ctl && !ctl[bb].active) return;
-    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
-    if (j < 1 || i < 1 || j >= nx - 1 || i >= ny - 1) return;
+    const int i = blockIdx.x * 32 + threadIdx.x, c = blockIdx.y * 8 + threadIdx.y;
+    if (i < 1 || i >= ny - 1 || c >= nx) return;
+    const int j = wmod(c - 2 * i, nx);
+    if (j < 1 || j >= nx - 1) return;
     const size_t N = (size_t) nx * ny;
-    const size_t c = (size_t) i * nx + j;
-    const double *al = AL + q * N;
-    const double b0 = -2 - al[c - 1], b1 = -2 - al[c - nx];
-    const double b2 = -2 - al[c], b3 = -2 - al[c];
+    const double *al = ALW + q * N;
+    const double alc = al[(size_t) c * ny + i];
+    const double b0 = -2 - al[(size_t) wmod(c - 1, nx) * ny + i], b1 = -2 - al[(size_t) wmod(c - 2, nx) * ny + i - 1];
+    const double b2 = -2 - alc, b3 = -2 - alc;
     const double a = 1 / b0;
     const double b = -(b0 + 1) / (b0 * b1 - 1);
     const double alf = 1 + a;
     const double gam = -a + b * alf;
     const double cc = (1 - gam) / (b2 + gam);
-    double *k = K + (q * N + c) * kRofK;
+    double *k = K + q * N * kRofK + (size_t) c * ny + i;
     k[0] = a;
-    k[1] = b;
-    k[2] = alf;
-    k[3] = gam;
-    k[4] = cc;
-    k[5] = b3 + gam + cc * (gam - 1);
-    k[6] = b2 + gam;
-    k[7] = b1 - a;
-    k[8] = b0;
+    k[N] = b;
+    k[2 * N] = alf;
+    k[3 * N] = gam;
+    k[4 * N] = cc;
+    k[5 * N] = b3 + gam + cc * (gam - 1);
+    k[6 * N] = b2 + gam;
+    k[7 * N] = b1 - a;
+    k[8 * N] = b0;
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p)
@@ -311,100 +371,133 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
+// How a cell of the Gauss-Seidel pass reaches the sides, f, alfa and the coefficients of a neighbour
+// (di rows down, dj columns right): row-major planes, or the wave layout with the step's column bases
+// cb[d + 4] = ((t + d) mod nx) * ny, d = -4 .. 2 (the same for every row of the step).
+struct RofRowMajor {
+    double *pS, *pE;
+    const double *f, *al;
+    int nx, c;
+    __device__ __forceinline__ double &ps(int di, int dj) const { return pS[c + di * nx + dj]; }
+    __device__ __forceinline__ double &pe(int di, int dj) const { return pE[c + di * nx + dj]; }
+    __device__ __forceinline__ double fv(int di, int dj) const { return f[c + di * nx + dj]; }
+    __device__ __forceinline__ double alv(int di, int dj) const { return al[c + di * nx + dj]; }
+    __device__ __forceinline__ double kv(int) const { return 0.0; }
+};
+
+struct RofWave {
+    double *pS, *pE;
+    const double *f, *al, *K;
+    size_t N;
+    int cb[7];
+    int i;
+    __device__ __forceinline__ double &ps(int di, int dj) const { return pS[cb[dj + 2 * di + 4] + i + di]; }
+    __device__ __forceinline__ double &pe(int di, int dj) const { return pE[cb[dj + 2 * di + 4] + i + di]; }
+    __device__ __forceinline__ double fv(int di, int dj) const { return f[cb[dj + 2 * di + 4] + i + di]; }
+    __device__ __forceinline__ double alv(int di, int dj) const { return al[cb[dj + 2 * di + 4] + i + di]; }
+    __device__ __forceinline__ double kv(int m) const { return K[m * N + cb[4] + i]; }
+};
+
 // One cell of the Gauss-Seidel pass: re-solves the 2x2 / 3x3 / 4x4 system of the cell's own sides with
 // relaxation omega (corner :206-247 / :304-331 / ..., edge :250-301 / :334-383 / ..., interior :385-482).
-// pS / pE are read and written through ordinary (coherent) accesses: other threads of the CTA wrote the
-// values this cell needs at earlier wavefront steps.
-__device__ __forceinline__ void rof_cell(int i, int j, int nx, int ny, double *pS, double *pE,
-                                         const double *__restrict__ f, const double *__restrict__ al,
-                                         const double *__restrict__ K, double omega)
+// The sides are read and written through ordinary (coherent) accesses: other threads of the CTA wrote the
+// values this cell needs at earlier wavefront steps.  USE_K: interior coefficients from k_occ_rof_coef.
+template <bool USE_K, class Acc>
+__device__ __forceinline__ void rof_cell(int i, int j, int nx, int ny, const Acc &A, double omega)
 {
     const bool hasW = j > 0, hasN = i > 0, hasS = i < ny - 1, hasE = j < nx - 1;
     const bool interior = hasW && hasN && hasS && hasE;
-    const int c = i * nx + j;
-#define PS_(ii, jj) ((ii) < 0 ? 0.0 : pS[(ii) * nx + (jj)])
-#define PE_(ii, jj) ((jj) < 0 ? 0.0 : pE[(ii) * nx + (jj)])
     double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    if (!interior) {
-        b0 = hasW ? -2 - al[c - 1] : 0; b1 = hasN ? -2 - al[c - nx] : 0;
-        b2 = hasS ? -2 - al[c] : 0; b3 = hasE ? -2 - al[c] : 0;
+    if (!(USE_K && interior)) {
+        b0 = hasW ? -2 - A.alv(0, -1) : 0; b1 = hasN ? -2 - A.alv(-1, 0) : 0;
+        b2 = hasS ? -2 - A.alv(0, 0) : 0; b3 = hasE ? -2 - A.alv(0, 0) : 0;
     }
     double W = 0, N = 0, S = 0, E = 0;
     const bool n_edge = !hasN && hasW && hasE;
-    const double fc = f[c];
+    const double fc = A.fv(0, 0);
     if (hasW) {
-        const double jm3 = PE_(i, j - 2), ip1_jm2 = pS[c - 1], im1_jm2 = PS_(i - 1, j - 1);
-        const double Fw = fc - f[c - 1];
+        const double jm3 = j >= 2 ? A.pe(0, -2) : 0.0, ip1_jm2 = A.ps(0, -1), im1_jm2 = hasN ? A.ps(-1, -1) : 0.0;
+        const double Fw = fc - A.fv(0, -1);
         W = n_edge ? -Fw - jm3 + ip1_jm2 - im1_jm2 : -jm3 + ip1_jm2 - im1_jm2 - Fw;
     }
     if (hasN) {
-        const double im3 = PS_(i - 2, j), im2_jp1 = pE[c - nx], im2_jm1 = PE_(i - 1, j - 1);
-        const double Fn = fc - f[c - nx];
+        const double im3 = i >= 2 ? A.ps(-2, 0) : 0.0, im2_jp1 = A.pe(-1, 0), im2_jm1 = hasW ? A.pe(-1, -1) : 0.0;
+        const double Fn = fc - A.fv(-1, 0);
         N = -im3 + im2_jp1 - im2_jm1 - Fn;
     }
     if (hasS) {
-        const double ip3 = pS[c + nx], ip2_jp1 = pE[c + nx], ip2_jm1 = PE_(i + 1, j - 1);
-        const double Fs = f[c + nx] - fc;
+        const double ip3 = A.ps(1, 0), ip2_jp1 = A.pe(1, 0), ip2_jm1 = hasW ? A.pe(1, -1) : 0.0;
+        const double Fs = A.fv(1, 0) - fc;
         S = n_edge ? -Fs - ip3 - ip2_jp1 + ip2_jm1 : -ip3 - ip2_jp1 + ip2_jm1 - Fs;
     }
     if (hasE) {
-        const double jp3 = pE[c + 1], ip1_jp2 = pS[c + 1], im1_jp2 = PS_(i - 1, j + 1);
-        const double Fe = f[c + 1] - fc;
+        const double jp3 = A.pe(0, 1), ip1_jp2 = A.ps(0, 1), im1_jp2 = hasN ? A.ps(-1, 1) : 0.0;
+        const double Fe = A.fv(0, 1) - fc;
         E = n_edge ? -Fe - jp3 - ip1_jp2 + im1_jp2 : -jp3 - ip1_jp2 + im1_jp2 - Fe;
     }
-#undef PS_
-#undef PE_
-    double *qW = pE + c - 1, *qN = pS + c - nx, *qS = pS + c, *qE = pE + c;
     double den;
-#define RELAX_(q, num) (*(q) = (1 - omega) * *(q) + omega * (num) / den)
+#define RELAX_(q, num) ((q) = (1 - omega) * (q) + omega * (num) / den)
     if (interior) {
-        const double *k = K + (size_t) c * kRofK;
-        const double a = k[0], b = k[1], alf = k[2], gam = k[3], cc = k[4];
+        double a, b, alf, gam, cc, dE, dS, dN, dW;
+        if (USE_K) {
+            a = A.kv(0); b = A.kv(1); alf = A.kv(2); gam = A.kv(3); cc = A.kv(4);
+            dE = A.kv(5); dS = A.kv(6); dN = A.kv(7); dW = A.kv(8);
+        } else {
+            a = 1 / b0;
+            b = -(b0 + 1) / (b0 * b1 - 1);
+            alf = 1 + a;
+            gam = -a + b * alf;
+            cc = (1 - gam) / (b2 + gam);
+            dE = b3 + gam + cc * (gam - 1);
+            dS = b2 + gam;
+            dN = b1 - a;
+            dW = b0;
+        }
         const double x = N + a * W;
         const double y = -a * W + b * x;
-        const double e = (1 - omega) * *qE + omega * (E + y + cc * (S + y)) / k[5];
-        *qE = e;
-        const double s = (1 - omega) * *qS + omega * (S + y + e * (1 - gam)) / k[6];
-        *qS = s;
-        const double n = (1 - omega) * *qN + omega * (x - alf * (e + s)) / k[7];
-        *qN = n;
-        *qW = (1 - omega) * *qW + omega * (W + n - s - e) / k[8];
+        const double e = (1 - omega) * A.pe(0, 0) + omega * (E + y + cc * (S + y)) / dE;
+        A.pe(0, 0) = e;
+        const double s = (1 - omega) * A.ps(0, 0) + omega * (S + y + e * (1 - gam)) / dS;
+        A.ps(0, 0) = s;
+        const double n = (1 - omega) * A.ps(-1, 0) + omega * (x - alf * (e + s)) / dN;
+        A.ps(-1, 0) = n;
+        A.pe(0, -1) = (1 - omega) * A.pe(0, -1) + omega * (W + n - s - e) / dW;
     } else if (!hasN && !hasW) {
         den = b2 * b3 - 1;
-        RELAX_(qS, S * b3 + E);
-        RELAX_(qE, E * b2 + S);
+        RELAX_(A.ps(0, 0), S * b3 + E);
+        RELAX_(A.pe(0, 0), E * b2 + S);
     } else if (!hasN && !hasE) {
         den = b0 * b2 - 1;
-        RELAX_(qW, W * b2 - S);
-        RELAX_(qS, S * b0 - W);
+        RELAX_(A.pe(0, -1), W * b2 - S);
+        RELAX_(A.ps(0, 0), S * b0 - W);
     } else if (!hasN) {
         den = b0 * b2 * b3 - b0 - b2 - b3 - 2;
-        RELAX_(qW, W * b2 * b3 - E * b2 - S * b3 - W - E - S);
-        RELAX_(qS, S * b0 * b3 - W * b3 + E * b0 - W + E - S);
-        RELAX_(qE, E * b0 * b2 - W * b2 + S * b0 - W - E + S);
+        RELAX_(A.pe(0, -1), W * b2 * b3 - E * b2 - S * b3 - W - E - S);
+        RELAX_(A.ps(0, 0), S * b0 * b3 - W * b3 + E * b0 - W + E - S);
+        RELAX_(A.pe(0, 0), E * b0 * b2 - W * b2 + S * b0 - W - E + S);
     } else if (!hasS && !hasW) {
         den = b3 * b1 - 1;
-        RELAX_(qN, b3 * N - E);
-        RELAX_(qE, b1 * E - N);
+        RELAX_(A.ps(-1, 0), b3 * N - E);
+        RELAX_(A.pe(0, 0), b1 * E - N);
     } else if (!hasS && !hasE) {
         den = b0 * b1 - 1;
-        RELAX_(qW, W * b1 + N);
-        RELAX_(qN, N * b0 + W);
+        RELAX_(A.pe(0, -1), W * b1 + N);
+        RELAX_(A.ps(-1, 0), N * b0 + W);
     } else if (!hasS) {
         den = b0 * b1 * b3 - b0 - b1 - b3 - 2;
-        RELAX_(qW, W * b1 * b3 - E + N - E * b1 - W + N * b3);
-        RELAX_(qN, N * b0 * b3 + W - E - N - E * b0 + W * b3);
-        RELAX_(qE, E * b0 * b1 - N - W - W * b1 - N * b0 - E);
+        RELAX_(A.pe(0, -1), W * b1 * b3 - E + N - E * b1 - W + N * b3);
+        RELAX_(A.ps(-1, 0), N * b0 * b3 + W - E - N - E * b0 + W * b3);
+        RELAX_(A.pe(0, 0), E * b0 * b1 - N - W - W * b1 - N * b0 - E);
     } else if (!hasW) {
         den = b1 * b2 * b3 - (b1 + b2 + b3) - 2;
-        RELAX_(qN, b2 * b3 * N - E * b2 - S * b3 - N - S - E);
-        RELAX_(qS, b1 * b3 * S + E * b1 - N * b3 - N - S + E);
-        RELAX_(qE, b1 * b2 * E - N * b2 + S * b1 - N + S - E);
+        RELAX_(A.ps(-1, 0), b2 * b3 * N - E * b2 - S * b3 - N - S - E);
+        RELAX_(A.ps(0, 0), b1 * b3 * S + E * b1 - N * b3 - N - S + E);
+        RELAX_(A.pe(0, 0), b1 * b2 * E - N * b2 + S * b1 - N + S - E);
     } else {
         den = (b0 * b1 * b2) + (-b0 - b1 - b2 - 2);
-        RELAX_(qW, W * b1 * b2 - S + N - S * b1 - W + N * b2);
-        RELAX_(qN, N * b0 * b2 + W - S - N - S * b0 + W * b2);
-        RELAX_(qS, S * b0 * b1 - N - W - W * b1 - N * b0 - S);
+        RELAX_(A.pe(0, -1), W * b1 * b2 - S + N - S * b1 - W + N * b2);
+        RELAX_(A.ps(-1, 0), N * b0 * b2 + W - S - N - S * b0 + W * b2);
+        RELAX_(A.ps(0, 0), S * b0 * b1 - N - W - W * b1 - N * b0 - S);
     }
 #undef RELAX_
 }
@@ -414,40 +507,88 @@ __device__ __forceinline__ void rof_cell(int i, int j, int nx, int ny, double *p
 // the OLD sides of (i, j+1), (i+1, j-1) and later cells.  Step t = 2i + j keeps exactly that: both
 // predecessors run at t - 1, both successors at t + 1, and the cells of one step -- (i, j) and
 // (i-1, j+2), ... -- touch disjoint sides.  Thread r owns rows r, r + blockDim.x, ...; one barrier per step.
+// Row-major planes (the A/B reference of the wave kernel below, OCC_GS_WAVE=0).
 __global__ void __launch_bounds__(1024) k_occ_rof_gs(const TripleCtl *__restrict__ ctl, double *P,
                                                  const double *__restrict__ F, const double *__restrict__ AL,
-                                                 const double *__restrict__ Kc, int nx, int ny, int B, double omega)
+                                                 int nx, int ny, int B, double omega)
 {
     const int q = blockIdx.x, k = q / B, b = q % B;
     if (ctl && !ctl[b].active) return;
     const size_t N = (size_t) nx * ny;
-    double *pS = P + ((size_t) (2 * k) * B + b) * N, *pE = P + ((size_t) (2 * k + 1) * B + b) * N;
-    const double *f = F + q * N, *al = AL + q * N, *K = Kc + q * N * kRofK;
+    RofRowMajor A;
+    A.pS = P + ((size_t) (2 * k) * B + b) * N;
+    A.pE = P + ((size_t) (2 * k + 1) * B + b) * N;
+    A.f = F + q * N;
+    A.al = AL + q * N;
+    A.nx = nx;
     const int steps = 2 * (ny - 1) + nx;
-    // The pass is a chain of dependent steps, so a step must not wait for DRAM: what the cell kPf columns
-    // ahead will read of f, alfa (read-only) and of the sides nobody has touched yet in this sweep (its own
-    // and the row below) is pulled into L2 now.  Sectors hold four doubles: one request per array and row
-    // every fourth column.
-    constexpr int kPf = 8;
     for (int t = 0; t < steps; t++) {
         for (int i = threadIdx.x; i < ny; i += blockDim.x) {
             const int j = t - 2 * i;
             if (j < 0) break;
             if (j < nx) {
-                const int jp = j + kPf;
-                if ((j & 3) == 0 && jp < nx) {
-                    const int c = i * nx + jp;
-                    prefetch_l2(f + c);
-                    prefetch_l2(al + c);
-                    prefetch_l2(pS + c);
-                    prefetch_l2(pE + c);
-                    if (i + 1 < ny) { prefetch_l2(f + c + nx); prefetch_l2(pS + c + nx); prefetch_l2(pE + c + nx); }
-                }
-                if (jp < nx) { prefetch_l2(K + (size_t) (i * nx + jp) * kRofK); prefetch_l2(K + (size_t) (i * nx + jp) * kRofK + 8); }
-                rof_cell(i, j, nx, ny, pS, pE, f, al, K, omega);
+                A.c = i * nx + j;
+                rof_cell<false>(i, j, nx, ny, A, omega);
             }
         }
         __syncthreads();
+    }
+}
+
+// The same pass on the wave layout (the default): P, FW, ALW, K are wave planes.  At step t every active
+// row works in wave column t mod nx, so the seven column bases a cell needs are the same for the whole CTA.
+// Rows whose row number is a multiple of four pull the sectors of the column kPf steps ahead into L2 (the
+// step is a chain of dependent operations: it must not wait for DRAM).
+template <bool USE_K>
+__global__ void __launch_bounds__(1024) k_occ_rof_gs_wave(const TripleCtl *__restrict__ ctl, double *P,
+                                                      const double *__restrict__ FW, const double *__restrict__ ALW,
+                                                      const double *__restrict__ Kc, int nx, int ny, int B, double omega)
+{
+    const int q = blockIdx.x, k = q / B, b = q % B;
+    if (ctl && !ctl[b].active) return;
+    constexpr int kPf = 6;
+    const size_t N = (size_t) nx * ny;
+    RofWave A;
+    A.pS = P + ((size_t) (2 * k) * B + b) * N;
+    A.pE = P + ((size_t) (2 * k + 1) * B + b) * N;
+    A.f = FW + q * N;
+    A.al = ALW + q * N;
+    A.K = Kc + q * N * kRofK;
+    A.N = N;
+    const int steps = 2 * (ny - 1) + nx;
+    int w = 0;                                      // t mod nx
+    for (int t = 0; t < steps; t++) {
+#pragma unroll
+        for (int d = -4; d <= 2; d++) {
+            int c = w + d;
+            c = c < 0 ? c + nx : (c >= nx ? c - nx : c);
+            if (nx < 4) c = wmod(w + d, nx);
+            A.cb[d + 4] = c * ny;
+        }
+        int cpf = w + kPf;
+        cpf = cpf >= nx ? wmod(cpf, nx) : cpf;
+        for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+            const int j = t - 2 * i;
+            if (j < 0) break;
+            if (j < nx) {
+                if ((i & 3) == 0 && j + kPf < nx) {
+                    const size_t o = (size_t) cpf * ny + i;
+                    prefetch_l2(A.pS + o);
+                    prefetch_l2(A.pE + o);
+                    prefetch_l2(A.f + o);
+                    if (USE_K) {
+#pragma unroll
+                        for (int m = 0; m < kRofK; m++) prefetch_l2(A.K + m * N + o);
+                    } else {
+                        prefetch_l2(A.al + o);
+                    }
+                }
+                A.i = i;
+                rof_cell<USE_K>(i, j, nx, ny, A, omega);
+            }
+        }
+        __syncthreads();
+        w = w + 1 == nx ? 0 : w + 1;
     }
 }
 

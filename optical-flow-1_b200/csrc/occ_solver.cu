@@ -41,7 +41,10 @@ struct Workspace {
     double *Ig = nullptr;             // [4][B][N]  I1x, I1y, I_1x, I_1y
     double *Wc = nullptr;             // [8][B][N]  I1wx, I1wy, I_1wx, I_1wy, rho1_c, rho3_c, grad1, grad3
     double *g = nullptr, *F = nullptr, *AL = nullptr, *P = nullptr, *ETA = nullptr, *Vfwd = nullptr,
-           *Vbck = nullptr, *C = nullptr, *Uprev = nullptr, *tmpU = nullptr, *K = nullptr;
+           *Vbck = nullptr, *C = nullptr, *Uprev = nullptr, *tmpU = nullptr;
+    // wave-layout side of the box relaxation: coefficients [2B][9][N], f and alfa [2B][N], and a row-major
+    // copy of the duals for the u update [4B][N] (P itself is kept in the wave layout, see rof_box)
+    double *K = nullptr, *FW = nullptr, *ALW = nullptr, *Pn = nullptr;
     TripleCtl *ctl = nullptr;
     double *partials = nullptr;
     int parts = 0;
@@ -61,6 +64,9 @@ struct occ_ctx {
     std::string err;
     bool profiling = false;
     int max_batch = 64;
+    bool gs_wave = true;             // OCC_GS_WAVE=0: Gauss-Seidel pass on row-major planes (A/B)
+    bool gs_coef = false;            // OCC_GS_COEF=1: interior coefficients from a parallel kernel (k_occ_rof_coef): three
+                                     // of seven divisions leave the serial pass, but their 72 B per cell cost more (A/B)
     bool chi_fused = true;           // OCC_CHI_FUSED=0: the two-kernel form of the occlusion-map iteration (A/B)
     int sm_count = 148;
     occ_stats stats{};
@@ -152,7 +158,7 @@ int ensure_workspace(occ_ctx *ctx, int nx, int ny, int nscales, double zfactor, 
     for (auto &l : w.lv) SN += l.N;
     const size_t N0 = w.lv[0].N, BN0 = (size_t) B * N0;
     const int n_im = filt_alias ? 3 : 4;
-    const size_t total = (size_t) B * SN * (n_im + 3) + BN0 * (4 + 8 + 1 + 2 + 2 + 4 + 2 + 2 + 2 + 5 + 2 + 2 + 2 * kRofK);
+    const size_t total = (size_t) B * SN * (n_im + 3) + BN0 * (4 + 8 + 1 + 2 + 2 + 4 + 2 + 2 + 2 + 5 + 2 + 2 + 2 * kRofK + 2 + 2 + 4);
     CK(cudaMalloc(&w.pool, total * sizeof(double)));
     w.pool_doubles = total;
     double *p = w.pool;
@@ -179,6 +185,9 @@ int ensure_workspace(occ_ctx *ctx, int nx, int ny, int nscales, double zfactor, 
     w.Uprev = take(2 * BN0);
     w.tmpU = take(2 * BN0);
     w.K = take(2 * kRofK * BN0);
+    w.FW = take(2 * BN0);
+    w.ALW = take(2 * BN0);
+    w.Pn = take(4 * BN0);
     w.parts = std::max(1, std::min(64, (int) (N0 / 4096)));
     CK(cudaMalloc(&w.ctl, sizeof(TripleCtl) * B));
     CK(cudaMalloc(&w.partials, sizeof(double) * B * w.parts));
@@ -274,19 +283,48 @@ int build_pyramid(occ_ctx *ctx, const double *const src[4])
 
 int rof_threads(int ny) { return std::max(32, std::min(1024, ceil_div(ny, 32) * 32)); }
 
-// Scalar_ROF_BoxCellCentered on `planes` problems (2B inside the solver, 1 for the hook)
-int rof_box(occ_ctx *ctx, const TripleCtl *ctl, double *U, const double *F, double *P, const double *g, double *AL,
-            double *K, int nx, int ny, int B, int planes, double lambda, double omega, int niter)
+struct RofBufs {
+    double *U, *P, *AL;            // row-major u [planes][N]; duals [2 planes][N] (wave layout if `wave`); alfa scratch
+    const double *F, *g;
+    double *K, *FW, *ALW, *Pn;     // wave mode only
+};
+
+// Scalar_ROF_BoxCellCentered on `planes` problems (2B inside the solver, 1 for the hook).  Wave mode (the
+// default): the duals live in the wave layout; per call f goes there once, per sweep alfa does, the
+// coefficient kernel and the Gauss-Seidel pass work there, and the u update reads a row-major copy.
+int rof_box(occ_ctx *ctx, const TripleCtl *ctl, const RofBufs &R, int nx, int ny, int B, int planes, double lambda,
+            double omega, int niter)
 {
+    cudaStream_t st = ctx->stream;
+    const dim3 gT(ceil_div(nx, 32), ceil_div(ny, 32), planes), gT2(gT.x, gT.y, 2 * planes);
+    if (ctx->gs_wave && niter > 0) {
+        k_occ_wave_transpose<true><<<gT, kBlock2d, 0, st>>>(ctl, R.F, R.FW, nx, ny, B);
+        CKL();
+    }
     for (int it = 0; it < niter; it++) {
-        k_occ_rof_alfa<<<grid2d(nx, ny, planes), kBlock2d, 0, ctx->stream>>>(ctl, U, g, AL, nx, ny, B, lambda);
+        k_occ_rof_alfa<<<grid2d(nx, ny, planes), kBlock2d, 0, st>>>(ctl, R.U, R.g, R.AL, nx, ny, B, lambda);
         CKL();
-        k_occ_rof_coef<<<grid2d(nx, ny, planes), kBlock2d, 0, ctx->stream>>>(ctl, AL, K, nx, ny, B);
-        CKL();
-        k_occ_rof_gs<<<planes, rof_threads(ny), 0, ctx->stream>>>(ctl, P, F, AL, K, nx, ny, B, omega);
-        CKL();
-        k_occ_rof_u<<<grid2d(nx, ny, planes), kBlock2d, 0, ctx->stream>>>(ctl, U, F, P, nx, ny, B, lambda);
-        CKL();
+        if (ctx->gs_wave) {
+            k_occ_wave_transpose<true><<<gT, kBlock2d, 0, st>>>(ctl, R.AL, R.ALW, nx, ny, B);
+            CKL();
+            if (ctx->gs_coef) {
+                k_occ_rof_coef<<<dim3(ceil_div(ny, 32), ceil_div(nx, 8), planes), kBlock2d, 0, st>>>(ctl, R.ALW, R.K, nx, ny, B);
+                CKL();
+                k_occ_rof_gs_wave<true><<<planes, rof_threads(ny), 0, st>>>(ctl, R.P, R.FW, R.ALW, R.K, nx, ny, B, omega);
+            } else {
+                k_occ_rof_gs_wave<false><<<planes, rof_threads(ny), 0, st>>>(ctl, R.P, R.FW, R.ALW, R.K, nx, ny, B, omega);
+            }
+            CKL();
+            k_occ_wave_transpose<false><<<gT2, kBlock2d, 0, st>>>(ctl, R.P, R.Pn, nx, ny, B);
+            CKL();
+            k_occ_rof_u<<<grid2d(nx, ny, planes), kBlock2d, 0, st>>>(ctl, R.U, R.F, R.Pn, nx, ny, B, lambda);
+            CKL();
+        } else {
+            k_occ_rof_gs<<<planes, rof_threads(ny), 0, st>>>(ctl, R.P, R.F, R.AL, nx, ny, B, omega);
+            CKL();
+            k_occ_rof_u<<<grid2d(nx, ny, planes), kBlock2d, 0, st>>>(ctl, R.U, R.F, R.P, nx, ny, B, lambda);
+            CKL();
+        }
         ctx->stats.box_sweeps++;
     }
     return OCC_OK;
@@ -363,8 +401,8 @@ int run_level(occ_ctx *ctx, int s, const occ_params &prm, int stat_base)
             }
             {
                 Scope sc(ctx, G_BOX);
-                TRY(rof_box(ctx, w.ctl, U, w.F, w.P, w.g, w.AL, w.K, nx, ny, B, 2 * B, prm.theta, OCC_OMEGA,
-                            OCC_MAX_ITERATIONS_U));
+                const RofBufs R = { U, w.P, w.AL, w.F, w.g, w.K, w.FW, w.ALW, w.Pn };
+                TRY(rof_box(ctx, w.ctl, R, nx, ny, B, 2 * B, prm.theta, OCC_OMEGA, OCC_MAX_ITERATIONS_U));
             }
             {
                 Scope sc(ctx, G_OTHER);
@@ -645,6 +683,8 @@ int occ_create(int device, occ_ctx **out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *s = getenv("OCC_MAX_BATCH")) ctx->max_batch = std::max(1, atoi(s));
     if (const char *s = getenv("OCC_CHI_FUSED")) ctx->chi_fused = s[0] != '0';
+    if (const char *s = getenv("OCC_GS_WAVE")) ctx->gs_wave = s[0] != '0';
+    if (const char *s = getenv("OCC_GS_COEF")) ctx->gs_coef = s[0] != '0';
     *out = ctx;
     return OCC_OK;
 }
@@ -740,18 +780,30 @@ int occ_rof_box_f64(occ_ctx *ctx, double *u, const double *f, double *p1, double
     CK(cudaSetDevice(ctx->device));
     ctx->stats = occ_stats{};
     const size_t N = (size_t) nx * ny;
-    TRY(ensure_stage(ctx, (6 + kRofK) * N));
+    TRY(ensure_stage(ctx, (12 + kRofK) * N));
     cudaStream_t st = ctx->stream;
-    double *dU = ctx->stage, *dF = dU + N, *dP = dF + N, *dG = dP + 2 * N, *dAL = dG + N, *dK = dAL + N;
+    double *dU = ctx->stage, *dF = dU + N, *dP = dF + N, *dG = dP + 2 * N, *dAL = dG + N, *dK = dAL + N,
+           *dFW = dK + kRofK * N, *dALW = dFW + N, *dPn = dALW + N, *dPin = dPn + 2 * N;
     CK(cudaMemcpyAsync(dU, u, N * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dF, f, N * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dP, p1, N * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dP + N, p2, N * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dG, g, N * sizeof(double), cudaMemcpyHostToDevice, st));
-    TRY(rof_box(ctx, nullptr, dU, dF, dP, dG, dAL, dK, nx, ny, 1, 1, lambda, omega, niter));
+    const dim3 gT2(ceil_div(nx, 32), ceil_div(ny, 32), 2);
+    double *dP0 = ctx->gs_wave ? dPin : dP;            // the caller's duals are row-major
+    CK(cudaMemcpyAsync(dP0, p1, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dP0 + N, p2, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (ctx->gs_wave) {
+        k_occ_wave_transpose<true><<<gT2, kBlock2d, 0, st>>>(nullptr, dPin, dP, nx, ny, 1);
+        CKL();
+    }
+    const RofBufs R = { dU, dP, dAL, dF, dG, dK, dFW, dALW, dPn };
+    TRY(rof_box(ctx, nullptr, R, nx, ny, 1, 1, lambda, omega, niter));
+    if (ctx->gs_wave) {
+        k_occ_wave_transpose<false><<<gT2, kBlock2d, 0, st>>>(nullptr, dP, dPin, nx, ny, 1);
+        CKL();
+    }
     CK(cudaMemcpyAsync(u, dU, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(p1, dP, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(p2, dP + N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p1, dP0, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p2, dP0 + N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return OCC_OK;
 }
