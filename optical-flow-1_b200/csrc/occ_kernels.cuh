@@ -816,6 +816,132 @@ __global__ void __launch_bounds__(256) k_occ_chi_fused(const TripleCtl *__restri
     }
 }
 
+// Temporal blocking of the same iteration (opt-in, OCC_CHI_TB=1: measured SLOWER than k_occ_chi_fused, 253 vs
+// 221 ms per 148 triples -- with a square root and two divisions per pixel-iteration in fp64 the loop is bound
+// by the fp64 pipe, and the halo recompute costs more than the saved HBM traffic).  Solver_wrt_chi runs a FIXED number of iterations
+// (MAX_ITERATIONS_CHI, no stopping rule), chi(p) after one iteration depends on the values within one pixel
+// of p, and nothing else changes meanwhile: a CTA loads its 32 x 32 tile plus a halo of kChiT pixels (the
+// three evolving planes into shared memory, the six constants of each of a thread's pixels into registers),
+// runs kChiT complete iterations on chip -- the values of the outermost ring go stale by one pixel per
+// iteration and never reach the tile -- and stores the tile.  HBM traffic per pixel-iteration falls from
+// ~90 B to ~25 B; the arithmetic (one square root and two divisions per pixel-iteration, fp64) is done
+// (32 + 2 kChiT)^2 / 32^2 / ... ~ 1.4 times.  Same formulas, same bits as the kernels above.
+constexpr int kChiT = 5;                                     // divides MAX_ITERATIONS_CHI, even number of launches
+constexpr int kChiBW = 32, kChiBH = 32;
+constexpr int kChiRW = kChiBW + 2 * kChiT, kChiRH = kChiBH + 2 * kChiT;
+constexpr int kChiTbThreads = 512;
+constexpr int kChiSlots = (kChiRW * kChiRH + kChiTbThreads - 1) / kChiTbThreads;
+constexpr size_t kChiTbSmem = 5 * sizeof(double) * kChiRW * kChiRH;
+
+__global__ void __launch_bounds__(kChiTbThreads) k_occ_chi_tb(const TripleCtl *__restrict__ ctl,
+                                                              const double *__restrict__ chi_in, double *__restrict__ chi_out,
+                                                              const double *__restrict__ g, const double *__restrict__ eta_in,
+                                                              double *__restrict__ eta_out, const double *__restrict__ C,
+                                                              int nx, int ny, int B, ChiParams P)
+{
+    const int b = blockIdx.z;
+    if (!ctl[b].active) return;
+    extern __shared__ double s_chi_tb[];
+    double *s_chi = s_chi_tb, *s_e1 = s_chi + kChiRW * kChiRH, *s_e2 = s_e1 + kChiRW * kChiRH,
+           *s_g1 = s_e2 + kChiRW * kChiRH, *s_g2 = s_g1 + kChiRW * kChiRH;
+    const size_t N = (size_t) nx * ny, BN = (size_t) B * N;
+    const size_t o = b * N;
+    const int rx0 = blockIdx.x * kChiBW - kChiT, ry0 = blockIdx.y * kChiBH - kChiT;
+    const int tid = threadIdx.x;
+    // this thread's pixels of the region (slot s: region index tid + s * threads)
+    int lpos[kChiSlots];                 // ly * kChiRW + lx, or -1 outside the region / image
+    double cg[kChiSlots], cF0[kChiSlots], cG0[kChiSlots], cF1[kChiSlots], cG1[kChiSlots], cbd[kChiSlots];
+#pragma unroll
+    for (int s = 0; s < kChiSlots; s++) {
+        const int k = tid + s * kChiTbThreads;
+        const int ly = k / kChiRW, lx = k - ly * kChiRW;
+        const int i = ry0 + ly, j = rx0 + lx;
+        lpos[s] = -1;
+        cg[s] = cF0[s] = cG0[s] = cF1[s] = cG1[s] = cbd[s] = 0.0;
+        if (k < kChiRW * kChiRH && i >= 0 && j >= 0 && i < ny && j < nx) {
+            const size_t p = o + (size_t) i * nx + j;
+            lpos[s] = k;
+            s_chi[k] = chi_in[p];
+            s_e1[k] = eta_in[p];
+            s_e2[k] = eta_in[BN + p];
+            cg[s] = g[p];
+            cF0[s] = C[p];
+            cG0[s] = C[BN + p];
+            cF1[s] = C[2 * BN + p];
+            cG1[s] = C[3 * BN + p];
+            cbd[s] = C[4 * BN + p];
+        }
+    }
+    __syncthreads();
+    for (int it = 0; it < kChiT; it++) {
+        // dual step + projection (:262-268, :33-52) at every pixel of the region
+#pragma unroll
+        for (int s = 0; s < kChiSlots; s++) {
+            const int k = lpos[s];
+            if (k < 0) continue;
+            const int ly = k / kChiRW, lx = k - ly * kChiRW;
+            const int i = ry0 + ly, j = rx0 + lx;
+            const double x = s_chi[k], gg = cg[s];
+            // forward differences: 0 on the last column / row of the IMAGE; at the edge of the region the
+            // neighbour is missing and the value is one of those that go stale
+            const double chix = (j < nx - 1 && lx + 1 < kChiRW) ? s_chi[k + 1] - x : 0;
+            const double chiy = (i < ny - 1 && ly + 1 < kChiRH) ? s_chi[k + kChiRW] - x : 0;
+            double e1 = s_e1[k] + P.tau_eta * gg * chix;
+            double e2 = s_e2[k] + P.tau_eta * gg * chiy;
+            const double norm2 = e1 * e1 + e2 * e2;
+            if (norm2 < P.is_zero) { e1 = 0.0; e2 = 0.0; }
+            else { const double norm = sqrt(norm2); e1 = e1 / norm; e2 = e2 / norm; }
+            s_e1[k] = e1;
+            s_e2[k] = e2;
+            s_g1[k] = gg * e1;
+            s_g2[k] = gg * e2;
+        }
+        __syncthreads();
+        // primal step (:270-325)
+#pragma unroll
+        for (int s = 0; s < kChiSlots; s++) {
+            const int k = lpos[s];
+            if (k < 0) continue;
+            const int ly = k / kChiRW, lx = k - ly * kChiRW;
+            const int i = ry0 + ly, j = rx0 + lx;
+            const double left = lx > 0 ? s_g1[k - 1] : 0.0, up = ly > 0 ? s_g2[k - kChiRW] : 0.0;
+            double div_eta;
+            if (i > 0 && i < ny - 1 && j > 0 && j < nx - 1) {
+                const double v1x = s_g1[k] - left;
+                const double v2y = s_g2[k] - up;
+                div_eta = v1x + v2y;
+            } else {
+                double a = 0;
+                bool first = true;
+                if (j < nx - 1) { a = s_g1[k]; first = false; }
+                if (j > 0) { a = first ? -left : a - left; first = false; }
+                if (i < ny - 1) { a = first ? s_g2[k] : a + s_g2[k]; first = false; }
+                if (i > 0) { a = first ? -up : a - up; first = false; }
+                div_eta = a;
+            }
+            double x = s_chi[k];
+            const bool lo = x < 0.5;
+            const double Fv = lo ? cF0[s] : cF1[s], Gv = lo ? cG0[s] : cG1[s];
+            x = x + P.tau_chi * (div_eta - Fv - Gv - cbd[s]);
+            if (x > 1.) x = 1.;
+            else if (x < 0.) x = 0.;
+            s_chi[k] = x;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < kChiSlots; s++) {
+        const int k = lpos[s];
+        if (k < 0) continue;
+        const int ly = k / kChiRW, lx = k - ly * kChiRW;
+        if (ly < kChiT || ly >= kChiT + kChiBH || lx < kChiT || lx >= kChiT + kChiBW) continue;
+        const size_t p = o + (size_t) (ry0 + ly) * nx + rx0 + lx;
+        chi_out[p] = s_chi[k];
+        eta_out[p] = s_e1[k];
+        eta_out[BN + p] = s_e2[k];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // outer loop: L2error (src/tvl1occflow.cpp:70-88) and the while test of :277.  Fixed-order fp64 sums:
 // per-CTA partials, then one thread per triple adds them in index order (the reference adds the pixels

@@ -67,6 +67,8 @@ struct occ_ctx {
     bool gs_wave = true;             // OCC_GS_WAVE=0: Gauss-Seidel pass on row-major planes (A/B)
     bool gs_coef = false;            // OCC_GS_COEF=1: interior coefficients from a parallel kernel (k_occ_rof_coef): three
                                      // of seven divisions leave the serial pass, but their 72 B per cell cost more (A/B)
+    bool chi_tb = false;             // OCC_CHI_TB=1: five occlusion-map iterations per launch on chip (k_occ_chi_tb; A/B:
+                                     // bit-identical, but the loop is fp64-bound, not HBM-bound: 253 vs 221 ms)
     bool chi_fused = true;           // OCC_CHI_FUSED=0: the two-kernel form of the occlusion-map iteration (A/B)
     int sm_count = 148;
     occ_stats stats{};
@@ -416,7 +418,17 @@ int run_level(occ_ctx *ctx, int s, const occ_params &prm, int stat_base)
                 k_occ_chi_setup<<<gB, kBlock2d, 0, st>>>(w.ctl, U, I1wx, I1wy, Im1wx, Im1wy, rho1, rho3, w.Vfwd, w.Vbck, w.C,
                                                      nx, ny, B, cp);
                 CKL();
-                if (ctx->chi_fused) {
+                if (ctx->chi_tb) {
+                    // kChiT iterations per launch on chip, ping-pong between (chi, ETA) and (tmpU, AL), both free here
+                    static_assert(OCC_MAX_ITERATIONS_CHI % (2 * kChiT) == 0, "an even number of launches ends where it began");
+                    const dim3 gT(ceil_div(nx, kChiBW), ceil_div(ny, kChiBH), B);
+                    for (int k = 0; k < OCC_MAX_ITERATIONS_CHI; k += 2 * kChiT) {
+                        k_occ_chi_tb<<<gT, kChiTbThreads, kChiTbSmem, st>>>(w.ctl, chi, w.tmpU, w.g, w.ETA, w.AL, w.C, nx, ny, B, cp);
+                        CKL();
+                        k_occ_chi_tb<<<gT, kChiTbThreads, kChiTbSmem, st>>>(w.ctl, w.tmpU, chi, w.g, w.AL, w.ETA, w.C, nx, ny, B, cp);
+                        CKL();
+                    }
+                } else if (ctx->chi_fused) {
                     // ping-pong between (chi, ETA) and (tmpU, AL), both free here; an even count ends where it began
                     static_assert(OCC_MAX_ITERATIONS_CHI % 2 == 0, "the fused occlusion-map loop ping-pongs");
                     const dim3 gF(ceil_div(nx, kChiTW), ceil_div(ny, kChiTH), B);
@@ -683,6 +695,11 @@ int occ_create(int device, occ_ctx **out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *s = getenv("OCC_MAX_BATCH")) ctx->max_batch = std::max(1, atoi(s));
     if (const char *s = getenv("OCC_CHI_FUSED")) ctx->chi_fused = s[0] != '0';
+    if (const char *s = getenv("OCC_CHI_TB")) ctx->chi_tb = s[0] == '1';
+    if (cudaFuncSetAttribute(k_occ_chi_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kChiTbSmem) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->chi_tb = false;
+    }
     if (const char *s = getenv("OCC_GS_WAVE")) ctx->gs_wave = s[0] != '0';
     if (const char *s = getenv("OCC_GS_COEF")) ctx->gs_coef = s[0] != '0';
     *out = ctx;

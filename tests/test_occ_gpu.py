@@ -106,6 +106,24 @@ def test_solver_equals_golden_bit_for_bit(gpu, occ_golden, name):
     assert st["kernel_launches"] > 0 and st["box_sweeps"] > 0
 
 
+@pytest.mark.parametrize("env", [{"OCC_GS_WAVE": "0"}, {"OCC_GS_COEF": "1"}, {"OCC_CHI_TB": "1"}, {"OCC_CHI_FUSED": "0"}],
+                         ids=["gs_row_major", "gs_coefficient_kernel", "chi_temporal_blocking", "chi_two_kernels"])
+def test_kernel_variants_give_the_same_bits(occ_golden, env, monkeypatch):
+    """The A/B variants kept in the library (row-major Gauss-Seidel pass, coefficient kernel, temporally blocked
+    and two-kernel occlusion-map iteration) against the golden vectors: every variant is the same arithmetic."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = pkg.TVL1Occ(device=0)
+    for name in ("occ_96x80_tight", "occ_61x47_z07"):
+        case = _cases.OCC_CASES[name]
+        I_1, I0, I1 = _cases.occ_inputs(case)
+        u1, u2, chi, iters, _ = g.Dual_TVL1_optic_flow_multiscale(I_1, I0, I1, None, **case["kw"])
+        assert np.array_equal(iters, occ_golden["f64/%s/iters" % name])
+        assert np.array_equal(u1, occ_golden["f64/%s/u1" % name]) and np.array_equal(u2, occ_golden["f64/%s/u2" % name])
+        assert np.array_equal(chi.astype(np.uint8), occ_golden["f64/%s/chi" % name])
+    g.close()
+
+
 def fresh_case(nx, ny, seed, **kw):
     p = dict(lam=0.15, alpha=0.01, beta=0.15, theta=0.3, nscales=3, zfactor=0.5, warps=2, eps=0.01)
     p.update(kw)
