@@ -133,8 +133,8 @@ struct tvl1_ctx {
     unsigned int *d_gather_ticket = nullptr;       // arrival counter of k_band_allgather
     const float *p2p_state_key = nullptr;
     unsigned char *d_handles = nullptr;            // [world][64] scratch for the handle all-gather
-    static constexpr int kMaxLanes = 4;
-    tvl1_ctx *sib[kMaxLanes - 1] = { nullptr, nullptr, nullptr };   // sibling contexts (extra lanes, same GPU)
+    static constexpr int kMaxLanes = 8;
+    tvl1_ctx *sib[kMaxLanes - 1] = {};   // sibling contexts (extra lanes, same GPU)
     int host_lanes = 4;                      // lanes used by the host-buffer batch entry points
     int short_div = 2;                       // host-buffer batches: first / last chunks of max_batch / short_div pairs
                                              // (TVL1_SHORT_DIV, 0 or 1 = all chunks equal)
@@ -1216,7 +1216,7 @@ void add_stats(tvl1_stats &a, const tvl1_stats &b)
 template <class Fn>
 int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
 {
-    tvl1_ctx *lanes[tvl1_ctx::kMaxLanes] = { ctx, nullptr, nullptr, nullptr };
+    tvl1_ctx *lanes[tvl1_ctx::kMaxLanes] = { ctx };
     int nlanes = 1;
     if (!ctx->is_sibling)
         nlanes = std::max(1, std::min(std::min(want_lanes, nchunks), (int) tvl1_ctx::kMaxLanes));
@@ -1239,7 +1239,7 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
         lanes[l] = sb;
     }
     for (int l = 0; l < nlanes; l++) lanes[l]->blocking_wait = lanes[l]->shared_gpu = nlanes > 1;
-    int rcs[tvl1_ctx::kMaxLanes] = { TVL1_OK, TVL1_OK, TVL1_OK, TVL1_OK };
+    int rcs[tvl1_ctx::kMaxLanes] = {};          // TVL1_OK == 0
     std::atomic<int> next{0};
     auto work = [&](int l) {
         tvl1_ctx *c = lanes[l];
@@ -1271,7 +1271,8 @@ void chunk_schedule(const tvl1_ctx *ctx, int npairs, int Bmax, int lanes, std::v
     const int nlanes = std::max(1, std::min(lanes, (int) tvl1_ctx::kMaxLanes));
     int first = 0;
     auto push = [&](int b) { out.emplace_back(first, b); first += b; };
-    if (small >= 1 && npairs >= 2 * nlanes * small + nlanes * Bmax) {
+    // (npairs % small != 0 would add a third, ragged size: a lane keeps workspaces for two)
+    if (small >= 1 && Bmax % small == 0 && npairs % small == 0 && npairs >= 2 * nlanes * small + nlanes * Bmax) {
         for (int l = 0; l < nlanes; l++) push(small);
         int rest = npairs - first - nlanes * small;
         while (rest >= Bmax) { push(Bmax); rest -= Bmax; }
