@@ -36,6 +36,11 @@ ap.add_argument("--ny", type=int, default=1080)
 ap.add_argument("--no-cpu", action="store_true")
 ap.add_argument("--skip-device", action="store_true", help="only the e2e (host-buffer) leg")
 ap.add_argument("--e2e-warmup", type=int, default=1)
+ap.add_argument("--skip-e2e", action="store_true", help="only the device-resident leg")
+ap.add_argument("--max-batch", type=int, default=148, help="device leg: lock-step batch (0: all pairs).  A launch lasts as "
+                "long as its slowest pair (150 sweeps against a mean of 65), so two lock-step batches of 148 pairs on two "
+                "lanes beat one of 296: 19.2 vs 15.2 pairs/s (profiles/r2o_hs_lanes.txt; 74 x 4 lanes 15.1, 37 x 8 12.7)")
+ap.add_argument("--lanes", type=int, default=2, help="device leg: lanes that take lock-step batches concurrently")
 args = ap.parse_args()
 nx, ny, P = args.nx, args.ny, args.pairs
 kw = dict(pkg.HS_DEFAULTS)
@@ -50,7 +55,9 @@ peak = float(peaks.get("hbm_gbs", 6556.5))
 
 I1, I2 = pkg.synth.make_batch_torch(P, nx, ny, seed=1234, device="cuda")
 u, v = torch.empty_like(I1), torch.empty_like(I1)
-g = pkg.HornSchunck(0, max_batch=P, profiling=True)
+MB = args.max_batch or P
+g = pkg.HornSchunck(0, max_batch=MB, profiling=True)
+g.set_lanes(host_lanes=4, dev_lanes=args.lanes)
 stream = torch.cuda.ExternalStream(g.stream())
 
 
@@ -67,6 +74,8 @@ if not args.skip_device:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sor_ms = px = launches = sor_launches = 0
+    import time as _time
+    t0 = _time.perf_counter()
     with torch.cuda.stream(stream):
         e0.record()
         for _ in range(args.steps):
@@ -77,12 +86,14 @@ if not args.skip_device:
         e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    if args.lanes > 1:      # the lanes run on their own streams: wall clock around the (synchronous) calls
+        ms = 1e3 * (_time.perf_counter() - t0) / args.steps
     line = {
         "metric": "Horn-Schunck 1080p frame-pairs/sec", "value": P / (ms * 1e-3), "unit": "frame-pairs/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "batch of %d synthetic %dx%d frame pairs, pyramidal Horn-Schunck, CLI default parameters"
-                               % (P, nx, ny), "params": kw, "lockstep_batch": P,
+                               % (P, nx, ny), "params": kw, "lockstep_batch": MB, "lanes": args.lanes,
                    "l2": "inputs and solver state exceed the 126 MB L2; no explicit flush"},
         "gpu_launches": launches,
         "sweeps_per_warp_step_mean": float(it.mean()), "sweeps_per_warp_step_max": int(it.max()),
@@ -96,36 +107,37 @@ if not args.skip_device:
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6556.5"},
     }
 
-# e2e: pinned host buffers through the public batch call
-E = min(args.e2e_pairs, P)
-hI1 = torch.empty((E, ny, nx), dtype=torch.float32).pin_memory()
-hI2 = torch.empty_like(hI1).pin_memory()
-hu = torch.empty_like(hI1).pin_memory()
-hv = torch.empty_like(hI1).pin_memory()
-hI1.copy_(I1[:E]); hI2.copy_(I2[:E])
-torch.cuda.synchronize()
-h = pkg.HornSchunck(0, max_batch=max(1, (E + 3) // 4))     # 4 lanes
-import ctypes as C
-prm = h._hs_params(kw["alpha"], kw["nscales"], kw["zfactor"], kw["warps"], kw["tol"], kw["maxiter"])
+if not args.skip_e2e:
+    # e2e: pinned host buffers through the public batch call
+    E = min(args.e2e_pairs, P)
+    hI1 = torch.empty((E, ny, nx), dtype=torch.float32).pin_memory()
+    hI2 = torch.empty_like(hI1).pin_memory()
+    hu = torch.empty_like(hI1).pin_memory()
+    hv = torch.empty_like(hI1).pin_memory()
+    hI1.copy_(I1[:E]); hI2.copy_(I2[:E])
+    torch.cuda.synchronize()
+    h = pkg.HornSchunck(0, max_batch=max(1, (E + 3) // 4))     # 4 lanes
+    import ctypes as C
+    prm = h._hs_params(kw["alpha"], kw["nscales"], kw["zfactor"], kw["warps"], kw["tol"], kw["maxiter"])
 
 
-def host_solve():
-    h._ck(h.lib.hs_solve_batch_f32(h.ctx, C.c_int(E), C.c_void_p(hI1.data_ptr()), C.c_void_p(hI2.data_ptr()),
-                                   C.c_void_p(hu.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_int(nx), C.c_int(ny),
-                                   C.byref(prm), None, None))
+    def host_solve():
+        h._ck(h.lib.hs_solve_batch_f32(h.ctx, C.c_int(E), C.c_void_p(hI1.data_ptr()), C.c_void_p(hI2.data_ptr()),
+                                       C.c_void_p(hu.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_int(nx), C.c_int(ny),
+                                       C.byref(prm), None, None))
 
 
-for _ in range(args.e2e_warmup):
+    for _ in range(args.e2e_warmup):
+        host_solve()
+    t0 = time.perf_counter()
     host_solve()
-t0 = time.perf_counter()
-host_solve()
-dt = time.perf_counter() - t0
-same = None if args.skip_device else bool(torch.equal(hu, u[:E].cpu()) and torch.equal(hv, v[:E].cpu()))
-line["e2e"] = {"value": E / dt, "unit": "frame-pairs/s", "pairs_per_step": E, "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": 2 * E * nx * ny * 4, "d2h_bytes_per_step": 2 * E * nx * ny * 4,
-               "api": "hs_solve_batch_f32 (host pinned fp32 in, host fp32 out)", "matches_device_path": same,
-               "warmup": args.e2e_warmup, "lanes": 4, "lockstep_batch": max(1, (E + 3) // 4),
-               "finite": bool(torch.isfinite(hu).all() and torch.isfinite(hv).all())}
+    dt = time.perf_counter() - t0
+    same = None if args.skip_device else bool(torch.equal(hu, u[:E].cpu()) and torch.equal(hv, v[:E].cpu()))
+    line["e2e"] = {"value": E / dt, "unit": "frame-pairs/s", "pairs_per_step": E, "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": 2 * E * nx * ny * 4, "d2h_bytes_per_step": 2 * E * nx * ny * 4,
+                   "api": "hs_solve_batch_f32 (host pinned fp32 in, host fp32 out)", "matches_device_path": same,
+                   "warmup": args.e2e_warmup, "lanes": 4, "lockstep_batch": max(1, (E + 3) // 4),
+                   "finite": bool(torch.isfinite(hu).all() and torch.isfinite(hv).all())}
 
 if not args.no_cpu and not args.skip_device:
     from oracle.loader import CpuTvl1, available
