@@ -509,6 +509,29 @@ def test_ragged_batch_keeps_both_workspaces(gpu):
         assert np.array_equal(u1, a[0][k]) and np.array_equal(u2, a[1][k]) and np.array_equal(it, a[2][k])
 
 
+@pytest.mark.parametrize("npairs,max_batch,lanes,short_div", [(24, 4, 3, 2), (21, 4, 3, 2), (24, 4, 4, 4), (13, 6, 2, 0),
+                                                              (40, 4, 8, 2), (9, 2, 4, 2)])
+def test_host_batch_chunk_schedules(gpu, npairs, max_batch, lanes, short_div, monkeypatch):
+    """Host-buffer batches are cut into lock-step chunks that lanes take from a shared queue -- short first /
+    last chunks when that adds no third chunk size, ragged remainders, more lanes than chunks, no temporal
+    blocking while lanes share the GPU: whatever the schedule, every pair's flow and iteration counts are the
+    bits of its individual solve."""
+    monkeypatch.setenv("TVL1_SHORT_DIV", str(short_div))
+    pairs = [_cases.synth.make_pair(128, 96, seed=500 + b, scale=0.3 + 0.02 * (b % 5)) for b in range(npairs)]
+    I0 = np.stack([p[0] for p in pairs])
+    I1 = np.stack([p[1] for p in pairs])
+    kw = dict(nscales=3, warps=2, eps=0.01)
+    g = pkg.TVL1(device=0, max_batch=max_batch)
+    g.set_lanes(host_lanes=lanes)
+    a = g.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)
+    b = g.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw)          # second call: workspaces and graphs re-used
+    g.close()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for k in range(0, npairs, 3):
+        u1, u2, it, _ = gpu.Dual_TVL1_optic_flow_multiscale(I0[k], I1[k], **kw)
+        assert np.array_equal(u1, a[0][k]) and np.array_equal(u2, a[1][k]) and np.array_equal(it, a[2][k]), k
+
+
 def test_band_code_path_single_rank(gpu, oracle_f64):
     """Row-band mode with one rank (a band = the whole level, NCCL communicator of size 1): the
     row-window kernels, the all-reduced stopping rule and the in-place all-gather must reproduce the
