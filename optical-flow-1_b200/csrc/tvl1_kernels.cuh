@@ -420,14 +420,22 @@ k_gauss_shfl(const float *__restrict__ in, int in_pitch, size_t in_stride, float
     for (int u = 0; u < W; u++) win[u][0] = win[u][1] = win[u][2] = win[u][3] = 0.f;
 
     const int iy_first = oy0 * D - R, iy_last = (oy1 - 1) * D + R;
+    // A warp walks down its strip row by row, so without help it has ONE row of loads in flight: the own
+    // columns of the row kGaussPf rows further down are pulled into L2 ahead (no registers: a register ring
+    // of prefetched rows was measured slower, 137 registers).
+    constexpr int kGaussPf = 8;
+    auto row_of = [&](int iy) {
+        int gy = iy < 0 ? -iy : (iy >= ny ? 2 * ny - 1 - iy : iy);
+        return src + (size_t) clampi(gy, 0, ny - 1) * in_pitch;
+    };
     for (int base = iy_first; base <= iy_last; base += W) {
 #pragma unroll
         for (int u = 0; u < W; u++) {
             const int iy = base + u;
             if (iy > iy_last) break;
-            int gy = iy < 0 ? -iy : (iy >= ny ? 2 * ny - 1 - iy : iy);
-            gy = clampi(gy, 0, ny - 1);
-            const float *row = src + (size_t) gy * in_pitch;
+            const float *row = row_of(iy);
+            if (fast && iy + kGaussPf <= iy_last)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(row_of(iy + kGaussPf) + ix0));
             // v[R .. R+OWN) = own columns, v[0 .. R) from the left neighbour, v[R+OWN .. R+OWN+NR) from the right
             float v[R + OWN + NR];
             if (fast) {
