@@ -853,6 +853,28 @@ def run_ours(args, rank, local_rank, world):
                            "api": "tvl1_solve_sequence_f32 (host pinned frames in, host fp32 flows out)",
                            "pairwise_same_pairs": world * S / (pair_ms / 1e3),
                            "matches_pairwise": bool(torch.equal(su1, pu1) and torch.equal(su2, pu2))}
+        # the same video as 8-bit frames (tvl1_solve_sequence_u8): a quarter of the upload
+        try:
+            h8 = torch.clamp(torch.round(hF), 0, 255).to(torch.uint8).pin_memory()
+            qu1 = torch.empty_like(su1).pin_memory()
+            qu2 = torch.empty_like(su1).pin_memory()
+            u8_ms = time_host(lambda: solver.solve_sequence_host_ptr(h8.data_ptr(), qu1.data_ptr(), qu2.data_ptr(),
+                                                                     S + 1, nx, ny, dtype="uint8", **PARAMS))
+            hW = h8.float().pin_memory()             # the same 8-bit frames widened on the host: the fp32 call's input
+            wu1 = torch.empty_like(su1).pin_memory()
+            wu2 = torch.empty_like(su1).pin_memory()
+            w_ms = time_host(lambda: solver.solve_sequence_host_ptr(hW.data_ptr(), wu1.data_ptr(), wu2.data_ptr(),
+                                                                    S + 1, nx, ny, **PARAMS))
+            e2e["sequence_u8"] = {"value": world * S / (u8_ms / 1e3), "unit": UNIT, "frames_per_rank_per_step": S + 1,
+                                  "h2d_bytes_per_step": (S + 1) * nx * ny, "d2h_bytes_per_step": 2 * S * nx * ny * 4,
+                                  "api": "tvl1_solve_sequence_u8 (host pinned 8-bit frames in, host fp32 flows out); the frames "
+                                         "are the video above rounded to 8 bits (quantisation changes the iteration counts, "
+                                         "so compare with fp32_same_frames, not with the rows above)",
+                                  "fp32_same_frames": world * S / (w_ms / 1e3),
+                                  "matches_fp32_same_frames": bool(torch.equal(qu1, wu1) and torch.equal(qu2, wu2))}
+            del h8, qu1, qu2, hW, wu1, wu2
+        except Exception as e:          # an extra: never lose the headline line over it
+            e2e["sequence_u8"] = {"error": repr(e)}
         del hF, sA, sB, su1, su2, pu1, pu2
 
     # ---- row bands (configs[3], configs[4]) on the same ranks: driver-visible at N > 1 ----

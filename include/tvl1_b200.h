@@ -123,6 +123,11 @@ int tvl1_solve_sequence_f32(tvl1_ctx *ctx, int nframes, const float *frames, flo
                             int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
 int tvl1_solve_sequence_f64(tvl1_ctx *ctx, int nframes, const double *frames, double *u1, double *u2,
                             int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
+/* 8-bit frames (what the reference's CLI reads from PGM / PNG files before it widens them to ofpix_t,
+ * src/tvl1flow_main.cpp:175-176 via iio_read_image_float): the frames cross PCIe as bytes and are widened
+ * on the device; flows in fp32.  Same bits as tvl1_solve_sequence_f32 on the widened frames. */
+int tvl1_solve_sequence_u8(tvl1_ctx *ctx, int nframes, const unsigned char *frames, float *u1, float *u2,
+                           int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out);
 /* Same, DEVICE buffers (dense, 16-byte aligned).  A device-resident frame sequence is the call
  * below with dI1 = dI0 + nx*ny (inputs are read-only and may overlap).   Work is issued on the context's stream and
  * complete on return.  iters_out / errs_out are HOST pointers. */

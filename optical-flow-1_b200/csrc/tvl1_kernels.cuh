@@ -783,6 +783,16 @@ __global__ void k_f64_to_f32(const double *__restrict__ in, float *__restrict__ 
          i += (size_t) gridDim.x * blockDim.x)
         out[i] = (float) in[i];
 }
+// 8-bit frames (video, PGM): four pixels per thread
+__global__ void k_u8_to_f32(const unsigned char *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) {
+        const uchar4 v = reinterpret_cast<const uchar4 *>(in)[i];
+        reinterpret_cast<float4 *>(out)[i] = make_float4((float) v.x, (float) v.y, (float) v.z, (float) v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[4 * n4 + threadIdx.x] = (float) in[4 * n4 + threadIdx.x];
+}
 __global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ out, size_t n)
 {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;

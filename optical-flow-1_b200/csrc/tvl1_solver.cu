@@ -1311,6 +1311,47 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
 }
 
 
+// 8-bit frame sequence (video): frames [nframes][ny][nx] of unsigned char in HOST memory -> nframes - 1 flows
+// in fp32.  A quarter of the upload of the fp32 form; the conversion is exact, so the flows are the bits
+// tvl1_solve_sequence_f32 gives on the same values.
+int solve_chunk_u8(tvl1_ctx *ctx, int first, int B, const unsigned char *frames, float *u1, float *u2, int nx, int ny,
+                   const tvl1_params *prm, int *iters_out, double *errs_out, int nstat)
+{
+    const size_t n = (size_t) nx * ny;
+    cudaStream_t st = ctx->stream;
+    const size_t in_cnt = (size_t) (B + 1) * n, out_cnt = (size_t) B * n, off = (size_t) first * n;
+    unsigned char *d8 = (unsigned char *) ctx->stage_in[1];
+    float *d0 = (float *) ctx->stage_in[0], *o0 = (float *) ctx->stage_out[0], *o1 = (float *) ctx->stage_out[1];
+    CK(cudaMemcpyAsync(d8, frames + off, in_cnt, cudaMemcpyHostToDevice, st));
+    k_u8_to_f32<<<(unsigned) std::min<size_t>((in_cnt / 4 + 255) / 256 + 1, 4096), 256, 0, st>>>(d8, d0, in_cnt);
+    CKL(ctx);
+    TRY(run_multiscale(ctx, B, d0, d0 + n, o0, o1, nx, ny, *prm, iters_out ? iters_out + (size_t) first * nstat : nullptr,
+                       errs_out ? errs_out + (size_t) first * nstat : nullptr));
+    CK(cudaMemcpyAsync(u1 + off, o0, out_cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(u2 + off, o1, out_cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(sleep_until_done(ctx));
+    return TVL1_OK;
+}
+
+int solve_sequence_u8(tvl1_ctx *ctx, int nframes, const unsigned char *frames, float *u1, float *u2, int nx, int ny,
+                      const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    TRY(check_common(ctx, frames, frames, u1, u2, nx, ny, prm, true));
+    if (nframes < 2) return fail_arg(ctx, "a frame sequence needs at least 2 frames");
+    reset_stats(ctx);
+    const int npairs = nframes - 1;
+    const size_t n = (size_t) nx * ny;
+    const int Bmax = std::min(npairs, ctx->max_batch);
+    const int nstat = prm->nscales * prm->warps;
+    std::vector<std::pair<int, int>> chunks;
+    chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
+    return run_lanes(ctx, (int) chunks.size(), ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
+        tvl1_ctx *ctx = c;   // for CK / TRY
+        TRY(ensure_stage(ctx, (size_t) (Bmax + 1) * n * sizeof(float), false));
+        return solve_chunk_u8(ctx, chunks[k].first, chunks[k].second, frames, u1, u2, nx, ny, prm, iters_out, errs_out, nstat);
+    });
+}
+
 // =================================================================================================
 // Row-band mode: ONE image pair split over the GPUs of a box (BASELINE configs[3..4]).
 // Every rank holds the full images and builds the full pyramids (cheap); coarse levels are solved
@@ -1945,6 +1986,13 @@ int tvl1_solve_sequence_f32(tvl1_ctx *ctx, int nframes, const float *frames, flo
 {
     if (ctx && nframes < 2) return fail_arg(ctx, "a frame sequence needs at least 2 frames");
     return solve_host<float>(ctx, nframes - 1, frames, nullptr, u1, u2, nx, ny, prm, iters_out, errs_out, true);
+}
+
+int tvl1_solve_sequence_u8(tvl1_ctx *ctx, int nframes, const unsigned char *frames, float *u1, float *u2,
+                           int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    if (!ctx) return TVL1_ERR_ARG;
+    return solve_sequence_u8(ctx, nframes, frames, u1, u2, nx, ny, prm, iters_out, errs_out);
 }
 
 int tvl1_solve_sequence_f64(tvl1_ctx *ctx, int nframes, const double *frames, double *u1, double *u2,

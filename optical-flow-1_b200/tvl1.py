@@ -224,6 +224,18 @@ class TVL1:
         (u1, u2, iters[F-1, nscales, warps], errs) -- the reference CLI's call
         (src/tvl1flow_main.cpp:203-206) looped over consecutive frames, each frame uploaded once."""
         frames = np.asarray(frames)
+        if frames.dtype == np.uint8:                      # 8-bit video: bytes over PCIe, fp32 flows
+            frames = np.ascontiguousarray(frames)
+            F, ny, nx = frames.shape
+            u1 = np.empty((max(F - 1, 0), ny, nx), np.float32)
+            u2 = np.empty_like(u1)
+            iters = np.zeros((max(F - 1, 0), nscales, warps), np.int32)
+            errs = np.zeros((max(F - 1, 0), nscales, warps), np.float64)
+            prm = self._params(tau, lam, theta, nscales, zfactor, warps, eps)
+            p = lambda a: a.ctypes.data_as(C.c_void_p)
+            self._ck(self.lib.tvl1_solve_sequence_u8(self.ctx, C.c_int(F), p(frames), p(u1), p(u2), C.c_int(nx), C.c_int(ny),
+                                                     C.byref(prm), p(iters), p(errs)))
+            return u1, u2, iters, errs
         dt = np.float64 if frames.dtype == np.float64 else np.float32
         frames = np.ascontiguousarray(frames, dt)
         F, ny, nx = frames.shape
@@ -243,7 +255,8 @@ class TVL1:
         p = dict(PAR_DEFAULTS)
         p.update(kw)
         prm = self._params(p["tau"], p["lam"], p["theta"], p["nscales"], p["zfactor"], p["warps"], p["eps"])
-        fn = self.lib.tvl1_solve_sequence_f64 if np.dtype(dtype) == np.float64 else self.lib.tvl1_solve_sequence_f32
+        fn = (self.lib.tvl1_solve_sequence_u8 if np.dtype(dtype) == np.uint8 else
+              self.lib.tvl1_solve_sequence_f64 if np.dtype(dtype) == np.float64 else self.lib.tvl1_solve_sequence_f32)
         self._ck(fn(self.ctx, C.c_int(nframes), C.c_void_p(pframes), C.c_void_p(pu1), C.c_void_p(pu2),
                     C.c_int(nx), C.c_int(ny), C.byref(prm), None, None))
 

@@ -488,6 +488,26 @@ def test_frame_sequence_equals_pairwise(gpu, dt):
         gpu.solve_sequence(frames[:1], **kw)
 
 
+def test_frame_sequence_of_8_bit_frames(gpu):
+    """tvl1_solve_sequence_u8: 8-bit frames cross PCIe as bytes and are widened on the device -- the same bits
+    as the fp32 sequence call on the widened frames, whole and cut into chunks, at a size whose pixel count is
+    not a multiple of four."""
+    F = 7
+    base = [_cases.synth.make_pair(97, 61, seed=190 + k, scale=0.3)[0] for k in range(2)]
+    frames = np.stack([np.roll(base[k % 2], (k, 2 * k), axis=(0, 1)) for k in range(F)])
+    q = np.clip(np.rint(frames), 0, 255).astype(np.uint8)
+    kw = dict(nscales=3, warps=2, eps=0.01)
+    for mb in (32, 2):
+        gpu.set_max_batch(mb)
+        a = gpu.solve_sequence(q, **kw)
+        b = gpu.solve_sequence(q.astype(np.float32), **kw)
+        assert a[0].dtype == np.float32 and a[0].shape == (F - 1, 61, 97)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    gpu.set_max_batch(32)
+    with pytest.raises(pkg.TVL1Error):
+        gpu.solve_sequence(q[:1], **kw)
+
+
 def test_ragged_batch_keeps_both_workspaces(gpu):
     """A batch that is not a multiple of the lock-step size alternates between two batch sizes; the
     displaced workspace and its solve graph are kept and swapped back in (profiles/run_e2e.py shows
