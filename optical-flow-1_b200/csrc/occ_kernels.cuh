@@ -816,6 +816,88 @@ __global__ void __launch_bounds__(256) k_occ_chi_fused(const TripleCtl *__restri
     }
 }
 
+// The same iteration as a row march (opt-in, OCC_CHI_MARCH=1): a warp owns 31 columns x kChiMR rows.  Lane l holds
+// column x0 + l - 1: lanes 1..31 own their pixel, lane 0 only evaluates the dual variable of the column to the
+// left, so the backward x-difference of the divergence is a shuffle; the warp walks down its strip carrying
+// chi of the next row and g * eta2 of the row above in registers, and starts one row above the strip for the
+// backward y-difference.  No shared memory, no barrier, no index division: k_occ_chi_fused spent two thirds
+// of its instructions on 64-bit index arithmetic and control (ncu source page: IMAD 16 %, DFMA+DMUL+DADD 18 %).
+// Same expressions, same bits.  chi / eta are read from one buffer and written to the other, as above.
+// Measured: 229.5 ms against 219.8 for the tiled kernel per 148 triples (and 302.7 with L2 prefetches of the
+// rows ahead): the instructions were not the limiter -- with ten fp64 planes per pixel-iteration the loop
+// sits on HBM -- so the tiled kernel stays the default.
+constexpr int kChiMR = 16;
+
+__global__ void __launch_bounds__(128) k_occ_chi_march(const TripleCtl *__restrict__ ctl, const double *__restrict__ chi_in,
+                                                       double *__restrict__ chi_out, const double *__restrict__ g,
+                                                       const double *__restrict__ eta_in, double *__restrict__ eta_out,
+                                                       const double *__restrict__ C, int nx, int ny, int B, ChiParams P)
+{
+    const int b = blockIdx.z;
+    if (!ctl[b].active) return;
+    const int lane = threadIdx.x;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * kChiMR;
+    if (y0 >= ny) return;                                        // warp-uniform
+    const int y1 = min(y0 + kChiMR, ny);
+    const int j = blockIdx.x * 31 + lane - 1;
+    const bool col = j >= 0 && j < nx;                           // this lane has a pixel at all
+    const bool own = lane >= 1 && col;
+    const size_t N = (size_t) nx * ny, BN = (size_t) B * N;
+    const double *chi_b = chi_in + b * N, *g_b = g + b * N, *e1_b = eta_in + b * N, *e2_b = eta_in + BN + b * N;
+    const double *c_b = C + b * N;
+    double *chi_o = chi_out + b * N, *e1_o = eta_out + b * N, *e2_o = eta_out + BN + b * N;
+    const int jc = col ? j : 0;                                  // a valid address for idle lanes
+    const bool has_right = col && j < nx - 1;
+    const int i_first = y0 > 0 ? y0 - 1 : 0;
+    int c = i_first * nx + jc;                                   // N < 2^30 (checked by the host)
+    double x = col ? chi_b[c] : 0.0;                             // chi of the current row
+    double up = 0.0;                                             // g * eta2 of the row above
+    for (int i = i_first; i < y1; i++, c += nx) {
+        const bool below = i < ny - 1;
+        const double xn = (col && below) ? chi_b[c + nx] : 0.0;  // chi of the next row (its x on the next turn)
+        double xr = __shfl_down_sync(0xffffffffu, x, 1);         // chi of the column to the right
+        if (lane == 31 && has_right) xr = chi_b[c + 1];
+        double ge1 = 0.0, ge2 = 0.0;
+        if (col) {
+            const double gg = g_b[c];
+            const double chix = has_right ? xr - x : 0, chiy = below ? xn - x : 0;
+            double e1 = e1_b[c] + P.tau_eta * gg * chix;
+            double e2 = e2_b[c] + P.tau_eta * gg * chiy;
+            const double norm2 = e1 * e1 + e2 * e2;
+            if (norm2 < P.is_zero) { e1 = 0.0; e2 = 0.0; }
+            else { const double norm = sqrt(norm2); e1 = e1 / norm; e2 = e2 / norm; }
+            if (own && i >= y0) { e1_o[c] = e1; e2_o[c] = e2; }
+            ge1 = gg * e1;
+            ge2 = gg * e2;
+        }
+        const double left = __shfl_up_sync(0xffffffffu, ge1, 1);
+        if (own && i >= y0) {
+            // divergence (src/operators.cpp:35-78) of (g eta1, g eta2), per-case association order
+            double div_eta;
+            if (i > 0 && i < ny - 1 && j > 0 && j < nx - 1) {
+                const double v1x = ge1 - left;
+                const double v2y = ge2 - up;
+                div_eta = v1x + v2y;
+            } else {
+                double a = 0;
+                bool first = true;
+                if (j < nx - 1) { a = ge1; first = false; }
+                if (j > 0) { a = first ? -left : a - left; first = false; }
+                if (i < ny - 1) { a = first ? ge2 : a + ge2; first = false; }
+                if (i > 0) { a = first ? -up : a - up; first = false; }
+                div_eta = a;
+            }
+            const double *cc = c_b + c + (x < 0.5 ? (size_t) 0 : 2 * BN);
+            double v = x + P.tau_chi * (div_eta - cc[0] - cc[BN] - c_b[4 * BN + c]);
+            if (v > 1.) v = 1.;
+            else if (v < 0.) v = 0.;
+            chi_o[c] = v;
+        }
+        up = ge2;
+        x = xn;
+    }
+}
+
 // Temporal blocking of the same iteration (opt-in, OCC_CHI_TB=1: measured SLOWER than k_occ_chi_fused, 253 vs
 // 221 ms per 148 triples -- with a square root and two divisions per pixel-iteration in fp64 the loop is bound
 // by the fp64 pipe, and the halo recompute costs more than the saved HBM traffic).  Solver_wrt_chi runs a FIXED number of iterations

@@ -69,6 +69,7 @@ struct occ_ctx {
                                      // of seven divisions leave the serial pass, but their 72 B per cell cost more (A/B)
     bool chi_tb = false;             // OCC_CHI_TB=1: five occlusion-map iterations per launch on chip (k_occ_chi_tb; A/B:
                                      // bit-identical, but the loop is fp64-bound, not HBM-bound: 253 vs 221 ms)
+    bool chi_march = false;          // OCC_CHI_MARCH=1: row-marching form of the occlusion-map iteration (A/B: 4 % slower)
     bool chi_fused = true;           // OCC_CHI_FUSED=0: the two-kernel form of the occlusion-map iteration (A/B)
     int sm_count = 148;
     occ_stats stats{};
@@ -428,6 +429,15 @@ int run_level(occ_ctx *ctx, int s, const occ_params &prm, int stat_base)
                         k_occ_chi_tb<<<gT, kChiTbThreads, kChiTbSmem, st>>>(w.ctl, w.tmpU, chi, w.g, w.AL, w.ETA, w.C, nx, ny, B, cp);
                         CKL();
                     }
+                } else if (ctx->chi_march) {
+                    static_assert(OCC_MAX_ITERATIONS_CHI % 2 == 0, "the occlusion-map loop ping-pongs");
+                    const dim3 gM(ceil_div(nx, 31), ceil_div(ny, 4 * kChiMR), B);
+                    for (int k = 0; k < OCC_MAX_ITERATIONS_CHI; k += 2) {
+                        k_occ_chi_march<<<gM, dim3(32, 4), 0, st>>>(w.ctl, chi, w.tmpU, w.g, w.ETA, w.AL, w.C, nx, ny, B, cp);
+                        CKL();
+                        k_occ_chi_march<<<gM, dim3(32, 4), 0, st>>>(w.ctl, w.tmpU, chi, w.g, w.AL, w.ETA, w.C, nx, ny, B, cp);
+                        CKL();
+                    }
                 } else if (ctx->chi_fused) {
                     // ping-pong between (chi, ETA) and (tmpU, AL), both free here; an even count ends where it began
                     static_assert(OCC_MAX_ITERATIONS_CHI % 2 == 0, "the fused occlusion-map loop ping-pongs");
@@ -696,6 +706,7 @@ int occ_create(int device, occ_ctx **out)
     if (const char *s = getenv("OCC_MAX_BATCH")) ctx->max_batch = std::max(1, atoi(s));
     if (const char *s = getenv("OCC_CHI_FUSED")) ctx->chi_fused = s[0] != '0';
     if (const char *s = getenv("OCC_CHI_TB")) ctx->chi_tb = s[0] == '1';
+    if (const char *s = getenv("OCC_CHI_MARCH")) ctx->chi_march = s[0] == '1';
     if (cudaFuncSetAttribute(k_occ_chi_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kChiTbSmem) != cudaSuccess) {
         cudaGetLastError();
         ctx->chi_tb = false;

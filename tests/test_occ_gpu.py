@@ -106,11 +106,12 @@ def test_solver_equals_golden_bit_for_bit(gpu, occ_golden, name):
     assert st["kernel_launches"] > 0 and st["box_sweeps"] > 0
 
 
-@pytest.mark.parametrize("env", [{"OCC_GS_WAVE": "0"}, {"OCC_GS_COEF": "1"}, {"OCC_CHI_TB": "1"}, {"OCC_CHI_FUSED": "0"}],
-                         ids=["gs_row_major", "gs_coefficient_kernel", "chi_temporal_blocking", "chi_two_kernels"])
+@pytest.mark.parametrize("env", [{"OCC_GS_WAVE": "0"}, {"OCC_GS_COEF": "1"}, {"OCC_CHI_TB": "1"}, {"OCC_CHI_MARCH": "1"},
+                                 {"OCC_CHI_FUSED": "0"}],
+                         ids=["gs_row_major", "gs_coefficient_kernel", "chi_temporal_blocking", "chi_row_march", "chi_two_kernels"])
 def test_kernel_variants_give_the_same_bits(occ_golden, env, monkeypatch):
     """The A/B variants kept in the library (row-major Gauss-Seidel pass, coefficient kernel, temporally blocked
-    and two-kernel occlusion-map iteration) against the golden vectors: every variant is the same arithmetic."""
+    row-marching and two-kernel occlusion-map iteration) against the golden vectors: every variant is the same arithmetic."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     g = pkg.TVL1Occ(device=0)
