@@ -1119,6 +1119,8 @@ struct IterParams {
     // than bulk_min pairs still iterate, the second (narrow grid) when none does
     cudaGraphConditionalHandle cond_bulk;
     int bulk_min;                      // -1: single-phase loop
+    int p_zero;                        // first iteration of a level: the duals are zero (src/tvl1flow.cpp:87-90) and
+                                       // are neither read nor were they written by a zeroing pass (k_iterate_t1 only)
     double *tb_partials;               // [batch][tb_parts][kTbT] per-CTA error sums of k_iterate_tb
     int tb_parts;
     int batch;                         // pairs in the lock-step batch (plane index = field * batch + pair)
@@ -1343,10 +1345,14 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
                 const size_t o = (size_t) y * pitch + x0;
                 r.u1 = ldg4(sin + F_U1 * fs + o);
                 r.u2 = ldg4(sin + F_U2 * fs + o);
-                r.p11 = ldg4(sin + F_P11 * fs + o);
-                r.p12 = ldg4(sin + F_P12 * fs + o);
-                r.p21 = ldg4(sin + F_P21 * fs + o);
-                r.p22 = ldg4(sin + F_P22 * fs + o);
+                if (P.p_zero) {                      // launch-uniform
+                    r.p11 = r.p12 = r.p21 = r.p22 = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    r.p11 = ldg4(sin + F_P11 * fs + o);
+                    r.p12 = ldg4(sin + F_P12 * fs + o);
+                    r.p21 = ldg4(sin + F_P21 * fs + o);
+                    r.p22 = ldg4(sin + F_P22 * fs + o);
+                }
                 r.ix = ldg4(cst + C_IX * fs + o);
                 r.iy = ldg4(cst + C_IY * fs + o);
                 r.rho = ldg4(cst + C_RHO * fs + o);
@@ -1362,7 +1368,7 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
             float l11 = __shfl_up_sync(0xffffffffu, r.p11.w, 1);
             float l21 = __shfl_up_sync(0xffffffffu, r.p21.w, 1);
             if (lane == 0) {
-                const bool has = x0 > 0;
+                const bool has = x0 > 0 && !P.p_zero;
                 const size_t o = (size_t) y * pitch + x0 - 1;
                 l11 = has ? __ldg(sin + F_P11 * fs + o) : 0.f;
                 l21 = has ? __ldg(sin + F_P21 * fs + o) : 0.f;
@@ -1449,7 +1455,7 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         Row4 ra, rb;
         float4 a12 = zero4, a22 = zero4;
-        if (ys > 0 && in_alloc) {
+        if (ys > 0 && in_alloc && !P.p_zero) {
             const size_t o = (size_t) (ys - 1) * pitch + x0;
             a12 = ldg4(sin + F_P12 * fs + o);
             a22 = ldg4(sin + F_P22 * fs + o);

@@ -102,6 +102,7 @@ struct tvl1_ctx {
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
     bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
+    bool zero_in_first = true;               // TVL1_ZERO_PASS=1: zero the duals of a streamed level with a pass of their own (A/B)
     bool gauss_shfl = true;                  // TVL1_GAUSS_SHFL=0: the marching blur that loads its own row inputs (A/B)
     bool warp_tma = true;                    // TVL1_WARP_TMA=0: stage the warp kernel's box with cp.async only
     int slot_ctas = 32768;                   // CTAs a full iteration launch should have at least (TVL1_SLOT_CTAS)
@@ -698,7 +699,10 @@ int add_while_node(tvl1_ctx *ctx, const IterParams &P, int B, cudaGraphCondition
     return TVL1_OK;
 }
 
-int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
+// first_zero: this is the first warp step of a level whose duals were NOT zeroed by a pass of their own: the
+// loop's first iteration (which always runs: error starts at infinity) is launched explicitly, with the duals
+// taken as zero instead of read, before the while nodes -- 32 B per pixel and level less HBM traffic.
+int add_while_loop(tvl1_ctx *ctx, IterParams P, int B, bool first_zero)
 {
     cudaStreamCaptureStatus status;
     cudaGraph_t g = nullptr;
@@ -719,6 +723,14 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
         CK(cudaGraphConditionalHandleCreate(&h_bulk, g, 1, cudaGraphCondAssignDefault));
         P.cond_bulk = h_bulk;
         P.bulk_min = ctx->tail_pairs;
+    }
+    if (first_zero) {
+        IterParams P0 = P;
+        P0.p_zero = 1;
+        P0.tb = 0;                      // every pair's first block is one iteration: the streaming kernel serves it
+        TRY(launch_iterate(ctx, P0, B));
+    }
+    if (two_phase) {
         TRY(add_while_node(ctx, P, B, h_bulk, false));
         // the pairs of the tail are the slow ones (tens of iterations where the batch needs two): worth
         // temporal blocking even where the full batch is not (a wide launch of both kernels costs more
@@ -733,13 +745,21 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B)
 // chunk of iteration launches, then read back how many pairs still iterate.  Launches for pairs
 // that already stopped exit at once, so over-shooting costs microseconds while every look costs
 // a stream synchronisation; the first chunk is the count the previous warp step needed.
-int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint)
+int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint, bool first_zero = false)
 {
     if (ctx->capturing) {
         Span sp(ctx, 0, P.level);
-        return add_while_loop(ctx, P, B);
+        return add_while_loop(ctx, P, B, first_zero);
     }
     int launched = 0;
+    if (first_zero) {
+        Span sp(ctx, 0, P.level);
+        IterParams P0 = P;
+        P0.p_zero = 1;
+        P0.tb = 0;
+        TRY(launch_iterate(ctx, P0, B));
+        launched = 1;
+    }
     int chunk = std::max(1, std::min(chunk_hint, P.max_iter));
     while (launched < P.max_iter) {
         const int k = std::min(chunk, P.max_iter - launched);
@@ -762,7 +782,10 @@ int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint)
 int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base, int &chunk_hint)
 {
     const Workspace &w = ctx->ws;
-    TRY(launch_zero(ctx, s, B, F_P11, 4));                                  // :87-90
+    // p = 0 (:87-90): a zeroing pass for the levels that live on chip; the streamed levels take the duals
+    // as zero in their first iteration instead (run_iterations, first_zero)
+    const bool zero_in_first = ctx->zero_in_first && w.res_cluster[s] == 0;
+    if (!zero_in_first) TRY(launch_zero(ctx, s, B, F_P11, 4));
     for (int wi = 0; wi < prm.warps; wi++) {                                // :92
         {
             Span sp(ctx, 1);
@@ -778,7 +801,7 @@ int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base
         CKL(ctx);
         IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations, s);
         P.tb = tb_usable(ctx, w.lv[s], B) ? 1 : 0;
-        TRY(run_iterations(ctx, P, B, chunk_hint));                         // :113-182
+        TRY(run_iterations(ctx, P, B, chunk_hint, zero_in_first && wi == 0));   // :113-182
     }
     return TVL1_OK;
 }
@@ -1855,6 +1878,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
+    if (const char *zp = std::getenv("TVL1_ZERO_PASS")) ctx->zero_in_first = !(zp[0] == '1');
     if (const char *gs = std::getenv("TVL1_GAUSS_SHFL")) ctx->gauss_shfl = !(gs[0] == '0');
     if (const char *wt = std::getenv("TVL1_WARP_TMA")) ctx->warp_tma = !(wt[0] == '0');
     if (const char *sc = std::getenv("TVL1_SLOT_CTAS")) ctx->slot_ctas = std::max(1, std::atoi(sc));
