@@ -87,10 +87,16 @@ void tvl1_destroy(tvl1_ctx *ctx);
 const char *tvl1_last_error(const tvl1_ctx *ctx);  /* ctx may be NULL: error of the last failed tvl1_create */
 int tvl1_set_profiling(tvl1_ctx *ctx, int on);     /* bracket kernels with CUDA events (tvl1_stats *_ms) */
 int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs);  /* pairs advanced in lock-step per workspace (default 32) */
-/* Batches larger than max_batch are cut into chunks that up to 4 lanes (sibling contexts on the same
- * GPU, one host thread each) process concurrently: copies of one chunk overlap kernels of another.
+/* Batches larger than max_batch are cut into chunks that up to 8 lanes (sibling contexts on the same
+ * GPU, one host thread each) process concurrently: copies of one chunk overlap kernels of another; with pinned
+ * host buffers the chunks of a call go through one upload -> solve -> download pipeline (tvl1_plan_chunks).
  * host_lanes: host-buffer entry points (default 4); dev_lanes: device-buffer entry point (default 2). */
 int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes);
+/* How a host-buffer batch of `npairs` pairs in PINNED memory is cut into lock-step chunks (no GPU needed): ramped
+ * sizes -- max_batch/8, /4, /2, full chunks, /2, /4, /8 -- so that the first kernels start and the last download
+ * ends one short chunk away from the ends of the call (csrc/tvl1_solver.cu: ramp_schedule, solve_host_pipelined).
+ * Writes up to `cap` chunk sizes to `sizes` and returns the number of chunks. */
+int tvl1_plan_chunks(int npairs, int max_batch, int *sizes, int cap);
 int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out);
 void *tvl1_get_stream(const tvl1_ctx *ctx);        /* the cudaStream_t all work of this context is issued on */
 void tvl1_default_params(tvl1_params *p);          /* tvl1flow_main.cpp:24-33 with nscales = 5 */

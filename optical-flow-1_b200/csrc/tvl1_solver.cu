@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -94,7 +95,9 @@ struct tvl1_ctx {
     int max_batch = 32;
     tvl1_stats stats{};
     Workspace ws;
-    Workspace ws_alt;                        // same image shape, other batch size (ragged last chunk)
+    static constexpr int kAltWs = 4;
+    Workspace ws_alt[kAltWs];                // same image shape, other batch sizes (ramped / ragged chunks of a host-buffer batch)
+    int alt_evict = 0;                       // round-robin victim when every alternate is in use
     LoopCtl *h_loop = nullptr;               // pinned
     cudaEvent_t sync_event = nullptr;        // blocking-sync event: lane threads sleep instead of spinning
     bool blocking_wait = false;              // set while several lanes share the GPU
@@ -116,7 +119,7 @@ struct tvl1_ctx {
     bool tb_when_shared = false;             // TVL1_TB_SHARED=1: temporal blocking also then (A/B)
     bool capturing = false;
     SolveGraph sg;
-    SolveGraph sg_alt;                       // solve graph of ws_alt
+    SolveGraph sg_alt[kAltWs];               // solve graphs of ws_alt[]
     SolveGraph *cap = nullptr;               // graph being captured (profiling events attach to it)
     SolveGraph level_sg[TVL1_MAX_LEVELS];    // row-band mode: one graph per pyramid level
     // row-band mode (one image over several GPUs)
@@ -149,6 +152,20 @@ struct tvl1_ctx {
     void *stage_out[2] = { nullptr, nullptr };
     float *stage_f32[4] = { nullptr, nullptr, nullptr, nullptr };
     size_t stage_bytes = 0, stage_f32_bytes = 0;
+    // ... pinned host buffers: a call-wide pipeline (solve_host_pipelined).  Chunks are uploaded in order on ONE copy
+    // stream into a ring of device slots, solved by the lanes, downloaded in order on a second copy stream.
+    struct HostSlot {
+        void *in[2] = { nullptr, nullptr };        // uploaded inputs (T), I0 / I1 stacks or one stack of frames
+        void *out[2] = { nullptr, nullptr };       // results (T) waiting for their download
+        cudaEvent_t up = nullptr, done = nullptr, down = nullptr;  // upload complete / solved (results in `out`) / download complete
+        bool down_recorded = false;
+    };
+    static constexpr int kMaxSlots = kMaxLanes + 3;
+    HostSlot slots[kMaxSlots];
+    size_t slot_in_bytes = 0, slot_out_bytes = 0;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    bool host_pipe = true;                         // TVL1_HOST_PIPE=0: lanes do their own copies (A/B)
+    std::vector<int> chunk_override;               // TVL1_CHUNKS=8,16,...: explicit chunk sizes (experiments)
     void *pipe_buf[2] = { nullptr, nullptr };      // pinned staging ring for pageable host buffers
     cudaEvent_t pipe_ev[2] = { nullptr, nullptr };
     int sm_count = 148;
@@ -297,21 +314,36 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
 {
     Workspace &w = ctx->ws;
     if (workspace_matches(ctx, w, nx, ny, nscales, zfactor, B, stat_stride, row_pad)) return TVL1_OK;
-    // A batch that is not a multiple of the lock-step size alternates between two batch sizes (full
-    // chunks and the ragged last one): the displaced workspace and its solve graph are kept as the
-    // alternate, so neither is rebuilt call after call.  Only the batch size may differ, so at most
-    // one extra (smaller or equal) workspace of the same image shape is ever held.
+    // A host-buffer batch is cut into chunks of a few different sizes (short first and last chunks, full
+    // ones in between, a ragged remainder: chunk_schedule), call after call: the displaced workspaces and
+    // their solve graphs are kept as alternates and swapped back in, so none is rebuilt.  Only the batch size
+    // may differ between the workspaces a context holds; another image shape drops the alternates.
     if (!ctx->nccl_comm) {
-        if (workspace_matches(ctx, ctx->ws_alt, nx, ny, nscales, zfactor, B, stat_stride, row_pad)) {
-            std::swap(ctx->ws, ctx->ws_alt);
-            std::swap(ctx->sg, ctx->sg_alt);
-            return TVL1_OK;
-        }
-        free_graph(ctx->sg_alt, ctx->ev_pool);
-        free_workspace(ctx->ws_alt);
-        if (w.state && w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B != B) {
-            std::swap(ctx->ws, ctx->ws_alt);
-            std::swap(ctx->sg, ctx->sg_alt);
+        for (int i = 0; i < tvl1_ctx::kAltWs; i++)
+            if (workspace_matches(ctx, ctx->ws_alt[i], nx, ny, nscales, zfactor, B, stat_stride, row_pad)) {
+                std::swap(ctx->ws, ctx->ws_alt[i]);
+                std::swap(ctx->sg, ctx->sg_alt[i]);
+                return TVL1_OK;
+            }
+        const bool same_shape = w.state && w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor &&
+                                w.row_pad == row_pad && w.B != B;
+        if (!same_shape) {
+            for (int i = 0; i < tvl1_ctx::kAltWs; i++) {
+                free_graph(ctx->sg_alt[i], ctx->ev_pool);
+                free_workspace(ctx->ws_alt[i]);
+            }
+        } else {
+            int slot = -1;
+            for (int i = 0; i < tvl1_ctx::kAltWs && slot < 0; i++)
+                if (!ctx->ws_alt[i].state) slot = i;
+            if (slot < 0) {
+                slot = ctx->alt_evict;
+                ctx->alt_evict = (ctx->alt_evict + 1) % tvl1_ctx::kAltWs;
+                free_graph(ctx->sg_alt[slot], ctx->ev_pool);
+                free_workspace(ctx->ws_alt[slot]);
+            }
+            std::swap(ctx->ws, ctx->ws_alt[slot]);
+            std::swap(ctx->sg, ctx->sg_alt[slot]);
         }
     }
     free_graph(ctx->sg, ctx->ev_pool);
@@ -1236,10 +1268,10 @@ void add_stats(tvl1_stats &a, const tvl1_stats &b)
 // driven by its own host thread.  Lanes take chunks round-robin and run concurrently on the GPU: the
 // copies of one chunk overlap the kernels of the other, and the sparse tail launches of one lane
 // (few pairs still iterating) are filled by the other lane's work.
-template <class Fn>
-int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
+// Lane 0 is `ctx`; the others are created on first use and take over the caller's settings.
+int setup_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, tvl1_ctx **lanes, int *nlanes_out)
 {
-    tvl1_ctx *lanes[tvl1_ctx::kMaxLanes] = { ctx };
+    lanes[0] = ctx;
     int nlanes = 1;
     if (!ctx->is_sibling)
         nlanes = std::max(1, std::min(std::min(want_lanes, nchunks), (int) tvl1_ctx::kMaxLanes));
@@ -1262,15 +1294,15 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
         lanes[l] = sb;
     }
     for (int l = 0; l < nlanes; l++) lanes[l]->blocking_wait = lanes[l]->shared_gpu = nlanes > 1;
-    int rcs[tvl1_ctx::kMaxLanes] = {};          // TVL1_OK == 0
-    std::atomic<int> next{0};
-    auto work = [&](int l) {
-        tvl1_ctx *c = lanes[l];
-        cudaSetDevice(c->device);
-        // chunks are taken from a shared queue in order (their sizes may differ, see chunk_schedule)
-        for (int k = next++; k < nchunks && rcs[l] == TVL1_OK; k = next++) rcs[l] = chunk_fn(c, k);
-        resolve_events(c);
-    };
+    *nlanes_out = nlanes;
+    return TVL1_OK;
+}
+
+// Runs `work(lane index)` on every lane (lane 0 on the calling thread), then folds the lanes' statistics and
+// the first error into `ctx`.
+template <class Fn>
+int join_lanes(tvl1_ctx *ctx, tvl1_ctx **lanes, int nlanes, int *rcs, Fn &&work)
+{
     std::vector<std::thread> threads;
     for (int l = 1; l < nlanes; l++) threads.emplace_back(work, l);
     work(0);
@@ -1280,6 +1312,23 @@ int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
         if (rcs[l] != TVL1_OK && rcs[0] == TVL1_OK) { ctx->err = lanes[l]->err; rcs[0] = rcs[l]; }
     }
     return rcs[0];
+}
+
+template <class Fn>
+int run_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, Fn &&chunk_fn)
+{
+    tvl1_ctx *lanes[tvl1_ctx::kMaxLanes];
+    int nlanes = 1;
+    TRY(setup_lanes(ctx, nchunks, want_lanes, lanes, &nlanes));
+    int rcs[tvl1_ctx::kMaxLanes] = {};          // TVL1_OK == 0
+    std::atomic<int> next{0};
+    return join_lanes(ctx, lanes, nlanes, rcs, [&](int l) {
+        tvl1_ctx *c = lanes[l];
+        cudaSetDevice(c->device);
+        // chunks are taken from a shared queue in order (their sizes may differ, see chunk_schedule)
+        for (int k = next++; k < nchunks && rcs[l] == TVL1_OK; k = next++) rcs[l] = chunk_fn(c, k);
+        resolve_events(c);
+    });
 }
 
 // Cuts a host-buffer batch into lock-step chunks.  The pipeline of a call cannot start computing before
@@ -1307,6 +1356,216 @@ void chunk_schedule(const tvl1_ctx *ctx, int npairs, int Bmax, int lanes, std::v
     }
 }
 
+// Chunk sizes for the pipelined host-buffer call (solve_host_pipelined).  The call cannot start computing before
+// its first chunk has arrived and cannot return before its last chunk has been downloaded, while chunks solve
+// at the full rate only when they are large: so the sizes RAMP -- Bmax/8, Bmax/4, Bmax/2 at the start, full
+// chunks in the middle, Bmax/2, Bmax/4, Bmax/8 at the end (uploads run ahead of the kernels: the copy engines
+// move a pair faster than the SMs solve it).  At most four sizes plus one ragged remainder occur, which is what
+// a lane keeps workspaces and solve graphs for (tvl1_ctx::kAltWs).
+void ramp_schedule(int npairs, int Bmax, const std::vector<int> &override_sizes, std::vector<std::pair<int, int>> &out)
+{
+    int first = 0;
+    auto push = [&](int b) { if (b > 0) { out.emplace_back(first, b); first += b; } };
+    if (!override_sizes.empty()) {
+        for (int b : override_sizes) push(std::min(std::min(std::max(b, 1), Bmax), npairs - first));
+        while (first < npairs) push(std::min(Bmax, npairs - first));
+        return;
+    }
+    std::vector<int> ramp;                          // ascending, distinct, below Bmax
+    for (int d = 8; d >= 2; d /= 2)
+        if (Bmax / d >= 1 && (ramp.empty() || ramp.back() != Bmax / d)) ramp.push_back(Bmax / d);
+    auto sum = [&]() { int t = 0; for (int b : ramp) t += b; return t; };
+    while (!ramp.empty() && npairs < 2 * sum() + Bmax) ramp.erase(ramp.begin());      // small batches: shorter ramps
+    for (int b : ramp) push(b);
+    int middle = npairs - first - sum();
+    while (middle >= Bmax) { push(Bmax); middle -= Bmax; }
+    // what is left of the middle joins the descending ramp (largest first), a ragged remainder goes last
+    std::vector<int> tail(ramp.rbegin(), ramp.rend());
+    for (int i = (int) ramp.size() - 1; i >= 0; i--)
+        if (middle >= ramp[i]) { tail.push_back(ramp[i]); middle -= ramp[i]; }
+    std::sort(tail.begin(), tail.end(), [](int a, int b) { return a > b; });
+    for (int b : tail) push(b);
+    push(middle);
+}
+
+int ensure_slots(tvl1_ctx *ctx, int nslots, size_t in_bytes, size_t out_bytes)
+{
+    if (!ctx->up_stream) CK(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+    if (!ctx->down_stream) CK(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+    const bool grow = ctx->slot_in_bytes < in_bytes || ctx->slot_out_bytes < out_bytes;
+    if (grow) {
+        for (auto &sl : ctx->slots)
+            for (int i = 0; i < 2; i++) {
+                cudaFree(sl.in[i]); sl.in[i] = nullptr;
+                cudaFree(sl.out[i]); sl.out[i] = nullptr;
+            }
+        ctx->slot_in_bytes = std::max(ctx->slot_in_bytes, in_bytes);
+        ctx->slot_out_bytes = std::max(ctx->slot_out_bytes, out_bytes);
+    }
+    for (int k = 0; k < nslots; k++) {
+        tvl1_ctx::HostSlot &sl = ctx->slots[k];
+        for (int i = 0; i < 2; i++) {
+            if (!sl.in[i]) CK(cudaMalloc(&sl.in[i], ctx->slot_in_bytes));
+            if (!sl.out[i]) CK(cudaMalloc(&sl.out[i], ctx->slot_out_bytes));
+        }
+        if (!sl.up) CK(cudaEventCreateWithFlags(&sl.up, cudaEventDisableTiming));
+        if (!sl.done) CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        if (!sl.down) CK(cudaEventCreateWithFlags(&sl.down, cudaEventBlockingSync | cudaEventDisableTiming));
+        sl.down_recorded = false;
+    }
+    return TVL1_OK;
+}
+
+int ensure_stage_f32(tvl1_ctx *ctx, size_t bytes_each)
+{
+    if (ctx->stage_f32_bytes < bytes_each) {
+        for (int i = 0; i < 4; i++) { cudaFree(ctx->stage_f32[i]); ctx->stage_f32[i] = nullptr; }
+        ctx->stage_f32_bytes = 0;
+        for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->stage_f32[i], bytes_each));
+        ctx->stage_f32_bytes = bytes_each;
+    }
+    return TVL1_OK;
+}
+
+// Pinned (or registered) host buffers: the whole call is ONE three-stage pipeline.
+//   upload    the chunks cross PCIe in order on one copy stream, each into a slot of a small ring of device
+//             buffers, up to `nslots` chunks ahead of the kernels (in order on one stream: the first chunk is not
+//             slowed by the second, which is what happens when every lane copies on a stream of its own);
+//   solve     the lanes (host thread + stream + workspace each, as in run_lanes) take the chunks in order; a lane
+//             waits for the chunk's upload event, solves it in place in the slot and is never idle for a copy;
+//   download  results leave in order on a second copy stream, behind the lane's completion event.
+// With the ramped chunk sizes of ramp_schedule the GPU starts after the upload of an eighth of a full chunk and
+// the call ends one such download after the last kernel.
+template <typename T>
+int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &chunks, const T *I0, const T *I1,
+                         T *u1, T *u2, int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+{
+    const bool sequence = I1 == nullptr, f64 = sizeof(T) == 8;
+    const size_t n = (size_t) nx * ny;
+    const int nchunks = (int) chunks.size();
+    const int nstat = prm->nscales * prm->warps;
+    int Bmax = 0;
+    for (const auto &c : chunks) Bmax = std::max(Bmax, c.second);
+    tvl1_ctx *lanes[tvl1_ctx::kMaxLanes];
+    int nlanes = 1;
+    TRY(setup_lanes(ctx, nchunks, ctx->host_lanes, lanes, &nlanes));
+    const int nslots = std::min(nchunks, std::min(nlanes + 3, (int) tvl1_ctx::kMaxSlots));
+    const size_t in_frames = (size_t) Bmax + (sequence ? 1 : 0);
+    TRY(ensure_slots(ctx, nslots, in_frames * n * sizeof(T), (size_t) Bmax * n * sizeof(T)));
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> computed(nchunks, 0);
+    int uploaded = 0, claimed = 0;
+    bool failed = false;
+    // (mu held) issue every upload whose slot is free: chunk j re-uses the slot of chunk j - nslots
+    auto pump = [&]() -> cudaError_t {
+        while (uploaded < nchunks && (uploaded < nslots || computed[uploaded - nslots])) {
+            const int first = chunks[uploaded].first, B = chunks[uploaded].second;
+            tvl1_ctx::HostSlot &sl = ctx->slots[uploaded % nslots];
+            const size_t off = (size_t) first * n, cnt = (size_t) B * n;
+            // (the slot's previous chunk has been solved: its lane said so under `mu`; the wait orders the copy
+            // engine behind that lane's stream whatever the solver's own host waits are)
+            cudaError_t e = uploaded >= nslots ? cudaStreamWaitEvent(ctx->up_stream, sl.done, 0) : cudaSuccess;
+            if (e != cudaSuccess) return e;
+            if (sequence)
+                e = cudaMemcpyAsync(sl.in[0], I0 + off, (cnt + n) * sizeof(T), cudaMemcpyHostToDevice, ctx->up_stream);
+            else {
+                e = cudaMemcpyAsync(sl.in[0], I0 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, ctx->up_stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(sl.in[1], I1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, ctx->up_stream);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(sl.up, ctx->up_stream);
+            if (e != cudaSuccess) return e;
+            uploaded++;
+        }
+        return cudaSuccess;
+    };
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        CK(pump());
+    }
+    int rcs[tvl1_ctx::kMaxLanes] = {};
+    auto chunk = [&](tvl1_ctx *c, int k) -> int {
+        tvl1_ctx *ctx_root = ctx;
+        tvl1_ctx *ctx = c;   // for CK / TRY
+        const int first = chunks[k].first, B = chunks[k].second;
+        const size_t cnt = (size_t) B * n;
+        tvl1_ctx::HostSlot &sl = ctx_root->slots[k % nslots];
+        cudaStream_t st = c->stream;
+        if (f64) TRY(ensure_stage_f32(c, in_frames * n * sizeof(float)));
+        CK(cudaStreamWaitEvent(st, sl.up, 0));
+        if (sl.down_recorded) CK(cudaStreamWaitEvent(st, sl.down, 0));    // the slot's previous results have left
+        float *d0, *d1, *o0, *o1;
+        const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
+        if (f64) {
+            d0 = c->stage_f32[0]; d1 = sequence ? d0 + n : c->stage_f32[1];
+            o0 = c->stage_f32[2]; o1 = c->stage_f32[3];
+            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) sl.in[0], d0, sequence ? cnt + n : cnt);
+            CKL(ctx);
+            if (!sequence) {
+                k_f64_to_f32<<<g, 256, 0, st>>>((const double *) sl.in[1], d1, cnt);
+                CKL(ctx);
+            }
+        } else {
+            d0 = (float *) sl.in[0]; d1 = sequence ? d0 + n : (float *) sl.in[1];
+            o0 = (float *) sl.out[0]; o1 = (float *) sl.out[1];
+        }
+        int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
+        double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
+        if (c->hs_mode) TRY(run_hs_multiscale(c, B, d0, d1, o0, o1, nx, ny, c->hs, it, er));
+        else TRY(run_multiscale(c, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
+        if (f64) {
+            k_f32_to_f64<<<g, 256, 0, st>>>(o0, (double *) sl.out[0], cnt);
+            CKL(ctx);
+            k_f32_to_f64<<<g, 256, 0, st>>>(o1, (double *) sl.out[1], cnt);
+            CKL(ctx);
+        }
+        CK(cudaEventRecord(sl.done, st));
+        std::lock_guard<std::mutex> lk(mu);
+        const size_t off = (size_t) first * n;
+        CK(cudaStreamWaitEvent(ctx_root->down_stream, sl.done, 0));
+        CK(cudaMemcpyAsync(u1 + off, sl.out[0], cnt * sizeof(T), cudaMemcpyDeviceToHost, ctx_root->down_stream));
+        CK(cudaMemcpyAsync(u2 + off, sl.out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, ctx_root->down_stream));
+        CK(cudaEventRecord(sl.down, ctx_root->down_stream));
+        sl.down_recorded = true;
+        computed[k] = 1;
+        CK(pump());
+        return TVL1_OK;
+    };
+    const int rc = join_lanes(ctx, lanes, nlanes, rcs, [&](int l) {
+        tvl1_ctx *c = lanes[l];
+        cudaSetDevice(c->device);
+        for (;;) {
+            int k;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (failed || claimed >= nchunks) break;
+                k = claimed++;
+                cv.wait(lk, [&] { return failed || uploaded > k; });
+                if (failed) break;
+            }
+            rcs[l] = chunk(c, k);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (rcs[l] != TVL1_OK) failed = true;
+            }
+            cv.notify_all();
+            if (rcs[l] != TVL1_OK) break;
+        }
+        resolve_events(c);
+    });
+    // the last downloads
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < nslots; k++)
+        if (ctx->slots[k].down_recorded) {
+            const cudaError_t ek = cudaEventSynchronize(ctx->slots[k].down);
+            if (e == cudaSuccess) e = ek;
+        }
+    if (rc != TVL1_OK) { cudaStreamSynchronize(ctx->up_stream); return rc; }
+    CK(e);
+    return TVL1_OK;
+}
+
 // Host-buffer driver shared by the f32/f64, multiscale/single-scale entry points.  A batch larger
 // than max_batch is cut into chunks; two lanes (this context and a private sibling on the same
 // GPU, each with its own stream, workspace and host thread) take alternate chunks, so the H2D/D2H
@@ -1324,6 +1583,12 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     const int nstat = (multiscale ? prm->nscales : 1) * prm->warps;
     const size_t stage_frames = (size_t) Bmax + (I1 ? 0 : 1);     // frame sequence: B+1 frames per chunk
     std::vector<std::pair<int, int>> chunks;                      // (first pair, pairs)
+    // pinned (or registered) buffers of a batch of several chunks: one call-wide pipeline with ramped chunk sizes
+    if (multiscale && ctx->host_pipe && !ctx->hs_mode && !ctx->is_sibling && npairs > Bmax && !is_pageable(I0) && (!I1 || !is_pageable(I1)) &&
+        !is_pageable(u1) && !is_pageable(u2)) {
+        ramp_schedule(npairs, Bmax, ctx->chunk_override, chunks);
+        return solve_host_pipelined<T>(ctx, chunks, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out);
+    }
     chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
     return run_lanes(ctx, (int) chunks.size(), ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
         tvl1_ctx *ctx = c;   // for CK / TRY
@@ -1887,6 +2152,15 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
     if (const char *ts = std::getenv("TVL1_TB_SHARED")) ctx->tb_when_shared = ts[0] == '1';
     if (const char *sd = std::getenv("TVL1_SHORT_DIV")) ctx->short_div = std::max(0, std::atoi(sd));
+    if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = !(hp[0] == '0');
+    if (const char *cs = std::getenv("TVL1_CHUNKS"))
+        for (const char *q = cs; *q;) {
+            char *end = nullptr;
+            const long v = std::strtol(q, &end, 10);
+            if (end == q) break;
+            ctx->chunk_override.push_back((int) std::max(1l, v));
+            q = *end == ',' ? end + 1 : end;
+        }
     if (const char *mp = std::getenv("TVL1_TB_MAX_MPIX")) ctx->tb_max_pixels = std::max(0ll, std::atoll(mp)) << 20;
     *out = ctx;
     return TVL1_OK;
@@ -1911,10 +2185,20 @@ void tvl1_destroy(tvl1_ctx *ctx)
     cudaFree(ctx->d_gather_ticket);
     free_graph(ctx->sg, ctx->ev_pool);
     free_workspace(ctx->ws);
-    free_graph(ctx->sg_alt, ctx->ev_pool);
-    free_workspace(ctx->ws_alt);
+    for (int i = 0; i < tvl1_ctx::kAltWs; i++) {
+        free_graph(ctx->sg_alt[i], ctx->ev_pool);
+        free_workspace(ctx->ws_alt[i]);
+    }
     for (int i = 0; i < 2; i++) { cudaFree(ctx->stage_in[i]); cudaFree(ctx->stage_out[i]); }
     for (int i = 0; i < 4; i++) cudaFree(ctx->stage_f32[i]);
+    for (auto &sl : ctx->slots) {
+        for (int i = 0; i < 2; i++) { cudaFree(sl.in[i]); cudaFree(sl.out[i]); }
+        if (sl.up) cudaEventDestroy(sl.up);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.down) cudaEventDestroy(sl.down);
+    }
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+    if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
     resolve_events(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
@@ -1954,6 +2238,15 @@ int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs)
     if (!ctx || pairs < 1) return TVL1_ERR_ARG;
     ctx->max_batch = pairs;
     return TVL1_OK;
+}
+
+int tvl1_plan_chunks(int npairs, int max_batch, int *sizes, int cap)
+{
+    if (npairs < 1 || max_batch < 1) return 0;
+    std::vector<std::pair<int, int>> chunks;
+    ramp_schedule(npairs, std::min(npairs, max_batch), {}, chunks);
+    for (int k = 0; k < (int) chunks.size() && k < cap && sizes; k++) sizes[k] = chunks[k].second;
+    return (int) chunks.size();
 }
 
 void *tvl1_get_stream(const tvl1_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }

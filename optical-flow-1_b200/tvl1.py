@@ -15,7 +15,7 @@ import sys
 import numpy as np
 
 __all__ = ["TVL1", "TVL1Error", "Params", "Stats", "library_path", "build_library",
-           "PAR_DEFAULTS", "clamp_nscales"]
+           "PAR_DEFAULTS", "clamp_nscales", "plan_chunks"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libtvl1_b200.so")
@@ -72,6 +72,17 @@ def clamp_nscales(nx, ny, nscales, zfactor):
     import math
     N = 1 + math.log(math.hypot(nx, ny) / 16.0) / math.log(1 / zfactor)
     return int(N) if N < nscales else nscales
+
+
+def plan_chunks(npairs, max_batch):
+    """Chunk sizes of a pinned host-buffer batch (include/tvl1_b200.h: tvl1_plan_chunks); needs no GPU."""
+    lib = _load()
+    lib.tvl1_plan_chunks.restype = C.c_int
+    lib.tvl1_plan_chunks.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    n = lib.tvl1_plan_chunks(npairs, max_batch, None, 0)
+    buf = (C.c_int * max(n, 1))()
+    lib.tvl1_plan_chunks(npairs, max_batch, buf, n)
+    return [int(buf[k]) for k in range(n)]
 
 
 def _load():
@@ -208,15 +219,21 @@ class TVL1:
             C.c_void_p(du2), C.c_int(nx), C.c_int(ny), C.byref(prm), ip, ep))
         return iters, errs
 
-    def solve_batch_host_ptr(self, pI0, pI1, pu1, pu2, npairs, nx, ny, dtype=np.float32, **kw):
+    def solve_batch_host_ptr(self, pI0, pI1, pu1, pu2, npairs, nx, ny, dtype=np.float32, iters=None, errs=None, **kw):
         """Host-resident batch by raw address (e.g. pinned torch tensors): the drop-in call with
-        H2D / D2H inside."""
+        H2D / D2H inside.  `iters` / `errs`: optional int32 / float64 arrays [npairs, nscales, warps]."""
         p = dict(PAR_DEFAULTS)
         p.update(kw)
         prm = self._params(p["tau"], p["lam"], p["theta"], p["nscales"], p["zfactor"], p["warps"], p["eps"])
         fn = self.lib.tvl1_solve_batch_f64 if np.dtype(dtype) == np.float64 else self.lib.tvl1_solve_batch_f32
         self._ck(fn(self.ctx, C.c_int(npairs), C.c_void_p(pI0), C.c_void_p(pI1), C.c_void_p(pu1),
-                    C.c_void_p(pu2), C.c_int(nx), C.c_int(ny), C.byref(prm), None, None))
+                    C.c_void_p(pu2), C.c_int(nx), C.c_int(ny), C.byref(prm),
+                    None if iters is None else iters.ctypes.data_as(C.c_void_p),
+                    None if errs is None else errs.ctypes.data_as(C.c_void_p)))
+
+    def plan_chunks(self, npairs, max_batch):
+        """Chunk sizes a pinned host-buffer batch is cut into (tvl1_plan_chunks)."""
+        return plan_chunks(npairs, max_batch)
 
     def solve_sequence(self, frames, tau=0.25, lam=0.15, theta=0.3, nscales=5, zfactor=0.5, warps=5,
                        eps=0.01):
@@ -250,7 +267,7 @@ class TVL1:
                     iters.ctypes.data_as(C.POINTER(C.c_int)), errs.ctypes.data_as(C.POINTER(C.c_double))))
         return u1, u2, iters, errs
 
-    def solve_sequence_host_ptr(self, pframes, pu1, pu2, nframes, nx, ny, dtype=np.float32, **kw):
+    def solve_sequence_host_ptr(self, pframes, pu1, pu2, nframes, nx, ny, dtype=np.float32, iters=None, errs=None, **kw):
         """Frame sequence by raw host address (pinned buffers)."""
         p = dict(PAR_DEFAULTS)
         p.update(kw)
@@ -258,7 +275,9 @@ class TVL1:
         fn = (self.lib.tvl1_solve_sequence_u8 if np.dtype(dtype) == np.uint8 else
               self.lib.tvl1_solve_sequence_f64 if np.dtype(dtype) == np.float64 else self.lib.tvl1_solve_sequence_f32)
         self._ck(fn(self.ctx, C.c_int(nframes), C.c_void_p(pframes), C.c_void_p(pu1), C.c_void_p(pu2),
-                    C.c_int(nx), C.c_int(ny), C.byref(prm), None, None))
+                    C.c_int(nx), C.c_int(ny), C.byref(prm),
+                    None if iters is None else iters.ctypes.data_as(C.c_void_p),
+                    None if errs is None else errs.ctypes.data_as(C.c_void_p)))
 
     # -- row-band mode: one image pair over several GPUs -------------------------------------------
     @staticmethod

@@ -552,6 +552,82 @@ def test_host_batch_chunk_schedules(gpu, npairs, max_batch, lanes, short_div, mo
         assert np.array_equal(u1, a[0][k]) and np.array_equal(u2, a[1][k]) and np.array_equal(it, a[2][k]), k
 
 
+@pytest.mark.parametrize("npairs,max_batch,lanes,dtype,form", [
+    (29, 8, 3, "float32", "pairs"), (29, 8, 3, "float64", "pairs"), (16, 4, 2, "float32", "sequence"),
+    (13, 4, 4, "float64", "sequence"), (40, 16, 1, "float32", "pairs"), (9, 2, 8, "float32", "pairs")])
+def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form):
+    """Pinned host buffers go through the call-wide upload -> solve -> download pipeline (solve_host_pipelined):
+    ramped chunk sizes (tvl1_plan_chunks), one ordered copy stream each way, a ring of device slots that chunks
+    re-use.  Whatever the schedule, fp32 or fp64 buffers, pairs or a frame sequence: every pair's flow and iteration
+    counts are the bits of its individual solve, call after call."""
+    import torch
+    nx, ny = 128, 96
+    kw = dict(nscales=3, warps=2, eps=0.01)
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    if form == "pairs":
+        pairs = [_cases.synth.make_pair(nx, ny, seed=700 + b, scale=0.3 + 0.02 * (b % 5)) for b in range(npairs)]
+        A = np.stack([p[0] for p in pairs]).astype(dtype)
+        Bm = np.stack([p[1] for p in pairs]).astype(dtype)
+        hA = torch.from_numpy(A).pin_memory()
+        hB = torch.from_numpy(Bm).pin_memory()
+    else:
+        fr = [_cases.synth.make_pair(nx, ny, seed=800 + b, scale=0.3)[b & 1] for b in range(npairs + 1)]
+        A = np.stack(fr).astype(dtype)
+        hA = torch.from_numpy(A).pin_memory()
+    assert len(pkg.tvl1.plan_chunks(npairs, max_batch)) > 1
+    g = pkg.TVL1(device=0, max_batch=max_batch)
+    g.set_lanes(host_lanes=lanes)
+    outs = []
+    for rep in range(2):                                        # second call: slots, workspaces and graphs re-used
+        hu1 = torch.full((npairs, ny, nx), float("nan"), dtype=tdt).pin_memory()
+        hu2 = torch.full((npairs, ny, nx), float("nan"), dtype=tdt).pin_memory()
+        it = np.zeros((npairs, kw["nscales"], kw["warps"]), np.int32)
+        er = np.zeros((npairs, kw["nscales"], kw["warps"]), np.float64)
+        if form == "pairs":
+            g.solve_batch_host_ptr(hA.data_ptr(), hB.data_ptr(), hu1.data_ptr(), hu2.data_ptr(), npairs, nx, ny,
+                                   dtype=dtype, iters=it, errs=er, **kw)
+        else:
+            g.solve_sequence_host_ptr(hA.data_ptr(), hu1.data_ptr(), hu2.data_ptr(), npairs + 1, nx, ny,
+                                      dtype=dtype, iters=it, errs=er, **kw)
+        outs.append((hu1.numpy().copy(), hu2.numpy().copy(), it, er))
+    g.close()
+    a, b = outs
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.isfinite(a[0]).all() and np.isfinite(a[1]).all()
+    for k in range(npairs):
+        I0k, I1k = (A[k], Bm[k]) if form == "pairs" else (A[k], A[k + 1])
+        u1, u2, itk, erk = gpu.Dual_TVL1_optic_flow_multiscale(I0k, I1k, **kw)
+        assert np.array_equal(u1, a[0][k]) and np.array_equal(u2, a[1][k]), k
+        assert np.array_equal(itk, a[2][k]) and np.array_equal(erk, a[3][k]), k
+
+
+def test_pinned_host_batch_pipeline_matches_lane_copies(monkeypatch):
+    """A/B switch: TVL1_HOST_PIPE=0 restores lanes that do their own copies; TVL1_CHUNKS overrides the sizes."""
+    import torch
+    nx, ny, npairs = 160, 120, 21
+    kw = dict(nscales=3, warps=2, eps=0.01)
+    pairs = [_cases.synth.make_pair(nx, ny, seed=900 + b, scale=0.4) for b in range(npairs)]
+    hA = torch.from_numpy(np.stack([p[0] for p in pairs])).pin_memory()
+    hB = torch.from_numpy(np.stack([p[1] for p in pairs])).pin_memory()
+    res = []
+    for env in ({"TVL1_HOST_PIPE": "1"}, {"TVL1_HOST_PIPE": "0"}, {"TVL1_CHUNKS": "1,5,3,2"}):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        g = pkg.TVL1(device=0, max_batch=6)
+        g.set_lanes(host_lanes=3)
+        hu1 = torch.zeros((npairs, ny, nx)).pin_memory()
+        hu2 = torch.zeros((npairs, ny, nx)).pin_memory()
+        it = np.zeros((npairs, 3, 2), np.int32)
+        g.solve_batch_host_ptr(hA.data_ptr(), hB.data_ptr(), hu1.data_ptr(), hu2.data_ptr(), npairs, nx, ny,
+                               dtype="float32", iters=it, **kw)
+        g.close()
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        res.append((hu1.numpy().copy(), hu2.numpy().copy(), it))
+    for r in res[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(res[0], r))
+
+
 def test_band_code_path_single_rank(gpu, oracle_f64):
     """Row-band mode with one rank (a band = the whole level, NCCL communicator of size 1): the
     row-window kernels, the all-reduced stopping rule and the in-place all-gather must reproduce the
