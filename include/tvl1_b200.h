@@ -88,11 +88,12 @@ const char *tvl1_last_error(const tvl1_ctx *ctx);  /* ctx may be NULL: error of 
 int tvl1_set_profiling(tvl1_ctx *ctx, int on);     /* bracket kernels with CUDA events (tvl1_stats *_ms) */
 int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs);  /* pairs advanced in lock-step per workspace (default 32) */
 /* Batches larger than max_batch are cut into chunks that up to 8 lanes (sibling contexts on the same
- * GPU, one host thread each) process concurrently: copies of one chunk overlap kernels of another; with pinned
- * host buffers the chunks of a call go through one upload -> solve -> download pipeline (tvl1_plan_chunks).
+ * GPU, one host thread each) process concurrently: copies of one chunk overlap kernels of another (with
+ * TVL1_HOST_PIPE=1 and pinned host buffers: one upload -> solve -> download pipeline per call, tvl1_plan_chunks).
  * host_lanes: host-buffer entry points (default 4); dev_lanes: device-buffer entry point (default 2). */
 int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes);
-/* How a host-buffer batch of `npairs` pairs in PINNED memory is cut into lock-step chunks (no GPU needed): ramped
+/* How a host-buffer batch of `npairs` pairs in PINNED memory is cut into lock-step chunks by the call-wide
+ * upload -> solve -> download pipeline (opt-in, TVL1_HOST_PIPE=1; no GPU needed for this query): ramped
  * sizes -- max_batch/8, /4, /2, full chunks, /2, /4, /8 -- so that the first kernels start and the last download
  * ends one short chunk away from the ends of the call (csrc/tvl1_solver.cu: ramp_schedule, solve_host_pipelined).
  * Writes up to `cap` chunk sizes to `sizes` and returns the number of chunks. */

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cmath>
 #include <cstdio>
@@ -164,7 +165,7 @@ struct tvl1_ctx {
     HostSlot slots[kMaxSlots];
     size_t slot_in_bytes = 0, slot_out_bytes = 0;
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
-    bool host_pipe = true;                         // TVL1_HOST_PIPE=0: lanes do their own copies (A/B)
+    bool host_pipe = false;                        // TVL1_HOST_PIPE=1: the call-wide pipeline (A/B; measured no faster)
     std::vector<int> chunk_override;               // TVL1_CHUNKS=8,16,...: explicit chunk sizes (experiments)
     void *pipe_buf[2] = { nullptr, nullptr };      // pinned staging ring for pageable host buffers
     cudaEvent_t pipe_ev[2] = { nullptr, nullptr };
@@ -301,11 +302,17 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
     return best;
 }
 
+// what the cluster choice of a workspace depends on besides the level sizes and the batch size
+int resident_key_of(const tvl1_ctx *ctx)
+{
+    return ctx->use_resident ? 1 + ctx->force_cluster : 0;
+}
+
 bool workspace_matches(const tvl1_ctx *ctx, const Workspace &w, int nx, int ny, int nscales, double zfactor, int B,
                        int stat_stride, int row_pad)
 {
     return w.nx == nx && w.ny == ny && w.nscales == nscales && w.zfactor == zfactor && w.B == B &&
-           w.stat_stride >= stat_stride && w.resident_key == (ctx->use_resident ? 1 + ctx->force_cluster : 0) &&
+           w.stat_stride >= stat_stride && w.resident_key == resident_key_of(ctx) &&
            w.row_pad == row_pad;
 }
 
@@ -351,7 +358,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     free_workspace(w);
     w.nx = nx; w.ny = ny; w.nscales = nscales; w.zfactor = zfactor; w.B = B;
     w.stat_stride = stat_stride;
-    w.resident_key = ctx->use_resident ? 1 + ctx->force_cluster : 0;
+    w.resident_key = resident_key_of(ctx);
     w.row_pad = row_pad;
     w.lv.resize(nscales);
     w.pyr_off.resize(nscales);
@@ -1268,6 +1275,18 @@ void add_stats(tvl1_stats &a, const tvl1_stats &b)
 // driven by its own host thread.  Lanes take chunks round-robin and run concurrently on the GPU: the
 // copies of one chunk overlap the kernels of the other, and the sparse tail launches of one lane
 // (few pairs still iterating) are filled by the other lane's work.
+// TVL1_PIPE_TRACE=1: one stderr line per chunk of a host-buffer batch (lane, pairs, host times in ms since the call began)
+struct ChunkTrace {
+    bool on = std::getenv("TVL1_PIPE_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    void line(const char *what, const tvl1_ctx *lane, int k, int B, double a, double b, double c) const
+    {
+        if (on) fprintf(stderr, "[tvl1 %s] chunk %2d pairs %3d lane %p: start %7.2f solved %7.2f done %7.2f\n", what, k, B,
+                        (const void *) lane, a, b, c);
+    }
+};
+
 // Lane 0 is `ctx`; the others are created on first use and take over the caller's settings.
 int setup_lanes(tvl1_ctx *ctx, int nchunks, int want_lanes, tvl1_ctx **lanes, int *nlanes_out)
 {
@@ -1454,18 +1473,26 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
     TRY(ensure_slots(ctx, nslots, in_frames * n * sizeof(T), (size_t) Bmax * n * sizeof(T)));
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<char> computed(nchunks, 0);
+    std::vector<int> slot_of(nchunks, -1), free_slots;
+    for (int k = nslots - 1; k >= 0; k--) free_slots.push_back(k);
+    std::vector<char> slot_used(nslots, 0);
     int uploaded = 0, claimed = 0;
     bool failed = false;
-    // (mu held) issue every upload whose slot is free: chunk j re-uses the slot of chunk j - nslots
+    // (mu held) issue uploads, in chunk order, while a slot is free.  A slot goes back on the free list as soon as its
+    // chunk has been solved, whichever chunk that is: a chunk that takes long (one slow pair keeps its lock-step
+    // batch iterating) must not hold up the uploads behind it.
     auto pump = [&]() -> cudaError_t {
-        while (uploaded < nchunks && (uploaded < nslots || computed[uploaded - nslots])) {
+        while (uploaded < nchunks && !free_slots.empty()) {
             const int first = chunks[uploaded].first, B = chunks[uploaded].second;
-            tvl1_ctx::HostSlot &sl = ctx->slots[uploaded % nslots];
+            const int si = free_slots.back();
+            free_slots.pop_back();
+            slot_of[uploaded] = si;
+            tvl1_ctx::HostSlot &sl = ctx->slots[si];
             const size_t off = (size_t) first * n, cnt = (size_t) B * n;
             // (the slot's previous chunk has been solved: its lane said so under `mu`; the wait orders the copy
             // engine behind that lane's stream whatever the solver's own host waits are)
-            cudaError_t e = uploaded >= nslots ? cudaStreamWaitEvent(ctx->up_stream, sl.done, 0) : cudaSuccess;
+            cudaError_t e = slot_used[si] ? cudaStreamWaitEvent(ctx->up_stream, sl.done, 0) : cudaSuccess;
+            slot_used[si] = 1;
             if (e != cudaSuccess) return e;
             if (sequence)
                 e = cudaMemcpyAsync(sl.in[0], I0 + off, (cnt + n) * sizeof(T), cudaMemcpyHostToDevice, ctx->up_stream);
@@ -1485,12 +1512,15 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
         CK(pump());
     }
     int rcs[tvl1_ctx::kMaxLanes] = {};
+    const ChunkTrace trace;
     auto chunk = [&](tvl1_ctx *c, int k) -> int {
+        const double t_start = trace.ms();
         tvl1_ctx *ctx_root = ctx;
         tvl1_ctx *ctx = c;   // for CK / TRY
         const int first = chunks[k].first, B = chunks[k].second;
         const size_t cnt = (size_t) B * n;
-        tvl1_ctx::HostSlot &sl = ctx_root->slots[k % nslots];
+        const int si = slot_of[k];
+        tvl1_ctx::HostSlot &sl = ctx_root->slots[si];
         cudaStream_t st = c->stream;
         if (f64) TRY(ensure_stage_f32(c, in_frames * n * sizeof(float)));
         CK(cudaStreamWaitEvent(st, sl.up, 0));
@@ -1521,6 +1551,7 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
             CKL(ctx);
         }
         CK(cudaEventRecord(sl.done, st));
+        const double t_solved = trace.ms();
         std::lock_guard<std::mutex> lk(mu);
         const size_t off = (size_t) first * n;
         CK(cudaStreamWaitEvent(ctx_root->down_stream, sl.done, 0));
@@ -1528,8 +1559,9 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
         CK(cudaMemcpyAsync(u2 + off, sl.out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, ctx_root->down_stream));
         CK(cudaEventRecord(sl.down, ctx_root->down_stream));
         sl.down_recorded = true;
-        computed[k] = 1;
+        free_slots.push_back(si);
         CK(pump());
+        trace.line("pipe", c, k, B, t_start, t_solved, trace.ms());
         return TVL1_OK;
     };
     const int rc = join_lanes(ctx, lanes, nlanes, rcs, [&](int l) {
@@ -1590,11 +1622,15 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
         return solve_host_pipelined<T>(ctx, chunks, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out);
     }
     chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
+    const ChunkTrace trace;
     return run_lanes(ctx, (int) chunks.size(), ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
         tvl1_ctx *ctx = c;   // for CK / TRY
+        const double t_start = trace.ms();
         TRY(ensure_stage(ctx, stage_frames * n * sizeof(T), f64));
-        return solve_chunk<T>(ctx, chunks[k].first, chunks[k].second, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out,
-                              multiscale, nstat);
+        const int rc = solve_chunk<T>(ctx, chunks[k].first, chunks[k].second, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out,
+                                      multiscale, nstat);
+        trace.line("lane", c, k, chunks[k].second, t_start, trace.ms(), trace.ms());
+        return rc;
     });
 }
 
@@ -2152,7 +2188,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
     if (const char *ts = std::getenv("TVL1_TB_SHARED")) ctx->tb_when_shared = ts[0] == '1';
     if (const char *sd = std::getenv("TVL1_SHORT_DIV")) ctx->short_div = std::max(0, std::atoi(sd));
-    if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = !(hp[0] == '0');
+    if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = hp[0] == '1';
     if (const char *cs = std::getenv("TVL1_CHUNKS"))
         for (const char *q = cs; *q;) {
             char *end = nullptr;

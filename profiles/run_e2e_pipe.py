@@ -22,17 +22,20 @@ for mb, lanes, env in cfgs:
     for k in env: del os.environ[k]
     best = 1e9
     try:
-        for rep in range(5):
+        times = []
+        for rep in range(int(os.environ.get('REPS', '5'))):
             torch.cuda.synchronize(); t = time.perf_counter()
             g.solve_batch_host_ptr(hI0.data_ptr(), hI1.data_ptr(), hu1.data_ptr(), hu2.data_ptr(), P, nx, ny, dtype="float32")
             torch.cuda.synchronize(); dt = 1e3 * (time.perf_counter() - t)
             if rep: best = min(best, dt)
+            times.append(round(dt, 1))
         if ref is None: ref = (hu1.clone(), hu2.clone())
         same = bool(torch.equal(ref[0], hu1) and torch.equal(ref[1], hu2))
         free, total = torch.cuda.mem_get_info()
         print("max_batch %3d lanes %d %-52s chunks %-40s: %.2f ms -> %.1f pairs/s  same=%s  dev mem used %.1f GB" % (
             mb, lanes, env, env.get("TVL1_CHUNKS") or (pkg.tvl1.plan_chunks(P, mb) if env.get("TVL1_HOST_PIPE") != "0" else "round-2 schedule"),
             best, P / best * 1e3, same, (total - free) / 2**30), flush=True)
+        if os.environ.get('REPS'): print("    per call:", times, flush=True)
     except Exception as e:
         print("max_batch %3d lanes %d %s: FAILED %s" % (mb, lanes, env, e), flush=True)
     g.close(); del g; torch.cuda.empty_cache()

@@ -555,12 +555,13 @@ def test_host_batch_chunk_schedules(gpu, npairs, max_batch, lanes, short_div, mo
 @pytest.mark.parametrize("npairs,max_batch,lanes,dtype,form", [
     (29, 8, 3, "float32", "pairs"), (29, 8, 3, "float64", "pairs"), (16, 4, 2, "float32", "sequence"),
     (13, 4, 4, "float64", "sequence"), (40, 16, 1, "float32", "pairs"), (9, 2, 8, "float32", "pairs")])
-def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form):
-    """Pinned host buffers go through the call-wide upload -> solve -> download pipeline (solve_host_pipelined):
+def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, monkeypatch):
+    """TVL1_HOST_PIPE=1: pinned host buffers go through the call-wide upload -> solve -> download pipeline (solve_host_pipelined):
     ramped chunk sizes (tvl1_plan_chunks), one ordered copy stream each way, a ring of device slots that chunks
     re-use.  Whatever the schedule, fp32 or fp64 buffers, pairs or a frame sequence: every pair's flow and iteration
     counts are the bits of its individual solve, call after call."""
     import torch
+    monkeypatch.setenv("TVL1_HOST_PIPE", "1")
     nx, ny = 128, 96
     kw = dict(nscales=3, warps=2, eps=0.01)
     tdt = torch.float32 if dtype == "float32" else torch.float64
@@ -602,7 +603,8 @@ def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form):
 
 
 def test_pinned_host_batch_pipeline_matches_lane_copies(monkeypatch):
-    """A/B switch: TVL1_HOST_PIPE=0 restores lanes that do their own copies; TVL1_CHUNKS overrides the sizes."""
+    """A/B switch: TVL1_HOST_PIPE=1 selects the call-wide pipeline instead of lanes that do their own copies;
+    TVL1_CHUNKS overrides its chunk sizes.  Same bits either way."""
     import torch
     nx, ny, npairs = 160, 120, 21
     kw = dict(nscales=3, warps=2, eps=0.01)
@@ -610,7 +612,7 @@ def test_pinned_host_batch_pipeline_matches_lane_copies(monkeypatch):
     hA = torch.from_numpy(np.stack([p[0] for p in pairs])).pin_memory()
     hB = torch.from_numpy(np.stack([p[1] for p in pairs])).pin_memory()
     res = []
-    for env in ({"TVL1_HOST_PIPE": "1"}, {"TVL1_HOST_PIPE": "0"}, {"TVL1_CHUNKS": "1,5,3,2"}):
+    for env in ({"TVL1_HOST_PIPE": "1"}, {"TVL1_HOST_PIPE": "0"}, {"TVL1_HOST_PIPE": "1", "TVL1_CHUNKS": "1,5,3,2"}):
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)
         g = pkg.TVL1(device=0, max_batch=6)
