@@ -466,7 +466,7 @@ int run_hs_single_scale(tvl1_ctx *ctx, int B, const float *dI1, const float *dI2
     TRY(hs_check_level(ctx, w.lv[0]));
     cudaStream_t st = ctx->stream;
     Span total(ctx, 2);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * kCounterWords, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
@@ -585,7 +585,7 @@ int hs_sor_f32(tvl1_ctx *ctx, const float *I2wx, const float *I2wy, const float 
     if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     const float *src[5] = { u, v, I2wx, I2wy, rho_c };
     for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(buf + k * n, src[k], n * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * kCounterWords, st));
     k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
     CKL(ctx);
     const dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);

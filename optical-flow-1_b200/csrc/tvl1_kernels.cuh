@@ -22,6 +22,9 @@ namespace tvl1 {
 constexpr int kMaxIterations = 300;       // src/tvl1flow.cpp:22
 constexpr float kGradIsZero = 1e-10f;     // src/tvl1flow.cpp:24
 constexpr int kStatLevels = 16;           // == TVL1_MAX_LEVELS
+constexpr int kCounterWords = 3 * kStatLevels;   // per level: pixel-iterations, iteration launches, sum over the loops of a
+                                          // solve of min(iterations, kLoopClip) (streamed levels: decide_block)
+constexpr int kLoopClip = 16;
 constexpr int kTbT = 4;                   // iterations per launch of the temporally blocked kernel
 constexpr int kMaxTaps = 16;              // (int)(5*sigma)+1 <= 16  <=>  sigma < 3.2 (zfactor > 0.19)
 
@@ -1125,7 +1128,9 @@ struct IterParams {
     int tb_parts;
     int batch;                         // pairs in the lock-step batch (plane index = field * batch + pair)
     int tb;                            // 1: pairs whose next block has more than one iteration belong
-                                       // to k_iterate_tb; this kernel only takes the nsteps == 1 pairs
+                                       // to k_iterate_tb; this kernel only takes the nsteps == 1 pairs.
+                                       // 2: ... to k_iterate_t2 (two iterations per launch in registers)
+    int tb_max;                        // longest block: kTbT (k_iterate_tb) or kT2T (k_iterate_t2)
     int row_begin, row_end;            // rows this launch owns (whole image: 0, ny; a row band otherwise)
     double *band_sum;                  // row-band mode: the rank's raw sum of squared updates goes here
                                        // and k_band_decide applies the stopping rule after the all-reduce
@@ -1180,6 +1185,7 @@ __device__ __forceinline__ void decide_block(const IterParams &P, PairCtl *ctl, 
         ctl->nsteps = 1;
         P.stat_iters[(size_t) b * P.stat_stride + P.stat_slot] = n;
         P.stat_errs[(size_t) b * P.stat_stride + P.stat_slot] = last;
+        atomicAdd(P.px_iters + 2 * kStatLevels + P.level, (unsigned long long) min(n, kLoopClip));
         atomicMax(&P.loop->max_n, n);
         const int left = atomicSub(&P.loop->active_pairs, 1) - 1;
         // the last pair to stop ends the device-side while loop of the solve graph
@@ -1191,12 +1197,16 @@ __device__ __forceinline__ void decide_block(const IterParams &P, PairCtl *ctl, 
     }
     int next = 1;
     if (P.tb && prev < INFINITY) {          // no history yet (first iteration of the warp step): stay at 1
-        next = kTbT;                        // error not falling: far from the stopping point
+        next = P.tb_max;                    // error not falling: far from the stopping point
         if (last < prev && last > P.eps2) {
             // error ~ last * r^k: iterations until it is below eps^2 (the decay usually slows down, so
-            // this under-estimates and a replay stays rare); keep one in hand
+            // this under-estimates and a replay stays rare)
             const double k = log(P.eps2 / last) / log(last / prev);
-            if (k < (double) (kTbT + 1)) next = max(1, (int) k - 1);
+            if (P.tb == 2) {
+                // two-iteration blocks in registers: a block saves 54 of 120 B per pixel when the pair has two more
+                // iterations to go and costs 66 B when it has one, so it pays from an even chance on
+                if (k < 2.0) next = 1;
+            } else if (k < (double) (kTbT + 1)) next = max(1, (int) k - 1);     // keep one in hand
         }
         next = max(1, min(next, P.max_iter - n));
     }
@@ -1519,6 +1529,227 @@ k_iterate_t1(const IterParams P)
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
         atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
     for_each_pair_of_slot<false>(P, false, [&](int b) { iterate_t1_pair<R, WY>(P, b); });
+}
+
+// (c') TWO iterations per launch, in registers: the marching kernel above with a second iteration following
+// the first one row behind.  For the lock-step batches whose streamed levels saturate HBM (where the
+// shared-memory kernel k_iterate_tb loses: it trades bytes for instruction issue, 243 instructions per useful
+// pixel-iteration against 110 here), this halves the bytes instead: every plane element is loaded once and
+// stored once per TWO iterations -- (36 B in + 24 B out) x halo overhead = 33 B per pixel-iteration against 60.
+// A warp owns 120 columns x R rows.  Lane l holds the 4 pixels at x = 120*bx - 4 + 4*l: lanes 1..30 own, lanes 0
+// and 31 are the one-pixel-per-iteration halo either side (a float4 each).  Rows: the first iteration runs on
+// rows ys-1 .. ye+1, the second on ys .. ye, stores on ys .. ye-1 (R + 3 rows loaded for R stored; the halo rows
+// are the neighbouring strips' own rows, i.e. L2 hits).  Three register blocks (rows t, t+1, t+2) rotate:
+//   A(t+2)  load row t+2 of the start state;  u' = first-iteration u_new  (needs p(t+1) of the start state)
+//   B(t+1)  p' (t+1) from u'(t+1), u'(t+2), in place
+//   C(t+1)  u''(t+1) from u'(t+1), p'(t+1), p'(t), in place
+//   D(t)    p''(t) from p'(t), u''(t), u''(t+1); store row t.
+// Same per-pixel functions as the other iteration kernels, hence the same bits; the error of each of the two
+// iterations is reduced separately and decide_block accepts the block, or has its first iteration replayed.
+constexpr int kT2W = 120;                 // owned columns per warp
+constexpr int kT2T = 2;                   // iterations per launch
+
+template <int R, int WY>
+__device__ __forceinline__ void iterate_t2_pair(const IterParams &P, const int b)
+{
+    PairCtl *ctl = P.ctl + b;
+    const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cur = ctl->cur;
+    const float *sin = P.state + (size_t) cur * P.set_stride + (size_t) b * P.plane0;
+    float *sout = P.state + (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0;
+    const float *cst = P.consts + (size_t) b * P.plane0;
+    const size_t fs = P.field_stride;
+
+    const int x0 = blockIdx.x * kT2W - 4 + lane * 4;
+    const int ys = P.row_begin + (blockIdx.y * WY + warp) * R;
+    const int ye = min(ys + R, P.row_end);
+    const bool in_alloc = x0 >= 0 && x0 < pitch;
+    const bool owner = in_alloc && lane >= 1 && lane <= 30 && x0 < nx;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    float err1 = 0.f, err2 = 0.f;
+
+    if (ys < P.row_end) {                           // warp-uniform
+        auto load_row = [&](int y, Row4 &r) {
+            if (in_alloc) {
+                const size_t o = (size_t) y * pitch + x0;
+                r.u1 = ldg4(sin + F_U1 * fs + o);
+                r.u2 = ldg4(sin + F_U2 * fs + o);
+                r.p11 = ldg4(sin + F_P11 * fs + o);
+                r.p12 = ldg4(sin + F_P12 * fs + o);
+                r.p21 = ldg4(sin + F_P21 * fs + o);
+                r.p22 = ldg4(sin + F_P22 * fs + o);
+                r.ix = ldg4(cst + C_IX * fs + o);
+                r.iy = ldg4(cst + C_IY * fs + o);
+                r.rho = ldg4(cst + C_RHO * fs + o);
+            } else {
+                r.u1 = r.u2 = r.p11 = r.p12 = r.p21 = r.p22 = r.ix = r.iy = r.rho = zero4;
+            }
+        };
+        // u_new of row y from the row's u, p and constants, in place; a12 / a22 = p12 / p22 of the row above
+        auto primal = [&](int y, Row4 &r, const float4 &a12, const float4 &a22, float &err, bool count) {
+            // left neighbours of p11 / p21: the previous lane's .w (lane 0 is halo: its .x is never used)
+            const float l11 = __shfl_up_sync(0xffffffffu, r.p11.w, 1);
+            const float l21 = __shfl_up_sync(0xffffffffu, r.p21.w, 1);
+            const bool last_row = (y == ny - 1);
+            const bool tally = count && owner;
+            float o1[4], o2[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float u1 = TVL1_F4_GET(r.u1, k), u2 = TVL1_F4_GET(r.u2, k);
+                const bool last_col = (x0 + k >= nx - 1);
+                primal_px(u1, u2, TVL1_F4_GET(r.ix, k), TVL1_F4_GET(r.iy, k), TVL1_F4_GET(r.rho, k),
+                          grad_of(TVL1_F4_GET(r.ix, k), TVL1_F4_GET(r.iy, k)),
+                          last_col ? 0.f : TVL1_F4_GET(r.p11, k), (k == 0) ? l11 : TVL1_F4_GET(r.p11, (k + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(r.p12, k), TVL1_F4_GET(a12, k),
+                          last_col ? 0.f : TVL1_F4_GET(r.p21, k), (k == 0) ? l21 : TVL1_F4_GET(r.p21, (k + 3) & 3),
+                          last_row ? 0.f : TVL1_F4_GET(r.p22, k), TVL1_F4_GET(a22, k),
+                          P.l_t, P.theta, o1[k], o2[k]);
+                const float sq = update_sq(o1[k], u1, o2[k], u2);
+                err = __fadd_rn(err, (tally && x0 + k < nx) ? sq : 0.f);
+            }
+            r.u1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            r.u2 = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        };
+        // dual update of row y from the u_new of rows y (in c) and y+1 (in d): q = new p of row y
+        auto dual = [&](int y, const Row4 &c, const Row4 &d, float4 &q11, float4 &q12, float4 &q21, float4 &q22) {
+            const bool has_below = (y + 1 < ny);
+            const float r1 = __shfl_down_sync(0xffffffffu, c.u1.x, 1);
+            const float r2 = __shfl_down_sync(0xffffffffu, c.u2.x, 1);
+            float a11[4], a12[4], a21[4], a22[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool last_col = (x0 + k >= nx - 1);
+                const float c1 = TVL1_F4_GET(c.u1, k), c2 = TVL1_F4_GET(c.u2, k);
+                const float e1 = (k == 3) ? r1 : TVL1_F4_GET(c.u1, (k + 1) & 3);
+                const float e2 = (k == 3) ? r2 : TVL1_F4_GET(c.u2, (k + 1) & 3);
+                a11[k] = TVL1_F4_GET(c.p11, k); a12[k] = TVL1_F4_GET(c.p12, k);
+                a21[k] = TVL1_F4_GET(c.p21, k); a22[k] = TVL1_F4_GET(c.p22, k);
+                dual_px(last_col ? 0.f : e1 - c1, has_below ? TVL1_F4_GET(d.u1, k) - c1 : 0.f,
+                        last_col ? 0.f : e2 - c2, has_below ? TVL1_F4_GET(d.u2, k) - c2 : 0.f,
+                        P.taut, a11[k], a12[k], a21[k], a22[k]);
+            }
+            q11 = make_float4(a11[0], a11[1], a11[2], a11[3]);
+            q12 = make_float4(a12[0], a12[1], a12[2], a12[3]);
+            q21 = make_float4(a21[0], a21[1], a21[2], a21[3]);
+            q22 = make_float4(a22[0], a22[1], a22[2], a22[3]);
+        };
+        // A: row y of the start state arrives in r; first-iteration u_new in place (`above` = the row above, start state)
+        auto stage_a = [&](int y, Row4 &r, const float4 &a12, const float4 &a22) {
+            load_row(y, r);
+            primal(y, r, a12, a22, err1, y >= ys && y < ye);
+        };
+        // B: first-iteration p of row y in place.  Left of the image (the halo lane of the first strip column) the
+        // duals are the zeros the divergence reads there (src/operators.cpp:35-78), not an update of padding.
+        auto stage_b = [&](int y, Row4 &c, const Row4 &d) {
+            float4 q11, q12, q21, q22;
+            dual(y, c, d, q11, q12, q21, q22);
+            const bool outside = x0 < 0;                       // whole float4 left of column 0 (lane 0 of strip column 0)
+            c.p11 = outside ? zero4 : q11; c.p12 = outside ? zero4 : q12;
+            c.p21 = outside ? zero4 : q21; c.p22 = outside ? zero4 : q22;
+        };
+        // D: second-iteration p of row y and the stores of the row
+        auto stage_d = [&](int y, const Row4 &c, const Row4 &d) {
+            float4 q11, q12, q21, q22;
+            dual(y, c, d, q11, q12, q21, q22);
+            if (owner) {
+                const size_t o = (size_t) y * pitch + x0;
+                st4(sout + F_U1 * fs + o, c.u1);
+                st4(sout + F_U2 * fs + o, c.u2);
+                st4(sout + F_P11 * fs + o, q11);
+                st4(sout + F_P12 * fs + o, q12);
+                st4(sout + F_P21 * fs + o, q21);
+                st4(sout + F_P22 * fs + o, q22);
+            }
+        };
+        // one step of the march: output row t.  On entry `c` = row t (p', u''), `d` = row t+1 (start p, u', constants);
+        // `e` receives row t+2.
+        auto step = [&](int t, Row4 &c, Row4 &d, Row4 &e) {
+            if (t + 2 < ny) stage_a(t + 2, e, d.p12, d.p22);
+            if (t + 1 < ny) {
+                stage_b(t + 1, d, e);
+                primal(t + 1, d, c.p12, c.p22, err2, t + 1 < ye);       // C
+            }
+            stage_d(t, c, d);
+        };
+
+        Row4 r0, r1, r2;
+        // prologue: rows ys-1, ys, ys+1 of the first iteration, p' of ys-1 and ys, u'' of ys
+        float4 a12 = zero4, a22 = zero4;
+        if (ys > 0) {
+            if (ys > 1 && in_alloc) {
+                const size_t o = (size_t) (ys - 2) * pitch + x0;
+                a12 = ldg4(sin + F_P12 * fs + o);
+                a22 = ldg4(sin + F_P22 * fs + o);
+            }
+            stage_a(ys - 1, r2, a12, a22);
+            a12 = r2.p12; a22 = r2.p22;
+        } else {
+            r2.u1 = r2.u2 = r2.p11 = r2.p12 = r2.p21 = r2.p22 = r2.ix = r2.iy = r2.rho = zero4;
+        }
+        stage_a(ys, r0, a12, a22);
+        if (ys + 1 < ny) stage_a(ys + 1, r1, r0.p12, r0.p22);
+        else r1 = r0;
+        if (ys > 0) stage_b(ys - 1, r2, r0);
+        stage_b(ys, r0, r1);
+        primal(ys, r0, r2.p12, r2.p22, err2, true);                     // C(ys): above = p'(ys-1), zeros on the first row
+        for (int t = ys; t < ye; t += 3) {
+            step(t, r0, r1, r2);
+            if (t + 1 < ye) step(t + 1, r1, r2, r0);
+            if (t + 2 < ye) step(t + 2, r2, r0, r1);
+        }
+    }
+
+    // ---- per-iteration error sums: warp shuffle -> CTA -> fixed-order sum by the pair's last CTA ----
+    __shared__ double s_part[kT2T][32];
+    __shared__ double s_tot[kT2T];
+    __shared__ int s_last;
+    const double e1 = warp_sum((double) err1), e2 = warp_sum((double) err2);
+    if (lane == 0) { s_part[0][warp] = e1; s_part[1][warp] = e2; }
+    __syncthreads();
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    double *part = P.tb_partials + ((size_t) b * P.tb_parts) * kTbT;
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < kT2T; t++) {
+            double s = 0.0;
+            for (int w = 0; w < WY; w++) s += s_part[t][w];
+            part[(size_t) blk * kTbT + t] = s;
+        }
+        __threadfence();
+        const unsigned int tk = atomicAdd(&ctl->arrive, 1u);
+        s_last = (tk == (unsigned int) nblk - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile double *vp = part;
+    for (int t = 0; t < kT2T; t++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nblk; i += 32 * WY) s += vp[(size_t) i * kTbT + t];
+        s = warp_sum(s);
+        __syncthreads();
+        if (lane == 0) s_part[0][warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < WY; w++) tot += s_part[0][w];
+            s_tot[t] = tot / ((double) nx * (double) ny);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        decide_block(P, ctl, b, cur, kT2T, s_tot, (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
+}
+
+template <int R, int WY>
+__global__ void __launch_bounds__(32 * WY, 3)
+k_iterate_t2(const IterParams P)
+{
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+        atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
+    for_each_pair_of_slot<false>(P, true, [&](int b) { iterate_t2_pair<R, WY>(P, b); });
 }
 
 // Row-band mode over peer memory: barrier of all ranks through the mailboxes (start of a solve: no rank

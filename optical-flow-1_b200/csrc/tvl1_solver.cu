@@ -106,6 +106,14 @@ struct tvl1_ctx {
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
     bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
+    // ... which pays on the levels whose loops are long enough for two-iteration blocks (measured on the 256-pair
+    // batch at default epsilon: 4.6 iterations per warp step on level 1, 32.6 -> 29.5 ms; 1.9 on level 0, 51.2 -> 54.1 ms).
+    // Per level, from the iteration counts of the context's previous solve, with hysteresis; until there is a previous
+    // solve: every level but the finest.  The flow does not depend on the choice (same bits from every kernel).
+    unsigned int t2_levels = ~1u;            // bit s: level s may use it
+    bool t2_adapt = true;                    // TVL1_T2_ADAPT=0: keep the initial mask (TVL1_T2_LEVELS=<mask>)
+    int use_t2 = 1;                          // TVL1_T2=0: never use the two-iterations-per-launch marching kernel; 2: wherever
+                                             // the shared-memory kernel is not used, however small the launch (tests)
     bool zero_in_first = true;               // TVL1_ZERO_PASS=1: zero the duals of a streamed level with a pass of their own (A/B)
     bool gauss_shfl = true;                  // TVL1_GAUSS_SHFL=0: the marching blur that loads its own row inputs (A/B)
     bool warp_tma = true;                    // TVL1_WARP_TMA=0: stage the warp kernel's box with cp.async only
@@ -379,6 +387,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
         off += 2 * (size_t) B * w.plane(s);
         parts = std::max(parts, iterate_parts(w.lv[s]));
         w.tb_parts = std::max(w.tb_parts, ceil_div(cx, kTbW) * ceil_div(cy, kTbH));
+        w.tb_parts = std::max(w.tb_parts, ceil_div(cx, kT2W) * ceil_div(cy, 16 * kIterWY));      // strips of k_iterate_t2
         w.res_cluster[s] = pick_cluster(ctx, w.lv[s], B, &w.res_rows[s]);
     }
     // row-band mode gathers equal-sized bands in place: round the rows of a plane up to a multiple of the rank count
@@ -398,7 +407,7 @@ int ensure_workspace(tvl1_ctx *ctx, int nx, int ny, int nscales, double zfactor,
     CK(cudaMalloc(&w.loop, sizeof(LoopCtl)));
     CK(cudaMalloc(&w.stat_iters, sizeof(int) * (size_t) B * stat_stride));
     CK(cudaMalloc(&w.stat_errs, sizeof(double) * (size_t) B * stat_stride));
-    CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS));
+    CK(cudaMalloc(&w.counters, sizeof(unsigned long long) * kCounterWords));
     w.bytes = (off + 2 * w.set_stride + C_COUNT * w.field_stride) * fl;
     // padding columns are never consumed, but keep them finite
     CK(cudaMemsetAsync(w.state, 0, 2 * w.set_stride * fl, ctx->stream));
@@ -510,7 +519,7 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
     IterParams P = {};
     P.state = w.state; P.consts = w.consts; P.ctl = w.ctl; P.partials = w.partials;
     P.loop = w.loop; P.cond = 0; P.use_cond = 0;
-    P.batch = w.B; P.tb_partials = w.tb_partials; P.tb_parts = w.tb_parts; P.tb = 0;
+    P.batch = w.B; P.tb_partials = w.tb_partials; P.tb_parts = w.tb_parts; P.tb = 0; P.tb_max = kTbT;
     P.row_begin = 0; P.row_end = lv.ny; P.band_sum = nullptr;
     P.stat_iters = w.stat_iters; P.stat_errs = w.stat_errs;
     P.px_iters = w.counters;
@@ -528,6 +537,25 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
 int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B, bool tail);
 bool tb_usable(tvl1_ctx *ctx, const Level &l, int B);
 
+// Two iterations per launch in registers (k_iterate_t2): for the launches that saturate HBM, i.e. where the
+// shared-memory kernel is not used -- big lock-step batches, and chunks solved while other lanes share the GPU.
+// Needs enough strips of 120 x 64 pixels to fill the GPU; whole images only (no row bands).
+bool t2_usable(const tvl1_ctx *ctx, const Level &l, int B, bool peers, int level)
+{
+    if (!ctx->use_t2 || peers) return false;
+    if (ctx->use_t2 == 2) return true;
+    if (!((ctx->t2_levels >> std::min(level, 31)) & 1u)) return false;
+    const long long strips = (long long) ceil_div(l.nx, kT2W) * ceil_div(l.ny, 16 * kIterWY) * B;
+    return l.nx >= kT2W && l.ny >= 16 && strips >= 4ll * ctx->sm_count;
+}
+
+// mode: 0 one iteration per launch, 1 blocks of up to kTbT through k_iterate_tb, 2 blocks of two through k_iterate_t2
+void set_blocking(IterParams &P, int mode)
+{
+    P.tb = mode;
+    P.tb_max = mode == 2 ? kT2T : kTbT;
+}
+
 // grid.z of the iteration kernels: pair slots (see for_each_pair_of_slot).  Enough slots that a launch
 // with every pair active still has a few thousand CTAs, few enough that a launch with hardly any
 // active pair does not spend its time starting CTAs that exit at once.
@@ -537,6 +565,25 @@ int pair_slots(const tvl1_ctx *ctx, int tiles, int B, bool tail = false, bool ro
     // kernel goes round again instead: any number of slots)
     if (tail) return std::min(B, std::max(rounds ? 1 : ceil_div(B, 32), ceil_div(ctx->tail_slot_ctas, std::max(tiles, 1))));
     return std::min(B, std::max(std::max(32, ceil_div(B, 32)), ceil_div(ctx->slot_ctas, std::max(tiles, 1))));
+}
+
+int launch_iterate_t2(tvl1_ctx *ctx, const IterParams &P, int B, bool tail)
+{
+    const int rows = P.row_end - P.row_begin;
+    const int tiles_x = ceil_div(P.lv.nx, kT2W);
+    const int Bw = tail ? std::max(1, ctx->tail_pairs / 8) : B;
+    // tall strips: the two halo rows above and the one below are loaded per strip
+    if ((long long) tiles_x * ceil_div(rows, 32 * kIterWY) * Bw >= 4ll * ctx->sm_count) {
+        dim3 g(tiles_x, ceil_div(rows, 32 * kIterWY), 1);
+        g.z = pair_slots(ctx, g.x * g.y, B, tail);
+        k_iterate_t2<32, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    } else {
+        dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), 1);
+        g.z = pair_slots(ctx, g.x * g.y, B, tail);
+        k_iterate_t2<16, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+    }
+    CK(cudaGetLastError());
+    return TVL1_OK;
 }
 
 // `tail`: narrow launch for the late iterations of a lock-step batch, when only a few pairs are left
@@ -565,7 +612,9 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B, bool tail = false)
         k_iterate_t1<4, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());      // launches of this kernel are counted on the device (fetch_stats)
-    if (P.tb) TRY(launch_iterate_tb(ctx, P, B, tail));   // pairs whose next block has more than one iteration
+    // pairs whose next block has more than one iteration
+    if (P.tb == 2) TRY(launch_iterate_t2(ctx, P, B, tail));
+    else if (P.tb) TRY(launch_iterate_tb(ctx, P, B, tail));
     return TVL1_OK;
 }
 
@@ -774,7 +823,7 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B, bool first_zero)
         // the pairs of the tail are the slow ones (tens of iterations where the batch needs two): worth
         // temporal blocking even where the full batch is not (a wide launch of both kernels costs more
         // than blocking saves; a narrow one does not)
-        if (!P.tb && ctx->tail_tb && tb_usable(ctx, P.lv, ctx->tail_pairs)) P.tb = 1;
+        if (P.tb != 1 && ctx->tail_tb && tb_usable(ctx, P.lv, ctx->tail_pairs)) set_blocking(P, 1);
         return add_while_node(ctx, P, B, h_all, true);
     }
     return add_while_node(ctx, P, B, h_all, false);
@@ -839,7 +888,9 @@ int run_level(tvl1_ctx *ctx, int s, int B, const tvl1_params &prm, int stat_base
         k_begin_warp<<<ceil_div(B, 128), 128, 0, ctx->stream>>>(w.ctl, w.loop, B);   // :111-112
         CKL(ctx);
         IterParams P = iter_params(ctx, w.lv[s], prm, stat_base + wi, kMaxIterations, s);
-        P.tb = tb_usable(ctx, w.lv[s], B) ? 1 : 0;
+        // blocks of two in registers where the launch saturates HBM and the level's loops are long enough, else blocks of up
+        // to four in shared memory where the launch is small enough for that to pay, else one iteration per launch
+        set_blocking(P, t2_usable(ctx, w.lv[s], B, false, s) ? 2 : tb_usable(ctx, w.lv[s], B) ? 1 : 0);
         TRY(run_iterations(ctx, P, B, chunk_hint, zero_in_first && wi == 0));   // :113-182
     }
     return TVL1_OK;
@@ -861,7 +912,7 @@ void reset_stats(tvl1_ctx *ctx) { ctx->stats = tvl1_stats{}; }
 int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_out)
 {
     const Workspace &w = ctx->ws;
-    unsigned long long c[2 * TVL1_MAX_LEVELS] = { 0 };
+    unsigned long long c[kCounterWords] = { 0 };
     CK(cudaMemcpyAsync(c, w.counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
     if (iters_out)
         CK(cudaMemcpy2DAsync(iters_out, sizeof(int) * nstat, w.stat_iters, sizeof(int) * w.stat_stride,
@@ -870,6 +921,19 @@ int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_ou
         CK(cudaMemcpy2DAsync(errs_out, sizeof(double) * nstat, w.stat_errs, sizeof(double) * w.stat_stride,
                              sizeof(double) * nstat, B, cudaMemcpyDeviceToHost, ctx->stream));
     CK(sleep_until_done(ctx));
+    if (ctx->t2_adapt && ctx->use_t2 == 1 && nstat > 0 && !ctx->hs_mode) {
+        // iterations per loop (pair and warp step) on each streamed level of this solve -> which levels the next one
+        // blocks (t2_usable).  Loops are counted up to kLoopClip iterations: one slow pair that runs to the cap must not
+        // switch the kernel for its whole chunk and back (every switch re-captures the solve graph).
+        const int nlev = (int) w.lv.size();
+        const int warps = std::max(1, nstat / std::max(1, nlev));
+        for (int l = 0; l < nlev && l < 16; l++) {
+            if (w.res_cluster[l] != 0) continue;
+            const double mean = (double) c[2 * TVL1_MAX_LEVELS + l] / ((double) B * warps);
+            if (mean >= 3.5) ctx->t2_levels |= 1u << l;
+            else if (mean < 2.5) ctx->t2_levels &= ~(1u << l);
+        }
+    }
     for (int l = 0; l < TVL1_MAX_LEVELS; l++) {
         ctx->stats.pixel_iterations += c[l];
         ctx->stats.level_pixel_iterations[l] += c[l];
@@ -950,7 +1014,11 @@ int run_coarse_to_fine(tvl1_ctx *ctx, int B, const tvl1_params &prm, bool multis
 {
     if (!ctx->use_graph) return enqueue_coarse_to_fine(ctx, B, prm, multiscale);
     // (the kernel choice depends on whether other lanes share the GPU: tb_usable)
-    return replay_graph(ctx, ctx->sg, prm, multiscale, ctx->shared_gpu ? 1 : 0,
+    // (... and on the levels the two-iteration kernel serves, which follow the previous solve: t2_adapt)
+    long long t2_key = 0;
+    for (int s = 0; s < (int) ctx->ws.lv.size() && s < 16; s++)
+        if (ctx->use_t2 == 1 && ctx->ws.res_cluster[s] == 0 && ((ctx->t2_levels >> s) & 1u)) t2_key |= 2ll << s;
+    return replay_graph(ctx, ctx->sg, prm, multiscale, (ctx->shared_gpu ? 1 : 0) | t2_key,
                         [&]() { return enqueue_coarse_to_fine(ctx, B, prm, multiscale); });
 }
 
@@ -966,7 +1034,7 @@ int build_pyramid(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, int 
     const double zsigma = TVL1_ZOOM_SIGMA_ZERO * std::sqrt(1.0 / (prm.zfactor * prm.zfactor) - 1.0);
     for (int s = 1; s < ns; s++) TRY(check_sigma(ctx, zsigma, w.lv[s - 1].nx, zoom));
 
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * kCounterWords, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
 
@@ -1033,7 +1101,7 @@ int run_single_scale(tvl1_ctx *ctx, int B, const float *dI0, const float *dI1, f
     Workspace &w = ctx->ws;
     cudaStream_t st = ctx->stream;
     Span total(ctx, 2);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * kCounterWords, st));
     k_init_ctl<<<ceil_div(B, 128), 128, 0, st>>>(w.ctl, w.mm, B);
     CKL(ctx);
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), B);
@@ -2179,6 +2247,9 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
+    if (const char *ml = std::getenv("TVL1_T2_LEVELS")) ctx->t2_levels = (unsigned int) std::strtoul(ml, nullptr, 0);
+    if (const char *ta = std::getenv("TVL1_T2_ADAPT")) ctx->t2_adapt = !(ta[0] == '0');
+    if (const char *t2 = std::getenv("TVL1_T2")) ctx->use_t2 = std::max(0, std::min(2, std::atoi(t2)));
     if (const char *zp = std::getenv("TVL1_ZERO_PASS")) ctx->zero_in_first = !(zp[0] == '1');
     if (const char *gs = std::getenv("TVL1_GAUSS_SHFL")) ctx->gauss_shfl = !(gs[0] == '0');
     if (const char *wt = std::getenv("TVL1_WARP_TMA")) ctx->warp_tma = !(wt[0] == '0');
@@ -2690,7 +2761,7 @@ int tvl1_iterate_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float *p12
     if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
     CKL(ctx);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * kCounterWords, st));
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
     float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
     for (int f = 0; f < 6; f++) {
@@ -2756,7 +2827,7 @@ int tvl1_iterate_resident_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, f
     if (!buf || !trace) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
     CKL(ctx);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * kCounterWords, st));
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
     float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
     for (int f = 0; f < 6; f++) {
@@ -2814,7 +2885,7 @@ int tvl1_iterate_loop_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float
     if (!buf) { ctx->err = "cudaMalloc failed"; return TVL1_ERR_CUDA; }
     k_init_ctl<<<1, 32, 0, st>>>(w.ctl, w.mm, 1);
     CKL(ctx);
-    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2 * TVL1_MAX_LEVELS, st));
+    CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * kCounterWords, st));
     dim3 g(ceil_div(nx, 32), ceil_div(ny, 8), 1);
     float *st_host[6] = { u1, u2, p11, p12, p21, p22 };
     for (int f = 0; f < 6; f++) {
@@ -2836,13 +2907,14 @@ int tvl1_iterate_loop_f32(tvl1_ctx *ctx, float *u1, float *u2, float *p11, float
     IterParams P = iter_params(ctx, w.lv[0], prm, 0, max_iter);
     if (epsilon < 0) P.eps2 = -1.0;                          // never stop before max_iter
     if (temporal_blocking) {
-        if (!tb_usable(ctx, w.lv[0], 1)) return fail_arg(ctx, "temporally blocked kernel not usable for this size");
-        P.tb = 1;
-        if (temporal_blocking > 1) {                          // force full blocks from the first launch on
+        const bool t2 = temporal_blocking >= 3;               // 3 / 4: the two-iteration marching kernel
+        if (!t2 && !tb_usable(ctx, w.lv[0], 1)) return fail_arg(ctx, "temporally blocked kernel not usable for this size");
+        set_blocking(P, t2 ? 2 : 1);
+        if (temporal_blocking == 2 || temporal_blocking == 4) {   // force full blocks from the first launch on
             PairCtl c;
             CK(cudaMemcpyAsync(&c, w.ctl, sizeof c, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            c.nsteps = std::min(kTbT, max_iter);
+            c.nsteps = std::min(P.tb_max, max_iter);
             CK(cudaMemcpyAsync(w.ctl, &c, sizeof c, cudaMemcpyHostToDevice, st));
         }
     }
@@ -2888,6 +2960,13 @@ int tvl1_bench_iterate(tvl1_ctx *ctx, int npairs, int nx, int ny, int launches, 
     prm.epsilon = 0.0;
     IterParams P = iter_params(ctx, w.lv[0], prm, 0, 1 << 30);
     P.eps2 = -1.0;   // never stop: every launch does the full work
+    // TVL1_BENCH_TB=1 / 2: blocks through k_iterate_tb / k_iterate_t2 (the device switches to full blocks after two
+    // single iterations: a launch then advances every pair by 4 / 2 iterations)
+    if (const char *bt = std::getenv("TVL1_BENCH_TB")) {
+        const int mode = std::atoi(bt);
+        if (mode == 1 && tb_usable(ctx, w.lv[0], 1)) set_blocking(P, 1);
+        if (mode == 2) set_blocking(P, 2);
+    }
     for (int i = 0; i < 3; i++) TRY(launch_iterate(ctx, P, npairs));
     cudaEvent_t a = take_event(ctx), b = take_event(ctx);
     CK(cudaEventRecord(a, st));

@@ -271,7 +271,26 @@ def test_iterate_temporally_blocked_fixed_count(gpu, oracle_f64, shape, iters):
     assert np.isclose(got[7], ref[6][-1], rtol=1e-4)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(96, 128), (75, 131), (270, 480), (33, 70), (17, 119), (130, 121), (64, 241), (5, 9), (1, 300), (300, 1)])
+@pytest.mark.parametrize("iters", [2, 7, 12])
+def test_iterate_two_per_launch_fixed_count(gpu, oracle_f64, shape, iters):
+    """k_iterate_t2 (two iterations per launch in registers: the marching kernel with a second iteration one row
+    behind the first, 120 owned columns + a halo lane either side per warp) for a fixed number of passes: the same
+    bits as one iteration per launch (k_iterate_t1), the reference's values within fp32, half the launches.  Shapes
+    around the strip width (119 / 120 / 121 / 241 columns), strips that end inside the image, degenerate images."""
+    u1, u2, p, rho_c, ix, iy, grad = _iterate_inputs(shape, seed=23)
+    got = gpu.iterate_loop(u1, u2, *p, rho_c, ix, iy, 0.25, 0.15, 0.3, -1.0, iters, temporal_blocking=4)
+    one = gpu.iterate_loop(u1, u2, *p, rho_c, ix, iy, 0.25, 0.15, 0.3, -1.0, iters, temporal_blocking=0)
+    ref = oracle_f64.iterate(u1, u2, *p, rho_c, ix, iy, grad, 0.25, 0.15, 0.3, iters)
+    assert got[6] == iters and one[6] == iters
+    assert got[8] == -(-iters // 2), "launches: %d" % got[8]          # ceil(iters / 2) blocks
+    for k, name in enumerate(("u1", "u2", "p11", "p12", "p21", "p22")):
+        assert np.array_equal(got[k], one[k]), name
+        assert np.abs(got[k] - ref[k]).max() < 2e-4 * iters, name
+    assert np.isclose(got[7], ref[6][-1], rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("eps", [0.05, 0.02])
 def test_iterate_loop_exact_stop(gpu, oracle_f64, mode, eps):
     """Exact stopping under temporal blocking: whatever mix of single iterations, blocks and replays
@@ -302,11 +321,12 @@ def test_kernel_variants_agree_bitwise(oracle_f64):
     import os
     I0, I1 = _cases.synth.make_pair(352, 264, seed=17, scale=0.6)
     kw = dict(nscales=3, warps=3, eps=0.01)
-    saved = {k: os.environ.pop(k, None) for k in ("TVL1_NO_TB", "TVL1_NO_RESIDENT")}
+    saved = {k: os.environ.pop(k, None) for k in ("TVL1_NO_TB", "TVL1_NO_RESIDENT", "TVL1_T2")}
     results = []
     try:
-        for env in ({}, {"TVL1_NO_TB": "1"}, {"TVL1_NO_RESIDENT": "1"}, {"TVL1_NO_TB": "1", "TVL1_NO_RESIDENT": "1"}):
-            for k in ("TVL1_NO_TB", "TVL1_NO_RESIDENT"):
+        for env in ({}, {"TVL1_NO_TB": "1"}, {"TVL1_NO_RESIDENT": "1"}, {"TVL1_NO_TB": "1", "TVL1_NO_RESIDENT": "1"},
+                    {"TVL1_NO_TB": "1", "TVL1_T2": "0"}, {"TVL1_NO_TB": "1", "TVL1_NO_RESIDENT": "1", "TVL1_T2": "0"}):
+            for k in ("TVL1_NO_TB", "TVL1_NO_RESIDENT", "TVL1_T2"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             g = pkg.TVL1(device=0)           # the switches are read when the context is made
@@ -323,6 +343,31 @@ def test_kernel_variants_agree_bitwise(oracle_f64):
         assert np.array_equal(a[0], r[0]) and np.array_equal(a[1], r[1])
 
 
+@pytest.mark.parametrize("nx,ny,B", [(250, 190, 5), (121, 67, 9)])
+def test_two_per_launch_kernel_in_the_solver(nx, ny, B, monkeypatch):
+    """The solver with its streamed levels on the two-iterations-per-launch kernel (TVL1_T2=2 forces it where the
+    launch would be too small to choose it) against one iteration per launch: the device's block predictions, the
+    rejected blocks and their replays must leave every pair with the same iteration counts and the same bits."""
+    pairs = [_cases.synth.make_pair(nx, ny, seed=40 + b, scale=0.3 + 0.1 * (b % 3)) for b in range(B)]
+    I0 = np.stack([p[0] for p in pairs])
+    I1 = np.stack([p[1] for p in pairs])
+    kw = dict(nscales=3, warps=3, eps=0.01)
+    monkeypatch.setenv("TVL1_NO_RESIDENT", "1")
+    monkeypatch.setenv("TVL1_NO_TB", "1")
+    out = []
+    for t2 in ("0", "2"):
+        monkeypatch.setenv("TVL1_T2", t2)
+        g = pkg.TVL1(device=0, max_batch=B)
+        out.append(g.Dual_TVL1_optic_flow_multiscale(I0, I1, **kw))
+        st = g.stats()
+        out[-1] = out[-1] + (sum(st["level_iterate_launches"]),)
+        g.close()
+    a, b = out
+    assert np.array_equal(a[2], b[2]), (a[2].tolist(), b[2].tolist())
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert b[4] != a[4]                     # the blocked path really ran (launch counts differ)
+
+
 def test_iterate_loop_variants_agree_bitwise(gpu, oracle_f64):
     """Fixed 13 iterations on one level: single iterations (mode 0) against blocks of 4 (mode 2)."""
     I0, I1 = _cases.synth.make_pair(200, 136, seed=5, scale=0.2)
@@ -330,9 +375,11 @@ def test_iterate_loop_variants_agree_bitwise(gpu, oracle_f64):
     c = oracle_f64.warp_precompute(I0, I1, z, z)
     a = gpu.iterate_loop(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, -1.0, 13, 0)
     b = gpu.iterate_loop(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, -1.0, 13, 2)
-    assert a[6] == b[6] == 13
+    t2 = gpu.iterate_loop(z, z, z, z, z, z, c["rho_c"], c["I1wx"], c["I1wy"], 0.25, 0.15, 0.3, -1.0, 13, 4)
+    assert a[6] == b[6] == t2[6] == 13
     for k in range(6):
         assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], t2[k]), k
 
 
 def test_iterate_loop_replay_on_immediate_stop(gpu, oracle_f64):
