@@ -99,6 +99,10 @@ int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes);
  * Writes up to `cap` chunk sizes to `sizes` and returns the number of chunks. */
 int tvl1_plan_chunks(int npairs, int max_batch, int *sizes, int cap);
 int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out);
+/* Bit s set: pyramid level s of the next solve may run two iterations per launch (k_iterate_t2) where the launch is
+ * large enough to saturate HBM.  Follows the loop lengths of the context's previous solve (diagnostics; the flow does
+ * not depend on it). */
+unsigned int tvl1_get_blocked_levels(const tvl1_ctx *ctx);
 void *tvl1_get_stream(const tvl1_ctx *ctx);        /* the cudaStream_t all work of this context is issued on */
 void tvl1_default_params(tvl1_params *p);          /* tvl1flow_main.cpp:24-33 with nscales = 5 */
 

@@ -2356,6 +2356,11 @@ int tvl1_plan_chunks(int npairs, int max_batch, int *sizes, int cap)
     return (int) chunks.size();
 }
 
+unsigned int tvl1_get_blocked_levels(const tvl1_ctx *ctx)
+{
+    return ctx && ctx->use_t2 ? (ctx->use_t2 == 2 ? ~0u : ctx->t2_levels) : 0u;
+}
+
 void *tvl1_get_stream(const tvl1_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
 
 int tvl1_get_stats(const tvl1_ctx *ctx, tvl1_stats *out)

@@ -140,6 +140,11 @@ class TVL1:
         self.lib.tvl1_get_stream.restype = C.c_void_p
         return int(self.lib.tvl1_get_stream(self.ctx) or 0)
 
+    def blocked_levels(self):
+        """Bit mask of the pyramid levels whose big launches run two iterations per launch (tvl1_get_blocked_levels)."""
+        self.lib.tvl1_get_blocked_levels.restype = C.c_uint
+        return int(self.lib.tvl1_get_blocked_levels(self.ctx))
+
     def stats(self):
         s = Stats()
         self._ck(self.lib.tvl1_get_stats(self.ctx, C.byref(s)))
