@@ -46,6 +46,10 @@ struct PairCtl {
     // that launch is the exact replay of a block that overshot the stopping point
     int nsteps;
     int replay;
+    // a level's first block ran two iterations from zero duals (k_iterate_t2 with p_zero) and overshot the stopping
+    // point: the replay of its first iteration takes the duals as zero again (the start state's were never written)
+    int pzero;
+    int pad;
 };
 
 // Whole-batch loop state of the current warp step.
@@ -712,6 +716,7 @@ __global__ void k_begin_warp(PairCtl *ctl, LoopCtl *loop, int B)
         const int n_old = ctl[b].n;
         ctl[b].nsteps = n_old >= 2 * kTbT ? kTbT : (n_old >= 4 ? 2 : 1);
         ctl[b].replay = 0;
+        ctl[b].pzero = 0;
         ctl[b].active = 1;
         ctl[b].n = 0;
         ctl[b].arrive = 0u;
@@ -1122,6 +1127,8 @@ struct IterParams {
     // than bulk_min pairs still iterate, the second (narrow grid) when none does
     cudaGraphConditionalHandle cond_bulk;
     int bulk_min;                      // -1: single-phase loop
+    int take_all;                      // this launch serves every active pair whatever its block length (a level's first
+                                       // block through k_iterate_t2)
     int p_zero;                        // first iteration of a level: the duals are zero (src/tvl1flow.cpp:87-90) and
                                        // are neither read nor were they written by a zeroing pass (k_iterate_t1 only)
     double *tb_partials;               // [batch][tb_parts][kTbT] per-CTA error sums of k_iterate_tb
@@ -1170,8 +1177,10 @@ __device__ __forceinline__ void decide_block(const IterParams &P, PairCtl *ctl, 
     if (stop_at >= 0 && stop_at < ns - 1) {                 // overshoot: replay exactly stop_at+1 iterations
         ctl->nsteps = stop_at + 1;
         ctl->replay = 1;
+        ctl->pzero = P.p_zero;                              // ... from zero duals if that is what the block started from
         return;
     }
+    ctl->pzero = 0;
     const double last = errs[ns - 1];
     const double prev = ns >= 2 ? errs[ns - 2] : ctl->err;
     const int n = n0 + ns;
@@ -1310,7 +1319,7 @@ __device__ __forceinline__ void for_each_pair_of_slot(const IterParams &P, bool 
             // every warp of the CTA reads the same values here
             const PairCtl *c = P.ctl + mine;
             const bool blocked = P.tb && c->nsteps > 1;
-            take = c->active && (blocked == tb_kernel);
+            take = c->active && (P.take_all || blocked == tb_kernel);
         }
         const unsigned int todo0 = __ballot_sync(0xffffffffu, take);
         if (todo0 == 0u) continue;                   // the common case of a late launch (CTA-uniform)
@@ -1336,6 +1345,7 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cur = ctl->cur;
+    const bool p_zero = P.p_zero || ctl->pzero;     // CTA-uniform: the duals of the start state read as zero
     const float *sin = P.state + (size_t) cur * P.set_stride + (size_t) b * P.plane0;
     float *sout = P.state + (size_t) (cur ^ 1) * P.set_stride + (size_t) b * P.plane0;
     const float *cst = P.consts + (size_t) b * P.plane0;
@@ -1355,7 +1365,7 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
                 const size_t o = (size_t) y * pitch + x0;
                 r.u1 = ldg4(sin + F_U1 * fs + o);
                 r.u2 = ldg4(sin + F_U2 * fs + o);
-                if (P.p_zero) {                      // launch-uniform
+                if (p_zero) {                        // CTA-uniform
                     r.p11 = r.p12 = r.p21 = r.p22 = make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
                     r.p11 = ldg4(sin + F_P11 * fs + o);
@@ -1378,7 +1388,7 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
             float l11 = __shfl_up_sync(0xffffffffu, r.p11.w, 1);
             float l21 = __shfl_up_sync(0xffffffffu, r.p21.w, 1);
             if (lane == 0) {
-                const bool has = x0 > 0 && !P.p_zero;
+                const bool has = x0 > 0 && !p_zero;
                 const size_t o = (size_t) y * pitch + x0 - 1;
                 l11 = has ? __ldg(sin + F_P11 * fs + o) : 0.f;
                 l21 = has ? __ldg(sin + F_P21 * fs + o) : 0.f;
@@ -1465,7 +1475,7 @@ __device__ __forceinline__ void iterate_t1_pair(const IterParams &P, const int b
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         Row4 ra, rb;
         float4 a12 = zero4, a22 = zero4;
-        if (ys > 0 && in_alloc && !P.p_zero) {
+        if (ys > 0 && in_alloc && !p_zero) {
             const size_t o = (size_t) (ys - 1) * pitch + x0;
             a12 = ldg4(sin + F_P12 * fs + o);
             a22 = ldg4(sin + F_P22 * fs + o);
@@ -1576,10 +1586,14 @@ __device__ __forceinline__ void iterate_t2_pair(const IterParams &P, const int b
                 const size_t o = (size_t) y * pitch + x0;
                 r.u1 = ldg4(sin + F_U1 * fs + o);
                 r.u2 = ldg4(sin + F_U2 * fs + o);
-                r.p11 = ldg4(sin + F_P11 * fs + o);
-                r.p12 = ldg4(sin + F_P12 * fs + o);
-                r.p21 = ldg4(sin + F_P21 * fs + o);
-                r.p22 = ldg4(sin + F_P22 * fs + o);
+                if (P.p_zero) {                      // launch-uniform: a level's first block (src/tvl1flow.cpp:87-90)
+                    r.p11 = r.p12 = r.p21 = r.p22 = zero4;
+                } else {
+                    r.p11 = ldg4(sin + F_P11 * fs + o);
+                    r.p12 = ldg4(sin + F_P12 * fs + o);
+                    r.p21 = ldg4(sin + F_P21 * fs + o);
+                    r.p22 = ldg4(sin + F_P22 * fs + o);
+                }
                 r.ix = ldg4(cst + C_IX * fs + o);
                 r.iy = ldg4(cst + C_IY * fs + o);
                 r.rho = ldg4(cst + C_RHO * fs + o);
@@ -1678,7 +1692,7 @@ __device__ __forceinline__ void iterate_t2_pair(const IterParams &P, const int b
         // prologue: rows ys-1, ys, ys+1 of the first iteration, p' of ys-1 and ys, u'' of ys
         float4 a12 = zero4, a22 = zero4;
         if (ys > 0) {
-            if (ys > 1 && in_alloc) {
+            if (ys > 1 && in_alloc && !P.p_zero) {
                 const size_t o = (size_t) (ys - 2) * pitch + x0;
                 a12 = ldg4(sin + F_P12 * fs + o);
                 a22 = ldg4(sin + F_P22 * fs + o);

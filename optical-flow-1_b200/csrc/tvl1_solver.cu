@@ -112,6 +112,7 @@ struct tvl1_ctx {
     // solve: every level but the finest.  The flow does not depend on the choice (same bits from every kernel).
     unsigned int t2_levels = ~1u;            // bit s: level s may use it
     bool t2_adapt = true;                    // TVL1_T2_ADAPT=0: keep the initial mask (TVL1_T2_LEVELS=<mask>)
+    bool t2_first = true;                    // TVL1_T2_FIRST=0: a streamed level's first launch is one iteration (k_iterate_t1)
     int use_t2 = 1;                          // TVL1_T2=0: never use the two-iterations-per-launch marching kernel; 2: wherever
                                              // the shared-memory kernel is not used, however small the launch (tests)
     bool zero_in_first = true;               // TVL1_ZERO_PASS=1: zero the duals of a streamed level with a pass of their own (A/B)
@@ -549,6 +550,19 @@ bool t2_usable(const tvl1_ctx *ctx, const Level &l, int B, bool peers, int level
     return l.nx >= kT2W && l.ny >= 16 && strips >= 4ll * ctx->sm_count;
 }
 
+// A streamed level starts from zero duals (src/tvl1flow.cpp:87-90), and its first warp step practically never stops
+// after one iteration: where the launch is big enough for k_iterate_t2, the level's first LAUNCH runs its first TWO
+// iterations for every pair, taking the duals as zero (no zeroing pass, no loads) -- 47 B per pixel instead of 44 + 60.
+// A pair that does stop after one iteration has the block rejected and its first iteration replayed, again from
+// zero duals (PairCtl::pzero).
+bool t2_first_usable(const tvl1_ctx *ctx, const IterParams &P, int B)
+{
+    if (!ctx->t2_first || ctx->use_t2 == 0 || P.peers.enabled || P.max_iter < 2) return false;
+    if (ctx->use_t2 == 2) return true;
+    const long long strips = (long long) ceil_div(P.lv.nx, kT2W) * ceil_div(P.lv.ny, 16 * kIterWY) * B;
+    return P.lv.nx >= kT2W && P.lv.ny >= 16 && strips >= 4ll * ctx->sm_count;
+}
+
 // mode: 0 one iteration per launch, 1 blocks of up to kTbT through k_iterate_tb, 2 blocks of two through k_iterate_t2
 void set_blocking(IterParams &P, int mode)
 {
@@ -790,6 +804,21 @@ int add_while_node(tvl1_ctx *ctx, const IterParams &P, int B, cudaGraphCondition
 // first_zero: this is the first warp step of a level whose duals were NOT zeroed by a pass of their own: the
 // loop's first iteration (which always runs: error starts at infinity) is launched explicitly, with the duals
 // taken as zero instead of read, before the while nodes -- 32 B per pixel and level less HBM traffic.
+// First launch of a streamed level (duals read as zero): two iterations for every pair through k_iterate_t2 where
+// that kernel fits (t2_first_usable), else one iteration through k_iterate_t1.
+int launch_first_zero(tvl1_ctx *ctx, const IterParams &P, int B)
+{
+    IterParams P0 = P;
+    P0.p_zero = 1;
+    if (t2_first_usable(ctx, P, B)) {
+        set_blocking(P0, 2);
+        P0.take_all = 1;
+        return launch_iterate_t2(ctx, P0, B, false);
+    }
+    P0.tb = 0;                          // every pair's first block is one iteration: the streaming kernel serves it
+    return launch_iterate(ctx, P0, B);
+}
+
 int add_while_loop(tvl1_ctx *ctx, IterParams P, int B, bool first_zero)
 {
     cudaStreamCaptureStatus status;
@@ -812,12 +841,7 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B, bool first_zero)
         P.cond_bulk = h_bulk;
         P.bulk_min = ctx->tail_pairs;
     }
-    if (first_zero) {
-        IterParams P0 = P;
-        P0.p_zero = 1;
-        P0.tb = 0;                      // every pair's first block is one iteration: the streaming kernel serves it
-        TRY(launch_iterate(ctx, P0, B));
-    }
+    if (first_zero) TRY(launch_first_zero(ctx, P, B));
     if (two_phase) {
         TRY(add_while_node(ctx, P, B, h_bulk, false));
         // the pairs of the tail are the slow ones (tens of iterations where the batch needs two): worth
@@ -842,11 +866,8 @@ int run_iterations(tvl1_ctx *ctx, const IterParams &P, int B, int &chunk_hint, b
     int launched = 0;
     if (first_zero) {
         Span sp(ctx, 0, P.level);
-        IterParams P0 = P;
-        P0.p_zero = 1;
-        P0.tb = 0;
-        TRY(launch_iterate(ctx, P0, B));
-        launched = 1;
+        TRY(launch_first_zero(ctx, P, B));
+        launched = 2;
     }
     int chunk = std::max(1, std::min(chunk_hint, P.max_iter));
     while (launched < P.max_iter) {
@@ -2248,6 +2269,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
     if (const char *ml = std::getenv("TVL1_T2_LEVELS")) ctx->t2_levels = (unsigned int) std::strtoul(ml, nullptr, 0);
+    if (const char *tf = std::getenv("TVL1_T2_FIRST")) ctx->t2_first = !(tf[0] == '0');
     if (const char *ta = std::getenv("TVL1_T2_ADAPT")) ctx->t2_adapt = !(ta[0] == '0');
     if (const char *t2 = std::getenv("TVL1_T2")) ctx->use_t2 = std::max(0, std::min(2, std::atoi(t2)));
     if (const char *zp = std::getenv("TVL1_ZERO_PASS")) ctx->zero_in_first = !(zp[0] == '1');

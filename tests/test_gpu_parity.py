@@ -351,6 +351,9 @@ def test_two_per_launch_kernel_in_the_solver(nx, ny, B, monkeypatch):
     pairs = [_cases.synth.make_pair(nx, ny, seed=40 + b, scale=0.3 + 0.1 * (b % 3)) for b in range(B)]
     I0 = np.stack([p[0] for p in pairs])
     I1 = np.stack([p[1] for p in pairs])
+    # a pair without motion stops after ONE iteration of every loop: the two-iteration first block of each level (duals
+    # taken as zero) overshoots, is rejected, and its first iteration is replayed from zero duals again
+    I1[1] = I0[1]
     kw = dict(nscales=3, warps=3, eps=0.01)
     monkeypatch.setenv("TVL1_NO_RESIDENT", "1")
     monkeypatch.setenv("TVL1_NO_TB", "1")
@@ -365,6 +368,7 @@ def test_two_per_launch_kernel_in_the_solver(nx, ny, B, monkeypatch):
     a, b = out
     assert np.array_equal(a[2], b[2]), (a[2].tolist(), b[2].tolist())
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.all(a[2][1] == 1)             # the still pair: one iteration per loop
     assert b[4] != a[4]                     # the blocked path really ran (launch counts differ)
 
 
