@@ -78,6 +78,9 @@ typedef struct tvl1_stats {
     unsigned long long level_pixel_iterations[TVL1_MAX_LEVELS];
     unsigned long long level_iterate_launches[TVL1_MAX_LEVELS];
     double level_iterate_ms[TVL1_MAX_LEVELS];
+    /* of level_iterate_ms: the level's first launch where it runs the first TWO iterations of every pair from zero
+     * duals (k_iterate_t2); 0 where the first launch is one iteration */
+    double level_first_block_ms[TVL1_MAX_LEVELS];
 } tvl1_stats;
 
 /* -- life cycle --------------------------------------------------------------------------- */

@@ -1558,9 +1558,17 @@ k_iterate_t1(const IterParams P)
 // iterations is reduced separately and decide_block accepts the block, or has its first iteration replayed.
 constexpr int kT2W = 120;                 // owned columns per warp
 constexpr int kT2T = 2;                   // iterations per launch
+// STAGE: the rows of the start state reach the registers through a per-warp ring in shared memory filled by cp.async
+// (kT2PF rows ahead, every lane only ever touches its own 16-byte slots: no barrier) instead of by loads that hold
+// their destination registers for the whole HBM latency -- at 168 registers and 12 warps per SM the kernel was
+// bound by that latency (DRAM at 74 % of peak, profiles/r3m_iterate_t2_full.csv), not by bandwidth.
+constexpr int kT2PF = 2;                  // rows in flight ahead of the one being consumed
+constexpr int kT2NS = kT2PF + 1;          // ring slots per warp
+constexpr int kT2RowF4 = 9 * 32;          // float4 per ring slot: nine planes x 32 lanes
+__host__ __device__ constexpr size_t t2_smem_bytes(int WY) { return (size_t) WY * kT2NS * kT2RowF4 * 16; }
 
-template <int R, int WY>
-__device__ __forceinline__ void iterate_t2_pair(const IterParams &P, const int b)
+template <int R, int WY, bool STAGE>
+__device__ __forceinline__ void iterate_t2_pair(const IterParams &P, const int b, float4 *t2_ring)
 {
     PairCtl *ctl = P.ctl + b;
     const int nx = P.lv.nx, ny = P.lv.ny, pitch = P.lv.pitch;
@@ -1581,8 +1589,51 @@ __device__ __forceinline__ void iterate_t2_pair(const IterParams &P, const int b
     float err1 = 0.f, err2 = 0.f;
 
     if (ys < P.row_end) {                           // warp-uniform
+        // ---- staged loads: this lane's 16-byte slots of the warp's ring ----
+        float4 *ring = t2_ring + (size_t) warp * kT2NS * kT2RowF4 + lane;
+        const int y_last = min(ye + 1, ny - 1);     // last row the march requests
+        int seq = 0, y_next = 0;                    // rows consumed so far; next row to put in flight
+        auto issue = [&](int y, int slot) {
+            if (in_alloc && y <= y_last) {
+                const size_t o = (size_t) y * pitch + x0;
+                float4 *d = ring + slot * kT2RowF4;
+                cp_async16((float *) (d + 0 * 32), sin + F_U1 * fs + o);
+                cp_async16((float *) (d + 1 * 32), sin + F_U2 * fs + o);
+                if (!P.p_zero) {
+                    cp_async16((float *) (d + 2 * 32), sin + F_P11 * fs + o);
+                    cp_async16((float *) (d + 3 * 32), sin + F_P12 * fs + o);
+                    cp_async16((float *) (d + 4 * 32), sin + F_P21 * fs + o);
+                    cp_async16((float *) (d + 5 * 32), sin + F_P22 * fs + o);
+                }
+                cp_async16((float *) (d + 6 * 32), cst + C_IX * fs + o);
+                cp_async16((float *) (d + 7 * 32), cst + C_IY * fs + o);
+                cp_async16((float *) (d + 8 * 32), cst + C_RHO * fs + o);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (STAGE) {
+            y_next = max(ys - 1, 0);
+#pragma unroll
+            for (int i = 0; i < kT2PF; i++) issue(y_next++, i);
+        }
         auto load_row = [&](int y, Row4 &r) {
-            if (in_alloc) {
+            if (STAGE) {
+                issue(y_next++, (seq + kT2PF) % kT2NS);
+                asm volatile("cp.async.wait_group %0;" :: "n"(kT2PF) : "memory");
+                const float4 *d = ring + (seq % kT2NS) * kT2RowF4;
+                seq++;
+                if (in_alloc) {
+                    r.u1 = d[0 * 32]; r.u2 = d[1 * 32];
+                    if (P.p_zero) {
+                        r.p11 = r.p12 = r.p21 = r.p22 = zero4;
+                    } else {
+                        r.p11 = d[2 * 32]; r.p12 = d[3 * 32]; r.p21 = d[4 * 32]; r.p22 = d[5 * 32];
+                    }
+                    r.ix = d[6 * 32]; r.iy = d[7 * 32]; r.rho = d[8 * 32];
+                } else {
+                    r.u1 = r.u2 = r.p11 = r.p12 = r.p21 = r.p22 = r.ix = r.iy = r.rho = zero4;
+                }
+            } else if (in_alloc) {
                 const size_t o = (size_t) y * pitch + x0;
                 r.u1 = ldg4(sin + F_U1 * fs + o);
                 r.u2 = ldg4(sin + F_U2 * fs + o);
@@ -1757,13 +1808,14 @@ __device__ __forceinline__ void iterate_t2_pair(const IterParams &P, const int b
         decide_block(P, ctl, b, cur, kT2T, s_tot, (unsigned long long) nx * (unsigned long long) (P.row_end - P.row_begin));
 }
 
-template <int R, int WY>
+template <int R, int WY, bool STAGE>
 __global__ void __launch_bounds__(32 * WY, 3)
 k_iterate_t2(const IterParams P)
 {
+    extern __shared__ __align__(16) float4 t2_ring[];      // [WY][kT2NS][9][32] when STAGE, else nothing
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
         atomicAdd(P.px_iters + kStatLevels + P.level, 1ull);
-    for_each_pair_of_slot<false>(P, true, [&](int b) { iterate_t2_pair<R, WY>(P, b); });
+    for_each_pair_of_slot<false>(P, true, [&](int b) { iterate_t2_pair<R, WY, STAGE>(P, b, t2_ring); });
 }
 
 // Row-band mode over peer memory: barrier of all ranks through the mailboxes (start of a solve: no rank

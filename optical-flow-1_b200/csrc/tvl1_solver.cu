@@ -112,6 +112,7 @@ struct tvl1_ctx {
     // solve: every level but the finest.  The flow does not depend on the choice (same bits from every kernel).
     unsigned int t2_levels = ~1u;            // bit s: level s may use it
     bool t2_adapt = true;                    // TVL1_T2_ADAPT=0: keep the initial mask (TVL1_T2_LEVELS=<mask>)
+    bool t2_stage = true;                    // TVL1_T2_STAGE=0: k_iterate_t2 loads its rows straight into registers (A/B)
     bool t2_first = true;                    // TVL1_T2_FIRST=0: a streamed level's first launch is one iteration (k_iterate_t1)
     int use_t2 = 1;                          // TVL1_T2=0: never use the two-iterations-per-launch marching kernel; 2: wherever
                                              // the shared-memory kernel is not used, however small the launch (tests)
@@ -467,6 +468,7 @@ void add_span_time(tvl1_ctx *ctx, const EventPair &p)
     else if (p.kind == 2) ctx->stats.total_ms += ms;
     else if (p.kind == 3) ctx->stats.pyramid_ms += ms;
     else if (p.kind == 4) ctx->stats.zoom_in_ms += ms;
+    else if (p.kind == 6) ctx->stats.level_first_block_ms[std::min(p.level, TVL1_MAX_LEVELS - 1)] += ms;   // (inside a kind-0 span)
     else ctx->stats.export_ms += ms;
 }
 
@@ -586,15 +588,31 @@ int launch_iterate_t2(tvl1_ctx *ctx, const IterParams &P, int B, bool tail)
     const int rows = P.row_end - P.row_begin;
     const int tiles_x = ceil_div(P.lv.nx, kT2W);
     const int Bw = tail ? std::max(1, ctx->tail_pairs / 8) : B;
+    // rows staged through shared memory (cp.async ring) need more than the default 48 KB per CTA
+    static bool attr_done[64] = { false };
+    bool stage = ctx->t2_stage;
+    if (stage && !attr_done[ctx->device & 63]) {
+        const int bytes = (int) t2_smem_bytes(kIterWY);
+        if (cudaFuncSetAttribute(k_iterate_t2<32, kIterWY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(k_iterate_t2<16, kIterWY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->t2_stage = stage = false;
+        } else {
+            attr_done[ctx->device & 63] = true;
+        }
+    }
+    const size_t smem = stage ? t2_smem_bytes(kIterWY) : 0;
     // tall strips: the two halo rows above and the one below are loaded per strip
     if ((long long) tiles_x * ceil_div(rows, 32 * kIterWY) * Bw >= 4ll * ctx->sm_count) {
         dim3 g(tiles_x, ceil_div(rows, 32 * kIterWY), 1);
         g.z = pair_slots(ctx, g.x * g.y, B, tail);
-        k_iterate_t2<32, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+        if (stage) k_iterate_t2<32, kIterWY, true><<<g, 32 * kIterWY, smem, ctx->stream>>>(P);
+        else k_iterate_t2<32, kIterWY, false><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     } else {
         dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), 1);
         g.z = pair_slots(ctx, g.x * g.y, B, tail);
-        k_iterate_t2<16, kIterWY><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
+        if (stage) k_iterate_t2<16, kIterWY, true><<<g, 32 * kIterWY, smem, ctx->stream>>>(P);
+        else k_iterate_t2<16, kIterWY, false><<<g, 32 * kIterWY, 0, ctx->stream>>>(P);
     }
     CK(cudaGetLastError());
     return TVL1_OK;
@@ -811,6 +829,7 @@ int launch_first_zero(tvl1_ctx *ctx, const IterParams &P, int B)
     IterParams P0 = P;
     P0.p_zero = 1;
     if (t2_first_usable(ctx, P, B)) {
+        Span sp(ctx, 6, P.level);
         set_blocking(P0, 2);
         P0.take_all = 1;
         return launch_iterate_t2(ctx, P0, B, false);
@@ -1356,6 +1375,7 @@ void add_stats(tvl1_stats &a, const tvl1_stats &b)
         a.level_pixel_iterations[l] += b.level_pixel_iterations[l];
         a.level_iterate_launches[l] += b.level_iterate_launches[l];
         a.level_iterate_ms[l] += b.level_iterate_ms[l];
+        a.level_first_block_ms[l] += b.level_first_block_ms[l];
     }
 }
 
@@ -2269,6 +2289,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
     if (const char *ml = std::getenv("TVL1_T2_LEVELS")) ctx->t2_levels = (unsigned int) std::strtoul(ml, nullptr, 0);
+    if (const char *ts2 = std::getenv("TVL1_T2_STAGE")) ctx->t2_stage = !(ts2[0] == '0');
     if (const char *tf = std::getenv("TVL1_T2_FIRST")) ctx->t2_first = !(tf[0] == '0');
     if (const char *ta = std::getenv("TVL1_T2_ADAPT")) ctx->t2_adapt = !(ta[0] == '0');
     if (const char *t2 = std::getenv("TVL1_T2")) ctx->use_t2 = std::max(0, std::min(2, std::atoi(t2)));

@@ -46,7 +46,8 @@ class Stats(C.Structure):
                 ("host_syncs", C.c_ulonglong),
                 ("level_pixel_iterations", C.c_ulonglong * 16),
                 ("level_iterate_launches", C.c_ulonglong * 16),
-                ("level_iterate_ms", C.c_double * 16)]
+                ("level_iterate_ms", C.c_double * 16),
+                ("level_first_block_ms", C.c_double * 16)]
 
     def as_dict(self):
         out = {}
