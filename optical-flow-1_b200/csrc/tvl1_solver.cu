@@ -23,6 +23,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 using namespace tvl1;
@@ -175,7 +176,8 @@ struct tvl1_ctx {
     HostSlot slots[kMaxSlots];
     size_t slot_in_bytes = 0, slot_out_bytes = 0;
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
-    bool host_pipe = false;                        // TVL1_HOST_PIPE=1: the call-wide pipeline (A/B; measured no faster)
+    bool host_pipe = true;                         // TVL1_HOST_PIPE=0: lanes that do their own copies also for pinned buffers (A/B)
+    int pipe_lanes = 3;                            // lanes of the pipeline (they only solve: three measured best, TVL1_PIPE_LANES)
     std::vector<int> chunk_override;               // TVL1_CHUNKS=8,16,...: explicit chunk sizes (experiments)
     void *pipe_buf[2] = { nullptr, nullptr };      // pinned staging ring for pageable host buffers
     cudaEvent_t pipe_ev[2] = { nullptr, nullptr };
@@ -1564,11 +1566,15 @@ int ensure_stage_f32(tvl1_ctx *ctx, size_t bytes_each)
 //   download  results leave in order on a second copy stream, behind the lane's completion event.
 // With the ramped chunk sizes of ramp_schedule the GPU starts after the upload of an eighth of a full chunk and
 // the call ends one such download after the last kernel.
-template <typename T>
-int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &chunks, const T *I0, const T *I1,
-                         T *u1, T *u2, int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
+// TI: element type of the host images (float, double, or unsigned char for 8-bit frame sequences: bytes over PCIe,
+// widened on the device); TO: element type of the host flows (float or double).
+template <typename TI, typename TO>
+int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &chunks, const TI *I0, const TI *I1,
+                         TO *u1, TO *u2, int nx, int ny, const tvl1_params *prm, int *iters_out, double *errs_out)
 {
-    const bool sequence = I1 == nullptr, f64 = sizeof(T) == 8;
+    const bool sequence = I1 == nullptr;
+    constexpr bool in_f32 = std::is_same<TI, float>::value, in_f64 = std::is_same<TI, double>::value;
+    constexpr bool out_f64 = std::is_same<TO, double>::value;
     const size_t n = (size_t) nx * ny;
     const int nchunks = (int) chunks.size();
     const int nstat = prm->nscales * prm->warps;
@@ -1576,10 +1582,10 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
     for (const auto &c : chunks) Bmax = std::max(Bmax, c.second);
     tvl1_ctx *lanes[tvl1_ctx::kMaxLanes];
     int nlanes = 1;
-    TRY(setup_lanes(ctx, nchunks, ctx->host_lanes, lanes, &nlanes));
+    TRY(setup_lanes(ctx, nchunks, std::min(ctx->host_lanes, ctx->pipe_lanes), lanes, &nlanes));
     const int nslots = std::min(nchunks, std::min(nlanes + 3, (int) tvl1_ctx::kMaxSlots));
     const size_t in_frames = (size_t) Bmax + (sequence ? 1 : 0);
-    TRY(ensure_slots(ctx, nslots, in_frames * n * sizeof(T), (size_t) Bmax * n * sizeof(T)));
+    TRY(ensure_slots(ctx, nslots, in_frames * n * sizeof(TI), (size_t) Bmax * n * sizeof(TO)));
     std::mutex mu;
     std::condition_variable cv;
     std::vector<int> slot_of(nchunks, -1), free_slots;
@@ -1604,11 +1610,11 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
             slot_used[si] = 1;
             if (e != cudaSuccess) return e;
             if (sequence)
-                e = cudaMemcpyAsync(sl.in[0], I0 + off, (cnt + n) * sizeof(T), cudaMemcpyHostToDevice, ctx->up_stream);
+                e = cudaMemcpyAsync(sl.in[0], I0 + off, (cnt + n) * sizeof(TI), cudaMemcpyHostToDevice, ctx->up_stream);
             else {
-                e = cudaMemcpyAsync(sl.in[0], I0 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, ctx->up_stream);
+                e = cudaMemcpyAsync(sl.in[0], I0 + off, cnt * sizeof(TI), cudaMemcpyHostToDevice, ctx->up_stream);
                 if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(sl.in[1], I1 + off, cnt * sizeof(T), cudaMemcpyHostToDevice, ctx->up_stream);
+                    e = cudaMemcpyAsync(sl.in[1], I1 + off, cnt * sizeof(TI), cudaMemcpyHostToDevice, ctx->up_stream);
             }
             if (e == cudaSuccess) e = cudaEventRecord(sl.up, ctx->up_stream);
             if (e != cudaSuccess) return e;
@@ -1631,29 +1637,32 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
         const int si = slot_of[k];
         tvl1_ctx::HostSlot &sl = ctx_root->slots[si];
         cudaStream_t st = c->stream;
-        if (f64) TRY(ensure_stage_f32(c, in_frames * n * sizeof(float)));
+        if (!in_f32 || out_f64) TRY(ensure_stage_f32(c, in_frames * n * sizeof(float)));
         CK(cudaStreamWaitEvent(st, sl.up, 0));
         if (sl.down_recorded) CK(cudaStreamWaitEvent(st, sl.down, 0));    // the slot's previous results have left
         float *d0, *d1, *o0, *o1;
         const unsigned g = (unsigned) std::min<size_t>((cnt + 255) / 256, 4096);
-        if (f64) {
+        if (in_f32) {
+            d0 = (float *) sl.in[0]; d1 = sequence ? d0 + n : (float *) sl.in[1];
+        } else {                         // narrowed (fp64) or widened (8-bit) on the device, into the lane's own buffers
             d0 = c->stage_f32[0]; d1 = sequence ? d0 + n : c->stage_f32[1];
-            o0 = c->stage_f32[2]; o1 = c->stage_f32[3];
-            k_f64_to_f32<<<g, 256, 0, st>>>((const double *) sl.in[0], d0, sequence ? cnt + n : cnt);
+            const size_t cnt0 = sequence ? cnt + n : cnt;
+            if (in_f64) k_f64_to_f32<<<g, 256, 0, st>>>((const double *) sl.in[0], d0, cnt0);
+            else k_u8_to_f32<<<(unsigned) std::min<size_t>((cnt0 / 4 + 255) / 256 + 1, 4096), 256, 0, st>>>((const unsigned char *) sl.in[0], d0, cnt0);
             CKL(ctx);
             if (!sequence) {
-                k_f64_to_f32<<<g, 256, 0, st>>>((const double *) sl.in[1], d1, cnt);
+                if (in_f64) k_f64_to_f32<<<g, 256, 0, st>>>((const double *) sl.in[1], d1, cnt);
+                else k_u8_to_f32<<<(unsigned) std::min<size_t>((cnt / 4 + 255) / 256 + 1, 4096), 256, 0, st>>>((const unsigned char *) sl.in[1], d1, cnt);
                 CKL(ctx);
             }
-        } else {
-            d0 = (float *) sl.in[0]; d1 = sequence ? d0 + n : (float *) sl.in[1];
-            o0 = (float *) sl.out[0]; o1 = (float *) sl.out[1];
         }
+        if (out_f64) { o0 = c->stage_f32[2]; o1 = c->stage_f32[3]; }
+        else { o0 = (float *) sl.out[0]; o1 = (float *) sl.out[1]; }
         int *it = iters_out ? iters_out + (size_t) first * nstat : nullptr;
         double *er = errs_out ? errs_out + (size_t) first * nstat : nullptr;
         if (c->hs_mode) TRY(run_hs_multiscale(c, B, d0, d1, o0, o1, nx, ny, c->hs, it, er));
         else TRY(run_multiscale(c, B, d0, d1, o0, o1, nx, ny, *prm, it, er));
-        if (f64) {
+        if (out_f64) {
             k_f32_to_f64<<<g, 256, 0, st>>>(o0, (double *) sl.out[0], cnt);
             CKL(ctx);
             k_f32_to_f64<<<g, 256, 0, st>>>(o1, (double *) sl.out[1], cnt);
@@ -1664,8 +1673,8 @@ int solve_host_pipelined(tvl1_ctx *ctx, const std::vector<std::pair<int, int>> &
         std::lock_guard<std::mutex> lk(mu);
         const size_t off = (size_t) first * n;
         CK(cudaStreamWaitEvent(ctx_root->down_stream, sl.done, 0));
-        CK(cudaMemcpyAsync(u1 + off, sl.out[0], cnt * sizeof(T), cudaMemcpyDeviceToHost, ctx_root->down_stream));
-        CK(cudaMemcpyAsync(u2 + off, sl.out[1], cnt * sizeof(T), cudaMemcpyDeviceToHost, ctx_root->down_stream));
+        CK(cudaMemcpyAsync(u1 + off, sl.out[0], cnt * sizeof(TO), cudaMemcpyDeviceToHost, ctx_root->down_stream));
+        CK(cudaMemcpyAsync(u2 + off, sl.out[1], cnt * sizeof(TO), cudaMemcpyDeviceToHost, ctx_root->down_stream));
         CK(cudaEventRecord(sl.down, ctx_root->down_stream));
         sl.down_recorded = true;
         free_slots.push_back(si);
@@ -1728,7 +1737,7 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     if (multiscale && ctx->host_pipe && !ctx->hs_mode && !ctx->is_sibling && npairs > Bmax && !is_pageable(I0) && (!I1 || !is_pageable(I1)) &&
         !is_pageable(u1) && !is_pageable(u2)) {
         ramp_schedule(npairs, Bmax, ctx->chunk_override, chunks);
-        return solve_host_pipelined<T>(ctx, chunks, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out);
+        return solve_host_pipelined<T, T>(ctx, chunks, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out);
     }
     chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
     const ChunkTrace trace;
@@ -1777,6 +1786,10 @@ int solve_sequence_u8(tvl1_ctx *ctx, int nframes, const unsigned char *frames, f
     const int Bmax = std::min(npairs, ctx->max_batch);
     const int nstat = prm->nscales * prm->warps;
     std::vector<std::pair<int, int>> chunks;
+    if (ctx->host_pipe && !ctx->is_sibling && npairs > Bmax && !is_pageable(frames) && !is_pageable(u1) && !is_pageable(u2)) {
+        ramp_schedule(npairs, Bmax, ctx->chunk_override, chunks);
+        return solve_host_pipelined<unsigned char, float>(ctx, chunks, frames, nullptr, u1, u2, nx, ny, prm, iters_out, errs_out);
+    }
     chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
     return run_lanes(ctx, (int) chunks.size(), ctx->host_lanes, [&](tvl1_ctx *c, int k) -> int {
         tvl1_ctx *ctx = c;   // for CK / TRY
@@ -2302,7 +2315,8 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
     if (const char *ts = std::getenv("TVL1_TB_SHARED")) ctx->tb_when_shared = ts[0] == '1';
     if (const char *sd = std::getenv("TVL1_SHORT_DIV")) ctx->short_div = std::max(0, std::atoi(sd));
-    if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = hp[0] == '1';
+    if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = !(hp[0] == '0');
+    if (const char *pl = std::getenv("TVL1_PIPE_LANES")) ctx->pipe_lanes = std::max(1, std::min((int) tvl1_ctx::kMaxLanes, std::atoi(pl)));
     if (const char *cs = std::getenv("TVL1_CHUNKS"))
         for (const char *q = cs; *q;) {
             char *end = nullptr;
@@ -2379,6 +2393,7 @@ int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes)
     if (!ctx || host_lanes < 1 || dev_lanes < 1 || host_lanes > tvl1_ctx::kMaxLanes || dev_lanes > tvl1_ctx::kMaxLanes)
         return TVL1_ERR_ARG;
     ctx->host_lanes = host_lanes;
+    ctx->pipe_lanes = host_lanes;            // an explicit choice also applies to the pinned-buffer pipeline (default there: 3)
     ctx->dev_lanes = dev_lanes;
     return TVL1_OK;
 }

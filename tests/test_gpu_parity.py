@@ -605,7 +605,8 @@ def test_host_batch_chunk_schedules(gpu, npairs, max_batch, lanes, short_div, mo
 
 @pytest.mark.parametrize("npairs,max_batch,lanes,dtype,form", [
     (29, 8, 3, "float32", "pairs"), (29, 8, 3, "float64", "pairs"), (16, 4, 2, "float32", "sequence"),
-    (13, 4, 4, "float64", "sequence"), (40, 16, 1, "float32", "pairs"), (9, 2, 8, "float32", "pairs")])
+    (13, 4, 4, "float64", "sequence"), (40, 16, 1, "float32", "pairs"), (9, 2, 8, "float32", "pairs"),
+    (14, 4, 3, "uint8", "sequence")])
 def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, monkeypatch):
     """TVL1_HOST_PIPE=1: pinned host buffers go through the call-wide upload -> solve -> download pipeline (solve_host_pipelined):
     ramped chunk sizes (tvl1_plan_chunks), one ordered copy stream each way, a ring of device slots that chunks
@@ -615,7 +616,7 @@ def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, 
     monkeypatch.setenv("TVL1_HOST_PIPE", "1")
     nx, ny = 128, 96
     kw = dict(nscales=3, warps=2, eps=0.01)
-    tdt = torch.float32 if dtype == "float32" else torch.float64
+    tdt = torch.float64 if dtype == "float64" else torch.float32          # 8-bit frames give fp32 flows
     if form == "pairs":
         pairs = [_cases.synth.make_pair(nx, ny, seed=700 + b, scale=0.3 + 0.02 * (b % 5)) for b in range(npairs)]
         A = np.stack([p[0] for p in pairs]).astype(dtype)
@@ -624,7 +625,8 @@ def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, 
         hB = torch.from_numpy(Bm).pin_memory()
     else:
         fr = [_cases.synth.make_pair(nx, ny, seed=800 + b, scale=0.3)[b & 1] for b in range(npairs + 1)]
-        A = np.stack(fr).astype(dtype)
+        A = np.stack(fr)
+        A = np.clip(np.rint(A), 0, 255).astype(np.uint8) if dtype == "uint8" else A.astype(dtype)
         hA = torch.from_numpy(A).pin_memory()
     assert len(pkg.tvl1.plan_chunks(npairs, max_batch)) > 1
     g = pkg.TVL1(device=0, max_batch=max_batch)
@@ -648,6 +650,8 @@ def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, 
     assert np.isfinite(a[0]).all() and np.isfinite(a[1]).all()
     for k in range(npairs):
         I0k, I1k = (A[k], Bm[k]) if form == "pairs" else (A[k], A[k + 1])
+        if dtype == "uint8":
+            I0k, I1k = I0k.astype(np.float32), I1k.astype(np.float32)
         u1, u2, itk, erk = gpu.Dual_TVL1_optic_flow_multiscale(I0k, I1k, **kw)
         assert np.array_equal(u1, a[0][k]) and np.array_equal(u2, a[1][k]), k
         assert np.array_equal(itk, a[2][k]) and np.array_equal(erk, a[3][k]), k
