@@ -123,6 +123,7 @@ struct tvl1_ctx {
     int slot_ctas = 32768;                   // CTAs a full iteration launch should have at least (TVL1_SLOT_CTAS)
     int tail_pairs = 16;                     // lock-step batches: once this few pairs still iterate, the loop goes on
                                              // with narrow launches of tail_slot_ctas CTAs (TVL1_TAIL_PAIRS, 0 = off)
+    int tail_pairs_shared = 2;               // ... the same for a chunk solved while other lanes share the GPU (TVL1_TAIL_PAIRS_SHARED)
     int tail_slot_ctas = 2048;               // (TVL1_TAIL_SLOT_CTAS)
     bool tail_tb = true;                     // temporal blocking in the tail even where the full batch runs without (TVL1_TAIL_TB)
     long long tb_max_pixels = 192ll << 20;   // ... which serves lock-step batches up to this many pixels per level
@@ -540,7 +541,7 @@ IterParams iter_params(const tvl1_ctx *ctx, const Level &lv, const tvl1_params &
 }
 
 int launch_iterate_tb(tvl1_ctx *ctx, const IterParams &P, int B, bool tail);
-bool tb_usable(tvl1_ctx *ctx, const Level &l, int B);
+bool tb_usable(tvl1_ctx *ctx, const Level &l, int B, bool tail = false);
 
 // Two iterations per launch in registers (k_iterate_t2): for the launches that saturate HBM, i.e. where the
 // shared-memory kernel is not used -- big lock-step batches, and chunks solved while other lanes share the GPU.
@@ -589,7 +590,7 @@ int launch_iterate_t2(tvl1_ctx *ctx, const IterParams &P, int B, bool tail)
 {
     const int rows = P.row_end - P.row_begin;
     const int tiles_x = ceil_div(P.lv.nx, kT2W);
-    const int Bw = tail ? std::max(1, ctx->tail_pairs / 8) : B;
+    const int Bw = tail ? std::max(1, (ctx->shared_gpu ? ctx->tail_pairs_shared : ctx->tail_pairs) / 8) : B;
     // rows staged through shared memory (cp.async ring) need more than the default 48 KB per CTA
     static bool attr_done[64] = { false };
     bool stage = ctx->t2_stage;
@@ -630,7 +631,7 @@ int launch_iterate(tvl1_ctx *ctx, const IterParams &P, int B, bool tail = false)
     const int tiles_x = ceil_div(P.lv.nx, 124);
     const long long want = 4ll * ctx->sm_count;
     // a tail launch serves the few pairs still iterating (often one or two): size the strips for an eighth of the switch-over count
-    const int Bw = tail ? std::max(1, ctx->tail_pairs / 8) : B;
+    const int Bw = tail ? std::max(1, (ctx->shared_gpu ? ctx->tail_pairs_shared : ctx->tail_pairs) / 8) : B;
     auto ctas = [&](int R) { return (long long) tiles_x * ceil_div(rows, R * kIterWY) * Bw; };
     if (ctas(16) >= want) {
         dim3 g(tiles_x, ceil_div(rows, 16 * kIterWY), 1);
@@ -691,7 +692,7 @@ bool make_plane_map(CUtensorMap *m, const float *base, int nx, int ny, int nplan
 }
 
 // B = pairs that a launch is expected to serve (the lock-step batch, or the tail of one)
-bool tb_usable(tvl1_ctx *ctx, const Level &l, int B)
+bool tb_usable(tvl1_ctx *ctx, const Level &l, int B, bool tail)
 {
     static bool attr_done[64] = { false };      // function attributes are per device
     bool &attr = attr_done[ctx->device & 63];
@@ -701,7 +702,9 @@ bool tb_usable(tvl1_ctx *ctx, const Level &l, int B)
     // streaming kernel once the SMs are saturated anyway -- by a big lock-step batch, or by the other
     // lanes of a chunked batch (measured, profiles/r2g_chunks.txt: 16 pairs x 4 lanes 178.9 -> 165.7 ms,
     // 64 x 4 lanes 163.7 -> 157.0 ms per 256 x 1080p without it).
-    if (ctx->shared_gpu && !ctx->tb_when_shared) return false;
+    // (the narrow launches of a tail are the exception: what they cost the other lanes is small, what they save the
+    // chunk's slow pairs is most of their time)
+    if (ctx->shared_gpu && !ctx->tb_when_shared && !tail) return false;
     if ((long long) B * l.nx * l.ny > ctx->tb_max_pixels) return false;
     if (l.nx < kTbBW || l.ny < kTbBH) return false;
     if (!attr) {
@@ -856,11 +859,15 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B, bool first_zero)
     // while more than tail_pairs pairs iterate, then narrow ones (a tenth of the CTAs: a launch with
     // little work costs what it does, not what it takes to start and retire 32k empty CTAs).  The
     // active count only falls within a warp step, so the second loop never has to hand back.
-    const bool two_phase = ctx->tail_pairs > 0 && B > 2 * ctx->tail_pairs && !P.peers.enabled;
+    // A chunk solved while other lanes share the GPU has a tail too: the one or two slow pairs that keep its lock-step
+    // loop turning.  They do not cost the GPU much (the other lanes fill it) but they decide when the chunk -- and, if it
+    // is a late one, the whole host-buffer call -- ends: the same hand-over, at tail_pairs_shared pairs.
+    const int tail_pairs = ctx->shared_gpu ? ctx->tail_pairs_shared : ctx->tail_pairs;
+    const bool two_phase = tail_pairs > 0 && B > 2 * tail_pairs && !P.peers.enabled;
     if (two_phase) {
         CK(cudaGraphConditionalHandleCreate(&h_bulk, g, 1, cudaGraphCondAssignDefault));
         P.cond_bulk = h_bulk;
-        P.bulk_min = ctx->tail_pairs;
+        P.bulk_min = tail_pairs;
     }
     if (first_zero) TRY(launch_first_zero(ctx, P, B));
     if (two_phase) {
@@ -868,7 +875,7 @@ int add_while_loop(tvl1_ctx *ctx, IterParams P, int B, bool first_zero)
         // the pairs of the tail are the slow ones (tens of iterations where the batch needs two): worth
         // temporal blocking even where the full batch is not (a wide launch of both kernels costs more
         // than blocking saves; a narrow one does not)
-        if (P.tb != 1 && ctx->tail_tb && tb_usable(ctx, P.lv, ctx->tail_pairs)) set_blocking(P, 1);
+        if (P.tb != 1 && ctx->tail_tb && tb_usable(ctx, P.lv, tail_pairs, true)) set_blocking(P, 1);
         return add_while_node(ctx, P, B, h_all, true);
     }
     return add_while_node(ctx, P, B, h_all, false);
@@ -2311,6 +2318,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *wt = std::getenv("TVL1_WARP_TMA")) ctx->warp_tma = !(wt[0] == '0');
     if (const char *sc = std::getenv("TVL1_SLOT_CTAS")) ctx->slot_ctas = std::max(1, std::atoi(sc));
     if (const char *tp = std::getenv("TVL1_TAIL_PAIRS")) ctx->tail_pairs = std::max(0, std::atoi(tp));
+    if (const char *tp = std::getenv("TVL1_TAIL_PAIRS_SHARED")) ctx->tail_pairs_shared = std::max(0, std::atoi(tp));
     if (const char *tc = std::getenv("TVL1_TAIL_SLOT_CTAS")) ctx->tail_slot_ctas = std::max(1, std::atoi(tc));
     if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
     if (const char *ts = std::getenv("TVL1_TB_SHARED")) ctx->tb_when_shared = ts[0] == '1';
