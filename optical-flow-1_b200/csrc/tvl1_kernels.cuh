@@ -1913,7 +1913,7 @@ struct ResParams {
 __host__ __device__ inline size_t resident_smem_bytes(int pitch, int rows_per_cta)
 {
     // u1,u2: rows+1 (halo below) | p11,p21: rows | p12,p22: rows+1 (halo above) | slots | mbarrier
-    return (size_t) pitch * (6 * rows_per_cta + 4) * sizeof(float) + (2 * kResMaxCluster) * sizeof(double) + 16;
+    return (size_t) pitch * (6 * rows_per_cta + 4) * sizeof(float) + (kResMaxCluster + kResThreads / 32) * sizeof(double) + 16;
 }
 
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -1941,8 +1941,8 @@ k_iterate_resident(const ResParams P)
     float *sP12 = sP21 + (size_t) RB * pitch;       // row 0 = halo above, own rows at 1..rows
     float *sP22 = sP12 + (size_t) (RB + 1) * pitch;
     double *sSlots = reinterpret_cast<double *>(sP22 + (size_t) (RB + 1) * pitch);   // [C] cluster partials
-    double *sWarp = sSlots + kResMaxCluster;                                          // [16] warp partials
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(sWarp + kResMaxCluster);
+    double *sWarp = sSlots + kResMaxCluster;                                          // [kResThreads / 32] warp partials
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(sWarp + kResThreads / 32);
 
     PairCtl *ctl = P.ctl + b;
     const int cur = ctl->cur;
