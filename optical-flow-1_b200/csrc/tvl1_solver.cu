@@ -106,7 +106,6 @@ struct tvl1_ctx {
     cudaStream_t body_stream = nullptr;      // capture stream for while-node bodies
     bool use_graph = true;                   // TVL1_NO_GRAPH=1 selects the host-driven loop
     bool use_resident = true;                // TVL1_NO_RESIDENT=1 keeps every level on the streaming kernel
-    int res_max_cluster = kResMaxCluster;    // TVL1_RES_MAX_CLUSTER: largest cluster of the on-chip kernel (levels that need more stream)
     bool use_tb = true;                      // TVL1_NO_TB=1: never use the temporally blocked kernel
     // ... which pays on the levels whose loops are long enough for two-iteration blocks (measured on the 256-pair
     // batch at default epsilon: 4.6 iterations per warp step on level 1, 32.6 -> 29.5 ms; 1.9 on level 0, 51.2 -> 54.1 ms).
@@ -274,7 +273,7 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
     if (!ctx->use_resident) return 0;
     static bool attr_done[64] = { false };
     int best = 0;
-    for (int C = 1; C <= std::min(kResMaxCluster, ctx->res_max_cluster); C *= 2) {
+    for (int C = 1; C <= kResMaxCluster; C *= 2) {
         if (ctx->force_cluster && C != ctx->force_cluster) continue;
         // a small batch cannot fill the GPU with minimal clusters: keep growing the cluster (shorter
         // bands, shorter iterations) while all clusters of the batch still run concurrently -- but
@@ -319,7 +318,7 @@ int pick_cluster(tvl1_ctx *ctx, const Level &l, int B, int *rows_out)
 // what the cluster choice of a workspace depends on besides the level sizes and the batch size
 int resident_key_of(const tvl1_ctx *ctx)
 {
-    return ctx->use_resident ? 1 + ctx->force_cluster + 32 * ctx->res_max_cluster : 0;
+    return ctx->use_resident ? 1 + ctx->force_cluster : 0;
 }
 
 bool workspace_matches(const tvl1_ctx *ctx, const Workspace &w, int nx, int ny, int nscales, double zfactor, int B,
@@ -2308,7 +2307,6 @@ int tvl1_create(int device, tvl1_ctx **out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *ng = std::getenv("TVL1_NO_GRAPH")) ctx->use_graph = !(ng[0] == '1');
     if (const char *nr = std::getenv("TVL1_NO_RESIDENT")) ctx->use_resident = !(nr[0] == '1');
-    if (const char *rc = std::getenv("TVL1_RES_MAX_CLUSTER")) ctx->res_max_cluster = std::max(1, std::atoi(rc));
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
     if (const char *ml = std::getenv("TVL1_T2_LEVELS")) ctx->t2_levels = (unsigned int) std::strtoul(ml, nullptr, 0);
     if (const char *ts2 = std::getenv("TVL1_T2_STAGE")) ctx->t2_stage = !(ts2[0] == '0');

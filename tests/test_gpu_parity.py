@@ -657,6 +657,38 @@ def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, 
         assert np.array_equal(itk, a[2][k]) and np.array_equal(erk, a[3][k]), k
 
 
+@pytest.mark.parametrize("env", [{}, {"TVL1_NO_RESIDENT": "1"}, {"TVL1_NO_RESIDENT": "1", "TVL1_HOST_PIPE": "0"}],
+                         ids=["default", "all_levels_streamed", "all_levels_streamed_lane_copies"])
+def test_pinned_host_batch_streamed_levels_in_small_chunks(gpu, env, monkeypatch):
+    """Host-buffer batch of mid-size images (640x360: the finest level streams through HBM, the next ones live on chip;
+    with TVL1_NO_RESIDENT=1 every level streams, down to 160x90) cut into chunks of 1..4 pairs on three lanes: small
+    streamed levels inside concurrently solved chunks, against the individual solves."""
+    import torch
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    nx, ny, npairs = 640, 360, 14
+    kw = dict(nscales=3, warps=2, eps=0.01)
+    pairs = [_cases.synth.make_pair(nx, ny, seed=950 + b, scale=0.5) for b in range(npairs)]
+    A = np.stack([p[0] for p in pairs])
+    Bm = np.stack([p[1] for p in pairs])
+    hA, hB = torch.from_numpy(A).pin_memory(), torch.from_numpy(Bm).pin_memory()
+    g = pkg.TVL1(device=0, max_batch=4)
+    g.set_lanes(host_lanes=3)
+    hu1 = torch.zeros((npairs, ny, nx)).pin_memory()
+    hu2 = torch.zeros((npairs, ny, nx)).pin_memory()
+    it = np.zeros((npairs, 3, 2), np.int32)
+    for rep in range(2):
+        g.solve_batch_host_ptr(hA.data_ptr(), hB.data_ptr(), hu1.data_ptr(), hu2.data_ptr(), npairs, nx, ny,
+                               dtype="float32", iters=it, **kw)
+    g.close()
+    for k_ in env:
+        monkeypatch.delenv(k_)
+    for k in range(0, npairs, 3):
+        u1, u2, itk, _ = gpu.Dual_TVL1_optic_flow_multiscale(A[k], Bm[k], **kw)
+        assert np.array_equal(u1, hu1[k].numpy()) and np.array_equal(u2, hu2[k].numpy()), k
+        assert np.array_equal(itk, it[k]), k
+
+
 def test_pinned_host_batch_pipeline_matches_lane_copies(monkeypatch):
     """A/B switch: TVL1_HOST_PIPE=1 selects the call-wide pipeline instead of lanes that do their own copies;
     TVL1_CHUNKS overrides its chunk sizes.  Same bits either way."""
