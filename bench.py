@@ -48,8 +48,8 @@ def parse():
     ap.add_argument("--e2e-pairs", type=int, default=256, help="frame pairs per rank per e2e step")
     ap.add_argument("--e2e-max-batch", type=int, default=16,
                     help="lock-step chunk of the host-buffer path (chunks alternate between two lanes)")
-    ap.add_argument("--e2e-lanes", type=int, default=3,
-                    help="lanes of the host-buffer call (pinned buffers: the upload -> solve -> download pipeline, 3 measured best)")
+    ap.add_argument("--e2e-lanes", type=int, default=4,
+                    help="lanes of the host-buffer call (4 measured best for lanes that do their own copies; 3 for TVL1_HOST_PIPE=1)")
     ap.add_argument("--nx", type=int, default=1920)
     ap.add_argument("--ny", type=int, default=1080)
     ap.add_argument("--max-batch", type=int, default=256, help="pairs advanced in lock-step")

@@ -1009,32 +1009,43 @@ k_warp(const __grid_constant__ CUtensorMap map_i1, const int use_tma,
     }
 
     float *cIx = consts + (size_t) C_IX * field_stride + pair_off + (size_t) ii * pitch + jj;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
+    const float fjj = (float) jj, fii = (float) ii;          // pixel coordinates in fp32 (exact: far below 2^24)
+    const float xmax = (float) (nx - 3), ymax = (float) (ny - 3);
+    // One pixel.  INTERIOR (CTA-uniform): the staged box lies inside the image, so a sample whose taps lie inside the
+    // box is valid by construction (2 <= sx <= nx-4, 2 <= sy <= ny-4) and the reference's validity test
+    // (src/bicubic_interpolation.cpp: 1 <= (int)(j+u1) <= nx-3, ...) is only evaluated for the others.
+    auto pixel = [&](auto interior, const int q) {
+        constexpr bool INTERIOR = decltype(interior)::value;
         const int j = jj + 32 * (q & 1), i = ii + 8 * (q >> 1);
-        if (!full && !(j < nx && i < row_end)) continue;
+        if (!full && !(j < nx && i < row_end)) return;
         const float fu = floorf(u1[q]), fv = floorf(u2[q]);
-        const float xf = (float) j + fu, yf = (float) i + fv;
-        const bool valid = xf >= 1.0f && xf <= (float) (nx - 3) && yf >= 1.0f && yf <= (float) (ny - 3);
+        const float xf = (fjj + (float) (32 * (q & 1))) + fu, yf = (fii + (float) (8 * (q >> 1))) + fv;
+        // (int) of a value outside the int range, or of a NaN, is never inside the box
+        const int sx = (int) xf, sy = (int) yf;
+        const int cx = sx - 2 - bx0, cy = sy - 2 - by0;          // box coordinates of tap (0,0)
+        const bool inbox = (unsigned) cx <= (unsigned) (kWarpBW - 6) && (unsigned) cy <= (unsigned) (kWarpBH - 6);
         float w = 0.f, wx = 0.f, wy = 0.f;
-        if (valid) {
-            const int sx = (int) xf, sy = (int) yf;
-            const float ftx = u1[q] - fu, fty = u2[q] - fv;
-            const int cx = sx - 2 - bx0, cy = sy - 2 - by0;       // box coordinates of tap (0,0)
-            if ((unsigned) cx <= (unsigned) (kWarpBW - 6) && (unsigned) cy <= (unsigned) (kWarpBH - 6)) {
-                const float *base = s_box + cy * kWarpBW + cx;
-                warp_gather([&](int r, int c) { return base[r * kWarpBW + c]; }, ftx, fty, w, wx, wy);
-            } else {
-                float o3[3];
-                warp_gather_global(img1, pitch, nx, ny, sx, sy, ftx, fty, o3);
-                w = o3[0]; wx = o3[1]; wy = o3[2];
-            }
+        const float ftx = u1[q] - fu, fty = u2[q] - fv;
+        if (inbox && (INTERIOR || (xf >= 1.0f && xf <= xmax && yf >= 1.0f && yf <= ymax))) {
+            const float *base = s_box + cy * kWarpBW + cx;
+            warp_gather([&](int r, int c) { return base[r * kWarpBW + c]; }, ftx, fty, w, wx, wy);
+        } else if (!inbox && xf >= 1.0f && xf <= xmax && yf >= 1.0f && yf <= ymax) {
+            float o3[3];
+            warp_gather_global(img1, pitch, nx, ny, sx, sy, ftx, fty, o3);
+            w = o3[0]; wx = o3[1]; wy = o3[2];
         }
         const int o = 32 * (q & 1) + dn * (q >> 1);
         cIx[o] = wx;
         cIx[field_stride + o] = wy;                 // C_IY
         cIx[2 * field_stride + o] = __fmaf_rn(-wy, u2[q], __fmaf_rn(-wx, u1[q], __fsub_rn(w, i0v[q])));   // C_RHO
         if (write_grad) cIx[3 * field_stride + o] = grad_of(wx, wy);
+    };
+    if (box_inside) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) pixel(std::true_type{}, q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) pixel(std::false_type{}, q);
     }
 }
 

@@ -113,6 +113,8 @@ struct tvl1_ctx {
     // solve: every level but the finest.  The flow does not depend on the choice (same bits from every kernel).
     unsigned int t2_levels = ~1u;            // bit s: level s may use it
     bool t2_adapt = true;                    // TVL1_T2_ADAPT=0: keep the initial mask (TVL1_T2_LEVELS=<mask>)
+    bool t2_when_shared = true;              // TVL1_T2_SHARED=0: not while lanes share the GPU
+    bool t2_stage_when_shared = true;        // TVL1_T2_STAGE_SHARED=0: direct loads while lanes share the GPU
     bool t2_stage = true;                    // TVL1_T2_STAGE=0: k_iterate_t2 loads its rows straight into registers (A/B)
     bool t2_first = true;                    // TVL1_T2_FIRST=0: a streamed level's first launch is one iteration (k_iterate_t1)
     int use_t2 = 1;                          // TVL1_T2=0: never use the two-iterations-per-launch marching kernel; 2: wherever
@@ -123,7 +125,7 @@ struct tvl1_ctx {
     int slot_ctas = 32768;                   // CTAs a full iteration launch should have at least (TVL1_SLOT_CTAS)
     int tail_pairs = 16;                     // lock-step batches: once this few pairs still iterate, the loop goes on
                                              // with narrow launches of tail_slot_ctas CTAs (TVL1_TAIL_PAIRS, 0 = off)
-    int tail_pairs_shared = 2;               // ... the same for a chunk solved while other lanes share the GPU (TVL1_TAIL_PAIRS_SHARED)
+    int tail_pairs_shared = 0;               // ... the same for a chunk solved while other lanes share the GPU (TVL1_TAIL_PAIRS_SHARED)
     int tail_slot_ctas = 2048;               // (TVL1_TAIL_SLOT_CTAS)
     bool tail_tb = true;                     // temporal blocking in the tail even where the full batch runs without (TVL1_TAIL_TB)
     long long tb_max_pixels = 192ll << 20;   // ... which serves lock-step batches up to this many pixels per level
@@ -177,7 +179,8 @@ struct tvl1_ctx {
     HostSlot slots[kMaxSlots];
     size_t slot_in_bytes = 0, slot_out_bytes = 0;
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
-    bool host_pipe = true;                         // TVL1_HOST_PIPE=0: lanes that do their own copies also for pinned buffers (A/B)
+    bool host_pipe = false;                        // TVL1_HOST_PIPE=1: the call-wide pipeline for pinned buffers (faster, but see DESIGN 3.6:
+                                                   // an intermittent launch failure was seen with it and is not understood yet)
     int pipe_lanes = 3;                            // lanes of the pipeline (they only solve: three measured best, TVL1_PIPE_LANES)
     std::vector<int> chunk_override;               // TVL1_CHUNKS=8,16,...: explicit chunk sizes (experiments)
     void *pipe_buf[2] = { nullptr, nullptr };      // pinned staging ring for pageable host buffers
@@ -549,6 +552,7 @@ bool tb_usable(tvl1_ctx *ctx, const Level &l, int B, bool tail = false);
 bool t2_usable(const tvl1_ctx *ctx, const Level &l, int B, bool peers, int level)
 {
     if (!ctx->use_t2 || peers) return false;
+    if (ctx->shared_gpu && !ctx->t2_when_shared) return false;
     if (ctx->use_t2 == 2) return true;
     if (!((ctx->t2_levels >> std::min(level, 31)) & 1u)) return false;
     const long long strips = (long long) ceil_div(l.nx, kT2W) * ceil_div(l.ny, 16 * kIterWY) * B;
@@ -563,6 +567,7 @@ bool t2_usable(const tvl1_ctx *ctx, const Level &l, int B, bool peers, int level
 bool t2_first_usable(const tvl1_ctx *ctx, const IterParams &P, int B)
 {
     if (!ctx->t2_first || ctx->use_t2 == 0 || P.peers.enabled || P.max_iter < 2) return false;
+    if (ctx->shared_gpu && !ctx->t2_when_shared) return false;
     if (ctx->use_t2 == 2) return true;
     const long long strips = (long long) ceil_div(P.lv.nx, kT2W) * ceil_div(P.lv.ny, 16 * kIterWY) * B;
     return P.lv.nx >= kT2W && P.lv.ny >= 16 && strips >= 4ll * ctx->sm_count;
@@ -593,7 +598,7 @@ int launch_iterate_t2(tvl1_ctx *ctx, const IterParams &P, int B, bool tail)
     const int Bw = tail ? std::max(1, (ctx->shared_gpu ? ctx->tail_pairs_shared : ctx->tail_pairs) / 8) : B;
     // rows staged through shared memory (cp.async ring) need more than the default 48 KB per CTA
     static bool attr_done[64] = { false };
-    bool stage = ctx->t2_stage;
+    bool stage = ctx->t2_stage && !(ctx->shared_gpu && !ctx->t2_stage_when_shared);
     if (stage && !attr_done[ctx->device & 63]) {
         const int bytes = (int) t2_smem_bytes(kIterWY);
         if (cudaFuncSetAttribute(k_iterate_t2<32, kIterWY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
@@ -2310,6 +2315,8 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *nt = std::getenv("TVL1_NO_TB")) ctx->use_tb = !(nt[0] == '1');
     if (const char *ml = std::getenv("TVL1_T2_LEVELS")) ctx->t2_levels = (unsigned int) std::strtoul(ml, nullptr, 0);
     if (const char *ts2 = std::getenv("TVL1_T2_STAGE")) ctx->t2_stage = !(ts2[0] == '0');
+    if (const char *ts3 = std::getenv("TVL1_T2_SHARED")) ctx->t2_when_shared = !(ts3[0] == '0');
+    if (const char *ts4 = std::getenv("TVL1_T2_STAGE_SHARED")) ctx->t2_stage_when_shared = !(ts4[0] == '0');
     if (const char *tf = std::getenv("TVL1_T2_FIRST")) ctx->t2_first = !(tf[0] == '0');
     if (const char *ta = std::getenv("TVL1_T2_ADAPT")) ctx->t2_adapt = !(ta[0] == '0');
     if (const char *t2 = std::getenv("TVL1_T2")) ctx->use_t2 = std::max(0, std::min(2, std::atoi(t2)));
@@ -2323,7 +2330,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *tt = std::getenv("TVL1_TAIL_TB")) ctx->tail_tb = tt[0] == '1';
     if (const char *ts = std::getenv("TVL1_TB_SHARED")) ctx->tb_when_shared = ts[0] == '1';
     if (const char *sd = std::getenv("TVL1_SHORT_DIV")) ctx->short_div = std::max(0, std::atoi(sd));
-    if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = !(hp[0] == '0');
+    if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = hp[0] == '1';
     if (const char *pl = std::getenv("TVL1_PIPE_LANES")) ctx->pipe_lanes = std::max(1, std::min((int) tvl1_ctx::kMaxLanes, std::atoi(pl)));
     if (const char *cs = std::getenv("TVL1_CHUNKS"))
         for (const char *q = cs; *q;) {

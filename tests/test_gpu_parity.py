@@ -603,6 +603,14 @@ def test_host_batch_chunk_schedules(gpu, npairs, max_batch, lanes, short_div, mo
         assert np.array_equal(u1, a[0][k]) and np.array_equal(u2, a[1][k]) and np.array_equal(it, a[2][k]), k
 
 
+# The call-wide pipeline is opt-in (TVL1_HOST_PIPE=1): an intermittent launch failure was seen with it on the 256 x 1080p
+# bench workload, and a launch failure would poison the CUDA context of the whole test process.  Its tests
+# (always green so far) therefore run on request only: TVL1_TEST_HOST_PIPE=1 pytest -m gpu -k pinned_host_batch_pipeline
+_PIPE_TESTS = pytest.mark.skipif(os.environ.get("TVL1_TEST_HOST_PIPE") != "1",
+                                 reason="opt-in host-buffer pipeline: set TVL1_TEST_HOST_PIPE=1")
+
+
+@_PIPE_TESTS
 @pytest.mark.parametrize("npairs,max_batch,lanes,dtype,form", [
     (29, 8, 3, "float32", "pairs"), (29, 8, 3, "float64", "pairs"), (16, 4, 2, "float32", "sequence"),
     (13, 4, 4, "float64", "sequence"), (40, 16, 1, "float32", "pairs"), (9, 2, 8, "float32", "pairs"),
@@ -657,8 +665,7 @@ def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, 
         assert np.array_equal(itk, a[2][k]) and np.array_equal(erk, a[3][k]), k
 
 
-@pytest.mark.parametrize("env", [{}, {"TVL1_NO_RESIDENT": "1"}, {"TVL1_NO_RESIDENT": "1", "TVL1_HOST_PIPE": "0"}],
-                         ids=["default", "all_levels_streamed", "all_levels_streamed_lane_copies"])
+@pytest.mark.parametrize("env", [{}, {"TVL1_NO_RESIDENT": "1"}], ids=["default", "all_levels_streamed"])
 def test_pinned_host_batch_streamed_levels_in_small_chunks(gpu, env, monkeypatch):
     """Host-buffer batch of mid-size images (640x360: the finest level streams through HBM, the next ones live on chip;
     with TVL1_NO_RESIDENT=1 every level streams, down to 160x90) cut into chunks of 1..4 pairs on three lanes: small
@@ -689,6 +696,7 @@ def test_pinned_host_batch_streamed_levels_in_small_chunks(gpu, env, monkeypatch
         assert np.array_equal(itk, it[k]), k
 
 
+@_PIPE_TESTS
 def test_pinned_host_batch_pipeline_matches_lane_copies(monkeypatch):
     """A/B switch: TVL1_HOST_PIPE=1 selects the call-wide pipeline instead of lanes that do their own copies;
     TVL1_CHUNKS overrides its chunk sizes.  Same bits either way."""
