@@ -91,7 +91,7 @@ const char *tvl1_last_error(const tvl1_ctx *ctx);  /* ctx may be NULL: error of 
 int tvl1_set_profiling(tvl1_ctx *ctx, int on);     /* bracket kernels with CUDA events (tvl1_stats *_ms) */
 int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs);  /* pairs advanced in lock-step per workspace (default 32) */
 /* Batches larger than max_batch are cut into chunks that up to 8 lanes (sibling contexts on the same
- * GPU, one host thread each) process concurrently: copies of one chunk overlap kernels of another (with
+ * GPU, one host thread each) process concurrently: copies of one chunk overlap kernels of another (experimental,
  * TVL1_HOST_PIPE=1 and pinned host buffers: one upload -> solve -> download pipeline per call, tvl1_plan_chunks).
  * host_lanes: host-buffer entry points (default 4); dev_lanes: device-buffer entry point (default 2). */
 int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes);
