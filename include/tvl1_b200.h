@@ -97,7 +97,7 @@ int tvl1_set_max_batch(tvl1_ctx *ctx, int pairs);  /* pairs advanced in lock-ste
 int tvl1_set_lanes(tvl1_ctx *ctx, int host_lanes, int dev_lanes);
 /* How a host-buffer batch of `npairs` pairs in PINNED memory is cut into lock-step chunks by the call-wide
  * upload -> solve -> download pipeline (opt-in, TVL1_HOST_PIPE=1; no GPU needed for this query): ramped
- * sizes -- max_batch/8, /4, /2, full chunks, /2, /4, /8 -- so that the first kernels start and the last download
+ * sizes -- max_batch/8, /4, /2 (none below 8 pairs), full chunks, /2, /4, /8 -- so that the first kernels start and the last download
  * ends one short chunk away from the ends of the call (csrc/tvl1_solver.cu: ramp_schedule, solve_host_pipelined).
  * Writes up to `cap` chunk sizes to `sizes` and returns the number of chunks. */
 int tvl1_plan_chunks(int npairs, int max_batch, int *sizes, int cap);

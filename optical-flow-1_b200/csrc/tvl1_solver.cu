@@ -181,6 +181,7 @@ struct tvl1_ctx {
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
     bool host_pipe = false;                        // TVL1_HOST_PIPE=1: the call-wide pipeline for pinned buffers (faster, but see DESIGN 3.6:
                                                    // an intermittent launch failure was seen with it and is not understood yet)
+    int ramp_min_chunk = 8;                        // smallest ramp step of its chunk schedule (TVL1_MIN_CHUNK; kRampMinChunk)
     int pipe_lanes = 3;                            // lanes of the pipeline (they only solve: three measured best, TVL1_PIPE_LANES)
     std::vector<int> chunk_override;               // TVL1_CHUNKS=8,16,...: explicit chunk sizes (experiments)
     void *pipe_buf[2] = { nullptr, nullptr };      // pinned staging ring for pageable host buffers
@@ -1504,7 +1505,11 @@ void chunk_schedule(const tvl1_ctx *ctx, int npairs, int Bmax, int lanes, std::v
 // chunks in the middle, Bmax/2, Bmax/4, Bmax/8 at the end (uploads run ahead of the kernels: the copy engines
 // move a pair faster than the SMs solve it).  At most four sizes plus one ragged remainder occur, which is what
 // a lane keeps workspaces and solve graphs for (tvl1_ctx::kAltWs).
-void ramp_schedule(int npairs, int Bmax, const std::vector<int> &override_sizes, std::vector<std::pair<int, int>> &out)
+// `min_chunk`: no ramp step below this many pairs.  Very small lock-step chunks make very short while-loop bodies, several
+// of them concurrently on several lanes: the one configuration in which an intermittent launch failure was seen.
+constexpr int kRampMinChunk = 8;
+void ramp_schedule(int npairs, int Bmax, const std::vector<int> &override_sizes, std::vector<std::pair<int, int>> &out,
+                   int min_chunk = kRampMinChunk)
 {
     int first = 0;
     auto push = [&](int b) { if (b > 0) { out.emplace_back(first, b); first += b; } };
@@ -1515,7 +1520,7 @@ void ramp_schedule(int npairs, int Bmax, const std::vector<int> &override_sizes,
     }
     std::vector<int> ramp;                          // ascending, distinct, below Bmax
     for (int d = 8; d >= 2; d /= 2)
-        if (Bmax / d >= 1 && (ramp.empty() || ramp.back() != Bmax / d)) ramp.push_back(Bmax / d);
+        if (Bmax / d >= std::max(1, min_chunk) && (ramp.empty() || ramp.back() != Bmax / d)) ramp.push_back(Bmax / d);
     auto sum = [&]() { int t = 0; for (int b : ramp) t += b; return t; };
     while (!ramp.empty() && npairs < 2 * sum() + Bmax) ramp.erase(ramp.begin());      // small batches: shorter ramps
     for (int b : ramp) push(b);
@@ -1748,7 +1753,7 @@ int solve_host(tvl1_ctx *ctx, int npairs, const T *I0, const T *I1, T *u1, T *u2
     // pinned (or registered) buffers of a batch of several chunks: one call-wide pipeline with ramped chunk sizes
     if (multiscale && ctx->host_pipe && !ctx->hs_mode && !ctx->is_sibling && npairs > Bmax && !is_pageable(I0) && (!I1 || !is_pageable(I1)) &&
         !is_pageable(u1) && !is_pageable(u2)) {
-        ramp_schedule(npairs, Bmax, ctx->chunk_override, chunks);
+        ramp_schedule(npairs, Bmax, ctx->chunk_override, chunks, ctx->ramp_min_chunk);
         return solve_host_pipelined<T, T>(ctx, chunks, I0, I1, u1, u2, nx, ny, prm, iters_out, errs_out);
     }
     chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
@@ -1799,7 +1804,7 @@ int solve_sequence_u8(tvl1_ctx *ctx, int nframes, const unsigned char *frames, f
     const int nstat = prm->nscales * prm->warps;
     std::vector<std::pair<int, int>> chunks;
     if (ctx->host_pipe && !ctx->is_sibling && npairs > Bmax && !is_pageable(frames) && !is_pageable(u1) && !is_pageable(u2)) {
-        ramp_schedule(npairs, Bmax, ctx->chunk_override, chunks);
+        ramp_schedule(npairs, Bmax, ctx->chunk_override, chunks, ctx->ramp_min_chunk);
         return solve_host_pipelined<unsigned char, float>(ctx, chunks, frames, nullptr, u1, u2, nx, ny, prm, iters_out, errs_out);
     }
     chunk_schedule(ctx, npairs, Bmax, ctx->host_lanes, chunks);
@@ -2331,6 +2336,7 @@ int tvl1_create(int device, tvl1_ctx **out)
     if (const char *ts = std::getenv("TVL1_TB_SHARED")) ctx->tb_when_shared = ts[0] == '1';
     if (const char *sd = std::getenv("TVL1_SHORT_DIV")) ctx->short_div = std::max(0, std::atoi(sd));
     if (const char *hp = std::getenv("TVL1_HOST_PIPE")) ctx->host_pipe = hp[0] == '1';
+    if (const char *mc = std::getenv("TVL1_MIN_CHUNK")) ctx->ramp_min_chunk = std::max(1, std::atoi(mc));
     if (const char *pl = std::getenv("TVL1_PIPE_LANES")) ctx->pipe_lanes = std::max(1, std::min((int) tvl1_ctx::kMaxLanes, std::atoi(pl)));
     if (const char *cs = std::getenv("TVL1_CHUNKS"))
         for (const char *q = cs; *q;) {

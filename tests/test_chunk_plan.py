@@ -20,6 +20,9 @@ def test_plan_covers_the_batch_with_few_sizes(npairs, max_batch):
 def test_plan_ramps_at_both_ends():
     c = tvl1.plan_chunks(256, 64)
     assert c == [8, 16, 32, 64, 64, 32, 16, 16, 8]
+    # no ramp step below 8 pairs (very small lock-step chunks: DESIGN 3.6)
+    assert tvl1.plan_chunks(256, 16) == [8] + [16] * 15 + [8]
+    assert tvl1.plan_chunks(24, 4) == [4] * 6
     c = tvl1.plan_chunks(1000, 64)
     assert c[:4] == [8, 16, 32, 64] and c[-1] == 8 and c.count(64) == 13
     # the tail never grows again

@@ -622,6 +622,7 @@ def test_pinned_host_batch_pipeline(gpu, npairs, max_batch, lanes, dtype, form, 
     counts are the bits of its individual solve, call after call."""
     import torch
     monkeypatch.setenv("TVL1_HOST_PIPE", "1")
+    monkeypatch.setenv("TVL1_MIN_CHUNK", "1")                  # ramps down to single pairs: every chunk size the lanes can meet
     nx, ny = 128, 96
     kw = dict(nscales=3, warps=2, eps=0.01)
     tdt = torch.float64 if dtype == "float64" else torch.float32          # 8-bit frames give fp32 flows
