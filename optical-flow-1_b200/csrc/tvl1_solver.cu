@@ -976,7 +976,9 @@ int fetch_stats(tvl1_ctx *ctx, int B, int nstat, int *iters_out, double *errs_ou
         CK(cudaMemcpy2DAsync(errs_out, sizeof(double) * nstat, w.stat_errs, sizeof(double) * w.stat_stride,
                              sizeof(double) * nstat, B, cudaMemcpyDeviceToHost, ctx->stream));
     CK(sleep_until_done(ctx));
-    if (ctx->t2_adapt && ctx->use_t2 == 1 && nstat > 0 && !ctx->hs_mode) {
+    // (not from the chunks of a host-buffer batch: the loop lengths of 8 or 16 pairs swing with a single slow pair, and
+    // every change of the mask re-captures the lane's solve graph while the other lanes are running)
+    if (ctx->t2_adapt && ctx->use_t2 == 1 && nstat > 0 && !ctx->hs_mode && !ctx->shared_gpu) {
         // iterations per loop (pair and warp step) on each streamed level of this solve -> which levels the next one
         // blocks (t2_usable).  Loops are counted up to kLoopClip iterations: one slow pair that runs to the cap must not
         // switch the kernel for its whole chunk and back (every switch re-captures the solve graph).
